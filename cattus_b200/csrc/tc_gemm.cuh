@@ -1,0 +1,195 @@
+// tc_gemm: the generic tcgen05/TMEM bf16 GEMM used for every dense contraction of ConvNetV1
+// (reference network: training/cattus_train/net_utils.py:45-89; engines it replaces: engine/src/net/model.rs:146-218).
+//
+//   D[128 x N] (fp32, TMEM) = sum over k-blocks of A[128 x 64] * B[N x 64]^T      (bf16 operands, 64 = one 128-byte row)
+//
+// mode 0 (matrix):  A is a row-major [rows][K] bf16 matrix (FC layers, 1x1 head convs).
+// mode 1 (conv3x3): A is the NHWC activation tensor [B][S][S][C]; the k-loop walks (tap, 64-channel slice) and each
+//                   A tile is ONE 4-D TMA box {64ch, S, S, nb boards} whose start coordinate is shifted by the tap
+//                   (dx, dy) in {-1,0,1}^2 -- TMA zero-fills the out-of-bounds halo, which is exactly `padding="same"`
+//                   (net_utils.py:13,29,32).  A tile always holds whole boards, so no tile straddles two positions.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one lane), warps 2..5 = epilogue
+// (TMEM -> registers -> +bias (+residual) -> ReLU -> bf16/f32 -> global).  4-stage smem ring, full/empty mbarriers.
+#pragma once
+#include "ptx.cuh"
+
+namespace cb2 {
+
+constexpr int kTcStages = 4;
+constexpr int kTcTileBytes = 128 * 128;  // 128 rows x 128 B
+constexpr int kTcThreads = 192;
+constexpr int kTcTmemCols = 128;
+constexpr int kTcSmemBytes = 2 * kTcStages * kTcTileBytes + 256 + 1024;  // tiles + barriers + alignment slack
+
+struct alignas(64) TcGemmParams {
+    CUtensorMap tma_a;
+    CUtensorMap tma_b;
+    const float* bias;            // [n_tiles * n_umma], zero padded
+    const __nv_bfloat16* resid;   // same layout as out (bf16) or nullptr
+    void* out;
+    uint32_t* err;
+    int mode;
+    int num_kb;         // number of 64-wide k-blocks
+    int kh;             // mode 1: 64-channel slices per tap
+    int n_umma;         // UMMA N: multiple of 16, <= 128
+    int n_store;        // columns written per row (bf16: multiple of 8; f32: n_umma)
+    int m_valid;        // mode 0: rows; mode 1: boards
+    int rows_per_tile;  // mode 0: 128; mode 1: nb * S * S
+    int s2;             // S * S
+    int nb;             // boards per tile
+    int ld_out;         // elements
+    int out_f32;
+    int relu;
+    uint32_t tx_bytes;  // bytes one stage's two TMA boxes deliver
+    int pad_;
+};
+
+__global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + kTcStages * kTcTileBytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + 2 * kTcStages * kTcTileBytes);
+    uint64_t* empty_bar = full_bar + kTcStages;
+    uint64_t* tmem_full_bar = empty_bar + kTcStages;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    const int m_tile = blockIdx.x;
+    const int n_tile = blockIdx.y;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&p.tma_a);
+        ptx::prefetch_tensormap(&p.tma_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kTcStages; ++s) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], 1);
+        }
+        ptx::mbar_init(tmem_full_bar, 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc(tmem_ptr, kTcTmemCols);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                const int s = kb % kTcStages;
+                const uint32_t ph = (kb / kTcStages) & 1;
+                ptx::mbar_wait(&empty_bar[s], ph ^ 1, p.err, 0x100 + s);
+                ptx::mbar_arrive_expect_tx(&full_bar[s], p.tx_bytes);
+                if (p.mode == 0) {
+                    ptx::tma_load_2d(smem_a + s * kTcTileBytes, &p.tma_a, &full_bar[s], kb * 64, m_tile * 128);
+                } else {
+                    const int tap = kb / p.kh, slice = kb - tap * p.kh;
+                    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                    ptx::tma_load_4d(smem_a + s * kTcTileBytes, &p.tma_a, &full_bar[s], slice * 64, dx, dy, m_tile * p.nb);
+                }
+                ptx::tma_load_2d(smem_b + s * kTcTileBytes, &p.tma_b, &full_bar[s], kb * 64, n_tile * p.n_umma);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = ptx::umma_idesc_bf16(128, p.n_umma);
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                const int s = kb % kTcStages;
+                const uint32_t ph = (kb / kTcStages) & 1;
+                ptx::mbar_wait(&full_bar[s], ph, p.err, 0x200 + s);
+                ptx::tc_fence_after();
+                const uint32_t a_addr = ptx::smem_u32(smem_a + s * kTcTileBytes);
+                const uint32_t b_addr = ptx::smem_u32(smem_b + s * kTcTileBytes);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {  // 4 x (K = 16 bf16 = 32 B) inside the 128-byte swizzle row
+                    ptx::umma_bf16_ss(tmem_base, ptx::umma_desc_sw128(a_addr + k * 32, 1024),
+                                      ptx::umma_desc_sw128(b_addr + k * 32, 1024), idesc, (kb | k) != 0);
+                }
+                ptx::umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+            }
+            ptx::umma_commit(tmem_full_bar);  // accumulator complete
+        }
+    } else {
+        // Epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32); warps 2,3,4,5 cover all four quarters.
+        const uint32_t q = warp & 3;
+        const int row = static_cast<int>(q * 32 + lane);
+        bool ok;
+        long long grow;
+        if (p.mode == 0) {
+            grow = static_cast<long long>(m_tile) * 128 + row;
+            ok = grow < p.m_valid;
+        } else {
+            ok = row < p.rows_per_tile && (m_tile * p.nb + row / p.s2) < p.m_valid;
+            grow = static_cast<long long>(m_tile) * p.rows_per_tile + row;
+        }
+        ptx::mbar_wait(tmem_full_bar, 0, p.err, 0x300);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + ((q * 32u) << 16);
+        for (int c0 = 0; c0 < p.n_umma; c0 += 16) {
+            float v[16];
+            ptx::tmem_ld_x16(taddr + c0, v);  // warp-collective: executed by all lanes regardless of `ok`
+            if (!ok || c0 >= p.n_store) continue;
+            const int col = n_tile * p.n_umma + c0;
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 b = __ldg(b4 + j);
+                v[4 * j + 0] += b.x;
+                v[4 * j + 1] += b.y;
+                v[4 * j + 2] += b.z;
+                v[4 * j + 3] += b.w;
+            }
+            const long long off = grow * p.ld_out + col;
+            if (p.resid != nullptr) {
+                const uint4* r4 = reinterpret_cast<const uint4*>(p.resid + off);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (c0 + 8 * (h + 1) > p.n_store) break;
+                    const uint4 r = __ldg(r4 + h);
+                    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
+                        v[8 * h + 2 * j + 0] += __bfloat162float(b2.x);
+                        v[8 * h + 2 * j + 1] += __bfloat162float(b2.y);
+                    }
+                }
+            }
+            if (p.relu) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
+            }
+            if (p.out_f32) {
+                float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            } else {
+                uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (c0 + 8 * (h + 1) > p.n_store) break;
+                    uint32_t w[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[8 * h + 2 * j], v[8 * h + 2 * j + 1]);
+                        w[j] = *reinterpret_cast<const uint32_t*>(&b2);
+                    }
+                    o4[h] = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) ptx::tmem_dealloc(tmem_base, kTcTmemCols);
+}
+
+}  // namespace cb2
