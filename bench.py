@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py -- NN evals/s of the batched leaf-evaluation hot path (BASELINE.json metric) on N B200s.
+
+One "step" = one pass of the hot path (encode -> conv trunk -> heads -> mask/softmax/tanh) over `positions_per_step`
+synthetic positions (SURVEY.md section 8d generator, random-init ConvNetV1 weights of the named architecture).
+
+  value     whole-job positions/s with the packed positions already resident in HBM, device time from CUDA events on
+            the evaluator stream, L2 flushed (256 MiB memset) before every device batch, max over ranks.
+  e2e       the same metric through the reference-facing C-ABI call `cattus_b200_eval_batch` with HOST buffers:
+            pack into the pinned block, cudaMemcpyAsync H2D, graph, D2H of probabilities and values, every step.
+  roofline  conv trunk (stem + residual blocks, the dense contraction) timed alone on the same stream:
+            algorithmic FLOP (2*MAC, unpadded) / average duration vs the measured bf16 peak of MEASURED_PEAKS.json.
+  cpu_baseline  the oracle's restatement of the reference's torch-py CPU engine on the box's host cores (rank 0, N=1).
+
+`--impl reference` times that CPU path alone (the reference has no GPU code of its own and its Rust engines cannot be
+built here: no cargo/rustc, no ONNX Runtime / tract / ExecuTorch wheels -- see DESIGN.md).
+
+Multi-GPU: replicas only -- one process per GPU (torchrun), each with its own evaluator, queue and positions; no
+collective on the data path (self-play games are independent).  torch.distributed is used for the barrier and the
+max-over-ranks of the timings only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    # name: (oracle config, device batch, device batches per step)
+    "chess10x128": ("chess10x128", 4096, 4),
+    "chess_dev": ("chess_dev", 4096, 4),
+    "hex5": ("hex5", 4096, 4),
+    "hex7": ("hex7", 4096, 4),
+    "hex4": ("hex4", 4096, 4),
+}
+DEFAULT_WORKLOAD = "chess10x128"
+CONFIG_NOTES = {
+    "chess10x128": "BASELINE.json configs[3]: chess, random-init AlphaZero-style ResNet 10 blocks x 128 filters (heads 32/32), bf16; "
+                   "the configuration the north star's tensor-core target is quoted on; fits one GPU",
+    "hex5": "BASELINE.json configs[1]: hex 5x5, ConvNetV1 7x16 (heads 16/16) random-init (shipped model/hex5 is an LFS stub)",
+    "hex7": "BASELINE.json configs[2]: hex 7x7, ConvNetV1 7x16 (heads 16/16) random-init",
+    "hex4": "BASELINE.json configs[0]: hex 4x4, ConvNetV1 7x16 (heads 16/16) random-init",
+    "chess_dev": "training/config/chess_dev.yaml: chess, ConvNetV1 7x16 (heads 8/8) random-init",
+}
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d["bf16_tflops"]),
+                "bf16_tflops_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.device)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nme, val in zip(names, f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_inputs(cfg, n, seed):
+    from oracle import games
+
+    if cfg.game == "chess":
+        return games.synth_chess_positions(n, seed)
+    words, _ = games.synth_hex_positions(n, cfg.board_size, seed)
+    return words, None
+
+
+def cpu_reference_step(model, cfg, words, bitmaps, liboracle):
+    """One pass of the reference's CPU path over a sample: planes_to_tensor (C restatement of net/mod.rs:121-156) ->
+    torch-py engine restated (model.rs:68-84) -> clamp + calc_moves_probs (C restatement of net/mod.rs:57-61,106-119)."""
+    import ctypes as C
+
+    n = len(words)
+    x = np.empty((n, cfg.planes, cfg.board_size, cfg.board_size), dtype=np.float32)
+    w = np.ascontiguousarray(words, dtype=np.uint64)
+    liboracle.oracle_planes_to_tensor(w.ctypes.data_as(C.c_void_p), n, n, cfg.planes, cfg.board_size, x.ctypes.data_as(C.c_void_p))
+    logits, values = model.run(x)
+    logits = np.ascontiguousarray(logits, dtype=np.float32)
+    if bitmaps is None:  # hex: legal = empty cells
+        wpp = (cfg.board_size ** 2 + 63) // 64
+        ww = w.reshape(n, cfg.planes, wpp)
+        empty = ww[:, 2] & ~(ww[:, 0] | ww[:, 1])
+        bm = np.ascontiguousarray(empty.view(np.uint8).reshape(n, wpp * 8))
+    else:
+        bm = np.ascontiguousarray(bitmaps, dtype=np.uint8)
+    probs = np.empty(n * cfg.moves, dtype=np.float32)
+    offsets = np.empty(n + 1, dtype=np.uint32)
+    liboracle.oracle_policy_batch(logits.ctypes.data_as(C.c_void_p), n, cfg.moves, bm.ctypes.data_as(C.c_void_p), bm.shape[1],
+                                  probs.ctypes.data_as(C.c_void_p), offsets.ctypes.data_as(C.c_void_p))
+    return probs[: offsets[n]], values
+
+
+def time_cpu_reference(cfg, sample_n, budget_s, steps=None, warmup=1, seed=1234):
+    """Returns (positions/s, cores, description).  Bounded: `steps` passes if given, else as many as fit in budget_s."""
+    import ctypes as C
+
+    from oracle import net
+
+    subprocess.run(["make", "-s", "-C", str(ROOT / "oracle")], check=True)
+    liboracle = C.CDLL(str(ROOT / "oracle" / "_build" / "liboracle.so"))
+    cores = len(os.sched_getaffinity(0))
+    sd = net.make_state_dict(cfg, 0)
+    model = net.TorchCpuModel(sd, cfg, sample_n, cores)
+    words, bitmaps = make_inputs(cfg, sample_n, seed)
+    for _ in range(max(1, warmup)):
+        cpu_reference_step(model, cfg, words, bitmaps, liboracle)
+    done, t0 = 0, time.perf_counter()
+    while True:
+        cpu_reference_step(model, cfg, words, bitmaps, liboracle)
+        done += 1
+        el = time.perf_counter() - t0
+        if (steps is not None and done >= steps) or (steps is None and el >= budget_s):
+            break
+    return done * sample_n / el, cores, el / done, f"{done} passes over {sample_n} positions, torch {cores} threads fp32 (reference torch-py engine restated) + C restatement of planes_to_tensor/calc_moves_probs"
+
+
+def run_reference_arm(args, rank, world):
+    from oracle import net
+
+    if rank != 0:
+        return
+    cfg_name, _, _ = WORKLOADS[args.workload]
+    cfg = net.CONFIGS[cfg_name]
+    sample_n = args.cpu_sample or (256 if cfg.filters >= 64 else 2048)
+    value, cores, sec_per_step, desc = time_cpu_reference(cfg, sample_n, budget_s=0, steps=max(1, args.steps), warmup=max(1, args.warmup))
+    line = {
+        "impl": "reference", "metric": "nn_evals_per_sec", "value": value, "unit": "positions/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "note": CONFIG_NOTES.get(args.workload, ""), "positions_per_step": sample_n,
+                   "reference": "CPU inference path of the reference (host cores only; the reference has no GPU kernels)"},
+        "cpu_baseline": {"value": value, "unit": "positions/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": "positions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cattus_b200", choices=["cattus_b200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="device batch (positions per launch sequence); default per workload")
+    ap.add_argument("--streams", type=int, default=3)
+    ap.add_argument("--cpu-sample", type=int, default=0)
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU baseline work (rank 0, N=1 only)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+
+    from cattus_b200 import CudaNetwork
+    from cattus_b200.export import export_blob
+    from oracle import net  # only for NetConfig / the seeded weight + position generators and the cpu_baseline leg
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(local_rank)
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    cfg_name, batch, per_step = WORKLOADS[args.workload]
+    if args.batch:
+        batch = args.batch
+    cfg = net.CONFIGS[cfg_name]
+    peaks = load_peaks()
+    sd = net.make_state_dict(cfg, 0)
+    nw = CudaNetwork(export_blob(sd, cfg.game), cfg.game, device=local_rank, batch_size=batch, n_streams=args.streams, precision="bf16")
+    positions_per_step = batch * per_step
+    words, bitmaps = make_inputs(cfg, positions_per_step, seed=0xCA7705 + rank)
+
+    # ---------------- device-resident throughput (value) and the trunk roofline
+    nw.resident_upload(words[:batch], None if bitmaps is None else bitmaps[:batch])
+    nw.time_stage(4, batch, args.warmup * per_step)
+    sampler = ClockSampler(local_rank)
+    launches0 = nw.metrics()["model.kernel_launches"]
+    barrier()
+    sampler.start()
+    ms_all = nw.time_stage(4, batch, args.steps * per_step)
+    barrier()
+    t_value = max_over_ranks(float(ms_all.sum()) * 1e-3)
+    # trunk alone (same stream, same L2 flush discipline)
+    nw.time_stage(1, batch, 3)
+    ms_trunk = nw.time_stage(1, batch, max(5, args.steps))
+    ms_enc = nw.time_stage(0, batch, max(5, args.steps))
+    ms_heads = nw.time_stage(2, batch, max(5, args.steps))
+    ms_tail = nw.time_stage(3, batch, max(5, args.steps))
+    barrier()
+
+    # ---------------- end to end through the C ABI with host buffers
+    for _ in range(args.warmup):
+        nw.eval_batch(words, bitmaps)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        probs, offsets, values = nw.eval_batch(words, bitmaps)
+    torch.cuda.synchronize(local_rank)
+    t_e2e_local = time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop()
+    t_e2e = max_over_ranks(t_e2e_local)
+    launches = nw.metrics()["model.kernel_launches"] - launches0
+    h2d = positions_per_step * (cfg.planes * ((cfg.board_size ** 2 + 63) // 64) * 8 + (((cfg.moves + 31) // 32 * 4 + 7) // 8 * 8 if bitmaps is not None else 0)) + 16 * per_step
+    d2h = int(offsets[-1]) * 4 + positions_per_step * 4
+    kernels_per_batch = nw.info.kernels_per_batch
+    fused = bool(nw.info.reserved)
+    nw.close()
+
+    total_positions = world * positions_per_step * args.steps
+    value = total_positions / t_value
+    e2e_value = total_positions / t_e2e
+    s2 = cfg.board_size ** 2
+    stem_flops = 2 * 9 * cfg.planes * cfg.filters * s2
+    trunk_flops = stem_flops + cfg.trunk_flops_per_position
+    t_trunk = float(np.mean(ms_trunk)) * 1e-3
+    achieved = batch * trunk_flops / t_trunk / 1e12
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
+                "traffic": None, "kernel": "trunk_fused_kernel (stem + residual blocks, one launch)" if fused else "tc_gemm_kernel x (1 + 2R) conv layers (stem + residual blocks)",
+                "peak_source": peaks["source"] + ", burst figure (stage timed alone)", "flop_per_position": trunk_flops, "positions_per_launch": batch,
+                "ms": t_trunk * 1e3,
+                "stages_ms": {"encode": float(np.mean(ms_enc)), "trunk": float(np.mean(ms_trunk)), "heads": float(np.mean(ms_heads)),
+                              "tail": float(np.mean(ms_tail)), "all_graph": float(np.mean(ms_all))},
+                "whole_net_tflops": batch * cfg.flops_per_position / (float(np.mean(ms_all)) * 1e-3) / 1e12}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sample_n = args.cpu_sample or (256 if cfg.filters >= 64 else 2048)
+        v, cores, _, desc = time_cpu_reference(cfg, sample_n, budget_s=args.cpu_budget)
+        cpu_baseline = {"value": v, "unit": "positions/s", "cores": cores, "kind": "port", "sample": desc}
+
+    if rank == 0:
+        line = {
+            "metric": "nn_evals_per_sec", "value": value, "unit": "positions/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": t_value / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": args.workload, "note": CONFIG_NOTES.get(args.workload, ""), "net": cfg.to_dict(), "device_batch": batch,
+                       "positions_per_step": positions_per_step, "streams": args.streams, "parallelism": f"replicas x{world}, no collective",
+                       "l2": "256 MiB memset between timed device batches", "weights": "random-init (numpy PCG64 seed 0), BN folded",
+                       "kernels_per_device_batch": kernels_per_batch},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "positions/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": t_e2e / args.steps * 1e3, "api": "cattus_b200_eval_batch (host buffers -> pinned block -> H2D -> graph -> D2H)"},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,94 @@
+"""ctypes binding of the C ABI declared in include/cattus_b200.h.
+
+This is the Python counterpart of the Rust FFI stub shown in INTEGRATION.md: same symbols, same argument meaning.
+The library is mandatory: importing this module on a machine without libcattus_b200.so raises, and `create`
+fails with ENODEV when no sm_100 device is present.  There is no CPU fallback anywhere in this package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+from . import build as _build
+
+OK, EINVAL, ENODEV, ECUDA, ENOMEM, ERANGE, EDEVICE = 0, -1, -2, -3, -4, -5, -6
+GAME_TTT, GAME_HEX, GAME_CHESS = 0, 1, 2
+PRECISION_BF16, PRECISION_FP32_CHECK = 0, 1
+GAME_IDS = {"ttt": GAME_TTT, "hex": GAME_HEX, "chess": GAME_CHESS}
+
+
+class Desc(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("game", C.c_uint32), ("board_size", C.c_uint32), ("planes", C.c_uint32),
+        ("moves", C.c_uint32), ("filters", C.c_uint32), ("blocks", C.c_uint32), ("value_channels", C.c_uint32),
+        ("policy_channels", C.c_uint32), ("device", C.c_int32), ("max_batch", C.c_uint32), ("n_streams", C.c_uint32),
+        ("precision", C.c_uint32), ("flags", C.c_uint32), ("weights_path", C.c_char_p),
+    ]
+
+
+class Metrics(C.Structure):
+    _fields_ = [
+        ("activation_count", C.c_uint64), ("positions", C.c_uint64), ("run_duration_last", C.c_double),
+        ("run_duration_ema", C.c_double), ("mean_batch_fill", C.c_double), ("kernel_launches", C.c_uint64),
+    ]
+
+
+class Info(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in (
+        "game", "board_size", "planes", "moves", "filters", "blocks", "value_channels", "policy_channels",
+        "words_per_plane", "legal_bitmap_bytes", "max_batch", "n_streams", "precision", "sm_count",
+        "kernels_per_batch", "reserved")]
+
+
+# every symbol include/cattus_b200.h declares: name -> (restype, argtypes)
+_H = C.c_void_p
+_u64p, _u8p, _f32p, _u32p = C.POINTER(C.c_uint64), C.POINTER(C.c_uint8), C.POINTER(C.c_float), C.POINTER(C.c_uint32)
+SYMBOLS = {
+    "cattus_b200_create": (C.c_int, [C.POINTER(Desc), C.POINTER(_H)]),
+    "cattus_b200_create_from_memory": (C.c_int, [C.POINTER(Desc), C.c_void_p, C.c_size_t, C.POINTER(_H)]),
+    "cattus_b200_destroy": (None, [_H]),
+    "cattus_b200_get_info": (C.c_int, [_H, C.POINTER(Info)]),
+    "cattus_b200_eval": (C.c_int, [_H, _u64p, _u8p, _f32p, C.c_uint32, _u32p, _f32p]),
+    "cattus_b200_eval_batch": (C.c_int, [_H, _u64p, _u8p, C.c_uint32, _f32p, C.c_size_t, _u32p, _f32p]),
+    "cattus_b200_encode": (C.c_int, [_H, _u64p, C.c_uint32, C.c_uint32, _f32p]),
+    "cattus_b200_run_dense": (C.c_int, [_H, _f32p, C.c_uint32, _f32p, _f32p]),
+    "cattus_b200_resident_upload": (C.c_int, [_H, _u64p, _u8p, C.c_uint32]),
+    "cattus_b200_eval_resident": (C.c_int, [_H, C.c_uint32, C.c_void_p]),
+    "cattus_b200_resident_download": (C.c_int, [_H, C.c_uint32, _f32p, C.c_size_t, _u32p, _f32p]),
+    "cattus_b200_time_stage": (C.c_int, [_H, C.c_uint32, C.c_uint32, C.c_uint32, _f32p]),
+    "cattus_b200_get_metrics": (C.c_int, [_H, C.POINTER(Metrics)]),
+    "cattus_b200_last_error": (C.c_char_p, []),
+    "cattus_b200_abi_version": (C.c_uint32, []),
+}
+
+_lib = None
+
+
+def library_path() -> Path:
+    return _build.LIB
+
+
+def load() -> C.CDLL:
+    """Loads (building first if the sources are newer) the shared library and types every exported symbol."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.build()
+    lib = C.CDLL(str(path))
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class CattusB200Error(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"cattus_b200 error {code}: {message}")
+        self.code = code
+
+
+def check(rc: int) -> None:
+    if rc != OK:
+        raise CattusB200Error(rc, (load().cattus_b200_last_error() or b"").decode(errors="replace"))

@@ -1,0 +1,1163 @@
+// Engine implementation + the extern "C" boundary (include/cattus_b200.h).  Single translation unit: the kernels
+// live in headers and are instantiated here.
+#include "engine.hpp"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+
+namespace cb2 {
+
+static inline uint32_t round_up(uint32_t x, uint32_t m) { return (x + m - 1) / m * m; }
+static inline uint32_t ceil_div(uint32_t x, uint32_t m) { return (x + m - 1) / m; }
+
+// ------------------------------------------------------------------------------------------------ blob
+static constexpr uint32_t kBlobMagic = 0x00324243u;  // "CB2\0"
+
+Blob Blob::parse(const void* bytes, size_t n) {
+    if (bytes == nullptr || n < 64) throw Error(CATTUS_B200_EINVAL, "weight blob too small");
+    const uint32_t* h = static_cast<const uint32_t*>(bytes);
+    if (h[0] != kBlobMagic) throw Error(CATTUS_B200_EINVAL, "weight blob: bad magic (expected CB2)");
+    if (h[1] != 1) throw Error(CATTUS_B200_EINVAL, "weight blob: unsupported version");
+    Blob b;
+    b.d.game = h[2];
+    b.d.s = h[3];
+    b.d.c_in = h[4];
+    b.d.moves = h[5];
+    b.d.f = h[6];
+    b.d.r = h[7];
+    b.d.vh = h[8];
+    b.d.ph = h[9];
+    b.d.hidden = h[10];
+    const NetDims& d = b.d;
+    if (d.game > 2 || d.s < 2 || d.s > 11 || d.c_in == 0 || d.c_in > 64 || d.moves == 0 || d.moves > 4096 || d.f == 0 ||
+        d.f > 256 || d.vh == 0 || d.vh > 64 || d.ph == 0 || d.ph > 64 || d.hidden != 128 || d.r > 64)
+        throw Error(CATTUS_B200_EINVAL, "weight blob: architecture out of the supported range");
+    size_t off = 0;
+    auto take = [&](size_t cnt) {
+        size_t o = off;
+        off += cnt;
+        return o;
+    };
+    auto conv = [&](uint32_t co, uint32_t ci, uint32_t k) {
+        Conv c;
+        c.co = co;
+        c.ci = ci;
+        c.k = k;
+        c.w = take(static_cast<size_t>(co) * ci * k * k);
+        c.b = take(co);
+        return c;
+    };
+    const uint32_t s2 = d.s2();
+    b.stem = conv(d.f, d.c_in, 3);
+    for (uint32_t i = 0; i < 2 * d.r; ++i) b.block_conv.push_back(conv(d.f, d.f, 3));
+    b.vconv = conv(d.vh, d.f, 1);
+    b.vfc1_w = take(static_cast<size_t>(d.hidden) * d.vh * s2);
+    b.vfc1_b = take(d.hidden);
+    b.vfc2_w = take(d.hidden);
+    b.vfc2_b = take(1);
+    b.pconv = conv(d.ph, d.f, 1);
+    b.pfc_w = take(static_cast<size_t>(d.moves) * d.ph * s2);
+    b.pfc_b = take(d.moves);
+    if (n != 64 + off * sizeof(float))
+        throw Error(CATTUS_B200_EINVAL, "weight blob: size " + std::to_string(n) + " does not match its header (expected " +
+                                            std::to_string(64 + off * sizeof(float)) + ")");
+    b.data.resize(off);
+    std::memcpy(b.data.data(), static_cast<const uint8_t*>(bytes) + 64, off * sizeof(float));
+    for (float v : b.data)
+        if (!std::isfinite(v)) throw Error(CATTUS_B200_EINVAL, "weight blob: non-finite weight");
+    return b;
+}
+
+// ------------------------------------------------------------------------------------------------ buffers
+void DeviceBuf::alloc(size_t n) {
+    free_();
+    bytes = std::max<size_t>(n, 256);
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+        p = nullptr;
+        throw Error(CATTUS_B200_ENOMEM, std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
+    }
+    CB2_CUDA(cudaMemset(p, 0, bytes));
+}
+void DeviceBuf::free_() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+}
+
+static std::vector<__nv_bfloat16> to_bf16(const std::vector<float>& v) {
+    std::vector<__nv_bfloat16> o(v.size());
+    for (size_t i = 0; i < v.size(); ++i) o[i] = __float2bfloat16_rn(v[i]);
+    return o;
+}
+template <class T>
+static void upload(DeviceBuf& buf, const std::vector<T>& v) {
+    buf.alloc(v.size() * sizeof(T));
+    CB2_CUDA(cudaMemcpy(buf.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+}
+
+// ------------------------------------------------------------------------------------------------ construction
+Engine::Engine(const cattus_b200_desc& desc, const void* blob_bytes, size_t blob_n) : desc_(desc) {
+    Blob blob = Blob::parse(blob_bytes, blob_n);
+    d_ = blob.d;
+    auto chk = [&](uint32_t want, uint32_t have, const char* what) {
+        if (want != 0 && want != have)
+            throw Error(CATTUS_B200_EINVAL, std::string("descriptor ") + what + "=" + std::to_string(want) +
+                                                " does not match the weight blob (" + std::to_string(have) + ")");
+    };
+    chk(desc.board_size, d_.s, "board_size");
+    chk(desc.planes, d_.c_in, "planes");
+    chk(desc.moves, d_.moves, "moves");
+    chk(desc.filters, d_.f, "filters");
+    chk(desc.blocks, d_.r, "blocks");
+    chk(desc.value_channels, d_.vh, "value_channels");
+    chk(desc.policy_channels, d_.ph, "policy_channels");
+    if (desc.game != d_.game) throw Error(CATTUS_B200_EINVAL, "descriptor game does not match the weight blob");
+    if (desc.max_batch == 0 || desc.max_batch > (1u << 16)) throw Error(CATTUS_B200_EINVAL, "max_batch must be in 1..65536");
+    if (desc.precision > CATTUS_B200_PRECISION_FP32_CHECK) throw Error(CATTUS_B200_EINVAL, "unknown precision");
+    max_batch_ = desc.max_batch;
+    precision_ = desc.precision;
+    const uint32_t n_streams = std::max<uint32_t>(1, std::min<uint32_t>(desc.n_streams, 8));
+
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        throw Error(CATTUS_B200_ENODEV, std::string("no CUDA device (") + cudaGetErrorString(e) + "); there is no CPU fallback");
+    if (desc.device < 0 || desc.device >= count) throw Error(CATTUS_B200_ENODEV, "device ordinal out of range");
+    device_ = desc.device;
+    cudaDeviceProp prop{};
+    CB2_CUDA(cudaGetDeviceProperties(&prop, device_));
+    if (prop.major != 10)
+        throw Error(CATTUS_B200_ENODEV, std::string("device ") + prop.name + " is compute capability " + std::to_string(prop.major) +
+                                            "." + std::to_string(prop.minor) + "; this library contains sm_100a code only and has no fallback");
+    CB2_CUDA(cudaSetDevice(device_));
+    sm_count_ = prop.multiProcessorCount;
+
+    // record layout shared by host packing and the kernels
+    derive_legal_ = (d_.game != CATTUS_B200_GAME_CHESS);
+    if (derive_legal_ && (d_.c_in < 3 || d_.moves != d_.s2()))
+        throw Error(CATTUS_B200_EINVAL, "derived legality needs >= 3 planes and moves == S*S");
+    rec_.planes = static_cast<int>(d_.c_in);
+    rec_.wpp = static_cast<int>(d_.wpp());
+    rec_.s = static_cast<int>(d_.s);
+    rec_.moves = static_cast<int>(d_.moves);
+    rec_.legal_words = static_cast<int>(ceil_div(d_.moves, 32));
+    const int plane_bytes = rec_.planes * rec_.wpp * 8;
+    rec_.legal_off = derive_legal_ ? -1 : plane_bytes;
+    rec_.rec_bytes = plane_bytes + (derive_legal_ ? 0 : static_cast<int>(round_up(static_cast<uint32_t>(rec_.legal_words) * 4, 8)));
+
+    // bf16 layout constants
+    cin_pad_ = round_up(d_.c_in, 64);
+    ca_ = round_up(d_.f, 64);
+    nb_ = std::max<uint32_t>(1, 128 / d_.s2());
+    vhp_ = round_up(d_.vh, 16);
+    php_ = round_up(d_.ph, 16);
+
+    {
+        cudaDriverEntryPointQueryResult q;
+        CB2_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &encode_tiled_, cudaEnableDefault, &q));
+        if (q != cudaDriverEntryPointSuccess || encode_tiled_ == nullptr)
+            throw Error(CATTUS_B200_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    }
+    CB2_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h_err_), 64, cudaHostAllocMapped));
+    std::memset(h_err_, 0, 64);
+    CB2_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_err_), h_err_, 0));
+    CB2_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+
+    upload_weights(blob);
+
+    for (uint32_t i = 0; i < n_streams; ++i) {
+        lanes_.emplace_back(new Lane());
+        lanes_.back()->index = static_cast<int>(i);
+        init_lane(*lanes_.back());
+    }
+    lane_busy_.assign(n_streams, 0);
+    const size_t in_bytes = 16 + static_cast<size_t>(max_batch_) * rec_.rec_bytes;
+    CB2_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&open_block_), in_bytes, cudaHostAllocDefault));
+    std::memset(open_block_, 0, in_bytes);
+    open_reqs_.reserve(max_batch_);
+
+    // warm the most common graph so the first leaf does not pay for capture
+    {
+        Lane& l = *lanes_[0];
+        *reinterpret_cast<uint32_t*>(l.h_in) = 0;
+        CB2_CUDA(cudaMemcpyAsync(l.d_in.p, l.h_in, 16, cudaMemcpyHostToDevice, l.stream));
+        run_bucket(l, bucket_for(max_batch_), l.stream, true, false);
+        cudaError_t se = cudaStreamSynchronize(l.stream);
+        if (se != cudaSuccess) throw_device_error("warm-up batch", se);
+        kernels_per_batch_ = static_cast<uint32_t>(ops_for(l, bucket_for(max_batch_), false).size());
+    }
+    for (uint32_t i = 0; i < n_streams; ++i) evaluators_.emplace_back([this] { evaluator_loop(); });
+}
+
+Engine::~Engine() {
+    {
+        std::lock_guard<std::mutex> g(q_mu_);
+        stopping_ = true;
+    }
+    q_cv_.notify_all();
+    q_space_cv_.notify_all();
+    for (auto& t : evaluators_) t.join();
+    cudaSetDevice(device_);
+    cudaDeviceSynchronize();
+    for (auto& lp : lanes_) {
+        Lane& l = *lp;
+        for (auto& kv : l.graphs) cudaGraphExecDestroy(kv.second);
+        if (l.stream) cudaStreamDestroy(l.stream);
+        if (l.done) cudaEventDestroy(l.done);
+        if (l.h_in) cudaFreeHost(l.h_in);
+        if (l.h_values) cudaFreeHost(l.h_values);
+        if (l.h_probs) cudaFreeHost(l.h_probs);
+        for (DeviceBuf* b : {&l.d_in, &l.d_values, &l.d_offsets, &l.d_probs, &l.d_x, &l.d_act[0], &l.d_act[1], &l.d_act[2], &l.d_hv,
+                             &l.d_hp, &l.d_hidden, &l.d_logits, &l.d_dense})
+            b->free_();
+    }
+    if (open_block_) cudaFreeHost(open_block_);
+    if (h_err_) cudaFreeHost(h_err_);
+    for (auto& c : convs_) {
+        c.w.free_();
+        c.b.free_();
+    }
+    for (GemmW* g : {&vconv_, &pconv_, &vfc1_, &pfc_}) {
+        g->w.free_();
+        g->b.free_();
+    }
+    vfc2_w_.free_();
+    fused_w_.free_();
+    fused_b_.free_();
+    flush_.free_();
+}
+
+// Weight layouts.
+//  bf16: every contraction is D[rows x N] = A[rows x K] * W[N x K]^T with K-major bf16 operands, so each weight is
+//        stored as [N_pad][K_pad] bf16 (+ f32 bias[N_pad]).  conv3x3: K index = tap * Cin_pad + c (tap = ky*3+kx);
+//        FC: K index = cell * C_pad + c, i.e. the NCHW flatten order of net_utils.py:70,80 permuted to the NHWC order
+//        the head convs write.
+//  fp32 check mode: the blob's PyTorch layouts, untouched.
+void Engine::upload_weights(const Blob& blob) {
+    const uint32_t s2 = d_.s2();
+    const float* D = blob.data.data();
+    if (precision_ == CATTUS_B200_PRECISION_FP32_CHECK) {
+        auto up = [&](GemmW& g, size_t w, size_t wn, size_t b, size_t bn) {
+            upload(g.w, std::vector<float>(D + w, D + w + wn));
+            upload(g.b, std::vector<float>(D + b, D + b + bn));
+        };
+        auto upc = [&](GemmW& g, const Blob::Conv& c) { up(g, c.w, static_cast<size_t>(c.co) * c.ci * c.k * c.k, c.b, c.co); };
+        convs_.resize(1 + blob.block_conv.size());
+        upc(convs_[0], blob.stem);
+        for (size_t i = 0; i < blob.block_conv.size(); ++i) upc(convs_[1 + i], blob.block_conv[i]);
+        upc(vconv_, blob.vconv);
+        upc(pconv_, blob.pconv);
+        up(vfc1_, blob.vfc1_w, static_cast<size_t>(d_.hidden) * d_.vh * s2, blob.vfc1_b, d_.hidden);
+        up(pfc_, blob.pfc_w, static_cast<size_t>(d_.moves) * d_.ph * s2, blob.pfc_b, d_.moves);
+        upload(vfc2_w_, std::vector<float>(D + blob.vfc2_w, D + blob.vfc2_w + d_.hidden));
+        vfc2_b_ = D[blob.vfc2_b];
+        return;
+    }
+    auto n_split = [](uint32_t n, uint32_t& n_umma, uint32_t& n_tiles) {
+        if (n <= 128) {
+            n_umma = round_up(n, 16);
+            n_tiles = 1;
+        } else {
+            n_umma = 128;
+            n_tiles = ceil_div(n, 128);
+        }
+    };
+    auto conv3 = [&](GemmW& g, const Blob::Conv& c, uint32_t ci_pad) {
+        n_split(c.co, g.n_umma, g.n_tiles);
+        const uint32_t np = g.n_umma * g.n_tiles;
+        g.k_pad = 9 * ci_pad;
+        std::vector<float> w(static_cast<size_t>(np) * g.k_pad, 0.0f), b(np, 0.0f);
+        for (uint32_t o = 0; o < c.co; ++o) {
+            b[o] = D[c.b + o];
+            for (uint32_t i = 0; i < c.ci; ++i)
+                for (uint32_t t = 0; t < 9; ++t) w[static_cast<size_t>(o) * g.k_pad + t * ci_pad + i] = D[c.w + (static_cast<size_t>(o) * c.ci + i) * 9 + t];
+        }
+        upload(g.w, to_bf16(w));
+        upload(g.b, b);
+    };
+    auto conv1 = [&](GemmW& g, const Blob::Conv& c, uint32_t co_pad) {
+        g.n_umma = co_pad;
+        g.n_tiles = 1;
+        g.k_pad = ca_;
+        std::vector<float> w(static_cast<size_t>(co_pad) * ca_, 0.0f), b(co_pad, 0.0f);
+        for (uint32_t o = 0; o < c.co; ++o) {
+            b[o] = D[c.b + o];
+            for (uint32_t i = 0; i < c.ci; ++i) w[static_cast<size_t>(o) * ca_ + i] = D[c.w + static_cast<size_t>(o) * c.ci + i];
+        }
+        upload(g.w, to_bf16(w));
+        upload(g.b, b);
+    };
+    auto fc = [&](GemmW& g, size_t w_off, size_t b_off, uint32_t n_out, uint32_t ch, uint32_t ch_pad) {
+        n_split(n_out, g.n_umma, g.n_tiles);
+        const uint32_t np = g.n_umma * g.n_tiles;
+        g.k_pad = round_up(s2 * ch_pad, 64);
+        std::vector<float> w(static_cast<size_t>(np) * g.k_pad, 0.0f), b(np, 0.0f);
+        for (uint32_t o = 0; o < n_out; ++o) {
+            b[o] = D[b_off + o];
+            for (uint32_t c = 0; c < ch; ++c)
+                for (uint32_t cell = 0; cell < s2; ++cell)
+                    w[static_cast<size_t>(o) * g.k_pad + cell * ch_pad + c] = D[w_off + static_cast<size_t>(o) * ch * s2 + c * s2 + cell];
+        }
+        upload(g.w, to_bf16(w));
+        upload(g.b, b);
+    };
+    convs_.resize(1 + blob.block_conv.size());
+    conv3(convs_[0], blob.stem, cin_pad_);
+    for (size_t i = 0; i < blob.block_conv.size(); ++i) conv3(convs_[1 + i], blob.block_conv[i], ca_);
+    conv1(vconv_, blob.vconv, vhp_);
+    conv1(pconv_, blob.pconv, php_);
+    fc(vfc1_, blob.vfc1_w, blob.vfc1_b, d_.hidden, d_.vh, vhp_);
+    fc(pfc_, blob.pfc_w, blob.pfc_b, d_.moves, d_.ph, php_);
+    upload(vfc2_w_, std::vector<float>(D + blob.vfc2_w, D + blob.vfc2_w + d_.hidden));
+    vfc2_b_ = D[blob.vfc2_b];
+}
+
+void Engine::init_lane(Lane& l) {
+    CB2_CUDA(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+    CB2_CUDA(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
+    const size_t in_bytes = 16 + static_cast<size_t>(max_batch_) * rec_.rec_bytes;
+    CB2_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&l.h_in), in_bytes, cudaHostAllocDefault));
+    std::memset(l.h_in, 0, in_bytes);
+    CB2_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&l.h_values), sizeof(float) * max_batch_, cudaHostAllocDefault));
+    CB2_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&l.h_probs), sizeof(float) * max_batch_ * d_.moves, cudaHostAllocDefault));
+    l.d_in.alloc(in_bytes);
+    l.d_values.alloc(sizeof(float) * max_batch_);
+    l.d_offsets.alloc(sizeof(uint32_t) * (max_batch_ + 1));
+    l.d_probs.alloc(sizeof(float) * max_batch_ * d_.moves);
+    const uint32_t s2 = d_.s2();
+    l.d_dense.alloc(sizeof(float) * max_batch_ * d_.c_in * s2);
+    l.d_hidden.alloc(sizeof(float) * max_batch_ * d_.hidden);
+    if (precision_ == CATTUS_B200_PRECISION_FP32_CHECK) {
+        l.d_x.alloc(sizeof(float) * max_batch_ * d_.c_in * s2);
+        for (auto& a : l.d_act) a.alloc(sizeof(float) * max_batch_ * d_.f * s2);
+        l.d_hv.alloc(sizeof(float) * max_batch_ * d_.vh * s2);
+        l.d_hp.alloc(sizeof(float) * max_batch_ * d_.ph * s2);
+        l.d_logits.alloc(sizeof(float) * max_batch_ * d_.moves);
+    } else {
+        const size_t rows = static_cast<size_t>(round_up(max_batch_, nb_)) * s2;
+        l.d_x.alloc(rows * cin_pad_ * 2);
+        for (auto& a : l.d_act) a.alloc(rows * ca_ * 2);
+        l.d_hv.alloc(rows * vhp_ * 2);
+        l.d_hp.alloc(rows * php_ * 2);
+        l.d_logits.alloc(sizeof(float) * max_batch_ * pfc_.n_umma * pfc_.n_tiles);
+    }
+}
+
+uint32_t Engine::bucket_for(uint32_t n) const {
+    uint32_t b = 1;
+    while (b < n) b <<= 1;
+    return std::min(b, max_batch_);
+}
+
+// ------------------------------------------------------------------------------------------------ tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+CUtensorMap Engine::make_map_2d(const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes, uint32_t box_rows) {
+    CUtensorMap m;
+    cuuint64_t gdim[2] = {inner, rows};
+    cuuint64_t gstr[1] = {row_stride_bytes};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = reinterpret_cast<EncodeTiledFn>(encode_tiled_)(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr,
+                                                                box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw Error(CATTUS_B200_ECUDA, "cuTensorMapEncodeTiled(2d) failed with " + std::to_string(static_cast<int>(r)));
+    return m;
+}
+
+// NHWC activations [boards][S][S][channels]; box = {64 channels, S, S, nb boards}.  Out-of-bounds halo -> zeros.
+CUtensorMap Engine::make_map_conv(const void* base, uint32_t channels, uint32_t boards, uint32_t nb) {
+    CUtensorMap m;
+    const uint64_t s = d_.s;
+    cuuint64_t gdim[4] = {channels, s, s, boards};
+    cuuint64_t gstr[3] = {channels * 2ull, s * channels * 2ull, s * s * channels * 2ull};
+    cuuint32_t box[4] = {64, static_cast<cuuint32_t>(s), static_cast<cuuint32_t>(s), nb};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = reinterpret_cast<EncodeTiledFn>(encode_tiled_)(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr,
+                                                                box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw Error(CATTUS_B200_ECUDA, "cuTensorMapEncodeTiled(4d) failed with " + std::to_string(static_cast<int>(r)));
+    return m;
+}
+
+Op Engine::make_tc_op(int stage, const char* name, const TcGemmParams& p, uint32_t m_tiles, uint32_t n_tiles) {
+    Op op;
+    op.stage = stage;
+    op.name = name;
+    const dim3 grid(m_tiles, n_tiles);
+    op.launch = [p, grid](cudaStream_t st) { tc_gemm_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(p); };
+    return op;
+}
+
+// ------------------------------------------------------------------------------------------------ op lists
+static inline int grid_for(long long work_items, int threads, int sm_count) {
+    long long blocks = (work_items + threads - 1) / threads;
+    const long long cap = static_cast<long long>(sm_count) * 16;
+    return static_cast<int>(std::max<long long>(1, std::min(blocks, cap)));
+}
+
+std::vector<Op>& Engine::ops_for(Lane& lane, uint32_t bucket, bool dense_input) {
+    const uint32_t key = bucket | (dense_input ? 0x80000000u : 0u);
+    auto it = lane.ops.find(key);
+    if (it != lane.ops.end()) return it->second;
+    std::vector<Op> ops;
+    if (precision_ == CATTUS_B200_PRECISION_FP32_CHECK)
+        build_ops_fp32(lane, bucket, ops, dense_input);
+    else
+        build_ops_bf16(lane, bucket, ops, dense_input);
+    return lane.ops.emplace(key, std::move(ops)).first->second;
+}
+
+void Engine::add_tail_ops(Lane& lane, uint32_t bucket, std::vector<Op>& ops, bool dense_input) {
+    const uint8_t* recs = lane.d_in.as<uint8_t>() + 16;
+    const uint32_t* n_ptr = lane.d_in.as<uint32_t>();
+    const RecLayout L = rec_;
+    const int ld_logits = precision_ == CATTUS_B200_PRECISION_FP32_CHECK ? static_cast<int>(d_.moves) : static_cast<int>(pfc_.n_umma * pfc_.n_tiles);
+    {
+        Op op;
+        op.stage = 3;
+        op.name = "value_tail";
+        const float* hidden = lane.d_hidden.as<float>();
+        const float* w2 = vfc2_w_.as<float>();
+        const float b2 = vfc2_b_;
+        float* values = lane.d_values.as<float>();
+        const int blocks = static_cast<int>(ceil_div(bucket * 32, 256));
+        op.launch = [=](cudaStream_t st) { value_tail_kernel<<<blocks, 256, 0, st>>>(hidden, 128, w2, b2, n_ptr, values); };
+        ops.push_back(op);
+    }
+    if (dense_input) return;  // run_dense returns raw logits (Model::run semantics)
+    {
+        Op op;
+        op.stage = 3;
+        op.name = "legal_offsets";
+        uint32_t* offsets = lane.d_offsets.as<uint32_t>();
+        op.launch = [=](cudaStream_t st) { legal_offsets_kernel<<<1, 1024, 0, st>>>(recs, L, n_ptr, offsets); };
+        ops.push_back(op);
+    }
+    {
+        Op op;
+        op.stage = 3;
+        op.name = "policy_tail";
+        const float* logits = lane.d_logits.as<float>();
+        const uint32_t* offsets = lane.d_offsets.as<uint32_t>();
+        float* probs = lane.d_probs.as<float>();
+        const int blocks = static_cast<int>(ceil_div(bucket * 32, 256));
+        op.launch = [=](cudaStream_t st) { policy_tail_kernel<<<blocks, 256, 0, st>>>(logits, ld_logits, recs, L, n_ptr, offsets, probs); };
+        ops.push_back(op);
+    }
+}
+
+void Engine::build_ops_fp32(Lane& lane, uint32_t bucket, std::vector<Op>& ops, bool dense_input) {
+    const int s = static_cast<int>(d_.s), s2 = static_cast<int>(d_.s2());
+    const int n = static_cast<int>(bucket);
+    const uint8_t* recs = lane.d_in.as<uint8_t>() + 16;
+    const uint32_t* n_ptr = lane.d_in.as<uint32_t>();
+    const RecLayout L = rec_;
+    const int sm = sm_count_;
+    const float* x = dense_input ? lane.d_dense.as<float>() : lane.d_x.as<float>();
+    if (!dense_input) {
+        Op op;
+        op.stage = 0;
+        op.name = "encode_nchw_f32";
+        float* out = lane.d_x.as<float>();
+        const long long total = static_cast<long long>(n) * d_.c_in * s2;
+        const int blocks = grid_for(total, 256, sm);
+        op.launch = [=](cudaStream_t st) { encode_nchw_f32_kernel<<<blocks, 256, 0, st>>>(recs, L, n_ptr, n, out); };
+        ops.push_back(op);
+    }
+    auto conv = [&](int stage, const char* name, const float* in, const GemmW& g, const float* resid, float* out, int ci, int co, int ks, int relu) {
+        Op op;
+        op.stage = stage;
+        op.name = name;
+        const float* w = g.w.as<float>();
+        const float* b = g.b.as<float>();
+        const long long total = static_cast<long long>(n) * co * s2;
+        const int blocks = grid_for(total, 128, sm);
+        op.launch = [=](cudaStream_t st) { conv_f32_kernel<<<blocks, 128, 0, st>>>(in, w, b, resid, out, n, ci, co, s, ks, relu); };
+        ops.push_back(op);
+    };
+    auto fc = [&](const char* name, const float* in, const GemmW& g, float* out, int k, int no, int ld, int relu) {
+        Op op;
+        op.stage = 2;
+        op.name = name;
+        const float* w = g.w.as<float>();
+        const float* b = g.b.as<float>();
+        const long long total = static_cast<long long>(n) * no * 32;
+        const int blocks = grid_for(total, 256, sm);
+        op.launch = [=](cudaStream_t st) { fc_f32_kernel<<<blocks, 256, 0, st>>>(in, w, b, out, n, k, no, ld, relu); };
+        ops.push_back(op);
+    };
+    float* act[3] = {lane.d_act[0].as<float>(), lane.d_act[1].as<float>(), lane.d_act[2].as<float>()};
+    const int F = static_cast<int>(d_.f);
+    conv(1, "stem", x, convs_[0], nullptr, act[0], static_cast<int>(d_.c_in), F, 3, 1);
+    int cur = 0;
+    for (uint32_t i = 0; i < d_.r; ++i) {
+        const int h = (cur + 1) % 3, o = (cur + 2) % 3;
+        conv(1, "block_conv1", act[cur], convs_[1 + 2 * i], nullptr, act[h], F, F, 3, 1);
+        conv(1, "block_conv2", act[h], convs_[2 + 2 * i], act[cur], act[o], F, F, 3, 1);
+        cur = o;
+    }
+    conv(2, "value_conv", act[cur], vconv_, nullptr, lane.d_hv.as<float>(), F, static_cast<int>(d_.vh), 1, 1);
+    conv(2, "policy_conv", act[cur], pconv_, nullptr, lane.d_hp.as<float>(), F, static_cast<int>(d_.ph), 1, 1);
+    fc("value_fc1", lane.d_hv.as<float>(), vfc1_, lane.d_hidden.as<float>(), static_cast<int>(d_.vh) * s2, 128, 128, 1);
+    fc("policy_fc", lane.d_hp.as<float>(), pfc_, lane.d_logits.as<float>(), static_cast<int>(d_.ph) * s2, static_cast<int>(d_.moves),
+       static_cast<int>(d_.moves), 0);
+    add_tail_ops(lane, bucket, ops, dense_input);
+}
+
+void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, bool dense_input) {
+    const uint32_t s2 = d_.s2();
+    const uint32_t tiles = ceil_div(bucket, nb_);
+    const uint32_t boards = tiles * nb_;
+    const uint32_t rows_total = boards * s2;
+    const uint8_t* recs = lane.d_in.as<uint8_t>() + 16;
+    const uint32_t* n_ptr = lane.d_in.as<uint32_t>();
+    const RecLayout L = rec_;
+    const int sm = sm_count_;
+    __nv_bfloat16* x = lane.d_x.as<__nv_bfloat16>();
+    {
+        Op op;
+        op.stage = 0;
+        const int blocks = grid_for(static_cast<long long>(rows_total) * (cin_pad_ / 8), 256, sm);
+        const int rt = static_cast<int>(rows_total);
+        if (dense_input) {
+            op.name = "nchw_f32_to_nhwc_bf16";
+            const float* in = lane.d_dense.as<float>();
+            const int n = static_cast<int>(bucket), ci = static_cast<int>(d_.c_in), is2 = static_cast<int>(s2);
+            const int blocks64 = grid_for(static_cast<long long>(rows_total) * 64, 256, sm);
+            if (cin_pad_ != 64) throw Error(CATTUS_B200_EINVAL, "planes > 64 not supported");
+            op.launch = [=](cudaStream_t st) { nchw_f32_to_nhwc_bf16_kernel<<<blocks64, 256, 0, st>>>(in, n, ci, is2, rt, x); };
+        } else {
+            op.name = "encode_nhwc_bf16";
+            op.launch = [=](cudaStream_t st) { encode_nhwc_bf16_kernel<<<blocks, 256, 0, st>>>(recs, L, n_ptr, rt, x); };
+        }
+        ops.push_back(op);
+    }
+    auto base_params = [&]() {
+        TcGemmParams p;
+        std::memset(&p, 0, sizeof(p));
+        p.err = d_err_;
+        p.s2 = static_cast<int>(s2);
+        p.nb = static_cast<int>(nb_);
+        return p;
+    };
+    // 3x3 conv: A = NHWC activations through the 4-D halo map, B = [Np][9*Cpad]
+    auto conv3 = [&](const char* name, const __nv_bfloat16* in, uint32_t cpad, const GemmW& g, const __nv_bfloat16* resid, __nv_bfloat16* out) {
+        TcGemmParams p = base_params();
+        p.tma_a = make_map_conv(in, cpad, boards, nb_);
+        p.tma_b = make_map_2d(g.w.p, g.k_pad, static_cast<uint64_t>(g.n_umma) * g.n_tiles, g.k_pad * 2ull, g.n_umma);
+        p.bias = g.b.as<float>();
+        p.resid = resid;
+        p.out = out;
+        p.mode = 1;
+        p.kh = static_cast<int>(cpad / 64);
+        p.num_kb = 9 * p.kh;
+        p.n_umma = static_cast<int>(g.n_umma);
+        p.n_store = static_cast<int>(g.n_umma);
+        p.m_valid = static_cast<int>(boards);
+        p.rows_per_tile = static_cast<int>(nb_ * s2);
+        p.ld_out = static_cast<int>(ca_);
+        p.out_f32 = 0;
+        p.relu = 1;
+        p.tx_bytes = nb_ * s2 * 128 + g.n_umma * 128;
+        ops.push_back(make_tc_op(1, name, p, tiles, g.n_tiles));
+    };
+    // plain GEMM: A = [rows][K] row-major bf16
+    auto gemm = [&](int stage, const char* name, const void* a, uint64_t k_real, uint64_t rows, uint64_t row_stride_bytes, const GemmW& g,
+                    void* out, uint32_t ld_out, bool out_f32, bool relu) {
+        TcGemmParams p = base_params();
+        p.tma_a = make_map_2d(a, k_real, rows, row_stride_bytes, 128);
+        p.tma_b = make_map_2d(g.w.p, g.k_pad, static_cast<uint64_t>(g.n_umma) * g.n_tiles, g.k_pad * 2ull, g.n_umma);
+        p.bias = g.b.as<float>();
+        p.out = out;
+        p.mode = 0;
+        p.kh = 1;
+        p.num_kb = static_cast<int>(g.k_pad / 64);
+        p.n_umma = static_cast<int>(g.n_umma);
+        p.n_store = static_cast<int>(g.n_umma);
+        p.m_valid = static_cast<int>(rows);
+        p.rows_per_tile = 128;
+        p.ld_out = static_cast<int>(ld_out);
+        p.out_f32 = out_f32 ? 1 : 0;
+        p.relu = relu ? 1 : 0;
+        p.tx_bytes = 128 * 128 + g.n_umma * 128;
+        ops.push_back(make_tc_op(stage, name, p, ceil_div(static_cast<uint32_t>(rows), 128), g.n_tiles));
+    };
+    __nv_bfloat16* act[3] = {lane.d_act[0].as<__nv_bfloat16>(), lane.d_act[1].as<__nv_bfloat16>(), lane.d_act[2].as<__nv_bfloat16>()};
+    conv3("stem", x, cin_pad_, convs_[0], nullptr, act[0]);
+    int cur = 0;
+    for (uint32_t i = 0; i < d_.r; ++i) {
+        const int h = (cur + 1) % 3, o = (cur + 2) % 3;
+        conv3("block_conv1", act[cur], ca_, convs_[1 + 2 * i], nullptr, act[h]);
+        conv3("block_conv2", act[h], ca_, convs_[2 + 2 * i], act[cur], act[o]);
+        cur = o;
+    }
+    gemm(2, "value_conv", act[cur], ca_, rows_total, ca_ * 2ull, vconv_, lane.d_hv.p, vhp_, false, true);
+    gemm(2, "policy_conv", act[cur], ca_, rows_total, ca_ * 2ull, pconv_, lane.d_hp.p, php_, false, true);
+    gemm(2, "value_fc1", lane.d_hv.p, static_cast<uint64_t>(s2) * vhp_, bucket, static_cast<uint64_t>(s2) * vhp_ * 2, vfc1_, lane.d_hidden.p, 128,
+         true, true);
+    gemm(2, "policy_fc", lane.d_hp.p, static_cast<uint64_t>(s2) * php_, bucket, static_cast<uint64_t>(s2) * php_ * 2, pfc_, lane.d_logits.p,
+         pfc_.n_umma * pfc_.n_tiles, true, false);
+    add_tail_ops(lane, bucket, ops, dense_input);
+}
+
+void Engine::run_bucket(Lane& lane, uint32_t bucket, cudaStream_t stream, bool use_graph, bool dense_input) {
+    std::vector<Op>& ops = ops_for(lane, bucket, dense_input);
+    if (!use_graph) {
+        for (const Op& op : ops) op.launch(stream);
+        CB2_CUDA(cudaGetLastError());
+        return;
+    }
+    const uint32_t key = bucket | (dense_input ? 0x80000000u : 0u);
+    auto it = lane.graphs.find(key);
+    if (it == lane.graphs.end()) {
+        // capture on the lane's own stream (never on a caller's stream)
+        cudaGraph_t graph = nullptr;
+        CB2_CUDA(cudaStreamBeginCapture(lane.stream, cudaStreamCaptureModeThreadLocal));
+        for (const Op& op : ops) op.launch(lane.stream);
+        cudaError_t ce = cudaStreamEndCapture(lane.stream, &graph);
+        if (ce != cudaSuccess) throw Error(CATTUS_B200_ECUDA, std::string("graph capture failed: ") + cudaGetErrorString(ce));
+        cudaGraphExec_t exec = nullptr;
+        ce = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) throw Error(CATTUS_B200_ECUDA, std::string("graph instantiate failed: ") + cudaGetErrorString(ce));
+        it = lane.graphs.emplace(key, exec).first;
+    }
+    CB2_CUDA(cudaGraphLaunch(it->second, stream));
+}
+
+void Engine::throw_device_error(const char* where, cudaError_t e) {
+    const uint32_t code = h_err_ ? *h_err_ : 0;
+    char buf[256];
+    std::snprintf(buf, sizeof(buf), "%s: %s (device fault word 0x%x)", where, cudaGetErrorString(e), code);
+    throw Error(code ? CATTUS_B200_EDEVICE : CATTUS_B200_ECUDA, buf);
+}
+
+// ------------------------------------------------------------------------------------------------ batches
+uint32_t Engine::pack_record(uint8_t* dst, const uint64_t* planes, const uint8_t* legal) const {
+    const int plane_bytes = rec_.planes * rec_.wpp * 8;
+    std::memcpy(dst, planes, plane_bytes);
+    uint32_t cnt = 0;
+    if (derive_legal_) {
+        for (int k = 0; k < rec_.wpp; ++k) {
+            uint64_t e = planes[2 * rec_.wpp + k] & ~(planes[k] | planes[rec_.wpp + k]);
+            const int rem = rec_.moves - 64 * k;
+            if (rem < 64) e &= (rem <= 0) ? 0ull : ((1ull << rem) - 1ull);
+            cnt += static_cast<uint32_t>(__builtin_popcountll(e));
+        }
+    } else {
+        if (legal == nullptr) throw Error(CATTUS_B200_EINVAL, "this game needs an explicit legal-move bitmap");
+        const int bm = static_cast<int>(d_.bitmap_bytes());
+        const int padded = rec_.rec_bytes - plane_bytes;
+        uint8_t* d = dst + plane_bytes;
+        std::memcpy(d, legal, bm);
+        std::memset(d + bm, 0, padded - bm);
+        if (rec_.moves % 8) d[bm - 1] &= static_cast<uint8_t>((1u << (rec_.moves % 8)) - 1u);
+        const uint64_t* w = reinterpret_cast<const uint64_t*>(d);
+        for (int k = 0; k < padded / 8; ++k) cnt += static_cast<uint32_t>(__builtin_popcountll(w[k]));
+    }
+    return cnt;
+}
+
+void Engine::submit(Lane& l, uint32_t n, uint32_t total_probs) {
+    *reinterpret_cast<uint32_t*>(l.h_in) = n;
+    CB2_CUDA(cudaMemcpyAsync(l.d_in.p, l.h_in, 16 + static_cast<size_t>(n) * rec_.rec_bytes, cudaMemcpyHostToDevice, l.stream));
+    run_bucket(l, bucket_for(n), l.stream, true, false);
+    CB2_CUDA(cudaMemcpyAsync(l.h_values, l.d_values.p, sizeof(float) * n, cudaMemcpyDeviceToHost, l.stream));
+    if (total_probs) CB2_CUDA(cudaMemcpyAsync(l.h_probs, l.d_probs.p, sizeof(float) * total_probs, cudaMemcpyDeviceToHost, l.stream));
+    CB2_CUDA(cudaEventRecord(l.done, l.stream));
+}
+
+void Engine::finish(Lane& l, uint32_t n) {
+    cudaError_t e = cudaEventSynchronize(l.done);
+    if (e != cudaSuccess) throw_device_error("batch", e);
+    (void)n;
+}
+
+Lane& Engine::acquire_lane() {
+    std::unique_lock<std::mutex> g(lane_mu_);
+    for (;;) {
+        for (size_t i = 0; i < lanes_.size(); ++i)
+            if (!lane_busy_[i]) {
+                lane_busy_[i] = 1;
+                return *lanes_[i];
+            }
+        lane_cv_.wait(g);
+    }
+}
+void Engine::release_lane(Lane& l) {
+    {
+        std::lock_guard<std::mutex> g(lane_mu_);
+        lane_busy_[l.index] = 0;
+    }
+    lane_cv_.notify_one();
+}
+
+void Engine::note_batch(uint32_t n, double seconds) {
+    std::lock_guard<std::mutex> g(m_mu_);
+    metrics_.activation_count += 1;
+    metrics_.positions += n;
+    metrics_.run_duration_last = seconds;
+    // RunningAverage(0.99): engine/src/util/metric.rs:1-20 -- first sample initialises, then ema = ema*(1-e) + x*e
+    metrics_.run_duration_ema = metrics_.activation_count == 1 ? seconds : metrics_.run_duration_ema * 0.01 + seconds * 0.99;
+    metrics_.mean_batch_fill = static_cast<double>(metrics_.positions) / (static_cast<double>(metrics_.activation_count) * max_batch_);
+    metrics_.kernel_launches += kernels_per_batch_;
+}
+
+// The per-leaf path.  A worker writes its record into the open pinned block under the queue lock, then sleeps on a
+// condition variable until an evaluator thread has shipped the block and scattered the results back.
+void Engine::eval_leaf(const uint64_t* planes, const uint8_t* legal, LeafRequest* req) {
+    std::unique_lock<std::mutex> g(q_mu_);
+    q_space_cv_.wait(g, [&] { return stopping_ || open_reqs_.size() < max_batch_; });
+    if (stopping_) throw Error(CATTUS_B200_EINVAL, "evaluator is shutting down");
+    const uint32_t slot = static_cast<uint32_t>(open_reqs_.size());
+    req->count = pack_record(open_block_ + 16 + static_cast<size_t>(slot) * rec_.rec_bytes, planes, legal);
+    if (req->count > req->probs_cap) throw Error(CATTUS_B200_ERANGE, "probs_cap is smaller than the number of legal moves");
+    req->status = 1;
+    open_reqs_.push_back(req);
+    open_total_ += req->count;
+    q_cv_.notify_one();
+    done_cv_.wait(g, [&] { return req->status != 1; });
+    if (req->status < 0) throw Error(req->status, req->error);
+}
+
+void Engine::evaluator_loop() {
+    cudaSetDevice(device_);
+    std::vector<LeafRequest*> reqs;
+    for (;;) {
+        {
+            std::unique_lock<std::mutex> g(q_mu_);
+            q_cv_.wait(g, [&] { return stopping_ || !open_reqs_.empty(); });
+            if (stopping_ && open_reqs_.empty()) return;
+        }
+        Lane& l = acquire_lane();
+        uint32_t total = 0;
+        {
+            std::lock_guard<std::mutex> g(q_mu_);
+            if (open_reqs_.empty()) {  // another evaluator took the block while we waited for a lane
+                release_lane(l);
+                continue;
+            }
+            std::swap(open_block_, l.h_in);
+            reqs.swap(open_reqs_);
+            open_reqs_.clear();
+            total = open_total_;
+            open_total_ = 0;
+        }
+        q_space_cv_.notify_all();
+        const uint32_t n = static_cast<uint32_t>(reqs.size());
+        int status = 0;
+        std::string err;
+        const auto t0 = std::chrono::steady_clock::now();
+        try {
+            submit(l, n, total);
+            finish(l, n);
+            note_batch(n, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+        } catch (const Error& e) {
+            status = e.code;
+            err = e.what();
+        }
+        {
+            std::lock_guard<std::mutex> g(q_mu_);
+            uint32_t off = 0;
+            for (uint32_t i = 0; i < n; ++i) {
+                LeafRequest* r = reqs[i];
+                if (status == 0) {
+                    std::memcpy(r->probs_out, l.h_probs + off, sizeof(float) * r->count);
+                    *r->n_probs = r->count;
+                    *r->value_out = l.h_values[i];
+                    r->status = 0;
+                } else {
+                    r->error = err;
+                    r->status = status;
+                }
+                off += r->count;
+            }
+        }
+        done_cv_.notify_all();
+        reqs.clear();
+        release_lane(l);
+    }
+}
+
+// Synchronous bulk path: chunks of max_batch pipelined over the lanes (pack chunk i+1 while chunk i runs).
+void Engine::eval_batch(const uint64_t* planes, const uint8_t* legal, uint32_t n, float* probs_out, size_t probs_cap, uint32_t* prob_offsets,
+                        float* values_out) {
+    if (n == 0) {
+        if (prob_offsets) prob_offsets[0] = 0;
+        return;
+    }
+    if (!planes || !probs_out || !prob_offsets || !values_out) throw Error(CATTUS_B200_EINVAL, "null argument");
+    CB2_CUDA(cudaSetDevice(device_));
+    struct InFlight {
+        Lane* lane;
+        uint32_t first, n, total;
+        size_t prob_base;
+        std::chrono::steady_clock::time_point t0;
+    };
+    std::deque<InFlight> inflight;
+    const size_t plane_words = static_cast<size_t>(rec_.planes) * rec_.wpp;
+    const size_t bm = d_.bitmap_bytes();
+    size_t prob_cursor = 0;
+    auto drain_one = [&]() {
+        InFlight f = inflight.front();
+        inflight.pop_front();
+        try {
+            finish(*f.lane, f.n);
+        } catch (...) {
+            release_lane(*f.lane);
+            for (auto& o : inflight) release_lane(*o.lane);
+            inflight.clear();
+            throw;
+        }
+        std::memcpy(values_out + f.first, f.lane->h_values, sizeof(float) * f.n);
+        std::memcpy(probs_out + f.prob_base, f.lane->h_probs, sizeof(float) * f.total);
+        note_batch(f.n, std::chrono::duration<double>(std::chrono::steady_clock::now() - f.t0).count());
+        release_lane(*f.lane);
+    };
+    try {
+        for (uint32_t first = 0; first < n; first += max_batch_) {
+            const uint32_t cn = std::min(max_batch_, n - first);
+            if (inflight.size() >= lanes_.size()) drain_one();
+            Lane& l = acquire_lane();
+            uint32_t total = 0;
+            try {
+                for (uint32_t i = 0; i < cn; ++i) {
+                    const uint32_t b = first + i;
+                    const uint32_t c = pack_record(l.h_in + 16 + static_cast<size_t>(i) * rec_.rec_bytes, planes + b * plane_words,
+                                                   legal ? legal + b * bm : nullptr);
+                    prob_offsets[b] = static_cast<uint32_t>(prob_cursor + total);
+                    total += c;
+                }
+                if (prob_cursor + total > probs_cap) throw Error(CATTUS_B200_ERANGE, "probs_cap is smaller than the number of legal moves");
+                InFlight f{&l, first, cn, total, prob_cursor, std::chrono::steady_clock::now()};
+                submit(l, cn, total);
+                inflight.push_back(f);
+            } catch (...) {
+                release_lane(l);
+                throw;
+            }
+            prob_cursor += total;
+        }
+        prob_offsets[n] = static_cast<uint32_t>(prob_cursor);
+        while (!inflight.empty()) drain_one();
+    } catch (...) {
+        while (!inflight.empty()) {
+            cudaEventSynchronize(inflight.front().lane->done);
+            release_lane(*inflight.front().lane);
+            inflight.pop_front();
+        }
+        throw;
+    }
+}
+
+void Engine::encode(const uint64_t* planes, uint32_t n, uint32_t batch, float* nchw_out) {
+    if (n < 1 || n > batch) throw Error(CATTUS_B200_EINVAL, "invalid sample len " + std::to_string(n) + ", 1..=" + std::to_string(batch));
+    if (batch > max_batch_) throw Error(CATTUS_B200_ERANGE, "batch_size exceeds max_batch");
+    CB2_CUDA(cudaSetDevice(device_));
+    Lane& l = acquire_lane();
+    try {
+        const size_t plane_bytes = static_cast<size_t>(rec_.planes) * rec_.wpp * 8;
+        for (uint32_t i = 0; i < n; ++i) {
+            uint8_t* dst = l.h_in + 16 + static_cast<size_t>(i) * rec_.rec_bytes;
+            std::memset(dst, 0, rec_.rec_bytes);
+            std::memcpy(dst, planes + i * (plane_bytes / 8), plane_bytes);
+        }
+        *reinterpret_cast<uint32_t*>(l.h_in) = n;
+        CB2_CUDA(cudaMemcpyAsync(l.d_in.p, l.h_in, 16 + static_cast<size_t>(n) * rec_.rec_bytes, cudaMemcpyHostToDevice, l.stream));
+        const long long total = static_cast<long long>(batch) * d_.c_in * d_.s2();
+        encode_nchw_f32_kernel<<<grid_for(total, 256, sm_count_), 256, 0, l.stream>>>(l.d_in.as<uint8_t>() + 16, rec_, l.d_in.as<uint32_t>(),
+                                                                                     static_cast<int>(batch), l.d_dense.as<float>());
+        CB2_CUDA(cudaGetLastError());
+        CB2_CUDA(cudaMemcpyAsync(nchw_out, l.d_dense.p, sizeof(float) * total, cudaMemcpyDeviceToHost, l.stream));
+        cudaError_t e = cudaStreamSynchronize(l.stream);
+        if (e != cudaSuccess) throw_device_error("encode", e);
+        {
+            std::lock_guard<std::mutex> g(m_mu_);
+            metrics_.kernel_launches += 1;
+        }
+    } catch (...) {
+        release_lane(l);
+        throw;
+    }
+    release_lane(l);
+}
+
+void Engine::run_dense(const float* nchw, uint32_t n, float* logits_out, float* values_out) {
+    if (n == 0) return;
+    if (!nchw || !logits_out || !values_out) throw Error(CATTUS_B200_EINVAL, "null argument");
+    CB2_CUDA(cudaSetDevice(device_));
+    const size_t per = static_cast<size_t>(d_.c_in) * d_.s2();
+    const uint32_t ld = precision_ == CATTUS_B200_PRECISION_FP32_CHECK ? d_.moves : pfc_.n_umma * pfc_.n_tiles;
+    Lane& l = acquire_lane();
+    try {
+        for (uint32_t first = 0; first < n; first += max_batch_) {
+            const uint32_t cn = std::min(max_batch_, n - first);
+            const uint32_t bucket = bucket_for(cn);
+            *reinterpret_cast<uint32_t*>(l.h_in) = cn;
+            CB2_CUDA(cudaMemcpyAsync(l.d_in.p, l.h_in, 16, cudaMemcpyHostToDevice, l.stream));
+            if (bucket > cn) CB2_CUDA(cudaMemsetAsync(l.d_dense.as<float>() + cn * per, 0, sizeof(float) * (bucket - cn) * per, l.stream));
+            CB2_CUDA(cudaMemcpyAsync(l.d_dense.p, nchw + first * per, sizeof(float) * cn * per, cudaMemcpyHostToDevice, l.stream));
+            run_bucket(l, bucket, l.stream, true, true);
+            CB2_CUDA(cudaMemcpy2DAsync(logits_out + static_cast<size_t>(first) * d_.moves, sizeof(float) * d_.moves, l.d_logits.p, sizeof(float) * ld,
+                                       sizeof(float) * d_.moves, cn, cudaMemcpyDeviceToHost, l.stream));
+            CB2_CUDA(cudaMemcpyAsync(values_out + first, l.d_values.p, sizeof(float) * cn, cudaMemcpyDeviceToHost, l.stream));
+            cudaError_t e = cudaStreamSynchronize(l.stream);
+            if (e != cudaSuccess) throw_device_error("run_dense", e);
+            std::lock_guard<std::mutex> g(m_mu_);
+            metrics_.kernel_launches += ops_for(l, bucket, true).size();
+        }
+    } catch (...) {
+        release_lane(l);
+        throw;
+    }
+    release_lane(l);
+}
+
+// Device-resident variant (lane 0): used by the bench to time the kernels with inputs already in HBM.
+void Engine::resident_upload(const uint64_t* planes, const uint8_t* legal, uint32_t n) {
+    if (n == 0 || n > max_batch_) throw Error(CATTUS_B200_ERANGE, "resident batch must be 1..max_batch");
+    CB2_CUDA(cudaSetDevice(device_));
+    Lane& l = *lanes_[0];
+    const size_t plane_words = static_cast<size_t>(rec_.planes) * rec_.wpp;
+    const size_t bm = d_.bitmap_bytes();
+    for (uint32_t i = 0; i < n; ++i)
+        pack_record(l.h_in + 16 + static_cast<size_t>(i) * rec_.rec_bytes, planes + i * plane_words, legal ? legal + i * bm : nullptr);
+    *reinterpret_cast<uint32_t*>(l.h_in) = n;
+    CB2_CUDA(cudaMemcpyAsync(l.d_in.p, l.h_in, 16 + static_cast<size_t>(n) * rec_.rec_bytes, cudaMemcpyHostToDevice, l.stream));
+    CB2_CUDA(cudaStreamSynchronize(l.stream));
+}
+
+void Engine::eval_resident(uint32_t n, cudaStream_t stream) {
+    if (n == 0 || n > max_batch_) throw Error(CATTUS_B200_ERANGE, "resident batch must be 1..max_batch");
+    CB2_CUDA(cudaSetDevice(device_));
+    Lane& l = *lanes_[0];
+    run_bucket(l, bucket_for(n), stream ? stream : l.stream, true, false);
+    std::lock_guard<std::mutex> g(m_mu_);
+    metrics_.kernel_launches += kernels_per_batch_;
+}
+
+void Engine::resident_download(uint32_t n, float* probs_out, size_t probs_cap, uint32_t* prob_offsets, float* values_out) {
+    if (n == 0 || n > max_batch_) throw Error(CATTUS_B200_ERANGE, "resident batch must be 1..max_batch");
+    CB2_CUDA(cudaSetDevice(device_));
+    Lane& l = *lanes_[0];
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) throw_device_error("eval_resident", e);
+    CB2_CUDA(cudaMemcpy(prob_offsets, l.d_offsets.p, sizeof(uint32_t) * (n + 1), cudaMemcpyDeviceToHost));
+    const uint32_t total = prob_offsets[n];
+    if (total > probs_cap) throw Error(CATTUS_B200_ERANGE, "probs_cap is smaller than the number of legal moves");
+    CB2_CUDA(cudaMemcpy(probs_out, l.d_probs.p, sizeof(float) * total, cudaMemcpyDeviceToHost));
+    CB2_CUDA(cudaMemcpy(values_out, l.d_values.p, sizeof(float) * n, cudaMemcpyDeviceToHost));
+}
+
+// ms_out[i] = device time of iteration i of the selected stage(s) on lane 0's stream, CUDA events on that stream,
+// with an L2 flush (256 MiB memset) before every iteration, outside the timed bracket.
+void Engine::time_stage(uint32_t stage, uint32_t n, uint32_t iters, float* ms_out) {
+    if (n == 0 || n > max_batch_ || iters == 0 || stage > 4) throw Error(CATTUS_B200_EINVAL, "time_stage: bad argument");
+    CB2_CUDA(cudaSetDevice(device_));
+    Lane& l = *lanes_[0];
+    if (flush_.p == nullptr) flush_.alloc(256ull << 20);
+    const uint32_t bucket = bucket_for(n);
+    std::vector<Op>& ops = ops_for(l, bucket, false);
+    std::vector<cudaEvent_t> ev(2 * iters);
+    for (auto& e : ev) CB2_CUDA(cudaEventCreate(&e));
+    uint64_t launched = 0;
+    for (uint32_t it = 0; it < iters; ++it) {
+        CB2_CUDA(cudaMemsetAsync(flush_.p, static_cast<int>(it & 0xFF), flush_.bytes, l.stream));
+        CB2_CUDA(cudaEventRecord(ev[2 * it], l.stream));
+        if (stage == 4) {
+            run_bucket(l, bucket, l.stream, true, false);
+            launched += ops.size();
+        } else {
+            for (const Op& op : ops)
+                if (op.stage == static_cast<int>(stage)) {
+                    op.launch(l.stream);
+                    ++launched;
+                }
+        }
+        CB2_CUDA(cudaEventRecord(ev[2 * it + 1], l.stream));
+    }
+    cudaError_t e = cudaStreamSynchronize(l.stream);
+    if (e != cudaSuccess) throw_device_error("time_stage", e);
+    for (uint32_t it = 0; it < iters; ++it) CB2_CUDA(cudaEventElapsedTime(&ms_out[it], ev[2 * it], ev[2 * it + 1]));
+    for (auto& x : ev) cudaEventDestroy(x);
+    std::lock_guard<std::mutex> g(m_mu_);
+    metrics_.kernel_launches += launched;
+}
+
+void Engine::get_info(cattus_b200_info* info) const {
+    std::memset(info, 0, sizeof(*info));
+    info->game = d_.game;
+    info->board_size = d_.s;
+    info->planes = d_.c_in;
+    info->moves = d_.moves;
+    info->filters = d_.f;
+    info->blocks = d_.r;
+    info->value_channels = d_.vh;
+    info->policy_channels = d_.ph;
+    info->words_per_plane = d_.wpp();
+    info->legal_bitmap_bytes = d_.bitmap_bytes();
+    info->max_batch = max_batch_;
+    info->n_streams = static_cast<uint32_t>(lanes_.size());
+    info->precision = precision_;
+    info->sm_count = static_cast<uint32_t>(sm_count_);
+    info->kernels_per_batch = kernels_per_batch_;
+    info->reserved = fused_trunk_ ? 1u : 0u;
+}
+
+void Engine::get_metrics(cattus_b200_metrics* m) const {
+    std::lock_guard<std::mutex> g(m_mu_);
+    *m = metrics_;
+}
+
+}  // namespace cb2
+
+// ================================================================================================ C ABI
+struct cattus_b200 {
+    cb2::Engine* engine;
+};
+
+static thread_local std::string g_last_error;
+
+template <class F>
+static int guarded(F&& f) {
+    try {
+        f();
+        g_last_error.clear();
+        return CATTUS_B200_OK;
+    } catch (const cb2::Error& e) {
+        g_last_error = e.what();
+        return e.code;
+    } catch (const std::bad_alloc&) {
+        g_last_error = "out of host memory";
+        return CATTUS_B200_ENOMEM;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return CATTUS_B200_EINVAL;
+    } catch (...) {
+        g_last_error = "unknown error";
+        return CATTUS_B200_EINVAL;
+    }
+}
+
+extern "C" {
+
+int cattus_b200_create_from_memory(const cattus_b200_desc* desc, const void* blob, size_t blob_bytes, cattus_b200_t** out) {
+    return guarded([&] {
+        if (!desc || !out) throw cb2::Error(CATTUS_B200_EINVAL, "null argument");
+        if (desc->struct_size != sizeof(cattus_b200_desc)) throw cb2::Error(CATTUS_B200_EINVAL, "descriptor struct_size mismatch (ABI version?)");
+        *out = nullptr;
+        std::unique_ptr<cb2::Engine> e(new cb2::Engine(*desc, blob, blob_bytes));
+        *out = new cattus_b200{e.release()};
+    });
+}
+
+int cattus_b200_create(const cattus_b200_desc* desc, cattus_b200_t** out) {
+    return guarded([&] {
+        if (!desc || !out) throw cb2::Error(CATTUS_B200_EINVAL, "null argument");
+        if (!desc->weights_path) throw cb2::Error(CATTUS_B200_EINVAL, "weights_path is NULL");
+        std::ifstream f(desc->weights_path, std::ios::binary);
+        if (!f) throw cb2::Error(CATTUS_B200_EINVAL, std::string("cannot open weight blob ") + desc->weights_path);
+        std::vector<char> bytes((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+        cattus_b200_t* h = nullptr;
+        const int rc = cattus_b200_create_from_memory(desc, bytes.data(), bytes.size(), &h);
+        if (rc != CATTUS_B200_OK) throw cb2::Error(rc, g_last_error);
+        *out = h;
+    });
+}
+
+void cattus_b200_destroy(cattus_b200_t* h) {
+    if (!h) return;
+    delete h->engine;
+    delete h;
+}
+
+int cattus_b200_get_info(const cattus_b200_t* h, cattus_b200_info* info) {
+    return guarded([&] {
+        if (!h || !info) throw cb2::Error(CATTUS_B200_EINVAL, "null argument");
+        h->engine->get_info(info);
+    });
+}
+
+int cattus_b200_eval(cattus_b200_t* h, const uint64_t* planes, const uint8_t* legal_bitmap, float* probs_out, uint32_t probs_cap,
+                     uint32_t* n_probs, float* value_out) {
+    return guarded([&] {
+        if (!h || !planes || !probs_out || !n_probs || !value_out) throw cb2::Error(CATTUS_B200_EINVAL, "null argument");
+        cb2::LeafRequest req;
+        req.probs_out = probs_out;
+        req.probs_cap = probs_cap;
+        req.n_probs = n_probs;
+        req.value_out = value_out;
+        h->engine->eval_leaf(planes, legal_bitmap, &req);
+    });
+}
+
+int cattus_b200_eval_batch(cattus_b200_t* h, const uint64_t* planes, const uint8_t* legal_bitmaps, uint32_t n, float* probs_out,
+                           size_t probs_cap, uint32_t* prob_offsets, float* values_out) {
+    return guarded([&] {
+        if (!h) throw cb2::Error(CATTUS_B200_EINVAL, "null handle");
+        h->engine->eval_batch(planes, legal_bitmaps, n, probs_out, probs_cap, prob_offsets, values_out);
+    });
+}
+
+int cattus_b200_encode(cattus_b200_t* h, const uint64_t* planes, uint32_t n, uint32_t batch_size, float* nchw_out) {
+    return guarded([&] {
+        if (!h || !planes || !nchw_out) throw cb2::Error(CATTUS_B200_EINVAL, "null argument");
+        h->engine->encode(planes, n, batch_size, nchw_out);
+    });
+}
+
+int cattus_b200_run_dense(cattus_b200_t* h, const float* nchw, uint32_t n, float* logits_out, float* values_out) {
+    return guarded([&] {
+        if (!h) throw cb2::Error(CATTUS_B200_EINVAL, "null handle");
+        h->engine->run_dense(nchw, n, logits_out, values_out);
+    });
+}
+
+int cattus_b200_resident_upload(cattus_b200_t* h, const uint64_t* planes, const uint8_t* legal_bitmaps, uint32_t n) {
+    return guarded([&] {
+        if (!h || !planes) throw cb2::Error(CATTUS_B200_EINVAL, "null argument");
+        h->engine->resident_upload(planes, legal_bitmaps, n);
+    });
+}
+
+int cattus_b200_eval_resident(cattus_b200_t* h, uint32_t n, void* stream) {
+    return guarded([&] {
+        if (!h) throw cb2::Error(CATTUS_B200_EINVAL, "null handle");
+        h->engine->eval_resident(n, static_cast<cudaStream_t>(stream));
+    });
+}
+
+int cattus_b200_resident_download(cattus_b200_t* h, uint32_t n, float* probs_out, size_t probs_cap, uint32_t* prob_offsets,
+                                  float* values_out) {
+    return guarded([&] {
+        if (!h || !probs_out || !prob_offsets || !values_out) throw cb2::Error(CATTUS_B200_EINVAL, "null argument");
+        h->engine->resident_download(n, probs_out, probs_cap, prob_offsets, values_out);
+    });
+}
+
+int cattus_b200_time_stage(cattus_b200_t* h, uint32_t stage, uint32_t n, uint32_t iters, float* ms_out) {
+    return guarded([&] {
+        if (!h || !ms_out) throw cb2::Error(CATTUS_B200_EINVAL, "null argument");
+        h->engine->time_stage(stage, n, iters, ms_out);
+    });
+}
+
+int cattus_b200_get_metrics(const cattus_b200_t* h, cattus_b200_metrics* out) {
+    return guarded([&] {
+        if (!h || !out) throw cb2::Error(CATTUS_B200_EINVAL, "null argument");
+        h->engine->get_metrics(out);
+    });
+}
+
+const char* cattus_b200_last_error(void) { return g_last_error.c_str(); }
+uint32_t cattus_b200_abi_version(void) { return CATTUS_B200_ABI_VERSION; }
+
+}  // extern "C"

@@ -1,6 +1,11 @@
 // Host runtime of the evaluator: weight blob -> device layouts, per-stream batch buffers ("lanes"), the launch
 // sequence for one batch (captured into a CUDA graph per batch-size bucket), the pinned batch queue that the
 // blocking per-leaf `eval` feeds, and metrics.  Everything here sits below the C ABI in include/cattus_b200.h.
+//
+// What it replaces in the reference (paths relative to /root/reference):
+//   Model::new / Model::run          engine/src/net/model.rs:61-144, :146-218   -> Engine::Engine / run_bucket
+//   Batcher::apply                   engine/src/util/batch.rs:49-177            -> Engine::eval_leaf + evaluator_loop
+//   NNetwork::run_net metrics        engine/src/net/mod.rs:41-72                -> Engine::note_batch
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -9,6 +14,7 @@
 #include <condition_variable>
 #include <cstdint>
 #include <deque>
+#include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -28,12 +34,12 @@ struct Error : std::runtime_error {
     Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
 };
 
-#define CB2_CUDA(expr)                                                                                          \
-    do {                                                                                                        \
-        cudaError_t e_ = (expr);                                                                                \
-        if (e_ != cudaSuccess)                                                                                  \
-            throw ::cb2::Error(CATTUS_B200_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e_) + " (" +   \
-                                                      __FILE__ + ":" + std::to_string(__LINE__) + ")");         \
+#define CB2_CUDA(expr)                                                                                        \
+    do {                                                                                                      \
+        cudaError_t e_ = (expr);                                                                              \
+        if (e_ != cudaSuccess)                                                                                \
+            throw ::cb2::Error(CATTUS_B200_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e_) + " (" + \
+                                                      __FILE__ + ":" + std::to_string(__LINE__) + ")");       \
     } while (0)
 
 struct NetDims {
@@ -47,39 +53,30 @@ struct NetDims {
 struct Blob {
     NetDims d;
     std::vector<float> data;
-    // offsets (in floats) into data
-    struct Conv { size_t w, b; uint32_t co, ci, k; };
+    struct Conv {
+        size_t w = 0, b = 0;  // offsets (in floats) into data
+        uint32_t co = 0, ci = 0, k = 0;
+    };
     Conv stem;
     std::vector<Conv> block_conv;  // 2 per block
     Conv vconv, pconv;
-    size_t vfc1_w, vfc1_b, vfc2_w, vfc2_b, pfc_w, pfc_b;
+    size_t vfc1_w = 0, vfc1_b = 0, vfc2_w = 0, vfc2_b = 0, pfc_w = 0, pfc_b = 0;
     static Blob parse(const void* bytes, size_t n);
 };
 
-enum class OpKind : int { EncodeNchw, EncodeNhwc, DenseToNhwc, ConvF32, FcF32, TcGemm, LegalOffsets, PolicyTail, ValueTail };
-
 struct Op {
-    OpKind kind;
-    int stage;  // 0 encode, 1 trunk, 2 heads, 3 tail
-    dim3 grid, block;
-    size_t smem = 0;
-    TcGemmParams tc;  // TcGemm
-    // small-kernel arguments
-    const void* in0 = nullptr;
-    const void* in1 = nullptr;
-    const void* in2 = nullptr;
-    const void* in3 = nullptr;
-    void* out0 = nullptr;
-    int i[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    float f0 = 0.0f;
+    int stage = 0;  // 0 encode, 1 trunk, 2 heads, 3 tail
+    const char* name = "";
+    std::function<void(cudaStream_t)> launch;
 };
 
 struct DeviceBuf {
     void* p = nullptr;
     size_t bytes = 0;
-    void alloc(size_t n);
+    void alloc(size_t n);  // zero-initialised
     void free_();
-    template <class T> T* as() const { return static_cast<T*>(p); }
+    template <class T>
+    T* as() const { return static_cast<T*>(p); }
 };
 
 // One evaluator stream with everything a batch needs: pinned I/O blocks, device I/O blocks, activations, graphs.
@@ -88,31 +85,29 @@ struct Lane {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
     // pinned host
-    uint8_t* h_in = nullptr;    // [16 B header: n][records]
+    uint8_t* h_in = nullptr;    // [16 B header: n][records]; swapped with the queue's open block
     float* h_values = nullptr;  // [max_batch]
     float* h_probs = nullptr;   // [max_batch * moves]
     // device
-    DeviceBuf d_in;                    // same layout as h_in
+    DeviceBuf d_in;  // same layout as h_in
     DeviceBuf d_values, d_offsets, d_probs;
-    DeviceBuf d_x;                     // bf16: encoded input NHWC [rows][64]; fp32: NCHW f32
-    DeviceBuf d_act[3];                // trunk activations
-    DeviceBuf d_hv, d_hp;              // head conv outputs
-    DeviceBuf d_hidden;                // value FC1 output [max_batch][128] f32
-    DeviceBuf d_logits;                // [max_batch][ld_logits] f32
-    DeviceBuf d_dense;                 // run_dense / encode staging (f32 NCHW)
-    std::map<uint32_t, std::vector<Op>> ops;     // per bucket
-    std::map<uint32_t, cudaGraphExec_t> graphs;  // per bucket
-    uint32_t resident_n = 0;
+    DeviceBuf d_x;       // bf16: encoded input NHWC [rows][64]; fp32: NCHW f32
+    DeviceBuf d_act[3];  // trunk activations
+    DeviceBuf d_hv, d_hp;  // head conv outputs
+    DeviceBuf d_hidden;    // value FC1 output [max_batch][128] f32
+    DeviceBuf d_logits;    // [max_batch][ld_logits] f32
+    DeviceBuf d_dense;     // run_dense / encode staging (f32 NCHW)
+    std::map<uint32_t, std::vector<Op>> ops;     // key: bucket | (dense_input << 31)
+    std::map<uint32_t, cudaGraphExec_t> graphs;  // same key
 };
 
 struct LeafRequest {
-    const uint64_t* planes;
-    const uint8_t* legal;
     float* probs_out;
     uint32_t probs_cap;
     uint32_t* n_probs;
     float* value_out;
-    int status = 1;  // 1 = pending, 0 = ok, <0 = error
+    uint32_t count = 0;  // legal moves of this leaf
+    int status = 1;      // 1 = pending, 0 = ok, <0 = error
     std::string error;
 };
 
@@ -124,7 +119,7 @@ class Engine {
     void get_info(cattus_b200_info* info) const;
     void get_metrics(cattus_b200_metrics* m) const;
 
-    void eval_leaf(LeafRequest* req);  // blocking
+    void eval_leaf(const uint64_t* planes, const uint8_t* legal, LeafRequest* req);  // blocking
     void eval_batch(const uint64_t* planes, const uint8_t* legal, uint32_t n, float* probs_out, size_t probs_cap,
                     uint32_t* prob_offsets, float* values_out);
     void encode(const uint64_t* planes, uint32_t n, uint32_t batch, float* nchw_out);
@@ -139,19 +134,18 @@ class Engine {
     void upload_weights(const Blob& blob);
     void init_lane(Lane& lane);
     uint32_t bucket_for(uint32_t n) const;
-    std::vector<Op>& ops_for(Lane& lane, uint32_t bucket);
+    std::vector<Op>& ops_for(Lane& lane, uint32_t bucket, bool dense_input);
     void build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, bool dense_input);
     void build_ops_fp32(Lane& lane, uint32_t bucket, std::vector<Op>& ops, bool dense_input);
-    void add_tail_ops(Lane& lane, uint32_t bucket, std::vector<Op>& ops, const float* logits, int ld_logits);
-    void launch_op(const Op& op, cudaStream_t stream);
-    void run_bucket(Lane& lane, uint32_t bucket, cudaStream_t stream, bool use_graph);
-    void check_device_error(const char* where);
+    void add_tail_ops(Lane& lane, uint32_t bucket, std::vector<Op>& ops, bool dense_input);
+    void run_bucket(Lane& lane, uint32_t bucket, cudaStream_t stream, bool use_graph, bool dense_input);
+    void throw_device_error(const char* where, cudaError_t e);
 
     // batch plumbing
-    uint32_t pack_records(Lane& lane, const uint64_t* planes, const uint8_t* legal, uint32_t n,
-                          std::vector<uint32_t>& counts);  // returns total legal moves
+    uint32_t pack_record(uint8_t* dst, const uint64_t* planes, const uint8_t* legal) const;  // returns #legal
     void submit(Lane& lane, uint32_t n, uint32_t total_probs);  // H2D + graph + D2H + event (async)
-    Lane& acquire_lane(int want = -1);
+    void finish(Lane& lane, uint32_t n);                         // wait + device error check + metrics
+    Lane& acquire_lane();
     void release_lane(Lane& lane);
     void evaluator_loop();
     void note_batch(uint32_t n, double seconds);
@@ -159,48 +153,55 @@ class Engine {
     // tensor maps
     CUtensorMap make_map_2d(const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes, uint32_t box_rows);
     CUtensorMap make_map_conv(const void* base, uint32_t channels, uint32_t boards, uint32_t nb);
-    Op make_tc_op(int stage, int mode, const CUtensorMap& a, const CUtensorMap& b, int num_kb, int kh, int n_umma,
-                  int n_tiles, int n_store, int m_valid, int rows_per_tile, int nb, int ld_out, bool out_f32, bool relu,
-                  const float* bias, const void* resid, void* out, uint32_t a_box_rows);
+    Op make_tc_op(int stage, const char* name, const TcGemmParams& p, uint32_t m_tiles, uint32_t n_tiles);
 
     NetDims d_;
-    cattus_b200_desc desc_;
+    cattus_b200_desc desc_{};
     int device_ = 0;
     int sm_count_ = 0;
     uint32_t max_batch_ = 0;
     uint32_t precision_ = 0;
-    RecLayout rec_;
+    RecLayout rec_{};
     bool derive_legal_ = false;
+    bool fused_trunk_ = false;  // S == 8 && F == 128: whole-trunk kernel (trunk_fused.cuh)
 
     // derived layout constants (bf16 path)
+    uint32_t cin_pad_ = 64;  // encoded-input channels (multiple of 64)
     uint32_t ca_ = 64;       // trunk activation channels (multiple of 64)
     uint32_t nb_ = 1;        // boards per 128-row tile
-    uint32_t fp_ = 16;       // UMMA N for trunk convs
-    uint32_t vhp_ = 8, php_ = 8;
-    uint32_t n_pol_ = 16, pol_tiles_ = 1, ld_logits_ = 16;
+    uint32_t vhp_ = 16, php_ = 16;
 
     // weights on device
-    struct ConvDev { DeviceBuf w, b; uint32_t co, ci, k; CUtensorMap map; uint32_t n_umma; uint32_t k_total; };
-    std::vector<ConvDev> convs_;  // stem, then 2 per block (bf16: [Np][9*Cin_pad] bf16; fp32: torch layout f32)
-    ConvDev vconv_, pconv_, vfc1_, pfc_;
+    struct GemmW {
+        DeviceBuf w, b;
+        uint32_t n_umma = 16, n_tiles = 1, k_pad = 64;
+    };
+    std::vector<GemmW> convs_;  // stem, then 2 per block (bf16: [Np][9*Cin_pad] bf16; fp32: torch layout f32)
+    GemmW vconv_, pconv_, vfc1_, pfc_;
     DeviceBuf vfc2_w_;
     float vfc2_b_ = 0.0f;
+    DeviceBuf fused_w_, fused_b_;  // trunk_fused.cuh weight images + biases
 
     std::vector<std::unique_ptr<Lane>> lanes_;
     std::vector<char> lane_busy_;
     std::mutex lane_mu_;
     std::condition_variable lane_cv_;
 
-    // leaf queue
+    // leaf queue: workers write their record straight into the open pinned block
     std::mutex q_mu_;
-    std::condition_variable q_cv_, done_cv_;
-    std::deque<LeafRequest*> queue_;
+    std::condition_variable q_cv_, q_space_cv_, done_cv_;
+    uint8_t* open_block_ = nullptr;  // pinned, same layout as Lane::h_in
+    std::vector<LeafRequest*> open_reqs_;
+    uint32_t open_total_ = 0;
     std::vector<std::thread> evaluators_;
     bool stopping_ = false;
 
     // error word (mapped pinned) written by kernels before a trap
     uint32_t* h_err_ = nullptr;
     uint32_t* d_err_ = nullptr;
+
+    // L2 flush scratch for time_stage
+    DeviceBuf flush_;
 
     // metrics
     mutable std::mutex m_mu_;

@@ -47,7 +47,9 @@ __device__ __forceinline__ uint32_t legal_word(const uint8_t* rec, const RecLayo
 
 // ---------------------------------------------------------------------------------------------- encode
 // Dense f32 NCHW, exactly planes_to_tensor: one thread per output element, rows >= n zero-filled.
-__global__ void encode_nchw_f32_kernel(const uint8_t* __restrict__ recs, RecLayout L, int n, int batch, float* __restrict__ out) {
+__global__ void encode_nchw_f32_kernel(const uint8_t* __restrict__ recs, RecLayout L, const uint32_t* __restrict__ n_ptr, int batch,
+                                       float* __restrict__ out) {
+    const int n = static_cast<int>(*n_ptr);
     const int s2 = L.s * L.s;
     const long long total = static_cast<long long>(batch) * L.planes * s2;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -63,8 +65,9 @@ __global__ void encode_nchw_f32_kernel(const uint8_t* __restrict__ recs, RecLayo
 
 // NHWC bf16 with the channel dimension padded to 64 (one 128-byte row per cell = one TMA / UMMA swizzle row).
 // One thread writes 8 channels (16 B); consecutive threads write consecutive 16-byte chunks -> fully coalesced.
-__global__ void encode_nhwc_bf16_kernel(const uint8_t* __restrict__ recs, RecLayout L, int n, int rows_total,
-                                        __nv_bfloat16* __restrict__ out) {
+__global__ void encode_nhwc_bf16_kernel(const uint8_t* __restrict__ recs, RecLayout L, const uint32_t* __restrict__ n_ptr,
+                                        int rows_total, __nv_bfloat16* __restrict__ out) {
+    const int n = static_cast<int>(*n_ptr);
     const int s2 = L.s * L.s;
     const long long total = static_cast<long long>(rows_total) * 8;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;

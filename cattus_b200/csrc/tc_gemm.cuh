@@ -9,13 +9,13 @@
 //                   (dx, dy) in {-1,0,1}^2 -- TMA zero-fills the out-of-bounds halo, which is exactly `padding="same"`
 //                   (net_utils.py:13,29,32).  A tile always holds whole boards, so no tile straddles two positions.
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one lane), warps 2..5 = epilogue
-// (TMEM -> registers -> +bias (+residual) -> ReLU -> bf16/f32 -> global).  4-stage smem ring, full/empty mbarriers.
+// (TMEM -> registers -> +bias (+residual) -> ReLU -> bf16/f32 -> global).  3-stage smem ring (two CTAs per SM), full/empty mbarriers.
 #pragma once
 #include "ptx.cuh"
 
 namespace cb2 {
 
-constexpr int kTcStages = 4;
+constexpr int kTcStages = 3;
 constexpr int kTcTileBytes = 128 * 128;  // 128 rows x 128 B
 constexpr int kTcThreads = 192;
 constexpr int kTcTmemCols = 128;
@@ -44,7 +44,7 @@ struct alignas(64) TcGemmParams {
     int pad_;
 };
 
-__global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
+__global__ void __launch_bounds__(kTcThreads, 2) tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint8_t* smem_a = smem;
