@@ -167,6 +167,10 @@ Engine::Engine(const cattus_b200_desc& desc, const void* blob_bytes, size_t blob
     std::memset(h_err_, 0, 64);
     CB2_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_err_), h_err_, 0));
     CB2_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+    // whole-trunk kernel: 8x8 boards, 128 filters (flags bit 0 forces the per-layer path, used by the parity tests)
+    fused_trunk_ = precision_ == CATTUS_B200_PRECISION_BF16 && d_.s == 8 && d_.f == 128 && d_.c_in <= 32 && d_.wpp() == 1 &&
+                   (desc.flags & 1u) == 0 && (sm_count_ >= 2);
+    if (fused_trunk_) CB2_CUDA(cudaFuncSetAttribute(trunk_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFtSmemBytes));
 
     upload_weights(blob);
 
@@ -309,6 +313,32 @@ void Engine::upload_weights(const Blob& blob) {
     convs_.resize(1 + blob.block_conv.size());
     conv3(convs_[0], blob.stem, cin_pad_);
     for (size_t i = 0; i < blob.block_conv.size(); ++i) conv3(convs_[1 + i], blob.block_conv[i], ca_);
+    if (fused_trunk_) {
+        // trunk_fused.cuh weight image: for each layer, each 16-channel k-chunk, each CTA rank (= half of the output
+        // channels): [tap 9][k-half 2][oc 64][ic 8] bf16 = one 18432-byte TMA stage.  Stem input channels padded to 32.
+        const uint32_t layers = 1 + static_cast<uint32_t>(blob.block_conv.size());
+        size_t stages = 2 + static_cast<size_t>(layers - 1) * 8;
+        std::vector<float> img(stages * 2 * (kFtWStage / 2), 0.0f), bias(static_cast<size_t>(layers) * 128, 0.0f);
+        for (uint32_t l = 0; l < layers; ++l) {
+            const Blob::Conv& c = l == 0 ? blob.stem : blob.block_conv[l - 1];
+            const uint32_t nkc = l == 0 ? 2 : 8;
+            const size_t base = l == 0 ? 0 : 2 + static_cast<size_t>(l - 1) * 8;
+            for (uint32_t o = 0; o < 128; ++o) bias[l * 128 + o] = D[c.b + o];
+            for (uint32_t kc = 0; kc < nkc; ++kc)
+                for (uint32_t rk = 0; rk < 2; ++rk) {
+                    float* blk = img.data() + ((base + kc) * 2 + rk) * (kFtWStage / 2);
+                    for (uint32_t tap = 0; tap < 9; ++tap)
+                        for (uint32_t kh = 0; kh < 2; ++kh)
+                            for (uint32_t n = 0; n < 64; ++n)
+                                for (uint32_t e = 0; e < 8; ++e) {
+                                    const uint32_t ic = kc * 16 + kh * 8 + e, oc = rk * 64 + n;
+                                    if (ic < c.ci) blk[((tap * 2 + kh) * 64 + n) * 8 + e] = D[c.w + (static_cast<size_t>(oc) * c.ci + ic) * 9 + tap];
+                                }
+                }
+        }
+        upload(fused_w_, to_bf16(img));
+        upload(fused_b_, bias);
+    }
     conv1(vconv_, blob.vconv, vhp_);
     conv1(pconv_, blob.pconv, php_);
     fc(vfc1_, blob.vfc1_w, blob.vfc1_b, d_.hidden, d_.vh, vhp_);
@@ -522,7 +552,8 @@ void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
     const RecLayout L = rec_;
     const int sm = sm_count_;
     __nv_bfloat16* x = lane.d_x.as<__nv_bfloat16>();
-    {
+    const bool fused = fused_trunk_ && !dense_input;
+    if (!fused) {
         Op op;
         op.stage = 0;
         const int blocks = grid_for(static_cast<long long>(rows_total) * (cin_pad_ / 8), 256, sm);
@@ -591,13 +622,45 @@ void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
         ops.push_back(make_tc_op(stage, name, p, ceil_div(static_cast<uint32_t>(rows), 128), g.n_tiles));
     };
     __nv_bfloat16* act[3] = {lane.d_act[0].as<__nv_bfloat16>(), lane.d_act[1].as<__nv_bfloat16>(), lane.d_act[2].as<__nv_bfloat16>()};
-    conv3("stem", x, cin_pad_, convs_[0], nullptr, act[0]);
     int cur = 0;
-    for (uint32_t i = 0; i < d_.r; ++i) {
-        const int h = (cur + 1) % 3, o = (cur + 2) % 3;
-        conv3("block_conv1", act[cur], ca_, convs_[1 + 2 * i], nullptr, act[h]);
-        conv3("block_conv2", act[h], ca_, convs_[2 + 2 * i], act[cur], act[o]);
-        cur = o;
+    if (fused) {
+        // encode + stem + all residual blocks in one persistent cluster launch (trunk_fused.cuh)
+        TrunkFusedParams fp;
+        std::memset(&fp, 0, sizeof(fp));
+        const uint64_t w_rows = fused_w_.bytes / 256;
+        {
+            cuuint64_t gdim[2] = {256, w_rows};
+            cuuint64_t gstr[1] = {256};
+            cuuint32_t box[2] = {256, static_cast<cuuint32_t>(kFtWRowsPerStage)};
+            cuuint32_t estr[2] = {1, 1};
+            CUresult r = reinterpret_cast<EncodeTiledFn>(encode_tiled_)(&fp.tma_w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, fused_w_.p, gdim, gstr, box, estr,
+                                                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) throw Error(CATTUS_B200_ECUDA, "cuTensorMapEncodeTiled(weights) failed with " + std::to_string(static_cast<int>(r)));
+        }
+        fp.recs = recs;
+        fp.n_ptr = n_ptr;
+        fp.bias = fused_b_.as<float>();
+        fp.out = act[0];
+        fp.err = d_err_;
+        fp.rec_bytes = rec_.rec_bytes;
+        fp.planes = static_cast<int>(d_.c_in);
+        fp.layers = 1 + 2 * static_cast<int>(d_.r);
+        fp.num_rounds = static_cast<int>(ceil_div(bucket, 8));
+        const int pairs = std::min(sm / 2, fp.num_rounds);
+        Op op;
+        op.stage = 1;
+        op.name = "trunk_fused";
+        op.launch = [fp, pairs](cudaStream_t st) { trunk_fused_kernel<<<2 * pairs, kFtThreads, kFtSmemBytes, st>>>(fp); };
+        ops.push_back(op);
+    } else {
+        conv3("stem", x, cin_pad_, convs_[0], nullptr, act[0]);
+        for (uint32_t i = 0; i < d_.r; ++i) {
+            const int h = (cur + 1) % 3, o = (cur + 2) % 3;
+            conv3("block_conv1", act[cur], ca_, convs_[1 + 2 * i], nullptr, act[h]);
+            conv3("block_conv2", act[h], ca_, convs_[2 + 2 * i], act[cur], act[o]);
+            cur = o;
+        }
     }
     gemm(2, "value_conv", act[cur], ca_, rows_total, ca_ * 2ull, vconv_, lane.d_hv.p, vhp_, false, true);
     gemm(2, "policy_conv", act[cur], ca_, rows_total, ca_ * 2ull, pconv_, lane.d_hp.p, php_, false, true);

@@ -26,6 +26,7 @@
 #include "../../include/cattus_b200.h"
 #include "kernels.cuh"
 #include "tc_gemm.cuh"
+#include "trunk_fused.cuh"
 
 namespace cb2 {
 

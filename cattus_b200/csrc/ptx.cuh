@@ -130,6 +130,80 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// ---------------------------------------------------------------- clusters / cta_group::2 (CTA pairs)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local_addr` (a shared::cta address) in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait with cluster-scope acquire (the arrivals come from the peer CTA's threads as well).
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, uint32_t* err, uint32_t code) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if (++spins > (1u << 24)) {
+            if (err) atomicExch(err, code);
+            __threadfence_system();
+            __trap();
+        }
+    }
+}
+// TMA tile load issued by either CTA of a pair; the transaction bytes are credited to `bar_addr`, which the caller
+// has already mapped to the leader CTA (peer bit cleared), so one barrier collects both CTAs' loads.
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint32_t leader_bar_addr, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {  // one warp in EACH CTA of the pair
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem, 256 rows over the CTA pair] (+)= A * B: each CTA supplies its 128 rows of A and its half of B's N rows.
+__device__ __forceinline__ void umma_bf16_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// commit of the pair's MMAs, arriving on the barrier at the same offset in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_pair_multicast(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"(cta_mask)
+                 : "memory");
+}
+
 // ---------------------------------------------------------------- descriptors
 // K-major operand tile in the canonical 128-byte-swizzle layout: rows of 128 B (64 bf16), 8-row groups `sbo_bytes`
 // apart (1024 for a dense tile), 16-byte chunks XOR-swizzled by (row % 8) -- what TMA SWIZZLE_128B writes.
@@ -145,6 +219,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t
     d |= static_cast<uint64_t>(2) << 61;
     return d;
 }
+// K-major operand WITHOUT swizzle: 8 x 16-byte core matrices (8 rows x 8 bf16, 128 contiguous bytes); `lbo_bytes` =
+// distance between the two core matrices of one K=16 step, `sbo_bytes` = distance between consecutive 8-row groups.
+// Neither has to be a multiple of 128 and the start only needs 16-byte alignment (probed: tools/umma_probe.cu).
+__device__ __forceinline__ uint64_t umma_desc_none_hi(uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    return d;
+}
+__device__ __forceinline__ uint64_t umma_desc_none(uint64_t hi, uint32_t smem_addr) { return hi | static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4); }
 // Instruction descriptor for kind::f16: D fp32 ([4,6)=1), A = B = bf16 ([7,10)=[10,13)=1), both K-major,
 // N>>3 at [17,23), M>>4 at [24,29).
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t m, uint32_t n) {

@@ -29,7 +29,7 @@ def _ptr(a: np.ndarray, typ):
 
 class CudaNetwork:
     def __init__(self, model, game: str, *, device: int = 0, batch_size: int = 64, n_streams: int = 2,
-                 precision: str = "bf16", cache: Optional[ValueFuncCache] = None):
+                 precision: str = "bf16", cache: Optional[ValueFuncCache] = None, fused_trunk: bool = True):
         """model: path to a .cb2 blob, or the blob bytes (cattus_b200.export.export_blob)."""
         self._lib = _lib.load()
         self._h = C.c_void_p()
@@ -41,6 +41,7 @@ class CudaNetwork:
         desc.device = device
         desc.max_batch = batch_size
         desc.n_streams = n_streams
+        desc.flags = 0 if fused_trunk else 1  # bit 0: force the per-layer kernels (parity tests compare both paths)
         desc.precision = {"bf16": _lib.PRECISION_BF16, "fp32-check": _lib.PRECISION_FP32_CHECK}[precision]
         if isinstance(model, (bytes, bytearray, memoryview)):
             buf = bytes(model)
@@ -59,6 +60,7 @@ class CudaNetwork:
         self.bitmap_bytes = info.legal_bitmap_bytes
         self.max_batch = info.max_batch
         self.needs_bitmap = game == "chess"
+        self.fused_trunk = bool(info.reserved & 1)
 
     # ------------------------------------------------------------------ lifetime
     def close(self):

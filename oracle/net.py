@@ -70,6 +70,9 @@ CONFIGS: Dict[str, NetConfig] = {
     "chess_1x1": NetConfig(8, 18, 1880, 1, 1, 1, 1, "chess"),
     "hex5_2x2": NetConfig(5, 3, 25, 2, 2, 4, 4, "hex"),
     "chess_2x128": NetConfig(8, 18, 1880, 128, 2, 32, 32, "chess"),
+    # depth ladder for the fused-trunk parity tests (stem only, one block)
+    "chess_0x128": NetConfig(8, 18, 1880, 128, 0, 32, 32, "chess"),
+    "chess_1x128": NetConfig(8, 18, 1880, 128, 1, 32, 32, "chess"),
 }
 
 

@@ -178,6 +178,27 @@ def test_non_finite_and_degenerate_policy_rows():
     assert probs[0] == 1.0 and abs(probs[1:].sum() - 1.0) < 1e-5 and np.isfinite(values).all()
 
 
+# ----------------------------------------------------------------------------------------------- fused trunk
+@pytest.mark.parametrize("name,n,batch", [("chess_0x128", 37, 64), ("chess_1x128", 37, 64), ("chess_2x128", 150, 64), ("chess10x128", 700, 512)])
+def test_fused_trunk_matches_per_layer_path_and_oracle(name, n, batch):
+    """The whole-trunk kernel (trunk_fused.cuh: encode + stem + residual blocks, activations resident in shared memory,
+    CTA pairs) against the per-layer tcgen05 GEMM path on the same handle parameters, and both against the oracle.
+    Depth ladder (0, 1, 2, 10 blocks) localises a fault to the stem / conv1 / conv2+residual / steady state."""
+    words, bitmaps, legal = synth_inputs(name, n, 313)
+    _, o_values, o_probs = oracle_eval(name, words, legal)
+    with make_network(name, batch_size=batch, fused_trunk=True) as a, make_network(name, batch_size=batch, fused_trunk=False) as b:
+        assert a.fused_trunk and not b.fused_trunk
+        assert a.info.kernels_per_batch < b.info.kernels_per_batch
+        pa, oa, va = a.eval_batch(words, bitmaps)
+        pb, ob, vb = b.eval_batch(words, bitmaps)
+    assert np.array_equal(oa, ob)
+    d_paths = max(float(np.abs(pa - pb).max()), float(np.abs(va - vb).max()))
+    worst = max(float(np.abs(pa[oa[i]:oa[i + 1]] - o_probs[i]).max()) for i in range(n))
+    worst_v = float(np.abs(va - o_values).max())
+    print(f"{name}: fused vs per-layer {d_paths:.3e}; fused vs oracle prob {worst:.3e} value {worst_v:.3e}")
+    assert d_paths <= TOL_BF16 and worst <= TOL_BF16 and worst_v <= TOL_BF16
+
+
 # ----------------------------------------------------------------------------------------------- batching semantics
 def test_per_leaf_eval_is_thread_safe_and_batch_invariant():
     """cattus_b200_eval from many threads (the Batcher replacement, util/batch.rs:49-177) must return exactly what the

@@ -23,10 +23,11 @@ def blob(name: str, seed: int = 0) -> bytes:
     return export_blob(state_dict(name, seed), net.CONFIGS[name].game)
 
 
-def make_network(name: str, precision: str = "bf16", batch_size: int = 64, n_streams: int = 2, cache=None):
+def make_network(name: str, precision: str = "bf16", batch_size: int = 64, n_streams: int = 2, cache=None, fused_trunk: bool = True):
     from cattus_b200 import CudaNetwork
 
-    return CudaNetwork(blob(name), net.CONFIGS[name].game, batch_size=batch_size, n_streams=n_streams, precision=precision, cache=cache)
+    return CudaNetwork(blob(name), net.CONFIGS[name].game, batch_size=batch_size, n_streams=n_streams, precision=precision, cache=cache,
+                       fused_trunk=fused_trunk)
 
 
 def synth_inputs(name: str, n: int, seed: int):
