@@ -466,9 +466,18 @@ void Engine::add_tail_ops(Lane& lane, uint32_t bucket, std::vector<Op>& ops, boo
     {
         Op op;
         op.stage = 3;
+        op.name = "legal_count";
+        uint32_t* offsets = lane.d_offsets.as<uint32_t>();
+        const int blocks = static_cast<int>(ceil_div(bucket * 32, 256));
+        op.launch = [=](cudaStream_t st) { legal_count_kernel<<<blocks, 256, 0, st>>>(recs, L, n_ptr, offsets); };
+        ops.push_back(op);
+    }
+    {
+        Op op;
+        op.stage = 3;
         op.name = "legal_offsets";
         uint32_t* offsets = lane.d_offsets.as<uint32_t>();
-        op.launch = [=](cudaStream_t st) { legal_offsets_kernel<<<1, 1024, 0, st>>>(recs, L, n_ptr, offsets); };
+        op.launch = [=](cudaStream_t st) { legal_offsets_kernel<<<1, 1024, 0, st>>>(n_ptr, offsets); };
         ops.push_back(op);
     }
     {

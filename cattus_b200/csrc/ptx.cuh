@@ -145,8 +145,12 @@ __device__ __forceinline__ uint32_t mapa(uint32_t local_addr, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
     return r;
 }
+// Arrive on a barrier of another CTA of the cluster.  Default semantics (.release.cta), as CUTLASS uses for the
+// pair's consumer->leader signals: the data being published lives in the ARRIVING CTA's own shared memory and is read
+// by that CTA's own tensor core, so no cluster-scope fence is needed -- and `.release.cluster` costs a
+// MEMBAR.ALL.GPU + ERRBAR per arrive (35 % of the epilogue warps' time in profiles/r01b).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
@@ -201,6 +205,24 @@ __device__ __forceinline__ void umma_bf16_ss_pair(uint32_t tmem_d, uint64_t desc
 __device__ __forceinline__ void umma_commit_pair_multicast(uint64_t* bar, uint16_t cta_mask) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
                  "h"(cta_mask)
+                 : "memory");
+}
+
+// Split form of tmem_ld_x16: issue, do independent work, then wait.  The wait lists the registers as in/out operands
+// so that the compiler cannot move a use of them above it.
+__device__ __forceinline__ void tmem_ld_x16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
                  : "memory");
 }
 

@@ -154,7 +154,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1) trunk
 #pragma unroll
                         for (int t = 0; t < 2; ++t) {
                             const int bi = t * 8 + kc;
-                            ptx::mbar_wait_cluster(&act_full[bi], (act_par >> bi) & 1u, p.err, 0x2200 + bi);
+                            ptx::mbar_wait(&act_full[bi], (act_par >> bi) & 1u, p.err, 0x2200 + bi);
                             act_par ^= 1u << bi;
                             ptx::tc_fence_after();
                             const uint32_t a_base = act_addr + (t * 2 + in_buf) * kFtBufBytes + (2 * kc) * kFtLbo + kFtCell0 * 16;
@@ -218,22 +218,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1) trunk
                 const bool last = l == p.layers - 1;
                 const bool has_resid = l >= 2 && par == 0;  // conv2 of a block: + block input (Q), result back into Q
                 uint8_t* outb = par ? bufP : bufQ;          // stem -> Q, conv1 -> P, conv2 -> Q
+                const float4* bias4 = reinterpret_cast<const float4*>(p.bias + l * 128);
+                float4 bn[4];  // bias of the chunk about to be processed, fetched one chunk ahead
+#pragma unroll
+                for (int i = 0; i < 4; ++i) bn[i] = __ldg(bias4 + i);
                 ptx::mbar_wait(&acc_full[t * 2 + par], (acc_par >> par) & 1u, p.err, 0x3100 + t * 2 + par);
                 acc_par ^= 1u << par;
                 ptx::tc_fence_after();
-                const float* bias = p.bias + l * 128;
 #pragma unroll 1
                 for (int kc = 0; kc < 8; ++kc) {
+                    uint32_t raw[16];
+                    ptx::tmem_ld_x16_issue(tmem_row + static_cast<uint32_t>(par * 128 + kc * 16), raw);
+                    float4 bc[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) bc[i] = bn[i];
+                    if (kc < 7) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) bn[i] = __ldg(bias4 + (kc + 1) * 4 + i);
+                    }
+                    ptx::tmem_ld_wait(raw);
                     float v[16];
-                    ptx::tmem_ld_x16(tmem_row + static_cast<uint32_t>(par * 128 + kc * 16), v);
-                    const float4* b4 = reinterpret_cast<const float4*>(bias + kc * 16);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const float4 b = __ldg(b4 + i);
-                        v[4 * i + 0] += b.x;
-                        v[4 * i + 1] += b.y;
-                        v[4 * i + 2] += b.z;
-                        v[4 * i + 3] += b.w;
+                        v[4 * i + 0] = __uint_as_float(raw[4 * i + 0]) + bc[i].x;
+                        v[4 * i + 1] = __uint_as_float(raw[4 * i + 1]) + bc[i].y;
+                        v[4 * i + 2] = __uint_as_float(raw[4 * i + 2]) + bc[i].z;
+                        v[4 * i + 3] = __uint_as_float(raw[4 * i + 3]) + bc[i].w;
                     }
                     if (has_resid) {
 #pragma unroll
