@@ -135,12 +135,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1) trunk
         __syncwarp();
     } else if (warp == 1) {
         // ================================================================== MMA issuer (leader CTA only)
-        if (rank == 0 && lane == 0) {
+        // The WHOLE warp runs this loop (warp-uniform control flow and addresses, so the compiler keeps descriptors in
+        // uniform registers); only the tcgen05 instructions themselves are issued by one elected lane.  An earlier
+        // version that ran the loop inside `if (lane == 0)` spent ~25 SASS instructions per MMA converting registers
+        // to uniform registers and was issue-bound at half the tensor-pipe rate (profiles/r01c).
+        if (rank == 0) {
             const uint32_t idesc = ptx::umma_idesc_bf16(256, 128);
-            const uint64_t a_hi = ptx::umma_desc_none_hi(kFtLbo, kFtSbo);
-            const uint64_t b_hi = ptx::umma_desc_none_hi(64 * 16, 128);
+            const uint64_t a_hi64 = ptx::umma_desc_none_hi(kFtLbo, kFtSbo);
+            const uint64_t b_hi64 = ptx::umma_desc_none_hi(64 * 16, 128);
+            const uint32_t a_hi = static_cast<uint32_t>(a_hi64 >> 32), a_lo_fixed = static_cast<uint32_t>(a_hi64);
+            const uint32_t b_hi = static_cast<uint32_t>(b_hi64 >> 32), b_lo_fixed = static_cast<uint32_t>(b_hi64);
             const uint32_t act_addr = ptx::smem_u32(act);
             const uint32_t w_addr = ptx::smem_u32(wring);
+            const bool leader_lane = ptx::elect_one();
             uint32_t act_par = 0;
             uint32_t it = 0;
             for (int rd = pair; rd < p.num_rounds; rd += num_pairs) {
@@ -150,24 +157,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1) trunk
                     for (int kc = 0; kc < nkc; ++kc, ++it) {
                         const uint32_t slot = it % 3, ph = (it / 3) & 1;
                         ptx::mbar_wait(&w_full[slot], ph, p.err, 0x2100 + slot);
-                        const uint32_t b_base = w_addr + slot * kFtWStage;
+                        const uint32_t b_lo0 = b_lo_fixed | ((w_addr + slot * kFtWStage) >> 4);
 #pragma unroll
                         for (int t = 0; t < 2; ++t) {
                             const int bi = t * 8 + kc;
                             ptx::mbar_wait(&act_full[bi], (act_par >> bi) & 1u, p.err, 0x2200 + bi);
                             act_par ^= 1u << bi;
                             ptx::tc_fence_after();
-                            const uint32_t a_base = act_addr + (t * 2 + in_buf) * kFtBufBytes + (2 * kc) * kFtLbo + kFtCell0 * 16;
+                            const uint32_t a_lo0 = a_lo_fixed | ((act_addr + (t * 2 + in_buf) * kFtBufBytes + (2 * kc) * kFtLbo + kFtCell0 * 16) >> 4);
                             const uint32_t d = tmem_base + static_cast<uint32_t>((t * 2 + (l & 1)) * 128);
+                            if (leader_lane) {
 #pragma unroll
-                            for (int tap = 0; tap < 9; ++tap) {
-                                const int shift = (18 * (tap / 3 - 1) + (tap % 3 - 1)) * 16;
-                                ptx::umma_bf16_ss_pair(d, ptx::umma_desc_none(a_hi, a_base + shift), ptx::umma_desc_none(b_hi, b_base + tap * kFtTapBytes),
-                                                       idesc, (kc | tap) != 0);
+                                for (int tap = 0; tap < 9; ++tap) {
+                                    const int shift16 = 18 * (tap / 3 - 1) + (tap % 3 - 1);  // in 16-byte units
+                                    ptx::umma_bf16_ss_pair_lohi(d, a_lo0 + shift16, a_hi, b_lo0 + tap * (kFtTapBytes / 16), b_hi, idesc,
+                                                                (kc | tap) != 0);
+                                }
+                                if (kc == nkc - 1) ptx::umma_commit_pair_multicast(&acc_full[t * 2 + (l & 1)], 3);
                             }
-                            if (kc == nkc - 1) ptx::umma_commit_pair_multicast(&acc_full[t * 2 + (l & 1)], 3);
                         }
-                        ptx::umma_commit_pair_multicast(&w_empty[slot], 3);
+                        if (leader_lane) ptx::umma_commit_pair_multicast(&w_empty[slot], 3);
+                        __syncwarp();
                     }
                 }
             }
