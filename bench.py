@@ -224,25 +224,15 @@ def main():
     from cattus_b200.export import export_blob
     from oracle import net  # only for NetConfig / the seeded weight + position generators and the cpu_baseline leg
 
-    dist = None
-    if world > 1:
-        import torch.distributed as dist_mod
+    from cattus_b200 import replicas
 
-        dist = dist_mod
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    rep = replicas.init_from_env("nccl")
 
     def barrier():
-        if dist is not None:
-            dist.barrier()
+        rep.barrier()
         torch.cuda.synchronize(local_rank)
 
-    def max_over_ranks(x: float) -> float:
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    max_over_ranks = rep.max_over_ranks
 
     cfg_name, batch, per_step = WORKLOADS[args.workload]
     if args.batch:
@@ -252,7 +242,7 @@ def main():
     sd = net.make_state_dict(cfg, 0)
     nw = CudaNetwork(export_blob(sd, cfg.game), cfg.game, device=local_rank, batch_size=batch, n_streams=args.streams, precision="bf16")
     positions_per_step = batch * per_step
-    words, bitmaps = make_inputs(cfg, positions_per_step, seed=0xCA7705 + rank)
+    words, bitmaps = make_inputs(cfg, positions_per_step, seed=replicas.rank_seed(0xCA7705, rank))
 
     # ---------------- device-resident throughput (value) and the trunk roofline
     nw.resident_upload(words[:batch], None if bitmaps is None else bitmaps[:batch])
@@ -330,9 +320,7 @@ def main():
             "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    rep.close()
 
 
 if __name__ == "__main__":
