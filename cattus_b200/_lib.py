@@ -40,7 +40,28 @@ class Info(C.Structure):
         "kernels_per_batch", "reserved")]
 
 
-# every symbol include/cattus_b200.h declares: name -> (restype, argtypes)
+class SelfPlayCfg(C.Structure):
+    """cattus_b200_selfplay_cfg (include/cattus_b200_selfplay.h)."""
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("game", C.c_uint32), ("board_size", C.c_uint32), ("sim_num", C.c_uint32),
+        ("explore_factor", C.c_float), ("temperature_moves", C.POINTER(C.c_uint32)), ("temperature_values", C.POINTER(C.c_float)),
+        ("n_temperatures", C.c_uint32), ("prior_noise_alpha", C.c_float), ("prior_noise_epsilon", C.c_float),
+        ("cache_size", C.c_uint32), ("threads", C.c_uint32), ("games_per_thread", C.c_uint32), ("leaf_queue", C.c_uint32),
+        ("games_num", C.c_uint32), ("first_game", C.c_uint32), ("game_stride", C.c_uint32), ("seed", C.c_uint64),
+        ("out_dir1", C.c_char_p), ("out_dir2", C.c_char_p), ("keep_records", C.c_uint32), ("reserved", C.c_uint32),
+    ]
+
+
+class SelfPlaySummary(C.Structure):
+    _fields_ = [
+        ("player1_wins", C.c_uint32), ("player2_wins", C.c_uint32), ("draws", C.c_uint32), ("games", C.c_uint32),
+        ("simulations", C.c_uint64), ("searches", C.c_uint64), ("evaluations", C.c_uint64), ("cache_hits", C.c_uint64),
+        ("cache_misses", C.c_uint64), ("batches", C.c_uint64), ("terminal_leaves", C.c_uint64), ("seconds", C.c_double),
+        ("search_duration", C.c_double), ("eval_wait_seconds", C.c_double),
+    ]
+
+
+# every symbol include/*.h declares: name -> (restype, argtypes)
 _H = C.c_void_p
 _u64p, _u8p, _f32p, _u32p = C.POINTER(C.c_uint64), C.POINTER(C.c_uint8), C.POINTER(C.c_float), C.POINTER(C.c_uint32)
 SYMBOLS = {
@@ -59,7 +80,19 @@ SYMBOLS = {
     "cattus_b200_get_metrics": (C.c_int, [_H, C.POINTER(Metrics)]),
     "cattus_b200_last_error": (C.c_char_p, []),
     "cattus_b200_abi_version": (C.c_uint32, []),
+    # include/cattus_b200_selfplay.h
+    "cattus_b200_selfplay_run": (C.c_int, [_H, _H, C.POINTER(SelfPlayCfg), C.POINTER(_H)]),
+    "cattus_b200_selfplay_run_with": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(SelfPlayCfg), C.POINTER(_H)]),
+    "cattus_b200_selfplay_summary_get": (C.c_int, [_H, C.POINTER(SelfPlaySummary)]),
+    "cattus_b200_selfplay_game_count": (C.c_int, [_H, _u32p]),
+    "cattus_b200_selfplay_game_info": (C.c_int, [_H, C.c_uint32, _u32p, _u32p, _u32p]),
+    "cattus_b200_selfplay_game_moves": (C.c_int, [_H, C.c_uint32, _u8p, C.c_uint32]),
+    "cattus_b200_selfplay_entry": (C.c_int, [_H, C.c_uint32, C.c_uint32, _u8p, C.c_size_t, C.POINTER(C.c_size_t), _u32p]),
+    "cattus_b200_selfplay_free": (None, [_H]),
+    "cattus_b200_selfplay_last_error": (C.c_char_p, []),
 }
+
+EVAL_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, _u64p, _u8p, C.c_uint32, _f32p, C.c_size_t, _u32p, _f32p)
 
 _lib = None
 

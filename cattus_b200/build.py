@@ -18,11 +18,14 @@ LIB = PKG / "libcattus_b200.so"
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread",
+    # host arithmetic of the MCTS driver must stay un-fused so its f32 selection scores match the reference's
+    "-Xcompiler", "-ffp-contract=off",
 ]
 
 
 def sources():
-    return sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.hpp")) + [ROOT / "include" / "cattus_b200.h"]
+    return (sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.hpp")) + sorted(CSRC.glob("*.cpp"))
+            + sorted((ROOT / "include").glob("*.h")))
 
 
 def is_stale() -> bool:
@@ -42,7 +45,7 @@ def nvcc_path() -> str:
 def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not is_stale():
         return LIB
-    cmd = [nvcc_path(), *NVCC_FLAGS, "-o", str(LIB), str(CSRC / "engine.cu")]
+    cmd = [nvcc_path(), *NVCC_FLAGS, "-o", str(LIB), str(CSRC / "engine.cu"), str(CSRC / "selfplay.cpp")]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

@@ -1,0 +1,1135 @@
+// Self-play driver: the caller side of the evaluation path (include/cattus_b200_selfplay.h).
+//
+// Restates, in host C++, the reference's MctsPlayer (engine/src/mcts/mod.rs:105-454), the Hex / TicTacToe rules
+// (engine/src/hex/core.rs:112-335, engine/src/ttt/core.rs:101-246), NNetwork::evaluate's flip + ValueFuncCache
+// (engine/src/net/mod.rs:74-87,158-182; engine/src/mcts/cache.rs:31-75), the self-play game loop
+// (training/self-play/src/self_play.rs:94-276) and the .traindata writers (self_play.rs:33-61, serialize/hex.rs:16-28,
+// serialize/ttt.rs:17-22).  The oracle it is tested against is oracle/mcts.py.
+//
+// B200-first arrangement: a worker thread advances `games_per_thread` games as state machines.  Each game runs its
+// simulations strictly in the reference's order (select -> evaluate -> expand -> backpropagate, one leaf in flight per
+// tree), but when a game needs the network it parks and the worker moves on to its next game; once every game of the
+// worker is parked, all their leaves go to the evaluator as one batch.  Nothing is shared between workers except the
+// evaluator and its position cache, so there is no cross-thread rendezvous on the leaf path at all.
+//
+// Third-party behaviour reproduced on purpose (see oracle/mcts.py for the derivation):
+//   * petgraph `edges()` iterates newest-edge-first and `Iterator::max_by` keeps the last maximum, so ties in `select`
+//     and in the temperature-0 move choice go to the child that was inserted FIRST;
+//   * `remove_all_but_subtree` re-inserts edges in iteration order, which reverses every kept node's child order at
+//     each tree reuse.
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include <sys/stat.h>
+#include <sys/types.h>
+
+#include "../../include/cattus_b200_selfplay.h"
+
+namespace sp {
+
+using u128 = unsigned __int128;
+using Clock = std::chrono::steady_clock;
+
+struct SpError {
+    int code;
+    std::string msg;
+};
+
+static inline int ctz128(u128 x) {
+    const uint64_t lo = static_cast<uint64_t>(x);
+    return lo ? __builtin_ctzll(lo) : 64 + __builtin_ctzll(static_cast<uint64_t>(x >> 64));
+}
+static inline int popcount128(u128 x) { return __builtin_popcountll(static_cast<uint64_t>(x)) + __builtin_popcountll(static_cast<uint64_t>(x >> 64)); }
+static inline u128 bit128(int i) { return static_cast<u128>(1) << i; }
+
+// ------------------------------------------------------------------------------------------------ random stream
+// The reference uses the unseeded thread-local rand::rng(); every game here owns this stream instead (same
+// definition in oracle/mcts.py so whole games can be compared).
+struct SplitMix64 {
+    uint64_t state;
+    explicit SplitMix64(uint64_t seed = 0) : state(seed) {}
+    uint64_t next_u64() {
+        state += 0x9E3779B97F4A7C15ull;
+        uint64_t z = state;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        return z ^ (z >> 31);
+    }
+    double next_f64() { return static_cast<double>(next_u64() >> 11) * (1.0 / 9007199254740992.0); }
+    double next_open_f64() { return (static_cast<double>(next_u64() >> 12) + 0.5) * (1.0 / 4503599627370496.0); }
+    double normal() {
+        const double u1 = next_open_f64();
+        const double u2 = next_f64();
+        return std::sqrt(-2.0 * std::log(u1)) * std::cos(2.0 * M_PI * u2);
+    }
+    double gamma(double alpha) {  // Marsaglia-Tsang; alpha < 1 boosted with U^(1/alpha)
+        if (alpha < 1.0) {
+            const double u = next_open_f64();
+            return gamma(alpha + 1.0) * std::pow(u, 1.0 / alpha);
+        }
+        const double d = alpha - 1.0 / 3.0;
+        const double c = 1.0 / std::sqrt(9.0 * d);
+        for (;;) {
+            const double x = normal();
+            double v = 1.0 + c * x;
+            if (v <= 0.0) continue;
+            v = v * v * v;
+            const double u = next_open_f64();
+            if (std::log(u) < 0.5 * x * x + d - d * v + d * std::log(v)) return d * v;
+        }
+    }
+};
+
+static inline uint64_t game_seed(uint64_t base, uint32_t game_idx) { return base ^ (0xD1B54A32D192ED03ull * (static_cast<uint64_t>(game_idx) + 1)); }
+
+// ------------------------------------------------------------------------------------------------ rules
+// status(): 0 ongoing, 1 Player1 won, 2 Player2 won, 3 draw
+struct PosKey {
+    u128 a, b;
+    bool operator==(const PosKey& o) const { return a == o.a && b == o.b; }
+};
+struct PosKeyHash {
+    size_t operator()(const PosKey& k) const {
+        auto mix = [](uint64_t x) {
+            x ^= x >> 33;
+            x *= 0xff51afd7ed558ccdull;
+            x ^= x >> 33;
+            return x;
+        };
+        uint64_t h = mix(static_cast<uint64_t>(k.a)) ^ (mix(static_cast<uint64_t>(k.a >> 64) + 0x9E3779B97F4A7C15ull) * 3);
+        h ^= mix(static_cast<uint64_t>(k.b) + 0x632BE59BD9B4E019ull) * 5 ^ (mix(static_cast<uint64_t>(k.b >> 64) + 0x1234567ull) * 7);
+        return static_cast<size_t>(mix(h));
+    }
+};
+
+struct HexPos {
+    u128 red = 0, blue = 0, left_red_reach = 0, top_blue_reach = 0;
+    uint8_t turn = 1, empty = 0, winner = 0;
+};
+
+// engine/src/hex/core.rs
+struct HexRules {
+    using Pos = HexPos;
+    int s = 0, cells = 0;
+    u128 full = 0, col0 = 0, col_last = 0, row0 = 0, row_last = 0;
+    u128 nb[121];
+    uint8_t tr[121];
+
+    explicit HexRules(int size) : s(size), cells(size * size) {
+        full = cells == 128 ? ~static_cast<u128>(0) : (bit128(cells) - 1);
+        const int dirs[6][2] = {{0, 1}, {-1, 0}, {-1, -1}, {0, -1}, {1, 0}, {1, 1}};  // core.rs:204
+        for (int r = 0; r < s; ++r)
+            for (int c = 0; c < s; ++c) {
+                const int i = r * s + c;
+                tr[i] = static_cast<uint8_t>(c * s + r);
+                nb[i] = 0;
+                for (auto& d : dirs) {
+                    const int nr = r + d[0], nc = c + d[1];
+                    if (nr >= 0 && nr < s && nc >= 0 && nc < s) nb[i] |= bit128(nr * s + nc);
+                }
+                if (c == 0) col0 |= bit128(i);
+                if (c == s - 1) col_last |= bit128(i);
+                if (r == 0) row0 |= bit128(i);
+                if (r == s - 1) row_last |= bit128(i);
+            }
+    }
+    int moves_num() const { return cells; }
+    int words_per_plane() const { return 2; }  // u128 -> [lo, hi] (serialize/hex.rs:16-28); the C ABI uses ceil(S*S/64)
+    Pos initial() const {
+        Pos p;
+        p.empty = static_cast<uint8_t>(cells);
+        return p;
+    }
+    int status(const Pos& p) const {  // core.rs:314-322
+        if (p.winner) return p.winner;
+        if (p.empty == 0) return 3;
+        return 0;
+    }
+    u128 legal_mask(const Pos& p) const { return full & ~(p.red | p.blue); }  // core.rs:297-305 (ascending index)
+    // core.rs:215-264: flood the player's reach map from the new stone; the first end-edge cell reached wins.
+    void update_reach(Pos& p, int idx, int player) const {
+        const u128 board = player == 1 ? p.red : p.blue;
+        u128& reach = player == 1 ? p.left_red_reach : p.top_blue_reach;
+        const u128 begin = player == 1 ? col0 : row0;
+        const u128 end = player == 1 ? col_last : row_last;
+        if (!((begin & bit128(idx)) || (nb[idx] & reach))) return;
+        u128 layer = bit128(idx);
+        reach |= layer;
+        while (layer) {
+            const int i = ctz128(layer);
+            layer &= ~bit128(i);
+            if (end & bit128(i)) {
+                p.winner = static_cast<uint8_t>(player);
+            } else {
+                const u128 add = nb[i] & board & ~reach;
+                reach |= add;
+                layer |= add;
+            }
+        }
+    }
+    Pos moved(const Pos& p, int m) const {  // core.rs:272-285
+        Pos r = p;
+        if (r.turn == 1)
+            r.red |= bit128(m);
+        else
+            r.blue |= bit128(m);
+        update_reach(r, m, r.turn);
+        r.empty -= 1;
+        r.turn = static_cast<uint8_t>(3 - r.turn);
+        return r;
+    }
+    u128 transpose(u128 bb) const {  // HexBitboard::flip, core.rs:61-71
+        u128 f = 0;
+        while (bb) {
+            const int i = ctz128(bb);
+            bb &= bb - 1;
+            f |= bit128(tr[i]);
+        }
+        return f;
+    }
+    Pos flipped(const Pos& p) const {  // core.rs:324-334
+        Pos r;
+        r.red = transpose(p.blue);
+        r.blue = transpose(p.red);
+        r.turn = static_cast<uint8_t>(3 - p.turn);
+        r.left_red_reach = transpose(p.top_blue_reach);
+        r.top_blue_reach = transpose(p.left_red_reach);
+        r.empty = p.empty;
+        r.winner = p.winner ? static_cast<uint8_t>(3 - p.winner) : 0;
+        return r;
+    }
+    int flip_move(int m) const { return tr[m]; }  // core.rs:36-38
+    bool same(const Pos& a, const Pos& b) const { return a.red == b.red && a.blue == b.blue && a.turn == b.turn; }
+    bool child_matches(const Pos& parent, int m, const Pos& target) const {
+        const u128 red = parent.turn == 1 ? (parent.red | bit128(m)) : parent.red;
+        const u128 blue = parent.turn == 1 ? parent.blue : (parent.blue | bit128(m));
+        return red == target.red && blue == target.blue && target.turn == 3 - parent.turn;
+    }
+    PosKey key(const Pos& p) const { return PosKey{p.red, p.blue}; }
+    // position_to_planes (hex/net.rs:14-24): [red, blue, ones]
+    void planes(const Pos& p, u128 out[3]) const {
+        out[0] = p.red;
+        out[1] = p.blue;
+        out[2] = full;
+    }
+};
+
+struct TttPos {
+    uint16_t x = 0, o = 0;
+    uint8_t turn = 1, winner = 0;
+};
+
+// engine/src/ttt/core.rs
+struct TttRules {
+    using Pos = TttPos;
+    int moves_num() const { return 9; }
+    int words_per_plane() const { return 1; }
+    Pos initial() const { return Pos(); }
+    static uint8_t winner_of(uint16_t x, uint16_t o) {  // core.rs:170-193: x before o on every line, in this order
+        static const uint16_t lines[8] = {0b111000000, 0b000111000, 0b000000111, 0b100100100, 0b010010010, 0b001001001, 0b100010001, 0b001010100};
+        for (uint16_t w : lines) {
+            if ((x & w) == w) return 1;
+            if ((o & w) == w) return 2;
+        }
+        return 0;
+    }
+    int status(const Pos& p) const {
+        if (p.winner) return p.winner;
+        if ((p.x | p.o) == 0x1FF) return 3;
+        return 0;
+    }
+    u128 legal_mask(const Pos& p) const { return static_cast<u128>(0x1FFu & ~(p.x | p.o)); }
+    Pos moved(const Pos& p, int m) const {
+        Pos r = p;
+        if (r.turn == 1)
+            r.x |= static_cast<uint16_t>(1u << m);
+        else
+            r.o |= static_cast<uint16_t>(1u << m);
+        r.turn = static_cast<uint8_t>(3 - r.turn);
+        r.winner = winner_of(r.x, r.o);
+        return r;
+    }
+    Pos flipped(const Pos& p) const {
+        Pos r;
+        r.x = p.o;
+        r.o = p.x;
+        r.turn = static_cast<uint8_t>(3 - p.turn);
+        r.winner = p.winner ? static_cast<uint8_t>(3 - p.winner) : 0;
+        return r;
+    }
+    int flip_move(int m) const { return m; }
+    bool same(const Pos& a, const Pos& b) const { return a.x == b.x && a.o == b.o && a.turn == b.turn; }
+    bool child_matches(const Pos& parent, int m, const Pos& target) const {
+        const Pos c = moved(parent, m);
+        return same(c, target);
+    }
+    PosKey key(const Pos& p) const { return PosKey{p.x, p.o}; }
+    void planes(const Pos& p, u128 out[3]) const {
+        out[0] = p.x;
+        out[1] = p.o;
+        out[2] = 0x1FF;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ cache
+// ValueFuncCache (mcts/cache.rs:31-75): position -> (per-move probabilities in legal_moves() order, value), FIFO
+// eviction.  Sharded (one mutex + FIFO per shard) instead of one RwLock; a hit returns exactly what was stored.
+using CacheVal = std::shared_ptr<const std::vector<float>>;  // probs..., value last
+
+class Cache {
+  public:
+    explicit Cache(size_t max_size) : per_shard_((max_size + kShards - 1) / kShards) {}
+    CacheVal find(const PosKey& k) {
+        Shard& s = shard(k);
+        std::lock_guard<std::mutex> g(s.mu);
+        auto it = s.map.find(k);
+        if (it == s.map.end()) return nullptr;
+        return it->second;
+    }
+    // returns the value to use (the already-cached one if another thread got there first) and whether it was inserted
+    CacheVal insert(const PosKey& k, CacheVal v, bool* inserted) {
+        Shard& s = shard(k);
+        std::lock_guard<std::mutex> g(s.mu);
+        auto it = s.map.find(k);
+        if (it != s.map.end()) {
+            *inserted = false;
+            return it->second;
+        }
+        while (s.fifo.size() >= per_shard_) {
+            s.map.erase(s.fifo.front());
+            s.fifo.pop_front();
+        }
+        s.map.emplace(k, v);
+        s.fifo.push_back(k);
+        *inserted = true;
+        return v;
+    }
+
+  private:
+    static constexpr size_t kShards = 64;
+    struct Shard {
+        std::mutex mu;
+        std::unordered_map<PosKey, CacheVal, PosKeyHash> map;
+        std::deque<PosKey> fifo;
+    };
+    Shard& shard(const PosKey& k) { return shards_[PosKeyHash()(k) >> 58]; }
+    Shard shards_[kShards];
+    size_t per_shard_;
+};
+
+// One evaluator = the reference's NNetwork: a network behind a callback plus its own cache.
+struct Evaluator {
+    cattus_b200_eval_fn fn = nullptr;
+    void* ctx = nullptr;
+    cattus_b200_t* leaf_handle = nullptr;  // non-null: single-position requests use the per-leaf pinned queue
+    std::unique_ptr<Cache> cache;
+};
+
+// ------------------------------------------------------------------------------------------------ tree
+struct Edge {
+    float init_score;
+    float score_w;
+    uint32_t simulations_n;
+    int32_t child;  // node index, -1 until first visited (positions of unvisited children are derived on demand)
+    uint8_t m;
+};
+template <class Pos>
+struct Node {
+    Pos pos;
+    int32_t first = -1;  // first edge; children are edges [first, first + count) in insertion order
+    int32_t count = 0;
+};
+template <class Pos>
+struct Tree {
+    std::vector<Node<Pos>> nodes;
+    std::vector<Edge> edges;
+    int32_t root = -1;
+    void clear() {
+        nodes.clear();
+        edges.clear();
+        root = -1;
+    }
+};
+
+struct Params {
+    uint32_t sim_num;
+    float explore_factor;
+    std::vector<std::pair<uint32_t, float>> temperatures;
+    float last_temperature;
+    float noise_alpha, noise_eps;
+    float temperature_at(size_t move_num) const {  // TemperaturePolicy::get_temperature, mod.rs:482-488
+        for (auto& t : temperatures)
+            if (move_num < t.first) return t.second;
+        return last_temperature;
+    }
+};
+
+struct GameRecord {
+    uint32_t game_idx = 0;
+    uint8_t winner = 0;
+    std::vector<uint8_t> moves;
+    std::vector<std::vector<uint8_t>> entries;
+    std::vector<uint8_t> entry_dir;
+};
+
+struct Shared {
+    std::atomic<uint64_t> simulations{0}, searches{0}, evaluations{0}, cache_hits{0}, cache_misses{0}, batches{0}, terminal{0};
+    std::atomic<uint32_t> w1{0}, w2{0}, d{0}, games{0};
+    std::atomic<uint32_t> next_game{0};
+    std::mutex mu;  // records, search_duration, first error
+    std::vector<GameRecord> records;
+    double search_duration = 0.0;
+    double eval_wait = 0.0;
+    int error_code = 0;
+    std::string error;
+    std::atomic<bool> failed{false};
+};
+
+template <class Rules>
+class Worker {
+    using Pos = typename Rules::Pos;
+
+    struct Player {
+        Tree<Pos> tree;
+    };
+    enum Phase { kIdle, kStartMove, kSimulate, kWaitEval };
+    struct Slot {
+        Phase phase = kIdle;
+        uint32_t game_idx = 0;
+        SplitMix64 rng;
+        std::vector<Pos> history;
+        Player players[2];
+        int cur = 0;  // index into players of the side searching now
+        uint32_t sims_left = 0;
+        std::vector<int32_t> path;  // edge indices root -> leaf
+        int32_t leaf = -1;
+        bool leaf_flipped = false;
+        Pos leaf_eval_pos;  // the position as sent to the network (Player1 to move)
+        Clock::time_point search_t0;
+        GameRecord rec;
+        std::vector<std::pair<Pos, std::vector<std::pair<uint8_t, float>>>> pending_entries;
+    };
+    struct Pending {  // one batch under construction for one evaluator
+        std::vector<uint64_t> planes;
+        std::vector<PosKey> keys;
+        std::vector<uint8_t> n_legal;
+        std::vector<std::vector<uint32_t>> waiters;  // slot indices per batch row
+        std::unordered_map<PosKey, uint32_t, PosKeyHash> index;
+        void clear() {
+            planes.clear();
+            keys.clear();
+            n_legal.clear();
+            waiters.clear();
+            index.clear();
+        }
+    };
+
+  public:
+    Worker(const Rules& rules, const cattus_b200_selfplay_cfg& cfg, const Params params[2], Evaluator* evals[2], Shared& sh)
+        : R(rules), cfg_(cfg), sh_(sh) {
+        params_[0] = params[0];
+        params_[1] = params[1];
+        evals_[0] = evals[0];
+        evals_[1] = evals[1];
+        slots_.resize(std::max<uint32_t>(1, cfg.games_per_thread));
+        abi_wpp_ = (R.moves_num() + 63) / 64;
+    }
+
+    void run() {
+        try {
+            for (auto& s : slots_) start_next_game(s);
+            for (;;) {
+                bool any = false;
+                for (uint32_t i = 0; i < slots_.size(); ++i) {
+                    Slot& s = slots_[i];
+                    if (s.phase == kIdle) continue;
+                    any = true;
+                    if (s.phase != kWaitEval) advance(i);
+                }
+                if (sh_.failed.load(std::memory_order_relaxed)) return;
+                bool flushed = false;
+                for (int e = 0; e < 2; ++e)
+                    if (!pending_[e].keys.empty()) {
+                        flush(e);
+                        flushed = true;
+                    }
+                if (!any && !flushed) break;
+            }
+        } catch (const SpError& e) {
+            std::lock_guard<std::mutex> g(sh_.mu);
+            if (!sh_.failed.exchange(true)) {
+                sh_.error_code = e.code;
+                sh_.error = e.msg;
+            }
+        }
+        std::lock_guard<std::mutex> g(sh_.mu);
+        sh_.eval_wait += eval_wait_;
+    }
+
+  private:
+    // ---------------------------------------------------------------- game loop (self_play.rs:179-246)
+    void start_next_game(Slot& s) {
+        const uint32_t stride = std::max<uint32_t>(1, cfg_.game_stride);
+        const uint32_t k = sh_.next_game.fetch_add(1);
+        const uint64_t idx = static_cast<uint64_t>(cfg_.first_game) + static_cast<uint64_t>(k) * stride;
+        if (idx >= cfg_.games_num) {
+            s.phase = kIdle;
+            return;
+        }
+        s.game_idx = static_cast<uint32_t>(idx);
+        s.rng = SplitMix64(game_seed(cfg_.seed, s.game_idx));
+        s.history.clear();
+        s.history.push_back(R.initial());
+        s.players[0].tree.clear();
+        s.players[1].tree.clear();
+        s.rec = GameRecord();
+        s.rec.game_idx = s.game_idx;
+        s.pending_entries.clear();
+        s.phase = kStartMove;
+    }
+
+    void advance(uint32_t si) {
+        Slot& s = slots_[si];
+        for (;;) {
+            if (s.phase == kStartMove) {
+                const Pos& pos = s.history.back();
+                const int st = R.status(pos);
+                if (st != 0) {
+                    finish_game(s, st);
+                    start_next_game(s);
+                    if (s.phase == kIdle) return;
+                    continue;
+                }
+                int who = pos.turn;  // self_play.rs:198-205
+                if (s.game_idx % 2 == 1) who = 3 - who;
+                s.cur = who - 1;
+                begin_search(s);
+                s.phase = kSimulate;
+            }
+            if (s.phase == kSimulate) {
+                while (s.sims_left > 0) {
+                    if (!simulate_once(si)) return;  // parked on the evaluator
+                }
+                end_search(s);
+                s.phase = kStartMove;
+            }
+        }
+    }
+
+    void finish_game(Slot& s, int status) {
+        const uint8_t winner = status == 3 ? 0 : static_cast<uint8_t>(status);
+        s.rec.winner = winner;
+        for (size_t pos_idx = 0; pos_idx < s.pending_entries.size(); ++pos_idx) {
+            auto& pe = s.pending_entries[pos_idx];
+            std::vector<uint8_t> bytes;
+            const int dir = make_entry(s.game_idx, pe.first, pe.second, winner, bytes);
+            if (cfg_.out_dir1 && cfg_.out_dir2) write_entry_file(dir == 1 ? cfg_.out_dir1 : cfg_.out_dir2, s.game_idx, pos_idx, bytes);
+            if (cfg_.keep_records) {
+                s.rec.entries.push_back(std::move(bytes));
+                s.rec.entry_dir.push_back(static_cast<uint8_t>(dir));
+            }
+        }
+        // winner counters: self_play.rs:226-241
+        uint8_t credited = winner;
+        if (credited && s.game_idx % 2 == 1) credited = static_cast<uint8_t>(3 - credited);
+        if (credited == 0)
+            sh_.d.fetch_add(1);
+        else if (credited == 1)
+            sh_.w1.fetch_add(1);
+        else
+            sh_.w2.fetch_add(1);
+        sh_.games.fetch_add(1);
+        if (cfg_.keep_records) {
+            std::lock_guard<std::mutex> g(sh_.mu);
+            sh_.records.push_back(std::move(s.rec));
+        }
+    }
+
+    // write_data_entry + serializers (self_play.rs:248-276, :33-61; serialize/hex.rs:16-28; serialize/ttt.rs:17-22)
+    int make_entry(uint32_t game_idx, const Pos& pos_in, const std::vector<std::pair<uint8_t, float>>& probs_in, uint8_t winner,
+                   std::vector<uint8_t>& bytes) const {
+        const int pair_p1[2] = {1, 2}, pair_p2[2] = {2, 1};
+        const int dir = (pos_in.turn == 1 ? pair_p1 : pair_p2)[game_idx % 2];
+        float w = winner == 0 ? 0.0f : (winner == 1 ? 1.0f : -1.0f);
+        Pos pos = pos_in;
+        const bool flipped = pos.turn != 1;
+        if (flipped) {
+            pos = R.flipped(pos);
+            w = -w;
+        }
+        const int M = R.moves_num();
+        std::vector<float> dense(M, -1.0f);
+        for (auto& mp : probs_in) dense[flipped ? R.flip_move(mp.first) : mp.first] = mp.second;
+        u128 pl[3];
+        R.planes(pos, pl);
+        const int wpp = R.words_per_plane();
+        bytes.resize(3 * wpp * 8 + M * 4 + 1);
+        uint8_t* p = bytes.data();
+        for (int c = 0; c < 3; ++c)
+            for (int k = 0; k < wpp; ++k) {
+                const uint64_t word = static_cast<uint64_t>(pl[c] >> (64 * k));
+                std::memcpy(p, &word, 8);
+                p += 8;
+            }
+        std::memcpy(p, dense.data(), M * 4);
+        p += M * 4;
+        *p = static_cast<uint8_t>(static_cast<int8_t>(static_cast<int>(w)));
+        return dir;
+    }
+
+    void write_entry_file(const char* dir, uint32_t game_idx, size_t pos_idx, const std::vector<uint8_t>& bytes) const {
+        char name[64];
+        std::snprintf(name, sizeof(name), "/%08u_%03zu.traindata", game_idx, pos_idx);  // format!("{game_idx:#08}_{pos_idx:#03}")
+        const std::string path = std::string(dir) + name;
+        FILE* f = std::fopen(path.c_str(), "wb");
+        if (!f) throw SpError{CATTUS_B200_EINVAL, "cannot create " + path};
+        const size_t n = std::fwrite(bytes.data(), 1, bytes.size(), f);
+        std::fclose(f);
+        if (n != bytes.size()) throw SpError{CATTUS_B200_EINVAL, "short write to " + path};
+    }
+
+    // ---------------------------------------------------------------- MctsPlayer
+    // calc_moves_probabilities up to develop_tree (mod.rs:335-362)
+    void begin_search(Slot& s) {
+        s.search_t0 = Clock::now();
+        Tree<Pos>& t = s.players[s.cur].tree;
+        const Pos& position = s.history.back();
+        if (t.root >= 0) {
+            const int32_t node = find_node_with_position(t, position);
+            if (node >= 0)
+                remove_all_but_subtree(s, t, node);
+            else
+                t.clear();
+        }
+        if (t.root < 0) {
+            t.nodes.emplace_back();
+            t.nodes.back().pos = position;
+            t.root = 0;
+        }
+        s.sims_left = params_[s.cur].sim_num;
+    }
+
+    // mod.rs:283-301, depth_limit = 3 (root, its children, their children).  Unvisited children have no node yet;
+    // their position is parent + move, compared on the fly and materialised on a match.
+    int32_t find_node_with_position(Tree<Pos>& t, const Pos& position) {
+        if (R.same(t.nodes[t.root].pos, position)) return t.root;
+        std::vector<int32_t> layer{t.root}, next;
+        for (int depth = 1; depth < 3; ++depth) {
+            next.clear();
+            for (int32_t n : layer) {
+                const int32_t first = t.nodes[n].first, count = t.nodes[n].count;
+                for (int32_t i = count - 1; i >= 0; --i) {
+                    const int32_t ei = first + i;
+                    const int32_t c = t.edges[ei].child;
+                    if (c >= 0) {
+                        if (R.same(t.nodes[c].pos, position)) return c;
+                        next.push_back(c);
+                    } else if (R.child_matches(t.nodes[n].pos, t.edges[ei].m, position)) {
+                        return materialise(t, n, ei);
+                    }
+                }
+            }
+            layer.swap(next);
+        }
+        return -1;
+    }
+
+    int32_t materialise(Tree<Pos>& t, int32_t parent, int32_t ei) {
+        const Pos child = R.moved(t.nodes[parent].pos, t.edges[ei].m);
+        t.nodes.emplace_back();
+        t.nodes.back().pos = child;
+        const int32_t idx = static_cast<int32_t>(t.nodes.size()) - 1;
+        t.edges[ei].child = idx;
+        return idx;
+    }
+
+    // mod.rs:303-333: copy the subtree; edges are re-inserted in iteration (newest-first) order => reversed
+    void remove_all_but_subtree(Slot& s, Tree<Pos>& t, int32_t sub_root) {
+        if (t.root == sub_root) return;
+        Tree<Pos> nt;
+        nt.nodes.reserve(t.nodes.size() / 4 + 16);
+        nt.edges.reserve(t.edges.size() / 4 + 16);
+        nt.nodes.emplace_back();
+        nt.nodes[0].pos = t.nodes[sub_root].pos;
+        nt.root = 0;
+        std::vector<std::pair<int32_t, int32_t>> stack{{sub_root, 0}};
+        while (!stack.empty()) {
+            const auto [old_n, new_n] = stack.back();
+            stack.pop_back();
+            const int32_t first = t.nodes[old_n].first, count = t.nodes[old_n].count;
+            if (count == 0) continue;
+            const int32_t nfirst = static_cast<int32_t>(nt.edges.size());
+            nt.nodes[new_n].first = nfirst;
+            nt.nodes[new_n].count = count;
+            for (int32_t i = count - 1; i >= 0; --i) nt.edges.push_back(t.edges[first + i]);
+            for (int32_t i = 0; i < count; ++i) {
+                Edge& e = nt.edges[nfirst + i];
+                if (e.child >= 0) {
+                    const int32_t old_c = e.child;
+                    nt.nodes.emplace_back();
+                    nt.nodes.back().pos = t.nodes[old_c].pos;
+                    e.child = static_cast<int32_t>(nt.nodes.size()) - 1;
+                    stack.push_back({old_c, e.child});
+                }
+            }
+        }
+        t = std::move(nt);
+        if (t.nodes[t.root].count > 0) add_dirichlet_noise(s, t, t.root);
+    }
+
+    // mod.rs:419-446
+    void add_dirichlet_noise(Slot& s, Tree<Pos>& t, int32_t node) {
+        const Params& P = params_[s.cur];
+        if (P.noise_alpha == 0.0f || P.noise_eps == 0.0f) return;
+        const int32_t first = t.nodes[node].first, count = t.nodes[node].count;
+        if (count < 2) return;
+        noise_.resize(count);
+        double tot = 0.0;
+        for (int i = 0; i < count; ++i) {
+            noise_[i] = s.rng.gamma(static_cast<double>(P.noise_alpha));
+            tot += noise_[i];
+        }
+        const float eps = P.noise_eps;
+        for (int i = 0; i < count; ++i) {  // zip(edges() order = newest first, noise)
+            Edge& e = t.edges[first + (count - 1 - i)];
+            const float nz = static_cast<float>(noise_[i] / tot);
+            e.init_score = (1.0f - eps) * e.init_score + eps * nz;
+        }
+    }
+
+    // One develop_tree iteration (mod.rs:158-195).  Returns false if the leaf was parked on the evaluator.
+    bool simulate_once(uint32_t si) {
+        Slot& s = slots_[si];
+        Tree<Pos>& t = s.players[s.cur].tree;
+        const Params& P = params_[s.cur];
+        // select (mod.rs:199-231)
+        s.path.clear();
+        int32_t node = t.root;
+        for (;;) {
+            const Node<Pos>& nd = t.nodes[node];
+            if (nd.count == 0 || R.status(nd.pos) != 0) break;
+            const Edge* e = &t.edges[nd.first];
+            uint32_t simcount = 1;
+            for (int32_t i = 0; i < nd.count; ++i) simcount += e[i].simulations_n;
+            const float sq = std::sqrt(static_cast<float>(simcount));
+            int32_t best = -1;
+            float best_val = 0.0f;
+            for (int32_t i = nd.count - 1; i >= 0; --i) {  // edges(): newest first; max_by keeps the last maximum
+                const float exploit = e[i].simulations_n == 0 ? 0.0f : e[i].score_w / static_cast<float>(e[i].simulations_n);
+                const float explore = P.explore_factor * e[i].init_score * (sq / static_cast<float>(1 + e[i].simulations_n));
+                const float v = exploit + explore;
+                if (best < 0 || !(v < best_val)) {
+                    best = i;
+                    best_val = v;
+                }
+            }
+            const int32_t ei = nd.first + best;
+            s.path.push_back(ei);
+            int32_t c = t.edges[ei].child;
+            if (c < 0) c = materialise(t, node, ei);
+            node = c;
+        }
+        s.leaf = node;
+        const Pos& leaf_pos = t.nodes[node].pos;
+        const int st = R.status(leaf_pos);
+        if (st != 0) {
+            sh_.terminal.fetch_add(1, std::memory_order_relaxed);
+            backpropagate(s, t, st == 3 ? 0.0f : (st == 1 ? 1.0f : -1.0f));
+            return true;
+        }
+        // NNetwork::evaluate (net/mod.rs:74-87): flip -> cache -> network
+        s.leaf_flipped = leaf_pos.turn != 1;
+        s.leaf_eval_pos = s.leaf_flipped ? R.flipped(leaf_pos) : leaf_pos;
+        Evaluator& ev = *evals_[s.cur];
+        const PosKey key = R.key(s.leaf_eval_pos);
+        if (ev.cache) {
+            if (CacheVal v = ev.cache->find(key)) {
+                sh_.cache_hits.fetch_add(1, std::memory_order_relaxed);
+                deliver(s, *v);
+                return true;
+            }
+        }
+        Pending& pb = pending_[evals_[0] == evals_[1] ? 0 : s.cur];
+        auto it = pb.index.find(key);
+        if (it != pb.index.end()) {
+            pb.waiters[it->second].push_back(si);
+        } else {
+            const uint32_t row = static_cast<uint32_t>(pb.keys.size());
+            pb.index.emplace(key, row);
+            pb.keys.push_back(key);
+            u128 pl[3];
+            R.planes(s.leaf_eval_pos, pl);
+            for (int c = 0; c < 3; ++c)
+                for (int k = 0; k < abi_wpp_; ++k) pb.planes.push_back(static_cast<uint64_t>(pl[c] >> (64 * k)));
+            pb.n_legal.push_back(static_cast<uint8_t>(popcount128(R.legal_mask(s.leaf_eval_pos))));
+            pb.waiters.emplace_back(1, si);
+        }
+        s.phase = kWaitEval;
+        return false;
+    }
+
+    // create_children + root noise + backpropagate for a leaf whose evaluation is known (mod.rs:180-194, :246-262)
+    void deliver(Slot& s, const std::vector<float>& val) {
+        Tree<Pos>& t = s.players[s.cur].tree;
+        const int32_t leaf = s.leaf;
+        u128 legal = R.legal_mask(s.leaf_eval_pos);
+        const int32_t first = static_cast<int32_t>(t.edges.size());
+        int32_t count = 0;
+        while (legal) {  // legal_moves() of the evaluated position, ascending; un-flipped by flip_score_if_needed
+            const int m = ctz128(legal);
+            legal &= legal - 1;
+            Edge e;
+            e.m = static_cast<uint8_t>(s.leaf_flipped ? R.flip_move(m) : m);
+            e.init_score = val[count];
+            e.score_w = 0.0f;
+            e.simulations_n = 0;
+            e.child = -1;
+            t.edges.push_back(e);
+            ++count;
+        }
+        t.nodes[leaf].first = first;
+        t.nodes[leaf].count = count;
+        if (leaf == t.root) add_dirichlet_noise(s, t, leaf);
+        float v = val[count];
+        if (s.leaf_flipped) v = -v;
+        backpropagate(s, t, v);
+    }
+
+    // mod.rs:270-281
+    void backpropagate(Slot& s, Tree<Pos>& t, float score) {
+        for (size_t i = 0; i < s.path.size(); ++i) {
+            Edge& e = t.edges[s.path[i]];
+            const uint8_t turn = t.nodes[path_nodes_at(s, t, i)].pos.turn;
+            e.simulations_n += 1;
+            e.score_w += turn == 1 ? score : -score;
+        }
+        s.sims_left -= 1;
+        sh_.simulations.fetch_add(1, std::memory_order_relaxed);
+    }
+    // source node of the i-th edge on the path: the root for i = 0, else the child of the previous edge
+    int32_t path_nodes_at(const Slot& s, const Tree<Pos>& t, size_t i) const { return i == 0 ? t.root : t.edges[s.path[i - 1]].child; }
+
+    // the rest of calc_moves_probabilities + choose_move_from_probabilities + the game step (mod.rs:364-417,
+    // self_play.rs:207-217)
+    void end_search(Slot& s) {
+        Tree<Pos>& t = s.players[s.cur].tree;
+        const Params& P = params_[s.cur];
+        const Node<Pos>& root = t.nodes[t.root];
+        std::vector<std::pair<uint8_t, float>> probs;
+        probs.reserve(root.count);
+        uint32_t total = 0;
+        for (int32_t i = 0; i < root.count; ++i) total += t.edges[root.first + i].simulations_n;
+        for (int32_t i = root.count - 1; i >= 0; --i) {  // edges() order
+            const Edge& e = t.edges[root.first + i];
+            probs.emplace_back(e.m, static_cast<float>(e.simulations_n) / static_cast<float>(total));
+        }
+        const double secs = std::chrono::duration<double>(Clock::now() - s.search_t0).count();
+        {
+            std::lock_guard<std::mutex> g(sh_.mu);  // RunningAverage(0.99), util/metric.rs:1-20
+            sh_.search_duration = (1.0 - 0.99) * sh_.search_duration + 0.99 * secs;
+        }
+        sh_.searches.fetch_add(1, std::memory_order_relaxed);
+        if (probs.empty()) throw SpError{CATTUS_B200_EINVAL, "search produced no moves"};
+        // choose_move_from_probabilities
+        const float temperature = P.temperature_at(s.history.size() / 2);
+        int chosen = 0;
+        if (temperature == 0.0f) {
+            for (size_t i = 1; i < probs.size(); ++i)
+                if (!(probs[i].second < probs[chosen].second)) chosen = static_cast<int>(i);  // max_by(total_cmp): last maximum
+        } else {
+            const float inv = 1.0f / temperature;
+            weights_.resize(probs.size());
+            float tot = 0.0f;
+            for (size_t i = 0; i < probs.size(); ++i) {
+                weights_[i] = static_cast<float>(std::pow(static_cast<double>(probs[i].second), static_cast<double>(inv)));
+                tot += weights_[i];
+            }
+            float cum = 0.0f, cum_tot = 0.0f;
+            for (size_t i = 0; i < probs.size(); ++i) {
+                weights_[i] = weights_[i] / tot;
+                cum_tot += weights_[i];
+            }
+            const double x = s.rng.next_f64() * static_cast<double>(cum_tot);
+            chosen = static_cast<int>(probs.size()) - 1;
+            for (size_t i = 0; i < probs.size(); ++i) {
+                cum += weights_[i];
+                if (static_cast<double>(cum) > x) {
+                    chosen = static_cast<int>(i);
+                    break;
+                }
+            }
+        }
+        const uint8_t mv = probs[chosen].first;
+        s.rec.moves.push_back(mv);
+        s.pending_entries.emplace_back(s.history.back(), std::move(probs));
+        s.history.push_back(R.moved(s.history.back(), mv));
+    }
+
+    // ---------------------------------------------------------------- evaluator batch
+    void flush(int e) {
+        Pending& pb = pending_[e];
+        Evaluator& ev = *evals_[e];
+        const uint32_t n = static_cast<uint32_t>(pb.keys.size());
+        size_t total = 0;
+        for (uint8_t c : pb.n_legal) total += c;
+        probs_.resize(total);
+        offsets_.resize(n + 1);
+        values_.resize(n);
+        const auto t0 = Clock::now();
+        int rc;
+        if (n == 1 && ev.leaf_handle) {
+            uint32_t np = 0;
+            rc = cattus_b200_eval(ev.leaf_handle, pb.planes.data(), nullptr, probs_.data(), static_cast<uint32_t>(total), &np, values_.data());
+            offsets_[0] = 0;
+            offsets_[1] = np;
+        } else {
+            rc = ev.fn(ev.ctx, pb.planes.data(), nullptr, n, probs_.data(), total, offsets_.data(), values_.data());
+        }
+        eval_wait_ += std::chrono::duration<double>(Clock::now() - t0).count();
+        if (rc != 0) throw SpError{rc, std::string("evaluator failed: ") + cattus_b200_last_error()};
+        sh_.batches.fetch_add(1, std::memory_order_relaxed);
+        sh_.evaluations.fetch_add(n, std::memory_order_relaxed);
+        for (uint32_t r = 0; r < n; ++r) {
+            if (offsets_[r + 1] - offsets_[r] != pb.n_legal[r]) throw SpError{CATTUS_B200_EINVAL, "evaluator returned a wrong number of probabilities"};
+            auto v = std::make_shared<std::vector<float>>(probs_.begin() + offsets_[r], probs_.begin() + offsets_[r + 1]);
+            v->push_back(values_[r]);
+            CacheVal use = v;
+            if (ev.cache) {
+                bool inserted = false;
+                use = ev.cache->insert(pb.keys[r], v, &inserted);
+                if (inserted)
+                    sh_.cache_misses.fetch_add(1, std::memory_order_relaxed);
+                else
+                    sh_.cache_hits.fetch_add(1, std::memory_order_relaxed);
+                if (pb.waiters[r].size() > 1) sh_.cache_hits.fetch_add(pb.waiters[r].size() - 1, std::memory_order_relaxed);
+            }
+            for (uint32_t si : pb.waiters[r]) {
+                Slot& s = slots_[si];
+                deliver(s, *use);
+                s.phase = kSimulate;
+            }
+        }
+        pb.clear();
+    }
+
+    const Rules& R;
+    const cattus_b200_selfplay_cfg& cfg_;
+    Shared& sh_;
+    Params params_[2];
+    Evaluator* evals_[2];
+    std::vector<Slot> slots_;
+    Pending pending_[2];
+    int abi_wpp_ = 1;
+    double eval_wait_ = 0.0;
+    std::vector<double> noise_;
+    std::vector<float> weights_, probs_, values_;
+    std::vector<uint32_t> offsets_;
+};
+
+static void make_dirs(const char* path) {
+    std::string p(path);
+    for (size_t i = 1; i <= p.size(); ++i)
+        if (i == p.size() || p[i] == '/') {
+            const std::string sub = p.substr(0, i);
+            ::mkdir(sub.c_str(), 0777);
+        }
+}
+
+}  // namespace sp
+
+struct cattus_b200_selfplay {
+    cattus_b200_selfplay_summary summary;
+    std::vector<sp::GameRecord> records;
+};
+
+static thread_local std::string g_sp_error;
+
+template <class Rules>
+static void run_games(const Rules& rules, const cattus_b200_selfplay_cfg& cfg, const sp::Params params[2], sp::Evaluator* evals[2], sp::Shared& sh) {
+    const uint32_t n_threads = std::max<uint32_t>(1, cfg.threads);
+    std::vector<std::unique_ptr<sp::Worker<Rules>>> workers;
+    for (uint32_t i = 0; i < n_threads; ++i) workers.emplace_back(new sp::Worker<Rules>(rules, cfg, params, evals, sh));
+    std::vector<std::thread> threads;
+    for (uint32_t i = 1; i < n_threads; ++i) threads.emplace_back([&, i] { workers[i]->run(); });
+    workers[0]->run();  // the calling thread does job 0 (self_play.rs:127-137)
+    for (auto& t : threads) t.join();
+}
+
+static int selfplay_impl(sp::Evaluator& e1, sp::Evaluator* e2_or_null, const cattus_b200_selfplay_cfg* cfg, cattus_b200_selfplay_t** out) {
+    try {
+        if (!cfg || !out) throw sp::SpError{CATTUS_B200_EINVAL, "null argument"};
+        if (cfg->struct_size != sizeof(cattus_b200_selfplay_cfg)) throw sp::SpError{CATTUS_B200_EINVAL, "selfplay cfg struct_size mismatch"};
+        *out = nullptr;
+        if (cfg->sim_num < 2) throw sp::SpError{CATTUS_B200_EINVAL, "sim_num must be > 1 (mcts/mod.rs:157)"};
+        if (!(cfg->explore_factor >= 0.0f) || !(cfg->prior_noise_alpha >= 0.0f) || !(cfg->prior_noise_epsilon >= 0.0f && cfg->prior_noise_epsilon <= 1.0f))
+            throw sp::SpError{CATTUS_B200_EINVAL, "bad mcts parameters (mcts/mod.rs:107-110)"};
+        if (cfg->games_num % 2 != 0) throw sp::SpError{CATTUS_B200_EINVAL, "Games num should be a multiple of 2 (self_play.rs:100)"};
+        if ((cfg->out_dir1 == nullptr) != (cfg->out_dir2 == nullptr)) throw sp::SpError{CATTUS_B200_EINVAL, "out_dir1 and out_dir2 must both be set or both NULL"};
+        sp::Params p;
+        p.sim_num = cfg->sim_num;
+        p.explore_factor = cfg->explore_factor;
+        p.noise_alpha = cfg->prior_noise_alpha;
+        p.noise_eps = cfg->prior_noise_epsilon;
+        p.last_temperature = 1.0f;
+        if (cfg->n_temperatures) {
+            if (!cfg->temperature_moves || !cfg->temperature_values) throw sp::SpError{CATTUS_B200_EINVAL, "temperature arrays are NULL"};
+            for (uint32_t i = 0; i + 1 < cfg->n_temperatures; ++i) {
+                if (!(cfg->temperature_values[i] >= 0.0f)) throw sp::SpError{CATTUS_B200_EINVAL, "negative temperature"};
+                if (i > 0 && cfg->temperature_moves[i] <= cfg->temperature_moves[i - 1]) throw sp::SpError{CATTUS_B200_EINVAL, "temperature thresholds must be strictly increasing"};
+                p.temperatures.emplace_back(cfg->temperature_moves[i], cfg->temperature_values[i]);
+            }
+            p.last_temperature = cfg->temperature_values[cfg->n_temperatures - 1];
+            if (!(p.last_temperature >= 0.0f)) throw sp::SpError{CATTUS_B200_EINVAL, "negative temperature"};
+        }
+        sp::Params params[2] = {p, p};
+        if (cfg->cache_size) {
+            e1.cache.reset(new sp::Cache(cfg->cache_size));
+            if (e2_or_null) e2_or_null->cache.reset(new sp::Cache(cfg->cache_size));
+        }
+        sp::Evaluator* evals[2] = {&e1, e2_or_null ? e2_or_null : &e1};
+        if (cfg->out_dir1) {
+            sp::make_dirs(cfg->out_dir1);
+            sp::make_dirs(cfg->out_dir2);
+        }
+        sp::Shared sh;
+        const auto t0 = sp::Clock::now();
+        if (cfg->game == CATTUS_B200_GAME_HEX) {
+            if (cfg->board_size < 2 || cfg->board_size > 11) throw sp::SpError{CATTUS_B200_EINVAL, "hex board_size must be 2..11"};
+            sp::HexRules rules(static_cast<int>(cfg->board_size));
+            run_games(rules, *cfg, params, evals, sh);
+        } else if (cfg->game == CATTUS_B200_GAME_TTT) {
+            sp::TttRules rules;
+            run_games(rules, *cfg, params, evals, sh);
+        } else {
+            throw sp::SpError{CATTUS_B200_EINVAL, "the self-play driver covers hex and tictactoe (chess move generation is the third-party crate `chess`)"};
+        }
+        if (sh.failed.load()) throw sp::SpError{sh.error_code, sh.error};
+        std::unique_ptr<cattus_b200_selfplay> r(new cattus_b200_selfplay());
+        cattus_b200_selfplay_summary& s = r->summary;
+        std::memset(&s, 0, sizeof(s));
+        s.player1_wins = sh.w1;
+        s.player2_wins = sh.w2;
+        s.draws = sh.d;
+        s.games = sh.games;
+        s.simulations = sh.simulations;
+        s.searches = sh.searches;
+        s.evaluations = sh.evaluations;
+        s.cache_hits = sh.cache_hits;
+        s.cache_misses = sh.cache_misses;
+        s.batches = sh.batches;
+        s.terminal_leaves = sh.terminal;
+        s.seconds = std::chrono::duration<double>(sp::Clock::now() - t0).count();
+        s.search_duration = sh.search_duration;
+        s.eval_wait_seconds = sh.eval_wait;
+        r->records = std::move(sh.records);
+        std::sort(r->records.begin(), r->records.end(), [](const sp::GameRecord& a, const sp::GameRecord& b) { return a.game_idx < b.game_idx; });
+        *out = r.release();
+        g_sp_error.clear();
+        return CATTUS_B200_OK;
+    } catch (const sp::SpError& e) {
+        g_sp_error = e.msg;
+        return e.code ? e.code : CATTUS_B200_EINVAL;
+    } catch (const std::exception& e) {
+        g_sp_error = e.what();
+        return CATTUS_B200_EINVAL;
+    }
+}
+
+static int engine_eval_thunk(void* ctx, const uint64_t* planes, const uint8_t* legal, uint32_t n, float* probs, size_t cap, uint32_t* offsets, float* values) {
+    return cattus_b200_eval_batch(static_cast<cattus_b200_t*>(ctx), planes, legal, n, probs, cap, offsets, values);
+}
+
+extern "C" {
+
+int cattus_b200_selfplay_run(cattus_b200_t* model1, cattus_b200_t* model2, const cattus_b200_selfplay_cfg* cfg, cattus_b200_selfplay_t** out) {
+    if (!model1) {
+        g_sp_error = "null evaluator handle (there is no CPU fallback)";
+        return CATTUS_B200_EINVAL;
+    }
+    sp::Evaluator e1, e2;
+    e1.fn = engine_eval_thunk;
+    e1.ctx = model1;
+    if (cfg && cfg->leaf_queue) e1.leaf_handle = model1;
+    const bool two = model2 && model2 != model1;
+    if (two) {
+        e2.fn = engine_eval_thunk;
+        e2.ctx = model2;
+        if (cfg && cfg->leaf_queue) e2.leaf_handle = model2;
+    }
+    return selfplay_impl(e1, two ? &e2 : nullptr, cfg, out);
+}
+
+int cattus_b200_selfplay_run_with(cattus_b200_eval_fn eval1, void* ctx1, cattus_b200_eval_fn eval2, void* ctx2, const cattus_b200_selfplay_cfg* cfg,
+                                  cattus_b200_selfplay_t** out) {
+    if (!eval1) {
+        g_sp_error = "null evaluator callback";
+        return CATTUS_B200_EINVAL;
+    }
+    sp::Evaluator e1, e2;
+    e1.fn = eval1;
+    e1.ctx = ctx1;
+    const bool two = eval2 && !(eval2 == eval1 && ctx2 == ctx1);
+    if (two) {
+        e2.fn = eval2;
+        e2.ctx = ctx2;
+    }
+    return selfplay_impl(e1, two ? &e2 : nullptr, cfg, out);
+}
+
+int cattus_b200_selfplay_summary_get(const cattus_b200_selfplay_t* r, cattus_b200_selfplay_summary* out) {
+    if (!r || !out) return CATTUS_B200_EINVAL;
+    *out = r->summary;
+    return CATTUS_B200_OK;
+}
+
+int cattus_b200_selfplay_game_count(const cattus_b200_selfplay_t* r, uint32_t* n) {
+    if (!r || !n) return CATTUS_B200_EINVAL;
+    *n = static_cast<uint32_t>(r->records.size());
+    return CATTUS_B200_OK;
+}
+
+int cattus_b200_selfplay_game_info(const cattus_b200_selfplay_t* r, uint32_t k, uint32_t* game_idx, uint32_t* winner, uint32_t* n_moves) {
+    if (!r || k >= r->records.size()) return CATTUS_B200_ERANGE;
+    if (game_idx) *game_idx = r->records[k].game_idx;
+    if (winner) *winner = r->records[k].winner;
+    if (n_moves) *n_moves = static_cast<uint32_t>(r->records[k].moves.size());
+    return CATTUS_B200_OK;
+}
+
+int cattus_b200_selfplay_game_moves(const cattus_b200_selfplay_t* r, uint32_t k, uint8_t* moves_out, uint32_t cap) {
+    if (!r || !moves_out || k >= r->records.size()) return CATTUS_B200_ERANGE;
+    const auto& m = r->records[k].moves;
+    if (cap < m.size()) return CATTUS_B200_ERANGE;
+    std::memcpy(moves_out, m.data(), m.size());
+    return CATTUS_B200_OK;
+}
+
+int cattus_b200_selfplay_entry(const cattus_b200_selfplay_t* r, uint32_t k, uint32_t pos_idx, uint8_t* bytes_out, size_t cap, size_t* n_bytes,
+                               uint32_t* out_dir) {
+    if (!r || k >= r->records.size() || pos_idx >= r->records[k].entries.size()) return CATTUS_B200_ERANGE;
+    const auto& b = r->records[k].entries[pos_idx];
+    if (n_bytes) *n_bytes = b.size();
+    if (out_dir) *out_dir = r->records[k].entry_dir[pos_idx];
+    if (bytes_out) {
+        if (cap < b.size()) return CATTUS_B200_ERANGE;
+        std::memcpy(bytes_out, b.data(), b.size());
+    }
+    return CATTUS_B200_OK;
+}
+
+void cattus_b200_selfplay_free(cattus_b200_selfplay_t* r) { delete r; }
+
+const char* cattus_b200_selfplay_last_error(void) { return g_sp_error.c_str(); }
+
+}  // extern "C"
