@@ -278,7 +278,8 @@ def main():
     h2d = positions_per_step * (cfg.planes * ((cfg.board_size ** 2 + 63) // 64) * 8 + (((cfg.moves + 31) // 32 * 4 + 7) // 8 * 8 if bitmaps is not None else 0)) + 16 * per_step
     d2h = int(offsets[-1]) * 4 + positions_per_step * 4
     kernels_per_batch = nw.info.kernels_per_batch
-    fused = bool(nw.info.reserved)
+    fused = bool(nw.info.reserved & 1)
+    small = bool(nw.info.reserved & 2)
     nw.close()
 
     total_positions = world * positions_per_step * args.steps
@@ -290,7 +291,9 @@ def main():
     t_trunk = float(np.mean(ms_trunk)) * 1e-3
     achieved = batch * trunk_flops / t_trunk / 1e12
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
-                "traffic": None, "kernel": "trunk_fused_kernel (stem + residual blocks, one launch)" if fused else "tc_gemm_kernel x (1 + 2R) conv layers (stem + residual blocks)",
+                "traffic": None, "kernel": ("trunk_fused_kernel (stem + residual blocks, one launch)" if fused else
+                           "trunk_small_kernel (encode + stem + residual blocks + head convs, one launch)" if small else
+                           "tc_gemm_kernel x (1 + 2R) conv layers (stem + residual blocks)"),
                 "peak_source": peaks["source"] + ", burst figure (stage timed alone)", "flop_per_position": trunk_flops, "positions_per_launch": batch,
                 "ms": t_trunk * 1e3,
                 "stages_ms": {"encode": float(np.mean(ms_enc)), "trunk": float(np.mean(ms_trunk)), "heads": float(np.mean(ms_heads)),

@@ -171,6 +171,13 @@ Engine::Engine(const cattus_b200_desc& desc, const void* blob_bytes, size_t blob
     fused_trunk_ = precision_ == CATTUS_B200_PRECISION_BF16 && d_.s == 8 && d_.f == 128 && d_.c_in <= 32 && d_.wpp() == 1 &&
                    (desc.flags & 1u) == 0 && (sm_count_ >= 2);
     if (fused_trunk_) CB2_CUDA(cudaFuncSetAttribute(trunk_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFtSmemBytes));
+    // 16-filter nets (every shipped training config): whole trunk + both head convs in one kernel
+    small_trunk_ = precision_ == CATTUS_B200_PRECISION_BF16 && d_.f == 16 && d_.c_in <= 32 && d_.s >= 3 && d_.s <= 11 && vhp_ + php_ <= 32 &&
+                   (desc.flags & 1u) == 0;
+    if (small_trunk_) {
+        small_stem_kc_ = ceil_div(d_.c_in, 16);
+        CB2_CUDA(cudaFuncSetAttribute(trunk_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    }
 
     upload_weights(blob);
 
@@ -233,6 +240,8 @@ Engine::~Engine() {
     vfc2_w_.free_();
     fused_w_.free_();
     fused_b_.free_();
+    small_w_.free_();
+    small_b_.free_();
     flush_.free_();
 }
 
@@ -338,6 +347,39 @@ void Engine::upload_weights(const Blob& blob) {
         }
         upload(fused_w_, to_bf16(img));
         upload(fused_b_, bias);
+    }
+    if (small_trunk_) {
+        // trunk_small.cuh weight image: per layer, per 16-channel k-chunk, per tap: [k-half 2][oc 16][ic 8] bf16 (512 B);
+        // then the two head convs as one [k-half 2][oc vhp + php][ic 8] tile (value channels first).  Biases: [layers][16], [nh].
+        const uint32_t layers = 1 + static_cast<uint32_t>(blob.block_conv.size());
+        const uint32_t nh = vhp_ + php_;
+        const size_t layer_elems = 9 * 256;
+        std::vector<float> img((small_stem_kc_ + (layers - 1)) * layer_elems + 2 * nh * 8, 0.0f), bias(static_cast<size_t>(layers) * 16 + nh, 0.0f);
+        size_t off = 0;
+        for (uint32_t l = 0; l < layers; ++l) {
+            const Blob::Conv& c = l == 0 ? blob.stem : blob.block_conv[l - 1];
+            const uint32_t nkc = l == 0 ? small_stem_kc_ : 1;
+            for (uint32_t o = 0; o < 16; ++o) bias[l * 16 + o] = D[c.b + o];
+            for (uint32_t kc = 0; kc < nkc; ++kc)
+                for (uint32_t tap = 0; tap < 9; ++tap)
+                    for (uint32_t kh = 0; kh < 2; ++kh)
+                        for (uint32_t o = 0; o < 16; ++o)
+                            for (uint32_t e = 0; e < 8; ++e) {
+                                const uint32_t ic = kc * 16 + kh * 8 + e;
+                                if (ic < c.ci) img[off + ((kc * 9 + tap) * 2 + kh) * 128 + o * 8 + e] = D[c.w + (static_cast<size_t>(o) * c.ci + ic) * 9 + tap];
+                            }
+            off += nkc * layer_elems;
+        }
+        for (uint32_t kh = 0; kh < 2; ++kh)
+            for (uint32_t e = 0; e < 8; ++e) {
+                const uint32_t ic = kh * 8 + e;
+                for (uint32_t o = 0; o < d_.vh; ++o) img[off + (kh * nh + o) * 8 + e] = D[blob.vconv.w + static_cast<size_t>(o) * 16 + ic];
+                for (uint32_t o = 0; o < d_.ph; ++o) img[off + (kh * nh + vhp_ + o) * 8 + e] = D[blob.pconv.w + static_cast<size_t>(o) * 16 + ic];
+            }
+        for (uint32_t o = 0; o < d_.vh; ++o) bias[static_cast<size_t>(layers) * 16 + o] = D[blob.vconv.b + o];
+        for (uint32_t o = 0; o < d_.ph; ++o) bias[static_cast<size_t>(layers) * 16 + vhp_ + o] = D[blob.pconv.b + o];
+        upload(small_w_, to_bf16(img));
+        upload(small_b_, bias);
     }
     conv1(vconv_, blob.vconv, vhp_);
     conv1(pconv_, blob.pconv, php_);
@@ -562,7 +604,8 @@ void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
     const int sm = sm_count_;
     __nv_bfloat16* x = lane.d_x.as<__nv_bfloat16>();
     const bool fused = fused_trunk_ && !dense_input;
-    if (!fused) {
+    const bool small = small_trunk_ && !dense_input;
+    if (!fused && !small) {
         Op op;
         op.stage = 0;
         const int blocks = grid_for(static_cast<long long>(rows_total) * (cin_pad_ / 8), 256, sm);
@@ -662,6 +705,49 @@ void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
         op.name = "trunk_fused";
         op.launch = [fp, pairs](cudaStream_t st) { trunk_fused_kernel<<<2 * pairs, kFtThreads, kFtSmemBytes, st>>>(fp); };
         ops.push_back(op);
+    } else if (small) {
+        // encode + stem + all residual blocks + both 1x1 head convs in one launch (trunk_small.cuh)
+        TrunkSmallParams sp;
+        std::memset(&sp, 0, sizeof(sp));
+        const int W = static_cast<int>(d_.s) + 1, BP = W * W;
+        // fewest tiles per CTA that still fit the batch on the SMs in one wave (small batches spread out for latency)
+        int T = kTsMaxTiles;
+        for (int cand = 1; cand <= kTsMaxTiles; cand *= 2) {
+            const int nbr = cand * 128 / BP;
+            if (nbr >= 1 && static_cast<int>(ceil_div(bucket, static_cast<uint32_t>(nbr))) <= sm) {
+                T = cand;
+                break;
+            }
+        }
+        sp.recs = recs;
+        sp.n_ptr = n_ptr;
+        sp.wimg = small_w_.as<uint4>();
+        sp.bias = small_b_.as<float>();
+        sp.out_v = lane.d_hv.as<__nv_bfloat16>();
+        sp.out_p = lane.d_hp.as<__nv_bfloat16>();
+        sp.err = d_err_;
+        sp.rec_bytes = rec_.rec_bytes;
+        sp.planes = static_cast<int>(d_.c_in);
+        sp.wpp = rec_.wpp;
+        sp.s = static_cast<int>(d_.s);
+        sp.layers = 1 + 2 * static_cast<int>(d_.r);
+        sp.stem_kc = static_cast<int>(small_stem_kc_);
+        sp.vhp = static_cast<int>(vhp_);
+        sp.php = static_cast<int>(php_);
+        sp.tiles = T;
+        sp.boards_per_round = T * 128 / BP;
+        sp.num_rounds = static_cast<int>(ceil_div(bucket, static_cast<uint32_t>(sp.boards_per_round)));
+        sp.w_bytes = static_cast<int>((small_stem_kc_ + 2 * d_.r) * 9 * kTsTapBytes + (vhp_ + php_) * 32);
+        sp.margin = (W + 1 + 7) / 8 * 8;
+        const TsSmemLayout lay = ts_smem_layout(sp.tiles, sp.stem_kc, sp.margin, sp.w_bytes);
+        if (lay.total > 200 * 1024) throw Error(CATTUS_B200_EINVAL, "trunk_small: network does not fit in shared memory");
+        const int grid = std::min(sm, sp.num_rounds);
+        const int smem_bytes = lay.total;
+        Op op;
+        op.stage = 1;
+        op.name = "trunk_small";
+        op.launch = [sp, grid, smem_bytes](cudaStream_t st) { trunk_small_kernel<<<grid, kTsThreads, smem_bytes, st>>>(sp); };
+        ops.push_back(op);
     } else {
         conv3("stem", x, cin_pad_, convs_[0], nullptr, act[0]);
         for (uint32_t i = 0; i < d_.r; ++i) {
@@ -671,8 +757,10 @@ void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
             cur = o;
         }
     }
-    gemm(2, "value_conv", act[cur], ca_, rows_total, ca_ * 2ull, vconv_, lane.d_hv.p, vhp_, false, true);
-    gemm(2, "policy_conv", act[cur], ca_, rows_total, ca_ * 2ull, pconv_, lane.d_hp.p, php_, false, true);
+    if (!small) {
+        gemm(2, "value_conv", act[cur], ca_, rows_total, ca_ * 2ull, vconv_, lane.d_hv.p, vhp_, false, true);
+        gemm(2, "policy_conv", act[cur], ca_, rows_total, ca_ * 2ull, pconv_, lane.d_hp.p, php_, false, true);
+    }
     gemm(2, "value_fc1", lane.d_hv.p, static_cast<uint64_t>(s2) * vhp_, bucket, static_cast<uint64_t>(s2) * vhp_ * 2, vfc1_, lane.d_hidden.p, 128,
          true, true);
     gemm(2, "policy_fc", lane.d_hp.p, static_cast<uint64_t>(s2) * php_, bucket, static_cast<uint64_t>(s2) * php_ * 2, pfc_, lane.d_logits.p,
@@ -777,8 +865,8 @@ void Engine::note_batch(uint32_t n, double seconds) {
     metrics_.activation_count += 1;
     metrics_.positions += n;
     metrics_.run_duration_last = seconds;
-    // RunningAverage(0.99): engine/src/util/metric.rs:1-20 -- first sample initialises, then ema = ema*(1-e) + x*e
-    metrics_.run_duration_ema = metrics_.activation_count == 1 ? seconds : metrics_.run_duration_ema * 0.01 + seconds * 0.99;
+    // RunningAverage(0.99): engine/src/util/metric.rs:1-20 -- value starts at 0, then value = (1 - e) * value + e * x
+    metrics_.run_duration_ema = metrics_.run_duration_ema * (1.0 - 0.99) + seconds * 0.99;
     metrics_.mean_batch_fill = static_cast<double>(metrics_.positions) / (static_cast<double>(metrics_.activation_count) * max_batch_);
     metrics_.kernel_launches += kernels_per_batch_;
 }
@@ -1081,7 +1169,7 @@ void Engine::get_info(cattus_b200_info* info) const {
     info->precision = precision_;
     info->sm_count = static_cast<uint32_t>(sm_count_);
     info->kernels_per_batch = kernels_per_batch_;
-    info->reserved = fused_trunk_ ? 1u : 0u;
+    info->reserved = (fused_trunk_ ? 1u : 0u) | (small_trunk_ ? 2u : 0u);
 }
 
 void Engine::get_metrics(cattus_b200_metrics* m) const {

@@ -27,6 +27,7 @@
 #include "kernels.cuh"
 #include "tc_gemm.cuh"
 #include "trunk_fused.cuh"
+#include "trunk_small.cuh"
 
 namespace cb2 {
 
@@ -165,6 +166,7 @@ class Engine {
     RecLayout rec_{};
     bool derive_legal_ = false;
     bool fused_trunk_ = false;  // S == 8 && F == 128: whole-trunk kernel (trunk_fused.cuh)
+    bool small_trunk_ = false;  // F == 16: whole trunk + head convs in one kernel (trunk_small.cuh)
 
     // derived layout constants (bf16 path)
     uint32_t cin_pad_ = 64;  // encoded-input channels (multiple of 64)
@@ -182,6 +184,8 @@ class Engine {
     DeviceBuf vfc2_w_;
     float vfc2_b_ = 0.0f;
     DeviceBuf fused_w_, fused_b_;  // trunk_fused.cuh weight images + biases
+    DeviceBuf small_w_, small_b_;  // trunk_small.cuh weight image + biases
+    uint32_t small_stem_kc_ = 1;
 
     std::vector<std::unique_ptr<Lane>> lanes_;
     std::vector<char> lane_busy_;

@@ -22,6 +22,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <memory>
@@ -283,49 +284,89 @@ struct TttRules {
 };
 
 // ------------------------------------------------------------------------------------------------ cache
-// ValueFuncCache (mcts/cache.rs:31-75): position -> (per-move probabilities in legal_moves() order, value), FIFO
-// eviction.  Sharded (one mutex + FIFO per shard) instead of one RwLock; a hit returns exactly what was stored.
-using CacheVal = std::shared_ptr<const std::vector<float>>;  // probs..., value last
-
+// ValueFuncCache (mcts/cache.rs:31-75): position -> (per-move probabilities in legal_moves() order, value).  A hit
+// returns exactly what was stored.  Laid out for many worker threads instead of one RwLock<HashMap>: a flat
+// set-associative table (8 ways per bucket, probabilities stored inline, striped spin locks), first-in-first-out
+// eviction WITHIN a bucket instead of over the whole table.  Capacity is max_size rounded up to whole buckets.
+// Eviction order only changes which later lookups hit, never a result (the evaluator is batch invariant).
 class Cache {
   public:
-    explicit Cache(size_t max_size) : per_shard_((max_size + kShards - 1) / kShards) {}
-    CacheVal find(const PosKey& k) {
-        Shard& s = shard(k);
-        std::lock_guard<std::mutex> g(s.mu);
-        auto it = s.map.find(k);
-        if (it == s.map.end()) return nullptr;
-        return it->second;
+    Cache(size_t max_size, int moves_num) : stride_(static_cast<size_t>(moves_num) + 1) {
+        n_buckets_ = 1;
+        while (n_buckets_ * kWays < max_size) n_buckets_ <<= 1;
+        keys_ = static_cast<PosKey*>(std::calloc(n_buckets_ * kWays, sizeof(PosKey)));
+        seq_ = static_cast<uint32_t*>(std::calloc(n_buckets_ * kWays, sizeof(uint32_t)));
+        vals_ = static_cast<float*>(std::calloc(n_buckets_ * kWays * stride_, sizeof(float)));
+        if (!keys_ || !seq_ || !vals_) throw SpError{CATTUS_B200_ENOMEM, "cannot allocate the position cache"};
+        for (auto& l : locks_) l.clear();
     }
-    // returns the value to use (the already-cached one if another thread got there first) and whether it was inserted
-    CacheVal insert(const PosKey& k, CacheVal v, bool* inserted) {
-        Shard& s = shard(k);
-        std::lock_guard<std::mutex> g(s.mu);
-        auto it = s.map.find(k);
-        if (it != s.map.end()) {
-            *inserted = false;
-            return it->second;
+    ~Cache() {
+        std::free(keys_);
+        std::free(seq_);
+        std::free(vals_);
+    }
+    Cache(const Cache&) = delete;
+    Cache& operator=(const Cache&) = delete;
+
+    // copies the stored (probs..., value) of `k` into out[0 .. n_legal] and returns true on a hit
+    bool find(const PosKey& k, int n_legal, float* out) {
+        const size_t b = bucket(k);
+        Guard g(locks_[b & (kLocks - 1)]);
+        const size_t base = b * kWays;
+        for (size_t w = 0; w < kWays; ++w)
+            if (seq_[base + w] && keys_[base + w] == k) {
+                std::memcpy(out, vals_ + (base + w) * stride_, sizeof(float) * (n_legal + 1));
+                return true;
+            }
+        return false;
+    }
+    // stores val[0 .. n_legal] unless the key is already there (another thread got there first), in which case the
+    // cached entry is copied back into `val` (cache.rs:52-63).  Returns true if it was inserted.
+    bool insert(const PosKey& k, int n_legal, float* val) {
+        const size_t b = bucket(k);
+        Guard g(locks_[b & (kLocks - 1)]);
+        const size_t base = b * kWays;
+        size_t victim = 0;
+        uint32_t oldest = UINT32_MAX;
+        for (size_t w = 0; w < kWays; ++w) {
+            const uint32_t sq = seq_[base + w];
+            if (sq && keys_[base + w] == k) {
+                std::memcpy(val, vals_ + (base + w) * stride_, sizeof(float) * (n_legal + 1));
+                return false;
+            }
+            if (sq < oldest) {  // empty ways (0) first, then the oldest insertion
+                oldest = sq;
+                victim = w;
+            }
         }
-        while (s.fifo.size() >= per_shard_) {
-            s.map.erase(s.fifo.front());
-            s.fifo.pop_front();
-        }
-        s.map.emplace(k, v);
-        s.fifo.push_back(k);
-        *inserted = true;
-        return v;
+        keys_[base + victim] = k;
+        uint32_t stamp = ++clock_[b & (kLocks - 1)];
+        if (stamp == 0) stamp = ++clock_[b & (kLocks - 1)];
+        seq_[base + victim] = stamp;
+        std::memcpy(vals_ + (base + victim) * stride_, val, sizeof(float) * (n_legal + 1));
+        return true;
     }
 
   private:
-    static constexpr size_t kShards = 64;
-    struct Shard {
-        std::mutex mu;
-        std::unordered_map<PosKey, CacheVal, PosKeyHash> map;
-        std::deque<PosKey> fifo;
+    static constexpr size_t kWays = 8, kLocks = 4096;
+    struct Guard {
+        std::atomic_flag& f;
+        explicit Guard(std::atomic_flag& fl) : f(fl) {
+            while (f.test_and_set(std::memory_order_acquire)) {
+#if defined(__x86_64__)
+                __builtin_ia32_pause();
+#endif
+            }
+        }
+        ~Guard() { f.clear(std::memory_order_release); }
     };
-    Shard& shard(const PosKey& k) { return shards_[PosKeyHash()(k) >> 58]; }
-    Shard shards_[kShards];
-    size_t per_shard_;
+    size_t bucket(const PosKey& k) const { return PosKeyHash()(k) & (n_buckets_ - 1); }
+    size_t stride_, n_buckets_;
+    PosKey* keys_ = nullptr;
+    uint32_t* seq_ = nullptr;
+    float* vals_ = nullptr;
+    std::atomic_flag locks_[kLocks];
+    uint32_t clock_[kLocks] = {};
 };
 
 // One evaluator = the reference's NNetwork: a network behind a callback plus its own cache.
@@ -384,8 +425,9 @@ struct GameRecord {
 };
 
 struct Shared {
-    std::atomic<uint64_t> simulations{0}, searches{0}, evaluations{0}, cache_hits{0}, cache_misses{0}, batches{0}, terminal{0};
-    std::atomic<uint32_t> w1{0}, w2{0}, d{0}, games{0};
+    // merged from the workers' private counters when they finish (no shared cache line on the per-simulation path)
+    uint64_t simulations = 0, searches = 0, evaluations = 0, cache_hits = 0, cache_misses = 0, batches = 0, terminal = 0;
+    uint32_t w1 = 0, w2 = 0, d = 0, games = 0;
     std::atomic<uint32_t> next_game{0};
     std::mutex mu;  // records, search_duration, first error
     std::vector<GameRecord> records;
@@ -416,6 +458,7 @@ class Worker {
         int32_t leaf = -1;
         bool leaf_flipped = false;
         Pos leaf_eval_pos;  // the position as sent to the network (Player1 to move)
+        uint32_t wait_row = 0;  // row of the pending batch this slot is parked on
         Clock::time_point search_t0;
         GameRecord rec;
         std::vector<std::pair<Pos, std::vector<std::pair<uint8_t, float>>>> pending_entries;
@@ -424,15 +467,38 @@ class Worker {
         std::vector<uint64_t> planes;
         std::vector<PosKey> keys;
         std::vector<uint8_t> n_legal;
-        std::vector<std::vector<uint32_t>> waiters;  // slot indices per batch row
-        std::unordered_map<PosKey, uint32_t, PosKeyHash> index;
+        std::vector<uint32_t> parked;  // slots waiting on this batch (each remembers its row)
+        std::vector<uint32_t> table;   // open addressing: row + 1 of a key already in the batch (in-batch dedupe)
+        std::vector<uint32_t> used;
+        void init(size_t slots) {
+            size_t cap = 16;
+            while (cap < 4 * slots) cap <<= 1;
+            table.assign(cap, 0);
+        }
+        // row of `k` in this batch, or -1 after reserving the table cell for the row about to be appended
+        int32_t find_or_reserve(const PosKey& k) {
+            const size_t mask = table.size() - 1;
+            size_t h = PosKeyHash()(k) & mask;
+            while (table[h]) {
+                if (keys[table[h] - 1] == k) return static_cast<int32_t>(table[h] - 1);
+                h = (h + 1) & mask;
+            }
+            table[h] = static_cast<uint32_t>(keys.size()) + 1;
+            used.push_back(static_cast<uint32_t>(h));
+            return -1;
+        }
         void clear() {
             planes.clear();
             keys.clear();
             n_legal.clear();
-            waiters.clear();
-            index.clear();
+            parked.clear();
+            for (uint32_t h : used) table[h] = 0;
+            used.clear();
         }
+    };
+    struct Counters {
+        uint64_t simulations = 0, searches = 0, evaluations = 0, cache_hits = 0, cache_misses = 0, batches = 0, terminal = 0;
+        uint32_t w1 = 0, w2 = 0, d = 0, games = 0;
     };
 
   public:
@@ -443,6 +509,9 @@ class Worker {
         evals_[0] = evals[0];
         evals_[1] = evals[1];
         slots_.resize(std::max<uint32_t>(1, cfg.games_per_thread));
+        pending_[0].init(slots_.size());
+        pending_[1].init(slots_.size());
+        val_.resize(static_cast<size_t>(R.moves_num()) + 1);
         abi_wpp_ = (R.moves_num() + 63) / 64;
     }
 
@@ -475,6 +544,17 @@ class Worker {
         }
         std::lock_guard<std::mutex> g(sh_.mu);
         sh_.eval_wait += eval_wait_;
+        sh_.simulations += c_.simulations;
+        sh_.searches += c_.searches;
+        sh_.evaluations += c_.evaluations;
+        sh_.cache_hits += c_.cache_hits;
+        sh_.cache_misses += c_.cache_misses;
+        sh_.batches += c_.batches;
+        sh_.terminal += c_.terminal;
+        sh_.w1 += c_.w1;
+        sh_.w2 += c_.w2;
+        sh_.d += c_.d;
+        sh_.games += c_.games;
     }
 
   private:
@@ -544,12 +624,12 @@ class Worker {
         uint8_t credited = winner;
         if (credited && s.game_idx % 2 == 1) credited = static_cast<uint8_t>(3 - credited);
         if (credited == 0)
-            sh_.d.fetch_add(1);
+            c_.d += 1;
         else if (credited == 1)
-            sh_.w1.fetch_add(1);
+            c_.w1 += 1;
         else
-            sh_.w2.fetch_add(1);
-        sh_.games.fetch_add(1);
+            c_.w2 += 1;
+        c_.games += 1;
         if (cfg_.keep_records) {
             std::lock_guard<std::mutex> g(sh_.mu);
             sh_.records.push_back(std::move(s.rec));
@@ -744,7 +824,7 @@ class Worker {
         const Pos& leaf_pos = t.nodes[node].pos;
         const int st = R.status(leaf_pos);
         if (st != 0) {
-            sh_.terminal.fetch_add(1, std::memory_order_relaxed);
+            c_.terminal += 1;
             backpropagate(s, t, st == 3 ? 0.0f : (st == 1 ? 1.0f : -1.0f));
             return true;
         }
@@ -753,34 +833,33 @@ class Worker {
         s.leaf_eval_pos = s.leaf_flipped ? R.flipped(leaf_pos) : leaf_pos;
         Evaluator& ev = *evals_[s.cur];
         const PosKey key = R.key(s.leaf_eval_pos);
-        if (ev.cache) {
-            if (CacheVal v = ev.cache->find(key)) {
-                sh_.cache_hits.fetch_add(1, std::memory_order_relaxed);
-                deliver(s, *v);
-                return true;
-            }
+        const int n_legal = popcount128(R.legal_mask(s.leaf_eval_pos));
+        if (ev.cache && ev.cache->find(key, n_legal, val_.data())) {
+            c_.cache_hits += 1;
+            deliver(s, val_.data());
+            return true;
         }
         Pending& pb = pending_[evals_[0] == evals_[1] ? 0 : s.cur];
-        auto it = pb.index.find(key);
-        if (it != pb.index.end()) {
-            pb.waiters[it->second].push_back(si);
+        const int32_t row = pb.find_or_reserve(key);
+        if (row >= 0) {
+            s.wait_row = static_cast<uint32_t>(row);
+            if (ev.cache) c_.cache_hits += 1;  // the reference would find it cached by the time it computed it
         } else {
-            const uint32_t row = static_cast<uint32_t>(pb.keys.size());
-            pb.index.emplace(key, row);
+            s.wait_row = static_cast<uint32_t>(pb.keys.size());
             pb.keys.push_back(key);
             u128 pl[3];
             R.planes(s.leaf_eval_pos, pl);
             for (int c = 0; c < 3; ++c)
                 for (int k = 0; k < abi_wpp_; ++k) pb.planes.push_back(static_cast<uint64_t>(pl[c] >> (64 * k)));
-            pb.n_legal.push_back(static_cast<uint8_t>(popcount128(R.legal_mask(s.leaf_eval_pos))));
-            pb.waiters.emplace_back(1, si);
+            pb.n_legal.push_back(static_cast<uint8_t>(n_legal));
         }
+        pb.parked.push_back(si);
         s.phase = kWaitEval;
         return false;
     }
 
     // create_children + root noise + backpropagate for a leaf whose evaluation is known (mod.rs:180-194, :246-262)
-    void deliver(Slot& s, const std::vector<float>& val) {
+    void deliver(Slot& s, const float* val) {
         Tree<Pos>& t = s.players[s.cur].tree;
         const int32_t leaf = s.leaf;
         u128 legal = R.legal_mask(s.leaf_eval_pos);
@@ -815,7 +894,7 @@ class Worker {
             e.score_w += turn == 1 ? score : -score;
         }
         s.sims_left -= 1;
-        sh_.simulations.fetch_add(1, std::memory_order_relaxed);
+        c_.simulations += 1;
     }
     // source node of the i-th edge on the path: the root for i = 0, else the child of the previous edge
     int32_t path_nodes_at(const Slot& s, const Tree<Pos>& t, size_t i) const { return i == 0 ? t.root : t.edges[s.path[i - 1]].child; }
@@ -839,7 +918,7 @@ class Worker {
             std::lock_guard<std::mutex> g(sh_.mu);  // RunningAverage(0.99), util/metric.rs:1-20
             sh_.search_duration = (1.0 - 0.99) * sh_.search_duration + 0.99 * secs;
         }
-        sh_.searches.fetch_add(1, std::memory_order_relaxed);
+        c_.searches += 1;
         if (probs.empty()) throw SpError{CATTUS_B200_EINVAL, "search produced no moves"};
         // choose_move_from_probabilities
         const float temperature = P.temperature_at(s.history.size() / 2);
@@ -898,27 +977,28 @@ class Worker {
         }
         eval_wait_ += std::chrono::duration<double>(Clock::now() - t0).count();
         if (rc != 0) throw SpError{rc, std::string("evaluator failed: ") + cattus_b200_last_error()};
-        sh_.batches.fetch_add(1, std::memory_order_relaxed);
-        sh_.evaluations.fetch_add(n, std::memory_order_relaxed);
+        c_.batches += 1;
+        c_.evaluations += n;
+        // rows -> (probs..., value), through the cache (cache.rs:44-73)
+        const size_t stride = val_.size();
+        rows_.resize(static_cast<size_t>(n) * stride);
         for (uint32_t r = 0; r < n; ++r) {
-            if (offsets_[r + 1] - offsets_[r] != pb.n_legal[r]) throw SpError{CATTUS_B200_EINVAL, "evaluator returned a wrong number of probabilities"};
-            auto v = std::make_shared<std::vector<float>>(probs_.begin() + offsets_[r], probs_.begin() + offsets_[r + 1]);
-            v->push_back(values_[r]);
-            CacheVal use = v;
+            const uint32_t cnt = pb.n_legal[r];
+            if (offsets_[r + 1] - offsets_[r] != cnt) throw SpError{CATTUS_B200_EINVAL, "evaluator returned a wrong number of probabilities"};
+            float* v = rows_.data() + r * stride;
+            std::memcpy(v, probs_.data() + offsets_[r], sizeof(float) * cnt);
+            v[cnt] = values_[r];
             if (ev.cache) {
-                bool inserted = false;
-                use = ev.cache->insert(pb.keys[r], v, &inserted);
-                if (inserted)
-                    sh_.cache_misses.fetch_add(1, std::memory_order_relaxed);
+                if (ev.cache->insert(pb.keys[r], static_cast<int>(cnt), v))
+                    c_.cache_misses += 1;
                 else
-                    sh_.cache_hits.fetch_add(1, std::memory_order_relaxed);
-                if (pb.waiters[r].size() > 1) sh_.cache_hits.fetch_add(pb.waiters[r].size() - 1, std::memory_order_relaxed);
+                    c_.cache_hits += 1;
             }
-            for (uint32_t si : pb.waiters[r]) {
-                Slot& s = slots_[si];
-                deliver(s, *use);
-                s.phase = kSimulate;
-            }
+        }
+        for (uint32_t si : pb.parked) {
+            Slot& s = slots_[si];
+            deliver(s, rows_.data() + s.wait_row * stride);
+            s.phase = kSimulate;
         }
         pb.clear();
     }
@@ -933,7 +1013,8 @@ class Worker {
     int abi_wpp_ = 1;
     double eval_wait_ = 0.0;
     std::vector<double> noise_;
-    std::vector<float> weights_, probs_, values_;
+    std::vector<float> weights_, probs_, values_, val_, rows_;
+    Counters c_;
     std::vector<uint32_t> offsets_;
 };
 
@@ -993,9 +1074,15 @@ static int selfplay_impl(sp::Evaluator& e1, sp::Evaluator* e2_or_null, const cat
             if (!(p.last_temperature >= 0.0f)) throw sp::SpError{CATTUS_B200_EINVAL, "negative temperature"};
         }
         sp::Params params[2] = {p, p};
+        if (cfg->game == CATTUS_B200_GAME_HEX) {
+            if (cfg->board_size < 2 || cfg->board_size > 11) throw sp::SpError{CATTUS_B200_EINVAL, "hex board_size must be 2..11"};
+        } else if (cfg->game != CATTUS_B200_GAME_TTT) {
+            throw sp::SpError{CATTUS_B200_EINVAL, "the self-play driver covers hex and tictactoe (chess move generation is the third-party crate `chess`)"};
+        }
         if (cfg->cache_size) {
-            e1.cache.reset(new sp::Cache(cfg->cache_size));
-            if (e2_or_null) e2_or_null->cache.reset(new sp::Cache(cfg->cache_size));
+            const int moves_num = cfg->game == CATTUS_B200_GAME_TTT ? 9 : static_cast<int>(cfg->board_size * cfg->board_size);
+            e1.cache.reset(new sp::Cache(cfg->cache_size, moves_num));
+            if (e2_or_null) e2_or_null->cache.reset(new sp::Cache(cfg->cache_size, moves_num));
         }
         sp::Evaluator* evals[2] = {&e1, e2_or_null ? e2_or_null : &e1};
         if (cfg->out_dir1) {
@@ -1005,14 +1092,11 @@ static int selfplay_impl(sp::Evaluator& e1, sp::Evaluator* e2_or_null, const cat
         sp::Shared sh;
         const auto t0 = sp::Clock::now();
         if (cfg->game == CATTUS_B200_GAME_HEX) {
-            if (cfg->board_size < 2 || cfg->board_size > 11) throw sp::SpError{CATTUS_B200_EINVAL, "hex board_size must be 2..11"};
             sp::HexRules rules(static_cast<int>(cfg->board_size));
             run_games(rules, *cfg, params, evals, sh);
-        } else if (cfg->game == CATTUS_B200_GAME_TTT) {
+        } else {
             sp::TttRules rules;
             run_games(rules, *cfg, params, evals, sh);
-        } else {
-            throw sp::SpError{CATTUS_B200_EINVAL, "the self-play driver covers hex and tictactoe (chess move generation is the third-party crate `chess`)"};
         }
         if (sh.failed.load()) throw sp::SpError{sh.error_code, sh.error};
         std::unique_ptr<cattus_b200_selfplay> r(new cattus_b200_selfplay());

@@ -1,0 +1,297 @@
+// trunk_small: the whole conv trunk of a 16-filter ConvNetV1 (stem + R residual blocks, training/cattus_train/
+// net_utils.py:60-65, :23-42) PLUS the two 1x1 head convolutions (net_utils.py:69, :79) and the board -> feature-plane
+// encoding of its input (engine/src/net/mod.rs:121-156) in ONE launch, for any board size 3..11 (tic-tac-toe, hex4..11,
+// chess_dev).  This is every shipped training configuration (residual_filter_num: 16); the 128-filter chess net has its
+// own kernel (trunk_fused.cuh).
+//
+// With 16 filters all weights of the net's convolutions fit in shared memory (1 + 2R layers x 9 taps x 512 B = 69 KB
+// for R = 7), so nothing streams: weights are copied in once per CTA, activations live in shared memory as bf16 for the
+// whole trunk, packed bitboards come in and the two head-conv outputs go out.
+//
+// Geometry.  A CTA owns `boards_per_round` boards per round, laid out in shared memory as ONE 1-D strip of 16-byte
+// cells (8 channels each) per 8-channel plane: every board row of S cells is followed by one zero cell, every board by
+// one zero row, so with row pitch W = S + 1 and board pitch BP = W * W the cell of (board b, y, x) is
+// q = b * BP + y * W + x, and the input of tap (dy, dx) for output cell q is simply cell q + dy * W + dx -- all
+// "same"-padding zeros are real zero cells of the strip.  The strip is cut into T tiles of 128 consecutive cells; one
+// tcgen05.mma covers M = 128 cells x N = 16 output channels x K = 16 input channels, its A operand being the strip
+// itself (K-major, no swizzle: 8 consecutive cells = one core-matrix row group, SBO = 128 B, LBO = plane size) with the
+// start address moved by (dy * W + dx) * 16 bytes.  No im2col, no per-tap copies.  Pad cells are computed too (and
+// forced back to zero by the epilogue): useful fraction S^2 / (S + 1)^2.
+//
+// Tiles are not independent (a tile's halo lies in its neighbours), so the layers run in lock step over the CTA's
+// tiles, pipelined: MMA(l + 1, t) needs the epilogues of (l, t - 1), (l, t), (l, t + 1); while the tensor core works
+// on the later tiles of layer l the epilogue warps are already draining its first tiles.  Accumulators are
+// double-buffered in TMEM by layer parity (16 columns per tile and parity), the head convolution has its own columns.
+//
+// Warps: 0..7 encode + epilogue (TMEM lane quarter = warp & 3, tiles of parity warp >> 2), warp 8 issues the MMAs
+// (whole warp runs the loop so descriptors stay in uniform registers, one elected lane issues) and owns TMEM.
+#pragma once
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+namespace cb2 {
+
+constexpr int kTsThreads = 288;
+constexpr int kTsMaxTiles = 8;
+constexpr int kTsTapBytes = 2 * 16 * 16;  // [k-half 2][oc 16][ic 8] bf16
+
+struct TrunkSmallParams {
+    const uint8_t* recs;      // packed records (planes first)
+    const uint32_t* n_ptr;    // number of valid positions
+    const uint4* wimg;        // weight image, see Engine::upload_weights
+    const float* bias;        // [layers][16] folded-BN bias, then [nh] head bias (value channels first)
+    __nv_bfloat16* out_v;     // [positions * S^2][vhp]  ReLU(value head conv)
+    __nv_bfloat16* out_p;     // [positions * S^2][php]  ReLU(policy head conv)
+    uint32_t* err;
+    int rec_bytes, planes, wpp, s;
+    int layers;   // 1 + 2R
+    int stem_kc;  // 16-channel k-chunks of the stem input: ceil(C_in / 16) (1 or 2)
+    int vhp, php; // padded head widths, vhp + php <= 32
+    int tiles;    // T in {1, 2, 4, 8}
+    int boards_per_round;
+    int num_rounds;
+    int w_bytes;  // bytes of wimg (multiple of 16)
+    int margin;   // zero cells before / after the strip, >= S + 2, multiple of 8
+};
+
+// byte offsets inside dynamic shared memory
+struct TsSmemLayout {
+    int plane_bytes, p_off, q_off, w_off, bar_off, total;
+};
+__host__ __device__ inline TsSmemLayout ts_smem_layout(int tiles, int stem_kc, int margin, int w_bytes) {
+    TsSmemLayout L;
+    L.plane_bytes = (tiles * 128 + 2 * margin) * 16;
+    const int p_planes = 2 * (stem_kc > 1 ? stem_kc : 1);
+    L.p_off = 0;
+    L.q_off = L.p_off + p_planes * L.plane_bytes;
+    L.w_off = (L.q_off + 2 * L.plane_bytes + 127) / 128 * 128;
+    L.bar_off = (L.w_off + w_bytes + 15) / 16 * 16;
+    L.total = L.bar_off + (2 * kTsMaxTiles) * 8 + 16 + 128;
+    return L;
+}
+
+__global__ void __launch_bounds__(kTsThreads, 1) trunk_small_kernel(const __grid_constant__ TrunkSmallParams p) {
+    extern __shared__ uint8_t ts_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ts_smem_raw) + 127) & ~static_cast<uintptr_t>(127));
+    const TsSmemLayout L = ts_smem_layout(p.tiles, p.stem_kc, p.margin, p.w_bytes);
+    uint8_t* bufP = smem + L.p_off;
+    uint8_t* bufQ = smem + L.q_off;
+    uint8_t* wsm = smem + L.w_off;
+    uint64_t* ready = reinterpret_cast<uint64_t*>(smem + L.bar_off);  // [tile]: inputs of the next layer are written
+    uint64_t* acc_full = ready + kTsMaxTiles;                          // [tile]: accumulator of the current layer is complete
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_full + kTsMaxTiles);
+
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    const int T = p.tiles;
+    const int W = p.s + 1;
+    const int BP = W * W;
+    const int n_valid = static_cast<int>(*p.n_ptr);
+    const int nh = p.vhp + p.php;
+    const uint32_t tmem_cols = static_cast<uint32_t>(64 * T);
+
+    // ---- one-time setup: zero both activation buffers (margins and pads stay zero), weights -> smem, barriers, TMEM
+    for (int i = threadIdx.x; i < L.w_off / 16; i += kTsThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < p.w_bytes / 16; i += kTsThreads) reinterpret_cast<uint4*>(wsm)[i] = __ldg(p.wimg + i);
+    if (warp == 0 && lane == 0) {
+        for (int t = 0; t < kTsMaxTiles; ++t) {
+            ptx::mbar_init(&ready[t], 4);  // the four quarter-warps of the tile
+            ptx::mbar_init(&acc_full[t], 1);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 8) {
+        ptx::tmem_alloc(tmem_ptr, tmem_cols);
+        ptx::tmem_relinquish();
+    }
+    ptx::fence_proxy_async_smem();
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t head_col0 = static_cast<uint32_t>(32 * T);
+
+    if (warp == 8) {
+        // ================================================================== MMA issuer
+        const uint32_t idesc = ptx::umma_idesc_bf16(128, 16);
+        const uint32_t idesc_head = ptx::umma_idesc_bf16(128, static_cast<uint32_t>(nh));
+        const uint64_t a_hi64 = ptx::umma_desc_none_hi(static_cast<uint32_t>(L.plane_bytes), 128);
+        const uint64_t b_hi64 = ptx::umma_desc_none_hi(16 * 16, 128);
+        const uint64_t bh_hi64 = ptx::umma_desc_none_hi(static_cast<uint32_t>(nh) * 16, 128);
+        const uint32_t a_hi = static_cast<uint32_t>(a_hi64 >> 32), a_lo_fixed = static_cast<uint32_t>(a_hi64);
+        const uint32_t b_hi = static_cast<uint32_t>(b_hi64 >> 32), b_lo_fixed = static_cast<uint32_t>(b_hi64);
+        const uint32_t bh_hi = static_cast<uint32_t>(bh_hi64 >> 32), bh_lo_fixed = static_cast<uint32_t>(bh_hi64);
+        const uint32_t p_addr = ptx::smem_u32(bufP) + static_cast<uint32_t>(p.margin) * 16;
+        const uint32_t q_addr = ptx::smem_u32(bufQ) + static_cast<uint32_t>(p.margin) * 16;
+        const uint32_t w_addr = ptx::smem_u32(wsm);
+        const bool leader_lane = ptx::elect_one();
+        for (int rd = blockIdx.x; rd < p.num_rounds; rd += gridDim.x) {
+            uint32_t w_off = 0;
+            for (int l = 0; l <= p.layers; ++l) {
+                const bool head = l == p.layers;
+                const int nkc = l == 0 ? p.stem_kc : 1;
+                const uint32_t in_addr = (l & 1) ? q_addr : p_addr;  // stem and conv2 read P, conv1 and the heads read Q
+                const uint32_t par = static_cast<uint32_t>(l & 1);   // (layers + 1) is even: stage parity = l & 1 in every round
+                for (int t = 0; t < T; ++t) {
+                    if (t == 0) ptx::mbar_wait(&ready[0], par, p.err, 0x5100);
+                    if (t + 1 < T) ptx::mbar_wait(&ready[t + 1], par, p.err, 0x5101 + t);
+                    ptx::tc_fence_after();
+                    const uint32_t a_lo0 = a_lo_fixed | ((in_addr + static_cast<uint32_t>(t) * 2048u) >> 4);
+                    if (head) {
+                        const uint32_t d = tmem_base + head_col0 + static_cast<uint32_t>(t * 32);
+                        if (leader_lane) {
+                            ptx::umma_bf16_ss_lohi(d, a_lo0, a_hi, bh_lo_fixed | ((w_addr + w_off) >> 4), bh_hi, idesc_head, 0u);
+                            ptx::umma_commit(&acc_full[t]);
+                        }
+                    } else {
+                        const uint32_t d = tmem_base + static_cast<uint32_t>((par * T + t) * 16);
+                        if (leader_lane) {
+                            for (int kc = 0; kc < nkc; ++kc) {
+                                const uint32_t a_kc = a_lo0 + static_cast<uint32_t>(kc * 2 * (L.plane_bytes >> 4));
+                                const uint32_t b_lo0 = b_lo_fixed | ((w_addr + w_off + static_cast<uint32_t>(kc * 9 * kTsTapBytes)) >> 4);
+#pragma unroll
+                                for (int tap = 0; tap < 9; ++tap) {
+                                    const int shift16 = (tap / 3 - 1) * W + (tap % 3 - 1);  // in 16-byte cells
+                                    ptx::umma_bf16_ss_lohi(d, a_kc + shift16, a_hi, b_lo0 + tap * (kTsTapBytes / 16), b_hi, idesc, (kc | tap) != 0);
+                                }
+                            }
+                            ptx::umma_commit(&acc_full[t]);
+                        }
+                    }
+                    __syncwarp();
+                }
+                w_off += head ? 0u : static_cast<uint32_t>(nkc * 9 * kTsTapBytes);
+            }
+        }
+    } else {
+        // ================================================================== encode + epilogue
+        const uint32_t q4 = warp & 3;  // TMEM lane quarter this warp may access
+        const int half = static_cast<int>(warp >> 2);
+        const int r = static_cast<int>(q4 * 32 + lane);
+        const int s2 = p.s * p.s;
+        for (int rd = blockIdx.x; rd < p.num_rounds; rd += gridDim.x) {
+            const int board0 = rd * p.boards_per_round;
+            // ---- planes_to_tensor into the stem input (buffer P), zeros on pads / beyond the batch
+            for (int t = half; t < T; t += 2) {
+                const int q = t * 128 + r;
+                const int bl = q / BP, rem = q - bl * BP;
+                const int y = rem / W, x = rem - y * W;
+                const int board = board0 + bl;
+                const bool valid = bl < p.boards_per_round && y < p.s && x < p.s && board < n_valid;
+                uint8_t* dst = bufP + (p.margin + q) * 16;
+                const uint64_t* pl = reinterpret_cast<const uint64_t*>(p.recs + static_cast<size_t>(valid ? board : 0) * p.rec_bytes);
+                const int cell = y * p.s + x;
+                for (int c8 = 0; c8 < 2 * p.stem_kc; ++c8) {
+                    uint32_t w[4] = {0, 0, 0, 0};
+                    if (valid) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int c = c8 * 8 + j;
+                            if (c < p.planes && plane_bit(pl, p.wpp, c, cell)) w[j >> 1] |= (j & 1) ? 0x3F800000u : 0x00003F80u;  // bf16 1.0
+                        }
+                    }
+                    *reinterpret_cast<uint4*>(dst + c8 * L.plane_bytes) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+                ptx::tc_fence_before();  // my earlier tcgen05.ld of this tile's accumulators precede the MMAs that overwrite them
+                ptx::fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&ready[t]);
+            }
+            for (int l = 0; l <= p.layers; ++l) {
+                const bool head = l == p.layers;
+                const uint32_t par = static_cast<uint32_t>(l & 1);
+                const bool has_resid = l >= 2 && par == 0;  // conv2 of a block: + block input (Q), result back into Q
+                uint8_t* outb = par ? bufP : bufQ;          // stem -> Q, conv1 -> P, conv2 -> Q
+                const float4* bias4 = reinterpret_cast<const float4*>(p.bias + l * 16);
+                for (int t = half; t < T; t += 2) {
+                    const int q = t * 128 + r;
+                    const int bl = q / BP, rem = q - bl * BP;
+                    const int y = rem / W, x = rem - y * W;
+                    const int board = board0 + bl;
+                    const bool valid = bl < p.boards_per_round && y < p.s && x < p.s && board < n_valid;
+                    ptx::mbar_wait(&acc_full[t], par, p.err, 0x6100 + t);
+                    ptx::tc_fence_after();
+                    const uint32_t lane_addr = tmem_base + ((q4 * 32u) << 16);
+                    if (!head) {
+                        uint32_t raw[16];
+                        ptx::tmem_ld_x16_issue(lane_addr + static_cast<uint32_t>((par * T + t) * 16), raw);
+                        float4 bc[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) bc[i] = __ldg(bias4 + i);
+                        uint8_t* cellp = outb + (p.margin + q) * 16;
+                        uint4 r0 = make_uint4(0, 0, 0, 0), r1 = make_uint4(0, 0, 0, 0);
+                        if (has_resid) {
+                            r0 = *reinterpret_cast<const uint4*>(cellp);
+                            r1 = *reinterpret_cast<const uint4*>(cellp + L.plane_bytes);
+                        }
+                        ptx::tmem_ld_wait(raw);
+                        float v[16];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            v[4 * i + 0] = __uint_as_float(raw[4 * i + 0]) + bc[i].x;
+                            v[4 * i + 1] = __uint_as_float(raw[4 * i + 1]) + bc[i].y;
+                            v[4 * i + 2] = __uint_as_float(raw[4 * i + 2]) + bc[i].z;
+                            v[4 * i + 3] = __uint_as_float(raw[4 * i + 3]) + bc[i].w;
+                        }
+                        if (has_resid) {
+                            const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[i]);
+                                v[2 * i + 0] += __bfloat162float(b2.x);
+                                v[2 * i + 1] += __bfloat162float(b2.y);
+                            }
+                        }
+                        uint32_t o[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const __nv_bfloat162 b2 = __floats2bfloat162_rn(fmaxf(v[2 * i], 0.0f), fmaxf(v[2 * i + 1], 0.0f));
+                            o[i] = valid ? *reinterpret_cast<const uint32_t*>(&b2) : 0u;  // pad cells must stay zero
+                        }
+                        *reinterpret_cast<uint4*>(cellp) = make_uint4(o[0], o[1], o[2], o[3]);
+                        *reinterpret_cast<uint4*>(cellp + L.plane_bytes) = make_uint4(o[4], o[5], o[6], o[7]);
+                        ptx::tc_fence_before();
+                        ptx::fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive(&ready[t]);
+                    } else {
+                        // ---- both 1x1 head convolutions: columns [0, vhp) value, [vhp, vhp + php) policy
+                        const float4* hb4 = reinterpret_cast<const float4*>(p.bias + p.layers * 16);
+                        const size_t row = static_cast<size_t>(board) * s2 + (y * p.s + x);
+                        for (int cb = 0; cb < nh; cb += 16) {
+                            uint32_t raw[16];
+                            ptx::tmem_ld_x16_issue(lane_addr + head_col0 + static_cast<uint32_t>(t * 32 + cb), raw);
+                            float4 bc[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) bc[i] = __ldg(hb4 + cb / 4 + i);
+                            ptx::tmem_ld_wait(raw);
+                            uint32_t o[8];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float v0 = fmaxf(__uint_as_float(raw[4 * i + 0]) + bc[i].x, 0.0f), v1 = fmaxf(__uint_as_float(raw[4 * i + 1]) + bc[i].y, 0.0f);
+                                const float v2 = fmaxf(__uint_as_float(raw[4 * i + 2]) + bc[i].z, 0.0f), v3 = fmaxf(__uint_as_float(raw[4 * i + 3]) + bc[i].w, 0.0f);
+                                const __nv_bfloat162 a = __floats2bfloat162_rn(v0, v1), b = __floats2bfloat162_rn(v2, v3);
+                                o[2 * i] = *reinterpret_cast<const uint32_t*>(&a);
+                                o[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&b);
+                            }
+                            if (valid) {
+                                // 16-column block cb lies entirely in the value part or entirely in the policy part (vhp % 16 == 0)
+                                uint4* og = cb < p.vhp ? reinterpret_cast<uint4*>(p.out_v + row * p.vhp + cb) : reinterpret_cast<uint4*>(p.out_p + row * p.php + (cb - p.vhp));
+                                og[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                                og[1] = make_uint4(o[4], o[5], o[6], o[7]);
+                            }
+                        }
+                        ptx::tc_fence_before();
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- teardown
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 8) ptx::tmem_dealloc(tmem_base, tmem_cols);
+}
+
+}  // namespace cb2

@@ -61,6 +61,7 @@ class CudaNetwork:
         self.max_batch = info.max_batch
         self.needs_bitmap = game == "chess"
         self.fused_trunk = bool(info.reserved & 1)
+        self.small_trunk = bool(info.reserved & 2)
 
     # ------------------------------------------------------------------ lifetime
     def close(self):

@@ -199,6 +199,30 @@ def test_fused_trunk_matches_per_layer_path_and_oracle(name, n, batch):
     assert d_paths <= TOL_BF16 and worst <= TOL_BF16 and worst_v <= TOL_BF16
 
 
+@pytest.mark.parametrize("name", ["ttt", "hex4", "hex5", "hex7", "hex9", "hex11", "chess_dev"])
+@pytest.mark.parametrize("n,batch", [(3, 4), (90, 128), (700, 1024), (5000, 4096)])
+def test_small_trunk_matches_per_layer_path_and_oracle(name, n, batch):
+    """The 16-filter whole-trunk kernel (trunk_small.cuh: encode + stem + residual blocks + both head convs, strip
+    layout in shared memory) against the per-layer tcgen05 GEMM path and the oracle, at batch sizes that select every
+    tiles-per-CTA variant (1, 2, 4, 8) and more than one round per CTA."""
+    words, bitmaps, legal = synth_inputs(name, n, 515)
+    with make_network(name, batch_size=batch, fused_trunk=True) as a, make_network(name, batch_size=batch, fused_trunk=False) as b:
+        assert a.small_trunk and not b.small_trunk
+        assert a.info.kernels_per_batch < b.info.kernels_per_batch
+        pa, oa, va = a.eval_batch(words, bitmaps)
+        pb, ob, vb = b.eval_batch(words, bitmaps)
+        p1, _, v1 = a.eval_batch(words[:1], None if bitmaps is None else bitmaps[:1])
+    assert np.array_equal(oa, ob)
+    assert np.array_equal(p1, pa[oa[0]:oa[1]]) and v1[0] == va[0]  # batch invariant across tile variants
+    d_paths = max(float(np.abs(pa - pb).max()), float(np.abs(va - vb).max()))
+    idx = np.linspace(0, n - 1, min(n, 40)).astype(int)
+    _, o_values, o_probs = oracle_eval(name, words[idx], [legal[i] for i in idx])
+    worst = max([float(np.abs(pa[oa[i]:oa[i + 1]] - o_probs[k]).max()) for k, i in enumerate(idx) if len(legal[i])] + [0.0])
+    worst_v = float(np.abs(va[idx] - o_values).max())
+    print(f"{name} n={n}: small-trunk vs per-layer {d_paths:.3e}; vs oracle prob {worst:.3e} value {worst_v:.3e}")
+    assert d_paths <= TOL_BF16 and worst <= TOL_BF16 and worst_v <= TOL_BF16
+
+
 # ----------------------------------------------------------------------------------------------- batching semantics
 def test_per_leaf_eval_is_thread_safe_and_batch_invariant():
     """cattus_b200_eval from many threads (the Batcher replacement, util/batch.rs:49-177) must return exactly what the

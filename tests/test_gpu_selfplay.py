@@ -1,0 +1,74 @@
+"""GPU (-m gpu): self-play through the C ABI with the B200 evaluator.
+
+North-star contract: "given identical net outputs, MCTS move choices must be identical".  The C++ driver plays whole
+games with batched leaf evaluation on the GPU; the oracle's MctsPlayer (oracle/mcts.py, restating
+engine/src/mcts/mod.rs) replays the same games fed with the SAME network's outputs taken one leaf at a time through
+`cattus_b200_eval` -- the evaluator is batch invariant, so every move, visit distribution and .traindata byte must
+be identical.
+"""
+import numpy as np
+import pytest
+
+from cattus_b200.selfplay import SelfPlayRunner
+from oracle import games, mcts as om
+from tests.test_selfplay_cpu import cfg_with, oracle_games
+from tests.util import make_network
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_net_fn(nw, s: int):
+    wpp = (s * s + 63) // 64
+
+    def net(a: int, b: int, ones: int):
+        words = games.pack_planes([[a, b, ones]], s).reshape(-1)
+        assert len(words) == 3 * wpp
+        probs, value = nw.eval_planes(words)
+        return np.asarray(probs, dtype=np.float32), np.float32(value)
+
+    return net
+
+
+@pytest.mark.parametrize("name,sim_num,games_num", [("hex4", 60, 4), ("hex5", 50, 2), ("hex9", 16, 2), ("ttt", 40, 4)])
+def test_gpu_selfplay_move_choices_identical_to_oracle(name, sim_num, games_num):
+    cfg = cfg_with(sim_num=sim_num, cache_size=10000, prior_noise_alpha=0.3, prior_noise_epsilon=0.25,
+                   temperature_policy=[[4, 1.0], [9999, 0.0]], threads=2, games_per_thread=3, seed=77)
+    s = 3 if name == "ttt" else int(name[3:])
+    with make_network(name, batch_size=64) as nw:
+        summary, records = SelfPlayRunner(name, cfg).generate_data(nw, None, games_num, keep_records=True)
+        ref, _ = oracle_games(name, cfg, gpu_net_fn(nw, s), None, range(games_num))
+    for rec, o in zip(records, ref):
+        assert rec.moves == o.moves and rec.winner == o.winner
+        for k, (pos, probs) in enumerate(o.entries):
+            assert rec.entries[k] == om.data_entry_bytes(pos, probs, o.winner)
+    m = summary["metrics"]
+    assert m["selfplay.simulations"] == m["selfplay.searches"] * sim_num
+    assert m["selfplay.evaluations"] > 0 and m["model.activation_count"] > 0
+
+
+def test_gpu_selfplay_is_independent_of_scheduling():
+    base = dict(sim_num=80, cache_size=50000, prior_noise_alpha=0.03, prior_noise_epsilon=0.25, temperature_policy=[[10, 1.0], [9999, 0.0]], seed=3)
+    results = []
+    with make_network("hex5", batch_size=256, n_streams=3) as nw:
+        for threads, gpt, leaf_queue in ((1, 1, 0), (4, 16, 0), (2, 64, 0), (8, 1, 1)):
+            cfg = cfg_with(threads=threads, games_per_thread=gpt, leaf_queue=leaf_queue, **base)
+            summary, recs = SelfPlayRunner("hex5", cfg).generate_data(nw, None, 16, keep_records=True)
+            results.append([(r.game_idx, r.moves, r.winner, r.entries) for r in recs])
+            assert summary["player1_wins"] + summary["player2_wins"] == 16  # hex has no draws
+    for r in results[1:]:
+        assert r == results[0]
+
+
+def test_gpu_selfplay_two_models_and_files(tmp_path):
+    cfg = cfg_with(sim_num=40, cache_size=1000, threads=2, games_per_thread=4)
+    from cattus_b200 import CudaNetwork
+    from tests.util import blob
+
+    with make_network("hex4") as nw1, CudaNetwork(blob("hex4", 1), "hex", batch_size=64) as nw2:
+        summary, recs = SelfPlayRunner("hex4", cfg).generate_data(nw1, nw2, 8, tmp_path / "d1", tmp_path / "d2", keep_records=True)
+    assert summary["player1_wins"] + summary["player2_wins"] == 8
+    files = list((tmp_path / "d1").glob("*.traindata")) + list((tmp_path / "d2").glob("*.traindata"))
+    assert len(files) == sum(len(r.entries) for r in recs)
+    for r in recs:
+        for k, (e, d) in enumerate(zip(r.entries, r.entry_dirs)):
+            assert (tmp_path / f"d{d}" / f"{r.game_idx:08d}_{k:03d}.traindata").read_bytes() == e

@@ -1,0 +1,52 @@
+#!/usr/bin/env python
+"""Sweeps the self-play driver's threads x games_per_thread on one GPU and prints sims/s (exploration tool; the
+judged number comes from bench.py)."""
+from __future__ import annotations
+
+import argparse
+import json
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--game", default="hex5")
+    ap.add_argument("--sim-num", type=int, default=1400)
+    ap.add_argument("--games", type=int, default=256)
+    ap.add_argument("--threads", type=int, nargs="+", default=[16])
+    ap.add_argument("--gpt", type=int, nargs="+", default=[16])
+    ap.add_argument("--streams", type=int, default=4)
+    ap.add_argument("--cache", type=int, default=1000000)
+    ap.add_argument("--leaf-queue", type=int, default=0)
+    args = ap.parse_args()
+
+    from cattus_b200 import CudaNetwork
+    from cattus_b200.export import export_blob
+    from cattus_b200.selfplay import SelfPlayRunner
+    from oracle import net
+
+    cfg_net = net.CONFIGS[args.game]
+    blob = export_blob(net.make_state_dict(cfg_net, 0), cfg_net.game)
+    for th in args.threads:
+        for gpt in args.gpt:
+            with CudaNetwork(blob, cfg_net.game, batch_size=max(64, min(4096, gpt)), n_streams=args.streams) as nw:
+                cfg = {"mcts": {"sim_num": args.sim_num, "explore_factor": 1.41421, "temperature_policy": [[10, 1.0], [9999, 0.0]],
+                                "prior_noise_alpha": 0.03, "prior_noise_epsilon": 0.25, "cache_size": args.cache},
+                       "threads": th, "games_per_thread": gpt, "leaf_queue": args.leaf_queue, "seed": 1}
+                games = max(2, (args.games + 1) // 2 * 2)
+                summary, _ = SelfPlayRunner(args.game, cfg).generate_data(nw, None, games)
+                m = summary["metrics"]
+                print(json.dumps({"threads": th, "gpt": gpt, "games": games, "sims_per_sec": round(m["selfplay.sims_per_sec"]),
+                                  "seconds": round(m["selfplay.seconds"], 3), "evals": m["selfplay.evaluations"], "batches": m["model.activation_count"],
+                                  "mean_batch": round(m["selfplay.evaluations"] / max(1, m["model.activation_count"]), 1),
+                                  "hit_rate": round(m["cache.hits"] / max(1, m["cache.hits"] + m["cache.misses"]), 3),
+                                  "eval_wait_frac": round(m["selfplay.eval_wait_seconds"] / max(1e-9, m["selfplay.seconds"] * th), 3),
+                                  "p1": summary["player1_wins"], "p2": summary["player2_wins"]}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
