@@ -275,7 +275,9 @@ def main():
     clocks = sampler.stop()
     t_e2e = max_over_ranks(t_e2e_local)
     launches = nw.metrics()["model.kernel_launches"] - launches0
-    h2d = positions_per_step * (cfg.planes * ((cfg.board_size ** 2 + 63) // 64) * 8 + (((cfg.moves + 31) // 32 * 4 + 7) // 8 * 8 if bitmaps is not None else 0)) + 16 * per_step
+    # per position: 8-byte prefix (probability offset, #legal) + packed planes (+ the legal bitmap padded to 8 B for chess)
+    rec_bytes = 8 + cfg.planes * ((cfg.board_size ** 2 + 63) // 64) * 8 + (((cfg.moves + 31) // 32 * 4 + 7) // 8 * 8 if bitmaps is not None else 0)
+    h2d = positions_per_step * rec_bytes + 16 * per_step
     d2h = int(offsets[-1]) * 4 + positions_per_step * 4
     kernels_per_batch = nw.info.kernels_per_batch
     fused = bool(nw.info.reserved & 1)

@@ -13,6 +13,8 @@ namespace cb2 {
 
 static inline uint32_t round_up(uint32_t x, uint32_t m) { return (x + m - 1) / m * m; }
 static inline uint32_t ceil_div(uint32_t x, uint32_t m) { return (x + m - 1) / m; }
+static constexpr int kRecPrefix = 8;             // per-record [prob offset, #legal]
+static constexpr int kRecs0 = 16 + kRecPrefix;  // byte offset of record 0's planes inside a batch block
 
 // ------------------------------------------------------------------------------------------------ blob
 static constexpr uint32_t kBlobMagic = 0x00324243u;  // "CB2\0"
@@ -148,7 +150,9 @@ Engine::Engine(const cattus_b200_desc& desc, const void* blob_bytes, size_t blob
     rec_.legal_words = static_cast<int>(ceil_div(d_.moves, 32));
     const int plane_bytes = rec_.planes * rec_.wpp * 8;
     rec_.legal_off = derive_legal_ ? -1 : plane_bytes;
-    rec_.rec_bytes = plane_bytes + (derive_legal_ ? 0 : static_cast<int>(round_up(static_cast<uint32_t>(rec_.legal_words) * 4, 8)));
+    // each record is preceded by an 8-byte prefix [u32 offset of its probabilities in the compact output][u32 #legal]
+    // written by the host while packing (it counts the legal moves anyway), so no device-side count + scan is needed
+    rec_.rec_bytes = kRecPrefix + plane_bytes + (derive_legal_ ? 0 : static_cast<int>(round_up(static_cast<uint32_t>(rec_.legal_words) * 4, 8)));
 
     // bf16 layout constants
     cin_pad_ = round_up(d_.c_in, 64);
@@ -187,7 +191,7 @@ Engine::Engine(const cattus_b200_desc& desc, const void* blob_bytes, size_t blob
         init_lane(*lanes_.back());
     }
     lane_busy_.assign(n_streams, 0);
-    const size_t in_bytes = 16 + static_cast<size_t>(max_batch_) * rec_.rec_bytes;
+    const size_t in_bytes = kRecs0 + static_cast<size_t>(max_batch_) * rec_.rec_bytes;
     CB2_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&open_block_), in_bytes, cudaHostAllocDefault));
     std::memset(open_block_, 0, in_bytes);
     open_reqs_.reserve(max_batch_);
@@ -223,7 +227,7 @@ Engine::~Engine() {
         if (l.h_in) cudaFreeHost(l.h_in);
         if (l.h_values) cudaFreeHost(l.h_values);
         if (l.h_probs) cudaFreeHost(l.h_probs);
-        for (DeviceBuf* b : {&l.d_in, &l.d_values, &l.d_offsets, &l.d_probs, &l.d_x, &l.d_act[0], &l.d_act[1], &l.d_act[2], &l.d_hv,
+        for (DeviceBuf* b : {&l.d_in, &l.d_values, &l.d_probs, &l.d_x, &l.d_act[0], &l.d_act[1], &l.d_act[2], &l.d_hv,
                              &l.d_hp, &l.d_hidden, &l.d_logits, &l.d_dense})
             b->free_();
     }
@@ -242,6 +246,7 @@ Engine::~Engine() {
     fused_b_.free_();
     small_w_.free_();
     small_b_.free_();
+    trace_.free_();
     flush_.free_();
 }
 
@@ -392,14 +397,13 @@ void Engine::upload_weights(const Blob& blob) {
 void Engine::init_lane(Lane& l) {
     CB2_CUDA(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
     CB2_CUDA(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
-    const size_t in_bytes = 16 + static_cast<size_t>(max_batch_) * rec_.rec_bytes;
+    const size_t in_bytes = kRecs0 + static_cast<size_t>(max_batch_) * rec_.rec_bytes;
     CB2_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&l.h_in), in_bytes, cudaHostAllocDefault));
     std::memset(l.h_in, 0, in_bytes);
     CB2_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&l.h_values), sizeof(float) * max_batch_, cudaHostAllocDefault));
     CB2_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&l.h_probs), sizeof(float) * max_batch_ * d_.moves, cudaHostAllocDefault));
     l.d_in.alloc(in_bytes);
     l.d_values.alloc(sizeof(float) * max_batch_);
-    l.d_offsets.alloc(sizeof(uint32_t) * (max_batch_ + 1));
     l.d_probs.alloc(sizeof(float) * max_batch_ * d_.moves);
     const uint32_t s2 = d_.s2();
     l.d_dense.alloc(sizeof(float) * max_batch_ * d_.c_in * s2);
@@ -487,12 +491,12 @@ std::vector<Op>& Engine::ops_for(Lane& lane, uint32_t bucket, bool dense_input) 
     return lane.ops.emplace(key, std::move(ops)).first->second;
 }
 
-void Engine::add_tail_ops(Lane& lane, uint32_t bucket, std::vector<Op>& ops, bool dense_input) {
-    const uint8_t* recs = lane.d_in.as<uint8_t>() + 16;
+void Engine::add_tail_ops(Lane& lane, uint32_t bucket, std::vector<Op>& ops, bool dense_input, bool value_tail, bool policy_tail) {
+    const uint8_t* recs = lane.d_in.as<uint8_t>() + kRecs0;
     const uint32_t* n_ptr = lane.d_in.as<uint32_t>();
     const RecLayout L = rec_;
     const int ld_logits = precision_ == CATTUS_B200_PRECISION_FP32_CHECK ? static_cast<int>(d_.moves) : static_cast<int>(pfc_.n_umma * pfc_.n_tiles);
-    {
+    if (value_tail) {
         Op op;
         op.stage = 3;
         op.name = "value_tail";
@@ -504,33 +508,15 @@ void Engine::add_tail_ops(Lane& lane, uint32_t bucket, std::vector<Op>& ops, boo
         op.launch = [=](cudaStream_t st) { value_tail_kernel<<<blocks, 256, 0, st>>>(hidden, 128, w2, b2, n_ptr, values); };
         ops.push_back(op);
     }
-    if (dense_input) return;  // run_dense returns raw logits (Model::run semantics)
-    {
-        Op op;
-        op.stage = 3;
-        op.name = "legal_count";
-        uint32_t* offsets = lane.d_offsets.as<uint32_t>();
-        const int blocks = static_cast<int>(ceil_div(bucket * 32, 256));
-        op.launch = [=](cudaStream_t st) { legal_count_kernel<<<blocks, 256, 0, st>>>(recs, L, n_ptr, offsets); };
-        ops.push_back(op);
-    }
-    {
-        Op op;
-        op.stage = 3;
-        op.name = "legal_offsets";
-        uint32_t* offsets = lane.d_offsets.as<uint32_t>();
-        op.launch = [=](cudaStream_t st) { legal_offsets_kernel<<<1, 1024, 0, st>>>(n_ptr, offsets); };
-        ops.push_back(op);
-    }
+    if (dense_input || !policy_tail) return;  // run_dense returns raw logits (Model::run semantics)
     {
         Op op;
         op.stage = 3;
         op.name = "policy_tail";
         const float* logits = lane.d_logits.as<float>();
-        const uint32_t* offsets = lane.d_offsets.as<uint32_t>();
         float* probs = lane.d_probs.as<float>();
         const int blocks = static_cast<int>(ceil_div(bucket * 32, 256));
-        op.launch = [=](cudaStream_t st) { policy_tail_kernel<<<blocks, 256, 0, st>>>(logits, ld_logits, recs, L, n_ptr, offsets, probs); };
+        op.launch = [=](cudaStream_t st) { policy_tail_kernel<<<blocks, 256, 0, st>>>(logits, ld_logits, recs, L, n_ptr, probs); };
         ops.push_back(op);
     }
 }
@@ -538,7 +524,7 @@ void Engine::add_tail_ops(Lane& lane, uint32_t bucket, std::vector<Op>& ops, boo
 void Engine::build_ops_fp32(Lane& lane, uint32_t bucket, std::vector<Op>& ops, bool dense_input) {
     const int s = static_cast<int>(d_.s), s2 = static_cast<int>(d_.s2());
     const int n = static_cast<int>(bucket);
-    const uint8_t* recs = lane.d_in.as<uint8_t>() + 16;
+    const uint8_t* recs = lane.d_in.as<uint8_t>() + kRecs0;
     const uint32_t* n_ptr = lane.d_in.as<uint32_t>();
     const RecLayout L = rec_;
     const int sm = sm_count_;
@@ -590,7 +576,7 @@ void Engine::build_ops_fp32(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
     fc("value_fc1", lane.d_hv.as<float>(), vfc1_, lane.d_hidden.as<float>(), static_cast<int>(d_.vh) * s2, 128, 128, 1);
     fc("policy_fc", lane.d_hp.as<float>(), pfc_, lane.d_logits.as<float>(), static_cast<int>(d_.ph) * s2, static_cast<int>(d_.moves),
        static_cast<int>(d_.moves), 0);
-    add_tail_ops(lane, bucket, ops, dense_input);
+    add_tail_ops(lane, bucket, ops, dense_input, true, true);
 }
 
 void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, bool dense_input) {
@@ -598,7 +584,7 @@ void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
     const uint32_t tiles = ceil_div(bucket, nb_);
     const uint32_t boards = tiles * nb_;
     const uint32_t rows_total = boards * s2;
-    const uint8_t* recs = lane.d_in.as<uint8_t>() + 16;
+    const uint8_t* recs = lane.d_in.as<uint8_t>() + kRecs0;
     const uint32_t* n_ptr = lane.d_in.as<uint32_t>();
     const RecLayout L = rec_;
     const int sm = sm_count_;
@@ -671,6 +657,7 @@ void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
         p.out_f32 = out_f32 ? 1 : 0;
         p.relu = relu ? 1 : 0;
         p.tx_bytes = 128 * 128 + g.n_umma * 128;
+        last_tc_params_ = p;
         ops.push_back(make_tc_op(stage, name, p, ceil_div(static_cast<uint32_t>(rows), 128), g.n_tiles));
     };
     __nv_bfloat16* act[3] = {lane.d_act[0].as<__nv_bfloat16>(), lane.d_act[1].as<__nv_bfloat16>(), lane.d_act[2].as<__nv_bfloat16>()};
@@ -710,15 +697,36 @@ void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
         TrunkSmallParams sp;
         std::memset(&sp, 0, sizeof(sp));
         const int W = static_cast<int>(d_.s) + 1, BP = W * W;
-        // fewest tiles per CTA that still fit the batch on the SMs in one wave (small batches spread out for latency)
-        int T = kTsMaxTiles;
+        // Tiles per CTA (T) and tiles per independent group: the fewest tiles that still fit the batch on the SMs in
+        // one wave (small batches spread out for latency); groups of whole boards, preferring >= 2 groups so that one
+        // group's epilogue hides behind another group's MMAs.
+        auto plan = [&](int cand, int& tpg, int& per_group) {
+            double best = -1.0;
+            for (int g = 1; g <= cand; g *= 2) {
+                const int bpg = g * 128 / BP, groups = cand / g;
+                // single-tile groups keep only 2 accumulator chains in flight (MMA latency-bound): mild penalty
+                const double score = static_cast<double>(bpg) * groups * (groups >= 2 ? 1.0 : 0.6) * (g == 1 && cand > 1 ? 0.9 : 1.0);
+                if (bpg >= 1 && score > best) {
+                    best = score;
+                    tpg = g;
+                    per_group = bpg;
+                }
+            }
+            return best > 0.0;
+        };
+        int T = kTsMaxTiles, tpg = kTsMaxTiles, bpg = 0;
         for (int cand = 1; cand <= kTsMaxTiles; cand *= 2) {
-            const int nbr = cand * 128 / BP;
-            if (nbr >= 1 && static_cast<int>(ceil_div(bucket, static_cast<uint32_t>(nbr))) <= sm) {
+            int g = 0, b = 0;
+            if (!plan(cand, g, b)) continue;
+            const int per_round = b * (cand / g);
+            if (cand == kTsMaxTiles || static_cast<int>(ceil_div(bucket, static_cast<uint32_t>(per_round))) <= sm) {
                 T = cand;
+                tpg = g;
+                bpg = b;
                 break;
             }
         }
+        if (bpg == 0) throw Error(CATTUS_B200_EINVAL, "trunk_small: board does not fit a tile group");
         sp.recs = recs;
         sp.n_ptr = n_ptr;
         sp.wimg = small_w_.as<uint4>();
@@ -726,6 +734,10 @@ void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
         sp.out_v = lane.d_hv.as<__nv_bfloat16>();
         sp.out_p = lane.d_hp.as<__nv_bfloat16>();
         sp.err = d_err_;
+        if (std::getenv("CATTUS_B200_TRACE_TRUNK")) {  // diagnostic: per-layer clock64 trace of CTA 0, printed by time_stage
+            if (trace_.p == nullptr) trace_.alloc(512 * sizeof(unsigned long long));
+            sp.dbg = trace_.as<unsigned long long>();
+        }
         sp.rec_bytes = rec_.rec_bytes;
         sp.planes = static_cast<int>(d_.c_in);
         sp.wpp = rec_.wpp;
@@ -735,7 +747,9 @@ void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
         sp.vhp = static_cast<int>(vhp_);
         sp.php = static_cast<int>(php_);
         sp.tiles = T;
-        sp.boards_per_round = T * 128 / BP;
+        sp.group_tiles = tpg;
+        sp.boards_per_group = bpg;
+        sp.boards_per_round = bpg * (T / tpg);
         sp.num_rounds = static_cast<int>(ceil_div(bucket, static_cast<uint32_t>(sp.boards_per_round)));
         sp.w_bytes = static_cast<int>((small_stem_kc_ + 2 * d_.r) * 9 * kTsTapBytes + (vhp_ + php_) * 32);
         sp.margin = (W + 1 + 7) / 8 * 8;
@@ -761,11 +775,35 @@ void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
         gemm(2, "value_conv", act[cur], ca_, rows_total, ca_ * 2ull, vconv_, lane.d_hv.p, vhp_, false, true);
         gemm(2, "policy_conv", act[cur], ca_, rows_total, ca_ * 2ull, pconv_, lane.d_hp.p, php_, false, true);
     }
+    // Tails fused into the FC epilogues (flags bit 0 keeps the separate tail kernels as the independent comparison path):
+    // value: always (the 128 hidden units are one N tile); policy: when all moves fit one N tile (tic-tac-toe, hex).
+    const bool fuse_tails = (desc_.flags & 1u) == 0;
+    const bool fuse_policy = fuse_tails && !dense_input && pfc_.n_tiles == 1;
     gemm(2, "value_fc1", lane.d_hv.p, static_cast<uint64_t>(s2) * vhp_, bucket, static_cast<uint64_t>(s2) * vhp_ * 2, vfc1_, lane.d_hidden.p, 128,
          true, true);
+    if (fuse_tails) {
+        Op& op = ops.back();
+        TcGemmParams p = last_tc_params_;
+        p.epi = 1;
+        p.w2 = vfc2_w_.as<float>();
+        p.b2 = vfc2_b_;
+        p.values = lane.d_values.as<float>();
+        p.n_ptr = n_ptr;
+        op = make_tc_op(2, "value_fc1_tanh", p, ceil_div(bucket, 128), 1);
+    }
     gemm(2, "policy_fc", lane.d_hp.p, static_cast<uint64_t>(s2) * php_, bucket, static_cast<uint64_t>(s2) * php_ * 2, pfc_, lane.d_logits.p,
          pfc_.n_umma * pfc_.n_tiles, true, false);
-    add_tail_ops(lane, bucket, ops, dense_input);
+    if (fuse_policy) {
+        Op& op = ops.back();
+        TcGemmParams p = last_tc_params_;
+        p.epi = 2;
+        p.recs = recs;
+        p.rl = L;
+        p.probs = lane.d_probs.as<float>();
+        p.n_ptr = n_ptr;
+        op = make_tc_op(2, "policy_fc_softmax", p, ceil_div(bucket, 128), 1);
+    }
+    add_tail_ops(lane, bucket, ops, dense_input, !fuse_tails, !fuse_policy);
 }
 
 void Engine::run_bucket(Lane& lane, uint32_t bucket, cudaStream_t stream, bool use_graph, bool dense_input) {
@@ -801,7 +839,7 @@ void Engine::throw_device_error(const char* where, cudaError_t e) {
 }
 
 // ------------------------------------------------------------------------------------------------ batches
-uint32_t Engine::pack_record(uint8_t* dst, const uint64_t* planes, const uint8_t* legal) const {
+uint32_t Engine::pack_record(uint8_t* dst, const uint64_t* planes, const uint8_t* legal, uint32_t prob_offset) const {
     const int plane_bytes = rec_.planes * rec_.wpp * 8;
     std::memcpy(dst, planes, plane_bytes);
     uint32_t cnt = 0;
@@ -815,7 +853,7 @@ uint32_t Engine::pack_record(uint8_t* dst, const uint64_t* planes, const uint8_t
     } else {
         if (legal == nullptr) throw Error(CATTUS_B200_EINVAL, "this game needs an explicit legal-move bitmap");
         const int bm = static_cast<int>(d_.bitmap_bytes());
-        const int padded = rec_.rec_bytes - plane_bytes;
+        const int padded = rec_.rec_bytes - kRecPrefix - plane_bytes;
         uint8_t* d = dst + plane_bytes;
         std::memcpy(d, legal, bm);
         std::memset(d + bm, 0, padded - bm);
@@ -823,6 +861,9 @@ uint32_t Engine::pack_record(uint8_t* dst, const uint64_t* planes, const uint8_t
         const uint64_t* w = reinterpret_cast<const uint64_t*>(d);
         for (int k = 0; k < padded / 8; ++k) cnt += static_cast<uint32_t>(__builtin_popcountll(w[k]));
     }
+    uint32_t* prefix = reinterpret_cast<uint32_t*>(dst - kRecPrefix);
+    prefix[0] = prob_offset;
+    prefix[1] = cnt;
     return cnt;
 }
 
@@ -878,7 +919,7 @@ void Engine::eval_leaf(const uint64_t* planes, const uint8_t* legal, LeafRequest
     q_space_cv_.wait(g, [&] { return stopping_ || open_reqs_.size() < max_batch_; });
     if (stopping_) throw Error(CATTUS_B200_EINVAL, "evaluator is shutting down");
     const uint32_t slot = static_cast<uint32_t>(open_reqs_.size());
-    req->count = pack_record(open_block_ + 16 + static_cast<size_t>(slot) * rec_.rec_bytes, planes, legal);
+    req->count = pack_record(open_block_ + kRecs0 + static_cast<size_t>(slot) * rec_.rec_bytes, planes, legal, open_total_);
     if (req->count > req->probs_cap) throw Error(CATTUS_B200_ERANGE, "probs_cap is smaller than the number of legal moves");
     req->status = 1;
     open_reqs_.push_back(req);
@@ -991,8 +1032,8 @@ void Engine::eval_batch(const uint64_t* planes, const uint8_t* legal, uint32_t n
             try {
                 for (uint32_t i = 0; i < cn; ++i) {
                     const uint32_t b = first + i;
-                    const uint32_t c = pack_record(l.h_in + 16 + static_cast<size_t>(i) * rec_.rec_bytes, planes + b * plane_words,
-                                                   legal ? legal + b * bm : nullptr);
+                    const uint32_t c = pack_record(l.h_in + kRecs0 + static_cast<size_t>(i) * rec_.rec_bytes, planes + b * plane_words,
+                                                   legal ? legal + b * bm : nullptr, total);
                     prob_offsets[b] = static_cast<uint32_t>(prob_cursor + total);
                     total += c;
                 }
@@ -1026,14 +1067,14 @@ void Engine::encode(const uint64_t* planes, uint32_t n, uint32_t batch, float* n
     try {
         const size_t plane_bytes = static_cast<size_t>(rec_.planes) * rec_.wpp * 8;
         for (uint32_t i = 0; i < n; ++i) {
-            uint8_t* dst = l.h_in + 16 + static_cast<size_t>(i) * rec_.rec_bytes;
-            std::memset(dst, 0, rec_.rec_bytes);
+            uint8_t* dst = l.h_in + kRecs0 + static_cast<size_t>(i) * rec_.rec_bytes;
+            std::memset(dst - kRecPrefix, 0, rec_.rec_bytes);
             std::memcpy(dst, planes + i * (plane_bytes / 8), plane_bytes);
         }
         *reinterpret_cast<uint32_t*>(l.h_in) = n;
         CB2_CUDA(cudaMemcpyAsync(l.d_in.p, l.h_in, 16 + static_cast<size_t>(n) * rec_.rec_bytes, cudaMemcpyHostToDevice, l.stream));
         const long long total = static_cast<long long>(batch) * d_.c_in * d_.s2();
-        encode_nchw_f32_kernel<<<grid_for(total, 256, sm_count_), 256, 0, l.stream>>>(l.d_in.as<uint8_t>() + 16, rec_, l.d_in.as<uint32_t>(),
+        encode_nchw_f32_kernel<<<grid_for(total, 256, sm_count_), 256, 0, l.stream>>>(l.d_in.as<uint8_t>() + kRecs0, rec_, l.d_in.as<uint32_t>(),
                                                                                      static_cast<int>(batch), l.d_dense.as<float>());
         CB2_CUDA(cudaGetLastError());
         CB2_CUDA(cudaMemcpyAsync(nchw_out, l.d_dense.p, sizeof(float) * total, cudaMemcpyDeviceToHost, l.stream));
@@ -1088,8 +1129,13 @@ void Engine::resident_upload(const uint64_t* planes, const uint8_t* legal, uint3
     Lane& l = *lanes_[0];
     const size_t plane_words = static_cast<size_t>(rec_.planes) * rec_.wpp;
     const size_t bm = d_.bitmap_bytes();
-    for (uint32_t i = 0; i < n; ++i)
-        pack_record(l.h_in + 16 + static_cast<size_t>(i) * rec_.rec_bytes, planes + i * plane_words, legal ? legal + i * bm : nullptr);
+    resident_offsets_.assign(n + 1, 0);
+    uint32_t total = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        resident_offsets_[i] = total;
+        total += pack_record(l.h_in + kRecs0 + static_cast<size_t>(i) * rec_.rec_bytes, planes + i * plane_words, legal ? legal + i * bm : nullptr, total);
+    }
+    resident_offsets_[n] = total;
     *reinterpret_cast<uint32_t*>(l.h_in) = n;
     CB2_CUDA(cudaMemcpyAsync(l.d_in.p, l.h_in, 16 + static_cast<size_t>(n) * rec_.rec_bytes, cudaMemcpyHostToDevice, l.stream));
     CB2_CUDA(cudaStreamSynchronize(l.stream));
@@ -1110,7 +1156,8 @@ void Engine::resident_download(uint32_t n, float* probs_out, size_t probs_cap, u
     Lane& l = *lanes_[0];
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) throw_device_error("eval_resident", e);
-    CB2_CUDA(cudaMemcpy(prob_offsets, l.d_offsets.p, sizeof(uint32_t) * (n + 1), cudaMemcpyDeviceToHost));
+    if (resident_offsets_.size() != static_cast<size_t>(n) + 1) throw Error(CATTUS_B200_EINVAL, "resident_download: n differs from the uploaded batch");
+    std::memcpy(prob_offsets, resident_offsets_.data(), sizeof(uint32_t) * (n + 1));
     const uint32_t total = prob_offsets[n];
     if (total > probs_cap) throw Error(CATTUS_B200_ERANGE, "probs_cap is smaller than the number of legal moves");
     CB2_CUDA(cudaMemcpy(probs_out, l.d_probs.p, sizeof(float) * total, cudaMemcpyDeviceToHost));
@@ -1147,6 +1194,25 @@ void Engine::time_stage(uint32_t stage, uint32_t n, uint32_t iters, float* ms_ou
     cudaError_t e = cudaStreamSynchronize(l.stream);
     if (e != cudaSuccess) throw_device_error("time_stage", e);
     for (uint32_t it = 0; it < iters; ++it) CB2_CUDA(cudaEventElapsedTime(&ms_out[it], ev[2 * it], ev[2 * it + 1]));
+    if (trace_.p != nullptr && stage == 1) {
+        std::vector<unsigned long long> t(512);
+        CB2_CUDA(cudaMemcpy(t.data(), trace_.p, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        const unsigned long long t0 = t[0];
+        std::fprintf(stderr, "trunk trace (cycles since layer 0 issue; n=%u): layer: inputs_ready mma_issued | acc_full ld_done stored fenced arrived\n", n);
+        for (uint32_t l = 0; l <= 1 + 2 * d_.r && l < 64; ++l) {
+            std::fprintf(stderr, "  l%-2u:", l);
+            for (int k = 0; k < 7; ++k) std::fprintf(stderr, " %8lld", static_cast<long long>(t[l * 8 + k] - t0));
+            std::fprintf(stderr, "\n");
+        }
+        std::fprintf(stderr, "issuer per (layer, first tile of group): arrive_at_wait inputs_ready issued\n");
+        for (uint32_t l = 0; l < 4; ++l)
+            for (uint32_t g0 = 0; g0 < 8; ++g0) {
+                const unsigned long long* e = &t[128 + (l * 8 + g0) * 3];
+                if (e[2] == 0) continue;
+                std::fprintf(stderr, "  l%u t%u: %8lld %8lld %8lld\n", l, g0, static_cast<long long>(e[0] - t0), static_cast<long long>(e[1] - t0),
+                             static_cast<long long>(e[2] - t0));
+            }
+    }
     for (auto& x : ev) cudaEventDestroy(x);
     std::lock_guard<std::mutex> g(m_mu_);
     metrics_.kernel_launches += launched;

@@ -92,7 +92,7 @@ struct Lane {
     float* h_probs = nullptr;   // [max_batch * moves]
     // device
     DeviceBuf d_in;  // same layout as h_in
-    DeviceBuf d_values, d_offsets, d_probs;
+    DeviceBuf d_values, d_probs;
     DeviceBuf d_x;       // bf16: encoded input NHWC [rows][64]; fp32: NCHW f32
     DeviceBuf d_act[3];  // trunk activations
     DeviceBuf d_hv, d_hp;  // head conv outputs
@@ -139,12 +139,12 @@ class Engine {
     std::vector<Op>& ops_for(Lane& lane, uint32_t bucket, bool dense_input);
     void build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, bool dense_input);
     void build_ops_fp32(Lane& lane, uint32_t bucket, std::vector<Op>& ops, bool dense_input);
-    void add_tail_ops(Lane& lane, uint32_t bucket, std::vector<Op>& ops, bool dense_input);
+    void add_tail_ops(Lane& lane, uint32_t bucket, std::vector<Op>& ops, bool dense_input, bool value_tail, bool policy_tail);
     void run_bucket(Lane& lane, uint32_t bucket, cudaStream_t stream, bool use_graph, bool dense_input);
     void throw_device_error(const char* where, cudaError_t e);
 
     // batch plumbing
-    uint32_t pack_record(uint8_t* dst, const uint64_t* planes, const uint8_t* legal) const;  // returns #legal
+    uint32_t pack_record(uint8_t* dst, const uint64_t* planes, const uint8_t* legal, uint32_t prob_offset) const;  // returns #legal
     void submit(Lane& lane, uint32_t n, uint32_t total_probs);  // H2D + graph + D2H + event (async)
     void finish(Lane& lane, uint32_t n);                         // wait + device error check + metrics
     Lane& acquire_lane();
@@ -185,6 +185,7 @@ class Engine {
     float vfc2_b_ = 0.0f;
     DeviceBuf fused_w_, fused_b_;  // trunk_fused.cuh weight images + biases
     DeviceBuf small_w_, small_b_;  // trunk_small.cuh weight image + biases
+    DeviceBuf trace_;              // optional clock64 trace of trunk_small (CATTUS_B200_TRACE_TRUNK=1)
     uint32_t small_stem_kc_ = 1;
 
     std::vector<std::unique_ptr<Lane>> lanes_;
@@ -205,6 +206,8 @@ class Engine {
     uint32_t* h_err_ = nullptr;
     uint32_t* d_err_ = nullptr;
 
+    std::vector<uint32_t> resident_offsets_;  // host copy of the resident batch's probability offsets
+
     // L2 flush scratch for time_stage
     DeviceBuf flush_;
 
@@ -212,6 +215,8 @@ class Engine {
     mutable std::mutex m_mu_;
     cattus_b200_metrics metrics_{};
     uint32_t kernels_per_batch_ = 0;
+
+    TcGemmParams last_tc_params_{};  // parameters of the most recent gemm() op (build-time scratch)
 
     // driver entry point
     void* encode_tiled_ = nullptr;

@@ -13,7 +13,9 @@
 namespace cb2 {
 
 // One input record per position in the (pinned and device) batch block:
+//   [u32 offset of its probabilities in the compact output][u32 #legal]   <- 8-byte prefix, written by the host
 //   [planes * wpp u64 words][legal bitmap padded to a multiple of 8 bytes (absent when derived)]
+// Kernels receive a pointer to record 0's PLANES; rec_bytes (the stride) includes the prefix.
 struct RecLayout {
     int rec_bytes;     // multiple of 8
     int planes;        // C_in
@@ -165,63 +167,11 @@ __global__ void fc_f32_kernel(const float* __restrict__ in, const float* __restr
 }
 
 // ---------------------------------------------------------------------------------------------- tails
-// counts[b] = number of legal moves of position b: one warp per position, coalesced reads of its bitmap words.
-__global__ void legal_count_kernel(const uint8_t* __restrict__ recs, RecLayout L, const uint32_t* __restrict__ n_ptr,
-                                   uint32_t* __restrict__ counts) {
-    const int n = static_cast<int>(*n_ptr);
-    const int lane = threadIdx.x & 31;
-    const int b = static_cast<int>((blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5);
-    if (b >= n) return;
-    const uint8_t* rec = recs + static_cast<size_t>(b) * L.rec_bytes;
-    uint32_t cnt = 0;
-    for (int j = lane; j < L.legal_words; j += 32) cnt += __popc(legal_word(rec, L, j));
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, d);
-    if (lane == 0) counts[b] = cnt;
-}
-
-// In place: offsets[b] = exclusive prefix sum of counts[0..n); offsets[n] = total.  One block of 1024 threads, each
-// owning a contiguous run of ceil(n / 1024) entries (n <= 65536).
-__global__ void legal_offsets_kernel(const uint32_t* __restrict__ n_ptr, uint32_t* __restrict__ offsets) {
-    __shared__ uint32_t warp_sums[32];
-    const int n = static_cast<int>(*n_ptr);
-    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-    const int per = (n + 1023) / 1024;
-    const int lo = min(t * per, n), hi = min(lo + per, n);
-    uint32_t sum = 0;
-    for (int i = lo; i < hi; ++i) sum += offsets[i];
-    uint32_t incl = sum;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-        if (lane >= d) incl += y;
-    }
-    if (lane == 31) warp_sums[wid] = incl;
-    __syncthreads();
-    if (wid == 0) {
-        uint32_t ws = warp_sums[lane];
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, ws, d);
-            if (lane >= d) ws += y;
-        }
-        warp_sums[lane] = ws;  // inclusive over warps
-    }
-    __syncthreads();
-    uint32_t run = (wid == 0 ? 0u : warp_sums[wid - 1]) + incl - sum;
-    for (int i = lo; i < hi; ++i) {
-        const uint32_t c = offsets[i];
-        offsets[i] = run;
-        run += c;
-    }
-    if (t == 1023) offsets[n] = run;  // the last thread's running total is the grand total (empty runs carry it through)
-}
-
 // One warp per position: clamp non-finite logits to -FLT_MAX, softmax over the legal moves only, write the
-// probabilities compactly (ascending nn index) at offsets[b].  Three passes over <= M logits held in L1/L2.
+// probabilities compactly (ascending nn index) at the offset the host stored in the record's prefix (it counts the
+// legal moves while packing, so the exclusive scan is free there).  Three passes over <= M logits held in L1/L2.
 __global__ void policy_tail_kernel(const float* __restrict__ logits, int ld_logits, const uint8_t* __restrict__ recs,
-                                   RecLayout L, const uint32_t* __restrict__ n_ptr, const uint32_t* __restrict__ offsets,
-                                   float* __restrict__ probs) {
+                                   RecLayout L, const uint32_t* __restrict__ n_ptr, float* __restrict__ probs) {
     const int n = static_cast<int>(*n_ptr);
     const int lane = threadIdx.x & 31;
     const int b = static_cast<int>((blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5);
@@ -250,7 +200,7 @@ __global__ void policy_tail_kernel(const float* __restrict__ logits, int ld_logi
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, d);
-    uint32_t pos = offsets[b];
+    uint32_t pos = *reinterpret_cast<const uint32_t*>(rec - 8);
     for (int j = 0; j < L.legal_words; ++j) {
         const uint32_t w = legal_word(rec, L, j);
         if ((w >> lane) & 1u) {

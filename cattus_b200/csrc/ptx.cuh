@@ -251,6 +251,17 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16]) {
                  : "memory");
 }
 
+// wait for two split loads at once
+__device__ __forceinline__ void tmem_ld_wait2(uint32_t (&r)[16], uint32_t (&q)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(q[0]), "+r"(q[1]),
+                   "+r"(q[2]), "+r"(q[3]), "+r"(q[4]), "+r"(q[5]), "+r"(q[6]), "+r"(q[7]), "+r"(q[8]), "+r"(q[9]), "+r"(q[10]),
+                   "+r"(q[11]), "+r"(q[12]), "+r"(q[13]), "+r"(q[14]), "+r"(q[15])
+                 :
+                 : "memory");
+}
+
 // ---------------------------------------------------------------- descriptors
 // K-major operand tile in the canonical 128-byte-swizzle layout: rows of 128 B (64 bf16), 8-row groups `sbo_bytes`
 // apart (1024 for a dense tile), 16-byte chunks XOR-swizzled by (row % 8) -- what TMA SWIZZLE_128B writes.

@@ -8,9 +8,17 @@
 //                   A tile is ONE 4-D TMA box {64ch, S, S, nb boards} whose start coordinate is shifted by the tap
 //                   (dx, dy) in {-1,0,1}^2 -- TMA zero-fills the out-of-bounds halo, which is exactly `padding="same"`
 //                   (net_utils.py:13,29,32).  A tile always holds whole boards, so no tile straddles two positions.
+// Epilogue variants (`epi`): 0 = +bias (+residual) -> ReLU -> bf16 / f32 store.
+//   1 = value head tail fused (N = 128 hidden units in one tile): relu(acc + b1) . w2 + b2 -> tanh -> values[row]
+//       (net_utils.py:71-74); the hidden activations never leave the SM.
+//   2 = policy tail fused (all M <= 128 moves in one tile: tic-tac-toe, hex): + bias, non-finite -> f32::MIN, softmax
+//       over the legal moves only, compact write at the offset stored in the record prefix (engine/src/net/mod.rs:57-61,
+//       :106-119).  One thread owns one position's whole logits row in TMEM; the sum runs in ascending move order like
+//       the reference's sequential `iter().sum()`.
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one lane), warps 2..5 = epilogue
 // (TMEM -> registers -> +bias (+residual) -> ReLU -> bf16/f32 -> global).  3-stage smem ring (two CTAs per SM), full/empty mbarriers.
 #pragma once
+#include "kernels.cuh"
 #include "ptx.cuh"
 
 namespace cb2 {
@@ -41,7 +49,17 @@ struct alignas(64) TcGemmParams {
     int out_f32;
     int relu;
     uint32_t tx_bytes;  // bytes one stage's two TMA boxes deliver
-    int pad_;
+    int epi;            // epilogue variant, see above
+    // epi 1
+    const float* w2;    // [128]
+    float b2;
+    float* values;      // [positions]
+    // epi 2
+    const uint8_t* recs;  // record 0's planes (kernels.cuh: RecLayout)
+    RecLayout rl;
+    float* probs;         // compact output
+    // epi 1, 2
+    const uint32_t* n_ptr;
 };
 
 __global__ void __launch_bounds__(kTcThreads, 2) tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
@@ -132,6 +150,73 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_gemm_kernel(const __grid_con
         ptx::mbar_wait(tmem_full_bar, 0, p.err, 0x300);
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + ((q * 32u) << 16);
+        if (p.epi == 1) {
+            // ---- value head: tanh(b2 + sum_j relu(acc_j + b1_j) * w2_j)
+            const int n = static_cast<int>(*p.n_ptr);
+            float dot = 0.0f;
+            for (int c0 = 0; c0 < 128; c0 += 16) {
+                float v[16];
+                ptx::tmem_ld_x16(taddr + c0, v);
+                const float4* b4 = reinterpret_cast<const float4*>(p.bias + c0);
+                const float4* w4 = reinterpret_cast<const float4*>(p.w2 + c0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 b = __ldg(b4 + j), w = __ldg(w4 + j);
+                    dot = fmaf(fmaxf(v[4 * j + 0] + b.x, 0.0f), w.x, dot);
+                    dot = fmaf(fmaxf(v[4 * j + 1] + b.y, 0.0f), w.y, dot);
+                    dot = fmaf(fmaxf(v[4 * j + 2] + b.z, 0.0f), w.z, dot);
+                    dot = fmaf(fmaxf(v[4 * j + 3] + b.w, 0.0f), w.w, dot);
+                }
+            }
+            if (grow < n) p.values[grow] = tanhf(dot + p.b2);
+        } else if (p.epi == 2) {
+            // ---- policy: masked softmax over this position's row, three passes over TMEM (max, sum, write)
+            const int n = static_cast<int>(*p.n_ptr);
+            const bool live = grow < n;
+            const uint8_t* rec = p.recs + static_cast<size_t>(live ? grow : 0) * p.rl.rec_bytes;
+            uint32_t legal[4] = {0, 0, 0, 0};
+            if (live) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (j < p.rl.legal_words) legal[j] = legal_word(rec, p.rl, j);
+            }
+            float mx = -FLT_MAX;
+            for (int c0 = 0; c0 < p.n_umma; c0 += 16) {
+                float v[16];
+                ptx::tmem_ld_x16(taddr + c0, v);
+                const uint32_t bits = (legal[c0 >> 5] >> (c0 & 31)) & 0xFFFFu;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float x = v[j] + __ldg(p.bias + c0 + j);
+                    if (!isfinite(x)) x = -FLT_MAX;
+                    if ((bits >> j) & 1u) mx = fmaxf(mx, x);
+                }
+            }
+            float sum = 0.0f;
+            for (int c0 = 0; c0 < p.n_umma; c0 += 16) {
+                float v[16];
+                ptx::tmem_ld_x16(taddr + c0, v);
+                const uint32_t bits = (legal[c0 >> 5] >> (c0 & 31)) & 0xFFFFu;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float x = v[j] + __ldg(p.bias + c0 + j);
+                    if (!isfinite(x)) x = -FLT_MAX;
+                    if ((bits >> j) & 1u) sum += expf(x - mx);
+                }
+            }
+            uint32_t pos = live ? *reinterpret_cast<const uint32_t*>(rec - 8) : 0u;
+            for (int c0 = 0; c0 < p.n_umma; c0 += 16) {
+                float v[16];
+                ptx::tmem_ld_x16(taddr + c0, v);
+                const uint32_t bits = (legal[c0 >> 5] >> (c0 & 31)) & 0xFFFFu;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float x = v[j] + __ldg(p.bias + c0 + j);
+                    if (!isfinite(x)) x = -FLT_MAX;
+                    if (live && ((bits >> j) & 1u)) p.probs[pos++] = expf(x - mx) / sum;
+                }
+            }
+        } else
         for (int c0 = 0; c0 < p.n_umma; c0 += 16) {
             float v[16];
             ptx::tmem_ld_x16(taddr + c0, v);  // warp-collective: executed by all lanes regardless of `ok`

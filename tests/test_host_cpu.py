@@ -18,7 +18,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     from cattus_b200 import _lib
 
     lib = _lib.load()
-    header = (ROOT / "include" / "cattus_b200.h").read_text()
+    header = "".join(p.read_text() for p in sorted((ROOT / "include").glob("*.h")))
     declared = set(re.findall(r"\b(cattus_b200_[a-z_0-9]+)\s*\(", header))
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for name in declared:
