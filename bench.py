@@ -174,6 +174,64 @@ def time_cpu_reference(cfg, sample_n, budget_s, steps=None, warmup=1, seed=1234)
     return done * sample_n / el, cores, el / done, f"{done} passes over {sample_n} positions, torch {cores} threads fp32 (reference torch-py engine restated) + C restatement of planes_to_tensor/calc_moves_probs"
 
 
+SELFPLAY_CFG = {
+    # training/config/hex5_cfg.yaml / hex7_cfg.yaml: engine.mcts with the self_play.engine_overrides applied
+    "hex5": {"sim_num": 1400, "explore_factor": 1.41421, "temperature_policy": [[10, 1.0], [9999, 0.0]], "prior_noise_alpha": 0.03,
+             "prior_noise_epsilon": 0.25, "cache_size": 1000000},
+    "hex7": {"sim_num": 600, "explore_factor": 1.41421, "temperature_policy": [[10, 1.0], [9999, 0.0]], "prior_noise_alpha": 0.03,
+             "prior_noise_epsilon": 0.25, "cache_size": 1000000},
+    "hex4": {"sim_num": 100, "explore_factor": 1.41421, "temperature_policy": [[4, 1.0], [9999, 0.0]], "prior_noise_alpha": 0.03,
+             "prior_noise_epsilon": 0.25, "cache_size": 1000000},
+}
+
+
+def selfplay_summary_to_dict(game, mcts_cfg, summary, games, threads, gpt, extra=None):
+    m = summary["metrics"]
+    d = {"metric": "selfplay_sims_per_sec", "unit": "sims/s", "workload": f"{game} self-play, sim_num {mcts_cfg['sim_num']}, noise + temperature as "
+         f"training/config/{game}_cfg.yaml", "games": games, "threads": threads, "games_per_thread": gpt, "simulations": m["selfplay.simulations"],
+         "seconds": m["selfplay.seconds"], "evaluations": m["selfplay.evaluations"], "evaluator_calls": m["model.activation_count"],
+         "mean_batch": m["selfplay.evaluations"] / max(1, m["model.activation_count"]),
+         "cache_hit_rate": m["cache.hits"] / max(1, m["cache.hits"] + m["cache.misses"]),
+         "eval_wait_frac": m["selfplay.eval_wait_seconds"] / max(1e-9, m["selfplay.seconds"] * threads),
+         "player1_wins": summary["player1_wins"], "player2_wins": summary["player2_wins"], "draws": summary["draws"]}
+    if extra:
+        d.update(extra)
+    return d
+
+
+def time_cpu_selfplay(game, games, threads):
+    """The reference's arrangement on the host cores: `threads` OS threads with one tree each (hex5_cfg.yaml: threads 8),
+    per-leaf evaluation by the reference's torch-py CPU engine restated (model.rs:68-84; calls are serialised like its
+    Mutex<Model>), same MCTS parameters.  Bounded sample: `games` games."""
+    from cattus_b200.selfplay import SelfPlayRunner
+    from oracle import games as og, net
+
+    cfg = net.CONFIGS[game]
+    sd = net.make_state_dict(cfg, 0)
+    cores = len(os.sched_getaffinity(0))
+    model = net.TorchCpuModel(sd, cfg, 1, 1)  # batch-1 evaluations of a 70 k-parameter net: one intra-op thread is the fastest setting
+    s = cfg.board_size
+
+    def cb(words, n):
+        x = og.planes_to_tensor_fast(words, s, cfg.planes)
+        probs, values = [], []
+        for i in range(n):
+            logits, v = model.run(x[i:i + 1])
+            ww = words[i].reshape(cfg.planes, -1)
+            legal = [k for k in range(s * s) if not ((int(ww[0][k >> 6]) | int(ww[1][k >> 6])) >> (k & 63)) & 1]
+            probs.append(og.calc_moves_probs(legal, og.clamp_non_finite(np.asarray(logits[0], dtype=np.float32))))
+            values.append(float(np.asarray(v).reshape(-1)[0]))
+        return probs, values
+
+    mc = SELFPLAY_CFG[game]
+    runner = SelfPlayRunner(game, {"mcts": mc, "threads": threads, "games_per_thread": 1, "seed": 1})
+    summary, _ = runner.run_with(cb, None, games)
+    return selfplay_summary_to_dict(game, mc, summary, games, threads, 1, {
+        "value": summary["metrics"]["selfplay.sims_per_sec"], "cores": cores, "kind": "port",
+        "sample": f"{games} games, {threads} threads x 1 tree each (the reference's arrangement; its Mutex<Model> serialises evaluations, so more "
+                  f"threads add nothing), per-leaf torch-CPU fp32 evaluation with 1 intra-op thread"})
+
+
 def run_reference_arm(args, rank, world):
     from oracle import net
 
@@ -193,6 +251,8 @@ def run_reference_arm(args, rank, world):
         "e2e": {"value": value, "unit": "positions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if not args.no_selfplay:
+        line["selfplay"] = time_cpu_selfplay(args.selfplay_game, 2, 2)
     print(json.dumps(line), flush=True)
 
 
@@ -208,6 +268,11 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU baseline work (rank 0, N=1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-selfplay", action="store_true", help="skip the self-play sims/s leg")
+    ap.add_argument("--selfplay-game", default="hex5", choices=sorted(SELFPLAY_CFG))
+    ap.add_argument("--selfplay-games", type=int, default=4096, help="games per GPU in the self-play leg")
+    ap.add_argument("--selfplay-threads", type=int, default=0, help="worker threads per GPU (0 = host cores / GPUs)")
+    ap.add_argument("--selfplay-gpt", type=int, default=256, help="concurrent games per worker thread")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -282,7 +347,47 @@ def main():
     kernels_per_batch = nw.info.kernels_per_batch
     fused = bool(nw.info.reserved & 1)
     small = bool(nw.info.reserved & 2)
+    # ---------------- batch-size sweep (BASELINE configs[4]): whole graph, inputs resident, L2 flushed, CUDA events
+    sweep = []
+    if rank == 0:
+        for nb in (1, 8, 64, 512):
+            if nb >= batch:
+                continue
+            nw.resident_upload(words[:nb], None if bitmaps is None else bitmaps[:nb])
+            nw.time_stage(4, nb, 3)
+            ms = float(np.mean(nw.time_stage(4, nb, 10)))
+            sweep.append({"batch": nb, "ms": ms, "positions_per_sec": nb / (ms * 1e-3)})
+        sweep.append({"batch": batch, "ms": float(np.mean(ms_all)), "positions_per_sec": batch / (float(np.mean(ms_all)) * 1e-3)})
     nw.close()
+
+    # ---------------- self-play MCTS sims/s (second half of the BASELINE metric): C++ driver + this GPU's evaluator
+    selfplay = None
+    if not args.no_selfplay:
+        from cattus_b200.selfplay import SelfPlayRunner
+
+        sp_cfg = net.CONFIGS[args.selfplay_game]
+        cores = len(os.sched_getaffinity(0))
+        threads = args.selfplay_threads or max(1, cores // max(1, world))
+        gpt = args.selfplay_gpt
+        games_total = max(2, args.selfplay_games * world // 2 * 2)
+        mc = SELFPLAY_CFG[args.selfplay_game]
+        with CudaNetwork(export_blob(net.make_state_dict(sp_cfg, 0), sp_cfg.game), sp_cfg.game, device=local_rank, batch_size=max(64, min(4096, gpt)),
+                         n_streams=4, precision="bf16") as sp_nw:
+            runner = SelfPlayRunner(args.selfplay_game, {"mcts": mc, "threads": threads, "games_per_thread": gpt, "seed": 1})
+            runner.generate_data(sp_nw, None, 2 * threads, first_game=rank, game_stride=world)  # warm-up (graphs, caches of the allocator)
+            l0 = sp_nw.metrics()["model.kernel_launches"]
+            barrier()
+            summary, _ = runner.generate_data(sp_nw, None, games_total, first_game=rank, game_stride=world)
+            barrier()
+            sp_launches = sp_nw.metrics()["model.kernel_launches"] - l0
+        m = summary["metrics"]
+        sims_all = rep.sum_over_ranks(float(m["selfplay.simulations"]))
+        secs = max_over_ranks(float(m["selfplay.seconds"]))
+        selfplay = selfplay_summary_to_dict(args.selfplay_game, mc, summary, games_total, threads, gpt, {
+            "value": sims_all / secs, "n_gpus": world, "host_cores": cores, "gpu_launches": int(sp_launches),
+            "note": "rank 0's counters shown; value = simulations of all ranks / max seconds; games partitioned by index across GPUs, no collective"})
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            selfplay["cpu_baseline"] = time_cpu_selfplay(args.selfplay_game, 2, 2)
 
     total_positions = world * positions_per_step * args.steps
     value = total_positions / t_value
@@ -320,9 +425,11 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "positions/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": t_e2e / args.steps * 1e3, "api": "cattus_b200_eval_batch (host buffers -> pinned block -> H2D -> graph -> D2H)"},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches) + (selfplay["gpu_launches"] if selfplay else 0),
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
+            "batch_sweep": sweep,
+            "selfplay": selfplay,
         }
         print(json.dumps(line), flush=True)
     rep.close()

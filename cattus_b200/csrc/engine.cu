@@ -638,6 +638,8 @@ void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
         p.tx_bytes = nb_ * s2 * 128 + g.n_umma * 128;
         ops.push_back(make_tc_op(1, name, p, tiles, g.n_tiles));
     };
+    TcGemmParams last_tc;  // parameters of the most recent gemm() op (the fused-tail variants are derived from them)
+    std::memset(&last_tc, 0, sizeof(last_tc));
     // plain GEMM: A = [rows][K] row-major bf16
     auto gemm = [&](int stage, const char* name, const void* a, uint64_t k_real, uint64_t rows, uint64_t row_stride_bytes, const GemmW& g,
                     void* out, uint32_t ld_out, bool out_f32, bool relu) {
@@ -657,7 +659,7 @@ void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
         p.out_f32 = out_f32 ? 1 : 0;
         p.relu = relu ? 1 : 0;
         p.tx_bytes = 128 * 128 + g.n_umma * 128;
-        last_tc_params_ = p;
+        last_tc = p;
         ops.push_back(make_tc_op(stage, name, p, ceil_div(static_cast<uint32_t>(rows), 128), g.n_tiles));
     };
     __nv_bfloat16* act[3] = {lane.d_act[0].as<__nv_bfloat16>(), lane.d_act[1].as<__nv_bfloat16>(), lane.d_act[2].as<__nv_bfloat16>()};
@@ -783,7 +785,7 @@ void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
          true, true);
     if (fuse_tails) {
         Op& op = ops.back();
-        TcGemmParams p = last_tc_params_;
+        TcGemmParams p = last_tc;
         p.epi = 1;
         p.w2 = vfc2_w_.as<float>();
         p.b2 = vfc2_b_;
@@ -795,7 +797,7 @@ void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
          pfc_.n_umma * pfc_.n_tiles, true, false);
     if (fuse_policy) {
         Op& op = ops.back();
-        TcGemmParams p = last_tc_params_;
+        TcGemmParams p = last_tc;
         p.epi = 2;
         p.recs = recs;
         p.rl = L;

@@ -216,8 +216,6 @@ class Engine {
     cattus_b200_metrics metrics_{};
     uint32_t kernels_per_batch_ = 0;
 
-    TcGemmParams last_tc_params_{};  // parameters of the most recent gemm() op (build-time scratch)
-
     // driver entry point
     void* encode_tiled_ = nullptr;
 };

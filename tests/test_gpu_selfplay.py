@@ -59,6 +59,19 @@ def test_gpu_selfplay_is_independent_of_scheduling():
         assert r == results[0]
 
 
+def test_gpu_selfplay_many_threads_many_lanes_same_games():
+    """Stress version of the above: more worker threads than evaluator lanes, fresh handles (so graphs and launch
+    sequences are built concurrently by several threads), hundreds of games -- every game must still be identical."""
+    base = dict(sim_num=40, cache_size=20000, prior_noise_alpha=0.3, prior_noise_epsilon=0.25, temperature_policy=[[6, 1.0], [9999, 0.0]], seed=11)
+    results = []
+    for threads, gpt, streams in ((32, 8, 8), (1, 512, 1), (24, 32, 4)):
+        with make_network("hex5", batch_size=512, n_streams=streams) as nw:
+            cfg = cfg_with(threads=threads, games_per_thread=gpt, **base)
+            _, recs = SelfPlayRunner("hex5", cfg).generate_data(nw, None, 512, keep_records=True)
+            results.append([(r.game_idx, r.moves, r.winner) for r in recs])
+    assert results[1] == results[0] and results[2] == results[0]
+
+
 def test_gpu_selfplay_two_models_and_files(tmp_path):
     cfg = cfg_with(sim_num=40, cache_size=1000, threads=2, games_per_thread=4)
     from cattus_b200 import CudaNetwork
