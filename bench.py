@@ -397,8 +397,17 @@ def main():
     trunk_flops = stem_flops + cfg.trunk_flops_per_position
     t_trunk = float(np.mean(ms_trunk)) * 1e-3
     achieved = batch * trunk_flops / t_trunk / 1e12
+    traffic = None
+    try:  # DRAM bytes of the same kernel from the committed `ncu --set full` capture (per launch, same workload and batch)
+        tj = json.loads((ROOT / "profiles" / "traffic.json").read_text())
+        te = tj.get("trunk_fused_kernel" if fused else "trunk_small_kernel" if small else "")
+        if te and te["workload"] == args.workload and te["positions_per_launch"] == batch:
+            traffic = {"bytes": te["dram_bytes_read"] + te["dram_bytes_write"], "dram_bytes_read": te["dram_bytes_read"],
+                       "dram_bytes_write": te["dram_bytes_write"], "source": te["source"]}
+    except Exception:
+        traffic = None
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
-                "traffic": None, "kernel": ("trunk_fused_kernel (stem + residual blocks, one launch)" if fused else
+                "traffic": traffic, "kernel": ("trunk_fused_kernel (stem + residual blocks, one launch)" if fused else
                            "trunk_small_kernel (encode + stem + residual blocks + head convs, one launch)" if small else
                            "tc_gemm_kernel x (1 + 2R) conv layers (stem + residual blocks)"),
                 "peak_source": peaks["source"] + ", burst figure (stage timed alone)", "flop_per_position": trunk_flops, "positions_per_launch": batch,

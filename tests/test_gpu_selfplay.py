@@ -85,3 +85,32 @@ def test_gpu_selfplay_two_models_and_files(tmp_path):
     for r in recs:
         for k, (e, d) in enumerate(zip(r.entries, r.entry_dirs)):
             assert (tmp_path / f"d{d}" / f"{r.game_idx:08d}_{k:03d}.traindata").read_bytes() == e
+
+
+def test_self_player_cli_is_a_drop_in_for_the_trainer(tmp_path):
+    """The command line and config file the trainer uses (train_process.py:151-170), the summary keys it reads
+    (:174-186) and the data-entry files its DataSet globs (data_set.py:48)."""
+    import json
+
+    from cattus_b200 import self_player
+    from tests.util import blob
+
+    model = tmp_path / "model.cb2"
+    model.write_bytes(blob("hex4"))
+    cfg = {"mcts": {"sim_num": 30, "explore_factor": 1.41421, "temperature_policy": [[4, 1.0], [9999, 0.0]], "prior_noise_alpha": 0.03,
+                    "prior_noise_epsilon": 0.25, "cache_size": 1000},
+           "model": {"batch_size": 4, "inference": {"engine": "cuda-b200"}}, "threads": 2}
+    (tmp_path / "config.json").write_text(json.dumps(cfg))
+    out = tmp_path / "games" / "run0"
+    summary_file = tmp_path / "summary.json"
+    rc = self_player.main([f"--model1-path={model}", f"--model2-path={model}", "--games-num=6", f"--out-dir1={out}", f"--out-dir2={out}",
+                           f"--summary-file={summary_file}", f"--config-file={tmp_path / 'config.json'}"])
+    assert rc == 0
+    s = json.loads(summary_file.read_text())
+    assert s["player1_wins"] + s["player2_wins"] + s["draws"] == 6
+    for key in ("model.activation_count", "model.run_duration", "mcts.search_duration", "cache.hits", "cache.misses"):
+        assert key in s["metrics"]
+    assert s["metrics"]["model.activation_count"] > 0 and s["metrics"]["cache.hits"] + s["metrics"]["cache.misses"] > 0
+    files = sorted(out.rglob("*.traindata"))
+    assert len(files) == s["metrics"]["selfplay.searches"] and files[0].name == "00000000_000.traindata"
+    assert all(f.stat().st_size == 6 * 8 + 16 * 4 + 1 for f in files)

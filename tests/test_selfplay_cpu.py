@@ -295,3 +295,27 @@ def test_bad_arguments_are_reported():
 
     with pytest.raises(SelfPlayError, match="wrong number"):
         SelfPlayRunner("hex4", cfg_with()).run_with(broken, None, 2)
+
+
+def test_self_player_cli_rejects_other_engines_and_foreign_models(tmp_path):
+    import json
+
+    from cattus_b200 import self_player
+    from tests.util import blob
+
+    model = tmp_path / "m.cb2"
+    model.write_bytes(blob("hex4"))
+    assert self_player.game_of_blob(model) == ("hex4", "hex")
+    (tmp_path / "c.json").write_text(json.dumps({"mcts": {"sim_num": 10}, "model": {"batch_size": 4, "inference": {"engine": "onnx-ort"}}, "threads": 1}))
+    argv = [f"--model1-path={model}", f"--model2-path={model}", "--games-num=2", f"--out-dir1={tmp_path}", f"--out-dir2={tmp_path}",
+            f"--config-file={tmp_path / 'c.json'}"]
+    with pytest.raises(SystemExit, match="no CPU fallback"):
+        self_player.main(argv)
+    bad = tmp_path / "bad.cb2"
+    bad.write_bytes(b"\0" * 128)
+    with pytest.raises(ValueError, match="not a .cb2"):
+        self_player.game_of_blob(bad)
+    chess = tmp_path / "chess.cb2"
+    chess.write_bytes(blob("chess_dev"))
+    with pytest.raises(ValueError, match="chess"):
+        self_player.game_of_blob(chess)
