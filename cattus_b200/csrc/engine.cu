@@ -171,9 +171,10 @@ Engine::Engine(const cattus_b200_desc& desc, const void* blob_bytes, size_t blob
     std::memset(h_err_, 0, 64);
     CB2_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_err_), h_err_, 0));
     CB2_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+    CB2_CUDA(cudaFuncSetAttribute(tc_gemm_dual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
     // whole-trunk kernel: 8x8 boards, 128 filters (flags bit 0 forces the per-layer path, used by the parity tests)
     fused_trunk_ = precision_ == CATTUS_B200_PRECISION_BF16 && d_.s == 8 && d_.f == 128 && d_.c_in <= 32 && d_.wpp() == 1 &&
-                   (desc.flags & 1u) == 0 && (sm_count_ >= 2);
+                   (desc.flags & 1u) == 0 && (sm_count_ >= 2) && vhp_ + php_ <= 64;
     if (fused_trunk_) CB2_CUDA(cudaFuncSetAttribute(trunk_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFtSmemBytes));
     // 16-filter nets (every shipped training config): whole trunk + both head convs in one kernel
     small_trunk_ = precision_ == CATTUS_B200_PRECISION_BF16 && d_.f == 16 && d_.c_in <= 32 && d_.s >= 3 && d_.s <= 11 && vhp_ + php_ <= 32 &&
@@ -331,8 +332,8 @@ void Engine::upload_weights(const Blob& blob) {
         // trunk_fused.cuh weight image: for each layer, each 16-channel k-chunk, each CTA rank (= half of the output
         // channels): [tap 9][k-half 2][oc 64][ic 8] bf16 = one 18432-byte TMA stage.  Stem input channels padded to 32.
         const uint32_t layers = 1 + static_cast<uint32_t>(blob.block_conv.size());
-        size_t stages = 2 + static_cast<size_t>(layers - 1) * 8;
-        std::vector<float> img(stages * 2 * (kFtWStage / 2), 0.0f), bias(static_cast<size_t>(layers) * 128, 0.0f);
+        size_t stages = 2 + static_cast<size_t>(layers - 1) * 8 + 1;  // + one stage for the two head convs
+        std::vector<float> img(stages * 2 * (kFtWStage / 2), 0.0f), bias(static_cast<size_t>(layers + 1) * 128, 0.0f);
         for (uint32_t l = 0; l < layers; ++l) {
             const Blob::Conv& c = l == 0 ? blob.stem : blob.block_conv[l - 1];
             const uint32_t nkc = l == 0 ? 2 : 8;
@@ -349,6 +350,25 @@ void Engine::upload_weights(const Blob& blob) {
                                     if (ic < c.ci) blk[((tap * 2 + kh) * 64 + n) * 8 + e] = D[c.w + (static_cast<size_t>(oc) * c.ci + ic) * 9 + tap];
                                 }
                 }
+        }
+        {
+            // head stage: [k-chunk 8][k-half 2][oc (vhp + php) / 2][ic 8] per CTA rank; channel list = value | policy
+            const uint32_t nh = vhp_ + php_, half = nh / 2;
+            const size_t base = 2 + static_cast<size_t>(layers - 1) * 8;
+            auto head_w = [&](uint32_t ch, uint32_t ic) -> float {
+                if (ch < vhp_) return ch < d_.vh ? D[blob.vconv.w + static_cast<size_t>(ch) * 128 + ic] : 0.0f;
+                const uint32_t pc = ch - vhp_;
+                return pc < d_.ph ? D[blob.pconv.w + static_cast<size_t>(pc) * 128 + ic] : 0.0f;
+            };
+            for (uint32_t rk = 0; rk < 2; ++rk) {
+                float* blk = img.data() + (base * 2 + rk) * (kFtWStage / 2);
+                for (uint32_t kc = 0; kc < 8; ++kc)
+                    for (uint32_t kh = 0; kh < 2; ++kh)
+                        for (uint32_t n = 0; n < half; ++n)
+                            for (uint32_t e = 0; e < 8; ++e) blk[((kc * 2 + kh) * half + n) * 8 + e] = head_w(rk * half + n, kc * 16 + kh * 8 + e);
+            }
+            for (uint32_t o = 0; o < d_.vh; ++o) bias[static_cast<size_t>(layers) * 128 + o] = D[blob.vconv.b + o];
+            for (uint32_t o = 0; o < d_.ph; ++o) bias[static_cast<size_t>(layers) * 128 + vhp_ + o] = D[blob.pconv.b + o];
         }
         upload(fused_w_, to_bf16(img));
         upload(fused_b_, bias);
@@ -682,7 +702,10 @@ void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
         fp.recs = recs;
         fp.n_ptr = n_ptr;
         fp.bias = fused_b_.as<float>();
-        fp.out = act[0];
+        fp.out_v = lane.d_hv.as<__nv_bfloat16>();
+        fp.out_p = lane.d_hp.as<__nv_bfloat16>();
+        fp.vhp = static_cast<int>(vhp_);
+        fp.php = static_cast<int>(php_);
         fp.err = d_err_;
         fp.rec_bytes = rec_.rec_bytes;
         fp.planes = static_cast<int>(d_.c_in);
@@ -773,7 +796,7 @@ void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
             cur = o;
         }
     }
-    if (!small) {
+    if (!small && !fused) {
         gemm(2, "value_conv", act[cur], ca_, rows_total, ca_ * 2ull, vconv_, lane.d_hv.p, vhp_, false, true);
         gemm(2, "policy_conv", act[cur], ca_, rows_total, ca_ * 2ull, pconv_, lane.d_hp.p, php_, false, true);
     }
@@ -781,6 +804,8 @@ void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
     // value: always (the 128 hidden units are one N tile); policy: when all moves fit one N tile (tic-tac-toe, hex).
     const bool fuse_tails = (desc_.flags & 1u) == 0;
     const bool fuse_policy = fuse_tails && !dense_input && pfc_.n_tiles == 1;
+    TcGemmParams value_tc;
+    std::memset(&value_tc, 0, sizeof(value_tc));
     gemm(2, "value_fc1", lane.d_hv.p, static_cast<uint64_t>(s2) * vhp_, bucket, static_cast<uint64_t>(s2) * vhp_ * 2, vfc1_, lane.d_hidden.p, 128,
          true, true);
     if (fuse_tails) {
@@ -792,20 +817,50 @@ void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
         p.values = lane.d_values.as<float>();
         p.n_ptr = n_ptr;
         op = make_tc_op(2, "value_fc1_tanh", p, ceil_div(bucket, 128), 1);
+        value_tc = p;
     }
     gemm(2, "policy_fc", lane.d_hp.p, static_cast<uint64_t>(s2) * php_, bucket, static_cast<uint64_t>(s2) * php_ * 2, pfc_, lane.d_logits.p,
          pfc_.n_umma * pfc_.n_tiles, true, false);
-    if (fuse_policy) {
+    const bool compact_policy = fuse_tails && !dense_input && pfc_.n_tiles > 1 && pfc_.n_umma == 128 && d_.moves <= 256 * 32;
+    if (fuse_policy || compact_policy) {
         Op& op = ops.back();
         TcGemmParams p = last_tc;
-        p.epi = 2;
+        p.epi = fuse_policy ? 2 : 3;
         p.recs = recs;
         p.rl = L;
         p.probs = lane.d_probs.as<float>();
         p.n_ptr = n_ptr;
-        op = make_tc_op(2, "policy_fc_softmax", p, ceil_div(bucket, 128), 1);
+        op = make_tc_op(2, fuse_policy ? "policy_fc_softmax" : "policy_fc_masked", p, ceil_div(bucket, 128), pfc_.n_tiles);
     }
-    add_tail_ops(lane, bucket, ops, dense_input, !fuse_tails, !fuse_policy);
+    if (fuse_tails && (fuse_policy || compact_policy)) {
+        // both FCs in one launch (tc_gemm_dual_kernel): y == 0 value, y >= 1 the policy's N tiles
+        TcGemmDualParams dp;
+        dp.b = last_tc;  // still the policy problem ...
+        dp.b.epi = fuse_policy ? 2 : 3;
+        dp.b.recs = recs;
+        dp.b.rl = L;
+        dp.b.probs = lane.d_probs.as<float>();
+        dp.b.n_ptr = n_ptr;
+        dp.a = value_tc;
+        ops.pop_back();
+        ops.pop_back();
+        Op op;
+        op.stage = 2;
+        op.name = "heads_fc_dual";
+        const dim3 grid(ceil_div(bucket, 128), 1 + pfc_.n_tiles);
+        op.launch = [dp, grid](cudaStream_t st) { tc_gemm_dual_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(dp); };
+        ops.push_back(op);
+    }
+    if (compact_policy) {
+        Op op;
+        op.stage = 3;
+        op.name = "softmax_compact";
+        float* probs = lane.d_probs.as<float>();
+        const int blocks = static_cast<int>(ceil_div(bucket * 32, 256));
+        op.launch = [=](cudaStream_t st) { softmax_compact_kernel<<<blocks, 256, 0, st>>>(recs, L, n_ptr, probs); };
+        ops.push_back(op);
+    }
+    add_tail_ops(lane, bucket, ops, dense_input, !fuse_tails, !(fuse_policy || compact_policy));
 }
 
 void Engine::run_bucket(Lane& lane, uint32_t bucket, cudaStream_t stream, bool use_graph, bool dense_input) {

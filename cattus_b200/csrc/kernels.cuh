@@ -212,6 +212,44 @@ __global__ void policy_tail_kernel(const float* __restrict__ logits, int ld_logi
     }
 }
 
+// In place over the compact legal logits the policy FC epilogue wrote (tc_gemm.cuh, epi 3): probs = softmax(logits) per
+// position (calc_moves_probs, engine/src/net/mod.rs:106-119).  One warp per position; offset and count come from the
+// record prefix.
+__global__ void softmax_compact_kernel(const uint8_t* __restrict__ recs, RecLayout L, const uint32_t* __restrict__ n_ptr,
+                                       float* __restrict__ probs) {
+    const int n = static_cast<int>(*n_ptr);
+    const int lane = threadIdx.x & 31;
+    const int b = static_cast<int>((blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5);
+    if (b >= n) return;
+    const uint32_t* prefix = reinterpret_cast<const uint32_t*>(recs + static_cast<size_t>(b) * L.rec_bytes - 8);
+    const uint32_t off = prefix[0], cnt = prefix[1];
+    float* row = probs + off;
+    float x[8];  // <= 256 legal moves per position (chess: <= 218)
+    float mx = -FLT_MAX;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t i = lane + 32u * k;
+        x[k] = i < cnt ? row[i] : -FLT_MAX;
+        mx = fmaxf(mx, x[k]);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, d));
+    float sum = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t i = lane + 32u * k;
+        x[k] = i < cnt ? expf(x[k] - mx) : 0.0f;
+        sum += x[k];
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, d);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t i = lane + 32u * k;
+        if (i < cnt) row[i] = x[k] / sum;
+    }
+}
+
 // value = tanh(b2 + sum_j hidden[b][j] * w2[j]); one warp per position (hidden width fixed 128: net_utils.py:71-73).
 __global__ void value_tail_kernel(const float* __restrict__ hidden, int ld_hidden, const float* __restrict__ w2, float b2,
                                   const uint32_t* __restrict__ n_ptr, float* __restrict__ values) {

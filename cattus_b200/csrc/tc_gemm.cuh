@@ -15,6 +15,9 @@
 //       over the legal moves only, compact write at the offset stored in the record prefix (engine/src/net/mod.rs:57-61,
 //       :106-119).  One thread owns one position's whole logits row in TMEM; the sum runs in ascending move order like
 //       the reference's sequential `iter().sum()`.
+//   3 = policy mask fused for M > 128 (chess, 15 N tiles): + bias, non-finite -> f32::MIN, and only the logits of LEGAL
+//       moves are written, compactly, at (record offset + number of legal moves in earlier columns) -- 0.5 MB instead of
+//       the 31.5 MB dense f32 logits tensor per 4096 chess positions; softmax_compact_kernel then normalises in place.
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one lane), warps 2..5 = epilogue
 // (TMEM -> registers -> +bias (+residual) -> ReLU -> bf16/f32 -> global).  3-stage smem ring (two CTAs per SM), full/empty mbarriers.
 #pragma once
@@ -62,7 +65,7 @@ struct alignas(64) TcGemmParams {
     const uint32_t* n_ptr;
 };
 
-__global__ void __launch_bounds__(kTcThreads, 2) tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
+__device__ __forceinline__ void tc_gemm_body(const TcGemmParams& p, const int m_tile, const int n_tile) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint8_t* smem_a = smem;
@@ -74,8 +77,6 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_gemm_kernel(const __grid_con
 
     const uint32_t warp = threadIdx.x >> 5;
     const uint32_t lane = threadIdx.x & 31;
-    const int m_tile = blockIdx.x;
-    const int n_tile = blockIdx.y;
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&p.tma_a);
@@ -216,6 +217,36 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_gemm_kernel(const __grid_con
                     if (live && ((bits >> j) & 1u)) p.probs[pos++] = expf(x - mx) / sum;
                 }
             }
+        } else if (p.epi == 3) {
+            // ---- policy, many N tiles: masked compact write of this tile's 128 columns (softmax runs afterwards)
+            const int n = static_cast<int>(*p.n_ptr);
+            const bool live = grow < n;
+            const uint8_t* rec = p.recs + static_cast<size_t>(live ? grow : 0) * p.rl.rec_bytes;
+            const int w0 = n_tile * (p.n_umma >> 5);  // first 32-bit legal word of this tile
+            uint32_t pos = 0;
+            uint32_t legal[4] = {0, 0, 0, 0};
+            if (live) {
+                pos = *reinterpret_cast<const uint32_t*>(rec - 8);
+                for (int j = 0; j < w0; ++j) pos += __popc(legal_word(rec, p.rl, j));
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (w0 + j < p.rl.legal_words) legal[j] = legal_word(rec, p.rl, w0 + j);
+            }
+            for (int c0 = 0; c0 < p.n_umma; c0 += 16) {
+                float v[16];
+                ptx::tmem_ld_x16(taddr + c0, v);
+                const uint32_t bits = (legal[c0 >> 5] >> (c0 & 31)) & 0xFFFFu;
+                if (bits == 0) continue;
+                const int col = n_tile * p.n_umma + c0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    if ((bits >> j) & 1u) {
+                        float x = v[j] + __ldg(p.bias + col + j);
+                        if (!isfinite(x)) x = -FLT_MAX;
+                        p.probs[pos++] = x;
+                    }
+                }
+            }
         } else
         for (int c0 = 0; c0 < p.n_umma; c0 += 16) {
             float v[16];
@@ -275,6 +306,24 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_gemm_kernel(const __grid_con
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 2) ptx::tmem_dealloc(tmem_base, kTcTmemCols);
+}
+
+__global__ void __launch_bounds__(kTcThreads, 2) tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
+    tc_gemm_body(p, blockIdx.x, blockIdx.y);
+}
+
+// Two independent GEMMs in one launch: blockIdx.y == 0 runs problem `a` (one N tile), blockIdx.y >= 1 runs N tile
+// blockIdx.y - 1 of problem `b`.  Used for the two head FCs (value FC1 + tanh tail | policy FC + mask / softmax): the
+// value problem alone has only ceil(B / 128) CTAs with a 32-step latency-bound k-loop, so it hides behind the policy's.
+struct alignas(64) TcGemmDualParams {
+    TcGemmParams a;
+    TcGemmParams b;
+};
+__global__ void __launch_bounds__(kTcThreads, 2) tc_gemm_dual_kernel(const __grid_constant__ TcGemmDualParams d) {
+    if (blockIdx.y == 0)
+        tc_gemm_body(d.a, blockIdx.x, 0);
+    else
+        tc_gemm_body(d.b, blockIdx.x, static_cast<int>(blockIdx.y) - 1);
 }
 
 }  // namespace cb2

@@ -32,6 +32,11 @@
 //                               "input chunk ready" barrier after every 16 channels -- the k-chunk-outer MMA order
 //                               lets layer l+1 start while layer l's epilogue is still draining.
 // With two tiles per CTA the issuer alternates tiles, so one tile's epilogue hides behind the other tile's MMAs.
+//
+// The two 1x1 head convolutions (net_utils.py:69, :79) ride along as one extra "layer": a single weight stage holding
+// all 8 k-chunks of the [VH + PH][128] matrix (N = VH + PH <= 64 split across the pair like every other layer), no
+// taps, whose epilogue writes ReLU(bf16) straight into the FC kernels' A operands.  The 67 MB trunk output tensor
+// (and the two launches that re-read it) of the unfused arrangement never exists.
 #pragma once
 #include "kernels.cuh"
 #include "ptx.cuh"
@@ -60,12 +65,14 @@ struct alignas(64) TrunkFusedParams {
     const uint8_t* recs;     // packed records (planes first)
     const uint32_t* n_ptr;   // number of valid positions
     const float* bias;       // [layers][128] folded-BN bias
-    __nv_bfloat16* out;      // NHWC [boards * 64][128]
+    __nv_bfloat16* out_v;    // [boards * 64][vhp]  ReLU(value head conv)
+    __nv_bfloat16* out_p;    // [boards * 64][php]  ReLU(policy head conv)
     uint32_t* err;
     int rec_bytes;
     int planes;      // C_in <= 32
     int layers;      // 1 + 2R
     int num_rounds;  // ceil(boards / 8)
+    int vhp, php;    // padded head widths (multiples of 16, vhp + php <= 64)
 };
 
 // first weight stage of layer l (stem has 2 k-chunks, every other layer 8)
@@ -117,8 +124,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1) trunk
         if (lane == 0) {
             uint32_t it = 0;
             for (int rd = pair; rd < p.num_rounds; rd += num_pairs) {
-                for (int l = 0; l < p.layers; ++l) {
-                    const int nkc = l == 0 ? 2 : 8;
+                for (int l = 0; l <= p.layers; ++l) {             // l == layers: the head convs, one stage for all k-chunks
+                    const int nkc = l == 0 ? 2 : (l == p.layers ? 1 : 8);
                     for (int kc = 0; kc < nkc; ++kc, ++it) {
                         const uint32_t slot = it % 3, ph = (it / 3) & 1;
                         ptx::mbar_wait(&w_empty[slot], ph ^ 1, p.err, 0x1100 + slot);
@@ -150,6 +157,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1) trunk
             const bool leader_lane = ptx::elect_one();
             uint32_t act_par = 0;
             uint32_t it = 0;
+            const int nh = p.vhp + p.php;
+            const uint32_t idesc_head = ptx::umma_idesc_bf16(256, static_cast<uint32_t>(nh));
+            const uint64_t bh_hi64 = ptx::umma_desc_none_hi(static_cast<uint32_t>(nh / 2) * 16, 128);
+            const uint32_t bh_hi = static_cast<uint32_t>(bh_hi64 >> 32), bh_lo_fixed = static_cast<uint32_t>(bh_hi64);
             for (int rd = pair; rd < p.num_rounds; rd += num_pairs) {
                 for (int l = 0; l < p.layers; ++l) {
                     const int nkc = l == 0 ? 2 : 8;
@@ -179,6 +190,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1) trunk
                         if (leader_lane) ptx::umma_commit_pair_multicast(&w_empty[slot], 3);
                         __syncwarp();
                     }
+                }
+                // ---- head convs: 8 k-chunks, no taps, N = vhp + php, input = Q (the last conv2 wrote it), accumulator parity 1
+                {
+                    const uint32_t slot = it % 3, ph = (it / 3) & 1;
+                    ++it;
+                    ptx::mbar_wait(&w_full[slot], ph, p.err, 0x2100 + slot);
+                    const uint32_t b_lo0 = bh_lo_fixed | ((w_addr + slot * kFtWStage) >> 4);
+#pragma unroll
+                    for (int t = 0; t < 2; ++t) {
+                        const uint32_t d = tmem_base + static_cast<uint32_t>((t * 2 + 1) * 128);
+                        for (int kc = 0; kc < 8; ++kc) {
+                            const int bi = t * 8 + kc;
+                            ptx::mbar_wait(&act_full[bi], (act_par >> bi) & 1u, p.err, 0x2300 + bi);
+                            act_par ^= 1u << bi;
+                            ptx::tc_fence_after();
+                            const uint32_t a_lo = a_lo_fixed | ((act_addr + (t * 2 + 1) * kFtBufBytes + (2 * kc) * kFtLbo + kFtCell0 * 16) >> 4);
+                            if (leader_lane) ptx::umma_bf16_ss_pair_lohi(d, a_lo, a_hi, b_lo0 + kc * (nh / 2) * 2, bh_hi, idesc_head, kc != 0);
+                        }
+                        if (leader_lane) ptx::umma_commit_pair_multicast(&acc_full[t * 2 + 1], 3);
+                    }
+                    if (leader_lane) ptx::umma_commit_pair_multicast(&w_empty[slot], 3);
+                    __syncwarp();
                 }
             }
         }
@@ -225,7 +258,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1) trunk
             }
             for (int l = 0; l < p.layers; ++l) {
                 const int par = l & 1;
-                const bool last = l == p.layers - 1;
                 const bool has_resid = l >= 2 && par == 0;  // conv2 of a block: + block input (Q), result back into Q
                 uint8_t* outb = par ? bufP : bufQ;          // stem -> Q, conv1 -> P, conv2 -> Q
                 const float4* bias4 = reinterpret_cast<const float4*>(p.bias + l * 128);
@@ -274,21 +306,46 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1) trunk
                         const __nv_bfloat162 b2 = __floats2bfloat162_rn(fmaxf(v[2 * i], 0.0f), fmaxf(v[2 * i + 1], 0.0f));
                         o[i] = *reinterpret_cast<const uint32_t*>(&b2);
                     }
-                    if (last) {
-                        if (valid) {
-                            uint4* og = reinterpret_cast<uint4*>(p.out + (static_cast<size_t>(board) * 64 + cell) * 128 + kc * 16);
-                            og[0] = make_uint4(o[0], o[1], o[2], o[3]);
-                            og[1] = make_uint4(o[4], o[5], o[6], o[7]);
-                        }
-                    } else {
-                        *reinterpret_cast<uint4*>(outb + (2 * kc) * kFtLbo) = make_uint4(o[0], o[1], o[2], o[3]);
-                        *reinterpret_cast<uint4*>(outb + (2 * kc + 1) * kFtLbo) = make_uint4(o[4], o[5], o[6], o[7]);
-                        ptx::tc_fence_before();
-                        ptx::fence_proxy_async_smem();
-                        __syncwarp();
-                        if (lane == 0) ptx::mbar_arrive_cluster(leader_act + kc * 8);
+                    *reinterpret_cast<uint4*>(outb + (2 * kc) * kFtLbo) = make_uint4(o[0], o[1], o[2], o[3]);
+                    *reinterpret_cast<uint4*>(outb + (2 * kc + 1) * kFtLbo) = make_uint4(o[4], o[5], o[6], o[7]);
+                    ptx::tc_fence_before();
+                    ptx::fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive_cluster(leader_act + kc * 8);
+                }
+            }
+            // ---- both 1x1 head convolutions: accumulator (t, parity 1), columns [0, vhp) value, [vhp, vhp + php) policy
+            {
+                const float4* hb4 = reinterpret_cast<const float4*>(p.bias + p.layers * 128);
+                ptx::mbar_wait(&acc_full[t * 2 + 1], (acc_par >> 1) & 1u, p.err, 0x3200 + t);
+                acc_par ^= 1u << 1;
+                ptx::tc_fence_after();
+                const size_t row = static_cast<size_t>(board) * 64 + cell;
+                const int nh = p.vhp + p.php;
+                for (int cb = 0; cb < nh; cb += 16) {
+                    uint32_t raw[16];
+                    ptx::tmem_ld_x16_issue(tmem_row + static_cast<uint32_t>(128 + cb), raw);
+                    float4 bc[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) bc[i] = __ldg(hb4 + cb / 4 + i);
+                    ptx::tmem_ld_wait(raw);
+                    uint32_t o[8];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const __nv_bfloat162 a = __floats2bfloat162_rn(fmaxf(__uint_as_float(raw[4 * i + 0]) + bc[i].x, 0.0f),
+                                                                       fmaxf(__uint_as_float(raw[4 * i + 1]) + bc[i].y, 0.0f));
+                        const __nv_bfloat162 b = __floats2bfloat162_rn(fmaxf(__uint_as_float(raw[4 * i + 2]) + bc[i].z, 0.0f),
+                                                                       fmaxf(__uint_as_float(raw[4 * i + 3]) + bc[i].w, 0.0f));
+                        o[2 * i] = *reinterpret_cast<const uint32_t*>(&a);
+                        o[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&b);
+                    }
+                    if (valid) {
+                        uint4* og = cb < p.vhp ? reinterpret_cast<uint4*>(p.out_v + row * p.vhp + cb) : reinterpret_cast<uint4*>(p.out_p + row * p.php + (cb - p.vhp));
+                        og[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                        og[1] = make_uint4(o[4], o[5], o[6], o[7]);
                     }
                 }
+                ptx::tc_fence_before();
             }
         }
     }
