@@ -264,7 +264,7 @@ def main():
     ap.add_argument("--impl", default="cattus_b200", choices=["cattus_b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="device batch (positions per launch sequence); default per workload")
-    ap.add_argument("--streams", type=int, default=3)
+    ap.add_argument("--streams", type=int, default=4)
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU baseline work (rank 0, N=1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -208,6 +208,7 @@ Engine::Engine(const cattus_b200_desc& desc, const void* blob_bytes, size_t blob
         kernels_per_batch_ = static_cast<uint32_t>(ops_for(l, bucket_for(max_batch_), false).size());
     }
     for (uint32_t i = 0; i < n_streams; ++i) evaluators_.emplace_back([this] { evaluator_loop(); });
+    pack_pool_.reset(new PackPool(std::min(7u, std::max(1u, std::thread::hardware_concurrency() / 2))));
 }
 
 Engine::~Engine() {
@@ -218,6 +219,7 @@ Engine::~Engine() {
     q_cv_.notify_all();
     q_space_cv_.notify_all();
     for (auto& t : evaluators_) t.join();
+    pack_pool_.reset();
     cudaSetDevice(device_);
     cudaDeviceSynchronize();
     for (auto& lp : lanes_) {
@@ -895,6 +897,67 @@ void Engine::throw_device_error(const char* where, cudaError_t e) {
     throw Error(code ? CATTUS_B200_EDEVICE : CATTUS_B200_ECUDA, buf);
 }
 
+// ------------------------------------------------------------------------------------------------ pack pool
+PackPool::PackPool(unsigned helpers) {
+    for (unsigned i = 0; i < helpers; ++i) threads_.emplace_back([this] { worker(); });
+}
+PackPool::~PackPool() {
+    {
+        std::lock_guard<std::mutex> g(mu_);
+        stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto& t : threads_) t.join();
+}
+void PackPool::worker() {
+    uint64_t seen = 0;
+    for (;;) {
+        const std::function<void(int)>* job;
+        int slices;
+        {
+            std::unique_lock<std::mutex> g(mu_);
+            cv_.wait(g, [&] { return stop_ || gen_ != seen; });
+            if (stop_) return;
+            seen = gen_;
+            job = job_;
+            slices = slices_;
+        }
+        int done = 0;
+        for (int i; (i = next_.fetch_add(1)) < slices;) {
+            (*job)(i);
+            ++done;
+        }
+        if (done) {
+            std::lock_guard<std::mutex> g(mu_);
+            remaining_ -= done;
+            if (remaining_ == 0) done_cv_.notify_all();
+        }
+    }
+}
+bool PackPool::try_run(int slices, const std::function<void(int)>& fn) {
+    std::unique_lock<std::mutex> run(run_mu_, std::try_to_lock);
+    if (!run.owns_lock()) return false;
+    {
+        std::lock_guard<std::mutex> g(mu_);
+        job_ = &fn;
+        slices_ = slices;
+        remaining_ = slices;
+        next_.store(0);
+        ++gen_;
+    }
+    cv_.notify_all();
+    int done = 0;
+    for (int i; (i = next_.fetch_add(1)) < slices;) {
+        fn(i);
+        ++done;
+    }
+    std::unique_lock<std::mutex> g(mu_);
+    remaining_ -= done;
+    done_cv_.wait(g, [&] { return remaining_ == 0; });
+    job_ = nullptr;
+    return true;
+}
+
 // ------------------------------------------------------------------------------------------------ batches
 uint32_t Engine::pack_record(uint8_t* dst, const uint64_t* planes, const uint8_t* legal, uint32_t prob_offset) const {
     const int plane_bytes = rec_.planes * rec_.wpp * 8;
@@ -1061,6 +1124,11 @@ void Engine::eval_batch(const uint64_t* planes, const uint8_t* legal, uint32_t n
         std::chrono::steady_clock::time_point t0;
     };
     std::deque<InFlight> inflight;
+    static const bool trace = std::getenv("CATTUS_B200_TRACE_BATCH") != nullptr;  // diagnostic timeline on stderr
+    const auto call_t0 = std::chrono::steady_clock::now();
+    auto stamp = [&](const char* what, uint32_t first) {
+        if (trace) std::fprintf(stderr, "eval_batch %8.1f us  %s %u\n", std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - call_t0).count(), what, first);
+    };
     const size_t plane_words = static_cast<size_t>(rec_.planes) * rec_.wpp;
     const size_t bm = d_.bitmap_bytes();
     size_t prob_cursor = 0;
@@ -1068,7 +1136,9 @@ void Engine::eval_batch(const uint64_t* planes, const uint8_t* legal, uint32_t n
         InFlight f = inflight.front();
         inflight.pop_front();
         try {
+            stamp("drain wait", f.first);
             finish(*f.lane, f.n);
+            stamp("drain done", f.first);
         } catch (...) {
             release_lane(*f.lane);
             for (auto& o : inflight) release_lane(*o.lane);
@@ -1079,6 +1149,7 @@ void Engine::eval_batch(const uint64_t* planes, const uint8_t* legal, uint32_t n
         std::memcpy(probs_out + f.prob_base, f.lane->h_probs, sizeof(float) * f.total);
         note_batch(f.n, std::chrono::duration<double>(std::chrono::steady_clock::now() - f.t0).count());
         release_lane(*f.lane);
+        stamp("copied out", f.first);
     };
     try {
         for (uint32_t first = 0; first < n; first += max_batch_) {
@@ -1087,16 +1158,53 @@ void Engine::eval_batch(const uint64_t* planes, const uint8_t* legal, uint32_t n
             Lane& l = acquire_lane();
             uint32_t total = 0;
             try {
-                for (uint32_t i = 0; i < cn; ++i) {
-                    const uint32_t b = first + i;
-                    const uint32_t c = pack_record(l.h_in + kRecs0 + static_cast<size_t>(i) * rec_.rec_bytes, planes + b * plane_words,
-                                                   legal ? legal + b * bm : nullptr, total);
-                    prob_offsets[b] = static_cast<uint32_t>(prob_cursor + total);
-                    total += c;
+                auto pack_range = [&](uint32_t lo, uint32_t hi) {  // offsets relative to `lo`'s first probability
+                    uint32_t run = 0;
+                    for (uint32_t i = lo; i < hi; ++i) {
+                        const uint32_t b = first + i;
+                        const uint32_t c = pack_record(l.h_in + kRecs0 + static_cast<size_t>(i) * rec_.rec_bytes, planes + b * plane_words,
+                                                       legal ? legal + b * bm : nullptr, run);
+                        prob_offsets[b] = run;
+                        run += c;
+                    }
+                    return run;
+                };
+                constexpr uint32_t kSlices = 8;
+                uint32_t slice_total[kSlices] = {0};
+                std::string slice_error;
+                int slice_code = 0;
+                const uint32_t per = (cn + kSlices - 1) / kSlices;
+                const std::function<void(int)> job = [&](int sl) {
+                    const uint32_t lo = std::min(cn, static_cast<uint32_t>(sl) * per), hi = std::min(cn, lo + per);
+                    try {
+                        slice_total[sl] = pack_range(lo, hi);
+                    } catch (const Error& e) {
+                        std::lock_guard<std::mutex> g(m_mu_);
+                        slice_code = e.code;
+                        slice_error = e.what();
+                    }
+                };
+                if (cn >= 1024 && pack_pool_ && pack_pool_->try_run(static_cast<int>(kSlices), job)) {
+                    if (slice_code) throw Error(slice_code, slice_error);
+                    uint32_t base = 0;  // turn slice-relative offsets into chunk-relative (record prefix) and call-relative (output)
+                    for (uint32_t sl = 0; sl < kSlices; ++sl) {
+                        const uint32_t lo = std::min(cn, sl * per), hi = std::min(cn, lo + per);
+                        for (uint32_t i = lo; i < hi; ++i) {
+                            *reinterpret_cast<uint32_t*>(l.h_in + kRecs0 + static_cast<size_t>(i) * rec_.rec_bytes - kRecPrefix) += base;
+                            prob_offsets[first + i] += static_cast<uint32_t>(prob_cursor) + base;
+                        }
+                        base += slice_total[sl];
+                    }
+                    total = base;
+                } else {
+                    total = pack_range(0, cn);
+                    for (uint32_t i = 0; i < cn; ++i) prob_offsets[first + i] += static_cast<uint32_t>(prob_cursor);
                 }
                 if (prob_cursor + total > probs_cap) throw Error(CATTUS_B200_ERANGE, "probs_cap is smaller than the number of legal moves");
                 InFlight f{&l, first, cn, total, prob_cursor, std::chrono::steady_clock::now()};
+                stamp("packed", first);
                 submit(l, cn, total);
+                stamp("submitted", first);
                 inflight.push_back(f);
             } catch (...) {
                 release_lane(l);

@@ -103,6 +103,27 @@ struct Lane {
     std::map<uint32_t, cudaGraphExec_t> graphs;  // same key
 };
 
+// A few helper threads that split the host-side packing of a large `eval_batch` chunk (memcpy + popcount per record)
+// so that the first chunk reaches the GPU sooner and the host keeps ahead of a fast evaluator.
+class PackPool {
+  public:
+    explicit PackPool(unsigned helpers);
+    ~PackPool();
+    // fn(slice) for slice in [0, slices); the caller takes part; returns false (nothing run) if the pool is busy
+    bool try_run(int slices, const std::function<void(int)>& fn);
+
+  private:
+    void worker();
+    std::vector<std::thread> threads_;
+    std::mutex mu_, run_mu_;
+    std::condition_variable cv_, done_cv_;
+    const std::function<void(int)>* job_ = nullptr;
+    int slices_ = 0, remaining_ = 0;
+    std::atomic<int> next_{0};
+    uint64_t gen_ = 0;
+    bool stop_ = false;
+};
+
 struct LeafRequest {
     float* probs_out;
     uint32_t probs_cap;
@@ -206,6 +227,7 @@ class Engine {
     uint32_t* h_err_ = nullptr;
     uint32_t* d_err_ = nullptr;
 
+    std::unique_ptr<PackPool> pack_pool_;
     std::vector<uint32_t> resident_offsets_;  // host copy of the resident batch's probability offsets
 
     // L2 flush scratch for time_stage

@@ -26,8 +26,10 @@
 // tile = [layer parity 2][even-tap / odd-tap accumulator 2][16 channels]; the head convolution (32 columns) reuses the
 // tile's parity-0 half, which its own input wait proves free.
 //
-// Warps: 0..15 encode + epilogue (TMEM lane quarter = warp & 3, tiles t = (warp >> 2) mod 4), warp 16 issues the MMAs
-// (whole warp runs the loop so descriptors stay in uniform registers, one elected lane issues) and owns TMEM.
+// Warps: 0..15 encode + epilogue (TMEM lane quarter = warp & 3, tiles t = (warp >> 2) mod 4); warps 16 and 17 issue the
+// MMAs of the even / odd tile groups (whole warp runs the loop so descriptors stay in uniform registers, one elected
+// lane issues): a `tcgen05.mma` issue blocks for about the MMA's own duration, so a single issuer leaves the tensor
+// core idle during its per-group barrier wait + commit (≈480 of 1680 cycles, profiles/r01g); two issuers alternate.
 // Per-cell geometry (local board, cell index, pad or not) and all biases are tabulated in shared memory once.
 #pragma once
 #include "kernels.cuh"
@@ -43,8 +45,8 @@
 
 namespace cb2 {
 
-constexpr int kTsThreads = 544;
-constexpr int kTsIssuerWarp = 16;
+constexpr int kTsThreads = 576;
+constexpr int kTsIssuerWarp = 16;  // warps 16 and 17 issue MMAs (even / odd tile groups)
 constexpr int kTsMaxTiles = 8;
 constexpr int kTsTapBytes = 2 * 16 * 16;  // [k-half 2][oc 16][ic 8] bf16
 
@@ -138,8 +140,9 @@ __global__ void __launch_bounds__(kTsThreads, 1) trunk_small_kernel(const __grid
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    if (warp == kTsIssuerWarp) {
-        // ================================================================== MMA issuer
+    if (warp >= kTsIssuerWarp) {
+        // ================================================================== MMA issuers (warp 16: even groups, 17: odd)
+        const int issuer = static_cast<int>(warp) - kTsIssuerWarp;
         const uint32_t idesc = ptx::umma_idesc_bf16(128, 16);
         const uint32_t idesc_head = ptx::umma_idesc_bf16(128, static_cast<uint32_t>(nh));
         const uint64_t a_hi64 = ptx::umma_desc_none_hi(static_cast<uint32_t>(L.plane_bytes), 128);
@@ -159,7 +162,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) trunk_small_kernel(const __grid
                 const int nkc = l == 0 ? p.stem_kc : 1;
                 const uint32_t in_addr = (l & 1) ? q_addr : p_addr;  // stem and conv2 read P, conv1 and the heads read Q
                 const uint32_t par = static_cast<uint32_t>(l & 1);   // (layers + 1) is even: stage parity = l & 1 in every round
-                for (int t0 = 0; t0 < T; t0 += p.group_tiles) {
+                for (int t0 = issuer * p.group_tiles; t0 < T; t0 += 2 * p.group_tiles) {
                     // inputs: the epilogues (or the encode) of every tile of this group
                     CB2_TS_TRACE(const bool trace = p.dbg != nullptr && blockIdx.x == 0 && rd == 0 && t0 == 0 && lane == 0;)
                     CB2_TS_TRACE(const bool trace2 = p.dbg != nullptr && blockIdx.x == 0 && rd == 0 && lane == 0 && l < 8;)
