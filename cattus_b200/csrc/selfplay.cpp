@@ -210,6 +210,15 @@ struct HexRules {
         r.winner = p.winner ? static_cast<uint8_t>(3 - p.winner) : 0;
         return r;
     }
+    // the part of flipped() the evaluator needs (planes, legal mask, cache key): boards and turn only
+    Pos flipped_boards(const Pos& p) const {
+        Pos r;
+        r.red = transpose(p.blue);
+        r.blue = transpose(p.red);
+        r.turn = static_cast<uint8_t>(3 - p.turn);
+        r.empty = p.empty;
+        return r;
+    }
     int flip_move(int m) const { return tr[m]; }  // core.rs:36-38
     bool same(const Pos& a, const Pos& b) const { return a.red == b.red && a.blue == b.blue && a.turn == b.turn; }
     bool child_matches(const Pos& parent, int m, const Pos& target) const {
@@ -269,6 +278,7 @@ struct TttRules {
         r.winner = p.winner ? static_cast<uint8_t>(3 - p.winner) : 0;
         return r;
     }
+    Pos flipped_boards(const Pos& p) const { return flipped(p); }
     int flip_move(int m) const { return m; }
     bool same(const Pos& a, const Pos& b) const { return a.x == b.x && a.o == b.o && a.turn == b.turn; }
     bool child_matches(const Pos& parent, int m, const Pos& target) const {
@@ -294,15 +304,15 @@ class Cache {
     Cache(size_t max_size, int moves_num) : stride_(static_cast<size_t>(moves_num) + 1) {
         n_buckets_ = 1;
         while (n_buckets_ * kWays < max_size) n_buckets_ <<= 1;
+        meta_ = static_cast<Meta*>(std::calloc(n_buckets_, sizeof(Meta)));
         keys_ = static_cast<PosKey*>(std::calloc(n_buckets_ * kWays, sizeof(PosKey)));
-        seq_ = static_cast<uint32_t*>(std::calloc(n_buckets_ * kWays, sizeof(uint32_t)));
         vals_ = static_cast<float*>(std::calloc(n_buckets_ * kWays * stride_, sizeof(float)));
-        if (!keys_ || !seq_ || !vals_) throw SpError{CATTUS_B200_ENOMEM, "cannot allocate the position cache"};
+        if (!meta_ || !keys_ || !vals_) throw SpError{CATTUS_B200_ENOMEM, "cannot allocate the position cache"};
         for (auto& l : locks_) l.clear();
     }
     ~Cache() {
+        std::free(meta_);
         std::free(keys_);
-        std::free(seq_);
         std::free(vals_);
     }
     Cache(const Cache&) = delete;
@@ -310,12 +320,14 @@ class Cache {
 
     // copies the stored (probs..., value) of `k` into out[0 .. n_legal] and returns true on a hit
     bool find(const PosKey& k, int n_legal, float* out) {
-        const size_t b = bucket(k);
+        const uint64_t h = PosKeyHash()(k);
+        const size_t b = h & (n_buckets_ - 1);
+        const uint16_t tag = tag_of(h);
         Guard g(locks_[b & (kLocks - 1)]);
-        const size_t base = b * kWays;
+        const Meta& m = meta_[b];
         for (size_t w = 0; w < kWays; ++w)
-            if (seq_[base + w] && keys_[base + w] == k) {
-                std::memcpy(out, vals_ + (base + w) * stride_, sizeof(float) * (n_legal + 1));
+            if (m.tag[w] == tag && keys_[b * kWays + w] == k) {
+                std::memcpy(out, vals_ + (b * kWays + w) * stride_, sizeof(float) * (n_legal + 1));
                 return true;
             }
         return false;
@@ -323,32 +335,44 @@ class Cache {
     // stores val[0 .. n_legal] unless the key is already there (another thread got there first), in which case the
     // cached entry is copied back into `val` (cache.rs:52-63).  Returns true if it was inserted.
     bool insert(const PosKey& k, int n_legal, float* val) {
-        const size_t b = bucket(k);
+        const uint64_t h = PosKeyHash()(k);
+        const size_t b = h & (n_buckets_ - 1);
+        const uint16_t tag = tag_of(h);
         Guard g(locks_[b & (kLocks - 1)]);
-        const size_t base = b * kWays;
-        size_t victim = 0;
-        uint32_t oldest = UINT32_MAX;
-        for (size_t w = 0; w < kWays; ++w) {
-            const uint32_t sq = seq_[base + w];
-            if (sq && keys_[base + w] == k) {
-                std::memcpy(val, vals_ + (base + w) * stride_, sizeof(float) * (n_legal + 1));
+        Meta& m = meta_[b];
+        for (size_t w = 0; w < kWays; ++w)
+            if (m.tag[w] == tag && keys_[b * kWays + w] == k) {
+                std::memcpy(val, vals_ + (b * kWays + w) * stride_, sizeof(float) * (n_legal + 1));
                 return false;
             }
-            if (sq < oldest) {  // empty ways (0) first, then the oldest insertion
-                oldest = sq;
+        size_t victim = kWays;
+        for (size_t w = 0; w < kWays; ++w)
+            if (m.tag[w] == 0) {
                 victim = w;
+                break;
             }
+        if (victim == kWays) {  // bucket full: first in, first out within the bucket
+            victim = m.next;
+            m.next = static_cast<uint16_t>((m.next + 1) % kWays);
         }
-        keys_[base + victim] = k;
-        uint32_t stamp = ++clock_[b & (kLocks - 1)];
-        if (stamp == 0) stamp = ++clock_[b & (kLocks - 1)];
-        seq_[base + victim] = stamp;
-        std::memcpy(vals_ + (base + victim) * stride_, val, sizeof(float) * (n_legal + 1));
+        m.tag[victim] = tag;
+        keys_[b * kWays + victim] = k;
+        std::memcpy(vals_ + (b * kWays + victim) * stride_, val, sizeof(float) * (n_legal + 1));
         return true;
     }
 
   private:
     static constexpr size_t kWays = 8, kLocks = 4096;
+    // one 32-byte record per bucket: 16-bit tags (0 = empty way) filter the key compares, so a miss touches one line
+    struct alignas(32) Meta {
+        uint16_t tag[kWays];
+        uint16_t next;  // FIFO cursor once the bucket is full (ways fill in order 0..7 first)
+        uint16_t pad[7];
+    };
+    static uint16_t tag_of(uint64_t h) {
+        const uint16_t t = static_cast<uint16_t>(h >> 48);
+        return t ? t : 1;
+    }
     struct Guard {
         std::atomic_flag& f;
         explicit Guard(std::atomic_flag& fl) : f(fl) {
@@ -360,13 +384,11 @@ class Cache {
         }
         ~Guard() { f.clear(std::memory_order_release); }
     };
-    size_t bucket(const PosKey& k) const { return PosKeyHash()(k) & (n_buckets_ - 1); }
     size_t stride_, n_buckets_;
+    Meta* meta_ = nullptr;
     PosKey* keys_ = nullptr;
-    uint32_t* seq_ = nullptr;
     float* vals_ = nullptr;
     std::atomic_flag locks_[kLocks];
-    uint32_t clock_[kLocks] = {};
 };
 
 // One evaluator = the reference's NNetwork: a network behind a callback plus its own cache.
@@ -508,7 +530,10 @@ class Worker {
         params_[1] = params[1];
         evals_[0] = evals[0];
         evals_[1] = evals[1];
-        slots_.resize(std::max<uint32_t>(1, cfg.games_per_thread));
+        // no more concurrent games per worker than an even split of this call's games (else the first workers take them all)
+        const uint32_t stride = std::max<uint32_t>(1, cfg.game_stride), threads = std::max<uint32_t>(1, cfg.threads);
+        const uint32_t my_games = cfg.games_num > cfg.first_game ? (cfg.games_num - cfg.first_game + stride - 1) / stride : 0;
+        slots_.resize(std::max<uint32_t>(1, std::min<uint32_t>(cfg.games_per_thread, (my_games + threads - 1) / threads)));
         pending_[0].init(slots_.size());
         pending_[1].init(slots_.size());
         val_.resize(static_cast<size_t>(R.moves_num()) + 1);
@@ -830,7 +855,7 @@ class Worker {
         }
         // NNetwork::evaluate (net/mod.rs:74-87): flip -> cache -> network
         s.leaf_flipped = leaf_pos.turn != 1;
-        s.leaf_eval_pos = s.leaf_flipped ? R.flipped(leaf_pos) : leaf_pos;
+        s.leaf_eval_pos = s.leaf_flipped ? R.flipped_boards(leaf_pos) : leaf_pos;
         Evaluator& ev = *evals_[s.cur];
         const PosKey key = R.key(s.leaf_eval_pos);
         const int n_legal = popcount128(R.legal_mask(s.leaf_eval_pos));
