@@ -358,6 +358,21 @@ def main():
             ms = float(np.mean(nw.time_stage(4, nb, 10)))
             sweep.append({"batch": nb, "ms": ms, "positions_per_sec": nb / (ms * 1e-3)})
         sweep.append({"batch": batch, "ms": float(np.mean(ms_all)), "positions_per_sec": batch / (float(np.mean(ms_all)) * 1e-3)})
+    # ---------------- per-leaf latency: one blocking cattus_b200_eval at a time (what a single-tree UCI search sees;
+    # BASELINE configs[4], `--sim-num 10000`: NN part of one search = 10000 x this)
+    leaf = None
+    if rank == 0:
+        k = min(2000, positions_per_step)
+        for i in range(50):
+            nw.eval_planes(words[i], None if bitmaps is None else bitmaps[i])
+        lat = np.empty(k)
+        for i in range(k):
+            t0 = time.perf_counter()
+            nw.eval_planes(words[i], None if bitmaps is None else bitmaps[i])
+            lat[i] = time.perf_counter() - t0
+        leaf = {"api": "cattus_b200_eval (one blocking leaf at a time, host buffers)", "calls": int(k), "median_us": float(np.median(lat) * 1e6),
+                "p90_us": float(np.percentile(lat, 90) * 1e6), "evals_per_sec": float(k / lat.sum()),
+                "nn_seconds_per_10000_sim_search": float(np.median(lat) * 10000)}
     nw.close()
 
     # ---------------- self-play MCTS sims/s (second half of the BASELINE metric): C++ driver + this GPU's evaluator
@@ -438,6 +453,7 @@ def main():
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "batch_sweep": sweep,
+            "leaf_latency": leaf,
             "selfplay": selfplay,
         }
         print(json.dumps(line), flush=True)

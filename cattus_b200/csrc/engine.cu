@@ -712,7 +712,9 @@ void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
         fp.rec_bytes = rec_.rec_bytes;
         fp.planes = static_cast<int>(d_.c_in);
         fp.layers = 1 + 2 * static_cast<int>(d_.r);
-        fp.num_rounds = static_cast<int>(ceil_div(bucket, 8));
+        // small batches: one tile per CTA (4 boards per pair) while that still fits one wave -- half the MMAs per round
+        fp.tiles = static_cast<int>(ceil_div(bucket, 4)) <= sm / 2 ? 1 : 2;
+        fp.num_rounds = static_cast<int>(ceil_div(bucket, 4u * static_cast<uint32_t>(fp.tiles)));
         const int pairs = std::min(sm / 2, fp.num_rounds);
         Op op;
         op.stage = 1;

@@ -71,7 +71,8 @@ struct alignas(64) TrunkFusedParams {
     int rec_bytes;
     int planes;      // C_in <= 32
     int layers;      // 1 + 2R
-    int num_rounds;  // ceil(boards / 8)
+    int num_rounds;  // ceil(boards / (4 * tiles))
+    int tiles;       // 128-row tiles per CTA in use: 2 (8 boards per pair and round) or, for small batches, 1 (4 boards: half the MMAs per round)
     int vhp, php;    // padded head widths (multiples of 16, vhp + php <= 64)
 };
 
@@ -171,6 +172,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1) trunk
                         const uint32_t b_lo0 = b_lo_fixed | ((w_addr + slot * kFtWStage) >> 4);
 #pragma unroll
                         for (int t = 0; t < 2; ++t) {
+                            if (t >= p.tiles) break;
                             const int bi = t * 8 + kc;
                             ptx::mbar_wait(&act_full[bi], (act_par >> bi) & 1u, p.err, 0x2200 + bi);
                             act_par ^= 1u << bi;
@@ -199,6 +201,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1) trunk
                     const uint32_t b_lo0 = bh_lo_fixed | ((w_addr + slot * kFtWStage) >> 4);
 #pragma unroll
                     for (int t = 0; t < 2; ++t) {
+                        if (t >= p.tiles) break;
                         const uint32_t d = tmem_base + static_cast<uint32_t>((t * 2 + 1) * 128);
                         for (int kc = 0; kc < 8; ++kc) {
                             const int bi = t * 8 + kc;
@@ -216,7 +219,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1) trunk
             }
         }
         __syncwarp();
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && static_cast<int>(warp - 4) >> 2 < p.tiles) {
         // ================================================================== encode + epilogue (4 warps per tile)
         const int t = static_cast<int>(warp - 4) >> 2;
         const uint32_t q = warp & 3;  // TMEM lane quarter this warp may access
@@ -231,7 +234,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1) trunk
         const uint32_t tmem_row = tmem_base + ((q * 32u) << 16) + static_cast<uint32_t>(t * 2 * 128);
         uint32_t acc_par = 0;
         for (int rd = pair; rd < p.num_rounds; rd += num_pairs) {
-            const int board = (((rd * 2 + static_cast<int>(rank)) * 2 + t) << 1) + j;
+            const int board = ((rd * p.tiles + t) * 2 + static_cast<int>(rank)) * 2 + j;  // tile-major: a 1-tile round is boards 4 rd .. 4 rd + 3
             const bool valid = board < n_valid;
             // ---- planes_to_tensor for my cell: channels 0..31 of the stem input (planes >= C_in are zero)
             {
