@@ -387,7 +387,7 @@ def main():
         games_total = max(2, args.selfplay_games * world // 2 * 2)
         mc = SELFPLAY_CFG[args.selfplay_game]
         with CudaNetwork(export_blob(net.make_state_dict(sp_cfg, 0), sp_cfg.game), sp_cfg.game, device=local_rank, batch_size=max(64, min(4096, gpt)),
-                         n_streams=4, precision="bf16") as sp_nw:
+                         n_streams=8, precision="bf16") as sp_nw:
             runner = SelfPlayRunner(args.selfplay_game, {"mcts": mc, "threads": threads, "games_per_thread": gpt, "seed": 1})
             runner.generate_data(sp_nw, None, 2 * threads, first_game=rank, game_stride=world)  # warm-up (graphs, caches of the allocator)
             l0 = sp_nw.metrics()["model.kernel_launches"]

@@ -123,7 +123,7 @@ Engine::Engine(const cattus_b200_desc& desc, const void* blob_bytes, size_t blob
     if (desc.precision > CATTUS_B200_PRECISION_FP32_CHECK) throw Error(CATTUS_B200_EINVAL, "unknown precision");
     max_batch_ = desc.max_batch;
     precision_ = desc.precision;
-    const uint32_t n_streams = std::max<uint32_t>(1, std::min<uint32_t>(desc.n_streams, 8));
+    const uint32_t n_streams = std::max<uint32_t>(1, std::min<uint32_t>(desc.n_streams, 32));
 
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);

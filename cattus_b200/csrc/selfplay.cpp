@@ -401,12 +401,33 @@ struct Evaluator {
 
 // ------------------------------------------------------------------------------------------------ tree
 struct Edge {
-    float init_score;
-    float score_w;
-    uint32_t simulations_n;
     int32_t child;  // node index, -1 until first visited (positions of unvisited children are derived on demand)
     uint8_t m;
 };
+
+// select's inner step (mod.rs:211-226) for one node, structure-of-arrays so the compiler can vectorise it (two IEEE
+// divisions per child dominate a simulation otherwise).  Per lane exactly the scalar operations of
+// calc_selection_heuristic (mod.rs:233-244) in the reference's order: exploit = n == 0 ? 0 : w / n;
+// explore = (ef * init) * (sqrt(parent_simcount) / (1 + n)).  Returns the child the reference picks: petgraph's
+// edges() runs newest-first and max_by keeps the LAST maximum, i.e. the maximal child with the smallest insertion index.
+__attribute__((target_clones("avx2", "default"))) static int select_child(const float* __restrict__ init, const float* __restrict__ w,
+                                                                          const int32_t* __restrict__ n, int count, float ef,
+                                                                          float* __restrict__ val) {
+    int32_t simcount = 1;  // counts stay far below 2^31; signed so that the int -> float conversion is one instruction
+    for (int i = 0; i < count; ++i) simcount += n[i];
+    const float sq = std::sqrt(static_cast<float>(simcount));
+    for (int i = 0; i < count; ++i) {
+        const float nf = static_cast<float>(n[i]);
+        const float exploit = n[i] == 0 ? 0.0f : w[i] / nf;
+        const float explore = ef * init[i] * (sq / static_cast<float>(1 + n[i]));
+        val[i] = exploit + explore;
+    }
+    float best = val[0];
+    for (int i = 1; i < count; ++i) best = val[i] > best ? val[i] : best;
+    for (int i = 0; i < count; ++i)
+        if (val[i] == best) return i;
+    return count - 1;  // only reachable with NaNs, which the reference asserts away (mod.rs:444)
+}
 template <class Pos>
 struct Node {
     Pos pos;
@@ -416,12 +437,24 @@ struct Node {
 template <class Pos>
 struct Tree {
     std::vector<Node<Pos>> nodes;
-    std::vector<Edge> edges;
+    std::vector<Edge> edges;        // cold per-edge fields
+    std::vector<float> init_score;  // hot per-edge fields, same index as `edges` (MctsEdge, mod.rs:32-56)
+    std::vector<float> score_w;
+    std::vector<int32_t> simulations_n;
     int32_t root = -1;
     void clear() {
         nodes.clear();
         edges.clear();
+        init_score.clear();
+        score_w.clear();
+        simulations_n.clear();
         root = -1;
+    }
+    void push_edge(uint8_t m, float init, float w, int32_t n, int32_t child) {
+        edges.push_back(Edge{child, m});
+        init_score.push_back(init);
+        score_w.push_back(w);
+        simulations_n.push_back(n);
     }
 };
 
@@ -545,7 +578,11 @@ class Worker {
             for (auto& s : slots_) start_next_game(s);
             for (;;) {
                 bool any = false;
-                for (uint32_t i = 0; i < slots_.size(); ++i) {
+                const uint32_t ns = static_cast<uint32_t>(slots_.size());
+                for (uint32_t i = 0; i < ns; ++i) {
+                    // hundreds of trees per worker do not fit the cache: pull the next games' root rows in early
+                    if (i + 2 < ns) prefetch_root_node(slots_[i + 2]);
+                    if (i + 1 < ns) prefetch_root_edges(slots_[i + 1]);
                     Slot& s = slots_[i];
                     if (s.phase == kIdle) continue;
                     any = true;
@@ -583,6 +620,25 @@ class Worker {
     }
 
   private:
+    static void prefetch_root_node(const Slot& s) {
+        if (s.phase != kSimulate) return;
+        const Tree<Pos>& t = s.players[s.cur].tree;
+        if (t.root >= 0) __builtin_prefetch(&t.nodes[t.root]);
+    }
+    static void prefetch_root_edges(const Slot& s) {
+        if (s.phase != kSimulate) return;
+        const Tree<Pos>& t = s.players[s.cur].tree;
+        if (t.root < 0) return;
+        const Node<Pos>& nd = t.nodes[t.root];
+        if (nd.count <= 0) return;
+        for (int off = 0; off < nd.count; off += 16) {
+            __builtin_prefetch(&t.init_score[nd.first + off]);
+            __builtin_prefetch(&t.score_w[nd.first + off]);
+            __builtin_prefetch(&t.simulations_n[nd.first + off]);
+        }
+        __builtin_prefetch(&t.edges[nd.first]);
+    }
+
     // ---------------------------------------------------------------- game loop (self_play.rs:179-246)
     void start_next_game(Slot& s) {
         const uint32_t stride = std::max<uint32_t>(1, cfg_.game_stride);
@@ -718,6 +774,7 @@ class Worker {
                 t.clear();
         }
         if (t.root < 0) {
+            t.nodes.reserve(static_cast<size_t>(params_[s.cur].sim_num) + 64);
             t.nodes.emplace_back();
             t.nodes.back().pos = position;
             t.root = 0;
@@ -765,6 +822,9 @@ class Worker {
         Tree<Pos> nt;
         nt.nodes.reserve(t.nodes.size() / 4 + 16);
         nt.edges.reserve(t.edges.size() / 4 + 16);
+        nt.init_score.reserve(t.edges.size() / 4 + 16);
+        nt.score_w.reserve(t.edges.size() / 4 + 16);
+        nt.simulations_n.reserve(t.edges.size() / 4 + 16);
         nt.nodes.emplace_back();
         nt.nodes[0].pos = t.nodes[sub_root].pos;
         nt.root = 0;
@@ -777,7 +837,8 @@ class Worker {
             const int32_t nfirst = static_cast<int32_t>(nt.edges.size());
             nt.nodes[new_n].first = nfirst;
             nt.nodes[new_n].count = count;
-            for (int32_t i = count - 1; i >= 0; --i) nt.edges.push_back(t.edges[first + i]);
+            for (int32_t i = count - 1; i >= 0; --i)
+                nt.push_edge(t.edges[first + i].m, t.init_score[first + i], t.score_w[first + i], t.simulations_n[first + i], t.edges[first + i].child);
             for (int32_t i = 0; i < count; ++i) {
                 Edge& e = nt.edges[nfirst + i];
                 if (e.child >= 0) {
@@ -807,9 +868,9 @@ class Worker {
         }
         const float eps = P.noise_eps;
         for (int i = 0; i < count; ++i) {  // zip(edges() order = newest first, noise)
-            Edge& e = t.edges[first + (count - 1 - i)];
+            float& init = t.init_score[first + (count - 1 - i)];
             const float nz = static_cast<float>(noise_[i] / tot);
-            e.init_score = (1.0f - eps) * e.init_score + eps * nz;
+            init = (1.0f - eps) * init + eps * nz;
         }
     }
 
@@ -824,21 +885,7 @@ class Worker {
         for (;;) {
             const Node<Pos>& nd = t.nodes[node];
             if (nd.count == 0 || R.status(nd.pos) != 0) break;
-            const Edge* e = &t.edges[nd.first];
-            uint32_t simcount = 1;
-            for (int32_t i = 0; i < nd.count; ++i) simcount += e[i].simulations_n;
-            const float sq = std::sqrt(static_cast<float>(simcount));
-            int32_t best = -1;
-            float best_val = 0.0f;
-            for (int32_t i = nd.count - 1; i >= 0; --i) {  // edges(): newest first; max_by keeps the last maximum
-                const float exploit = e[i].simulations_n == 0 ? 0.0f : e[i].score_w / static_cast<float>(e[i].simulations_n);
-                const float explore = P.explore_factor * e[i].init_score * (sq / static_cast<float>(1 + e[i].simulations_n));
-                const float v = exploit + explore;
-                if (best < 0 || !(v < best_val)) {
-                    best = i;
-                    best_val = v;
-                }
-            }
+            const int32_t best = select_child(&t.init_score[nd.first], &t.score_w[nd.first], &t.simulations_n[nd.first], nd.count, P.explore_factor, sel_);
             const int32_t ei = nd.first + best;
             s.path.push_back(ei);
             int32_t c = t.edges[ei].child;
@@ -887,20 +934,25 @@ class Worker {
     void deliver(Slot& s, const float* val) {
         Tree<Pos>& t = s.players[s.cur].tree;
         const int32_t leaf = s.leaf;
-        u128 legal = R.legal_mask(s.leaf_eval_pos);
+        const u128 legal = R.legal_mask(s.leaf_eval_pos);
         const int32_t first = static_cast<int32_t>(t.edges.size());
-        int32_t count = 0;
-        while (legal) {  // legal_moves() of the evaluated position, ascending; un-flipped by flip_score_if_needed
-            const int m = ctz128(legal);
-            legal &= legal - 1;
-            Edge e;
-            e.m = static_cast<uint8_t>(s.leaf_flipped ? R.flip_move(m) : m);
-            e.init_score = val[count];
-            e.score_w = 0.0f;
-            e.simulations_n = 0;
-            e.child = -1;
-            t.edges.push_back(e);
-            ++count;
+        const int32_t count = popcount128(legal);
+        t.edges.resize(first + count);
+        t.init_score.resize(first + count);
+        t.score_w.resize(first + count);  // value-initialised: 0.0f
+        t.simulations_n.resize(first + count);
+        Edge* ed = t.edges.data() + first;
+        std::memcpy(t.init_score.data() + first, val, sizeof(float) * count);
+        int32_t k = 0;
+        for (int half = 0; half < 2; ++half) {  // legal_moves() of the evaluated position, ascending; un-flipped by flip_score_if_needed
+            uint64_t bits = static_cast<uint64_t>(legal >> (64 * half));
+            while (bits) {
+                const int m = 64 * half + __builtin_ctzll(bits);
+                bits &= bits - 1;
+                ed[k].child = -1;
+                ed[k].m = static_cast<uint8_t>(s.leaf_flipped ? R.flip_move(m) : m);
+                ++k;
+            }
         }
         t.nodes[leaf].first = first;
         t.nodes[leaf].count = count;
@@ -913,10 +965,9 @@ class Worker {
     // mod.rs:270-281
     void backpropagate(Slot& s, Tree<Pos>& t, float score) {
         for (size_t i = 0; i < s.path.size(); ++i) {
-            Edge& e = t.edges[s.path[i]];
             const uint8_t turn = t.nodes[path_nodes_at(s, t, i)].pos.turn;
-            e.simulations_n += 1;
-            e.score_w += turn == 1 ? score : -score;
+            t.simulations_n[s.path[i]] += 1;
+            t.score_w[s.path[i]] += turn == 1 ? score : -score;
         }
         s.sims_left -= 1;
         c_.simulations += 1;
@@ -933,11 +984,9 @@ class Worker {
         std::vector<std::pair<uint8_t, float>> probs;
         probs.reserve(root.count);
         uint32_t total = 0;
-        for (int32_t i = 0; i < root.count; ++i) total += t.edges[root.first + i].simulations_n;
-        for (int32_t i = root.count - 1; i >= 0; --i) {  // edges() order
-            const Edge& e = t.edges[root.first + i];
-            probs.emplace_back(e.m, static_cast<float>(e.simulations_n) / static_cast<float>(total));
-        }
+        for (int32_t i = 0; i < root.count; ++i) total += static_cast<uint32_t>(t.simulations_n[root.first + i]);
+        for (int32_t i = root.count - 1; i >= 0; --i)  // edges() order
+            probs.emplace_back(t.edges[root.first + i].m, static_cast<float>(t.simulations_n[root.first + i]) / static_cast<float>(total));
         const double secs = std::chrono::duration<double>(Clock::now() - s.search_t0).count();
         {
             std::lock_guard<std::mutex> g(sh_.mu);  // RunningAverage(0.99), util/metric.rs:1-20
@@ -1039,6 +1088,7 @@ class Worker {
     double eval_wait_ = 0.0;
     std::vector<double> noise_;
     std::vector<float> weights_, probs_, values_, val_, rows_;
+    float sel_[128];  // selection values of one node's children (<= 121 moves)
     Counters c_;
     std::vector<uint32_t> offsets_;
 };
