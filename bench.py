@@ -271,6 +271,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU baseline work (rank 0, N=1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-selfplay", action="store_true", help="skip the self-play sims/s leg")
+    ap.add_argument("--no-other-workloads", action="store_true", help="skip the brief hex5 evals/s leg of the default run")
     ap.add_argument("--selfplay-game", default="hex5", choices=sorted(SELFPLAY_CFG))
     ap.add_argument("--selfplay-games", type=int, default=4096, help="games per GPU in the self-play leg")
     ap.add_argument("--selfplay-threads", type=int, default=0, help="worker threads per GPU (0 = host cores / GPUs)")
@@ -377,6 +378,34 @@ def main():
                 "nn_seconds_per_10000_sim_search": float(np.median(lat) * 10000)}
     nw.close()
 
+    # ---------------- the other single-GPU configuration of BASELINE.json (configs[1], hex5) in the same line, briefly
+    others = []
+    if args.workload == DEFAULT_WORKLOAD and not args.no_other_workloads:
+        for oname in ("hex5",):
+            ocfg_name, obatch, oper = WORKLOADS[oname]
+            ocfg = net.CONFIGS[ocfg_name]
+            owords, _ = make_inputs(ocfg, obatch * oper, seed=replicas.rank_seed(0xCA7705, rank))
+            with CudaNetwork(export_blob(net.make_state_dict(ocfg, 0), ocfg.game), ocfg.game, device=local_rank, batch_size=obatch, n_streams=args.streams,
+                             precision="bf16") as onw:
+                onw.resident_upload(owords[:obatch])
+                onw.time_stage(4, obatch, 3)
+                barrier()
+                oms = onw.time_stage(4, obatch, 3 * oper)
+                barrier()
+                ot = max_over_ranks(float(oms.sum()) * 1e-3)
+                for _ in range(2):
+                    onw.eval_batch(owords)
+                barrier()
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    onw.eval_batch(owords)
+                ote = max_over_ranks(time.perf_counter() - t0)
+                barrier()
+                olaunches = 3 * oper * onw.info.kernels_per_batch + 5 * oper * onw.info.kernels_per_batch
+            others.append({"workload": oname, "note": CONFIG_NOTES[oname], "device_batch": obatch, "value": world * 3 * oper * obatch / ot,
+                           "e2e": world * 3 * oper * obatch / ote, "unit": "positions/s", "ms_per_device_batch": float(np.mean(oms)),
+                           "gpu_launches": int(olaunches)})
+
     # ---------------- self-play MCTS sims/s (second half of the BASELINE metric): C++ driver + this GPU's evaluator
     selfplay = None
     if not args.no_selfplay:
@@ -451,11 +480,12 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "positions/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": t_e2e / args.steps * 1e3, "api": "cattus_b200_eval_batch (host buffers -> pinned block -> H2D -> graph -> D2H)"},
-            "gpu_launches": int(launches) + (selfplay["gpu_launches"] if selfplay else 0),
+            "gpu_launches": int(launches) + (selfplay["gpu_launches"] if selfplay else 0) + sum(o["gpu_launches"] for o in others),
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "batch_sweep": sweep,
             "leaf_latency": leaf,
+            "other_workloads": others,
             "selfplay": selfplay,
         }
         print(json.dumps(line), flush=True)
