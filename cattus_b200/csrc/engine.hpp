@@ -132,6 +132,7 @@ struct LeafRequest {
     uint32_t count = 0;  // legal moves of this leaf
     int status = 1;      // 1 = pending, 0 = ok, <0 = error
     std::string error;
+    std::atomic<int> done{0};  // set (release) after status / outputs are written: callers spin on it before sleeping
 };
 
 class Engine {
@@ -220,6 +221,7 @@ class Engine {
     uint8_t* open_block_ = nullptr;  // pinned, same layout as Lane::h_in
     std::vector<LeafRequest*> open_reqs_;
     uint32_t open_total_ = 0;
+    std::atomic<uint32_t> open_count_{0};  // open_reqs_.size(), readable without the lock (evaluators spin on it briefly)
     std::vector<std::thread> evaluators_;
     bool stopping_ = false;
 

@@ -284,3 +284,48 @@ def test_full_size_properties(name, n, batch):
     _, ov, op = oracle_eval(name, words[idx], [legal[i] for i in idx])
     worst = max(float(np.abs(probs[offsets[i]:offsets[i + 1]] - op[k]).max()) for k, i in enumerate(idx) if len(legal[i]))
     assert worst <= TOL_BF16 and np.abs(values[idx] - ov).max() <= TOL_BF16
+
+
+@pytest.mark.parametrize("name", ["hex4", "chess_dev"])
+@pytest.mark.parametrize("precision", ["bf16", "fp32-check"])
+def test_non_finite_logits_are_clamped_like_the_reference(name, precision):
+    """run_net replaces non-finite logits by f32::MIN before the softmax (net/mod.rs:57-61): a legal move whose logit
+    overflowed gets probability 0, and a position whose legal moves ALL overflowed gets the uniform distribution
+    (exp(MIN - MIN) = 1 each).  Forced here with two policy-FC rows of 3e38 (finite weights, infinite dot product)."""
+    from cattus_b200 import CudaNetwork
+    from cattus_b200.export import export_blob
+
+    cfg = net.CONFIGS[name]
+    sd = {k: np.array(v, copy=True) for k, v in state_dict(name).items()}
+    hot = [3, 7]
+    sd["_policy_head.2.weight"][hot, :] = 3.0e38
+    n = 24
+    words, bitmaps, legal = synth_inputs(name, n, 77)
+    if bitmaps is not None:  # chess: make the hot moves legal everywhere, and ONLY them in the last two positions
+        for i in range(n):
+            keep = set(hot) if i >= n - 2 else set(legal[i]) | set(hot)
+            legal[i] = sorted(keep)
+            bitmaps[i] = games.bitmap_from_legal(legal[i], cfg.moves)
+    x = games.planes_to_tensor_fast(words, cfg.board_size, cfg.planes)
+    logits, o_values = net.convnet_forward(sd, cfg, x)
+    assert not np.isfinite(logits[:, hot]).any(), "the construction did not overflow the hot logits"
+    with CudaNetwork(export_blob(sd, cfg.game), cfg.game, batch_size=32, precision=precision) as nw:
+        probs, offsets, values = nw.eval_batch(words, bitmaps)
+    tol = TOL_BF16 if precision == "bf16" else TOL_FP32
+    seen_partial = seen_all = 0
+    for i in range(n):
+        ref = games.calc_moves_probs(legal[i], games.clamp_non_finite(logits[i]))
+        got = probs[offsets[i]:offsets[i + 1]]
+        assert len(got) == len(ref)
+        if not len(ref):
+            continue
+        assert np.abs(got - ref).max() <= tol
+        is_hot = np.array([m in hot for m in legal[i]])
+        if is_hot.all():
+            assert np.allclose(got, 1.0 / len(got), atol=1e-6)
+            seen_all += 1
+        elif is_hot.any():
+            assert (got[is_hot] == 0.0).all() and abs(float(got.sum()) - 1.0) < 1e-4
+            seen_partial += 1
+    assert seen_partial > 0 and (seen_all > 0 or bitmaps is None)
+    assert np.abs(values - o_values.reshape(-1)).max() <= tol
