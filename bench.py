@@ -176,6 +176,25 @@ def time_cpu_reference(cfg, sample_n, budget_s, steps=None, warmup=1, seed=1234)
     return done * sample_n / el, cores, el / done, f"{done} passes over {sample_n} positions, torch {cores} threads fp32 (reference torch-py engine restated) + C restatement of planes_to_tensor/calc_moves_probs"
 
 
+def time_cpu_run_duration_batch1(cfg, calls=200, seed=4321):
+    """model.run_duration of the reference's own bench (bench/inference_engine/main.py: batch_size 1, threads 1): median
+    seconds of one torch-py Model::run on one position."""
+    from oracle import games as og, net
+
+    sd = net.make_state_dict(cfg, 0)
+    model = net.TorchCpuModel(sd, cfg, 1, 1)
+    words, _ = make_inputs(cfg, 8, seed)
+    x = og.planes_to_tensor_fast(words, cfg.board_size, cfg.planes)
+    for i in range(10):
+        model.run(x[i % 8:i % 8 + 1])
+    t = np.empty(calls)
+    for i in range(calls):
+        t0 = time.perf_counter()
+        model.run(x[i % 8:i % 8 + 1])
+        t[i] = time.perf_counter() - t0
+    return float(np.median(t))
+
+
 SELFPLAY_CFG = {
     # training/config/hex5_cfg.yaml / hex7_cfg.yaml: engine.mcts with the self_play.engine_overrides applied
     "hex5": {"sim_num": 1400, "explore_factor": 1.41421, "temperature_policy": [[10, 1.0], [9999, 0.0]], "prior_noise_alpha": 0.03,
@@ -249,7 +268,8 @@ def run_reference_arm(args, rank, world):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "note": CONFIG_NOTES.get(args.workload, ""), "positions_per_step": sample_n,
                    "reference": "CPU inference path of the reference (host cores only; the reference has no GPU kernels)"},
-        "cpu_baseline": {"value": value, "unit": "positions/s", "cores": cores, "kind": "port", "sample": desc},
+        "cpu_baseline": {"value": value, "unit": "positions/s", "cores": cores, "kind": "port", "sample": desc,
+                         "model_run_duration_batch1_us": time_cpu_run_duration_batch1(cfg) * 1e6},
         "e2e": {"value": value, "unit": "positions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -374,6 +394,9 @@ def main():
             nw.eval_planes(words[i], None if bitmaps is None else bitmaps[i])
             lat[i] = time.perf_counter() - t0
         leaf = {"api": "cattus_b200_eval (one blocking leaf at a time, host buffers)", "calls": int(k), "median_us": float(np.median(lat) * 1e6),
+                # the score of the reference's own bench (bench/inference_engine/main.py:103: summary["metrics"]["model.run_duration"],
+                # RunningAverage(0.99) of the seconds around one Model::run at batch_size 1)
+                "model_run_duration_us": float(nw.metrics()["model.run_duration"] * 1e6),
                 "p90_us": float(np.percentile(lat, 90) * 1e6), "evals_per_sec": float(k / lat.sum()),
                 "nn_seconds_per_10000_sim_search": float(np.median(lat) * 10000)}
     nw.close()
@@ -466,7 +489,8 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sample_n = args.cpu_sample or (256 if cfg.filters >= 64 else 2048)
         v, cores, _, desc = time_cpu_reference(cfg, sample_n, budget_s=args.cpu_budget)
-        cpu_baseline = {"value": v, "unit": "positions/s", "cores": cores, "kind": "port", "sample": desc}
+        cpu_baseline = {"value": v, "unit": "positions/s", "cores": cores, "kind": "port", "sample": desc,
+                        "model_run_duration_batch1_us": time_cpu_run_duration_batch1(cfg) * 1e6}
 
     if rank == 0:
         line = {
