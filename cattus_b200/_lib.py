@@ -48,7 +48,7 @@ class SelfPlayCfg(C.Structure):
         ("n_temperatures", C.c_uint32), ("prior_noise_alpha", C.c_float), ("prior_noise_epsilon", C.c_float),
         ("cache_size", C.c_uint32), ("threads", C.c_uint32), ("games_per_thread", C.c_uint32), ("leaf_queue", C.c_uint32),
         ("games_num", C.c_uint32), ("first_game", C.c_uint32), ("game_stride", C.c_uint32), ("seed", C.c_uint64),
-        ("out_dir1", C.c_char_p), ("out_dir2", C.c_char_p), ("keep_records", C.c_uint32), ("reserved", C.c_uint32),
+        ("out_dir1", C.c_char_p), ("out_dir2", C.c_char_p), ("keep_records", C.c_uint32), ("groups_per_thread", C.c_uint32),
     ]
 
 
@@ -71,6 +71,8 @@ SYMBOLS = {
     "cattus_b200_get_info": (C.c_int, [_H, C.POINTER(Info)]),
     "cattus_b200_eval": (C.c_int, [_H, _u64p, _u8p, _f32p, C.c_uint32, _u32p, _f32p]),
     "cattus_b200_eval_batch": (C.c_int, [_H, _u64p, _u8p, C.c_uint32, _f32p, C.c_size_t, _u32p, _f32p]),
+    "cattus_b200_eval_batch_submit": (C.c_int, [_H, _u64p, _u8p, C.c_uint32, C.c_int, C.POINTER(C.c_int32)]),
+    "cattus_b200_eval_batch_wait": (C.c_int, [_H, C.c_int32, _f32p, C.c_size_t, _u32p, _f32p]),
     "cattus_b200_encode": (C.c_int, [_H, _u64p, C.c_uint32, C.c_uint32, _f32p]),
     "cattus_b200_run_dense": (C.c_int, [_H, _f32p, C.c_uint32, _f32p, _f32p]),
     "cattus_b200_resident_upload": (C.c_int, [_H, _u64p, _u8p, C.c_uint32]),

@@ -1015,6 +1015,15 @@ Lane& Engine::acquire_lane() {
         lane_cv_.wait(g);
     }
 }
+Lane* Engine::try_acquire_lane() {
+    std::lock_guard<std::mutex> g(lane_mu_);
+    for (size_t i = 0; i < lanes_.size(); ++i)
+        if (!lane_busy_[i]) {
+            lane_busy_[i] = 1;
+            return lanes_[i].get();
+        }
+    return nullptr;
+}
 void Engine::release_lane(Lane& l) {
     {
         std::lock_guard<std::mutex> g(lane_mu_);
@@ -1249,6 +1258,64 @@ void Engine::eval_batch(const uint64_t* planes, const uint8_t* legal, uint32_t n
         }
         throw;
     }
+}
+
+// Split form of eval_batch for one device batch: lets a caller keep several batches in flight (the self-play driver
+// simulates one group of games while another group's leaves are on the GPU).
+int Engine::eval_batch_submit(const uint64_t* planes, const uint8_t* legal, uint32_t n, bool block) {
+    if (n == 0 || n > max_batch_) throw Error(CATTUS_B200_ERANGE, "eval_batch_submit: n must be 1..max_batch");
+    if (!planes) throw Error(CATTUS_B200_EINVAL, "null argument");
+    CB2_CUDA(cudaSetDevice(device_));
+    Lane* lp = block ? &acquire_lane() : try_acquire_lane();
+    if (lp == nullptr) return -1;
+    Lane& l = *lp;
+    try {
+        const size_t plane_words = static_cast<size_t>(rec_.planes) * rec_.wpp;
+        const size_t bm = d_.bitmap_bytes();
+        l.async_counts.resize(n);
+        uint32_t total = 0;
+        for (uint32_t i = 0; i < n; ++i) {
+            const uint32_t c = pack_record(l.h_in + kRecs0 + static_cast<size_t>(i) * rec_.rec_bytes, planes + i * plane_words, legal ? legal + i * bm : nullptr, total);
+            l.async_counts[i] = c;
+            total += c;
+        }
+        l.async_n = n;
+        l.async_total = total;
+        l.async_t0 = std::chrono::steady_clock::now();
+        submit(l, n, total);
+    } catch (...) {
+        release_lane(l);
+        throw;
+    }
+    return l.index;
+}
+
+void Engine::eval_batch_wait(int ticket, float* probs_out, size_t probs_cap, uint32_t* prob_offsets, float* values_out) {
+    if (ticket < 0 || ticket >= static_cast<int>(lanes_.size())) throw Error(CATTUS_B200_EINVAL, "eval_batch_wait: bad ticket");
+    Lane& l = *lanes_[ticket];
+    if (l.async_n == 0) throw Error(CATTUS_B200_EINVAL, "eval_batch_wait: nothing in flight on this ticket");
+    const uint32_t n = l.async_n, total = l.async_total;
+    try {
+        if (!probs_out || !prob_offsets || !values_out) throw Error(CATTUS_B200_EINVAL, "null argument");
+        if (total > probs_cap) throw Error(CATTUS_B200_ERANGE, "probs_cap is smaller than the number of legal moves");
+        finish(l, n);
+        uint32_t run = 0;
+        for (uint32_t i = 0; i < n; ++i) {
+            prob_offsets[i] = run;
+            run += l.async_counts[i];
+        }
+        prob_offsets[n] = run;
+        std::memcpy(values_out, l.h_values, sizeof(float) * n);
+        std::memcpy(probs_out, l.h_probs, sizeof(float) * total);
+        note_batch(n, std::chrono::duration<double>(std::chrono::steady_clock::now() - l.async_t0).count());
+    } catch (...) {
+        cudaEventSynchronize(l.done);
+        l.async_n = 0;
+        release_lane(l);
+        throw;
+    }
+    l.async_n = 0;
+    release_lane(l);
 }
 
 void Engine::encode(const uint64_t* planes, uint32_t n, uint32_t batch, float* nchw_out) {
@@ -1522,6 +1589,20 @@ int cattus_b200_eval_batch(cattus_b200_t* h, const uint64_t* planes, const uint8
     return guarded([&] {
         if (!h) throw cb2::Error(CATTUS_B200_EINVAL, "null handle");
         h->engine->eval_batch(planes, legal_bitmaps, n, probs_out, probs_cap, prob_offsets, values_out);
+    });
+}
+
+int cattus_b200_eval_batch_submit(cattus_b200_t* h, const uint64_t* planes, const uint8_t* legal_bitmaps, uint32_t n, int block, int32_t* ticket) {
+    return guarded([&] {
+        if (!h || !ticket) throw cb2::Error(CATTUS_B200_EINVAL, "null argument");
+        *ticket = h->engine->eval_batch_submit(planes, legal_bitmaps, n, block != 0);
+    });
+}
+
+int cattus_b200_eval_batch_wait(cattus_b200_t* h, int32_t ticket, float* probs_out, size_t probs_cap, uint32_t* prob_offsets, float* values_out) {
+    return guarded([&] {
+        if (!h) throw cb2::Error(CATTUS_B200_EINVAL, "null handle");
+        h->engine->eval_batch_wait(ticket, probs_out, probs_cap, prob_offsets, values_out);
     });
 }
 

@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdint>
 #include <deque>
@@ -101,6 +102,10 @@ struct Lane {
     DeviceBuf d_dense;     // run_dense / encode staging (f32 NCHW)
     std::map<uint32_t, std::vector<Op>> ops;     // key: bucket | (dense_input << 31)
     std::map<uint32_t, cudaGraphExec_t> graphs;  // same key
+    // asynchronous batch in flight on this lane (eval_batch_submit .. eval_batch_wait)
+    uint32_t async_n = 0, async_total = 0;
+    std::vector<uint32_t> async_counts;
+    std::chrono::steady_clock::time_point async_t0;
 };
 
 // A few helper threads that split the host-side packing of a large `eval_batch` chunk (memcpy + popcount per record)
@@ -146,6 +151,10 @@ class Engine {
     void eval_leaf(const uint64_t* planes, const uint8_t* legal, LeafRequest* req);  // blocking
     void eval_batch(const uint64_t* planes, const uint8_t* legal, uint32_t n, float* probs_out, size_t probs_cap,
                     uint32_t* prob_offsets, float* values_out);
+    // split form of eval_batch for one device batch (n <= max_batch): submit returns a ticket (the lane) or -1 when
+    // `block` is false and every lane is busy; wait blocks, writes the outputs and frees the lane
+    int eval_batch_submit(const uint64_t* planes, const uint8_t* legal, uint32_t n, bool block);
+    void eval_batch_wait(int ticket, float* probs_out, size_t probs_cap, uint32_t* prob_offsets, float* values_out);
     void encode(const uint64_t* planes, uint32_t n, uint32_t batch, float* nchw_out);
     void run_dense(const float* nchw, uint32_t n, float* logits_out, float* values_out);
     void resident_upload(const uint64_t* planes, const uint8_t* legal, uint32_t n);
@@ -170,6 +179,7 @@ class Engine {
     void submit(Lane& lane, uint32_t n, uint32_t total_probs);  // H2D + graph + D2H + event (async)
     void finish(Lane& lane, uint32_t n);                         // wait + device error check + metrics
     Lane& acquire_lane();
+    Lane* try_acquire_lane();
     void release_lane(Lane& lane);
     void evaluator_loop();
     void note_batch(uint32_t n, double seconds);

@@ -80,6 +80,7 @@ class SelfPlayRunner:
         c.threads = int(cfg.get("threads", 1))
         c.games_per_thread = int(cfg.get("games_per_thread", 1))
         c.leaf_queue = int(cfg.get("leaf_queue", 0))
+        c.groups_per_thread = int(cfg.get("groups_per_thread", 0))
         c.seed = int(cfg.get("seed", 0)) & 0xFFFFFFFFFFFFFFFF
         self._c = c
 

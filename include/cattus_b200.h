@@ -129,6 +129,17 @@ int cattus_b200_eval(cattus_b200_t* h, const uint64_t* planes, const uint8_t* le
 int cattus_b200_eval_batch(cattus_b200_t* h, const uint64_t* planes, const uint8_t* legal_bitmaps, uint32_t n,
                            float* probs_out, size_t probs_cap, uint32_t* prob_offsets, float* values_out);
 
+/* Split form of eval_batch for ONE device batch (1 <= n <= max_batch), so that a caller can keep several batches in
+ * flight: submit packs the positions into a free evaluator stream's pinned block and enqueues copy-in, graph and
+ * copy-out; *ticket identifies the stream, or is -1 when `block` is 0 and every stream is busy (with `block` != 0 the
+ * call waits for a free stream).  wait blocks until that batch is done, writes the same outputs as eval_batch
+ * (prob_offsets has n + 1 entries) and frees the stream.  Every submitted ticket must be waited exactly once.
+ * Used by the self-play driver: one group of games is simulated while another group's leaves are on the GPU. */
+int cattus_b200_eval_batch_submit(cattus_b200_t* h, const uint64_t* planes, const uint8_t* legal_bitmaps, uint32_t n,
+                                  int block, int32_t* ticket);
+int cattus_b200_eval_batch_wait(cattus_b200_t* h, int32_t ticket, float* probs_out, size_t probs_cap,
+                                uint32_t* prob_offsets, float* values_out);
+
 /* Mirrors planes_to_tensor (engine/src/net/mod.rs:121-156) through the device encode kernel: writes the dense
  * f32 NCHW tensor [batch_size][planes][S][S]; rows >= n are zero.  Used by the bit-exact parity tests. */
 int cattus_b200_encode(cattus_b200_t* h, const uint64_t* planes, uint32_t n, uint32_t batch_size, float* nchw_out);

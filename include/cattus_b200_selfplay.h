@@ -11,7 +11,7 @@
  * evaluator never sees more than `threads` (<= 16) positions at once.  Here each worker thread advances
  * `games_per_thread` independent games as state machines; every game still runs its simulations strictly in the
  * reference's order (one leaf in flight per tree, so move choices are unchanged), but the leaves of all games of a
- * worker go to the GPU as ONE batch.  With `games_per_thread = 1` and `leaf_queue = 1` it degenerates to the
+ * worker (or of one of its slot groups, `groups_per_thread`) go to the GPU as ONE batch.  With `games_per_thread = 1` and `leaf_queue = 1` it degenerates to the
  * reference's arrangement: one blocking `cattus_b200_eval` per leaf, batched across threads by the pinned queue.
  *
  * Randomness: the reference draws Dirichlet noise and temperature samples from the unseeded thread-local
@@ -64,7 +64,8 @@ typedef struct cattus_b200_selfplay_cfg {
     const char* out_dir1; /* NULL: do not write .traindata files */
     const char* out_dir2;
     uint32_t keep_records; /* 1: keep every game's moves and data entries in memory for the accessors below */
-    uint32_t reserved;
+    uint32_t groups_per_thread; /* slot groups per worker, each with its own batch in flight while the worker simulates
+                                 * the next group (0 or 1 = one group; > 1 needs the B200 evaluator) */
 } cattus_b200_selfplay_cfg;
 
 /* Mirrors the summary file (self_play_cmd.rs:131-149) and the metric keys the trainer reads

@@ -114,3 +114,45 @@ def test_self_player_cli_is_a_drop_in_for_the_trainer(tmp_path):
     files = sorted(out.rglob("*.traindata"))
     assert len(files) == s["metrics"]["selfplay.searches"] and files[0].name == "00000000_000.traindata"
     assert all(f.stat().st_size == 6 * 8 + 16 * 4 + 1 for f in files)
+
+
+def test_gpu_selfplay_groups_with_batches_in_flight_same_games():
+    """groups_per_thread > 1: several batches of one worker in flight through eval_batch_submit / _wait, including more
+    groups than evaluator streams (the worker then takes its own oldest batch back first) -- same games as one group."""
+    base = dict(sim_num=40, cache_size=20000, prior_noise_alpha=0.3, prior_noise_epsilon=0.25, temperature_policy=[[6, 1.0], [9999, 0.0]], seed=11)
+    results = []
+    for threads, gpt, groups, streams in ((2, 64, 1, 2), (2, 64, 4, 8), (4, 32, 8, 2), (1, 128, 16, 3)):
+        with make_network("hex5", batch_size=128, n_streams=streams) as nw:
+            cfg = cfg_with(threads=threads, games_per_thread=gpt, groups_per_thread=groups, **base)
+            summary, recs = SelfPlayRunner("hex5", cfg).generate_data(nw, None, 128, keep_records=True)
+            results.append([(r.game_idx, r.moves, r.winner) for r in recs])
+            assert summary["player1_wins"] + summary["player2_wins"] == 128
+    for r in results[1:]:
+        assert r == results[0]
+
+
+def test_eval_batch_submit_wait_matches_eval_batch():
+    import ctypes as C
+
+    from cattus_b200 import _lib
+    from tests.util import synth_inputs
+
+    words, _, legal = synth_inputs("hex7", 100, 5)
+    with make_network("hex7", batch_size=64, n_streams=2) as nw:
+        ref_p, ref_o, ref_v = nw.eval_batch(words[:64])
+        lib = _lib.load()
+        t1, t2, t3 = C.c_int32(-5), C.c_int32(-5), C.c_int32(-5)
+        w = np.ascontiguousarray(words, dtype=np.uint64)
+        ptr = lambda a, t: a.ctypes.data_as(t)  # noqa: E731
+        _lib.check(lib.cattus_b200_eval_batch_submit(nw._h, ptr(w[:64], _lib._u64p), None, 64, 0, C.byref(t1)))
+        _lib.check(lib.cattus_b200_eval_batch_submit(nw._h, ptr(w[64:], _lib._u64p), None, 36, 0, C.byref(t2)))
+        _lib.check(lib.cattus_b200_eval_batch_submit(nw._h, ptr(w[:8], _lib._u64p), None, 8, 0, C.byref(t3)))
+        assert t1.value >= 0 and t2.value >= 0 and t1.value != t2.value and t3.value == -1  # both streams busy, non-blocking
+        probs = np.empty(64 * 49, np.float32)
+        offs = np.empty(65, np.uint32)
+        vals = np.empty(64, np.float32)
+        _lib.check(lib.cattus_b200_eval_batch_wait(nw._h, t1.value, ptr(probs, _lib._f32p), probs.size, ptr(offs, _lib._u32p), ptr(vals, _lib._f32p)))
+        assert np.array_equal(offs, ref_o) and np.array_equal(probs[: offs[64]], ref_p) and np.array_equal(vals, ref_v)
+        _lib.check(lib.cattus_b200_eval_batch_wait(nw._h, t2.value, ptr(probs, _lib._f32p), probs.size, ptr(offs, _lib._u32p), ptr(vals, _lib._f32p)))
+        assert offs[36] == sum(len(l) for l in legal[64:])
+        assert lib.cattus_b200_eval_batch_wait(nw._h, t2.value, ptr(probs, _lib._f32p), probs.size, ptr(offs, _lib._u32p), ptr(vals, _lib._f32p)) == _lib.EINVAL
