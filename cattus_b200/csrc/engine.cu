@@ -744,7 +744,9 @@ void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
             return best > 0.0;
         };
         int T = kTsMaxTiles, tpg = kTsMaxTiles, bpg = 0;
-        for (int cand = 1; cand <= kTsMaxTiles; cand *= 2) {
+        int min_tiles = 1;
+        if (const char* e = std::getenv("CATTUS_B200_TRUNK_MIN_TILES")) min_tiles = std::max(1, std::atoi(e));  // experiment knob
+        for (int cand = min_tiles; cand <= kTsMaxTiles; cand *= 2) {
             int g = 0, b = 0;
             if (!plan(cand, g, b)) continue;
             const int per_round = b * (cand / g);
