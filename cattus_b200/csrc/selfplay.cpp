@@ -515,6 +515,10 @@ class Worker {
         bool leaf_flipped = false;
         Pos leaf_eval_pos;  // the position as sent to the network (Player1 to move)
         uint32_t wait_row = 0;  // row of the pending batch this slot is parked on
+        int32_t sel_node = -1;  // node the in-progress select stands on (-1: no simulation in progress)
+        bool sel_rows_ready = false;  // its children's rows have been requested (prefetched) one ring turn ago
+        PosKey leaf_key{0, 0};        // cache key of the leaf being evaluated
+        int leaf_n_legal = 0;
         uint32_t group = 0;     // slot group (one batch per group and evaluator)
         Clock::time_point search_t0;
         GameRecord rec;
@@ -596,6 +600,7 @@ class Worker {
             for (uint32_t i = 0; i < gr.count; ++i) slots_[gr.first + i].group = g;
         }
         val_.resize(static_cast<size_t>(R.moves_num()) + 1);
+        if (const char* e = std::getenv("CATTUS_B200_SELFPLAY_RING")) ring_size_ = std::max(1, std::min<int>(kMaxRing, std::atoi(e)));
         abi_wpp_ = (R.moves_num() + 63) / 64;
     }
 
@@ -607,16 +612,7 @@ class Worker {
                 for (Group& gr : groups_) {
                     for (int e = 0; e < 2; ++e)
                         if (gr.ticket[e] >= 0) collect(gr, e);
-                    for (uint32_t k = 0; k < gr.count; ++k) {
-                        const uint32_t i = gr.first + k;
-                        // many trees per worker do not fit the cache: pull the next games' root rows in early
-                        if (k + 2 < gr.count) prefetch_root_node(slots_[i + 2]);
-                        if (k + 1 < gr.count) prefetch_root_edges(slots_[i + 1]);
-                        Slot& s = slots_[i];
-                        if (s.phase == kIdle) continue;
-                        any = true;
-                        if (s.phase != kWaitEval) advance(i);
-                    }
+                    any |= run_group(gr);
                     if (sh_.failed.load(std::memory_order_relaxed)) {
                         drain_all();
                         return;
@@ -653,25 +649,6 @@ class Worker {
     }
 
   private:
-    static void prefetch_root_node(const Slot& s) {
-        if (s.phase != kSimulate) return;
-        const Tree<Pos>& t = s.players[s.cur].tree;
-        if (t.root >= 0) __builtin_prefetch(&t.nodes[t.root]);
-    }
-    static void prefetch_root_edges(const Slot& s) {
-        if (s.phase != kSimulate) return;
-        const Tree<Pos>& t = s.players[s.cur].tree;
-        if (t.root < 0) return;
-        const Node<Pos>& nd = t.nodes[t.root];
-        if (nd.count <= 0) return;
-        for (int off = 0; off < nd.count; off += 16) {
-            __builtin_prefetch(&t.init_score[nd.first + off]);
-            __builtin_prefetch(&t.score_w[nd.first + off]);
-            __builtin_prefetch(&t.simulations_n[nd.first + off]);
-        }
-        __builtin_prefetch(&t.edges[nd.first]);
-    }
-
     // ---------------------------------------------------------------- game loop (self_play.rs:179-246)
     void start_next_game(Slot& s) {
         const uint32_t stride = std::max<uint32_t>(1, cfg_.game_stride);
@@ -693,32 +670,99 @@ class Worker {
         s.phase = kStartMove;
     }
 
-    void advance(uint32_t si) {
-        Slot& s = slots_[si];
-        for (;;) {
-            if (s.phase == kStartMove) {
-                const Pos& pos = s.history.back();
-                const int st = R.status(pos);
-                if (st != 0) {
-                    finish_game(s, st);
-                    start_next_game(s);
-                    if (s.phase == kIdle) return;
-                    continue;
-                }
-                int who = pos.turn;  // self_play.rs:198-205
-                if (s.game_idx % 2 == 1) who = 3 - who;
-                s.cur = who - 1;
-                begin_search(s);
-                s.phase = kSimulate;
+    // The games of a group are advanced INTERLEAVED: a ring of `ring_size_` games each does one small step per turn (one level
+    // of select, split into "request the node's child rows" and "pick the child"), so that the cache misses of one
+    // game's tree walk overlap with the work of the others -- with hundreds of trees per worker nearly every node
+    // visit is a miss.  Each game still runs its own simulations strictly in order; only the interleaving between
+    // games changes, which no result depends on.
+    bool run_group(Group& gr) {
+        bool any = false;
+        uint32_t ring[kMaxRing];
+        uint32_t in_ring = 0, next = 0;
+        auto admit = [&]() {
+            while (next < gr.count && in_ring < ring_size_) {
+                const uint32_t i = gr.first + next++;
+                const Slot& s = slots_[i];
+                if (s.phase == kIdle) continue;
+                any = true;
+                if (s.phase == kWaitEval) continue;
+                ring[in_ring++] = i;
             }
-            if (s.phase == kSimulate) {
-                while (s.sims_left > 0) {
-                    if (!simulate_once(si)) return;  // parked on the evaluator
+        };
+        admit();
+        while (in_ring) {
+            for (uint32_t r = 0; r < in_ring;) {
+                if (step(ring[r])) {
+                    ++r;
+                } else {  // parked on the evaluator or out of games: hand the ring place to the next game of the group
+                    ring[r] = ring[--in_ring];
+                    admit();
                 }
-                end_search(s);
-                s.phase = kStartMove;
             }
         }
+        return any;
+    }
+
+    // One small unit of work for game `si`; false when the game left the runnable state (parked or idle).
+    bool step(uint32_t si) {
+        Slot& s = slots_[si];
+        if (s.phase == kStartMove) {
+            const Pos& pos = s.history.back();
+            const int st = R.status(pos);
+            if (st != 0) {
+                finish_game(s, st);
+                start_next_game(s);
+                return s.phase != kIdle;
+            }
+            int who = pos.turn;  // self_play.rs:198-205
+            if (s.game_idx % 2 == 1) who = 3 - who;
+            s.cur = who - 1;
+            begin_search(s);
+            s.phase = kSimulate;
+            s.sel_node = -1;
+            return true;
+        }
+        // kSimulate
+        Tree<Pos>& t = s.players[s.cur].tree;
+        if (s.sel_node < 0) {
+            if (s.sims_left == 0) {
+                end_search(s);
+                s.phase = kStartMove;
+                return true;
+            }
+            s.path.clear();  // select (mod.rs:199-231) starts at the root
+            s.sel_node = t.root;
+            s.sel_rows_ready = false;
+            __builtin_prefetch(&t.nodes[t.root]);
+            return true;
+        }
+        const int32_t node = s.sel_node;
+        const Node<Pos>& nd = t.nodes[node];
+        if (nd.count == 0 || R.status(nd.pos) != 0) {
+            s.sel_node = -1;
+            if (at_leaf(s, node)) return true;  // terminal: backpropagated
+            return evaluate_leaf(si);
+        }
+        if (!s.sel_rows_ready) {
+            for (int off = 0; off < nd.count; off += 16) {
+                __builtin_prefetch(&t.init_score[nd.first + off]);
+                __builtin_prefetch(&t.score_w[nd.first + off]);
+                __builtin_prefetch(&t.simulations_n[nd.first + off]);
+            }
+            s.sel_rows_ready = true;
+            return true;
+        }
+        const int32_t best = select_child(&t.init_score[nd.first], &t.score_w[nd.first], &t.simulations_n[nd.first], nd.count, params_[s.cur].explore_factor, sel_);
+        const int32_t ei = nd.first + best;
+        s.path.push_back(ei);
+        int32_t c = t.edges[ei].child;
+        if (c < 0)
+            c = materialise(t, node, ei);
+        else
+            __builtin_prefetch(&t.nodes[c]);
+        s.sel_node = c;
+        s.sel_rows_ready = false;
+        return true;
     }
 
     void finish_game(Slot& s, int status) {
@@ -907,24 +951,10 @@ class Worker {
         }
     }
 
-    // One develop_tree iteration (mod.rs:158-195).  Returns false if the leaf was parked on the evaluator.
-    bool simulate_once(uint32_t si) {
-        Slot& s = slots_[si];
+    // The rest of one develop_tree iteration once select has reached `node` (mod.rs:162-195), first half: terminal
+    // leaves are backpropagated at once (returns true); otherwise the position to evaluate and its cache key are set up.
+    bool at_leaf(Slot& s, int32_t node) {
         Tree<Pos>& t = s.players[s.cur].tree;
-        const Params& P = params_[s.cur];
-        // select (mod.rs:199-231)
-        s.path.clear();
-        int32_t node = t.root;
-        for (;;) {
-            const Node<Pos>& nd = t.nodes[node];
-            if (nd.count == 0 || R.status(nd.pos) != 0) break;
-            const int32_t best = select_child(&t.init_score[nd.first], &t.score_w[nd.first], &t.simulations_n[nd.first], nd.count, P.explore_factor, sel_);
-            const int32_t ei = nd.first + best;
-            s.path.push_back(ei);
-            int32_t c = t.edges[ei].child;
-            if (c < 0) c = materialise(t, node, ei);
-            node = c;
-        }
         s.leaf = node;
         const Pos& leaf_pos = t.nodes[node].pos;
         const int st = R.status(leaf_pos);
@@ -936,9 +966,17 @@ class Worker {
         // NNetwork::evaluate (net/mod.rs:74-87): flip -> cache -> network
         s.leaf_flipped = leaf_pos.turn != 1;
         s.leaf_eval_pos = s.leaf_flipped ? R.flipped_boards(leaf_pos) : leaf_pos;
+        s.leaf_key = R.key(s.leaf_eval_pos);
+        s.leaf_n_legal = popcount128(R.legal_mask(s.leaf_eval_pos));
+        return false;
+    }
+
+    // cache lookup, else join the group's batch.  Returns false if the leaf was parked on the evaluator.
+    bool evaluate_leaf(uint32_t si) {
+        Slot& s = slots_[si];
         Evaluator& ev = *evals_[s.cur];
-        const PosKey key = R.key(s.leaf_eval_pos);
-        const int n_legal = popcount128(R.legal_mask(s.leaf_eval_pos));
+        const PosKey key = s.leaf_key;
+        const int n_legal = s.leaf_n_legal;
         if (ev.cache && ev.cache->find(key, n_legal, val_.data())) {
             c_.cache_hits += 1;
             deliver(s, val_.data());
@@ -1188,6 +1226,8 @@ class Worker {
     std::vector<double> noise_;
     std::vector<float> weights_, probs_, values_, val_, rows_;
     float sel_[128];  // selection values of one node's children (<= 121 moves)
+    static constexpr uint32_t kMaxRing = 32;
+    uint32_t ring_size_ = 8;  // games advanced interleaved (memory-level parallelism of the tree walks); CATTUS_B200_SELFPLAY_RING
     Counters c_;
     std::vector<uint32_t> offsets_;
 };
