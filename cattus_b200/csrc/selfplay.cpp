@@ -114,21 +114,29 @@ struct PosKeyHash {
     }
 };
 
-struct HexPos {
-    u128 red = 0, blue = 0, left_red_reach = 0, top_blue_reach = 0;
+// Board word W: uint64_t for boards up to 8x8 (every shipped hex config: half the node size and single-instruction bit
+// operations), unsigned __int128 up to 11x11 (the reference's u128, hex/core.rs:52-54).
+static inline int ctz_word(uint64_t x) { return __builtin_ctzll(x); }
+static inline int ctz_word(u128 x) { return ctz128(x); }
+
+template <class W>
+struct HexPosT {
+    W red = 0, blue = 0, left_red_reach = 0, top_blue_reach = 0;
     uint8_t turn = 1, empty = 0, winner = 0;
 };
 
 // engine/src/hex/core.rs
-struct HexRules {
-    using Pos = HexPos;
+template <class W>
+struct HexRulesT {
+    using Pos = HexPosT<W>;
+    static W bit(int i) { return static_cast<W>(1) << i; }
     int s = 0, cells = 0;
-    u128 full = 0, col0 = 0, col_last = 0, row0 = 0, row_last = 0;
-    u128 nb[121];
+    W full = 0, col0 = 0, col_last = 0, row0 = 0, row_last = 0;
+    W nb[121];
     uint8_t tr[121];
 
-    explicit HexRules(int size) : s(size), cells(size * size) {
-        full = cells == 128 ? ~static_cast<u128>(0) : (bit128(cells) - 1);
+    explicit HexRulesT(int size) : s(size), cells(size * size) {
+        full = cells == static_cast<int>(8 * sizeof(W)) ? ~static_cast<W>(0) : static_cast<W>(bit(cells) - 1);
         const int dirs[6][2] = {{0, 1}, {-1, 0}, {-1, -1}, {0, -1}, {1, 0}, {1, 1}};  // core.rs:204
         for (int r = 0; r < s; ++r)
             for (int c = 0; c < s; ++c) {
@@ -137,12 +145,12 @@ struct HexRules {
                 nb[i] = 0;
                 for (auto& d : dirs) {
                     const int nr = r + d[0], nc = c + d[1];
-                    if (nr >= 0 && nr < s && nc >= 0 && nc < s) nb[i] |= bit128(nr * s + nc);
+                    if (nr >= 0 && nr < s && nc >= 0 && nc < s) nb[i] |= bit(nr * s + nc);
                 }
-                if (c == 0) col0 |= bit128(i);
-                if (c == s - 1) col_last |= bit128(i);
-                if (r == 0) row0 |= bit128(i);
-                if (r == s - 1) row_last |= bit128(i);
+                if (c == 0) col0 |= bit(i);
+                if (c == s - 1) col_last |= bit(i);
+                if (r == 0) row0 |= bit(i);
+                if (r == s - 1) row_last |= bit(i);
             }
     }
     int moves_num() const { return cells; }
@@ -157,23 +165,23 @@ struct HexRules {
         if (p.empty == 0) return 3;
         return 0;
     }
-    u128 legal_mask(const Pos& p) const { return full & ~(p.red | p.blue); }  // core.rs:297-305 (ascending index)
+    u128 legal_mask(const Pos& p) const { return static_cast<u128>(static_cast<W>(full & ~(p.red | p.blue))); }  // core.rs:297-305 (ascending index)
     // core.rs:215-264: flood the player's reach map from the new stone; the first end-edge cell reached wins.
     void update_reach(Pos& p, int idx, int player) const {
-        const u128 board = player == 1 ? p.red : p.blue;
-        u128& reach = player == 1 ? p.left_red_reach : p.top_blue_reach;
-        const u128 begin = player == 1 ? col0 : row0;
-        const u128 end = player == 1 ? col_last : row_last;
-        if (!((begin & bit128(idx)) || (nb[idx] & reach))) return;
-        u128 layer = bit128(idx);
+        const W board = player == 1 ? p.red : p.blue;
+        W& reach = player == 1 ? p.left_red_reach : p.top_blue_reach;
+        const W begin = player == 1 ? col0 : row0;
+        const W end = player == 1 ? col_last : row_last;
+        if (!((begin & bit(idx)) || (nb[idx] & reach))) return;
+        W layer = bit(idx);
         reach |= layer;
         while (layer) {
-            const int i = ctz128(layer);
-            layer &= ~bit128(i);
-            if (end & bit128(i)) {
+            const int i = ctz_word(layer);
+            layer &= static_cast<W>(~bit(i));
+            if (end & bit(i)) {
                 p.winner = static_cast<uint8_t>(player);
             } else {
-                const u128 add = nb[i] & board & ~reach;
+                const W add = nb[i] & board & static_cast<W>(~reach);
                 reach |= add;
                 layer |= add;
             }
@@ -182,20 +190,20 @@ struct HexRules {
     Pos moved(const Pos& p, int m) const {  // core.rs:272-285
         Pos r = p;
         if (r.turn == 1)
-            r.red |= bit128(m);
+            r.red |= bit(m);
         else
-            r.blue |= bit128(m);
+            r.blue |= bit(m);
         update_reach(r, m, r.turn);
         r.empty -= 1;
         r.turn = static_cast<uint8_t>(3 - r.turn);
         return r;
     }
-    u128 transpose(u128 bb) const {  // HexBitboard::flip, core.rs:61-71
-        u128 f = 0;
+    W transpose(W bb) const {  // HexBitboard::flip, core.rs:61-71
+        W f = 0;
         while (bb) {
-            const int i = ctz128(bb);
+            const int i = ctz_word(bb);
             bb &= bb - 1;
-            f |= bit128(tr[i]);
+            f |= bit(tr[i]);
         }
         return f;
     }
@@ -222,11 +230,11 @@ struct HexRules {
     int flip_move(int m) const { return tr[m]; }  // core.rs:36-38
     bool same(const Pos& a, const Pos& b) const { return a.red == b.red && a.blue == b.blue && a.turn == b.turn; }
     bool child_matches(const Pos& parent, int m, const Pos& target) const {
-        const u128 red = parent.turn == 1 ? (parent.red | bit128(m)) : parent.red;
-        const u128 blue = parent.turn == 1 ? parent.blue : (parent.blue | bit128(m));
+        const W red = parent.turn == 1 ? static_cast<W>(parent.red | bit(m)) : parent.red;
+        const W blue = parent.turn == 1 ? parent.blue : static_cast<W>(parent.blue | bit(m));
         return red == target.red && blue == target.blue && target.turn == 3 - parent.turn;
     }
-    PosKey key(const Pos& p) const { return PosKey{p.red, p.blue}; }
+    PosKey key(const Pos& p) const { return PosKey{static_cast<u128>(p.red), static_cast<u128>(p.blue)}; }
     // position_to_planes (hex/net.rs:14-24): [red, blue, ones]
     void planes(const Pos& p, u128 out[3]) const {
         out[0] = p.red;
@@ -1306,8 +1314,13 @@ static int selfplay_impl(sp::Evaluator& e1, sp::Evaluator* e2_or_null, const cat
         sp::Shared sh;
         const auto t0 = sp::Clock::now();
         if (cfg->game == CATTUS_B200_GAME_HEX) {
-            sp::HexRules rules(static_cast<int>(cfg->board_size));
-            run_games(rules, *cfg, params, evals, sh);
+            if (cfg->board_size <= 8) {
+                sp::HexRulesT<uint64_t> rules(static_cast<int>(cfg->board_size));
+                run_games(rules, *cfg, params, evals, sh);
+            } else {
+                sp::HexRulesT<sp::u128> rules(static_cast<int>(cfg->board_size));
+                run_games(rules, *cfg, params, evals, sh);
+            }
         } else {
             sp::TttRules rules;
             run_games(rules, *cfg, params, evals, sh);
