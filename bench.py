@@ -401,6 +401,30 @@ def main():
                 "nn_seconds_per_10000_sim_search": float(np.median(lat) * 10000)}
     nw.close()
 
+    # ---------------- HBM-bound kernels (north star: "achieved HBM GB/s for encode and softmax against B200 peak").
+    # On the production path both are fused away (encode into the trunk kernels, mask/softmax into the policy FC
+    # epilogue), so the standalone kernels of the unfused comparison path (flags bit 0) are timed here as evidence.
+    hbm_kernels = []
+    if rank == 0 and not args.no_other_workloads:
+        with CudaNetwork(export_blob(sd, cfg.game), cfg.game, device=local_rank, batch_size=batch, n_streams=1, precision="bf16", fused_trunk=False) as unf:
+            unf.resident_upload(words[:batch], None if bitmaps is None else bitmaps[:batch])
+            for st in (0, 3):
+                unf.time_stage(st, batch, 3)
+            t_enc = float(np.mean(unf.time_stage(0, batch, 10))) * 1e-3
+            t_tail = float(np.mean(unf.time_stage(3, batch, 10))) * 1e-3
+        s2 = cfg.board_size ** 2
+        wpp = (s2 + 63) // 64
+        enc_alg = cfg.planes * wpp * 8 + cfg.planes * s2 * 2           # packed planes in + unpadded bf16 activations out
+        enc_act = cfg.planes * wpp * 8 + s2 * 64 * 2                   # what the kernel really writes: channels padded to 64
+        legal_mean = float(offsets[-1]) / positions_per_step
+        tail_alg = 2 * 4 * cfg.moves + (cfg.moves + 7) // 8 + 512       # logits read (twice counted in SURVEY 8d) + mask + value hidden row
+        for name_k, t_k, alg, act in (("encode_nhwc_bf16_kernel", t_enc, enc_alg, enc_act),
+                                      ("value_tail_kernel + policy_tail_kernel", t_tail, tail_alg, 4 * cfg.moves + (cfg.moves + 7) // 8 + 512 + 4 * legal_mean)):
+            hbm_kernels.append({"kernel": name_k, "bound": "hbm", "ms": t_k * 1e3, "positions_per_launch": batch, "algorithmic_bytes_per_position": alg,
+                                "actual_bytes_per_position": act, "achieved": batch * alg / t_k / 1e9, "achieved_actual": batch * act / t_k / 1e9,
+                                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": batch * alg / t_k / 1e9 / peaks["hbm_gbs"],
+                                "note": "unfused comparison path (flags bit 0); fused away on the production path"})
+
     # ---------------- the other single-GPU configuration of BASELINE.json (configs[1], hex5) in the same line, briefly
     others = []
     if args.workload == DEFAULT_WORKLOAD and not args.no_other_workloads:
@@ -509,6 +533,7 @@ def main():
             "cpu_baseline": cpu_baseline,
             "batch_sweep": sweep,
             "leaf_latency": leaf,
+            "hbm_kernels": hbm_kernels,
             "other_workloads": others,
             "selfplay": selfplay,
         }
