@@ -422,8 +422,10 @@ void Engine::init_lane(Lane& l) {
     const size_t in_bytes = kRecs0 + static_cast<size_t>(max_batch_) * rec_.rec_bytes;
     CB2_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&l.h_in), in_bytes, cudaHostAllocDefault));
     std::memset(l.h_in, 0, in_bytes);
-    CB2_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&l.h_values), sizeof(float) * max_batch_, cudaHostAllocDefault));
-    CB2_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&l.h_probs), sizeof(float) * max_batch_ * d_.moves, cudaHostAllocDefault));
+    CB2_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&l.h_values), sizeof(float) * max_batch_, cudaHostAllocMapped));
+    CB2_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&l.h_probs), sizeof(float) * max_batch_ * d_.moves, cudaHostAllocMapped));
+    CB2_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&l.zc_values), l.h_values, 0));
+    CB2_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&l.zc_probs), l.h_probs, 0));
     l.d_in.alloc(in_bytes);
     l.d_values.alloc(sizeof(float) * max_batch_);
     l.d_probs.alloc(sizeof(float) * max_batch_ * d_.moves);
@@ -525,7 +527,7 @@ void Engine::add_tail_ops(Lane& lane, uint32_t bucket, std::vector<Op>& ops, boo
         const float* hidden = lane.d_hidden.as<float>();
         const float* w2 = vfc2_w_.as<float>();
         const float b2 = vfc2_b_;
-        float* values = lane.d_values.as<float>();
+        float* values = zero_copy_out(bucket, dense_input) ? lane.zc_values : lane.d_values.as<float>();
         const int blocks = static_cast<int>(ceil_div(bucket * 32, 256));
         op.launch = [=](cudaStream_t st) { value_tail_kernel<<<blocks, 256, 0, st>>>(hidden, 128, w2, b2, n_ptr, values); };
         ops.push_back(op);
@@ -536,7 +538,7 @@ void Engine::add_tail_ops(Lane& lane, uint32_t bucket, std::vector<Op>& ops, boo
         op.stage = 3;
         op.name = "policy_tail";
         const float* logits = lane.d_logits.as<float>();
-        float* probs = lane.d_probs.as<float>();
+        float* probs = zero_copy_out(bucket, dense_input) ? lane.zc_probs : lane.d_probs.as<float>();
         const int blocks = static_cast<int>(ceil_div(bucket * 32, 256));
         op.launch = [=](cudaStream_t st) { policy_tail_kernel<<<blocks, 256, 0, st>>>(logits, ld_logits, recs, L, n_ptr, probs); };
         ops.push_back(op);
@@ -820,7 +822,7 @@ void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
         p.epi = 1;
         p.w2 = vfc2_w_.as<float>();
         p.b2 = vfc2_b_;
-        p.values = lane.d_values.as<float>();
+        p.values = zero_copy_out(bucket, dense_input) ? lane.zc_values : lane.d_values.as<float>();
         p.n_ptr = n_ptr;
         op = make_tc_op(2, "value_fc1_tanh", p, ceil_div(bucket, 128), 1);
         value_tc = p;
@@ -834,7 +836,7 @@ void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
         p.epi = fuse_policy ? 2 : 3;
         p.recs = recs;
         p.rl = L;
-        p.probs = lane.d_probs.as<float>();
+        p.probs = zero_copy_out(bucket, dense_input) ? lane.zc_probs : lane.d_probs.as<float>();
         p.n_ptr = n_ptr;
         op = make_tc_op(2, fuse_policy ? "policy_fc_softmax" : "policy_fc_masked", p, ceil_div(bucket, 128), pfc_.n_tiles);
     }
@@ -845,7 +847,7 @@ void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
         dp.b.epi = fuse_policy ? 2 : 3;
         dp.b.recs = recs;
         dp.b.rl = L;
-        dp.b.probs = lane.d_probs.as<float>();
+        dp.b.probs = zero_copy_out(bucket, dense_input) ? lane.zc_probs : lane.d_probs.as<float>();
         dp.b.n_ptr = n_ptr;
         dp.a = value_tc;
         ops.pop_back();
@@ -861,7 +863,7 @@ void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
         Op op;
         op.stage = 3;
         op.name = "softmax_compact";
-        float* probs = lane.d_probs.as<float>();
+        float* probs = zero_copy_out(bucket, dense_input) ? lane.zc_probs : lane.d_probs.as<float>();
         const int blocks = static_cast<int>(ceil_div(bucket * 32, 256));
         op.launch = [=](cudaStream_t st) { softmax_compact_kernel<<<blocks, 256, 0, st>>>(recs, L, n_ptr, probs); };
         ops.push_back(op);
@@ -995,8 +997,10 @@ void Engine::submit(Lane& l, uint32_t n, uint32_t total_probs) {
     *reinterpret_cast<uint32_t*>(l.h_in) = n;
     CB2_CUDA(cudaMemcpyAsync(l.d_in.p, l.h_in, 16 + static_cast<size_t>(n) * rec_.rec_bytes, cudaMemcpyHostToDevice, l.stream));
     run_bucket(l, bucket_for(n), l.stream, true, false);
-    CB2_CUDA(cudaMemcpyAsync(l.h_values, l.d_values.p, sizeof(float) * n, cudaMemcpyDeviceToHost, l.stream));
-    if (total_probs) CB2_CUDA(cudaMemcpyAsync(l.h_probs, l.d_probs.p, sizeof(float) * total_probs, cudaMemcpyDeviceToHost, l.stream));
+    if (!zero_copy_out(bucket_for(n), false)) {  // small batches wrote h_values / h_probs directly (mapped pinned memory)
+        CB2_CUDA(cudaMemcpyAsync(l.h_values, l.d_values.p, sizeof(float) * n, cudaMemcpyDeviceToHost, l.stream));
+        if (total_probs) CB2_CUDA(cudaMemcpyAsync(l.h_probs, l.d_probs.p, sizeof(float) * total_probs, cudaMemcpyDeviceToHost, l.stream));
+    }
     CB2_CUDA(cudaEventRecord(l.done, l.stream));
 }
 
@@ -1421,8 +1425,13 @@ void Engine::resident_download(uint32_t n, float* probs_out, size_t probs_cap, u
     std::memcpy(prob_offsets, resident_offsets_.data(), sizeof(uint32_t) * (n + 1));
     const uint32_t total = prob_offsets[n];
     if (total > probs_cap) throw Error(CATTUS_B200_ERANGE, "probs_cap is smaller than the number of legal moves");
-    CB2_CUDA(cudaMemcpy(probs_out, l.d_probs.p, sizeof(float) * total, cudaMemcpyDeviceToHost));
-    CB2_CUDA(cudaMemcpy(values_out, l.d_values.p, sizeof(float) * n, cudaMemcpyDeviceToHost));
+    if (zero_copy_out(bucket_for(n), false)) {
+        std::memcpy(probs_out, l.h_probs, sizeof(float) * total);
+        std::memcpy(values_out, l.h_values, sizeof(float) * n);
+    } else {
+        CB2_CUDA(cudaMemcpy(probs_out, l.d_probs.p, sizeof(float) * total, cudaMemcpyDeviceToHost));
+        CB2_CUDA(cudaMemcpy(values_out, l.d_values.p, sizeof(float) * n, cudaMemcpyDeviceToHost));
+    }
 }
 
 // ms_out[i] = device time of iteration i of the selected stage(s) on lane 0's stream, CUDA events on that stream,

@@ -91,6 +91,8 @@ struct Lane {
     uint8_t* h_in = nullptr;    // [16 B header: n][records]; swapped with the queue's open block
     float* h_values = nullptr;  // [max_batch]
     float* h_probs = nullptr;   // [max_batch * moves]
+    float* zc_values = nullptr; // device-side aliases of h_values / h_probs (mapped pinned memory): small batches write
+    float* zc_probs = nullptr;  // their outputs straight to the host, which takes two D2H copies off the critical path
     // device
     DeviceBuf d_in;  // same layout as h_in
     DeviceBuf d_values, d_probs;
@@ -167,6 +169,7 @@ class Engine {
     void upload_weights(const Blob& blob);
     void init_lane(Lane& lane);
     uint32_t bucket_for(uint32_t n) const;
+    bool zero_copy_out(uint32_t bucket, bool dense_input) const { return !dense_input && bucket <= 512; }
     std::vector<Op>& ops_for(Lane& lane, uint32_t bucket, bool dense_input);
     void build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, bool dense_input);
     void build_ops_fp32(Lane& lane, uint32_t bucket, std::vector<Op>& ops, bool dense_input);
