@@ -860,6 +860,11 @@ class Worker {
         }
         if (t.root < 0) {
             t.nodes.reserve(static_cast<size_t>(params_[s.cur].sim_num) + 64);
+            const size_t edge_cap = (static_cast<size_t>(params_[s.cur].sim_num) + 8) * static_cast<size_t>(R.moves_num());
+            t.edges.reserve(edge_cap);
+            t.init_score.reserve(edge_cap);
+            t.score_w.reserve(edge_cap);
+            t.simulations_n.reserve(edge_cap);
             t.nodes.emplace_back();
             t.nodes.back().pos = position;
             t.root = 0;
@@ -905,11 +910,14 @@ class Worker {
     void remove_all_but_subtree(Slot& s, Tree<Pos>& t, int32_t sub_root) {
         if (t.root == sub_root) return;
         Tree<Pos> nt;
-        nt.nodes.reserve(t.nodes.size() / 4 + 16);
-        nt.edges.reserve(t.edges.size() / 4 + 16);
-        nt.init_score.reserve(t.edges.size() / 4 + 16);
-        nt.score_w.reserve(t.edges.size() / 4 + 16);
-        nt.simulations_n.reserve(t.edges.size() / 4 + 16);
+        // room for the kept subtree plus one more search (capacity is only reserved address space until touched)
+        const size_t more_nodes = static_cast<size_t>(params_[s.cur].sim_num) + 64;
+        const size_t more_edges = (static_cast<size_t>(params_[s.cur].sim_num) + 8) * static_cast<size_t>(R.moves_num());
+        nt.nodes.reserve(t.nodes.size() / 4 + more_nodes);
+        nt.edges.reserve(t.edges.size() / 4 + more_edges);
+        nt.init_score.reserve(t.edges.size() / 4 + more_edges);
+        nt.score_w.reserve(t.edges.size() / 4 + more_edges);
+        nt.simulations_n.reserve(t.edges.size() / 4 + more_edges);
         nt.nodes.emplace_back();
         nt.nodes[0].pos = t.nodes[sub_root].pos;
         nt.root = 0;
@@ -1006,6 +1014,20 @@ class Worker {
         }
         pb.parked.push_back(si);
         s.phase = kWaitEval;
+        {
+            // The evaluation will append this node's children at the tails of the tree's edge arrays: request those
+            // lines for writing now, they arrive while the batch is on the GPU (a cold tail costs a DRAM read per array).
+            Tree<Pos>& t = s.players[s.cur].tree;
+            const size_t tail = t.edges.size();
+            if (t.edges.capacity() >= tail + static_cast<size_t>(n_legal)) {
+                for (int off = 0; off < n_legal; off += 8) __builtin_prefetch(t.edges.data() + tail + off, 1);
+                for (int off = 0; off < n_legal; off += 16) {
+                    __builtin_prefetch(t.init_score.data() + tail + off, 1);
+                    __builtin_prefetch(t.score_w.data() + tail + off, 1);
+                    __builtin_prefetch(t.simulations_n.data() + tail + off, 1);
+                }
+            }
+        }
         return false;
     }
 
