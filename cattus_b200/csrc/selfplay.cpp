@@ -742,6 +742,7 @@ class Worker {
             s.sel_node = t.root;
             s.sel_rows_ready = false;
             __builtin_prefetch(&t.nodes[t.root]);
+            if (t.nodes.capacity() > t.nodes.size()) __builtin_prefetch(t.nodes.data() + t.nodes.size(), 1);  // a first visit appends a node
             return true;
         }
         const int32_t node = s.sel_node;
@@ -1065,16 +1066,15 @@ class Worker {
 
     // mod.rs:270-281
     void backpropagate(Slot& s, Tree<Pos>& t, float score) {
+        const uint8_t root_turn = t.nodes[t.root].pos.turn;  // the side to move alternates along the path in hex and tic-tac-toe
         for (size_t i = 0; i < s.path.size(); ++i) {
-            const uint8_t turn = t.nodes[path_nodes_at(s, t, i)].pos.turn;
+            const uint8_t turn = (i & 1) ? static_cast<uint8_t>(3 - root_turn) : root_turn;
             t.simulations_n[s.path[i]] += 1;
             t.score_w[s.path[i]] += turn == 1 ? score : -score;
         }
         s.sims_left -= 1;
         c_.simulations += 1;
     }
-    // source node of the i-th edge on the path: the root for i = 0, else the child of the previous edge
-    int32_t path_nodes_at(const Slot& s, const Tree<Pos>& t, size_t i) const { return i == 0 ? t.root : t.edges[s.path[i - 1]].child; }
 
     // the rest of calc_moves_probabilities + choose_move_from_probabilities + the game step (mod.rs:364-417,
     // self_play.rs:207-217)
