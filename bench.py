@@ -253,6 +253,29 @@ def time_cpu_selfplay(game, games, threads):
                   f"threads add nothing), per-leaf torch-CPU fp32 evaluation with 1 intra-op thread"})
 
 
+def cpu_batch_sweep(cfg, batches=(1, 8, 64, 256, 1024), seconds_each=1.2, seed=99):
+    """the CPU path at the batch sizes the shipped configs use and beyond (bounded: ~1 s per point)."""
+    import ctypes as C
+
+    from oracle import net
+
+    liboracle = C.CDLL(str(ROOT / "oracle" / "_build" / "liboracle.so"))
+    cores = len(os.sched_getaffinity(0))
+    sd = net.make_state_dict(cfg, 0)
+    out = []
+    for b in batches:
+        model = net.TorchCpuModel(sd, cfg, b, 1 if b == 1 else cores)
+        words, bitmaps = make_inputs(cfg, b, seed)
+        cpu_reference_step(model, cfg, words, bitmaps, liboracle)
+        done, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < seconds_each:
+            cpu_reference_step(model, cfg, words, bitmaps, liboracle)
+            done += 1
+        el = time.perf_counter() - t0
+        out.append({"batch": b, "ms": el / done * 1e3, "positions_per_sec": done * b / el, "threads": 1 if b == 1 else cores})
+    return out
+
+
 def run_reference_arm(args, rank, world):
     from oracle import net
 
@@ -273,6 +296,7 @@ def run_reference_arm(args, rank, world):
         "e2e": {"value": value, "unit": "positions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    line["batch_sweep"] = cpu_batch_sweep(cfg)
     if not args.no_selfplay:
         line["selfplay"] = time_cpu_selfplay(args.selfplay_game, 2, 2)
     print(json.dumps(line), flush=True)
