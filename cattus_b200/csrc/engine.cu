@@ -746,7 +746,11 @@ void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
             return best > 0.0;
         };
         int T = kTsMaxTiles, tpg = kTsMaxTiles, bpg = 0;
-        int min_tiles = 1;
+        // One tile per CTA gives the lowest latency for a batch that is alone on the GPU, but costs ~2.6x the SM time
+        // per position (per-CTA setup, latency-bound MMA chains).  Self-play keeps many batches of 100-300 positions in
+        // flight at once (one per worker thread), where that SM time is the bottleneck: measured 16 threads, hex5:
+        // 17.4 M sims/s with 1 tile, 18.2 M with >= 2, 17.8 M with >= 4 (no cache: 15.5 M vs 18.0 M with >= 4).
+        int min_tiles = bucket >= 128 ? 2 : 1;
         if (const char* e = std::getenv("CATTUS_B200_TRUNK_MIN_TILES")) min_tiles = std::max(1, std::atoi(e));  // experiment knob
         for (int cand = min_tiles; cand <= kTsMaxTiles; cand *= 2) {
             int g = 0, b = 0;
