@@ -32,6 +32,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <sys/types.h>
 
@@ -312,16 +313,16 @@ class Cache {
     Cache(size_t max_size, int moves_num) : stride_(static_cast<size_t>(moves_num) + 1) {
         n_buckets_ = 1;
         while (n_buckets_ * kWays < max_size) n_buckets_ <<= 1;
-        meta_ = static_cast<Meta*>(std::calloc(n_buckets_, sizeof(Meta)));
-        keys_ = static_cast<PosKey*>(std::calloc(n_buckets_ * kWays, sizeof(PosKey)));
-        vals_ = static_cast<float*>(std::calloc(n_buckets_ * kWays * stride_, sizeof(float)));
+        meta_ = static_cast<Meta*>(zeroed_huge(n_buckets_ * sizeof(Meta)));
+        keys_ = static_cast<PosKey*>(zeroed_huge(n_buckets_ * kWays * sizeof(PosKey)));
+        vals_ = static_cast<float*>(zeroed_huge(n_buckets_ * kWays * stride_ * sizeof(float)));
         if (!meta_ || !keys_ || !vals_) throw SpError{CATTUS_B200_ENOMEM, "cannot allocate the position cache"};
         for (auto& l : locks_) l.clear();
     }
     ~Cache() {
-        std::free(meta_);
-        std::free(keys_);
-        std::free(vals_);
+        free_huge(meta_, n_buckets_ * sizeof(Meta));
+        free_huge(keys_, n_buckets_ * kWays * sizeof(PosKey));
+        free_huge(vals_, n_buckets_ * kWays * stride_ * sizeof(float));
     }
     Cache(const Cache&) = delete;
     Cache& operator=(const Cache&) = delete;
@@ -370,6 +371,20 @@ class Cache {
     }
 
   private:
+    // Zero pages straight from the kernel, backed by transparent huge pages where the system allows it (the table is
+    // probed at random: with 4 KB pages nearly every probe is also a TLB miss).
+    static void* zeroed_huge(size_t bytes) {
+        const size_t len = (bytes + (2u << 20) - 1) & ~static_cast<size_t>((2u << 20) - 1);
+        void* p = ::mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (p == MAP_FAILED) return nullptr;
+#ifdef MADV_HUGEPAGE
+        ::madvise(p, len, MADV_HUGEPAGE);
+#endif
+        return p;
+    }
+    static void free_huge(void* p, size_t bytes) {
+        if (p) ::munmap(p, (bytes + (2u << 20) - 1) & ~static_cast<size_t>((2u << 20) - 1));
+    }
     static constexpr size_t kWays = 8, kLocks = 4096;
     // one 32-byte record per bucket: 16-bit tags (0 = empty way) filter the key compares, so a miss touches one line
     struct alignas(32) Meta {
