@@ -14,7 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 from pathlib import Path
-from typing import Optional, Sequence, Tuple
+from typing import Optional, Tuple
 
 import numpy as np
 

@@ -1,7 +1,6 @@
 import os, sys, time
 os.environ["CATTUS_B200_TRACE_BATCH"]="1"
 sys.path.insert(0,'/root/repo')
-import numpy as np
 from cattus_b200 import CudaNetwork
 from cattus_b200.export import export_blob
 from oracle import games, net
