@@ -133,3 +133,17 @@ def test_value_func_cache_fifo_and_counters():
     assert cache.get_or_compute(2, mk(2)) == 20  # still cached
     assert cache.get_or_compute(1, mk(1)) == 10  # recomputed
     assert calls == [1, 2, 3, 1] and cache.metrics() == {"cache.hits": 2, "cache.misses": 4}
+
+
+def test_product_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under cattus_b200/ (Python or C++) may import, include, link or execute
+    it, and the only other users are tests/, __graft_entry__.smoke() and bench.py's CPU-baseline / reference legs."""
+    pkg = ROOT / "cattus_b200"
+    for f in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")) + list(pkg.rglob("*.cpp")) + list(pkg.rglob("*.hpp")):
+        text = f.read_text()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f
+        assert not re.search(r'#\s*include\s*[<"][^>"]*oracle', text), f
+        assert "liboracle" not in text, f
+    entry = (ROOT / "__graft_entry__.py").read_text()
+    build_fn = entry[entry.index("def build()"):entry.index("def smoke()")]
+    assert "import oracle" not in build_fn and "from oracle" not in build_fn  # build() only compiles the checker
