@@ -170,8 +170,8 @@ Engine::Engine(const cattus_b200_desc& desc, const void* blob_bytes, size_t blob
     CB2_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h_err_), 64, cudaHostAllocMapped));
     std::memset(h_err_, 0, 64);
     CB2_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_err_), h_err_, 0));
-    CB2_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
-    CB2_CUDA(cudaFuncSetAttribute(tc_gemm_dual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+    CB2_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(kTcStagesDeep)));
+    CB2_CUDA(cudaFuncSetAttribute(tc_gemm_dual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(kTcStagesDeep)));
     // whole-trunk kernel: 8x8 boards, 128 filters (flags bit 0 forces the per-layer path, used by the parity tests)
     fused_trunk_ = precision_ == CATTUS_B200_PRECISION_BF16 && d_.s == 8 && d_.f == 128 && d_.c_in <= 32 && d_.wpp() == 1 &&
                    (desc.flags & 1u) == 0 && (sm_count_ >= 2) && vhp_ + php_ <= 64;
@@ -487,12 +487,20 @@ CUtensorMap Engine::make_map_conv(const void* base, uint32_t channels, uint32_t 
     return m;
 }
 
+// Ring depth of the GEMM kernel.  A 6-deep ring (one CTA per SM) for grids that leave SMs idle was measured and does
+// not help (chess B = 1 graph 0.123 -> 0.126 ms, hex5 0.035 -> 0.037 ms): the small-batch k-loop is not bound by TMA
+// round trips, so every launch keeps 3 stages and two CTAs per SM.
+int Engine::tc_stages_for(uint32_t) const { return kTcStages; }
+
 Op Engine::make_tc_op(int stage, const char* name, const TcGemmParams& p, uint32_t m_tiles, uint32_t n_tiles) {
     Op op;
     op.stage = stage;
     op.name = name;
     const dim3 grid(m_tiles, n_tiles);
-    op.launch = [p, grid](cudaStream_t st) { tc_gemm_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(p); };
+    TcGemmParams q = p;
+    q.stages = tc_stages_for(m_tiles * n_tiles);
+    const int smem_bytes = tc_smem_bytes(q.stages);
+    op.launch = [q, grid, smem_bytes](cudaStream_t st) { tc_gemm_kernel<<<grid, kTcThreads, smem_bytes, st>>>(q); };
     return op;
 }
 
@@ -860,7 +868,9 @@ void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
         op.stage = 2;
         op.name = "heads_fc_dual";
         const dim3 grid(ceil_div(bucket, 128), 1 + pfc_.n_tiles);
-        op.launch = [dp, grid](cudaStream_t st) { tc_gemm_dual_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(dp); };
+        dp.a.stages = dp.b.stages = tc_stages_for(grid.x * grid.y);
+        const int smem_bytes = tc_smem_bytes(dp.a.stages);
+        op.launch = [dp, grid, smem_bytes](cudaStream_t st) { tc_gemm_dual_kernel<<<grid, kTcThreads, smem_bytes, st>>>(dp); };
         ops.push_back(op);
     }
     if (compact_policy) {

@@ -26,11 +26,13 @@
 
 namespace cb2 {
 
-constexpr int kTcStages = 3;
+constexpr int kTcStages = 3;      // ring depth of large grids (two CTAs per SM)
+constexpr int kTcStagesDeep = 6;  // small grids (one latency-bound CTA per SM): deeper prefetch, see tc_smem_bytes()
 constexpr int kTcTileBytes = 128 * 128;  // 128 rows x 128 B
 constexpr int kTcThreads = 192;
 constexpr int kTcTmemCols = 128;
 constexpr int kTcSmemBytes = 2 * kTcStages * kTcTileBytes + 256 + 1024;  // tiles + barriers + alignment slack
+constexpr int tc_smem_bytes(int stages) { return 2 * stages * kTcTileBytes + 256 + 1024; }
 
 struct alignas(64) TcGemmParams {
     CUtensorMap tma_a;
@@ -52,6 +54,7 @@ struct alignas(64) TcGemmParams {
     int out_f32;
     int relu;
     uint32_t tx_bytes;  // bytes one stage's two TMA boxes deliver
+    int stages;         // smem ring depth (kTcStages or kTcStagesDeep); the launch passes tc_smem_bytes(stages)
     int epi;            // epilogue variant, see above
     // epi 1
     const float* w2;    // [128]
@@ -69,10 +72,11 @@ __device__ __forceinline__ void tc_gemm_body(const TcGemmParams& p, const int m_
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem + kTcStages * kTcTileBytes;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + 2 * kTcStages * kTcTileBytes);
-    uint64_t* empty_bar = full_bar + kTcStages;
-    uint64_t* tmem_full_bar = empty_bar + kTcStages;
+    const int stages = p.stages;
+    uint8_t* smem_b = smem + stages * kTcTileBytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + 2 * stages * kTcTileBytes);
+    uint64_t* empty_bar = full_bar + stages;
+    uint64_t* tmem_full_bar = empty_bar + stages;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
     const uint32_t warp = threadIdx.x >> 5;
@@ -83,7 +87,7 @@ __device__ __forceinline__ void tc_gemm_body(const TcGemmParams& p, const int m_
         ptx::prefetch_tensormap(&p.tma_b);
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < kTcStages; ++s) {
+        for (int s = 0; s < stages; ++s) {
             ptx::mbar_init(&full_bar[s], 1);
             ptx::mbar_init(&empty_bar[s], 1);
         }
@@ -102,8 +106,8 @@ __device__ __forceinline__ void tc_gemm_body(const TcGemmParams& p, const int m_
     if (warp == 0) {
         if (lane == 0) {
             for (int kb = 0; kb < p.num_kb; ++kb) {
-                const int s = kb % kTcStages;
-                const uint32_t ph = (kb / kTcStages) & 1;
+                const int s = kb % stages;
+                const uint32_t ph = (kb / stages) & 1;
                 ptx::mbar_wait(&empty_bar[s], ph ^ 1, p.err, 0x100 + s);
                 ptx::mbar_arrive_expect_tx(&full_bar[s], p.tx_bytes);
                 if (p.mode == 0) {
@@ -120,8 +124,8 @@ __device__ __forceinline__ void tc_gemm_body(const TcGemmParams& p, const int m_
         if (lane == 0) {
             const uint32_t idesc = ptx::umma_idesc_bf16(128, p.n_umma);
             for (int kb = 0; kb < p.num_kb; ++kb) {
-                const int s = kb % kTcStages;
-                const uint32_t ph = (kb / kTcStages) & 1;
+                const int s = kb % stages;
+                const uint32_t ph = (kb / stages) & 1;
                 ptx::mbar_wait(&full_bar[s], ph, p.err, 0x200 + s);
                 ptx::tc_fence_after();
                 const uint32_t a_addr = ptx::smem_u32(smem_a + s * kTcTileBytes);
