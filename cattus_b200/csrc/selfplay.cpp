@@ -424,11 +424,6 @@ struct Evaluator {
 };
 
 // ------------------------------------------------------------------------------------------------ tree
-struct Edge {
-    int32_t child;  // node index, -1 until first visited (positions of unvisited children are derived on demand)
-    uint8_t m;
-};
-
 // select's inner step (mod.rs:211-226) for one node, structure-of-arrays so the compiler can vectorise it (two IEEE
 // divisions per child dominate a simulation otherwise).  Per lane exactly the scalar operations of
 // calc_selection_heuristic (mod.rs:233-244) in the reference's order: exploit = n == 0 ? 0 : w / n;
@@ -455,30 +450,35 @@ __attribute__((target_clones("avx2", "default"))) static int select_child(const 
 template <class Pos>
 struct Node {
     Pos pos;
-    int32_t first = -1;  // first edge; children are edges [first, first + count) in insertion order
-    int32_t count = 0;
+    int32_t first = -1;  // word offset of this node's child block in Tree::pool (-1: not expanded)
+    int32_t count = 0;   // number of children
 };
+// The children of an expanded node (MctsEdge, mod.rs:32-56) live in ONE contiguous block of 4 * count 32-bit words,
+// in insertion order:  init_score[count] (f32) | score_w[count] (f32) | simulations_n[count] (i32) | edge[count], where
+// edge = (child node index + 1) in the low 24 bits (0: not visited yet, its position is derived on demand) and the
+// move in the high 8.  One block = one run of cache lines per node visit (select reads the first three arrays).
 template <class Pos>
 struct Tree {
     std::vector<Node<Pos>> nodes;
-    std::vector<Edge> edges;        // cold per-edge fields
-    std::vector<float> init_score;  // hot per-edge fields, same index as `edges` (MctsEdge, mod.rs:32-56)
-    std::vector<float> score_w;
-    std::vector<int32_t> simulations_n;
+    std::vector<uint32_t> pool;
     int32_t root = -1;
     void clear() {
         nodes.clear();
-        edges.clear();
-        init_score.clear();
-        score_w.clear();
-        simulations_n.clear();
+        pool.clear();
         root = -1;
     }
-    void push_edge(uint8_t m, float init, float w, int32_t n, int32_t child) {
-        edges.push_back(Edge{child, m});
-        init_score.push_back(init);
-        score_w.push_back(w);
-        simulations_n.push_back(n);
+    float* init_score(const Node<Pos>& nd) { return reinterpret_cast<float*>(pool.data() + nd.first); }
+    float* score_w(const Node<Pos>& nd) { return reinterpret_cast<float*>(pool.data() + nd.first + nd.count); }
+    int32_t* simulations_n(const Node<Pos>& nd) { return reinterpret_cast<int32_t*>(pool.data() + nd.first + 2 * nd.count); }
+    uint32_t* edge(const Node<Pos>& nd) { return pool.data() + nd.first + 3 * nd.count; }
+    static uint32_t pack_edge(int32_t child, uint8_t m) { return (static_cast<uint32_t>(child + 1) & 0xFFFFFFu) | (static_cast<uint32_t>(m) << 24); }
+    static int32_t edge_child(uint32_t e) { return static_cast<int32_t>(e & 0xFFFFFFu) - 1; }
+    static uint8_t edge_move(uint32_t e) { return static_cast<uint8_t>(e >> 24); }
+    // appends a zero-filled block for `count` children and returns its word offset
+    int32_t append_block(int32_t count) {
+        const size_t first = pool.size();
+        pool.resize(first + 4 * static_cast<size_t>(count));
+        return static_cast<int32_t>(first);
     }
 };
 
@@ -533,7 +533,11 @@ class Worker {
         Player players[2];
         int cur = 0;  // index into players of the side searching now
         uint32_t sims_left = 0;
-        std::vector<int32_t> path;  // edge indices root -> leaf
+        struct PathStep {
+            int32_t w_idx;  // word index of the taken child's score_w in the tree's pool
+            int32_t count;  // children of that node: simulations_n is `count` words further
+        };
+        std::vector<PathStep> path;  // root -> leaf
         int32_t leaf = -1;
         bool leaf_flipped = false;
         Pos leaf_eval_pos;  // the position as sent to the network (Player1 to move)
@@ -768,20 +772,16 @@ class Worker {
             return evaluate_leaf(si);
         }
         if (!s.sel_rows_ready) {
-            for (int off = 0; off < nd.count; off += 16) {
-                __builtin_prefetch(&t.init_score[nd.first + off]);
-                __builtin_prefetch(&t.score_w[nd.first + off]);
-                __builtin_prefetch(&t.simulations_n[nd.first + off]);
-            }
+            const uint32_t* blk = t.pool.data() + nd.first;
+            for (int off = 0; off < 3 * nd.count; off += 16) __builtin_prefetch(blk + off);
             s.sel_rows_ready = true;
             return true;
         }
-        const int32_t best = select_child(&t.init_score[nd.first], &t.score_w[nd.first], &t.simulations_n[nd.first], nd.count, params_[s.cur].explore_factor, sel_);
-        const int32_t ei = nd.first + best;
-        s.path.push_back(ei);
-        int32_t c = t.edges[ei].child;
+        const int32_t best = select_child(t.init_score(nd), t.score_w(nd), t.simulations_n(nd), nd.count, params_[s.cur].explore_factor, sel_);
+        s.path.push_back({nd.first + nd.count + best, nd.count});
+        int32_t c = Tree<Pos>::edge_child(t.edge(nd)[best]);
         if (c < 0)
-            c = materialise(t, node, ei);
+            c = materialise(t, node, best);
         else
             __builtin_prefetch(&t.nodes[c]);
         s.sel_node = c;
@@ -876,11 +876,7 @@ class Worker {
         }
         if (t.root < 0) {
             t.nodes.reserve(static_cast<size_t>(params_[s.cur].sim_num) + 64);
-            const size_t edge_cap = (static_cast<size_t>(params_[s.cur].sim_num) + 8) * static_cast<size_t>(R.moves_num());
-            t.edges.reserve(edge_cap);
-            t.init_score.reserve(edge_cap);
-            t.score_w.reserve(edge_cap);
-            t.simulations_n.reserve(edge_cap);
+            t.pool.reserve(4 * (static_cast<size_t>(params_[s.cur].sim_num) + 8) * static_cast<size_t>(R.moves_num()));
             t.nodes.emplace_back();
             t.nodes.back().pos = position;
             t.root = 0;
@@ -896,15 +892,15 @@ class Worker {
         for (int depth = 1; depth < 3; ++depth) {
             next.clear();
             for (int32_t n : layer) {
-                const int32_t first = t.nodes[n].first, count = t.nodes[n].count;
+                const int32_t count = t.nodes[n].count;
                 for (int32_t i = count - 1; i >= 0; --i) {
-                    const int32_t ei = first + i;
-                    const int32_t c = t.edges[ei].child;
+                    const uint32_t e = t.edge(t.nodes[n])[i];
+                    const int32_t c = Tree<Pos>::edge_child(e);
                     if (c >= 0) {
                         if (R.same(t.nodes[c].pos, position)) return c;
                         next.push_back(c);
-                    } else if (R.child_matches(t.nodes[n].pos, t.edges[ei].m, position)) {
-                        return materialise(t, n, ei);
+                    } else if (R.child_matches(t.nodes[n].pos, Tree<Pos>::edge_move(e), position)) {
+                        return materialise(t, n, i);
                     }
                 }
             }
@@ -913,12 +909,14 @@ class Worker {
         return -1;
     }
 
-    int32_t materialise(Tree<Pos>& t, int32_t parent, int32_t ei) {
-        const Pos child = R.moved(t.nodes[parent].pos, t.edges[ei].m);
+    int32_t materialise(Tree<Pos>& t, int32_t parent, int32_t i) {
+        const uint8_t m = Tree<Pos>::edge_move(t.edge(t.nodes[parent])[i]);
+        const Pos child = R.moved(t.nodes[parent].pos, m);
         t.nodes.emplace_back();
         t.nodes.back().pos = child;
         const int32_t idx = static_cast<int32_t>(t.nodes.size()) - 1;
-        t.edges[ei].child = idx;
+        if (idx >= 0xFFFFFE) throw SpError{CATTUS_B200_ERANGE, "search tree exceeds 2^24 nodes"};
+        t.edge(t.nodes[parent])[i] = Tree<Pos>::pack_edge(idx, m);
         return idx;
     }
 
@@ -930,10 +928,7 @@ class Worker {
         const size_t more_nodes = static_cast<size_t>(params_[s.cur].sim_num) + 64;
         const size_t more_edges = (static_cast<size_t>(params_[s.cur].sim_num) + 8) * static_cast<size_t>(R.moves_num());
         nt.nodes.reserve(t.nodes.size() / 4 + more_nodes);
-        nt.edges.reserve(t.edges.size() / 4 + more_edges);
-        nt.init_score.reserve(t.edges.size() / 4 + more_edges);
-        nt.score_w.reserve(t.edges.size() / 4 + more_edges);
-        nt.simulations_n.reserve(t.edges.size() / 4 + more_edges);
+        nt.pool.reserve(t.pool.size() / 4 + 4 * more_edges);
         nt.nodes.emplace_back();
         nt.nodes[0].pos = t.nodes[sub_root].pos;
         nt.root = 0;
@@ -941,22 +936,26 @@ class Worker {
         while (!stack.empty()) {
             const auto [old_n, new_n] = stack.back();
             stack.pop_back();
-            const int32_t first = t.nodes[old_n].first, count = t.nodes[old_n].count;
+            const Node<Pos>& on = t.nodes[old_n];
+            const int32_t count = on.count;
             if (count == 0) continue;
-            const int32_t nfirst = static_cast<int32_t>(nt.edges.size());
-            nt.nodes[new_n].first = nfirst;
+            nt.nodes[new_n].first = nt.append_block(count);
             nt.nodes[new_n].count = count;
-            for (int32_t i = count - 1; i >= 0; --i)
-                nt.push_edge(t.edges[first + i].m, t.init_score[first + i], t.score_w[first + i], t.simulations_n[first + i], t.edges[first + i].child);
-            for (int32_t i = 0; i < count; ++i) {
-                Edge& e = nt.edges[nfirst + i];
-                if (e.child >= 0) {
-                    const int32_t old_c = e.child;
+            for (int32_t i = 0; i < count; ++i) {  // new insertion order = old iteration order (newest first)
+                const int32_t o = count - 1 - i;
+                const uint32_t e = t.edge(on)[o];
+                nt.init_score(nt.nodes[new_n])[i] = t.init_score(on)[o];
+                nt.score_w(nt.nodes[new_n])[i] = t.score_w(on)[o];
+                nt.simulations_n(nt.nodes[new_n])[i] = t.simulations_n(on)[o];
+                int32_t nc = -1;
+                const int32_t old_c = Tree<Pos>::edge_child(e);
+                if (old_c >= 0) {
                     nt.nodes.emplace_back();
                     nt.nodes.back().pos = t.nodes[old_c].pos;
-                    e.child = static_cast<int32_t>(nt.nodes.size()) - 1;
-                    stack.push_back({old_c, e.child});
+                    nc = static_cast<int32_t>(nt.nodes.size()) - 1;
+                    stack.push_back({old_c, nc});
                 }
+                nt.edge(nt.nodes[new_n])[i] = Tree<Pos>::pack_edge(nc, Tree<Pos>::edge_move(e));
             }
         }
         t = std::move(nt);
@@ -967,7 +966,7 @@ class Worker {
     void add_dirichlet_noise(Slot& s, Tree<Pos>& t, int32_t node) {
         const Params& P = params_[s.cur];
         if (P.noise_alpha == 0.0f || P.noise_eps == 0.0f) return;
-        const int32_t first = t.nodes[node].first, count = t.nodes[node].count;
+        const int32_t count = t.nodes[node].count;
         if (count < 2) return;
         noise_.resize(count);
         double tot = 0.0;
@@ -977,7 +976,7 @@ class Worker {
         }
         const float eps = P.noise_eps;
         for (int i = 0; i < count; ++i) {  // zip(edges() order = newest first, noise)
-            float& init = t.init_score[first + (count - 1 - i)];
+            float& init = t.init_score(t.nodes[node])[count - 1 - i];
             const float nz = static_cast<float>(noise_[i] / tot);
             init = (1.0f - eps) * init + eps * nz;
         }
@@ -1034,15 +1033,9 @@ class Worker {
             // The evaluation will append this node's children at the tails of the tree's edge arrays: request those
             // lines for writing now, they arrive while the batch is on the GPU (a cold tail costs a DRAM read per array).
             Tree<Pos>& t = s.players[s.cur].tree;
-            const size_t tail = t.edges.size();
-            if (t.edges.capacity() >= tail + static_cast<size_t>(n_legal)) {
-                for (int off = 0; off < n_legal; off += 8) __builtin_prefetch(t.edges.data() + tail + off, 1);
-                for (int off = 0; off < n_legal; off += 16) {
-                    __builtin_prefetch(t.init_score.data() + tail + off, 1);
-                    __builtin_prefetch(t.score_w.data() + tail + off, 1);
-                    __builtin_prefetch(t.simulations_n.data() + tail + off, 1);
-                }
-            }
+            const size_t tail = t.pool.size();
+            if (t.pool.capacity() >= tail + 4 * static_cast<size_t>(n_legal))
+                for (int off = 0; off < 4 * n_legal; off += 16) __builtin_prefetch(t.pool.data() + tail + off, 1);
         }
         return false;
     }
@@ -1052,23 +1045,17 @@ class Worker {
         Tree<Pos>& t = s.players[s.cur].tree;
         const int32_t leaf = s.leaf;
         const u128 legal = R.legal_mask(s.leaf_eval_pos);
-        const int32_t first = static_cast<int32_t>(t.edges.size());
         const int32_t count = popcount128(legal);
-        t.edges.resize(first + count);
-        t.init_score.resize(first + count);
-        t.score_w.resize(first + count);  // value-initialised: 0.0f
-        t.simulations_n.resize(first + count);
-        Edge* ed = t.edges.data() + first;
-        std::memcpy(t.init_score.data() + first, val, sizeof(float) * count);
+        const int32_t first = t.append_block(count);  // score_w and simulations_n start at zero
+        std::memcpy(t.pool.data() + first, val, sizeof(float) * count);
+        uint32_t* ed = t.pool.data() + first + 3 * count;
         int32_t k = 0;
         for (int half = 0; half < 2; ++half) {  // legal_moves() of the evaluated position, ascending; un-flipped by flip_score_if_needed
             uint64_t bits = static_cast<uint64_t>(legal >> (64 * half));
             while (bits) {
                 const int m = 64 * half + __builtin_ctzll(bits);
                 bits &= bits - 1;
-                ed[k].child = -1;
-                ed[k].m = static_cast<uint8_t>(s.leaf_flipped ? R.flip_move(m) : m);
-                ++k;
+                ed[k++] = Tree<Pos>::pack_edge(-1, static_cast<uint8_t>(s.leaf_flipped ? R.flip_move(m) : m));
             }
         }
         t.nodes[leaf].first = first;
@@ -1084,8 +1071,8 @@ class Worker {
         const uint8_t root_turn = t.nodes[t.root].pos.turn;  // the side to move alternates along the path in hex and tic-tac-toe
         for (size_t i = 0; i < s.path.size(); ++i) {
             const uint8_t turn = (i & 1) ? static_cast<uint8_t>(3 - root_turn) : root_turn;
-            t.simulations_n[s.path[i]] += 1;
-            t.score_w[s.path[i]] += turn == 1 ? score : -score;
+            reinterpret_cast<int32_t*>(t.pool.data())[s.path[i].w_idx + s.path[i].count] += 1;
+            reinterpret_cast<float*>(t.pool.data())[s.path[i].w_idx] += turn == 1 ? score : -score;
         }
         s.sims_left -= 1;
         c_.simulations += 1;
@@ -1100,9 +1087,11 @@ class Worker {
         std::vector<std::pair<uint8_t, float>> probs;
         probs.reserve(root.count);
         uint32_t total = 0;
-        for (int32_t i = 0; i < root.count; ++i) total += static_cast<uint32_t>(t.simulations_n[root.first + i]);
+        const int32_t* rn = t.simulations_n(root);
+        const uint32_t* re = t.edge(root);
+        for (int32_t i = 0; i < root.count; ++i) total += static_cast<uint32_t>(rn[i]);
         for (int32_t i = root.count - 1; i >= 0; --i)  // edges() order
-            probs.emplace_back(t.edges[root.first + i].m, static_cast<float>(t.simulations_n[root.first + i]) / static_cast<float>(total));
+            probs.emplace_back(Tree<Pos>::edge_move(re[i]), static_cast<float>(rn[i]) / static_cast<float>(total));
         const double secs = std::chrono::duration<double>(Clock::now() - s.search_t0).count();
         {
             std::lock_guard<std::mutex> g(sh_.mu);  // RunningAverage(0.99), util/metric.rs:1-20
