@@ -22,6 +22,8 @@ NVCC_FLAGS = [
     "-Xcompiler", "-ffp-contract=off",
     # lets g++ vectorise the selection loop (a masked IEEE division); results are unchanged, only FP exception flags differ
     "-Xcompiler", "-fno-trapping-math",
+    # the self-play driver keeps typed headers and rows in one pool of 32-bit words
+    "-Xcompiler", "-fno-strict-aliasing",
 ]
 
 

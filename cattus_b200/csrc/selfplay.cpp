@@ -447,38 +447,49 @@ __attribute__((target_clones("avx2", "default"))) static int select_child(const 
         if (val[i] == best) return i;
     return count - 1;  // only reachable with NaNs, which the reference asserts away (mod.rs:444)
 }
-template <class Pos>
-struct Node {
-    Pos pos;
-    int32_t first = -1;  // word offset of this node's child block in Tree::pool (-1: not expanded)
-    int32_t count = 0;   // number of children
-};
-// The children of an expanded node (MctsEdge, mod.rs:32-56) live in ONE contiguous block of 4 * count 32-bit words,
-// in insertion order:  init_score[count] (f32) | score_w[count] (f32) | simulations_n[count] (i32) | edge[count], where
-// edge = (child node index + 1) in the low 24 bits (0: not visited yet, its position is derived on demand) and the
-// move in the high 8.  One block = one run of cache lines per node visit (select reads the first three arrays).
+// Search tree storage.  Every visited node is ONE 16-byte-aligned block of 32-bit words in `pool`:
+//   Header { position, count, expanded } | init_score[count] (f32) | score_w[count] (f32) | simulations_n[count] (i32) |
+//   edge[count]
+// with count = number of legal moves (known from the position when the node is first visited; the rows are filled in
+// when its evaluation arrives) and edge = (child block offset / 4 + 1) in the low 24 bits (0: child not visited yet, its
+// position is derived on demand) + the move in the high 8 (MctsNode / MctsEdge, mod.rs:21-56).  A node visit during
+// select touches one run of cache lines, and the run can be requested as soon as the parent has picked the child.
 template <class Pos>
 struct Tree {
-    std::vector<Node<Pos>> nodes;
+    struct alignas(16) Header {
+        Pos pos;
+        int32_t count;     // children (legal moves of pos; 0 for finished positions)
+        int32_t expanded;  // rows are valid: create_children has run (mod.rs:246-262)
+    };
+    static constexpr int32_t kHdrWords = static_cast<int32_t>((sizeof(Header) + 15) / 16 * 4);
     std::vector<uint32_t> pool;
     int32_t root = -1;
     void clear() {
-        nodes.clear();
         pool.clear();
         root = -1;
     }
-    float* init_score(const Node<Pos>& nd) { return reinterpret_cast<float*>(pool.data() + nd.first); }
-    float* score_w(const Node<Pos>& nd) { return reinterpret_cast<float*>(pool.data() + nd.first + nd.count); }
-    int32_t* simulations_n(const Node<Pos>& nd) { return reinterpret_cast<int32_t*>(pool.data() + nd.first + 2 * nd.count); }
-    uint32_t* edge(const Node<Pos>& nd) { return pool.data() + nd.first + 3 * nd.count; }
-    static uint32_t pack_edge(int32_t child, uint8_t m) { return (static_cast<uint32_t>(child + 1) & 0xFFFFFFu) | (static_cast<uint32_t>(m) << 24); }
-    static int32_t edge_child(uint32_t e) { return static_cast<int32_t>(e & 0xFFFFFFu) - 1; }
+    Header& hdr(int32_t b) { return *reinterpret_cast<Header*>(pool.data() + b); }
+    const Header& hdr(int32_t b) const { return *reinterpret_cast<const Header*>(pool.data() + b); }
+    float* init_score(int32_t b) { return reinterpret_cast<float*>(pool.data() + b + kHdrWords); }
+    float* score_w(int32_t b) { return init_score(b) + hdr(b).count; }
+    int32_t* simulations_n(int32_t b) { return reinterpret_cast<int32_t*>(pool.data() + b + kHdrWords + 2 * hdr(b).count); }
+    uint32_t* edge(int32_t b) { return pool.data() + b + kHdrWords + 3 * hdr(b).count; }
+    static uint32_t pack_edge(int32_t child_block, uint8_t m) {
+        return (child_block < 0 ? 0u : (static_cast<uint32_t>(child_block >> 2) + 1u)) | (static_cast<uint32_t>(m) << 24);
+    }
+    static int32_t edge_child(uint32_t e) { return (e & 0xFFFFFFu) ? static_cast<int32_t>(((e & 0xFFFFFFu) - 1u) << 2) : -1; }
     static uint8_t edge_move(uint32_t e) { return static_cast<uint8_t>(e >> 24); }
-    // appends a zero-filled block for `count` children and returns its word offset
-    int32_t append_block(int32_t count) {
-        const size_t first = pool.size();
-        pool.resize(first + 4 * static_cast<size_t>(count));
-        return static_cast<int32_t>(first);
+    // appends the block of a newly visited node (rows zeroed, not expanded) and returns its offset; invalidates pointers
+    int32_t new_block(const Pos& pos, int32_t count) {
+        const size_t b = pool.size();
+        if (b + kHdrWords + 4 * static_cast<size_t>(count) >= (static_cast<size_t>(0xFFFFFE) << 2))
+            throw SpError{CATTUS_B200_ERANGE, "search tree exceeds its 2^26-word address space"};
+        pool.resize(b + kHdrWords + 4 * static_cast<size_t>(count));
+        Header& h = hdr(static_cast<int32_t>(b));
+        h.pos = pos;
+        h.count = count;
+        h.expanded = 0;
+        return static_cast<int32_t>(b);
     }
 };
 
@@ -542,8 +553,7 @@ class Worker {
         bool leaf_flipped = false;
         Pos leaf_eval_pos;  // the position as sent to the network (Player1 to move)
         uint32_t wait_row = 0;  // row of the pending batch this slot is parked on
-        int32_t sel_node = -1;  // node the in-progress select stands on (-1: no simulation in progress)
-        bool sel_rows_ready = false;  // its children's rows have been requested (prefetched) one ring turn ago
+        int32_t sel_node = -1;  // block of the node the in-progress select stands on (-1: no simulation in progress)
         PosKey leaf_key{0, 0};        // cache key of the leaf being evaluated
         int leaf_n_legal = 0;
         uint32_t group = 0;     // slot group (one batch per group and evaluator)
@@ -759,34 +769,37 @@ class Worker {
             }
             s.path.clear();  // select (mod.rs:199-231) starts at the root
             s.sel_node = t.root;
-            s.sel_rows_ready = false;
-            __builtin_prefetch(&t.nodes[t.root]);
-            if (t.nodes.capacity() > t.nodes.size()) __builtin_prefetch(t.nodes.data() + t.nodes.size(), 1);  // a first visit appends a node
+            prefetch_block(t, t.root, t.hdr(t.root).count);
+            // a first visit appends a block at the tail of the pool: request those lines for writing
+            if (t.pool.capacity() >= t.pool.size() + 128)
+                for (int off = 0; off < 128; off += 16) __builtin_prefetch(t.pool.data() + t.pool.size() + off, 1);
             return true;
         }
         const int32_t node = s.sel_node;
-        const Node<Pos>& nd = t.nodes[node];
-        if (nd.count == 0 || R.status(nd.pos) != 0) {
+        const typename Tree<Pos>::Header& nd = t.hdr(node);
+        if (!nd.expanded || R.status(nd.pos) != 0) {
             s.sel_node = -1;
             if (at_leaf(s, node)) return true;  // terminal: backpropagated
             return evaluate_leaf(si);
         }
-        if (!s.sel_rows_ready) {
-            const uint32_t* blk = t.pool.data() + nd.first;
-            for (int off = 0; off < 3 * nd.count; off += 16) __builtin_prefetch(blk + off);
-            s.sel_rows_ready = true;
-            return true;
-        }
-        const int32_t best = select_child(t.init_score(nd), t.score_w(nd), t.simulations_n(nd), nd.count, params_[s.cur].explore_factor, sel_);
-        s.path.push_back({nd.first + nd.count + best, nd.count});
-        int32_t c = Tree<Pos>::edge_child(t.edge(nd)[best]);
+        const int32_t count = nd.count;
+        const int32_t best = select_child(t.init_score(node), t.score_w(node), t.simulations_n(node), count, params_[s.cur].explore_factor, sel_);
+        s.path.push_back({node + Tree<Pos>::kHdrWords + count + best, count});
+        int32_t c = Tree<Pos>::edge_child(t.edge(node)[best]);
         if (c < 0)
             c = materialise(t, node, best);
         else
-            __builtin_prefetch(&t.nodes[c]);
+            prefetch_block(t, c, count);
         s.sel_node = c;
-        s.sel_rows_ready = false;
         return true;
+    }
+
+    // requests a node's header and the three arrays select reads; `children` is the caller's estimate of the node's
+    // child count (its parent's: each move removes one legal move in hex and tic-tac-toe)
+    static void prefetch_block(const Tree<Pos>& t, int32_t b, int32_t children) {
+        const uint32_t* p = t.pool.data() + b;
+        const int words = Tree<Pos>::kHdrWords + 3 * children;
+        for (int off = 0; off < words; off += 16) __builtin_prefetch(p + off);
     }
 
     void finish_game(Slot& s, int status) {
@@ -875,11 +888,8 @@ class Worker {
                 t.clear();
         }
         if (t.root < 0) {
-            t.nodes.reserve(static_cast<size_t>(params_[s.cur].sim_num) + 64);
-            t.pool.reserve(4 * (static_cast<size_t>(params_[s.cur].sim_num) + 8) * static_cast<size_t>(R.moves_num()));
-            t.nodes.emplace_back();
-            t.nodes.back().pos = position;
-            t.root = 0;
+            t.pool.reserve((static_cast<size_t>(params_[s.cur].sim_num) + 8) * (Tree<Pos>::kHdrWords + 4 * static_cast<size_t>(R.moves_num())));
+            t.root = t.new_block(position, children_of(position));
         }
         s.sims_left = params_[s.cur].sim_num;
     }
@@ -887,19 +897,20 @@ class Worker {
     // mod.rs:283-301, depth_limit = 3 (root, its children, their children).  Unvisited children have no node yet;
     // their position is parent + move, compared on the fly and materialised on a match.
     int32_t find_node_with_position(Tree<Pos>& t, const Pos& position) {
-        if (R.same(t.nodes[t.root].pos, position)) return t.root;
+        if (R.same(t.hdr(t.root).pos, position)) return t.root;
         std::vector<int32_t> layer{t.root}, next;
         for (int depth = 1; depth < 3; ++depth) {
             next.clear();
             for (int32_t n : layer) {
-                const int32_t count = t.nodes[n].count;
+                if (!t.hdr(n).expanded) continue;
+                const int32_t count = t.hdr(n).count;
                 for (int32_t i = count - 1; i >= 0; --i) {
-                    const uint32_t e = t.edge(t.nodes[n])[i];
+                    const uint32_t e = t.edge(n)[i];
                     const int32_t c = Tree<Pos>::edge_child(e);
                     if (c >= 0) {
-                        if (R.same(t.nodes[c].pos, position)) return c;
+                        if (R.same(t.hdr(c).pos, position)) return c;
                         next.push_back(c);
-                    } else if (R.child_matches(t.nodes[n].pos, Tree<Pos>::edge_move(e), position)) {
+                    } else if (R.child_matches(t.hdr(n).pos, Tree<Pos>::edge_move(e), position)) {
                         return materialise(t, n, i);
                     }
                 }
@@ -909,15 +920,14 @@ class Worker {
         return -1;
     }
 
+    int32_t children_of(const Pos& pos) const { return R.status(pos) != 0 ? 0 : popcount128(R.legal_mask(pos)); }
+
     int32_t materialise(Tree<Pos>& t, int32_t parent, int32_t i) {
-        const uint8_t m = Tree<Pos>::edge_move(t.edge(t.nodes[parent])[i]);
-        const Pos child = R.moved(t.nodes[parent].pos, m);
-        t.nodes.emplace_back();
-        t.nodes.back().pos = child;
-        const int32_t idx = static_cast<int32_t>(t.nodes.size()) - 1;
-        if (idx >= 0xFFFFFE) throw SpError{CATTUS_B200_ERANGE, "search tree exceeds 2^24 nodes"};
-        t.edge(t.nodes[parent])[i] = Tree<Pos>::pack_edge(idx, m);
-        return idx;
+        const uint8_t m = Tree<Pos>::edge_move(t.edge(parent)[i]);
+        const Pos child = R.moved(t.hdr(parent).pos, m);
+        const int32_t cb = t.new_block(child, children_of(child));
+        t.edge(parent)[i] = Tree<Pos>::pack_edge(cb, m);
+        return cb;
     }
 
     // mod.rs:303-333: copy the subtree; edges are re-inserted in iteration (newest-first) order => reversed
@@ -925,48 +935,39 @@ class Worker {
         if (t.root == sub_root) return;
         Tree<Pos> nt;
         // room for the kept subtree plus one more search (capacity is only reserved address space until touched)
-        const size_t more_nodes = static_cast<size_t>(params_[s.cur].sim_num) + 64;
-        const size_t more_edges = (static_cast<size_t>(params_[s.cur].sim_num) + 8) * static_cast<size_t>(R.moves_num());
-        nt.nodes.reserve(t.nodes.size() / 4 + more_nodes);
-        nt.pool.reserve(t.pool.size() / 4 + 4 * more_edges);
-        nt.nodes.emplace_back();
-        nt.nodes[0].pos = t.nodes[sub_root].pos;
-        nt.root = 0;
-        std::vector<std::pair<int32_t, int32_t>> stack{{sub_root, 0}};
+        nt.pool.reserve(t.pool.size() / 4 + (static_cast<size_t>(params_[s.cur].sim_num) + 8) * (Tree<Pos>::kHdrWords + 4 * static_cast<size_t>(R.moves_num())));
+        nt.root = nt.new_block(t.hdr(sub_root).pos, t.hdr(sub_root).count);
+        std::vector<std::pair<int32_t, int32_t>> stack{{sub_root, nt.root}};
         while (!stack.empty()) {
             const auto [old_n, new_n] = stack.back();
             stack.pop_back();
-            const Node<Pos>& on = t.nodes[old_n];
-            const int32_t count = on.count;
-            if (count == 0) continue;
-            nt.nodes[new_n].first = nt.append_block(count);
-            nt.nodes[new_n].count = count;
+            if (!t.hdr(old_n).expanded) continue;
+            const int32_t count = t.hdr(old_n).count;
+            nt.hdr(new_n).expanded = 1;
             for (int32_t i = 0; i < count; ++i) {  // new insertion order = old iteration order (newest first)
                 const int32_t o = count - 1 - i;
-                const uint32_t e = t.edge(on)[o];
-                nt.init_score(nt.nodes[new_n])[i] = t.init_score(on)[o];
-                nt.score_w(nt.nodes[new_n])[i] = t.score_w(on)[o];
-                nt.simulations_n(nt.nodes[new_n])[i] = t.simulations_n(on)[o];
+                const uint32_t e = t.edge(old_n)[o];
+                nt.init_score(new_n)[i] = t.init_score(old_n)[o];
+                nt.score_w(new_n)[i] = t.score_w(old_n)[o];
+                nt.simulations_n(new_n)[i] = t.simulations_n(old_n)[o];
                 int32_t nc = -1;
                 const int32_t old_c = Tree<Pos>::edge_child(e);
                 if (old_c >= 0) {
-                    nt.nodes.emplace_back();
-                    nt.nodes.back().pos = t.nodes[old_c].pos;
-                    nc = static_cast<int32_t>(nt.nodes.size()) - 1;
+                    nc = nt.new_block(t.hdr(old_c).pos, t.hdr(old_c).count);  // may move nt.pool: pointers are re-derived below
                     stack.push_back({old_c, nc});
                 }
-                nt.edge(nt.nodes[new_n])[i] = Tree<Pos>::pack_edge(nc, Tree<Pos>::edge_move(e));
+                nt.edge(new_n)[i] = Tree<Pos>::pack_edge(nc, Tree<Pos>::edge_move(e));
             }
         }
         t = std::move(nt);
-        if (t.nodes[t.root].count > 0) add_dirichlet_noise(s, t, t.root);
+        if (t.hdr(t.root).expanded && t.hdr(t.root).count > 0) add_dirichlet_noise(s, t, t.root);
     }
 
     // mod.rs:419-446
     void add_dirichlet_noise(Slot& s, Tree<Pos>& t, int32_t node) {
         const Params& P = params_[s.cur];
         if (P.noise_alpha == 0.0f || P.noise_eps == 0.0f) return;
-        const int32_t count = t.nodes[node].count;
+        const int32_t count = t.hdr(node).count;
         if (count < 2) return;
         noise_.resize(count);
         double tot = 0.0;
@@ -976,7 +977,7 @@ class Worker {
         }
         const float eps = P.noise_eps;
         for (int i = 0; i < count; ++i) {  // zip(edges() order = newest first, noise)
-            float& init = t.init_score(t.nodes[node])[count - 1 - i];
+            float& init = t.init_score(node)[count - 1 - i];
             const float nz = static_cast<float>(noise_[i] / tot);
             init = (1.0f - eps) * init + eps * nz;
         }
@@ -987,7 +988,7 @@ class Worker {
     bool at_leaf(Slot& s, int32_t node) {
         Tree<Pos>& t = s.players[s.cur].tree;
         s.leaf = node;
-        const Pos& leaf_pos = t.nodes[node].pos;
+        const Pos leaf_pos = t.hdr(node).pos;
         const int st = R.status(leaf_pos);
         if (st != 0) {
             c_.terminal += 1;
@@ -1029,14 +1030,6 @@ class Worker {
         }
         pb.parked.push_back(si);
         s.phase = kWaitEval;
-        {
-            // The evaluation will append this node's children at the tails of the tree's edge arrays: request those
-            // lines for writing now, they arrive while the batch is on the GPU (a cold tail costs a DRAM read per array).
-            Tree<Pos>& t = s.players[s.cur].tree;
-            const size_t tail = t.pool.size();
-            if (t.pool.capacity() >= tail + 4 * static_cast<size_t>(n_legal))
-                for (int off = 0; off < 4 * n_legal; off += 16) __builtin_prefetch(t.pool.data() + tail + off, 1);
-        }
         return false;
     }
 
@@ -1045,10 +1038,9 @@ class Worker {
         Tree<Pos>& t = s.players[s.cur].tree;
         const int32_t leaf = s.leaf;
         const u128 legal = R.legal_mask(s.leaf_eval_pos);
-        const int32_t count = popcount128(legal);
-        const int32_t first = t.append_block(count);  // score_w and simulations_n start at zero
-        std::memcpy(t.pool.data() + first, val, sizeof(float) * count);
-        uint32_t* ed = t.pool.data() + first + 3 * count;
+        const int32_t count = t.hdr(leaf).count;  // == popcount(legal): the block was sized when the node was first visited
+        std::memcpy(t.init_score(leaf), val, sizeof(float) * count);
+        uint32_t* ed = t.edge(leaf);
         int32_t k = 0;
         for (int half = 0; half < 2; ++half) {  // legal_moves() of the evaluated position, ascending; un-flipped by flip_score_if_needed
             uint64_t bits = static_cast<uint64_t>(legal >> (64 * half));
@@ -1058,8 +1050,7 @@ class Worker {
                 ed[k++] = Tree<Pos>::pack_edge(-1, static_cast<uint8_t>(s.leaf_flipped ? R.flip_move(m) : m));
             }
         }
-        t.nodes[leaf].first = first;
-        t.nodes[leaf].count = count;
+        t.hdr(leaf).expanded = 1;
         if (leaf == t.root) add_dirichlet_noise(s, t, leaf);
         float v = val[count];
         if (s.leaf_flipped) v = -v;
@@ -1068,7 +1059,7 @@ class Worker {
 
     // mod.rs:270-281
     void backpropagate(Slot& s, Tree<Pos>& t, float score) {
-        const uint8_t root_turn = t.nodes[t.root].pos.turn;  // the side to move alternates along the path in hex and tic-tac-toe
+        const uint8_t root_turn = t.hdr(t.root).pos.turn;  // the side to move alternates along the path in hex and tic-tac-toe
         for (size_t i = 0; i < s.path.size(); ++i) {
             const uint8_t turn = (i & 1) ? static_cast<uint8_t>(3 - root_turn) : root_turn;
             reinterpret_cast<int32_t*>(t.pool.data())[s.path[i].w_idx + s.path[i].count] += 1;
@@ -1083,12 +1074,12 @@ class Worker {
     void end_search(Slot& s) {
         Tree<Pos>& t = s.players[s.cur].tree;
         const Params& P = params_[s.cur];
-        const Node<Pos>& root = t.nodes[t.root];
+        const typename Tree<Pos>::Header& root = t.hdr(t.root);
         std::vector<std::pair<uint8_t, float>> probs;
         probs.reserve(root.count);
         uint32_t total = 0;
-        const int32_t* rn = t.simulations_n(root);
-        const uint32_t* re = t.edge(root);
+        const int32_t* rn = t.simulations_n(t.root);
+        const uint32_t* re = t.edge(t.root);
         for (int32_t i = 0; i < root.count; ++i) total += static_cast<uint32_t>(rn[i]);
         for (int32_t i = root.count - 1; i >= 0; --i)  // edges() order
             probs.emplace_back(Tree<Pos>::edge_move(re[i]), static_cast<float>(rn[i]) / static_cast<float>(total));
