@@ -327,6 +327,13 @@ class Cache {
     Cache(const Cache&) = delete;
     Cache& operator=(const Cache&) = delete;
 
+    // requests the bucket of `k` (tags, first keys) so that a find / insert a little later does not stall on memory
+    void prefetch(const PosKey& k) const {
+        const size_t b = PosKeyHash()(k) & (n_buckets_ - 1);
+        __builtin_prefetch(&meta_[b]);
+        __builtin_prefetch(&keys_[b * kWays]);
+        __builtin_prefetch(&keys_[b * kWays + 4]);
+    }
     // copies the stored (probs..., value) of `k` into out[0 .. n_legal] and returns true on a hit
     bool find(const PosKey& k, int n_legal, float* out) {
         const uint64_t h = PosKeyHash()(k);
@@ -555,6 +562,7 @@ class Worker {
         uint32_t wait_row = 0;  // row of the pending batch this slot is parked on
         int32_t sel_node = -1;  // block of the node the in-progress select stands on (-1: no simulation in progress)
         PosKey leaf_key{0, 0};        // cache key of the leaf being evaluated
+        int32_t prepared_leaf = -1;   // block whose evaluation inputs (leaf_*) were set up early, at its first visit
         int leaf_n_legal = 0;
         uint32_t group = 0;     // slot group (one batch per group and evaluator)
         Clock::time_point search_t0;
@@ -768,6 +776,7 @@ class Worker {
                 return true;
             }
             s.path.clear();  // select (mod.rs:199-231) starts at the root
+            s.prepared_leaf = -1;
             s.sel_node = t.root;
             prefetch_block(t, t.root, t.hdr(t.root).count);
             // a first visit appends a block at the tail of the pool: request those lines for writing
@@ -786,10 +795,12 @@ class Worker {
         const int32_t best = select_child(t.init_score(node), t.score_w(node), t.simulations_n(node), count, params_[s.cur].explore_factor, sel_);
         s.path.push_back({node + Tree<Pos>::kHdrWords + count + best, count});
         int32_t c = Tree<Pos>::edge_child(t.edge(node)[best]);
-        if (c < 0)
+        if (c < 0) {
             c = materialise(t, node, best);
-        else
+            prepare_leaf(s, t, c);  // a first visit is this simulation's leaf: set up its evaluation and request its cache bucket now
+        } else {
             prefetch_block(t, c, count);
+        }
         s.sel_node = c;
         return true;
     }
@@ -995,12 +1006,20 @@ class Worker {
             backpropagate(s, t, st == 3 ? 0.0f : (st == 1 ? 1.0f : -1.0f));
             return true;
         }
-        // NNetwork::evaluate (net/mod.rs:74-87): flip -> cache -> network
+        if (s.prepared_leaf != node) prepare_leaf(s, t, node);
+        return false;
+    }
+
+    // NNetwork::evaluate (net/mod.rs:74-87), first part: flip to the side-to-move view, cache key, legal count
+    void prepare_leaf(Slot& s, Tree<Pos>& t, int32_t node) {
+        const Pos& leaf_pos = t.hdr(node).pos;
+        s.prepared_leaf = node;
+        if (R.status(leaf_pos) != 0) return;
         s.leaf_flipped = leaf_pos.turn != 1;
         s.leaf_eval_pos = s.leaf_flipped ? R.flipped_boards(leaf_pos) : leaf_pos;
         s.leaf_key = R.key(s.leaf_eval_pos);
-        s.leaf_n_legal = popcount128(R.legal_mask(s.leaf_eval_pos));
-        return false;
+        s.leaf_n_legal = t.hdr(node).count;
+        if (evals_[s.cur]->cache) evals_[s.cur]->cache->prefetch(s.leaf_key);
     }
 
     // cache lookup, else join the group's batch.  Returns false if the leaf was parked on the evaluator.
