@@ -317,9 +317,10 @@ def main():
     ap.add_argument("--no-selfplay", action="store_true", help="skip the self-play sims/s leg")
     ap.add_argument("--no-other-workloads", action="store_true", help="skip the brief hex5 evals/s leg of the default run")
     ap.add_argument("--selfplay-game", default="hex5", choices=sorted(SELFPLAY_CFG))
-    ap.add_argument("--selfplay-games", type=int, default=6144, help="games per GPU in the self-play leg")
+    ap.add_argument("--selfplay-games", type=int, default=8192, help="games per GPU in the self-play leg")
     ap.add_argument("--selfplay-threads", type=int, default=0, help="worker threads per GPU (0 = host cores / GPUs)")
-    ap.add_argument("--selfplay-gpt", type=int, default=384, help="concurrent games per worker thread")
+    ap.add_argument("--selfplay-gpt", type=int, default=512, help="concurrent games per worker thread")
+    ap.add_argument("--selfplay-groups", type=int, default=2, help="slot groups per worker thread (one batch in flight per group)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -489,8 +490,9 @@ def main():
         games_total = max(2, args.selfplay_games * world // 2 * 2)
         mc = SELFPLAY_CFG[args.selfplay_game]
         with CudaNetwork(export_blob(net.make_state_dict(sp_cfg, 0), sp_cfg.game), sp_cfg.game, device=local_rank, batch_size=max(64, min(4096, gpt)),
-                         n_streams=max(4, min(32, threads)), precision="bf16") as sp_nw:
-            runner = SelfPlayRunner(args.selfplay_game, {"mcts": mc, "threads": threads, "games_per_thread": gpt, "seed": 1})
+                         n_streams=max(4, min(32, threads * args.selfplay_groups)), precision="bf16") as sp_nw:
+            runner = SelfPlayRunner(args.selfplay_game, {"mcts": mc, "threads": threads, "games_per_thread": gpt, "groups_per_thread": args.selfplay_groups,
+                                                          "seed": 1})
             runner.generate_data(sp_nw, None, 2 * threads, first_game=rank, game_stride=world)  # warm-up (graphs, caches of the allocator)
             l0 = sp_nw.metrics()["model.kernel_launches"]
             barrier()

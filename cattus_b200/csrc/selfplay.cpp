@@ -945,7 +945,14 @@ class Worker {
     void remove_all_but_subtree(Slot& s, Tree<Pos>& t, int32_t sub_root) {
         if (t.root == sub_root) return;
         Tree<Pos> nt;
-        // room for the kept subtree plus one more search (capacity is only reserved address space until touched)
+        // The copy goes into a recycled buffer (every move of every game replaces a tree: fresh allocations of ~1 MB
+        // each mean an mmap, a few hundred page faults and an munmap per move); room for the kept subtree plus one
+        // more search.
+        if (!pool_free_.empty()) {
+            nt.pool = std::move(pool_free_.back());
+            pool_free_.pop_back();
+            nt.pool.clear();
+        }
         nt.pool.reserve(t.pool.size() / 4 + (static_cast<size_t>(params_[s.cur].sim_num) + 8) * (Tree<Pos>::kHdrWords + 4 * static_cast<size_t>(R.moves_num())));
         nt.root = nt.new_block(t.hdr(sub_root).pos, t.hdr(sub_root).count);
         std::vector<std::pair<int32_t, int32_t>> stack{{sub_root, nt.root}};
@@ -970,6 +977,7 @@ class Worker {
                 nt.edge(new_n)[i] = Tree<Pos>::pack_edge(nc, Tree<Pos>::edge_move(e));
             }
         }
+        pool_free_.push_back(std::move(t.pool));
         t = std::move(nt);
         if (t.hdr(t.root).expanded && t.hdr(t.root).count > 0) add_dirichlet_noise(s, t, t.root);
     }
@@ -1264,6 +1272,7 @@ class Worker {
     Evaluator* evals_[2];
     std::vector<Slot> slots_;
     std::vector<Group> groups_;
+    std::vector<std::vector<uint32_t>> pool_free_;  // retired tree buffers, reused by the next tree copy
     std::deque<std::pair<uint32_t, int>> inflight_;  // (group, evaluator) of this worker's batches in flight, oldest first
     int abi_wpp_ = 1;
     double eval_wait_ = 0.0;
