@@ -45,6 +45,8 @@ WORKLOADS = {
     "hex5": ("hex5", 16384, 4),
     "hex7": ("hex7", 16384, 4),
     "hex4": ("hex4", 16384, 4),
+    "hex9": ("hex9", 16384, 4),
+    "hex11": ("hex11", 8192, 4),
 }
 DEFAULT_WORKLOAD = "chess10x128"
 CONFIG_NOTES = {
@@ -54,6 +56,8 @@ CONFIG_NOTES = {
     "hex7": "BASELINE.json configs[2]: hex 7x7, ConvNetV1 7x16 (heads 16/16) random-init",
     "hex4": "BASELINE.json configs[0]: hex 4x4, ConvNetV1 7x16 (heads 16/16) random-init",
     "chess_dev": "training/config/chess_dev.yaml: chess, ConvNetV1 7x16 (heads 8/8) random-init",
+    "hex9": "hex 9x9 (training/self-play/src/bin/hex9_self_player.rs), ConvNetV1 7x16 (heads 16/16) random-init",
+    "hex11": "hex 11x11, the reference's standard board (engine/src/hex/core.rs:341), ConvNetV1 7x16 (heads 16/16) random-init",
 }
 
 
@@ -201,6 +205,10 @@ SELFPLAY_CFG = {
              "prior_noise_epsilon": 0.25, "cache_size": 1000000},
     "hex7": {"sim_num": 600, "explore_factor": 1.41421, "temperature_policy": [[10, 1.0], [9999, 0.0]], "prior_noise_alpha": 0.03,
              "prior_noise_epsilon": 0.25, "cache_size": 1000000},
+    "hex9": {"sim_num": 600, "explore_factor": 1.41421, "temperature_policy": [[10, 1.0], [9999, 0.0]], "prior_noise_alpha": 0.03,
+             "prior_noise_epsilon": 0.25, "cache_size": 1000000},
+    "hex11": {"sim_num": 600, "explore_factor": 1.41421, "temperature_policy": [[10, 1.0], [9999, 0.0]], "prior_noise_alpha": 0.03,
+              "prior_noise_epsilon": 0.25, "cache_size": 1000000},
     "hex4": {"sim_num": 100, "explore_factor": 1.41421, "temperature_policy": [[4, 1.0], [9999, 0.0]], "prior_noise_alpha": 0.03,
              "prior_noise_epsilon": 0.25, "cache_size": 1000000},
 }
