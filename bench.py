@@ -329,6 +329,9 @@ def main():
     ap.add_argument("--selfplay-threads", type=int, default=0, help="worker threads per GPU (0 = host cores / GPUs)")
     ap.add_argument("--selfplay-gpt", type=int, default=512, help="concurrent games per worker thread")
     ap.add_argument("--selfplay-groups", type=int, default=2, help="slot groups per worker thread (one batch in flight per group)")
+    ap.add_argument("--single-search", action="store_true",
+                    help="also time ONE tree searching with --sim-num 10000 (BASELINE configs[4]'s UCI setting, on the self-play game): "
+                         "two games, one thread, one leaf at a time through cattus_b200_eval")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -515,6 +518,16 @@ def main():
             "note": "rank 0's counters shown; value = simulations of all ranks / max seconds; games partitioned by index across GPUs, no collective"})
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             selfplay["cpu_baseline"] = time_cpu_selfplay(args.selfplay_game, 2, 2)
+        if rank == 0 and args.single_search:
+            with CudaNetwork(export_blob(net.make_state_dict(sp_cfg, 0), sp_cfg.game), sp_cfg.game, device=local_rank, batch_size=64, n_streams=1,
+                             precision="bf16") as ss_nw:
+                ss_mc = dict(mc, sim_num=10000)
+                ss_sum, _ = SelfPlayRunner(args.selfplay_game, {"mcts": ss_mc, "threads": 1, "games_per_thread": 1, "leaf_queue": 1, "seed": 1}).generate_data(
+                    ss_nw, None, 2)
+            sm = ss_sum["metrics"]
+            selfplay["single_search"] = {"sim_num": 10000, "searches": sm["selfplay.searches"], "seconds_per_search": sm["selfplay.seconds"] / max(1, sm["selfplay.searches"]),
+                                         "sims_per_sec": sm["selfplay.sims_per_sec"], "evaluations": sm["selfplay.evaluations"],
+                                         "note": "one tree, one leaf in flight (the reference's UCI arrangement), per-leaf cattus_b200_eval"}
 
     total_positions = world * positions_per_step * args.steps
     value = total_positions / t_value
