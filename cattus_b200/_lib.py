@@ -61,8 +61,18 @@ class SelfPlaySummary(C.Structure):
     ]
 
 
+class ChessInfo(C.Structure):
+    """cattus_b200_chess_info (include/cattus_b200_chess.h)."""
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("turn", C.c_uint32), ("status", C.c_uint32), ("fifty_rule_count", C.c_uint32),
+        ("in_check", C.c_uint32), ("n_legal", C.c_uint32), ("planes", C.c_uint64 * 18), ("legal_bitmap", C.c_uint8 * 235),
+        ("pad", C.c_uint8), ("moves", C.c_uint16 * 224), ("nn_index", C.c_uint16 * 224),
+    ]
+
+
 # every symbol include/*.h declares: name -> (restype, argtypes)
 _H = C.c_void_p
+_u16p = C.POINTER(C.c_uint16)
 _u64p, _u8p, _f32p, _u32p = C.POINTER(C.c_uint64), C.POINTER(C.c_uint8), C.POINTER(C.c_float), C.POINTER(C.c_uint32)
 SYMBOLS = {
     "cattus_b200_create": (C.c_int, [C.POINTER(Desc), C.POINTER(_H)]),
@@ -89,9 +99,15 @@ SYMBOLS = {
     "cattus_b200_selfplay_game_count": (C.c_int, [_H, _u32p]),
     "cattus_b200_selfplay_game_info": (C.c_int, [_H, C.c_uint32, _u32p, _u32p, _u32p]),
     "cattus_b200_selfplay_game_moves": (C.c_int, [_H, C.c_uint32, _u8p, C.c_uint32]),
+    "cattus_b200_selfplay_game_moves16": (C.c_int, [_H, C.c_uint32, _u16p, C.c_uint32]),
     "cattus_b200_selfplay_entry": (C.c_int, [_H, C.c_uint32, C.c_uint32, _u8p, C.c_size_t, C.POINTER(C.c_size_t), _u32p]),
     "cattus_b200_selfplay_free": (None, [_H]),
     "cattus_b200_selfplay_last_error": (C.c_char_p, []),
+    # include/cattus_b200_chess.h
+    "cattus_b200_chess_position": (C.c_int, [C.c_char_p, _u16p, C.c_uint32, C.POINTER(ChessInfo)]),
+    "cattus_b200_chess_perft": (C.c_int, [C.c_char_p, C.c_uint32, C.POINTER(C.c_uint64)]),
+    "cattus_b200_chess_nn_table": (C.c_int, [_u16p, C.c_uint32]),
+    "cattus_b200_chess_last_error": (C.c_char_p, []),
 }
 
 EVAL_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, _u64p, _u8p, C.c_uint32, _f32p, C.c_size_t, _u32p, _f32p)

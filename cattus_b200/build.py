@@ -49,7 +49,7 @@ def nvcc_path() -> str:
 def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not is_stale():
         return LIB
-    cmd = [nvcc_path(), *NVCC_FLAGS, "-o", str(LIB), str(CSRC / "engine.cu"), str(CSRC / "selfplay.cpp")]
+    cmd = [nvcc_path(), *NVCC_FLAGS, "-o", str(LIB), str(CSRC / "engine.cu"), str(CSRC / "selfplay.cpp"), str(CSRC / "chess_api.cpp")]
     if os.environ.get("CATTUS_B200_TRUNK_TRACE"):  # diagnostic build with clock64 trace points (tools/trace_trunk.py)
         cmd.insert(1, "-DCB2_TRUNK_TRACE")
     if verbose:

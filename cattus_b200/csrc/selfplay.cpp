@@ -37,6 +37,7 @@
 #include <sys/types.h>
 
 #include "../../include/cattus_b200_selfplay.h"
+#include "chess_rules.hpp"
 
 namespace sp {
 
@@ -130,6 +131,9 @@ struct HexPosT {
 template <class W>
 struct HexRulesT {
     using Pos = HexPosT<W>;
+    using Move = uint8_t;
+    static constexpr bool kChess = false;
+    int max_children() const { return cells; }
     static W bit(int i) { return static_cast<W>(1) << i; }
     int s = 0, cells = 0;
     W full = 0, col0 = 0, col_last = 0, row0 = 0, row_last = 0;
@@ -252,6 +256,9 @@ struct TttPos {
 // engine/src/ttt/core.rs
 struct TttRules {
     using Pos = TttPos;
+    using Move = uint8_t;
+    static constexpr bool kChess = false;
+    int max_children() const { return 9; }
     int moves_num() const { return 9; }
     int words_per_plane() const { return 1; }
     Pos initial() const { return Pos(); }
@@ -456,12 +463,12 @@ __attribute__((target_clones("avx2", "default"))) static int select_child(const 
 }
 // Search tree storage.  Every visited node is ONE 16-byte-aligned block of 32-bit words in `pool`:
 //   Header { position, count, expanded } | init_score[count] (f32) | score_w[count] (f32) | simulations_n[count] (i32) |
-//   edge[count]
+//   edge[count] | move16[count] (chess only: 16-bit moves, two per word)
 // with count = number of legal moves (known from the position when the node is first visited; the rows are filled in
 // when its evaluation arrives) and edge = (child block offset / 4 + 1) in the low 24 bits (0: child not visited yet, its
 // position is derived on demand) + the move in the high 8 (MctsNode / MctsEdge, mod.rs:21-56).  A node visit during
 // select touches one run of cache lines, and the run can be requested as soon as the parent has picked the child.
-template <class Pos>
+template <class Pos, bool Wide = false>
 struct Tree {
     struct alignas(16) Header {
         Pos pos;
@@ -481,6 +488,11 @@ struct Tree {
     float* score_w(int32_t b) { return init_score(b) + hdr(b).count; }
     int32_t* simulations_n(int32_t b) { return reinterpret_cast<int32_t*>(pool.data() + b + kHdrWords + 2 * hdr(b).count); }
     uint32_t* edge(int32_t b) { return pool.data() + b + kHdrWords + 3 * hdr(b).count; }
+    uint16_t* move16(int32_t b) { return reinterpret_cast<uint16_t*>(pool.data() + b + kHdrWords + 4 * hdr(b).count); }
+    static size_t block_words(int32_t count) {
+        const size_t c = static_cast<size_t>(count);
+        return kHdrWords + 4 * c + (Wide ? (c + 1) / 2 : 0);
+    }
     static uint32_t pack_edge(int32_t child_block, uint8_t m) {
         return (child_block < 0 ? 0u : (static_cast<uint32_t>(child_block >> 2) + 1u)) | (static_cast<uint32_t>(m) << 24);
     }
@@ -489,9 +501,9 @@ struct Tree {
     // appends the block of a newly visited node (rows zeroed, not expanded) and returns its offset; invalidates pointers
     int32_t new_block(const Pos& pos, int32_t count) {
         const size_t b = pool.size();
-        if (b + kHdrWords + 4 * static_cast<size_t>(count) >= (static_cast<size_t>(0xFFFFFE) << 2))
-            throw SpError{CATTUS_B200_ERANGE, "search tree exceeds its 2^26-word address space"};
-        pool.resize(b + kHdrWords + 4 * static_cast<size_t>(count));
+        const size_t words = (block_words(count) + 3) & ~static_cast<size_t>(3);  // blocks stay 16-byte aligned
+        if (b + words >= (static_cast<size_t>(0xFFFFFE) << 2)) throw SpError{CATTUS_B200_ERANGE, "search tree exceeds its 2^26-word address space"};
+        pool.resize(b + words);
         Header& h = hdr(static_cast<int32_t>(b));
         h.pos = pos;
         h.count = count;
@@ -516,7 +528,7 @@ struct Params {
 struct GameRecord {
     uint32_t game_idx = 0;
     uint8_t winner = 0;
-    std::vector<uint8_t> moves;
+    std::vector<uint16_t> moves;  // hex / ttt: cell index; chess: from | to << 6 | promotion << 12, real board coordinates
     std::vector<std::vector<uint8_t>> entries;
     std::vector<uint8_t> entry_dir;
 };
@@ -538,9 +550,12 @@ struct Shared {
 template <class Rules>
 class Worker {
     using Pos = typename Rules::Pos;
+    using Move = typename Rules::Move;
+    using TreeT = Tree<Pos, Rules::kChess>;
+    static constexpr bool kChess = Rules::kChess;
 
     struct Player {
-        Tree<Pos> tree;
+        TreeT tree;
     };
     enum Phase { kIdle, kStartMove, kSimulate, kWaitEval };
     struct Slot {
@@ -554,6 +569,7 @@ class Worker {
         struct PathStep {
             int32_t w_idx;  // word index of the taken child's score_w in the tree's pool
             int32_t count;  // children of that node: simulations_n is `count` words further
+            int32_t child;  // block of the node the step leads to
         };
         std::vector<PathStep> path;  // root -> leaf
         int32_t leaf = -1;
@@ -567,12 +583,14 @@ class Worker {
         uint32_t group = 0;     // slot group (one batch per group and evaluator)
         Clock::time_point search_t0;
         GameRecord rec;
-        std::vector<std::pair<Pos, std::vector<std::pair<uint8_t, float>>>> pending_entries;
+        std::vector<std::pair<Pos, std::vector<std::pair<Move, float>>>> pending_entries;
+        bool repetition = false;  // ChessGame::repetition_detected (chess/core.rs:441-449)
     };
     struct Pending {  // one batch under construction for one evaluator
         std::vector<uint64_t> planes;
         std::vector<PosKey> keys;
         std::vector<uint8_t> n_legal;
+        std::vector<uint8_t> legal;    // chess: one 235-byte legal-move bitmap per row
         std::vector<uint32_t> parked;  // slots waiting on this batch (each remembers its row)
         std::vector<uint32_t> table;   // open addressing: row + 1 of a key already in the batch (in-batch dedupe)
         std::vector<uint32_t> used;
@@ -597,6 +615,7 @@ class Worker {
             planes.clear();
             keys.clear();
             n_legal.clear();
+            legal.clear();
             parked.clear();
             for (uint32_t h : used) table[h] = 0;
             used.clear();
@@ -644,7 +663,7 @@ class Worker {
             gr.pend[1].init(gr.count);
             for (uint32_t i = 0; i < gr.count; ++i) slots_[gr.first + i].group = g;
         }
-        val_.resize(static_cast<size_t>(R.moves_num()) + 1);
+        val_.resize(static_cast<size_t>(R.max_children()) + 1);
         if (const char* e = std::getenv("CATTUS_B200_SELFPLAY_RING")) ring_size_ = std::max(1, std::min<int>(kMaxRing, std::atoi(e)));
         abi_wpp_ = (R.moves_num() + 63) / 64;
     }
@@ -712,6 +731,7 @@ class Worker {
         s.rec = GameRecord();
         s.rec.game_idx = s.game_idx;
         s.pending_entries.clear();
+        s.repetition = false;
         s.phase = kStartMove;
     }
 
@@ -753,7 +773,7 @@ class Worker {
         Slot& s = slots_[si];
         if (s.phase == kStartMove) {
             const Pos& pos = s.history.back();
-            const int st = R.status(pos);
+            const int st = s.repetition ? 3 : R.status(pos);  // ChessGame::status: a threefold repetition is a draw
             if (st != 0) {
                 finish_game(s, st);
                 start_next_game(s);
@@ -768,7 +788,7 @@ class Worker {
             return true;
         }
         // kSimulate
-        Tree<Pos>& t = s.players[s.cur].tree;
+        TreeT& t = s.players[s.cur].tree;
         if (s.sel_node < 0) {
             if (s.sims_left == 0) {
                 end_search(s);
@@ -785,7 +805,7 @@ class Worker {
             return true;
         }
         const int32_t node = s.sel_node;
-        const typename Tree<Pos>::Header& nd = t.hdr(node);
+        const typename TreeT::Header& nd = t.hdr(node);
         if (!nd.expanded || R.status(nd.pos) != 0) {
             s.sel_node = -1;
             if (at_leaf(s, node)) return true;  // terminal: backpropagated
@@ -793,23 +813,23 @@ class Worker {
         }
         const int32_t count = nd.count;
         const int32_t best = select_child(t.init_score(node), t.score_w(node), t.simulations_n(node), count, params_[s.cur].explore_factor, sel_);
-        s.path.push_back({node + Tree<Pos>::kHdrWords + count + best, count});
-        int32_t c = Tree<Pos>::edge_child(t.edge(node)[best]);
+        int32_t c = TreeT::edge_child(t.edge(node)[best]);
         if (c < 0) {
             c = materialise(t, node, best);
             prepare_leaf(s, t, c);  // a first visit is this simulation's leaf: set up its evaluation and request its cache bucket now
         } else {
             prefetch_block(t, c, count);
         }
+        s.path.push_back({node + TreeT::kHdrWords + count + best, count, c});
         s.sel_node = c;
         return true;
     }
 
     // requests a node's header and the three arrays select reads; `children` is the caller's estimate of the node's
     // child count (its parent's: each move removes one legal move in hex and tic-tac-toe)
-    static void prefetch_block(const Tree<Pos>& t, int32_t b, int32_t children) {
+    static void prefetch_block(const TreeT& t, int32_t b, int32_t children) {
         const uint32_t* p = t.pool.data() + b;
-        const int words = Tree<Pos>::kHdrWords + 3 * children;
+        const int words = TreeT::kHdrWords + 3 * children;
         for (int off = 0; off < words; off += 16) __builtin_prefetch(p + off);
     }
 
@@ -843,11 +863,38 @@ class Worker {
     }
 
     // write_data_entry + serializers (self_play.rs:248-276, :33-61; serialize/hex.rs:16-28; serialize/ttt.rs:17-22)
-    int make_entry(uint32_t game_idx, const Pos& pos_in, const std::vector<std::pair<uint8_t, float>>& probs_in, uint8_t winner,
+    int make_entry(uint32_t game_idx, const Pos& pos_in, const std::vector<std::pair<Move, float>>& probs_in, uint8_t winner,
                    std::vector<uint8_t>& bytes) const {
         const int pair_p1[2] = {1, 2}, pair_p2[2] = {2, 1};
         const int dir = (pos_in.turn == 1 ? pair_p1 : pair_p2)[game_idx % 2];
         float w = winner == 0 ? 0.0f : (winner == 1 ? 1.0f : -1.0f);
+        if constexpr (kChess) {
+            // ChessSerializer (serialize/chess.rs:18-57).  The stored position and its moves already are the flipped,
+            // Player1-to-move view write_data_entry asks for (self_play.rs:260-268); only the winner's sign follows the turn.
+            if (pos_in.turn != 1) w = -w;
+            std::vector<std::pair<uint16_t, float>> by_idx;
+            by_idx.reserve(probs_in.size());
+            for (auto& mp : probs_in) by_idx.emplace_back(static_cast<uint16_t>(R.nn_idx(mp.first)), mp.second);
+            std::sort(by_idx.begin(), by_idx.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+            if (by_idx.size() > 225) throw SpError{CATTUS_B200_ERANGE, "more than 225 legal moves"};
+            uint64_t pl[Rules::kPlanes];
+            R.planes(pos_in, pl);
+            bytes.assign(Rules::kPlanes * 8 + Rules::kLegalBytes + 225 * 4 + 1, 0);
+            uint8_t* p = bytes.data();
+            std::memcpy(p, pl, sizeof(pl));
+            p += sizeof(pl);
+            float probs[225];
+            for (float& x : probs) x = -1.0f;
+            for (size_t k = 0; k < by_idx.size(); ++k) {
+                p[by_idx[k].first >> 3] |= static_cast<uint8_t>(1u << (by_idx[k].first & 7));
+                probs[k] = by_idx[k].second;
+            }
+            p += Rules::kLegalBytes;
+            std::memcpy(p, probs, sizeof(probs));
+            p += sizeof(probs);
+            *p = static_cast<uint8_t>(static_cast<int8_t>(static_cast<int>(w)));
+            return dir;
+        } else {
         Pos pos = pos_in;
         const bool flipped = pos.turn != 1;
         if (flipped) {
@@ -872,6 +919,7 @@ class Worker {
         p += M * 4;
         *p = static_cast<uint8_t>(static_cast<int8_t>(static_cast<int>(w)));
         return dir;
+        }
     }
 
     void write_entry_file(const char* dir, uint32_t game_idx, size_t pos_idx, const std::vector<uint8_t>& bytes) const {
@@ -889,7 +937,7 @@ class Worker {
     // calc_moves_probabilities up to develop_tree (mod.rs:335-362)
     void begin_search(Slot& s) {
         s.search_t0 = Clock::now();
-        Tree<Pos>& t = s.players[s.cur].tree;
+        TreeT& t = s.players[s.cur].tree;
         const Pos& position = s.history.back();
         if (t.root >= 0) {
             const int32_t node = find_node_with_position(t, position);
@@ -899,15 +947,15 @@ class Worker {
                 t.clear();
         }
         if (t.root < 0) {
-            t.pool.reserve((static_cast<size_t>(params_[s.cur].sim_num) + 8) * (Tree<Pos>::kHdrWords + 4 * static_cast<size_t>(R.moves_num())));
-            t.root = t.new_block(position, children_of(position));
+            t.pool.reserve((static_cast<size_t>(params_[s.cur].sim_num) + 8) * TreeT::block_words(typical_children()));
+            t.root = add_node(t, position);
         }
         s.sims_left = params_[s.cur].sim_num;
     }
 
     // mod.rs:283-301, depth_limit = 3 (root, its children, their children).  Unvisited children have no node yet;
     // their position is parent + move, compared on the fly and materialised on a match.
-    int32_t find_node_with_position(Tree<Pos>& t, const Pos& position) {
+    int32_t find_node_with_position(TreeT& t, const Pos& position) {
         if (R.same(t.hdr(t.root).pos, position)) return t.root;
         std::vector<int32_t> layer{t.root}, next;
         for (int depth = 1; depth < 3; ++depth) {
@@ -917,11 +965,11 @@ class Worker {
                 const int32_t count = t.hdr(n).count;
                 for (int32_t i = count - 1; i >= 0; --i) {
                     const uint32_t e = t.edge(n)[i];
-                    const int32_t c = Tree<Pos>::edge_child(e);
+                    const int32_t c = TreeT::edge_child(e);
                     if (c >= 0) {
                         if (R.same(t.hdr(c).pos, position)) return c;
                         next.push_back(c);
-                    } else if (R.child_matches(t.hdr(n).pos, Tree<Pos>::edge_move(e), position)) {
+                    } else if (child_matches(t.hdr(n).pos, move_at(t, n, i), position)) {
                         return materialise(t, n, i);
                     }
                 }
@@ -931,20 +979,50 @@ class Worker {
         return -1;
     }
 
-    int32_t children_of(const Pos& pos) const { return R.status(pos) != 0 ? 0 : popcount128(R.legal_mask(pos)); }
+    // block size hint: every hex / tic-tac-toe node could have all cells free; a chess position has ~35 moves
+    int32_t typical_children() const { return kChess ? 48 : R.moves_num(); }
 
-    int32_t materialise(Tree<Pos>& t, int32_t parent, int32_t i) {
-        const uint8_t m = Tree<Pos>::edge_move(t.edge(parent)[i]);
+    Move move_at(TreeT& t, int32_t node, int32_t i) const {
+        if constexpr (kChess)
+            return t.move16(node)[i];
+        else
+            return TreeT::edge_move(t.edge(node)[i]);
+    }
+    bool child_matches(const Pos& parent, Move m, const Pos& target) const {
+        if constexpr (kChess)
+            return Rules::same(R.moved(parent, m), target);
+        else
+            return R.child_matches(parent, m, target);
+    }
+
+    // Appends the block of a node visited for the first time.  Its child count is the number of legal moves (0 for a
+    // finished position); for chess the moves themselves are generated here, once, in the order NNetwork::evaluate
+    // returns them, and kept in the block.
+    int32_t add_node(TreeT& t, const Pos& pos) {
+        if constexpr (kChess) {
+            Pos p = pos;
+            Move buf[256];
+            const int32_t n = R.children(p, buf);
+            const int32_t b = t.new_block(p, n);
+            if (n) std::memcpy(t.move16(b), buf, sizeof(Move) * n);
+            return b;
+        } else {
+            return t.new_block(pos, R.status(pos) != 0 ? 0 : popcount128(R.legal_mask(pos)));
+        }
+    }
+
+    int32_t materialise(TreeT& t, int32_t parent, int32_t i) {
+        const Move m = move_at(t, parent, i);
         const Pos child = R.moved(t.hdr(parent).pos, m);
-        const int32_t cb = t.new_block(child, children_of(child));
-        t.edge(parent)[i] = Tree<Pos>::pack_edge(cb, m);
+        const int32_t cb = add_node(t, child);
+        t.edge(parent)[i] = TreeT::pack_edge(cb, kChess ? 0 : static_cast<uint8_t>(m));
         return cb;
     }
 
     // mod.rs:303-333: copy the subtree; edges are re-inserted in iteration (newest-first) order => reversed
-    void remove_all_but_subtree(Slot& s, Tree<Pos>& t, int32_t sub_root) {
+    void remove_all_but_subtree(Slot& s, TreeT& t, int32_t sub_root) {
         if (t.root == sub_root) return;
-        Tree<Pos> nt;
+        TreeT nt;
         // The copy goes into a recycled buffer (every move of every game replaces a tree: fresh allocations of ~1 MB
         // each mean an mmap, a few hundred page faults and an munmap per move); room for the kept subtree plus one
         // more search.
@@ -953,28 +1031,33 @@ class Worker {
             pool_free_.pop_back();
             nt.pool.clear();
         }
-        nt.pool.reserve(t.pool.size() / 4 + (static_cast<size_t>(params_[s.cur].sim_num) + 8) * (Tree<Pos>::kHdrWords + 4 * static_cast<size_t>(R.moves_num())));
+        nt.pool.reserve(t.pool.size() / 4 + (static_cast<size_t>(params_[s.cur].sim_num) + 8) * TreeT::block_words(typical_children()));
         nt.root = nt.new_block(t.hdr(sub_root).pos, t.hdr(sub_root).count);
         std::vector<std::pair<int32_t, int32_t>> stack{{sub_root, nt.root}};
         while (!stack.empty()) {
             const auto [old_n, new_n] = stack.back();
             stack.pop_back();
-            if (!t.hdr(old_n).expanded) continue;
+            if (!t.hdr(old_n).expanded) {
+                // visited but never expanded: no edges yet, so nothing to reverse -- its moves keep their generated order
+                if constexpr (kChess) std::memcpy(nt.move16(new_n), t.move16(old_n), sizeof(Move) * t.hdr(old_n).count);
+                continue;
+            }
             const int32_t count = t.hdr(old_n).count;
             nt.hdr(new_n).expanded = 1;
             for (int32_t i = 0; i < count; ++i) {  // new insertion order = old iteration order (newest first)
                 const int32_t o = count - 1 - i;
+                if constexpr (kChess) nt.move16(new_n)[i] = t.move16(old_n)[o];
                 const uint32_t e = t.edge(old_n)[o];
                 nt.init_score(new_n)[i] = t.init_score(old_n)[o];
                 nt.score_w(new_n)[i] = t.score_w(old_n)[o];
                 nt.simulations_n(new_n)[i] = t.simulations_n(old_n)[o];
                 int32_t nc = -1;
-                const int32_t old_c = Tree<Pos>::edge_child(e);
+                const int32_t old_c = TreeT::edge_child(e);
                 if (old_c >= 0) {
                     nc = nt.new_block(t.hdr(old_c).pos, t.hdr(old_c).count);  // may move nt.pool: pointers are re-derived below
                     stack.push_back({old_c, nc});
                 }
-                nt.edge(new_n)[i] = Tree<Pos>::pack_edge(nc, Tree<Pos>::edge_move(e));
+                nt.edge(new_n)[i] = TreeT::pack_edge(nc, TreeT::edge_move(e));
             }
         }
         pool_free_.push_back(std::move(t.pool));
@@ -983,7 +1066,7 @@ class Worker {
     }
 
     // mod.rs:419-446
-    void add_dirichlet_noise(Slot& s, Tree<Pos>& t, int32_t node) {
+    void add_dirichlet_noise(Slot& s, TreeT& t, int32_t node) {
         const Params& P = params_[s.cur];
         if (P.noise_alpha == 0.0f || P.noise_eps == 0.0f) return;
         const int32_t count = t.hdr(node).count;
@@ -1005,8 +1088,15 @@ class Worker {
     // The rest of one develop_tree iteration once select has reached `node` (mod.rs:162-195), first half: terminal
     // leaves are backpropagated at once (returns true); otherwise the position to evaluate and its cache key are set up.
     bool at_leaf(Slot& s, int32_t node) {
-        Tree<Pos>& t = s.players[s.cur].tree;
+        TreeT& t = s.players[s.cur].tree;
         s.leaf = node;
+        if constexpr (kChess) {
+            if (detect_repetition(s, t)) {  // mod.rs:162,174-175: scored as a draw, the leaf stays as it is
+                c_.terminal += 1;
+                backpropagate(s, t, 0.0f);
+                return true;
+            }
+        }
         const Pos leaf_pos = t.hdr(node).pos;
         const int st = R.status(leaf_pos);
         if (st != 0) {
@@ -1018,14 +1108,39 @@ class Worker {
         return false;
     }
 
+    // MctsPlayer::detect_repetition (mod.rs:133-154): does any position occur REPETITION_LIMIT (3) times in the game's
+    // history followed by the positions along the selected path?  The history alone never does (the game would be over),
+    // so each path position is counted against what precedes it; equal positions lie an even number of plies apart and
+    // not beyond the last pawn move or capture (`rev`).
+    bool detect_repetition(const Slot& s, TreeT& t) const {
+        const int32_t H = static_cast<int32_t>(s.history.size());
+        for (int32_t j = 0; j < static_cast<int32_t>(s.path.size()); ++j) {
+            const Pos& p = t.hdr(s.path[j].child).pos;
+            int seen = 1;
+            for (int32_t d = 2; d <= p.rev; d += 2) {
+                const int32_t idx = H + j - d;
+                if (idx < 0) break;
+                const Pos& q = idx >= H ? t.hdr(s.path[idx - H].child).pos : s.history[idx];
+                if (Rules::same(p, q) && ++seen >= 3) return true;
+            }
+        }
+        return false;
+    }
+
     // NNetwork::evaluate (net/mod.rs:74-87), first part: flip to the side-to-move view, cache key, legal count
-    void prepare_leaf(Slot& s, Tree<Pos>& t, int32_t node) {
+    void prepare_leaf(Slot& s, TreeT& t, int32_t node) {
         const Pos& leaf_pos = t.hdr(node).pos;
         s.prepared_leaf = node;
         if (R.status(leaf_pos) != 0) return;
         s.leaf_flipped = leaf_pos.turn != 1;
-        s.leaf_eval_pos = s.leaf_flipped ? R.flipped_boards(leaf_pos) : leaf_pos;
-        s.leaf_key = R.key(s.leaf_eval_pos);
+        if constexpr (kChess) {
+            uint64_t q[4];  // the stored position already is the evaluator's view
+            R.key_planes(leaf_pos, q);
+            s.leaf_key = PosKey{static_cast<u128>(q[0]) | (static_cast<u128>(q[1]) << 64), static_cast<u128>(q[2]) | (static_cast<u128>(q[3]) << 64)};
+        } else {
+            s.leaf_eval_pos = s.leaf_flipped ? R.flipped_boards(leaf_pos) : leaf_pos;
+            s.leaf_key = R.key(s.leaf_eval_pos);
+        }
         s.leaf_n_legal = t.hdr(node).count;
         if (evals_[s.cur]->cache) evals_[s.cur]->cache->prefetch(s.leaf_key);
     }
@@ -1049,10 +1164,24 @@ class Worker {
         } else {
             s.wait_row = static_cast<uint32_t>(pb.keys.size());
             pb.keys.push_back(key);
-            u128 pl[3];
-            R.planes(s.leaf_eval_pos, pl);
-            for (int c = 0; c < 3; ++c)
-                for (int k = 0; k < abi_wpp_; ++k) pb.planes.push_back(static_cast<uint64_t>(pl[c] >> (64 * k)));
+            if constexpr (kChess) {
+                TreeT& t = s.players[s.cur].tree;
+                uint64_t pl[Rules::kPlanes];
+                R.planes(t.hdr(s.leaf).pos, pl);
+                pb.planes.insert(pb.planes.end(), pl, pl + Rules::kPlanes);
+                const size_t at = pb.legal.size();
+                pb.legal.resize(at + Rules::kLegalBytes, 0);
+                const Move* mv = t.move16(s.leaf);
+                for (int k = 0; k < n_legal; ++k) {
+                    const int idx = R.nn_idx(mv[k]);
+                    pb.legal[at + (idx >> 3)] |= static_cast<uint8_t>(1u << (idx & 7));
+                }
+            } else {
+                u128 pl[3];
+                R.planes(s.leaf_eval_pos, pl);
+                for (int c = 0; c < 3; ++c)
+                    for (int k = 0; k < abi_wpp_; ++k) pb.planes.push_back(static_cast<uint64_t>(pl[c] >> (64 * k)));
+            }
             pb.n_legal.push_back(static_cast<uint8_t>(n_legal));
         }
         pb.parked.push_back(si);
@@ -1062,10 +1191,20 @@ class Worker {
 
     // create_children + root noise + backpropagate for a leaf whose evaluation is known (mod.rs:180-194, :246-262)
     void deliver(Slot& s, const float* val) {
-        Tree<Pos>& t = s.players[s.cur].tree;
+        TreeT& t = s.players[s.cur].tree;
         const int32_t leaf = s.leaf;
+        const int32_t count = t.hdr(leaf).count;  // the legal moves: the block was sized when the node was first visited
+        if constexpr (kChess) {
+            // calc_moves_probs (net/mod.rs:106-119) gathers per legal move; the evaluator returns the probabilities compact in
+            // ascending nn index, so child i takes the entry at the rank of its nn index among the legal ones
+            const Move* mv = t.move16(leaf);
+            uint32_t order[256];
+            for (int32_t i = 0; i < count; ++i) order[i] = (static_cast<uint32_t>(R.nn_idx(mv[i])) << 8) | static_cast<uint32_t>(i);
+            std::sort(order, order + count);
+            float* init = t.init_score(leaf);
+            for (int32_t r = 0; r < count; ++r) init[order[r] & 0xFF] = val[r];
+        } else {
         const u128 legal = R.legal_mask(s.leaf_eval_pos);
-        const int32_t count = t.hdr(leaf).count;  // == popcount(legal): the block was sized when the node was first visited
         std::memcpy(t.init_score(leaf), val, sizeof(float) * count);
         uint32_t* ed = t.edge(leaf);
         int32_t k = 0;
@@ -1074,8 +1213,9 @@ class Worker {
             while (bits) {
                 const int m = 64 * half + __builtin_ctzll(bits);
                 bits &= bits - 1;
-                ed[k++] = Tree<Pos>::pack_edge(-1, static_cast<uint8_t>(s.leaf_flipped ? R.flip_move(m) : m));
+                ed[k++] = TreeT::pack_edge(-1, static_cast<uint8_t>(s.leaf_flipped ? R.flip_move(m) : m));
             }
+        }
         }
         t.hdr(leaf).expanded = 1;
         if (leaf == t.root) add_dirichlet_noise(s, t, leaf);
@@ -1085,7 +1225,7 @@ class Worker {
     }
 
     // mod.rs:270-281
-    void backpropagate(Slot& s, Tree<Pos>& t, float score) {
+    void backpropagate(Slot& s, TreeT& t, float score) {
         const uint8_t root_turn = t.hdr(t.root).pos.turn;  // the side to move alternates along the path in hex and tic-tac-toe
         for (size_t i = 0; i < s.path.size(); ++i) {
             const uint8_t turn = (i & 1) ? static_cast<uint8_t>(3 - root_turn) : root_turn;
@@ -1099,17 +1239,16 @@ class Worker {
     // the rest of calc_moves_probabilities + choose_move_from_probabilities + the game step (mod.rs:364-417,
     // self_play.rs:207-217)
     void end_search(Slot& s) {
-        Tree<Pos>& t = s.players[s.cur].tree;
+        TreeT& t = s.players[s.cur].tree;
         const Params& P = params_[s.cur];
-        const typename Tree<Pos>::Header& root = t.hdr(t.root);
-        std::vector<std::pair<uint8_t, float>> probs;
+        const typename TreeT::Header& root = t.hdr(t.root);
+        std::vector<std::pair<Move, float>> probs;
         probs.reserve(root.count);
         uint32_t total = 0;
         const int32_t* rn = t.simulations_n(t.root);
-        const uint32_t* re = t.edge(t.root);
         for (int32_t i = 0; i < root.count; ++i) total += static_cast<uint32_t>(rn[i]);
         for (int32_t i = root.count - 1; i >= 0; --i)  // edges() order
-            probs.emplace_back(Tree<Pos>::edge_move(re[i]), static_cast<float>(rn[i]) / static_cast<float>(total));
+            probs.emplace_back(move_at(t, t.root, i), static_cast<float>(rn[i]) / static_cast<float>(total));
         const double secs = std::chrono::duration<double>(Clock::now() - s.search_t0).count();
         {
             std::lock_guard<std::mutex> g(sh_.mu);  // RunningAverage(0.99), util/metric.rs:1-20
@@ -1146,13 +1285,28 @@ class Worker {
                 }
             }
         }
-        const uint8_t mv = probs[chosen].first;
-        s.rec.moves.push_back(mv);
+        const Move mv = probs[chosen].first;
         s.pending_entries.emplace_back(s.history.back(), std::move(probs));
-        s.history.push_back(R.moved(s.history.back(), mv));
+        if constexpr (kChess) {
+            s.rec.moves.push_back(Rules::real_move(s.history.back(), mv));
+            Pos np = R.moved(s.history.back(), mv);
+            Move buf[256];
+            R.children(np, buf);  // settles status()
+            // ChessGame::play_single_turn (chess/core.rs:441-449): the third occurrence of a position ends the game
+            int seen = 1;
+            const int32_t H = static_cast<int32_t>(s.history.size());
+            for (int32_t d = 2; d <= np.rev && d <= H; d += 2)
+                if (Rules::same(np, s.history[H - d])) ++seen;
+            if (seen >= 3) s.repetition = true;
+            s.history.push_back(np);
+        } else {
+            s.rec.moves.push_back(mv);
+            s.history.push_back(R.moved(s.history.back(), mv));
+        }
     }
 
     // ---------------------------------------------------------------- evaluator batch
+    static const uint8_t* legal_ptr(const Pending& pb) { return kChess ? pb.legal.data() : nullptr; }
     // Ship group `gr`'s batch for evaluator `e`: asynchronously when the evaluator supports it (collected at the
     // group's next turn), else evaluated and delivered on the spot.
     void send(Group& gr, int e) {
@@ -1162,17 +1316,17 @@ class Worker {
         if (ev.async_handle && !(n == 1 && ev.leaf_handle)) {
             const auto t0 = Clock::now();
             int32_t ticket = -1;
-            int rc = cattus_b200_eval_batch_submit(ev.async_handle, pb.planes.data(), nullptr, n, 0, &ticket);
+            int rc = cattus_b200_eval_batch_submit(ev.async_handle, pb.planes.data(), legal_ptr(pb), n, 0, &ticket);
             while (rc == 0 && ticket < 0) {
                 // Every stream is busy.  Take back our own oldest batch (its results go to its games right away) and try
                 // again; a worker only ever BLOCKS for a stream while holding none, so workers cannot deadlock each other.
                 if (inflight_.empty()) {
-                    rc = cattus_b200_eval_batch_submit(ev.async_handle, pb.planes.data(), nullptr, n, 1, &ticket);
+                    rc = cattus_b200_eval_batch_submit(ev.async_handle, pb.planes.data(), legal_ptr(pb), n, 1, &ticket);
                     break;
                 }
                 const std::pair<uint32_t, int> oldest = inflight_.front();
                 collect(groups_[oldest.first], oldest.second);
-                rc = cattus_b200_eval_batch_submit(ev.async_handle, pb.planes.data(), nullptr, n, 0, &ticket);
+                rc = cattus_b200_eval_batch_submit(ev.async_handle, pb.planes.data(), legal_ptr(pb), n, 0, &ticket);
             }
             eval_wait_ += std::chrono::duration<double>(Clock::now() - t0).count();
             if (rc != 0) throw SpError{rc, std::string("evaluator failed: ") + cattus_b200_last_error()};
@@ -1190,11 +1344,11 @@ class Worker {
         int rc;
         if (n == 1 && ev.leaf_handle) {
             uint32_t np = 0;
-            rc = cattus_b200_eval(ev.leaf_handle, pb.planes.data(), nullptr, probs_.data(), static_cast<uint32_t>(total), &np, values_.data());
+            rc = cattus_b200_eval(ev.leaf_handle, pb.planes.data(), legal_ptr(pb), probs_.data(), static_cast<uint32_t>(total), &np, values_.data());
             offsets_[0] = 0;
             offsets_[1] = np;
         } else {
-            rc = ev.fn(ev.ctx, pb.planes.data(), nullptr, n, probs_.data(), total, offsets_.data(), values_.data());
+            rc = ev.fn(ev.ctx, pb.planes.data(), legal_ptr(pb), n, probs_.data(), total, offsets_.data(), values_.data());
         }
         eval_wait_ += std::chrono::duration<double>(Clock::now() - t0).count();
         if (rc != 0) throw SpError{rc, std::string("evaluator failed: ") + cattus_b200_last_error()};
@@ -1278,7 +1432,7 @@ class Worker {
     double eval_wait_ = 0.0;
     std::vector<double> noise_;
     std::vector<float> weights_, probs_, values_, val_, rows_;
-    float sel_[128];  // selection values of one node's children (<= 121 moves)
+    float sel_[256];  // selection values of one node's children (<= 121 cells, <= 218 chess moves)
     static constexpr uint32_t kMaxRing = 32;
     uint32_t ring_size_ = 8;  // games advanced interleaved (memory-level parallelism of the tree walks); CATTUS_B200_SELFPLAY_RING
     Counters c_;
@@ -1343,11 +1497,14 @@ static int selfplay_impl(sp::Evaluator& e1, sp::Evaluator* e2_or_null, const cat
         sp::Params params[2] = {p, p};
         if (cfg->game == CATTUS_B200_GAME_HEX) {
             if (cfg->board_size < 2 || cfg->board_size > 11) throw sp::SpError{CATTUS_B200_EINVAL, "hex board_size must be 2..11"};
-        } else if (cfg->game != CATTUS_B200_GAME_TTT) {
-            throw sp::SpError{CATTUS_B200_EINVAL, "the self-play driver covers hex and tictactoe (chess move generation is the third-party crate `chess`)"};
+        } else if (cfg->game != CATTUS_B200_GAME_TTT && cfg->game != CATTUS_B200_GAME_CHESS) {
+            throw sp::SpError{CATTUS_B200_EINVAL, "unknown game"};
         }
         if (cfg->cache_size) {
-            const int moves_num = cfg->game == CATTUS_B200_GAME_TTT ? 9 : static_cast<int>(cfg->board_size * cfg->board_size);
+            // room per entry: the most legal moves a position can have, plus the value
+            const int moves_num = cfg->game == CATTUS_B200_GAME_TTT     ? 9
+                                  : cfg->game == CATTUS_B200_GAME_CHESS ? sp::ChessRules::kMaxMoves
+                                                                        : static_cast<int>(cfg->board_size * cfg->board_size);
             e1.cache.reset(new sp::Cache(cfg->cache_size, moves_num));
             if (e2_or_null) e2_or_null->cache.reset(new sp::Cache(cfg->cache_size, moves_num));
         }
@@ -1366,6 +1523,9 @@ static int selfplay_impl(sp::Evaluator& e1, sp::Evaluator* e2_or_null, const cat
                 sp::HexRulesT<sp::u128> rules(static_cast<int>(cfg->board_size));
                 run_games(rules, *cfg, params, evals, sh);
             }
+        } else if (cfg->game == CATTUS_B200_GAME_CHESS) {
+            sp::ChessRules rules;
+            run_games(rules, *cfg, params, evals, sh);
         } else {
             sp::TttRules rules;
             run_games(rules, *cfg, params, evals, sh);
@@ -1469,7 +1629,18 @@ int cattus_b200_selfplay_game_moves(const cattus_b200_selfplay_t* r, uint32_t k,
     if (!r || !moves_out || k >= r->records.size()) return CATTUS_B200_ERANGE;
     const auto& m = r->records[k].moves;
     if (cap < m.size()) return CATTUS_B200_ERANGE;
-    std::memcpy(moves_out, m.data(), m.size());
+    for (size_t i = 0; i < m.size(); ++i) {
+        if (m[i] > 0xFF) return CATTUS_B200_ERANGE;  // chess moves need cattus_b200_selfplay_game_moves16
+        moves_out[i] = static_cast<uint8_t>(m[i]);
+    }
+    return CATTUS_B200_OK;
+}
+
+int cattus_b200_selfplay_game_moves16(const cattus_b200_selfplay_t* r, uint32_t k, uint16_t* moves_out, uint32_t cap) {
+    if (!r || !moves_out || k >= r->records.size()) return CATTUS_B200_ERANGE;
+    const auto& m = r->records[k].moves;
+    if (cap < m.size()) return CATTUS_B200_ERANGE;
+    std::memcpy(moves_out, m.data(), m.size() * sizeof(uint16_t));
     return CATTUS_B200_OK;
 }
 

@@ -29,20 +29,22 @@ from ._lib import SelfPlayCfg, SelfPlaySummary
 
 
 def parse_game(game: str) -> Tuple[int, int]:
-    """'hex5' -> (GAME_HEX, 5); 'ttt' / 'tictactoe' -> (GAME_TTT, 3)."""
+    """'hex5' -> (GAME_HEX, 5); 'ttt' / 'tictactoe' -> (GAME_TTT, 3); 'chess' -> (GAME_CHESS, 8)."""
     if game in ("ttt", "tictactoe"):
         return _lib.GAME_TTT, 3
+    if game == "chess":
+        return _lib.GAME_CHESS, 8
     m = re.fullmatch(r"hex(\d+)?", game)
     if m:
         return _lib.GAME_HEX, int(m.group(1) or 11)
-    raise ValueError(f"the self-play driver covers hex and tictactoe, not {game!r}")
+    raise ValueError(f"unknown game {game!r} (hex<S>, ttt, chess)")
 
 
 @dataclass
 class GameRecord:
     game_idx: int
     winner: Optional[int]  # None, 1, 2
-    moves: List[int]
+    moves: List[int]       # hex / ttt: cell index; chess: from | to << 6 | promotion << 12 (cattus_b200_chess.h)
     entries: List[bytes]   # exact .traindata bytes per position
     entry_dirs: List[int]  # 1 -> out_dir1, 2 -> out_dir2
 
@@ -106,17 +108,22 @@ class SelfPlayRunner:
 
     def run_with(self, eval1: Callable, eval2: Optional[Callable], games_num: int, out_dir1=None, out_dir2=None, *,
                  keep_records: bool = False, first_game: int = 0, game_stride: int = 1):
-        """eval(planes u64 [n, words], n) -> (list of n probability arrays over the legal moves ascending, values[n])."""
+        """eval(planes u64 [n, words], n) -> (list of n probability arrays over the legal moves ascending, values[n]);
+        for chess eval(planes, n, legal u8 [n, 235]) with the legal-move bitmaps over the nn indices."""
         c = self._fill(games_num, out_dir1, out_dir2, keep_records, first_game, game_stride)
-        _, s = parse_game(self.game)
-        words = 3 * ((s * s + 63) // 64)
+        g, s = parse_game(self.game)
+        chess = g == _lib.GAME_CHESS
+        words = 18 if chess else 3 * ((s * s + 63) // 64)
         errors: list = []
 
         def thunk_for(fn):
-            def thunk(_ctx, planes, _legal, n, probs_out, probs_cap, prob_offsets, values_out):
+            def thunk(_ctx, planes, legal, n, probs_out, probs_cap, prob_offsets, values_out):
                 try:
                     w = np.ctypeslib.as_array(planes, shape=(n, words)).copy()
-                    probs, values = fn(w, n)
+                    if chess:
+                        probs, values = fn(w, n, np.ctypeslib.as_array(legal, shape=(n, 235)).copy())
+                    else:
+                        probs, values = fn(w, n)
                     off = 0
                     for i in range(n):
                         p = np.asarray(probs[i], dtype=np.float32)
@@ -167,8 +174,8 @@ class SelfPlayRunner:
                 for k in range(n.value):
                     gi, w, nm = C.c_uint32(), C.c_uint32(), C.c_uint32()
                     _check(lib, lib.cattus_b200_selfplay_game_info(h, k, C.byref(gi), C.byref(w), C.byref(nm)))
-                    mv = (C.c_uint8 * max(1, nm.value))()
-                    _check(lib, lib.cattus_b200_selfplay_game_moves(h, k, mv, nm.value))
+                    mv = (C.c_uint16 * max(1, nm.value))()
+                    _check(lib, lib.cattus_b200_selfplay_game_moves16(h, k, mv, nm.value))
                     entries, dirs = [], []
                     for pi in range(nm.value):
                         nb, od = C.c_size_t(), C.c_uint32()

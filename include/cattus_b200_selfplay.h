@@ -4,8 +4,10 @@
  * TicTacToe rules it needs (engine/src/hex/core.rs:112-335, engine/src/ttt/core.rs:101-246), `NNetwork::evaluate`'s
  * flip + `ValueFuncCache` (engine/src/net/mod.rs:74-87,158-182; engine/src/mcts/cache.rs:31-75), the self-play game
  * loop (training/self-play/src/self_play.rs:94-276) and the `.traindata` writers (self_play.rs:33-61,
- * serialize/hex.rs:16-28, serialize/ttt.rs:17-22), restated in C++ so that "self-play MCTS sims/s" can be measured
- * without a Rust toolchain.  Chess is not driven from here (its move generator is the third-party crate `chess`).
+ * serialize/hex.rs:16-28, serialize/ttt.rs:17-22, serialize/chess.rs:18-57), restated in C++ so that "self-play MCTS
+ * sims/s" can be measured without a Rust toolchain.  Chess (engine/src/chess/core.rs, threefold repetition through
+ * MctsPlayer::detect_repetition, mcts/mod.rs:133-154) runs on the rules of cattus_b200/csrc/chess_rules.hpp, a
+ * restatement of the third-party crate `chess` the reference uses (see include/cattus_b200_chess.h).
  *
  * What differs from the reference, on purpose: a worker thread there owns ONE tree with one leaf in flight, so the
  * evaluator never sees more than `threads` (<= 16) positions at once.  Here each worker thread advances
@@ -40,8 +42,8 @@ typedef int (*cattus_b200_eval_fn)(void* ctx, const uint64_t* planes, const uint
  * command line (:14-31). */
 typedef struct cattus_b200_selfplay_cfg {
     uint32_t struct_size;
-    uint32_t game;       /* CATTUS_B200_GAME_HEX or _TTT */
-    uint32_t board_size; /* hex: 2..11; ttt: 3 */
+    uint32_t game;       /* CATTUS_B200_GAME_HEX, _TTT or _CHESS */
+    uint32_t board_size; /* hex: 2..11; ttt: 3; chess: 8 */
     /* mcts.* */
     uint32_t sim_num;
     float explore_factor;
@@ -103,8 +105,11 @@ int cattus_b200_selfplay_summary_get(const cattus_b200_selfplay_t* r, cattus_b20
 int cattus_b200_selfplay_game_count(const cattus_b200_selfplay_t* r, uint32_t* n);
 int cattus_b200_selfplay_game_info(const cattus_b200_selfplay_t* r, uint32_t k, uint32_t* game_idx, uint32_t* winner,
                                    uint32_t* n_moves);
-/* moves_out[n_moves]: the move indices (row * S + col) played. */
+/* moves_out[n_moves]: the move indices (row * S + col) played (hex, tic-tac-toe). */
 int cattus_b200_selfplay_game_moves(const cattus_b200_selfplay_t* r, uint32_t k, uint8_t* moves_out, uint32_t cap);
+/* The same for any game; chess moves are from | to << 6 | promotion << 12 in real board coordinates
+ * (include/cattus_b200_chess.h). */
+int cattus_b200_selfplay_game_moves16(const cattus_b200_selfplay_t* r, uint32_t k, uint16_t* moves_out, uint32_t cap);
 /* The exact bytes of `{game_idx:08}_{pos_idx:03}.traindata` and which out_dir (1 or 2) it belongs to. */
 int cattus_b200_selfplay_entry(const cattus_b200_selfplay_t* r, uint32_t k, uint32_t pos_idx, uint8_t* bytes_out,
                                size_t cap, size_t* n_bytes, uint32_t* out_dir);

@@ -425,6 +425,8 @@ class MctsPlayer:
         self.rng = rng
         self.root: Optional[_Node] = None
         self.sims_done = 0
+        self.terminal_leaves = 0   # simulations that ended on a finished position or a repetition (no evaluation)
+        self.repetition_hits = 0
 
     # -- mod.rs:233-244
     def _heuristic(self, e: _Edge, parent_simcount: int) -> np.float32:
@@ -448,15 +450,34 @@ class MctsPlayer:
             path.append((node, best))
             node = best.target
 
+    # -- mod.rs:133-154
+    @staticmethod
+    def _detect_repetition(pos_history: Sequence, path) -> bool:
+        limit = getattr(type(pos_history[-1]), "REPETITION_LIMIT", None)
+        if limit is None or limit <= 1:
+            return False
+        counts: dict = {}
+        for pos in list(pos_history) + [e.target.position for _, e in path]:
+            counts[pos] = counts.get(pos, 0) + 1
+            if counts[pos] >= limit:
+                return True
+        return False
+
     # -- mod.rs:156-196
-    def _develop_tree(self) -> None:
+    def _develop_tree(self, pos_history: Sequence) -> None:
         assert self.p.sim_num > 1
         for _ in range(self.p.sim_num):
             path = self._select()
+            repetition_reached = self._detect_repetition(pos_history, path)
             leaf = path[-1][1].target if path else self.root
-            st, winner = leaf.position.status()
-            if st == "finished":
+            st, winner = (None, None) if repetition_reached else leaf.position.status()
+            if repetition_reached:
+                ev = f32(0.0)
+                self.terminal_leaves += 1
+                self.repetition_hits += 1
+            elif st == "finished":
                 ev = f32(to_signed_one(winner))
+                self.terminal_leaves += 1
             else:
                 per_move, ev = self.evaluator.evaluate(leaf.position)
                 for m, p in per_move:  # create_children, mod.rs:246-262
@@ -523,7 +544,7 @@ class MctsPlayer:
         if self.root is None:
             self.root = _Node(position)
         assert self.root.position == position
-        self._develop_tree()
+        self._develop_tree(pos_history)
         ms = [(e.m, e.n) for e in _edges(self.root)]
         total = sum(n for _, n in ms)
         return [(m, f32(f32(n) / f32(total))) for m, n in ms]
@@ -577,6 +598,8 @@ class GameRecord:
     moves: List[int]
     entries: List[Tuple[object, List[Tuple[int, np.float32]]]]  # (position before the move, MCTS probabilities)
     sims: int
+    terminal_leaves: int = 0
+    repetition_hits: int = 0
 
 
 def play_game(game_idx: int, new_position: Callable[[], object], params1: MctsParams, params2: MctsParams, eval1: Evaluator,
@@ -587,8 +610,13 @@ def play_game(game_idx: int, new_position: Callable[[], object], params1: MctsPa
     history = [new_position()]
     entries, moves = [], []
     switch = game_idx % 2 == 1
+    # ChessGame (chess/core.rs:402-451): a position seen REPETITION_LIMIT times ends the game as a draw
+    limit = getattr(type(history[0]), "REPETITION_LIMIT", None)
+    seen = {history[0]: 1} if limit else None
     while True:
         st, winner = history[-1].status()
+        if seen is not None and seen[history[-1]] >= limit:
+            st, winner = "finished", None
         if st == "finished":
             break
         who = history[-1].turn
@@ -600,7 +628,10 @@ def play_game(game_idx: int, new_position: Callable[[], object], params1: MctsPa
         entries.append((history[-1], probs))
         moves.append(mv)
         history.append(history[-1].moved_position(mv))
-    return GameRecord(game_idx, winner, moves, entries, player1.sims_done + player2.sims_done)
+        if seen is not None:
+            seen[history[-1]] = seen.get(history[-1], 0) + 1
+    return GameRecord(game_idx, winner, moves, entries, player1.sims_done + player2.sims_done,
+                      player1.terminal_leaves + player2.terminal_leaves, player1.repetition_hits + player2.repetition_hits)
 
 
 def data_entry_bytes(pos, probs, winner: Optional[int]) -> bytes:
@@ -609,6 +640,10 @@ def data_entry_bytes(pos, probs, winner: Optional[int]) -> bytes:
     dense f32 probabilities with -1 for illegal moves, winner as i8."""
     import struct
 
+    from . import chess as _chess
+
+    if isinstance(pos, _chess.ChessPosition):
+        return _chess.serialize_entry(pos, probs, winner)
     w = f32(to_signed_one(winner))
     flipped = pos.turn != P1
     if flipped:

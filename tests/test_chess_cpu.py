@@ -1,0 +1,283 @@
+"""CPU tests of the chess side of the self-play driver: the rules (csrc/chess_rules.hpp through
+include/cattus_b200_chess.h) against the published perft counts and against the independent mailbox restatement in
+oracle/chess.py, and whole chess self-play games (csrc/selfplay.cpp) against oracle/mcts.py.
+
+The reference's move generator is the crate `chess` 3.2.0, which is not in the tree: the legal move SET is pinned by
+perft; the ORDER of `MoveGen::new_legal` is restated twice (bitboards in C++, sort key over a mailbox board in Python)
+and the two must agree on every position visited below.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import random
+
+import numpy as np
+import pytest
+
+from cattus_b200 import _lib
+from cattus_b200.selfplay import SelfPlayRunner
+from oracle import chess as oc
+from oracle import games as og
+from oracle import mcts as om
+
+START = "rnbqkbnr/pppppppp/8/8/8/8/PPPPPPPP/RNBQKBNR w KQkq -"
+KIWIPETE = "r3k2r/p1ppqpb1/bn2pnp1/3PN3/1p2P3/2N2Q1p/PPPBBPPP/R3K2R w KQkq -"
+# the standard move-generator test positions with their published node counts
+PERFT = [
+    (START, [20, 400, 8902, 197281, 4865609]),
+    (KIWIPETE, [48, 2039, 97862, 4085603]),
+    ("8/2p5/3p4/KP5r/1R3p1k/8/4P1P1/8 w - -", [14, 191, 2812, 43238, 674624]),
+    ("r3k2r/Pppp1ppp/1b3nbN/nP6/BBP1P3/q4N2/Pp1P2PP/R2Q1RK1 w kq - 0 1", [6, 264, 9467, 422333]),
+    ("r2q1rk1/pP1p2pp/Q4n2/bbp1p3/Np6/1B3NBn/pPPP1PPP/R3K2R b KQ - 0 1", [6, 264, 9467, 422333]),
+    ("rnbq1k1r/pp1Pbppp/2p5/8/2B5/8/PPP1NnPP/RNBQK2R w KQ - 1 8", [44, 1486, 62379, 2103487]),
+    ("r4rk1/1pp1qppp/p1np1n2/2b1p1B1/2B1P1b1/P1NP1N2/1PP1QPPP/R4RK1 w - - 0 10", [46, 2079, 89890, 3894594]),
+]
+
+
+def chess_info(fen: str, moves=()):
+    lib = _lib.load()
+    info = _lib.ChessInfo()
+    info.struct_size = C.sizeof(_lib.ChessInfo)
+    arr = (C.c_uint16 * max(1, len(moves)))(*moves)
+    rc = lib.cattus_b200_chess_position(fen.encode(), arr, len(moves), C.byref(info))
+    assert rc == 0, lib.cattus_b200_chess_last_error()
+    return info
+
+
+@pytest.mark.parametrize("fen,counts", PERFT)
+def test_perft_matches_published_counts(fen, counts):
+    lib = _lib.load()
+    for depth, want in enumerate(counts, 1):
+        n = C.c_uint64()
+        assert lib.cattus_b200_chess_perft(fen.encode(), depth, C.byref(n)) == 0
+        assert n.value == want, (fen, depth)
+    pos = oc.ChessPosition.from_fen(fen)  # the oracle, as deep as pure Python goes in a moment
+    for depth, want in enumerate(counts[:2], 1):
+        assert oc.perft(pos, depth) == want
+
+
+def test_nn_index_table_matches_oracle_table():
+    lib = _lib.load()
+    table = (C.c_uint16 * (64 * 64 + 88))()
+    assert lib.cattus_b200_chess_nn_table(table, len(table)) == 0
+    assert np.array_equal(np.frombuffer(table, dtype=np.uint16), og.chess_move_to_nn_index_table())
+    assert lib.cattus_b200_chess_nn_table(table, 10) != 0
+
+
+def test_fixture_planes():
+    """planes of the reference's chess fixtures (training/tests/test_net_output.py:199-203)."""
+    info = chess_info(START)
+    assert list(info.planes)[:12] == [0xFF00, 0x42, 0x24, 0x81, 0x08, 0x10, 0x00FF000000000000, 0x4200000000000000, 0x2400000000000000,
+                                      0x8100000000000000, 0x0800000000000000, 0x1000000000000000]
+    assert list(info.planes)[12:] == [og.U64_ALL] * 4 + [0, og.U64_ALL]
+    assert info.n_legal == 20 and info.turn == 1 and info.status == 0
+    info = chess_info("4k2r/6r1/8/8/8/8/3R4/R3K3 w Qk -")
+    pl = list(info.planes)
+    assert pl[3] == 0x801 and pl[5] == 0x10 and pl[9] == 0x8040000000000000 and pl[11] == 0x1000000000000000
+    assert pl[12:16] == [0, og.U64_ALL, og.U64_ALL, 0] and pl[16] == 0
+    # en passant: recorded only when a pawn of the side to move stands beside the pawn that just advanced
+    assert chess_info("rnbqkbnr/pppp1ppp/8/8/4pP2/8/PPPPP1PP/RNBQKBNR b KQkq f3").planes[16] == 1 << (32 + 5)  # black's view: rank mirrored
+    assert chess_info("rnbqkbnr/pppppppp/8/8/4P3/8/PPPP1PPP/RNBQKBNR b KQkq e3").planes[16] == 0
+    for bad in ("", "8/8/8/8/8/8/8/8 w - -", "rnbqkbnr/pppppppp/8/8/8/8/PPPPPPPP/RNBQKBN w KQkq -", "4k3/8/8/8/8/8/8/4K3 w K -"):
+        info = _lib.ChessInfo()
+        info.struct_size = C.sizeof(_lib.ChessInfo)
+        assert _lib.load().cattus_b200_chess_position(bad.encode(), None, 0, C.byref(info)) != 0
+
+
+def _eval_order(p: oc.ChessPosition):
+    """legal_moves() as NNetwork::evaluate hands them to the tree (net/mod.rs:74-87, :166-182) and the evaluated view."""
+    if p.turn == oc.P1:
+        return p.legal_moves(), p
+    f = p.flipped()
+    return [oc.ChessPosition.flip_move(m) for m in f.legal_moves()], f
+
+
+def test_rules_match_oracle_on_random_playouts():
+    rng = random.Random(11)
+    fens = [f for f, _ in PERFT]
+    ends = {}
+    for g in range(24):
+        fen = fens[g % len(fens)]
+        p = oc.ChessPosition.from_fen(fen)
+        moves = []
+        for _ply in range(220):
+            info = chess_info(fen, moves)
+            mv, view = _eval_order(p)
+            st, w = p.status()
+            want = 0 if st == "ongoing" else (3 if w is None else w)
+            assert (info.turn, info.status, info.fifty_rule_count, info.in_check) == (p.turn, want, p.fifty, int(p.in_check()))
+            assert list(info.planes) == view.planes()
+            assert view.flipped() == (p if p.turn != oc.P1 else p.flipped())
+            if want:
+                assert info.n_legal == 0
+                ends[want] = ends.get(want, 0) + 1
+                break
+            assert [oc.move_from_u16(info.moves[i]) for i in range(info.n_legal)] == mv
+            nn = [oc.ChessPosition.to_nn_idx(m if p.turn == oc.P1 else oc.ChessPosition.flip_move(m)) for m in mv]
+            assert [info.nn_index[i] for i in range(info.n_legal)] == nn
+            assert bytes(info.legal_bitmap) == og.bitmap_from_legal(nn, og.CHESS_MOVES_NUM).tobytes()
+            m = rng.choice(mv)
+            moves.append(oc.move_to_u16(m))
+            p = p.moved_position(m)
+    assert ends  # some playouts reach mate, stalemate or the fifty-move draw
+    bad = _lib.ChessInfo()
+    bad.struct_size = C.sizeof(_lib.ChessInfo)
+    illegal = (C.c_uint16 * 1)(oc.move_to_u16((12, 36, None)))  # e2e5
+    assert _lib.load().cattus_b200_chess_position(START.encode(), illegal, 1, C.byref(bad)) != 0
+
+
+def test_oracle_flip_and_fifty_rule():
+    """flip_rand / fifty-move bookkeeping (chess/core.rs:607-730 tests the same properties with a random player)."""
+    rng = random.Random(3)
+    p = oc.ChessPosition.new()
+    for _ in range(120):
+        if p.is_finished():
+            break
+        f = p.flipped()
+        assert f.flipped() == p and f.turn == 3 - p.turn and f.fifty == p.fifty
+        assert {oc.ChessPosition.flip_move(m) for m in f.legal_moves()} == set(p.legal_moves())
+        p = p.moved_position(rng.choice(p.legal_moves()))
+    # knights out and back: no pawn move or capture, so only white's moves count (core.rs:334-343)
+    p = oc.ChessPosition.new()
+    for lan in ["g1f3", "g8f6", "f3g1", "f6g8"] * 3:
+        m = (og.chess_move_to_idx(lan) // 64, og.chess_move_to_idx(lan) % 64, None)
+        p = p.moved_position(m)
+    assert p.fifty == 6 and p == oc.ChessPosition.new()  # equality ignores the counter (core.rs:292-309)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# whole games: the C++ driver against oracle/mcts.py, both driven by the same deterministic "network"
+# --------------------------------------------------------------------------------------------------------------
+def _mix(x: int) -> int:
+    x &= (1 << 64) - 1
+    x ^= x >> 33
+    x = (x * 0xFF51AFD7ED558CCD) & ((1 << 64) - 1)
+    x ^= x >> 33
+    return x
+
+
+def chess_fake_net(kind: str, salt: int = 0):
+    """net(planes[18], legal nn indices ascending) -> (probabilities in that order, value)."""
+
+    def net(planes, legal):
+        if kind == "uniform":
+            return np.full(len(legal), np.float32(1.0) / np.float32(len(legal)), dtype=np.float32), np.float32(0.0)
+        h = salt
+        for w in planes[:17]:
+            h = _mix(h * 0x9E3779B97F4A7C15 + int(w) + 1)
+        logits = np.array([((_mix(h + 977 * i) % 1000) / 250.0) - 2.0 for i in legal], dtype=np.float32)
+        e = np.exp(logits - logits.max()).astype(np.float32)
+        p = (e / e.sum(dtype=np.float32)).astype(np.float32)
+        v = np.float32(((h >> 7) % 2001) / 1000.0 - 1.0)
+        if kind == "coarse":
+            v = np.float32(round(float(v) * 2) / 2)
+        return p, v
+
+    return net
+
+
+def chess_cb(net):
+    def cb(words: np.ndarray, n: int, legal: np.ndarray):
+        probs, values = [], []
+        for i in range(n):
+            idx = og.legal_from_bitmap(legal[i], og.CHESS_MOVES_NUM)
+            p, v = net([int(w) for w in words[i]], idx)
+            probs.append(p)
+            values.append(v)
+        return probs, values
+
+    return cb
+
+
+def chess_oracle_fn(net):
+    def fn(pos: oc.ChessPosition):
+        moves = pos.legal_moves()
+        nn = [oc.ChessPosition.to_nn_idx(m) for m in moves]
+        order = sorted(nn)
+        p, v = net(pos.planes(), order)
+        rank = {idx: k for k, idx in enumerate(order)}
+        return [p[rank[i]] for i in nn], v  # calc_moves_probs gathers per legal move (net/mod.rs:106-119)
+
+    return fn
+
+
+def _params(cfg):
+    mc = cfg["mcts"]
+    return om.MctsParams(sim_num=mc["sim_num"], explore_factor=mc.get("explore_factor", math.sqrt(2.0)),
+                         temperature=om.TemperaturePolicy.from_config(mc.get("temperature_policy", [[0, 1.0]])),
+                         prior_noise_alpha=mc.get("prior_noise_alpha", 0.0), prior_noise_epsilon=mc.get("prior_noise_epsilon", 0.0))
+
+
+def check_chess_against_oracle(cfg: dict, kind: str, games_num: int, kind2=None):
+    net1 = chess_fake_net(kind)
+    net2 = chess_fake_net(kind2, salt=99) if kind2 else None
+    summary, records = SelfPlayRunner("chess", cfg).run_with(chess_cb(net1), chess_cb(net2) if net2 else None, games_num, keep_records=True)
+    mc = cfg["mcts"]
+    e1 = om.Evaluator(chess_oracle_fn(net1), om.ValueFuncCache(mc["cache_size"]) if mc.get("cache_size") else None)
+    e2 = e1 if net2 is None else om.Evaluator(chess_oracle_fn(net2), om.ValueFuncCache(mc["cache_size"]) if mc.get("cache_size") else None)
+    params = _params(cfg)
+    ref = [om.play_game(g, oc.ChessPosition.new, params, params, e1, e2, cfg.get("seed", 0)) for g in range(games_num)]
+    how = []
+    for rec, o in zip(records, ref):
+        assert rec.game_idx == o.game_idx
+        assert rec.moves == [oc.move_to_u16(m) for m in o.moves], (rec.game_idx, len(rec.moves), len(o.moves))
+        assert rec.winner == o.winner
+        assert len(rec.entries) == len(o.entries)
+        for k, (pos, probs) in enumerate(o.entries):
+            assert rec.entries[k] == om.data_entry_bytes(pos, probs, o.winner), (rec.game_idx, k)
+            assert len(rec.entries[k]) == 18 * 8 + 235 + 225 * 4 + 1
+            assert rec.entry_dirs[k] == om.data_entry_dir(pos.turn, o.game_idx)
+        last = oc.ChessPosition.new()
+        for m in o.moves:
+            last = last.moved_position(m)
+        st, _ = last.status()
+        how.append("repetition" if st == "ongoing" else ("fifty" if last.legal_moves() else ("mate" if last.in_check() else "stalemate")))
+    m = summary["metrics"]
+    assert m["selfplay.simulations"] == sum(o.sims for o in ref) == m["selfplay.searches"] * cfg["mcts"]["sim_num"]
+    assert summary["player1_wins"] + summary["player2_wins"] + summary["draws"] == games_num
+    assert m["selfplay.terminal_leaves"] == sum(o.terminal_leaves for o in ref)
+    summary["oracle.repetition_hits"] = sum(o.repetition_hits for o in ref)
+    return summary, records, how
+
+
+CHESS_BASE = {"mcts": {"sim_num": 12, "explore_factor": 1.41421, "temperature_policy": [[9999, 0.0]], "prior_noise_alpha": 0.0,
+                       "prior_noise_epsilon": 0.0, "cache_size": 0}, "threads": 1, "games_per_thread": 1, "seed": 5}
+
+
+def chess_cfg(**kw):
+    c = {"mcts": dict(CHESS_BASE["mcts"]), "threads": 1, "games_per_thread": 1, "seed": 5}
+    for k, v in kw.items():
+        if k in c["mcts"]:
+            c["mcts"][k] = v
+        else:
+            c[k] = v
+    return c
+
+
+def test_chess_games_match_oracle_and_end_by_repetition():
+    # a deterministic net at temperature 0 shuffles pieces: these games end by threefold repetition, which exercises
+    # MctsPlayer::detect_repetition inside the searches on the way
+    s, _, how = check_chess_against_oracle(chess_cfg(), "hash", games_num=2)
+    assert "repetition" in how and s["oracle.repetition_hits"] > 0
+
+
+def test_chess_games_with_noise_temperature_and_cache_match_oracle():
+    cfg = chess_cfg(sim_num=10, prior_noise_alpha=0.3, prior_noise_epsilon=0.25, temperature_policy=[[30, 1.0], [9999, 0.0]],
+                    cache_size=50000, seed=77)
+    s, _, _ = check_chess_against_oracle(cfg, "coarse", games_num=2)
+    assert s["metrics"]["cache.hits"] > 0
+
+
+def test_chess_uniform_net_ties_match_oracle():
+    check_chess_against_oracle(chess_cfg(sim_num=8, temperature_policy=[[9999, 1.0]], seed=9), "uniform", games_num=2)
+
+
+def test_chess_results_do_not_depend_on_threads_or_batching():
+    net = chess_fake_net("hash")
+    kw = dict(sim_num=8, prior_noise_alpha=0.3, prior_noise_epsilon=0.25, temperature_policy=[[20, 1.0], [9999, 0.0]])
+    _, ref = SelfPlayRunner("chess", chess_cfg(**kw)).run_with(chess_cb(net), None, 6, keep_records=True)
+    for threads, gpt, cache in ((3, 1, 0), (2, 3, 1000), (1, 6, 7)):
+        summary, got = SelfPlayRunner("chess", chess_cfg(threads=threads, games_per_thread=gpt, cache_size=cache, **kw)).run_with(
+            chess_cb(net), None, 6, keep_records=True)
+        assert [(r.game_idx, r.moves, r.winner, r.entries) for r in got] == [(r.game_idx, r.moves, r.winner, r.entries) for r in ref]

@@ -288,7 +288,7 @@ def test_bad_arguments_are_reported():
     with pytest.raises(SelfPlayError, match="sim_num"):
         SelfPlayRunner("hex4", cfg_with(sim_num=1)).run_with(cb_for(net, 1), None, 2)
     with pytest.raises(ValueError):
-        SelfPlayRunner("chess", cfg_with())
+        SelfPlayRunner("go", cfg_with())
 
     def broken(words, n):
         return [np.zeros(1, np.float32)] * n, [0.0] * n
