@@ -211,13 +211,30 @@ SELFPLAY_CFG = {
               "prior_noise_epsilon": 0.25, "cache_size": 1000000},
     "hex4": {"sim_num": 100, "explore_factor": 1.41421, "temperature_policy": [[4, 1.0], [9999, 0.0]], "prior_noise_alpha": 0.03,
              "prior_noise_epsilon": 0.25, "cache_size": 1000000},
+    # training/config/chess_dev.yaml (engine.mcts + self_play.engine_overrides) on BASELINE config 4's 10 x 128 net and on the yaml's own net
+    "chess10x128": {"sim_num": 600, "explore_factor": 1.41421, "temperature_policy": [[30, 1.0], [9999, 0.0]], "prior_noise_alpha": 0.03,
+                    "prior_noise_epsilon": 0.25, "cache_size": 1000000},
+    "chess_dev": {"sim_num": 600, "explore_factor": 1.41421, "temperature_policy": [[30, 1.0], [9999, 0.0]], "prior_noise_alpha": 0.03,
+                  "prior_noise_epsilon": 0.25, "cache_size": 1000000},
 }
 
 
-def selfplay_summary_to_dict(game, mcts_cfg, summary, games, threads, gpt, extra=None):
+def selfplay_max_moves(args) -> int:
+    if args.selfplay_max_moves >= 0:
+        return args.selfplay_max_moves
+    return 40 if args.selfplay_game.startswith("chess") else 0
+
+
+def runner_game(name: str) -> str:
+    """SelfPlayRunner's game name for a net configuration name."""
+    return "chess" if name.startswith("chess") else name
+
+
+def selfplay_summary_to_dict(game, mcts_cfg, summary, games, threads, gpt, extra=None, max_moves=0):
     m = summary["metrics"]
+    yaml = "chess_dev.yaml" if game.startswith("chess") else f"{game}_cfg.yaml"
     d = {"metric": "selfplay_sims_per_sec", "unit": "sims/s", "workload": f"{game} self-play, sim_num {mcts_cfg['sim_num']}, noise + temperature as "
-         f"training/config/{game}_cfg.yaml", "games": games, "threads": threads, "games_per_thread": gpt, "simulations": m["selfplay.simulations"],
+         f"training/config/{yaml}" + (f", games stopped after {max_moves} moves" if max_moves else ""), "games": games, "threads": threads, "games_per_thread": gpt, "simulations": m["selfplay.simulations"],
          "seconds": m["selfplay.seconds"], "evaluations": m["selfplay.evaluations"], "evaluator_calls": m["model.activation_count"],
          "mean_batch": m["selfplay.evaluations"] / max(1, m["model.activation_count"]),
          "cache_hit_rate": m["cache.hits"] / max(1, m["cache.hits"] + m["cache.misses"]),
@@ -228,7 +245,7 @@ def selfplay_summary_to_dict(game, mcts_cfg, summary, games, threads, gpt, extra
     return d
 
 
-def time_cpu_selfplay(game, games, threads):
+def time_cpu_selfplay(game, games, threads, max_moves=0):
     """The reference's arrangement on the host cores: `threads` OS threads with one tree each (hex5_cfg.yaml: threads 8),
     per-leaf evaluation by the reference's torch-py CPU engine restated (model.rs:68-84; calls are serialised like its
     Mutex<Model>), same MCTS parameters.  Bounded sample: `games` games."""
@@ -241,21 +258,24 @@ def time_cpu_selfplay(game, games, threads):
     model = net.TorchCpuModel(sd, cfg, 1, 1)  # batch-1 evaluations of a 70 k-parameter net: one intra-op thread is the fastest setting
     s = cfg.board_size
 
-    def cb(words, n):
+    def cb(words, n, bitmaps=None):
         x = og.planes_to_tensor_fast(words, s, cfg.planes)
         probs, values = [], []
         for i in range(n):
             logits, v = model.run(x[i:i + 1])
-            ww = words[i].reshape(cfg.planes, -1)
-            legal = [k for k in range(s * s) if not ((int(ww[0][k >> 6]) | int(ww[1][k >> 6])) >> (k & 63)) & 1]
+            if bitmaps is not None:  # chess: the legal moves come as a bitmap over the nn indices
+                legal = og.legal_from_bitmap(bitmaps[i], cfg.moves)
+            else:
+                ww = words[i].reshape(cfg.planes, -1)
+                legal = [k for k in range(s * s) if not ((int(ww[0][k >> 6]) | int(ww[1][k >> 6])) >> (k & 63)) & 1]
             probs.append(og.calc_moves_probs(legal, og.clamp_non_finite(np.asarray(logits[0], dtype=np.float32))))
             values.append(float(np.asarray(v).reshape(-1)[0]))
         return probs, values
 
     mc = SELFPLAY_CFG[game]
-    runner = SelfPlayRunner(game, {"mcts": mc, "threads": threads, "games_per_thread": 1, "seed": 1})
+    runner = SelfPlayRunner(runner_game(game), {"mcts": mc, "threads": threads, "games_per_thread": 1, "seed": 1, "max_moves": max_moves})
     summary, _ = runner.run_with(cb, None, games)
-    return selfplay_summary_to_dict(game, mc, summary, games, threads, 1, {
+    return selfplay_summary_to_dict(game, mc, summary, games, threads, 1, max_moves=max_moves, extra={
         "value": summary["metrics"]["selfplay.sims_per_sec"], "cores": cores, "kind": "port",
         "sample": f"{games} games, {threads} threads x 1 tree each (the reference's arrangement; its Mutex<Model> serialises evaluations, so more "
                   f"threads add nothing), per-leaf torch-CPU fp32 evaluation with 1 intra-op thread"})
@@ -306,7 +326,7 @@ def run_reference_arm(args, rank, world):
     }
     line["batch_sweep"] = cpu_batch_sweep(cfg)
     if not args.no_selfplay:
-        line["selfplay"] = time_cpu_selfplay(args.selfplay_game, 2, 2)
+        line["selfplay"] = time_cpu_selfplay(args.selfplay_game, 2, 2, selfplay_max_moves(args))
     print(json.dumps(line), flush=True)
 
 
@@ -329,6 +349,9 @@ def main():
     ap.add_argument("--selfplay-threads", type=int, default=0, help="worker threads per GPU (0 = host cores / GPUs)")
     ap.add_argument("--selfplay-gpt", type=int, default=512, help="concurrent games per worker thread")
     ap.add_argument("--selfplay-groups", type=int, default=2, help="slot groups per worker thread (one batch in flight per group)")
+    ap.add_argument("--selfplay-max-moves", type=int, default=-1,
+                    help="stop self-play games after this many moves (0 = play to the end as the reference does; default: 0 for hex, 40 for chess, "
+                         "whose random-net games run for hundreds of moves)")
     ap.add_argument("--single-search", action="store_true",
                     help="also time ONE tree searching with --sim-num 10000 (BASELINE configs[4]'s UCI setting, on the self-play game): "
                          "two games, one thread, one leaf at a time through cattus_b200_eval")
@@ -502,8 +525,9 @@ def main():
         mc = SELFPLAY_CFG[args.selfplay_game]
         with CudaNetwork(export_blob(net.make_state_dict(sp_cfg, 0), sp_cfg.game), sp_cfg.game, device=local_rank, batch_size=max(64, min(4096, gpt)),
                          n_streams=max(4, min(32, threads * args.selfplay_groups)), precision="bf16") as sp_nw:
-            runner = SelfPlayRunner(args.selfplay_game, {"mcts": mc, "threads": threads, "games_per_thread": gpt, "groups_per_thread": args.selfplay_groups,
-                                                          "seed": 1})
+            sp_max_moves = selfplay_max_moves(args)
+            runner = SelfPlayRunner(runner_game(args.selfplay_game), {"mcts": mc, "threads": threads, "games_per_thread": gpt,
+                                                                       "groups_per_thread": args.selfplay_groups, "seed": 1, "max_moves": sp_max_moves})
             runner.generate_data(sp_nw, None, 2 * threads, first_game=rank, game_stride=world)  # warm-up (graphs, caches of the allocator)
             l0 = sp_nw.metrics()["model.kernel_launches"]
             barrier()
@@ -513,17 +537,18 @@ def main():
         m = summary["metrics"]
         sims_all = rep.sum_over_ranks(float(m["selfplay.simulations"]))
         secs = max_over_ranks(float(m["selfplay.seconds"]))
-        selfplay = selfplay_summary_to_dict(args.selfplay_game, mc, summary, games_total, threads, gpt, {
+        selfplay = selfplay_summary_to_dict(args.selfplay_game, mc, summary, games_total, threads, gpt, max_moves=sp_max_moves, extra={
             "value": sims_all / secs, "n_gpus": world, "host_cores": cores, "gpu_launches": int(sp_launches),
             "note": "rank 0's counters shown; value = simulations of all ranks / max seconds; games partitioned by index across GPUs, no collective"})
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
-            selfplay["cpu_baseline"] = time_cpu_selfplay(args.selfplay_game, 2, 2)
+            selfplay["cpu_baseline"] = time_cpu_selfplay(args.selfplay_game, 2, 2, min(sp_max_moves, 4) if sp_max_moves else 0)
         if rank == 0 and args.single_search:
             with CudaNetwork(export_blob(net.make_state_dict(sp_cfg, 0), sp_cfg.game), sp_cfg.game, device=local_rank, batch_size=64, n_streams=1,
                              precision="bf16") as ss_nw:
                 ss_mc = dict(mc, sim_num=10000)
-                ss_sum, _ = SelfPlayRunner(args.selfplay_game, {"mcts": ss_mc, "threads": 1, "games_per_thread": 1, "leaf_queue": 1, "seed": 1}).generate_data(
-                    ss_nw, None, 2)
+                # chess games are hundreds of moves long: one search per game from the start position is the UCI `go` case
+                ss_sum, _ = SelfPlayRunner(runner_game(args.selfplay_game), {"mcts": ss_mc, "threads": 1, "games_per_thread": 1, "leaf_queue": 1, "seed": 1,
+                                                                              "max_moves": 1 if sp_cfg.game == "chess" else 0}).generate_data(ss_nw, None, 2)
             sm = ss_sum["metrics"]
             selfplay["single_search"] = {"sim_num": 10000, "searches": sm["selfplay.searches"], "seconds_per_search": sm["selfplay.seconds"] / max(1, sm["selfplay.searches"]),
                                          "sims_per_sec": sm["selfplay.sims_per_sec"], "evaluations": sm["selfplay.evaluations"],

@@ -773,7 +773,8 @@ class Worker {
         Slot& s = slots_[si];
         if (s.phase == kStartMove) {
             const Pos& pos = s.history.back();
-            const int st = s.repetition ? 3 : R.status(pos);  // ChessGame::status: a threefold repetition is a draw
+            int st = s.repetition ? 3 : R.status(pos);  // ChessGame::status: a threefold repetition is a draw
+            if (st == 0 && cfg_.max_moves && s.rec.moves.size() >= cfg_.max_moves) st = 3;  // bounded runs only (not in the reference)
             if (st != 0) {
                 finish_game(s, st);
                 start_next_game(s);

@@ -10,7 +10,8 @@ invokes it (training/cattus_train/train_process.py:159-170, :341-352):
 * `config.model.inference` may carry `{"engine": "cuda-b200", "device": 0, "precision": "bf16", "streams": 4}`;
   `config.model.batch_size` is the evaluator's max batch; the optional top-level keys `games_per_thread`, `leaf_queue`
   and `seed` select this backend's many-games-per-thread arrangement (default 64 games per worker thread);
-* `.traindata` files are byte-for-byte what the reference's serializers write, named `{game_idx:08}_{pos_idx:03}`;
+* `.traindata` files are byte-for-byte what the reference's serializers write (hex, tic-tac-toe and chess:
+  serialize/{hex,ttt,chess}.rs), named `{game_idx:08}_{pos_idx:03}`;
 * the summary file has the reference's layout (:131-149): player1_wins, player2_wins, draws and the metric keys the
   trainer reads -- model.activation_count, model.run_duration, mcts.search_duration, cache.hits, cache.misses.
 
@@ -30,7 +31,7 @@ from .selfplay import SelfPlayRunner
 
 
 def game_of_blob(path: Path):
-    """('hex5', 'hex') / ('ttt', 'ttt') from the .cb2 header (export.py)."""
+    """('hex5', 'hex') / ('ttt', 'ttt') / ('chess', 'chess') from the .cb2 header (export.py)."""
     with open(path, "rb") as f:
         h = struct.unpack("<16I", f.read(64))
     if h[0] != 0x00324243:
@@ -40,7 +41,9 @@ def game_of_blob(path: Path):
         return f"hex{s}", "hex"
     if game_id == _lib.GAME_TTT:
         return "ttt", "ttt"
-    raise ValueError("the self-play driver covers hex and tictactoe; chess needs the reference's move generator (crate `chess`)")
+    if game_id == _lib.GAME_CHESS:
+        return "chess", "chess"
+    raise ValueError(f"{path}: unknown game id {game_id}")
 
 
 def main(argv=None) -> int:

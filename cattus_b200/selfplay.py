@@ -7,7 +7,7 @@
 `cfg` is the same JSON object the reference executable reads (self_play_cmd.rs:34-53; written by
 training/cattus_train/self_play.py): {"model": {"batch_size", "inference"}, "mcts": {"sim_num", "explore_factor",
 "temperature_policy", "prior_noise_alpha", "prior_noise_epsilon", "cache_size"}, "threads"} plus the optional keys
-"games_per_thread", "leaf_queue" and "seed" that only this backend understands.  The returned summary has the layout of
+"games_per_thread", "groups_per_thread", "leaf_queue", "max_moves" and "seed" that only this backend understands.  The returned summary has the layout of
 the reference's summary file (self_play_cmd.rs:131-149) with the metric keys the trainer reads
 (training/cattus_train/train_process.py:176-186).
 
@@ -83,6 +83,7 @@ class SelfPlayRunner:
         c.games_per_thread = int(cfg.get("games_per_thread", 1))
         c.leaf_queue = int(cfg.get("leaf_queue", 0))
         c.groups_per_thread = int(cfg.get("groups_per_thread", 0))
+        c.max_moves = int(cfg.get("max_moves", 0))
         c.seed = int(cfg.get("seed", 0)) & 0xFFFFFFFFFFFFFFFF
         self._c = c
 

@@ -68,6 +68,9 @@ typedef struct cattus_b200_selfplay_cfg {
     uint32_t keep_records; /* 1: keep every game's moves and data entries in memory for the accessors below */
     uint32_t groups_per_thread; /* slot groups per worker, each with its own batch in flight while the worker simulates
                                  * the next group (0 or 1 = one group; > 1 needs the B200 evaluator) */
+    uint32_t max_moves; /* 0 (the reference): play every game to its end.  > 0: stop a game after this many moves and
+                         * record it as a draw -- for benches and tools that need a bounded amount of work */
+    uint32_t reserved;
 } cattus_b200_selfplay_cfg;
 
 /* Mirrors the summary file (self_play_cmd.rs:131-149) and the metric keys the trainer reads

@@ -603,7 +603,7 @@ class GameRecord:
 
 
 def play_game(game_idx: int, new_position: Callable[[], object], params1: MctsParams, params2: MctsParams, eval1: Evaluator,
-              eval2: Evaluator, base_seed: int) -> GameRecord:
+              eval2: Evaluator, base_seed: int, max_moves: int = 0) -> GameRecord:
     rng = SplitMix64(game_seed(base_seed, game_idx))
     player1 = MctsPlayer(params1, eval1, rng)
     player2 = MctsPlayer(params2, eval2, rng)
@@ -616,6 +616,8 @@ def play_game(game_idx: int, new_position: Callable[[], object], params1: MctsPa
     while True:
         st, winner = history[-1].status()
         if seen is not None and seen[history[-1]] >= limit:
+            st, winner = "finished", None
+        if st != "finished" and max_moves and len(moves) >= max_moves:  # the product's bounded-run option (not in the reference)
             st, winner = "finished", None
         if st == "finished":
             break

@@ -281,3 +281,15 @@ def test_chess_results_do_not_depend_on_threads_or_batching():
         summary, got = SelfPlayRunner("chess", chess_cfg(threads=threads, games_per_thread=gpt, cache_size=cache, **kw)).run_with(
             chess_cb(net), None, 6, keep_records=True)
         assert [(r.game_idx, r.moves, r.winner, r.entries) for r in got] == [(r.game_idx, r.moves, r.winner, r.entries) for r in ref]
+
+
+def test_chess_max_moves_bounds_a_game_like_the_oracle():
+    """`max_moves` (bench / tool option, not in the reference): the game stops as a draw after that many moves."""
+    net = chess_fake_net("hash")
+    cfg = chess_cfg(sim_num=6, max_moves=5)
+    summary, records = SelfPlayRunner("chess", cfg).run_with(chess_cb(net), None, 2, keep_records=True)
+    ev = om.Evaluator(chess_oracle_fn(net), None)
+    ref = [om.play_game(g, oc.ChessPosition.new, _params(cfg), _params(cfg), ev, ev, cfg["seed"], max_moves=5) for g in range(2)]
+    for rec, o in zip(records, ref):
+        assert len(rec.moves) == 5 and rec.moves == [oc.move_to_u16(m) for m in o.moves] and rec.winner is None and o.winner is None
+    assert summary["draws"] == 2

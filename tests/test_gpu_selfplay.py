@@ -156,3 +156,51 @@ def test_eval_batch_submit_wait_matches_eval_batch():
         _lib.check(lib.cattus_b200_eval_batch_wait(nw._h, t2.value, ptr(probs, _lib._f32p), probs.size, ptr(offs, _lib._u32p), ptr(vals, _lib._f32p)))
         assert offs[36] == sum(len(l) for l in legal[64:])
         assert lib.cattus_b200_eval_batch_wait(nw._h, t2.value, ptr(probs, _lib._f32p), probs.size, ptr(offs, _lib._u32p), ptr(vals, _lib._f32p)) == _lib.EINVAL
+
+
+def chess_gpu_net(nw):
+    """net(planes[18], legal nn indices ascending) through one blocking cattus_b200_eval per position."""
+
+    def net(planes, legal):
+        probs, value = nw.eval_planes(np.array(planes, dtype=np.uint64), games.bitmap_from_legal(legal, games.CHESS_MOVES_NUM))
+        return np.asarray(probs, dtype=np.float32), np.float32(value)
+
+    return net
+
+
+@pytest.mark.parametrize("name,sim_num,max_moves", [("chess_dev", 24, 0), ("chess_2x128", 12, 60)])
+def test_gpu_chess_selfplay_move_choices_identical_to_oracle(name, sim_num, max_moves):
+    """Chess: 18 planes + the 235-byte legal bitmap per leaf, probabilities mapped from nn-index order back to the move
+    generator's order, threefold repetition inside the searches -- whole games against oracle/mcts.py + oracle/chess.py."""
+    from oracle import chess as oc
+    from tests.test_chess_cpu import _params, chess_cfg, chess_oracle_fn
+
+    cfg = chess_cfg(sim_num=sim_num, cache_size=20000, prior_noise_alpha=0.3, prior_noise_epsilon=0.25, temperature_policy=[[12, 1.0], [9999, 0.0]],
+                    threads=2, games_per_thread=2, seed=21, max_moves=max_moves)
+    with make_network(name, batch_size=64) as nw:
+        summary, records = SelfPlayRunner("chess", cfg).generate_data(nw, None, 4, keep_records=True)
+        ev = om.Evaluator(chess_oracle_fn(chess_gpu_net(nw)), om.ValueFuncCache(20000))
+        params = _params(cfg)
+        ref = [om.play_game(g, oc.ChessPosition.new, params, params, ev, ev, cfg["seed"], max_moves=max_moves) for g in range(4)]
+    for rec, o in zip(records, ref):
+        assert rec.moves == [oc.move_to_u16(m) for m in o.moves] and rec.winner == o.winner
+        for k, (pos, probs) in enumerate(o.entries):
+            assert rec.entries[k] == om.data_entry_bytes(pos, probs, o.winner)
+    m = summary["metrics"]
+    assert m["selfplay.simulations"] == m["selfplay.searches"] * sim_num == sum(o.sims for o in ref)
+    assert m["selfplay.terminal_leaves"] == sum(o.terminal_leaves for o in ref)
+    assert m["selfplay.evaluations"] > 0 and m["model.activation_count"] > 0
+
+
+def test_gpu_chess_selfplay_is_independent_of_scheduling():
+    from tests.test_chess_cpu import chess_cfg
+
+    base = dict(sim_num=40, cache_size=50000, prior_noise_alpha=0.03, prior_noise_epsilon=0.25, temperature_policy=[[30, 1.0], [9999, 0.0]], seed=3,
+                max_moves=24)
+    results = []
+    with make_network("chess_dev", batch_size=256, n_streams=4) as nw:
+        for threads, gpt, groups in ((1, 1, 0), (4, 16, 0), (2, 32, 2)):
+            cfg = chess_cfg(threads=threads, games_per_thread=gpt, groups_per_thread=groups, **base)
+            _, recs = SelfPlayRunner("chess", cfg).generate_data(nw, None, 64, keep_records=True)
+            results.append([(r.game_idx, r.moves, r.winner, r.entries) for r in recs])
+    assert results[1] == results[0] and results[2] == results[0]

@@ -317,5 +317,4 @@ def test_self_player_cli_rejects_other_engines_and_foreign_models(tmp_path):
         self_player.game_of_blob(bad)
     chess = tmp_path / "chess.cb2"
     chess.write_bytes(blob("chess_dev"))
-    with pytest.raises(ValueError, match="chess"):
-        self_player.game_of_blob(chess)
+    assert self_player.game_of_blob(chess) == ("chess", "chess")

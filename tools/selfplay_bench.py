@@ -23,6 +23,8 @@ def main():
     ap.add_argument("--cache", type=int, default=1000000)
     ap.add_argument("--leaf-queue", type=int, default=0)
     ap.add_argument("--groups", type=int, nargs="+", default=[0])
+    ap.add_argument("--max-moves", type=int, default=0)
+    ap.add_argument("--batch", type=int, default=0, help="evaluator max batch (0 = games per thread, clamped to 64..4096)")
     args = ap.parse_args()
 
     from cattus_b200 import CudaNetwork
@@ -34,19 +36,20 @@ def main():
     blob = export_blob(net.make_state_dict(cfg_net, 0), cfg_net.game)
     for th in args.threads:
         for gpt, groups in [(g, k) for g in args.gpt for k in args.groups]:
-            with CudaNetwork(blob, cfg_net.game, batch_size=max(64, min(4096, gpt)), n_streams=args.streams) as nw:
+            with CudaNetwork(blob, cfg_net.game, batch_size=args.batch or max(64, min(4096, gpt)), n_streams=args.streams) as nw:
                 cfg = {"mcts": {"sim_num": args.sim_num, "explore_factor": 1.41421, "temperature_policy": [[10, 1.0], [9999, 0.0]],
                                 "prior_noise_alpha": 0.03, "prior_noise_epsilon": 0.25, "cache_size": args.cache},
-                       "threads": th, "games_per_thread": gpt, "groups_per_thread": groups, "leaf_queue": args.leaf_queue, "seed": 1}
+                       "threads": th, "games_per_thread": gpt, "groups_per_thread": groups, "leaf_queue": args.leaf_queue, "seed": 1,
+                       "max_moves": args.max_moves}
                 games = max(2, (args.games + 1) // 2 * 2)
-                summary, _ = SelfPlayRunner(args.game, cfg).generate_data(nw, None, games)
+                summary, _ = SelfPlayRunner("chess" if args.game.startswith("chess") else args.game, cfg).generate_data(nw, None, games)
                 m = summary["metrics"]
                 print(json.dumps({"threads": th, "gpt": gpt, "groups": groups, "games": games, "sims_per_sec": round(m["selfplay.sims_per_sec"]),
                                   "seconds": round(m["selfplay.seconds"], 3), "evals": m["selfplay.evaluations"], "batches": m["model.activation_count"],
                                   "mean_batch": round(m["selfplay.evaluations"] / max(1, m["model.activation_count"]), 1),
                                   "hit_rate": round(m["cache.hits"] / max(1, m["cache.hits"] + m["cache.misses"]), 3),
                                   "eval_wait_frac": round(m["selfplay.eval_wait_seconds"] / max(1e-9, m["selfplay.seconds"] * th), 3),
-                                  "p1": summary["player1_wins"], "p2": summary["player2_wins"]}), flush=True)
+                                  "p1": summary["player1_wins"], "p2": summary["player2_wins"], "draws": summary["draws"]}), flush=True)
 
 
 if __name__ == "__main__":
