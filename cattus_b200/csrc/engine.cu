@@ -647,6 +647,7 @@ void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
         p.err = d_err_;
         p.s2 = static_cast<int>(s2);
         p.nb = static_cast<int>(nb_);
+        p.n_ptr = n_ptr;  // M tiles of nothing but padding positions return at once
         return p;
     };
     // 3x3 conv: A = NHWC activations through the 4-D halo map, B = [Np][9*Cpad]
@@ -939,18 +940,21 @@ void PackPool::worker() {
             cv_.wait(g, [&] { return stop_ || gen_ != seen; });
             if (stop_) return;
             seen = gen_;
+            if (job_ == nullptr) continue;  // woke up after that run was over
             job = job_;
             slices = slices_;
+            ++active_;  // try_run does not return (and the next run cannot reset next_) while a helper holds its job
         }
         int done = 0;
         for (int i; (i = next_.fetch_add(1)) < slices;) {
             (*job)(i);
             ++done;
         }
-        if (done) {
+        {
             std::lock_guard<std::mutex> g(mu_);
             remaining_ -= done;
-            if (remaining_ == 0) done_cv_.notify_all();
+            --active_;
+            if (remaining_ == 0 && active_ == 0) done_cv_.notify_all();
         }
     }
 }
@@ -973,7 +977,7 @@ bool PackPool::try_run(int slices, const std::function<void(int)>& fn) {
     }
     std::unique_lock<std::mutex> g(mu_);
     remaining_ -= done;
-    done_cv_.wait(g, [&] { return remaining_ == 0; });
+    done_cv_.wait(g, [&] { return remaining_ == 0 && active_ == 0; });
     job_ = nullptr;
     return true;
 }

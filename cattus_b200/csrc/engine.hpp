@@ -125,7 +125,7 @@ class PackPool {
     std::mutex mu_, run_mu_;
     std::condition_variable cv_, done_cv_;
     const std::function<void(int)>* job_ = nullptr;
-    int slices_ = 0, remaining_ = 0;
+    int slices_ = 0, remaining_ = 0, active_ = 0;
     std::atomic<int> next_{0};
     uint64_t gen_ = 0;
     bool stop_ = false;

@@ -69,6 +69,10 @@ struct alignas(64) TcGemmParams {
 };
 
 __device__ __forceinline__ void tc_gemm_body(const TcGemmParams& p, const int m_tile, const int n_tile) {
+    // An M tile that holds nothing but padding positions (the launch is sized for the batch bucket) has no live output.
+    // Mode 1 tiles are whole boards; mode 0 rows are positions only for the head FCs (the epilogues 1-3), elsewhere rows
+    // are board cells and the tile is always computed.
+    if (p.n_ptr != nullptr && (p.mode == 1 || p.epi != 0) && m_tile * (p.mode == 0 ? 128 : p.nb) >= static_cast<int>(*p.n_ptr)) return;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint8_t* smem_a = smem;

@@ -96,6 +96,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1) trunk
     const int pair = blockIdx.x >> 1;
     const int num_pairs = gridDim.x >> 1;
     const int n_valid = static_cast<int>(*p.n_ptr);
+    // Rounds that hold at least one valid position: the launch is sized for the batch bucket, but a round of nothing but
+    // padding is skipped (every thread of both CTAs derives the same bound, so the barrier phases stay in step).
+    const int rounds = min(p.num_rounds, (n_valid + 4 * p.tiles - 1) / (4 * p.tiles));
 
     // ---- one-time setup: zero the activation planes (halo cells stay zero for the whole kernel), barriers, TMEM
     for (int i = threadIdx.x; i < kFtActBytes / 16; i += kFtThreads) reinterpret_cast<uint4*>(act)[i] = make_uint4(0, 0, 0, 0);
@@ -124,7 +127,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1) trunk
         // ================================================================== weight producer (both CTAs)
         if (lane == 0) {
             uint32_t it = 0;
-            for (int rd = pair; rd < p.num_rounds; rd += num_pairs) {
+            for (int rd = pair; rd < rounds; rd += num_pairs) {
                 for (int l = 0; l <= p.layers; ++l) {             // l == layers: the head convs, one stage for all k-chunks
                     const int nkc = l == 0 ? 2 : (l == p.layers ? 1 : 8);
                     for (int kc = 0; kc < nkc; ++kc, ++it) {
@@ -162,7 +165,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1) trunk
             const uint32_t idesc_head = ptx::umma_idesc_bf16(256, static_cast<uint32_t>(nh));
             const uint64_t bh_hi64 = ptx::umma_desc_none_hi(static_cast<uint32_t>(nh / 2) * 16, 128);
             const uint32_t bh_hi = static_cast<uint32_t>(bh_hi64 >> 32), bh_lo_fixed = static_cast<uint32_t>(bh_hi64);
-            for (int rd = pair; rd < p.num_rounds; rd += num_pairs) {
+            for (int rd = pair; rd < rounds; rd += num_pairs) {
                 for (int l = 0; l < p.layers; ++l) {
                     const int nkc = l == 0 ? 2 : 8;
                     const int in_buf = (l & 1) ? 1 : 0;  // stem and conv2 read P (0), conv1 reads Q (1)
@@ -233,7 +236,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1) trunk
         const uint32_t leader_act = ptx::mapa(ptx::smem_u32(&act_full[t * 8]), 0);
         const uint32_t tmem_row = tmem_base + ((q * 32u) << 16) + static_cast<uint32_t>(t * 2 * 128);
         uint32_t acc_par = 0;
-        for (int rd = pair; rd < p.num_rounds; rd += num_pairs) {
+        for (int rd = pair; rd < rounds; rd += num_pairs) {
             const int board = ((rd * p.tiles + t) * 2 + static_cast<int>(rank)) * 2 + j;  // tile-major: a 1-tile round is boards 4 rd .. 4 rd + 3
             const bool valid = board < n_valid;
             // ---- planes_to_tensor for my cell: channels 0..31 of the stem input (planes >= C_in are zero)

@@ -110,6 +110,8 @@ __global__ void __launch_bounds__(kTsThreads, 1) trunk_small_kernel(const __grid
     const int W = p.s + 1;
     const int BP = W * W;
     const int n_valid = static_cast<int>(*p.n_ptr);
+    // rounds holding at least one valid position (the launch is sized for the batch bucket; all-padding rounds are skipped)
+    const int rounds = min(p.num_rounds, (n_valid + p.boards_per_round - 1) / p.boards_per_round);
     const int nh = p.vhp + p.php;
     const uint32_t tmem_cols = static_cast<uint32_t>(64 * T);
 
@@ -155,7 +157,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) trunk_small_kernel(const __grid
         const uint32_t q_addr = ptx::smem_u32(bufQ) + static_cast<uint32_t>(p.margin) * 16;
         const uint32_t w_addr = ptx::smem_u32(wsm);
         const bool leader_lane = ptx::elect_one();
-        for (int rd = blockIdx.x; rd < p.num_rounds; rd += gridDim.x) {
+        for (int rd = blockIdx.x; rd < rounds; rd += gridDim.x) {
             uint32_t w_off = 0;
             for (int l = 0; l <= p.layers; ++l) {
                 const bool head = l == p.layers;
@@ -210,7 +212,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) trunk_small_kernel(const __grid
         const int slot = static_cast<int>(warp >> 2);  // tiles slot, slot + 4
         const int r = static_cast<int>(q4 * 32 + lane);
         const int s2 = p.s * p.s;
-        for (int rd = blockIdx.x; rd < p.num_rounds; rd += gridDim.x) {
+        for (int rd = blockIdx.x; rd < rounds; rd += gridDim.x) {
             const int board0 = rd * p.boards_per_round;
             // ---- planes_to_tensor into the stem input (buffer P), zeros on pads / beyond the batch
             for (int t = slot; t < T; t += 4) {

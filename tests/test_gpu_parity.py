@@ -250,6 +250,32 @@ def test_per_leaf_eval_is_thread_safe_and_batch_invariant():
         print("leaf batches:", m["model.activation_count"], "fill:", m["model.mean_batch_fill"])
 
 
+@pytest.mark.parametrize("name", ["chess_dev", "hex5"])
+def test_concurrent_bulk_batches_of_ragged_sizes(name):
+    """Many host threads in cattus_b200_eval_batch at once with batch sizes that leave most of a bucket as padding (the
+    self-play regime: all-padding rounds and tiles are skipped on the device) and chunks large enough for the shared
+    packing helpers: every caller must get exactly the rows a single caller gets."""
+    sizes = [1, 37, 129, 300, 650, 1100, 1290, 1500]
+    words, bitmaps, _ = synth_inputs(name, 1500, 77)
+    with make_network(name, precision="bf16", batch_size=2048, n_streams=8) as nw:
+        ref_probs, ref_off, ref_vals = nw.eval_batch(words, bitmaps)
+        errors = []
+
+        def worker(k):
+            try:
+                for it in range(6):
+                    b = sizes[(k + it) % len(sizes)]
+                    p, o, v = nw.eval_batch(words[:b], None if bitmaps is None else bitmaps[:b])
+                    assert np.array_equal(o, ref_off[: b + 1]) and np.array_equal(p, ref_probs[: ref_off[b]]) and np.array_equal(v, ref_vals[:b])
+            except Exception as e:  # surfaced in the main thread below
+                errors.append(e)
+
+        threads = [threading.Thread(target=worker, args=(k,)) for k in range(12)]
+        [t.start() for t in threads]
+        [t.join() for t in threads]
+        assert not errors, errors[0]
+
+
 def test_chess_per_leaf_with_bitmap_and_cache():
     from cattus_b200 import ValueFuncCache
 
