@@ -222,7 +222,12 @@ SELFPLAY_CFG = {
 def selfplay_max_moves(args) -> int:
     if args.selfplay_max_moves >= 0:
         return args.selfplay_max_moves
-    return 40 if args.selfplay_game.startswith("chess") else 0
+    return 16 if args.selfplay_game.startswith("chess") else 0
+
+
+def cpu_selfplay_max_moves(args) -> int:
+    """The CPU arm's bounded sample: a chess 10 x 128 leaf costs ~10 ms on one core, so one 600-simulation search per game."""
+    return 1 if args.selfplay_game.startswith("chess") else selfplay_max_moves(args)
 
 
 def runner_game(name: str) -> str:
@@ -326,7 +331,7 @@ def run_reference_arm(args, rank, world):
     }
     line["batch_sweep"] = cpu_batch_sweep(cfg)
     if not args.no_selfplay:
-        line["selfplay"] = time_cpu_selfplay(args.selfplay_game, 2, 2, selfplay_max_moves(args))
+        line["selfplay"] = time_cpu_selfplay(args.selfplay_game, 2, 2, cpu_selfplay_max_moves(args))
     print(json.dumps(line), flush=True)
 
 
@@ -345,12 +350,12 @@ def main():
     ap.add_argument("--no-selfplay", action="store_true", help="skip the self-play sims/s leg")
     ap.add_argument("--no-other-workloads", action="store_true", help="skip the brief hex5 evals/s leg of the default run")
     ap.add_argument("--selfplay-game", default="hex5", choices=sorted(SELFPLAY_CFG))
-    ap.add_argument("--selfplay-games", type=int, default=8192, help="games per GPU in the self-play leg")
+    ap.add_argument("--selfplay-games", type=int, default=0, help="games per GPU in the self-play leg (0 = 8192; chess 16384)")
     ap.add_argument("--selfplay-threads", type=int, default=0, help="worker threads per GPU (0 = host cores / GPUs)")
-    ap.add_argument("--selfplay-gpt", type=int, default=512, help="concurrent games per worker thread")
+    ap.add_argument("--selfplay-gpt", type=int, default=0, help="concurrent games per worker thread (0 = 512; chess 1024)")
     ap.add_argument("--selfplay-groups", type=int, default=2, help="slot groups per worker thread (one batch in flight per group)")
     ap.add_argument("--selfplay-max-moves", type=int, default=-1,
-                    help="stop self-play games after this many moves (0 = play to the end as the reference does; default: 0 for hex, 40 for chess, "
+                    help="stop self-play games after this many moves (0 = play to the end as the reference does; default: 0 for hex, 16 for chess, "
                          "whose random-net games run for hundreds of moves)")
     ap.add_argument("--single-search", action="store_true",
                     help="also time ONE tree searching with --sim-num 10000 (BASELINE configs[4]'s UCI setting, on the self-play game): "
@@ -520,8 +525,10 @@ def main():
         sp_cfg = net.CONFIGS[args.selfplay_game]
         cores = len(os.sched_getaffinity(0))
         threads = args.selfplay_threads or max(1, cores // max(1, world))
-        gpt = args.selfplay_gpt
-        games_total = max(2, args.selfplay_games * world // 2 * 2)
+        # chess leaves cost ~100x a hex leaf on the GPU: twice the games per worker keep its batches at ~430 positions
+        chess_sp = sp_cfg.game == "chess"
+        gpt = args.selfplay_gpt or (1024 if chess_sp else 512)
+        games_total = max(2, (args.selfplay_games or (16384 if chess_sp else 8192)) * world // 2 * 2)
         mc = SELFPLAY_CFG[args.selfplay_game]
         with CudaNetwork(export_blob(net.make_state_dict(sp_cfg, 0), sp_cfg.game), sp_cfg.game, device=local_rank, batch_size=max(64, min(4096, gpt)),
                          n_streams=max(4, min(32, threads * args.selfplay_groups)), precision="bf16") as sp_nw:
@@ -541,18 +548,32 @@ def main():
             "value": sims_all / secs, "n_gpus": world, "host_cores": cores, "gpu_launches": int(sp_launches),
             "note": "rank 0's counters shown; value = simulations of all ranks / max seconds; games partitioned by index across GPUs, no collective"})
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
-            selfplay["cpu_baseline"] = time_cpu_selfplay(args.selfplay_game, 2, 2, min(sp_max_moves, 4) if sp_max_moves else 0)
+            selfplay["cpu_baseline"] = time_cpu_selfplay(args.selfplay_game, 2, 2, cpu_selfplay_max_moves(args))
         if rank == 0 and args.single_search:
             with CudaNetwork(export_blob(net.make_state_dict(sp_cfg, 0), sp_cfg.game), sp_cfg.game, device=local_rank, batch_size=64, n_streams=1,
                              precision="bf16") as ss_nw:
                 ss_mc = dict(mc, sim_num=10000)
-                # chess games are hundreds of moves long: one search per game from the start position is the UCI `go` case
-                ss_sum, _ = SelfPlayRunner(runner_game(args.selfplay_game), {"mcts": ss_mc, "threads": 1, "games_per_thread": 1, "leaf_queue": 1, "seed": 1,
-                                                                              "max_moves": 1 if sp_cfg.game == "chess" else 0}).generate_data(ss_nw, None, 2)
-            sm = ss_sum["metrics"]
-            selfplay["single_search"] = {"sim_num": 10000, "searches": sm["selfplay.searches"], "seconds_per_search": sm["selfplay.seconds"] / max(1, sm["selfplay.searches"]),
-                                         "sims_per_sec": sm["selfplay.sims_per_sec"], "evaluations": sm["selfplay.evaluations"],
-                                         "note": "one tree, one leaf in flight (the reference's UCI arrangement), per-leaf cattus_b200_eval"}
+                if sp_cfg.game == "chess":
+                    # BASELINE config 5: the UCI loop's `position` + `go` (cattus_b200/uci.py), a new player per position
+                    from cattus_b200.selfplay import ChessSearch
+
+                    per = []
+                    for fen in (None, "r3k2r/p1ppqpb1/bn2pnp1/3PN3/1p2P3/2N2Q1p/PPPBBPPP/R3K2R w KQkq -"):
+                        with ChessSearch({"mcts": ss_mc, "seed": 1}, model=ss_nw) as search:
+                            best, st = search.go(fen, [])
+                        per.append({"position": fen or "startpos", "bestmove": best, "seconds": st["seconds"], "evaluations": st["evaluations"],
+                                    "cache_hits": st["cache_hits"], "sims_per_sec": st["simulations"] / st["seconds"]})
+                    selfplay["single_search"] = {"sim_num": 10000, "searches": per, "seconds_per_search": float(np.mean([p["seconds"] for p in per])),
+                                                 "note": "UCI `go` at sim_num 10000: one tree, one leaf in flight (the reference's arrangement), per-leaf "
+                                                         "cattus_b200_eval; cache hits are transpositions inside the one search"}
+                else:
+                    ss_sum, _ = SelfPlayRunner(args.selfplay_game, {"mcts": ss_mc, "threads": 1, "games_per_thread": 1, "leaf_queue": 1,
+                                                                    "seed": 1}).generate_data(ss_nw, None, 2)
+                    sm = ss_sum["metrics"]
+                    selfplay["single_search"] = {"sim_num": 10000, "searches": sm["selfplay.searches"],
+                                                 "seconds_per_search": sm["selfplay.seconds"] / max(1, sm["selfplay.searches"]),
+                                                 "sims_per_sec": sm["selfplay.sims_per_sec"], "evaluations": sm["selfplay.evaluations"],
+                                                 "note": "one tree, one leaf in flight (the reference's UCI arrangement), per-leaf cattus_b200_eval"}
 
     total_positions = world * positions_per_step * args.steps
     value = total_positions / t_value

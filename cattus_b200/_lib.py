@@ -62,6 +62,15 @@ class SelfPlaySummary(C.Structure):
     ]
 
 
+class ChessSearchStats(C.Structure):
+    """cattus_b200_chess_search_stats (include/cattus_b200_selfplay.h)."""
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("root_children", C.c_uint32), ("best_visits", C.c_uint32), ("reserved", C.c_uint32),
+        ("simulations", C.c_uint64), ("evaluations", C.c_uint64), ("cache_hits", C.c_uint64), ("terminal_leaves", C.c_uint64),
+        ("seconds", C.c_double),
+    ]
+
+
 class ChessInfo(C.Structure):
     """cattus_b200_chess_info (include/cattus_b200_chess.h)."""
     _fields_ = [
@@ -104,6 +113,10 @@ SYMBOLS = {
     "cattus_b200_selfplay_entry": (C.c_int, [_H, C.c_uint32, C.c_uint32, _u8p, C.c_size_t, C.POINTER(C.c_size_t), _u32p]),
     "cattus_b200_selfplay_free": (None, [_H]),
     "cattus_b200_selfplay_last_error": (C.c_char_p, []),
+    "cattus_b200_chess_search_create": (C.c_int, [_H, C.POINTER(SelfPlayCfg), C.POINTER(_H)]),
+    "cattus_b200_chess_search_create_with": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(SelfPlayCfg), C.POINTER(_H)]),
+    "cattus_b200_chess_search_go": (C.c_int, [_H, C.c_char_p, _u16p, C.c_uint32, _u16p, C.POINTER(ChessSearchStats)]),
+    "cattus_b200_chess_search_destroy": (None, [_H]),
     # include/cattus_b200_chess.h
     "cattus_b200_chess_position": (C.c_int, [C.c_char_p, _u16p, C.c_uint32, C.POINTER(ChessInfo)]),
     "cattus_b200_chess_perft": (C.c_int, [C.c_char_p, C.c_uint32, C.POINTER(C.c_uint64)]),

@@ -712,6 +712,51 @@ class Worker {
         sh_.games += c_.games;
     }
 
+    // One search at a time on slot 0, driven from outside: GamePlayer::next_move(pos_history) as the reference's UCI loop
+    // calls it per `go` (engine/src/chess/uci.rs:158-161, mcts/mod.rs:448-454).  The tree is kept between calls and reused
+    // when the new position is found in it (mod.rs:335-352).  Returns false if the position has no move to search.
+    struct SearchStats {
+        uint64_t simulations = 0, evaluations = 0, cache_hits = 0, terminal = 0;
+        double seconds = 0.0;
+        uint32_t root_visits_best = 0, root_children = 0;
+    };
+    void reseed(uint64_t seed) { slots_[0].rng = SplitMix64(game_seed(seed, 0)); }
+    bool search_from(const std::vector<Pos>& history, Move* best, SearchStats* stats) {
+        Slot& s = slots_[0];
+        s.history = history;
+        s.pending_entries.clear();
+        s.rec.moves.clear();
+        s.repetition = false;
+        if (R.status(s.history.back()) != 0) return false;
+        const Counters before = c_;
+        const auto t0 = Clock::now();
+        s.cur = 0;
+        begin_search(s);
+        s.phase = kSimulate;
+        s.sel_node = -1;
+        Group& gr = groups_[0];
+        while (s.phase != kStartMove) {
+            if (!step(0))  // parked on the evaluator: evaluate now (one leaf in flight, like the reference)
+                for (int e = 0; e < 2; ++e)
+                    if (!gr.pend[e].keys.empty()) send(gr, e);
+        }
+        if (sh_.failed.load()) return false;
+        *best = static_cast<Move>(s.rec.moves.back());
+        if (stats) {
+            stats->simulations = c_.simulations - before.simulations;
+            stats->evaluations = c_.evaluations - before.evaluations;
+            stats->cache_hits = c_.cache_hits - before.cache_hits;
+            stats->terminal = c_.terminal - before.terminal;
+            stats->seconds = std::chrono::duration<double>(Clock::now() - t0).count();
+            const auto& probs = s.pending_entries.back().second;
+            stats->root_children = static_cast<uint32_t>(probs.size());
+            float top = 0.0f;
+            for (auto& mp : probs) top = std::max(top, mp.second);
+            stats->root_visits_best = static_cast<uint32_t>(top * static_cast<float>(params_[0].sim_num) + 0.5f);
+        }
+        return true;
+    }
+
   private:
     // ---------------------------------------------------------------- game loop (self_play.rs:179-246)
     void start_next_game(Slot& s) {
@@ -1469,32 +1514,38 @@ static void run_games(const Rules& rules, const cattus_b200_selfplay_cfg& cfg, c
     for (auto& t : threads) t.join();
 }
 
+// MctsParams from the config (mcts/mod.rs:72-110; TemperaturePolicy::scheduled, self_play_cmd.rs:68-72)
+static sp::Params parse_params(const cattus_b200_selfplay_cfg* cfg) {
+    if (cfg->sim_num < 2) throw sp::SpError{CATTUS_B200_EINVAL, "sim_num must be > 1 (mcts/mod.rs:157)"};
+    if (!(cfg->explore_factor >= 0.0f) || !(cfg->prior_noise_alpha >= 0.0f) || !(cfg->prior_noise_epsilon >= 0.0f && cfg->prior_noise_epsilon <= 1.0f))
+        throw sp::SpError{CATTUS_B200_EINVAL, "bad mcts parameters (mcts/mod.rs:107-110)"};
+    sp::Params p;
+    p.sim_num = cfg->sim_num;
+    p.explore_factor = cfg->explore_factor;
+    p.noise_alpha = cfg->prior_noise_alpha;
+    p.noise_eps = cfg->prior_noise_epsilon;
+    p.last_temperature = 1.0f;
+    if (cfg->n_temperatures) {
+        if (!cfg->temperature_moves || !cfg->temperature_values) throw sp::SpError{CATTUS_B200_EINVAL, "temperature arrays are NULL"};
+        for (uint32_t i = 0; i + 1 < cfg->n_temperatures; ++i) {
+            if (!(cfg->temperature_values[i] >= 0.0f)) throw sp::SpError{CATTUS_B200_EINVAL, "negative temperature"};
+            if (i > 0 && cfg->temperature_moves[i] <= cfg->temperature_moves[i - 1]) throw sp::SpError{CATTUS_B200_EINVAL, "temperature thresholds must be strictly increasing"};
+            p.temperatures.emplace_back(cfg->temperature_moves[i], cfg->temperature_values[i]);
+        }
+        p.last_temperature = cfg->temperature_values[cfg->n_temperatures - 1];
+        if (!(p.last_temperature >= 0.0f)) throw sp::SpError{CATTUS_B200_EINVAL, "negative temperature"};
+    }
+    return p;
+}
+
 static int selfplay_impl(sp::Evaluator& e1, sp::Evaluator* e2_or_null, const cattus_b200_selfplay_cfg* cfg, cattus_b200_selfplay_t** out) {
     try {
         if (!cfg || !out) throw sp::SpError{CATTUS_B200_EINVAL, "null argument"};
         if (cfg->struct_size != sizeof(cattus_b200_selfplay_cfg)) throw sp::SpError{CATTUS_B200_EINVAL, "selfplay cfg struct_size mismatch"};
         *out = nullptr;
-        if (cfg->sim_num < 2) throw sp::SpError{CATTUS_B200_EINVAL, "sim_num must be > 1 (mcts/mod.rs:157)"};
-        if (!(cfg->explore_factor >= 0.0f) || !(cfg->prior_noise_alpha >= 0.0f) || !(cfg->prior_noise_epsilon >= 0.0f && cfg->prior_noise_epsilon <= 1.0f))
-            throw sp::SpError{CATTUS_B200_EINVAL, "bad mcts parameters (mcts/mod.rs:107-110)"};
         if (cfg->games_num % 2 != 0) throw sp::SpError{CATTUS_B200_EINVAL, "Games num should be a multiple of 2 (self_play.rs:100)"};
         if ((cfg->out_dir1 == nullptr) != (cfg->out_dir2 == nullptr)) throw sp::SpError{CATTUS_B200_EINVAL, "out_dir1 and out_dir2 must both be set or both NULL"};
-        sp::Params p;
-        p.sim_num = cfg->sim_num;
-        p.explore_factor = cfg->explore_factor;
-        p.noise_alpha = cfg->prior_noise_alpha;
-        p.noise_eps = cfg->prior_noise_epsilon;
-        p.last_temperature = 1.0f;
-        if (cfg->n_temperatures) {
-            if (!cfg->temperature_moves || !cfg->temperature_values) throw sp::SpError{CATTUS_B200_EINVAL, "temperature arrays are NULL"};
-            for (uint32_t i = 0; i + 1 < cfg->n_temperatures; ++i) {
-                if (!(cfg->temperature_values[i] >= 0.0f)) throw sp::SpError{CATTUS_B200_EINVAL, "negative temperature"};
-                if (i > 0 && cfg->temperature_moves[i] <= cfg->temperature_moves[i - 1]) throw sp::SpError{CATTUS_B200_EINVAL, "temperature thresholds must be strictly increasing"};
-                p.temperatures.emplace_back(cfg->temperature_moves[i], cfg->temperature_values[i]);
-            }
-            p.last_temperature = cfg->temperature_values[cfg->n_temperatures - 1];
-            if (!(p.last_temperature >= 0.0f)) throw sp::SpError{CATTUS_B200_EINVAL, "negative temperature"};
-        }
+        const sp::Params p = parse_params(cfg);
         sp::Params params[2] = {p, p};
         if (cfg->game == CATTUS_B200_GAME_HEX) {
             if (cfg->board_size < 2 || cfg->board_size > 11) throw sp::SpError{CATTUS_B200_EINVAL, "hex board_size must be 2..11"};
@@ -1659,6 +1710,121 @@ int cattus_b200_selfplay_entry(const cattus_b200_selfplay_t* r, uint32_t k, uint
 }
 
 void cattus_b200_selfplay_free(cattus_b200_selfplay_t* r) { delete r; }
+
+// ---------------------------------------------------------------- one chess search at a time (the UCI loop's player)
+struct cattus_b200_chess_search {
+    sp::ChessRules rules;
+    cattus_b200_selfplay_cfg cfg;
+    sp::Params params[2];
+    sp::Evaluator ev;
+    sp::Evaluator* evals[2];
+    sp::Shared sh;
+    std::unique_ptr<sp::Worker<sp::ChessRules>> worker;
+};
+
+static int chess_search_create_impl(cattus_b200_eval_fn fn, void* ctx, cattus_b200_t* leaf_handle, const cattus_b200_selfplay_cfg* cfg,
+                                    cattus_b200_chess_search_t** out) {
+    try {
+        if (!cfg || !out || !fn) throw sp::SpError{CATTUS_B200_EINVAL, "null argument"};
+        if (cfg->struct_size != sizeof(cattus_b200_selfplay_cfg)) throw sp::SpError{CATTUS_B200_EINVAL, "selfplay cfg struct_size mismatch"};
+        *out = nullptr;
+        std::unique_ptr<cattus_b200_chess_search> s(new cattus_b200_chess_search());
+        s->params[0] = s->params[1] = parse_params(cfg);
+        s->cfg = *cfg;
+        s->cfg.game = CATTUS_B200_GAME_CHESS;
+        s->cfg.board_size = 8;
+        s->cfg.temperature_moves = nullptr;  // consumed by parse_params; the caller's arrays need not outlive this call
+        s->cfg.temperature_values = nullptr;
+        s->cfg.threads = s->cfg.games_per_thread = 1;
+        s->cfg.groups_per_thread = s->cfg.keep_records = s->cfg.max_moves = s->cfg.first_game = 0;
+        s->cfg.game_stride = 1;
+        s->cfg.games_num = 2;
+        s->cfg.out_dir1 = s->cfg.out_dir2 = nullptr;
+        s->ev.fn = fn;
+        s->ev.ctx = ctx;
+        s->ev.leaf_handle = leaf_handle;
+        if (cfg->cache_size) s->ev.cache.reset(new sp::Cache(cfg->cache_size, sp::ChessRules::kMaxMoves));
+        s->evals[0] = s->evals[1] = &s->ev;
+        s->worker.reset(new sp::Worker<sp::ChessRules>(s->rules, s->cfg, s->params, s->evals, s->sh));
+        s->worker->reseed(cfg->seed);
+        *out = s.release();
+        g_sp_error.clear();
+        return CATTUS_B200_OK;
+    } catch (const sp::SpError& e) {
+        g_sp_error = e.msg;
+        return e.code ? e.code : CATTUS_B200_EINVAL;
+    } catch (const std::exception& e) {
+        g_sp_error = e.what();
+        return CATTUS_B200_EINVAL;
+    }
+}
+
+int cattus_b200_chess_search_create(cattus_b200_t* model, const cattus_b200_selfplay_cfg* cfg, cattus_b200_chess_search_t** out) {
+    if (!model) {
+        g_sp_error = "null evaluator handle (there is no CPU fallback)";
+        return CATTUS_B200_EINVAL;
+    }
+    return chess_search_create_impl(engine_eval_thunk, model, model, cfg, out);
+}
+
+int cattus_b200_chess_search_create_with(cattus_b200_eval_fn eval, void* ctx, const cattus_b200_selfplay_cfg* cfg, cattus_b200_chess_search_t** out) {
+    return chess_search_create_impl(eval, ctx, nullptr, cfg, out);
+}
+
+int cattus_b200_chess_search_go(cattus_b200_chess_search_t* s, const char* fen, const uint16_t* moves, uint32_t n_moves, uint16_t* best_move,
+                                cattus_b200_chess_search_stats* stats) {
+    try {
+        if (!s || !best_move || (n_moves && !moves)) throw sp::SpError{CATTUS_B200_EINVAL, "null argument"};
+        const sp::ChessRules& R = s->rules;
+        std::vector<sp::ChessPos> history;
+        sp::ChessPos p;
+        if (fen) {
+            const std::string err = R.from_fen(fen, p);
+            if (!err.empty()) throw sp::SpError{CATTUS_B200_EINVAL, "bad FEN: " + err};
+        } else {
+            p = R.initial();
+        }
+        history.push_back(p);
+        sp::ChessRules::Move buf[256];
+        for (uint32_t i = 0; i < n_moves; ++i) {  // cmd_position (uci.rs:76-93): moved_position per move, every position kept
+            const int n = R.children(p, buf);
+            const sp::ChessRules::Move want = sp::ChessRules::real_move(p, moves[i]);
+            bool found = false;
+            for (int k = 0; k < n; ++k) found |= buf[k] == want;
+            if (!found) throw sp::SpError{CATTUS_B200_EINVAL, "move " + std::to_string(i) + " is not legal here"};
+            p = R.moved(p, want);
+            R.children(p, buf);  // settles status()
+            history.push_back(p);
+        }
+        sp::Worker<sp::ChessRules>::SearchStats st;
+        sp::ChessRules::Move best = 0;
+        if (!s->worker->search_from(history, &best, &st)) {
+            if (s->sh.failed.load()) throw sp::SpError{s->sh.error_code, s->sh.error};
+            throw sp::SpError{CATTUS_B200_EINVAL, "the game is over in this position: no move to search"};
+        }
+        *best_move = best;
+        if (stats) {
+            if (stats->struct_size != sizeof(cattus_b200_chess_search_stats)) throw sp::SpError{CATTUS_B200_EINVAL, "search stats struct_size mismatch"};
+            stats->simulations = st.simulations;
+            stats->evaluations = st.evaluations;
+            stats->cache_hits = st.cache_hits;
+            stats->terminal_leaves = st.terminal;
+            stats->seconds = st.seconds;
+            stats->root_children = st.root_children;
+            stats->best_visits = st.root_visits_best;
+        }
+        g_sp_error.clear();
+        return CATTUS_B200_OK;
+    } catch (const sp::SpError& e) {
+        g_sp_error = e.msg;
+        return e.code ? e.code : CATTUS_B200_EINVAL;
+    } catch (const std::exception& e) {
+        g_sp_error = e.what();
+        return CATTUS_B200_EINVAL;
+    }
+}
+
+void cattus_b200_chess_search_destroy(cattus_b200_chess_search_t* s) { delete s; }
 
 const char* cattus_b200_selfplay_last_error(void) { return g_sp_error.c_str(); }
 

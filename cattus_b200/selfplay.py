@@ -58,6 +58,35 @@ def _check(lib, rc: int) -> None:
         raise SelfPlayError(f"cattus_b200_selfplay error {rc}: {(lib.cattus_b200_selfplay_last_error() or b'').decode(errors='replace')}")
 
 
+def _eval_thunk(fn: Callable, words: int, chess: bool, errors: list):
+    """Wraps a Python evaluator as a cattus_b200_eval_fn (keep the returned object alive while C may call it)."""
+
+    def thunk(_ctx, planes, legal, n, probs_out, probs_cap, prob_offsets, values_out):
+        try:
+            w = np.ctypeslib.as_array(planes, shape=(n, words)).copy()
+            if chess:
+                probs, values = fn(w, n, np.ctypeslib.as_array(legal, shape=(n, 235)).copy())
+            else:
+                probs, values = fn(w, n)
+            off = 0
+            for i in range(n):
+                p = np.asarray(probs[i], dtype=np.float32)
+                if off + len(p) > probs_cap:
+                    return _lib.ERANGE
+                prob_offsets[i] = off
+                for k, x in enumerate(p):
+                    probs_out[off + k] = float(x)
+                off += len(p)
+                values_out[i] = float(np.float32(values[i]))
+            prob_offsets[n] = off
+            return 0
+        except Exception as e:  # never let an exception cross the C boundary
+            errors.append(e)
+            return _lib.EINVAL
+
+    return _lib.EVAL_FN(thunk)
+
+
 class SelfPlayRunner:
     def __init__(self, game: str, cfg: dict):
         self._lib = _lib.load()
@@ -118,29 +147,7 @@ class SelfPlayRunner:
         errors: list = []
 
         def thunk_for(fn):
-            def thunk(_ctx, planes, legal, n, probs_out, probs_cap, prob_offsets, values_out):
-                try:
-                    w = np.ctypeslib.as_array(planes, shape=(n, words)).copy()
-                    if chess:
-                        probs, values = fn(w, n, np.ctypeslib.as_array(legal, shape=(n, 235)).copy())
-                    else:
-                        probs, values = fn(w, n)
-                    off = 0
-                    for i in range(n):
-                        p = np.asarray(probs[i], dtype=np.float32)
-                        if off + len(p) > probs_cap:
-                            return _lib.ERANGE
-                        prob_offsets[i] = off
-                        for k, x in enumerate(p):
-                            probs_out[off + k] = float(x)
-                        off += len(p)
-                        values_out[i] = float(np.float32(values[i]))
-                    prob_offsets[n] = off
-                    return 0
-                except Exception as e:  # never let an exception cross the C boundary
-                    errors.append(e)
-                    return _lib.EINVAL
-            return _lib.EVAL_FN(thunk)
+            return _eval_thunk(fn, words, chess, errors)
 
         t1 = thunk_for(eval1)
         t2 = thunk_for(eval2) if eval2 is not None else None
@@ -189,3 +196,82 @@ class SelfPlayRunner:
             return summary, records
         finally:
             lib.cattus_b200_selfplay_free(h)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# one chess search at a time: the player of the reference's UCI loop (engine/src/chess/uci.rs)
+# ---------------------------------------------------------------------------------------------------------------------
+_PROMO = (None, "q", "n", "r", "b")
+
+
+def move_to_lan(m: int) -> str:
+    """from | to << 6 | promotion << 12 -> 'e2e4' / 'e7e8q' (the crate's ChessMove Display, which the UCI loop prints)."""
+    sq = lambda x: "abcdefgh"[x & 7] + "12345678"[x >> 3]  # noqa: E731
+    return sq(m & 63) + sq((m >> 6) & 63) + (_PROMO[m >> 12] or "")
+
+
+def move_from_lan(lan: str) -> int:
+    """ChessMove::from_lan (chess/core.rs:24-51)."""
+    if len(lan) not in (4, 5):
+        raise ValueError(f"Invalid LAN length: {lan!r}")
+    f = (ord(lan[1]) - 49) * 8 + ord(lan[0]) - 97
+    t = (ord(lan[3]) - 49) * 8 + ord(lan[2]) - 97
+    if not (0 <= f < 64 and 0 <= t < 64):
+        raise ValueError(f"bad squares in {lan!r}")
+    promo = 0
+    if len(lan) == 5:
+        if lan[4] not in "qnrb":
+            raise ValueError(f"Unknown promotion char: {lan[4]!r} in lan str {lan!r}")
+        promo = _PROMO.index(lan[4])
+    return f | (t << 6) | (promo << 12)
+
+
+class ChessSearch:
+    """MctsPlayer<ChessGame> over include/cattus_b200_selfplay.h's cattus_b200_chess_search_*: `ChessSearch(cfg, model)`
+    is `ucinewgame`, `go(fen, moves)` is `position ...` + `go` and returns (bestmove as LAN, stats)."""
+
+    def __init__(self, cfg: dict, model=None, eval_fn: Optional[Callable] = None):
+        self._lib = _lib.load()
+        self._runner = SelfPlayRunner("chess", cfg)  # fills the mcts.* fields of the C struct
+        c = self._runner._fill(2, None, None, False, 0, 1)
+        self._errors: list = []
+        h = C.c_void_p()
+        if model is not None:
+            self._thunk = None
+            _check(self._lib, self._lib.cattus_b200_chess_search_create(model._h, C.byref(c), C.byref(h)))
+        else:
+            assert eval_fn is not None, "either a CudaNetwork or an evaluator callback"
+            self._thunk = _eval_thunk(eval_fn, 18, True, self._errors)
+            _check(self._lib, self._lib.cattus_b200_chess_search_create_with(C.cast(self._thunk, C.c_void_p), None, C.byref(c), C.byref(h)))
+        self._h = h
+
+    def go(self, fen: Optional[str] = None, moves=()):
+        mv = [move_from_lan(m) if isinstance(m, str) else int(m) for m in moves]
+        arr = (C.c_uint16 * max(1, len(mv)))(*mv)
+        best = C.c_uint16()
+        st = _lib.ChessSearchStats()
+        st.struct_size = C.sizeof(_lib.ChessSearchStats)
+        rc = self._lib.cattus_b200_chess_search_go(self._h, None if fen is None else fen.encode(), arr, len(mv), C.byref(best), C.byref(st))
+        if self._errors:
+            raise self._errors.pop()
+        _check(self._lib, rc)
+        return move_to_lan(best.value), {"simulations": st.simulations, "evaluations": st.evaluations, "cache_hits": st.cache_hits,
+                                         "terminal_leaves": st.terminal_leaves, "seconds": st.seconds, "root_children": st.root_children,
+                                         "best_visits": st.best_visits}
+
+    def close(self):
+        if self._h:
+            self._lib.cattus_b200_chess_search_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

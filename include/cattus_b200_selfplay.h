@@ -117,6 +117,29 @@ int cattus_b200_selfplay_game_moves16(const cattus_b200_selfplay_t* r, uint32_t 
 int cattus_b200_selfplay_entry(const cattus_b200_selfplay_t* r, uint32_t k, uint32_t pos_idx, uint8_t* bytes_out,
                                size_t cap, size_t* n_bytes, uint32_t* out_dir);
 void cattus_b200_selfplay_free(cattus_b200_selfplay_t* r);
+
+/* ---- one chess search at a time: the player behind the reference's UCI loop (engine/src/chess/uci.rs) ----
+ * create = `ucinewgame` (MctsPlayer::new, uci.rs:59); the mcts.* fields, cache_size and seed of cfg are used.
+ * go     = `position ...` + `go` (uci.rs:76-93, :158-161): the history is the FEN's position (NULL: the start position)
+ *          followed by one position per move; GamePlayer::next_move(pos_history) (mcts/mod.rs:448-454) searches with one
+ *          leaf in flight (per-leaf cattus_b200_eval), reusing the tree of the previous `go` when the new position is
+ *          in it (mod.rs:335-352).  Moves are from | to << 6 | promotion << 12 in real board coordinates
+ *          (include/cattus_b200_chess.h). */
+typedef struct cattus_b200_chess_search cattus_b200_chess_search_t;
+typedef struct cattus_b200_chess_search_stats {
+    uint32_t struct_size;
+    uint32_t root_children;  /* legal moves of the searched position */
+    uint32_t best_visits;    /* simulations that went through the most visited root child */
+    uint32_t reserved;
+    uint64_t simulations, evaluations, cache_hits, terminal_leaves; /* of this search */
+    double seconds;
+} cattus_b200_chess_search_stats;
+int cattus_b200_chess_search_create(cattus_b200_t* model, const cattus_b200_selfplay_cfg* cfg, cattus_b200_chess_search_t** out);
+int cattus_b200_chess_search_create_with(cattus_b200_eval_fn eval, void* ctx, const cattus_b200_selfplay_cfg* cfg,
+                                         cattus_b200_chess_search_t** out);
+int cattus_b200_chess_search_go(cattus_b200_chess_search_t* s, const char* fen, const uint16_t* moves, uint32_t n_moves,
+                                uint16_t* best_move, cattus_b200_chess_search_stats* stats);
+void cattus_b200_chess_search_destroy(cattus_b200_chess_search_t* s);
 /* thread-local message of the last failed cattus_b200_selfplay_* call on this thread */
 const char* cattus_b200_selfplay_last_error(void);
 

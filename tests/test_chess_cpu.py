@@ -293,3 +293,66 @@ def test_chess_max_moves_bounds_a_game_like_the_oracle():
     for rec, o in zip(records, ref):
         assert len(rec.moves) == 5 and rec.moves == [oc.move_to_u16(m) for m in o.moves] and rec.winner is None and o.winner is None
     assert summary["draws"] == 2
+
+
+# --------------------------------------------------------------------------------------------------------------
+# one search at a time: the UCI loop's player (cattus_b200_chess_search_*, cattus_b200/uci.py)
+# --------------------------------------------------------------------------------------------------------------
+def test_search_session_matches_oracle_player_with_tree_reuse():
+    """`ucinewgame`, then `position ... moves ...` + `go` with the engine's move and a reply appended each time: the
+    tree of the previous search is found two plies down and reused (mcts/mod.rs:335-352).  Same moves as the oracle's
+    MctsPlayer fed the same history."""
+    from cattus_b200.selfplay import ChessSearch, move_from_lan
+
+    net = chess_fake_net("hash")
+    cfg = chess_cfg(sim_num=30, prior_noise_alpha=0.3, prior_noise_epsilon=0.25, temperature_policy=[[4, 1.0], [9999, 0.0]], cache_size=10000, seed=13)
+    player = om.MctsPlayer(_params(cfg), om.Evaluator(chess_oracle_fn(net), om.ValueFuncCache(10000)), om.SplitMix64(om.game_seed(13, 0)))
+    rng = random.Random(2)
+    fen = KIWIPETE
+    history = [oc.ChessPosition.from_fen(fen)]
+    moves = []
+    with ChessSearch(cfg, eval_fn=chess_cb(net)) as search:
+        for _ in range(6):
+            best, stats = search.go(fen, moves)
+            probs = player.calc_moves_probabilities(history)
+            want = player.choose_move_from_probabilities(history, probs)
+            assert best == oc.move_to_lan(want)
+            assert stats["simulations"] == 30 and stats["root_children"] == len(history[-1].legal_moves())
+            moves.append(best)
+            history.append(history[-1].moved_position(want))
+            if history[-1].is_finished():
+                break
+            reply = rng.choice(history[-1].legal_moves())
+            moves.append(oc.move_to_lan(reply))
+            history.append(history[-1].moved_position(reply))
+        assert move_from_lan("e7e8q") == 52 | (60 << 6) | (1 << 12)
+        with pytest.raises(Exception, match="not legal"):
+            search.go(None, ["e2e5"])
+        with pytest.raises(Exception, match="over"):
+            search.go("7k/5Q2/6K1/8/8/8/8/8 b - -", [])  # stalemate: nothing to search
+
+
+def test_uci_loop_commands():
+    """The command set of engine/src/chess/uci.rs:27-73 over a deterministic evaluator."""
+    import io
+
+    from cattus_b200.uci import UCI
+
+    out = io.StringIO()
+    cfg = chess_cfg(sim_num=20, seed=3)
+    uci = UCI(cfg, eval_fn=chess_cb(chess_fake_net("hash")), out=out)
+    script = ["uci", "isready", "setoption name Hash value 16", "ucinewgame", "position startpos moves e2e4 e7e5", "go movetime 1000",
+              "position fen r3k2r/p1ppqpb1/bn2pnp1/3PN3/1p2P3/2N2Q1p/PPPBBPPP/R3K2R w KQkq - moves e1g1", "go", "stop", "bogus", "quit", "go"]
+    uci.run(io.StringIO("\n".join(script) + "\n"))
+    lines = out.getvalue().split("\n")
+    assert lines[:4] == ["id name cattus_b200 v1.0.0", "id author cattus_b200", "uciok", "readyok"]
+    best = [ln.split()[1] for ln in lines if ln.startswith("bestmove")]
+    assert len(best) == 2  # nothing after quit
+    start = oc.ChessPosition.new()
+    for lan in ("e2e4", "e7e5"):
+        start = start.moved_position(next(m for m in start.legal_moves() if oc.move_to_lan(m) == lan))
+    assert best[0] in [oc.move_to_lan(m) for m in start.legal_moves()]
+    kiwi = oc.ChessPosition.from_fen(KIWIPETE)
+    kiwi = kiwi.moved_position(next(m for m in kiwi.legal_moves() if oc.move_to_lan(m) == "e1g1"))
+    assert best[1] in [oc.move_to_lan(m) for m in kiwi.legal_moves()]
+    assert uci.options == {"Hash": "16"} and uci.last_stats["simulations"] == 20

@@ -204,3 +204,32 @@ def test_gpu_chess_selfplay_is_independent_of_scheduling():
             _, recs = SelfPlayRunner("chess", cfg).generate_data(nw, None, 64, keep_records=True)
             results.append([(r.game_idx, r.moves, r.winner, r.entries) for r in recs])
     assert results[1] == results[0] and results[2] == results[0]
+
+
+def test_gpu_uci_search_matches_oracle_player():
+    """`position` + `go` through cattus_b200_chess_search_* with the B200 evaluator behind it (per-leaf cattus_b200_eval),
+    against the oracle's MctsPlayer fed the same network's outputs; the second `go` reuses the first one's tree."""
+    import io
+
+    from cattus_b200.selfplay import ChessSearch
+    from cattus_b200.uci import UCI
+    from oracle import chess as oc
+    from tests.test_chess_cpu import KIWIPETE, _params, chess_cfg, chess_oracle_fn
+
+    cfg = chess_cfg(sim_num=200, prior_noise_alpha=0.03, prior_noise_epsilon=0.25, cache_size=100000, seed=4)
+    with make_network("chess_2x128", batch_size=8, n_streams=1) as nw:
+        player = om.MctsPlayer(_params(cfg), om.Evaluator(chess_oracle_fn(chess_gpu_net(nw)), om.ValueFuncCache(100000)), om.SplitMix64(om.game_seed(4, 0)))
+        history = [oc.ChessPosition.from_fen(KIWIPETE)]
+        moves = []
+        with ChessSearch(cfg, model=nw) as search:
+            for _ in range(3):
+                best, stats = search.go(KIWIPETE, moves)
+                want = player.choose_move_from_probabilities(history, player.calc_moves_probabilities(history))
+                assert best == oc.move_to_lan(want) and stats["simulations"] == 200 and stats["evaluations"] > 0
+                history.append(history[-1].moved_position(want))
+                reply = history[-1].legal_moves()[0]
+                history.append(history[-1].moved_position(reply))
+                moves += [best, oc.move_to_lan(reply)]
+        out = io.StringIO()
+        UCI(cfg, model=nw, out=out).run(io.StringIO("uci\nucinewgame\nposition startpos\ngo\nquit\n"))
+        assert any(ln.startswith("bestmove ") for ln in out.getvalue().split("\n"))
