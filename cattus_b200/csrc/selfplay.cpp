@@ -1244,11 +1244,21 @@ class Worker {
             // calc_moves_probs (net/mod.rs:106-119) gathers per legal move; the evaluator returns the probabilities compact in
             // ascending nn index, so child i takes the entry at the rank of its nn index among the legal ones
             const Move* mv = t.move16(leaf);
-            uint32_t order[256];
-            for (int32_t i = 0; i < count; ++i) order[i] = (static_cast<uint32_t>(R.nn_idx(mv[i])) << 8) | static_cast<uint32_t>(i);
-            std::sort(order, order + count);
+            constexpr int kWords = (Rules::kMovesNum + 63) / 64;
+            uint64_t bits[kWords] = {0};
+            uint16_t idx[256], before[kWords];
+            for (int32_t i = 0; i < count; ++i) {
+                idx[i] = static_cast<uint16_t>(R.nn_idx(mv[i]));
+                bits[idx[i] >> 6] |= 1ull << (idx[i] & 63);
+            }
+            uint16_t run = 0;
+            for (int w = 0; w < kWords; ++w) {
+                before[w] = run;
+                run = static_cast<uint16_t>(run + __builtin_popcountll(bits[w]));
+            }
             float* init = t.init_score(leaf);
-            for (int32_t r = 0; r < count; ++r) init[order[r] & 0xFF] = val[r];
+            for (int32_t i = 0; i < count; ++i)
+                init[i] = val[before[idx[i] >> 6] + __builtin_popcountll(bits[idx[i] >> 6] & ((1ull << (idx[i] & 63)) - 1))];
         } else {
         const u128 legal = R.legal_mask(s.leaf_eval_pos);
         std::memcpy(t.init_score(leaf), val, sizeof(float) * count);
