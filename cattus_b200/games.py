@@ -116,6 +116,30 @@ class ChessPosition:
         # the caller supplies nn indices for the side-to-move view, so the legal list is carried over unchanged
         return ChessPosition(tuple(out), self.legal, 3 - self.turn)
 
+    @staticmethod
+    def from_fen(fen: str, moves=()) -> "ChessPosition":
+        """ChessPosition::from_fen (chess/core.rs:170-172) followed by `moved_position` for each move (from | to << 6 |
+        promotion << 12, real board coordinates), through the library's chess rules (include/cattus_b200_chess.h)."""
+        import ctypes as C
+
+        from . import _lib
+
+        lib = _lib.load()
+        info = _lib.ChessInfo()
+        info.struct_size = C.sizeof(_lib.ChessInfo)
+        arr = (C.c_uint16 * max(1, len(moves)))(*moves)
+        if lib.cattus_b200_chess_position(fen.encode(), arr, len(moves), C.byref(info)) != 0:
+            raise ValueError((lib.cattus_b200_chess_last_error() or b"").decode(errors="replace"))
+        promo = (None, "q", "n", "r", "b")
+        view = ChessPosition(tuple(int(x) for x in info.planes), (), 1)  # the evaluator's view: side to move plays white
+        legal = []
+        for k in range(info.n_legal):
+            m = int(info.moves[k])
+            real = (m & 63, (m >> 6) & 63, promo[m >> 12])
+            legal.append((real if info.turn == 1 else ChessPosition.flip_move(real), int(info.nn_index[k])))
+        planes = view.planes if info.turn == 1 else view.flipped().planes
+        return ChessPosition(planes, tuple(legal), int(info.turn))
+
     def legal_moves(self):
         return [m for m, _ in self.legal]
 

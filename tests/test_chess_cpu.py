@@ -356,3 +356,20 @@ def test_uci_loop_commands():
     kiwi = kiwi.moved_position(next(m for m in kiwi.legal_moves() if oc.move_to_lan(m) == "e1g1"))
     assert best[1] in [oc.move_to_lan(m) for m in kiwi.legal_moves()]
     assert uci.options == {"Hash": "16"} and uci.last_stats["simulations"] == 20
+
+
+def test_host_mirror_position_from_fen_matches_oracle():
+    """cattus_b200.games.ChessPosition.from_fen: what CudaNetwork.evaluate needs (real planes, the legal moves of the
+    evaluated view with their nn indices), against the oracle for a white-to-move and a black-to-move position."""
+    from cattus_b200.games import ChessPosition
+
+    for fen, moves in ((KIWIPETE, []), (START, [oc.move_to_u16((12, 28, None))])):  # the second: after 1. e4, black to move
+        host = ChessPosition.from_fen(fen, moves)
+        p = oc.ChessPosition.from_fen(fen)
+        for m in moves:
+            p = p.moved_position(oc.move_from_u16(m))
+        assert host.turn == p.turn and list(host.planes) == p.planes()
+        view = p if p.turn == oc.P1 else p.flipped()
+        assert host.legal_moves() == view.legal_moves()
+        assert [host.move_to_nn_idx(m) for m in host.legal_moves()] == [oc.ChessPosition.to_nn_idx(m) for m in view.legal_moves()]
+        assert list((host if host.turn == 1 else host.flipped()).planes) == view.planes()
