@@ -219,15 +219,15 @@ SELFPLAY_CFG = {
 }
 
 
-def selfplay_max_moves(args) -> int:
+def selfplay_max_moves(args, game: str) -> int:
     if args.selfplay_max_moves >= 0:
         return args.selfplay_max_moves
-    return 16 if args.selfplay_game.startswith("chess") else 0
+    return 16 if game.startswith("chess") else 0
 
 
-def cpu_selfplay_max_moves(args) -> int:
+def cpu_selfplay_max_moves(args, game: str) -> int:
     """The CPU arm's bounded sample: a chess 10 x 128 leaf costs ~10 ms on one core, so one 600-simulation search per game."""
-    return 1 if args.selfplay_game.startswith("chess") else selfplay_max_moves(args)
+    return 1 if game.startswith("chess") else selfplay_max_moves(args, game)
 
 
 def runner_game(name: str) -> str:
@@ -331,7 +331,9 @@ def run_reference_arm(args, rank, world):
     }
     line["batch_sweep"] = cpu_batch_sweep(cfg)
     if not args.no_selfplay:
-        line["selfplay"] = time_cpu_selfplay(args.selfplay_game, 2, 2, cpu_selfplay_max_moves(args))
+        legs = [time_cpu_selfplay(g, 2, 2, cpu_selfplay_max_moves(args, g)) for g in args.selfplay_game]
+        line["selfplay"] = legs[0]
+        line["selfplay_others"] = legs[1:]
     print(json.dumps(line), flush=True)
 
 
@@ -349,8 +351,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-selfplay", action="store_true", help="skip the self-play sims/s leg")
     ap.add_argument("--no-other-workloads", action="store_true", help="skip the brief hex5 evals/s leg of the default run")
-    ap.add_argument("--selfplay-game", default="hex5", choices=sorted(SELFPLAY_CFG))
-    ap.add_argument("--selfplay-games", type=int, default=0, help="games per GPU in the self-play leg (0 = 8192; chess 16384)")
+    ap.add_argument("--selfplay-game", nargs="+", default=["hex5", "chess10x128"], choices=sorted(SELFPLAY_CFG),
+                    help="self-play legs: the first is reported as `selfplay` (BASELINE configs[1]), the rest under `selfplay_others` (configs[3])")
+    ap.add_argument("--selfplay-games", type=int, default=0, help="games per GPU in a self-play leg (0 = 8192; chess: one wave, threads x games per thread)")
     ap.add_argument("--selfplay-threads", type=int, default=0, help="worker threads per GPU (0 = host cores / GPUs)")
     ap.add_argument("--selfplay-gpt", type=int, default=0, help="concurrent games per worker thread (0 = 512; chess 1024)")
     ap.add_argument("--selfplay-groups", type=int, default=2, help="slot groups per worker thread (one batch in flight per group)")
@@ -518,22 +521,22 @@ def main():
                            "gpu_launches": int(olaunches)})
 
     # ---------------- self-play MCTS sims/s (second half of the BASELINE metric): C++ driver + this GPU's evaluator
-    selfplay = None
-    if not args.no_selfplay:
+    selfplay_legs = []
+    for sp_game in ([] if args.no_selfplay else args.selfplay_game):
         from cattus_b200.selfplay import SelfPlayRunner
 
-        sp_cfg = net.CONFIGS[args.selfplay_game]
+        sp_cfg = net.CONFIGS[sp_game]
         cores = len(os.sched_getaffinity(0))
         threads = args.selfplay_threads or max(1, cores // max(1, world))
         # chess leaves cost ~100x a hex leaf on the GPU: twice the games per worker keep its batches at ~430 positions
         chess_sp = sp_cfg.game == "chess"
         gpt = args.selfplay_gpt or (1024 if chess_sp else 512)
-        games_total = max(2, (args.selfplay_games or (16384 if chess_sp else 8192)) * world // 2 * 2)
-        mc = SELFPLAY_CFG[args.selfplay_game]
+        games_total = max(2, (args.selfplay_games or (threads * gpt if chess_sp else 8192)) * world // 2 * 2)
+        mc = SELFPLAY_CFG[sp_game]
         with CudaNetwork(export_blob(net.make_state_dict(sp_cfg, 0), sp_cfg.game), sp_cfg.game, device=local_rank, batch_size=max(64, min(4096, gpt)),
                          n_streams=max(4, min(32, threads * args.selfplay_groups)), precision="bf16") as sp_nw:
-            sp_max_moves = selfplay_max_moves(args)
-            runner = SelfPlayRunner(runner_game(args.selfplay_game), {"mcts": mc, "threads": threads, "games_per_thread": gpt,
+            sp_max_moves = selfplay_max_moves(args, sp_game)
+            runner = SelfPlayRunner(runner_game(sp_game), {"mcts": mc, "threads": threads, "games_per_thread": gpt,
                                                                        "groups_per_thread": args.selfplay_groups, "seed": 1, "max_moves": sp_max_moves})
             runner.generate_data(sp_nw, None, 2 * threads, first_game=rank, game_stride=world)  # warm-up (graphs, caches of the allocator)
             l0 = sp_nw.metrics()["model.kernel_launches"]
@@ -544,11 +547,11 @@ def main():
         m = summary["metrics"]
         sims_all = rep.sum_over_ranks(float(m["selfplay.simulations"]))
         secs = max_over_ranks(float(m["selfplay.seconds"]))
-        selfplay = selfplay_summary_to_dict(args.selfplay_game, mc, summary, games_total, threads, gpt, max_moves=sp_max_moves, extra={
+        selfplay = selfplay_summary_to_dict(sp_game, mc, summary, games_total, threads, gpt, max_moves=sp_max_moves, extra={
             "value": sims_all / secs, "n_gpus": world, "host_cores": cores, "gpu_launches": int(sp_launches),
             "note": "rank 0's counters shown; value = simulations of all ranks / max seconds; games partitioned by index across GPUs, no collective"})
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
-            selfplay["cpu_baseline"] = time_cpu_selfplay(args.selfplay_game, 2, 2, cpu_selfplay_max_moves(args))
+            selfplay["cpu_baseline"] = time_cpu_selfplay(sp_game, 2, 2, cpu_selfplay_max_moves(args, sp_game))
         if rank == 0 and args.single_search:
             with CudaNetwork(export_blob(net.make_state_dict(sp_cfg, 0), sp_cfg.game), sp_cfg.game, device=local_rank, batch_size=64, n_streams=1,
                              precision="bf16") as ss_nw:
@@ -567,13 +570,15 @@ def main():
                                                  "note": "UCI `go` at sim_num 10000: one tree, one leaf in flight (the reference's arrangement), per-leaf "
                                                          "cattus_b200_eval; cache hits are transpositions inside the one search"}
                 else:
-                    ss_sum, _ = SelfPlayRunner(args.selfplay_game, {"mcts": ss_mc, "threads": 1, "games_per_thread": 1, "leaf_queue": 1,
+                    ss_sum, _ = SelfPlayRunner(sp_game, {"mcts": ss_mc, "threads": 1, "games_per_thread": 1, "leaf_queue": 1,
                                                                     "seed": 1}).generate_data(ss_nw, None, 2)
                     sm = ss_sum["metrics"]
                     selfplay["single_search"] = {"sim_num": 10000, "searches": sm["selfplay.searches"],
                                                  "seconds_per_search": sm["selfplay.seconds"] / max(1, sm["selfplay.searches"]),
                                                  "sims_per_sec": sm["selfplay.sims_per_sec"], "evaluations": sm["selfplay.evaluations"],
                                                  "note": "one tree, one leaf in flight (the reference's UCI arrangement), per-leaf cattus_b200_eval"}
+        selfplay_legs.append(selfplay)
+    selfplay = selfplay_legs[0] if selfplay_legs else None
 
     total_positions = world * positions_per_step * args.steps
     value = total_positions / t_value
@@ -621,7 +626,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "positions/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": t_e2e / args.steps * 1e3, "api": "cattus_b200_eval_batch (host buffers -> pinned block -> H2D -> graph -> D2H)"},
-            "gpu_launches": int(launches) + (selfplay["gpu_launches"] if selfplay else 0) + sum(o["gpu_launches"] for o in others),
+            "gpu_launches": int(launches) + sum(leg["gpu_launches"] for leg in selfplay_legs) + sum(o["gpu_launches"] for o in others),
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "batch_sweep": sweep,
@@ -629,6 +634,7 @@ def main():
             "hbm_kernels": hbm_kernels,
             "other_workloads": others,
             "selfplay": selfplay,
+            "selfplay_others": selfplay_legs[1:],
         }
         print(json.dumps(line), flush=True)
     rep.close()
