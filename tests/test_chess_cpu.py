@@ -373,3 +373,17 @@ def test_host_mirror_position_from_fen_matches_oracle():
         assert host.legal_moves() == view.legal_moves()
         assert [host.move_to_nn_idx(m) for m in host.legal_moves()] == [oc.ChessPosition.to_nn_idx(m) for m in view.legal_moves()]
         assert list((host if host.turn == 1 else host.flipped()).planes) == view.planes()
+
+
+def test_chess_partition_by_stride_is_the_union():
+    """Multi-GPU arrangement (first_game = rank, game_stride = world): the ranks' games are exactly the whole job's."""
+    net = chess_fake_net("hash")
+    cfg = chess_cfg(sim_num=6, max_moves=10, prior_noise_alpha=0.3, prior_noise_epsilon=0.25, temperature_policy=[[9999, 1.0]])
+    _, whole = SelfPlayRunner("chess", cfg).run_with(chess_cb(net), None, 4, keep_records=True)
+    parts = []
+    for r in range(2):
+        _, p = SelfPlayRunner("chess", cfg).run_with(chess_cb(net), None, 4, keep_records=True, first_game=r, game_stride=2)
+        assert [x.game_idx for x in p] == [r, r + 2]
+        parts += p
+    parts.sort(key=lambda x: x.game_idx)
+    assert [(r.moves, r.entries) for r in parts] == [(r.moves, r.entries) for r in whole]
