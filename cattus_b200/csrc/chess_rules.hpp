@@ -425,6 +425,7 @@ struct ChessRules {
         for (; *c && *c != ' '; ++c) {
             if (*c == '/') {
                 if (file != 8) return "bad rank length";
+                if (rank == 0 && (c[1] == ' ' || c[1] == 0)) break;  // a trailing '/' (one of the reference's own fixtures has it)
                 rank -= 1;
                 file = 0;
             } else if (*c >= '1' && *c <= '8') {
@@ -441,6 +442,7 @@ struct ChessRules {
             }
         }
         if (rank != 0 || file != 8) return "bad piece placement";
+        if (*c == '/') ++c;
         while (*c == ' ') ++c;
         if (*c != 'w' && *c != 'b') return "bad side to move";
         const bool black = *c == 'b';

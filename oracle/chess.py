@@ -98,7 +98,7 @@ class ChessPosition:
     def from_fen(fen: str) -> "ChessPosition":
         fields = fen.split()
         board: List[Optional[str]] = [None] * 64
-        for i, row in enumerate(fields[0].split("/")):
+        for i, row in enumerate(fields[0].rstrip("/").split("/")):
             rank, file = 7 - i, 0
             for ch in row:
                 if ch.isdigit():

@@ -145,6 +145,31 @@ def test_reference_fixture_positions_end_to_end():
                 assert np.abs(np.array([p for _, p in mp]) - op[0]).max() <= tol and abs(val - ov[0]) <= tol
 
 
+def test_reference_chess_fixture_positions_end_to_end():
+    """The 5 chess positions of training/tests/test_net_output.py:198-204 from their FENs: the library's chess rules give
+    planes, legal moves and policy indices (cattus_b200.games.ChessPosition.from_fen), evaluate() runs the net; checked
+    against the oracle's rules (oracle/chess.py) + the oracle net, both precisions, the reference test's 1 x 1 net."""
+    from cattus_b200.games import ChessPosition
+    from oracle import chess as oc
+    from oracle.gen_golden import CHESS_FIXTURES
+
+    for precision, tol in (("fp32-check", TOL_FP32), ("bf16", TOL_BF16)):
+        with make_network("chess_1x1", precision=precision, batch_size=8) as nw:
+            for fen in CHESS_FIXTURES + ["rnbqkbnr/pppp1ppp/8/8/4pP2/8/PPPPP1PP/RNBQKBNR b KQkq f3 0 2"]:  # + black to move, en passant
+                mp, val = nw.evaluate(ChessPosition.from_fen(fen))
+                p = oc.ChessPosition.from_fen(fen)
+                view = p if p.turn == oc.P1 else p.flipped()
+                moves = view.legal_moves()
+                nn = [oc.ChessPosition.to_nn_idx(m) for m in moves]
+                _, ov, op = oracle_eval("chess_1x1", np.array([view.planes()], dtype=np.uint64), [sorted(nn)])
+                rank = {idx: k for k, idx in enumerate(sorted(nn))}
+                want = [op[0][rank[i]] for i in nn]
+                real = moves if p.turn == oc.P1 else [oc.ChessPosition.flip_move(m) for m in moves]
+                assert [m for m, _ in mp] == real
+                assert np.abs(np.array([q for _, q in mp]) - np.array(want)).max() <= tol
+                assert abs(val - (ov[0] if p.turn == oc.P1 else -ov[0])) <= tol
+
+
 def test_flip_path_player2_to_move():
     """Not covered by any reference parity test: blue to move -> planes [T(blue), T(red), ones],
     moves transposed back, value negated (hex/core.rs:324-334, :36-38; net/mod.rs:166-182)."""
