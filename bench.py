@@ -360,7 +360,9 @@ def main():
     ap.add_argument("--selfplay-max-moves", type=int, default=-1,
                     help="stop self-play games after this many moves (0 = play to the end as the reference does; default: 0 for hex, 16 for chess, "
                          "whose random-net games run for hundreds of moves)")
-    ap.add_argument("--single-search", action="store_true",
+    ap.add_argument("--no-single-search", dest="single_search", action="store_false",
+                    help="skip the one-tree search at sim_num 10000 (BASELINE configs[4]) that each self-play leg adds")
+    ap.add_argument("--single-search", action="store_true", default=True,
                     help="also time ONE tree searching with --sim-num 10000 (BASELINE configs[4]'s UCI setting, on the self-play game): "
                          "two games, one thread, one leaf at a time through cattus_b200_eval")
     args = ap.parse_args()

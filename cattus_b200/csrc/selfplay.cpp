@@ -1,10 +1,11 @@
 // Self-play driver: the caller side of the evaluation path (include/cattus_b200_selfplay.h).
 //
 // Restates, in host C++, the reference's MctsPlayer (engine/src/mcts/mod.rs:105-454), the Hex / TicTacToe rules
-// (engine/src/hex/core.rs:112-335, engine/src/ttt/core.rs:101-246), NNetwork::evaluate's flip + ValueFuncCache
-// (engine/src/net/mod.rs:74-87,158-182; engine/src/mcts/cache.rs:31-75), the self-play game loop
-// (training/self-play/src/self_play.rs:94-276) and the .traindata writers (self_play.rs:33-61, serialize/hex.rs:16-28,
-// serialize/ttt.rs:17-22).  The oracle it is tested against is oracle/mcts.py.
+// (engine/src/hex/core.rs:112-335, engine/src/ttt/core.rs:101-246; chess: chess_rules.hpp), NNetwork::evaluate's flip +
+// ValueFuncCache (engine/src/net/mod.rs:74-87,158-182; engine/src/mcts/cache.rs:31-75), the self-play game loop
+// (training/self-play/src/self_play.rs:94-276), the .traindata writers (self_play.rs:33-61, serialize/hex.rs:16-28,
+// serialize/ttt.rs:17-22, serialize/chess.rs:18-57) and the player behind the UCI loop (engine/src/chess/uci.rs).  The
+// oracles it is tested against are oracle/mcts.py and oracle/chess.py.
 //
 // B200-first arrangement: a worker thread advances `games_per_thread` games as state machines.  Each game runs its
 // simulations strictly in the reference's order (select -> evaluate -> expand -> backpropagate, one leaf in flight per
