@@ -49,7 +49,7 @@ class SelfPlayCfg(C.Structure):
         ("cache_size", C.c_uint32), ("threads", C.c_uint32), ("games_per_thread", C.c_uint32), ("leaf_queue", C.c_uint32),
         ("games_num", C.c_uint32), ("first_game", C.c_uint32), ("game_stride", C.c_uint32), ("seed", C.c_uint64),
         ("out_dir1", C.c_char_p), ("out_dir2", C.c_char_p), ("keep_records", C.c_uint32), ("groups_per_thread", C.c_uint32),
-        ("max_moves", C.c_uint32), ("reserved", C.c_uint32),
+        ("max_moves", C.c_uint32), ("speculate", C.c_uint32),
     ]
 
 
@@ -65,7 +65,7 @@ class SelfPlaySummary(C.Structure):
 class ChessSearchStats(C.Structure):
     """cattus_b200_chess_search_stats (include/cattus_b200_selfplay.h)."""
     _fields_ = [
-        ("struct_size", C.c_uint32), ("root_children", C.c_uint32), ("best_visits", C.c_uint32), ("reserved", C.c_uint32),
+        ("struct_size", C.c_uint32), ("root_children", C.c_uint32), ("best_visits", C.c_uint32), ("speculative_evaluations", C.c_uint32),
         ("simulations", C.c_uint64), ("evaluations", C.c_uint64), ("cache_hits", C.c_uint64), ("terminal_leaves", C.c_uint64),
         ("seconds", C.c_double),
     ]

@@ -719,8 +719,13 @@ class Worker {
     struct SearchStats {
         uint64_t simulations = 0, evaluations = 0, cache_hits = 0, terminal = 0;
         double seconds = 0.0;
-        uint32_t root_visits_best = 0, root_children = 0;
+        uint32_t root_visits_best = 0, root_children = 0, speculative = 0;
     };
+    // Search sessions only: while a leaf waits for the network, up to `rows` more positions ride in the same evaluator call
+    // and land in the cache -- the best-prior unvisited children of recently expanded nodes, which is where the next visits
+    // of those nodes go (all their children have n = 0, so select picks the largest prior).  The cache returns exactly what
+    // a fresh evaluation returns (the evaluator is batch invariant), so the search is unchanged; only its waiting is.
+    void set_speculation(uint32_t rows) { speculate_ = rows; }
     void reseed(uint64_t seed) { slots_[0].rng = SplitMix64(game_seed(seed, 0)); }
     bool search_from(const std::vector<Pos>& history, Move* best, SearchStats* stats) {
         Slot& s = slots_[0];
@@ -735,11 +740,16 @@ class Worker {
         begin_search(s);
         s.phase = kSimulate;
         s.sel_node = -1;
+        spec_queue_.clear();  // block offsets of the previous tree
+        spec_head_ = 0;
+        spec_rows_ = 0;
         Group& gr = groups_[0];
         while (s.phase != kStartMove) {
-            if (!step(0))  // parked on the evaluator: evaluate now (one leaf in flight, like the reference)
+            if (!step(0)) {  // parked on the evaluator: evaluate now (one leaf in flight, like the reference)
+                add_speculative_rows(s, gr);
                 for (int e = 0; e < 2; ++e)
                     if (!gr.pend[e].keys.empty()) send(gr, e);
+            }
         }
         if (sh_.failed.load()) return false;
         *best = static_cast<Move>(s.rec.moves.back());
@@ -754,6 +764,7 @@ class Worker {
             float top = 0.0f;
             for (auto& mp : probs) top = std::max(top, mp.second);
             stats->root_visits_best = static_cast<uint32_t>(top * static_cast<float>(params_[0].sim_num) + 0.5f);
+            stats->speculative = spec_rows_;
         }
         return true;
     }
@@ -843,6 +854,7 @@ class Worker {
                 return true;
             }
             s.path.clear();  // select (mod.rs:199-231) starts at the root
+            sim_cands_.clear();
             s.prepared_leaf = -1;
             s.sel_node = t.root;
             prefetch_block(t, t.root, t.hdr(t.root).count);
@@ -860,6 +872,15 @@ class Worker {
         }
         const int32_t count = nd.count;
         const int32_t best = select_child(t.init_score(node), t.score_w(node), t.simulations_n(node), count, params_[s.cur].explore_factor, sel_);
+        if constexpr (kChess) {
+            if (speculate_) {  // the best-scoring child of this node that has no node yet, other than the one taken: a likely next leaf
+                const uint32_t* ed = t.edge(node);
+                int32_t alt = -1;
+                for (int32_t i = 0; i < count; ++i)
+                    if (i != best && TreeT::edge_child(ed[i]) < 0 && (alt < 0 || sel_[i] > sel_[alt])) alt = i;
+                if (alt >= 0) sim_cands_.emplace_back(node, alt);
+            }
+        }
         int32_t c = TreeT::edge_child(t.edge(node)[best]);
         if (c < 0) {
             c = materialise(t, node, best);
@@ -1276,6 +1297,22 @@ class Worker {
         }
         t.hdr(leaf).expanded = 1;
         if (leaf == t.root) add_dirichlet_noise(s, t, leaf);
+        if constexpr (kChess) {
+            if (speculate_ && count > 0) {  // remember this node's two best-prior children as candidates to evaluate ahead
+                const float* init = t.init_score(leaf);
+                int32_t a = 0, b = -1;
+                for (int32_t i = 1; i < count; ++i) {
+                    if (init[i] > init[a]) {
+                        b = a;
+                        a = i;
+                    } else if (b < 0 || init[i] > init[b]) {
+                        b = i;
+                    }
+                }
+                spec_queue_.emplace_back(leaf, a);
+                if (b >= 0) spec_queue_.emplace_back(leaf, b);
+            }
+        }
         float v = val[count];
         if (s.leaf_flipped) v = -v;
         backpropagate(s, t, v);
@@ -1359,6 +1396,55 @@ class Worker {
         } else {
             s.rec.moves.push_back(mv);
             s.history.push_back(R.moved(s.history.back(), mv));
+        }
+    }
+
+    // Appends up to `speculate_` candidate positions to the batch about to be sent; nobody is parked on those rows, so
+    // finish_batch only stores them in the cache.
+    void add_speculative_rows(Slot& s, Group& gr) {
+        if constexpr (kChess) {
+            Evaluator& ev = *evals_[s.cur];
+            if (!speculate_ || !ev.cache) return;
+            TreeT& t = s.players[s.cur].tree;
+            Pending& pb = gr.pend[0];
+            if (pb.keys.empty()) return;
+            uint32_t added = 0;
+            size_t sim_next = 0;
+            while (added < speculate_ && (sim_next < sim_cands_.size() || spec_head_ < spec_queue_.size())) {
+                // first the runner-up children along this simulation's path (deepest last), then the best-prior children of
+                // the nodes expanded before
+                const std::pair<int32_t, int32_t> cand = sim_next < sim_cands_.size() ? sim_cands_[sim_next++] : spec_queue_[spec_head_++];
+                if (TreeT::edge_child(t.edge(cand.first)[cand.second]) >= 0) continue;  // visited in the meantime
+                Pos child = R.moved(t.hdr(cand.first).pos, t.move16(cand.first)[cand.second]);
+                Move buf[256];
+                const int n = R.children(child, buf);
+                if (n == 0) continue;  // a finished position is never evaluated
+                uint64_t q[4];
+                R.key_planes(child, q);
+                const PosKey key{static_cast<u128>(q[0]) | (static_cast<u128>(q[1]) << 64), static_cast<u128>(q[2]) | (static_cast<u128>(q[3]) << 64)};
+                if (ev.cache->find(key, n, val_.data())) continue;
+                if (pb.find_or_reserve(key) >= 0) continue;
+                pb.keys.push_back(key);
+                uint64_t pl[Rules::kPlanes];
+                R.planes(child, pl);
+                pb.planes.insert(pb.planes.end(), pl, pl + Rules::kPlanes);
+                const size_t at = pb.legal.size();
+                pb.legal.resize(at + Rules::kLegalBytes, 0);
+                for (int k = 0; k < n; ++k) {
+                    const int idx = R.nn_idx(buf[k]);
+                    pb.legal[at + (idx >> 3)] |= static_cast<uint8_t>(1u << (idx & 7));
+                }
+                pb.n_legal.push_back(static_cast<uint8_t>(n));
+                ++added;
+            }
+            spec_rows_ += added;
+            if (spec_head_ == spec_queue_.size()) {
+                spec_queue_.clear();
+                spec_head_ = 0;
+            }
+        } else {
+            (void)s;
+            (void)gr;
         }
     }
 
@@ -1484,6 +1570,10 @@ class Worker {
     std::vector<Slot> slots_;
     std::vector<Group> groups_;
     std::vector<std::vector<uint32_t>> pool_free_;  // retired tree buffers, reused by the next tree copy
+    uint32_t speculate_ = 0, spec_rows_ = 0;              // search sessions: rows evaluated ahead per call / so far in this search
+    std::vector<std::pair<int32_t, int32_t>> spec_queue_;  // (node block, child index) candidates of the current tree
+    std::vector<std::pair<int32_t, int32_t>> sim_cands_;   // candidates seen along the simulation in progress
+    size_t spec_head_ = 0;
     std::deque<std::pair<uint32_t, int>> inflight_;  // (group, evaluator) of this worker's batches in flight, oldest first
     int abi_wpp_ = 1;
     double eval_wait_ = 0.0;
@@ -1758,6 +1848,7 @@ static int chess_search_create_impl(cattus_b200_eval_fn fn, void* ctx, cattus_b2
         s->evals[0] = s->evals[1] = &s->ev;
         s->worker.reset(new sp::Worker<sp::ChessRules>(s->rules, s->cfg, s->params, s->evals, s->sh));
         s->worker->reseed(cfg->seed);
+        s->worker->set_speculation(cfg->speculate);
         *out = s.release();
         g_sp_error.clear();
         return CATTUS_B200_OK;
@@ -1823,6 +1914,7 @@ int cattus_b200_chess_search_go(cattus_b200_chess_search_t* s, const char* fen, 
             stats->seconds = st.seconds;
             stats->root_children = st.root_children;
             stats->best_visits = st.root_visits_best;
+            stats->speculative_evaluations = st.speculative;
         }
         g_sp_error.clear();
         return CATTUS_B200_OK;

@@ -113,6 +113,7 @@ class SelfPlayRunner:
         c.leaf_queue = int(cfg.get("leaf_queue", 0))
         c.groups_per_thread = int(cfg.get("groups_per_thread", 0))
         c.max_moves = int(cfg.get("max_moves", 0))
+        c.speculate = int(cfg.get("speculate", 0))
         c.seed = int(cfg.get("seed", 0)) & 0xFFFFFFFFFFFFFFFF
         self._c = c
 
@@ -257,7 +258,7 @@ class ChessSearch:
         _check(self._lib, rc)
         return move_to_lan(best.value), {"simulations": st.simulations, "evaluations": st.evaluations, "cache_hits": st.cache_hits,
                                          "terminal_leaves": st.terminal_leaves, "seconds": st.seconds, "root_children": st.root_children,
-                                         "best_visits": st.best_visits}
+                                         "best_visits": st.best_visits, "speculative_evaluations": st.speculative_evaluations}
 
     def close(self):
         if self._h:

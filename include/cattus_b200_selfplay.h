@@ -70,7 +70,10 @@ typedef struct cattus_b200_selfplay_cfg {
                                  * the next group (0 or 1 = one group; > 1 needs the B200 evaluator) */
     uint32_t max_moves; /* 0 (the reference): play every game to its end.  > 0: stop a game after this many moves and
                          * record it as a draw -- for benches and tools that need a bounded amount of work */
-    uint32_t reserved;
+    uint32_t speculate; /* cattus_b200_chess_search_* only (needs cache_size > 0): while a leaf waits for the network, up to
+                         * this many more positions ride in the same evaluator call and land in the cache -- the best-prior
+                         * unvisited children of recently expanded nodes.  The search itself is unchanged (the cache
+                         * returns what a fresh evaluation would); 0 = off, as the reference */
 } cattus_b200_selfplay_cfg;
 
 /* Mirrors the summary file (self_play_cmd.rs:131-149) and the metric keys the trainer reads
@@ -130,7 +133,7 @@ typedef struct cattus_b200_chess_search_stats {
     uint32_t struct_size;
     uint32_t root_children;  /* legal moves of the searched position */
     uint32_t best_visits;    /* simulations that went through the most visited root child */
-    uint32_t reserved;
+    uint32_t speculative_evaluations; /* of `evaluations`: positions evaluated ahead into the cache (cfg.speculate) */
     uint64_t simulations, evaluations, cache_hits, terminal_leaves; /* of this search */
     double seconds;
 } cattus_b200_chess_search_stats;

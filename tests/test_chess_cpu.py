@@ -387,3 +387,40 @@ def test_chess_partition_by_stride_is_the_union():
         parts += p
     parts.sort(key=lambda x: x.game_idx)
     assert [(r.moves, r.entries) for r in parts] == [(r.moves, r.entries) for r in whole]
+
+
+def test_speculative_evaluation_does_not_change_the_search():
+    """cfg.speculate: extra positions ride along with the waiting leaf and only land in the cache, so the chosen moves
+    and the simulation counts are those of the plain search; fewer evaluator CALLS are needed for the same search."""
+    from cattus_b200.selfplay import ChessSearch
+
+    net = chess_fake_net("hash")
+    calls = {"plain": 0, "spec": 0}
+
+    def counting(tag):
+        inner = chess_cb(net)
+
+        def cb(words, n, legal):
+            calls[tag] += 1
+            return inner(words, n, legal)
+
+        return cb
+
+    base = dict(sim_num=300, prior_noise_alpha=0.3, prior_noise_epsilon=0.25, cache_size=100000, seed=8)
+    moves, out = [], {}
+    for tag, speculate in (("plain", 0), ("spec", 7)):
+        got = []
+        with ChessSearch(chess_cfg(speculate=speculate, **base), eval_fn=counting(tag)) as search:
+            played = []
+            for _ in range(3):
+                best, stats = search.go(KIWIPETE, played)
+                got.append((best, stats["simulations"], stats["terminal_leaves"]))
+                played = played + [best]
+                reply = oc.ChessPosition.from_fen(KIWIPETE)
+                for lan in played:
+                    reply = reply.moved_position(next(m for m in reply.legal_moves() if oc.move_to_lan(m) == lan))
+                played.append(oc.move_to_lan(reply.legal_moves()[0]))
+            out[tag] = (got, stats)
+    assert out["plain"][0] == out["spec"][0]
+    assert out["plain"][1]["speculative_evaluations"] == 0 and out["spec"][1]["speculative_evaluations"] > 0
+    assert calls["spec"] < 0.8 * calls["plain"], calls

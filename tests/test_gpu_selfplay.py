@@ -233,3 +233,24 @@ def test_gpu_uci_search_matches_oracle_player():
         out = io.StringIO()
         UCI(cfg, model=nw, out=out).run(io.StringIO("uci\nucinewgame\nposition startpos\ngo\nquit\n"))
         assert any(ln.startswith("bestmove ") for ln in out.getvalue().split("\n"))
+
+
+def test_gpu_uci_speculation_same_moves_fewer_round_trips():
+    """cfg.speculate on the real evaluator: likely next leaves ride along with the waiting leaf into the cache.  The
+    evaluator is batch invariant, so every `go` must return the move of the plain search."""
+    from cattus_b200.selfplay import ChessSearch
+    from tests.test_chess_cpu import KIWIPETE, chess_cfg
+
+    base = dict(sim_num=600, prior_noise_alpha=0.03, prior_noise_epsilon=0.25, cache_size=100000, seed=6)
+    results = {}
+    for speculate in (0, 7):
+        with make_network("chess_2x128", batch_size=8, n_streams=1) as nw:
+            with ChessSearch(chess_cfg(speculate=speculate, **base), model=nw) as search:
+                moves, out = [], []
+                for _ in range(3):
+                    best, stats = search.go(KIWIPETE, moves)
+                    out.append((best, stats["simulations"], stats["terminal_leaves"]))
+                    moves = moves + [best]
+                results[speculate] = (out, stats, nw.metrics()["model.activation_count"])
+    assert results[0][0] == results[7][0]
+    assert results[7][1]["speculative_evaluations"] > 0 and results[7][2] < 0.8 * results[0][2]
