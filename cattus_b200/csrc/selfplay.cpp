@@ -725,7 +725,11 @@ class Worker {
     // and land in the cache -- the best-prior unvisited children of recently expanded nodes, which is where the next visits
     // of those nodes go (all their children have n = 0, so select picks the largest prior).  The cache returns exactly what
     // a fresh evaluation returns (the evaluator is batch invariant), so the search is unchanged; only its waiting is.
-    void set_speculation(uint32_t rows) { speculate_ = rows; }
+    void set_speculation(uint32_t rows) {
+        speculate_ = std::min<uint32_t>(rows, 255);
+        for (Group& gr : groups_)  // the in-batch dedupe tables must hold the extra rows too
+            for (Pending& pb : gr.pend) pb.init(gr.count + speculate_);
+    }
     void reseed(uint64_t seed) { slots_[0].rng = SplitMix64(game_seed(seed, 0)); }
     bool search_from(const std::vector<Pos>& history, Move* best, SearchStats* stats) {
         Slot& s = slots_[0];
@@ -873,12 +877,20 @@ class Worker {
         const int32_t count = nd.count;
         const int32_t best = select_child(t.init_score(node), t.score_w(node), t.simulations_n(node), count, params_[s.cur].explore_factor, sel_);
         if constexpr (kChess) {
-            if (speculate_) {  // the best-scoring child of this node that has no node yet, other than the one taken: a likely next leaf
+            if (speculate_) {  // the best-scoring children of this node that have no node yet, other than the one taken: likely next leaves
                 const uint32_t* ed = t.edge(node);
-                int32_t alt = -1;
-                for (int32_t i = 0; i < count; ++i)
-                    if (i != best && TreeT::edge_child(ed[i]) < 0 && (alt < 0 || sel_[i] > sel_[alt])) alt = i;
-                if (alt >= 0) sim_cands_.emplace_back(node, alt);
+                int32_t alt[kSpecPerLevel];
+                int n_alt = 0;
+                for (int32_t i = 0; i < count; ++i) {
+                    if (i == best || TreeT::edge_child(ed[i]) >= 0) continue;
+                    int at = n_alt;  // insertion into the short list sorted by descending score
+                    while (at > 0 && sel_[i] > sel_[alt[at - 1]]) --at;
+                    if (at >= kSpecPerLevel) continue;
+                    for (int k = std::min(n_alt, kSpecPerLevel - 1); k > at; --k) alt[k] = alt[k - 1];
+                    alt[at] = i;
+                    n_alt = std::min(n_alt + 1, kSpecPerLevel);
+                }
+                for (int k = 0; k < n_alt; ++k) sim_cands_.push_back({node, alt[k], k});
             }
         }
         int32_t c = TreeT::edge_child(t.edge(node)[best]);
@@ -1410,10 +1422,17 @@ class Worker {
             if (pb.keys.empty()) return;
             uint32_t added = 0;
             size_t sim_next = 0;
+            // first the runner-up children along this simulation's path (every level's best before any level's second best),
+            // then the best-prior children of the nodes expanded before
+            std::stable_sort(sim_cands_.begin(), sim_cands_.end(), [](const SimCand& a, const SimCand& b) { return a.rank < b.rank; });
             while (added < speculate_ && (sim_next < sim_cands_.size() || spec_head_ < spec_queue_.size())) {
-                // first the runner-up children along this simulation's path (deepest last), then the best-prior children of
-                // the nodes expanded before
-                const std::pair<int32_t, int32_t> cand = sim_next < sim_cands_.size() ? sim_cands_[sim_next++] : spec_queue_[spec_head_++];
+                std::pair<int32_t, int32_t> cand;
+                if (sim_next < sim_cands_.size()) {
+                    cand = {sim_cands_[sim_next].node, sim_cands_[sim_next].child};
+                    ++sim_next;
+                } else {
+                    cand = spec_queue_[spec_head_++];
+                }
                 if (TreeT::edge_child(t.edge(cand.first)[cand.second]) >= 0) continue;  // visited in the meantime
                 Pos child = R.moved(t.hdr(cand.first).pos, t.move16(cand.first)[cand.second]);
                 Move buf[256];
@@ -1572,7 +1591,12 @@ class Worker {
     std::vector<std::vector<uint32_t>> pool_free_;  // retired tree buffers, reused by the next tree copy
     uint32_t speculate_ = 0, spec_rows_ = 0;              // search sessions: rows evaluated ahead per call / so far in this search
     std::vector<std::pair<int32_t, int32_t>> spec_queue_;  // (node block, child index) candidates of the current tree
-    std::vector<std::pair<int32_t, int32_t>> sim_cands_;   // candidates seen along the simulation in progress
+    struct SimCand {
+        int32_t node, child;
+        int rank;  // 0: the node's best unvisited alternative, 1: its second best, ...
+    };
+    static constexpr int kSpecPerLevel = 4;
+    std::vector<SimCand> sim_cands_;  // candidates seen along the simulation in progress
     size_t spec_head_ = 0;
     std::deque<std::pair<uint32_t, int>> inflight_;  // (group, evaluator) of this worker's batches in flight, oldest first
     int abi_wpp_ = 1;
@@ -1844,7 +1868,10 @@ static int chess_search_create_impl(cattus_b200_eval_fn fn, void* ctx, cattus_b2
         s->ev.fn = fn;
         s->ev.ctx = ctx;
         s->ev.leaf_handle = leaf_handle;
-        if (cfg->cache_size) s->ev.cache.reset(new sp::Cache(cfg->cache_size, sp::ChessRules::kMaxMoves));
+        // One tree fills the table slowly (<= sim_num entries per search), and every entry of a table sized for a million
+        // positions would land on a fresh page: most of a search's host time went into page faults.  128 Ki entries hold the
+        // last dozen searches; a smaller cache only changes hit rates, never results.
+        if (cfg->cache_size) s->ev.cache.reset(new sp::Cache(std::min<uint32_t>(cfg->cache_size, 1u << 17), sp::ChessRules::kMaxMoves));
         s->evals[0] = s->evals[1] = &s->ev;
         s->worker.reset(new sp::Worker<sp::ChessRules>(s->rules, s->cfg, s->params, s->evals, s->sh));
         s->worker->reseed(cfg->seed);

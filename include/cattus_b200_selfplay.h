@@ -124,7 +124,7 @@ void cattus_b200_selfplay_free(cattus_b200_selfplay_t* r);
 /* ---- one chess search at a time: the player behind the reference's UCI loop (engine/src/chess/uci.rs) ----
  * create = `ucinewgame` (MctsPlayer::new, uci.rs:59); the mcts.* fields, cache_size and seed of cfg are used.
  * go     = `position ...` + `go` (uci.rs:76-93, :158-161): the history is the FEN's position (NULL: the start position)
- *          followed by one position per move; GamePlayer::next_move(pos_history) (mcts/mod.rs:448-454) searches with one
+ *          followed by one position per move (the cache holds at most 128 Ki entries here); GamePlayer::next_move(pos_history) (mcts/mod.rs:448-454) searches with one
  *          leaf in flight (per-leaf cattus_b200_eval), reusing the tree of the previous `go` when the new position is
  *          in it (mod.rs:335-352).  Moves are from | to << 6 | promotion << 12 in real board coordinates
  *          (include/cattus_b200_chess.h). */

@@ -92,7 +92,7 @@ int main(int argc, char** argv) {
     cfg.n_temperatures = 2;
     cfg.prior_noise_alpha = 0.03f;
     cfg.prior_noise_epsilon = 0.25f;
-    cfg.cache_size = 1000000;
+    cfg.cache_size = std::getenv("CACHE") ? std::atoi(std::getenv("CACHE")) : 1000000;
     cfg.game_stride = 1;
     cfg.seed = 1;
     cattus_b200_selfplay_t* res = nullptr;
