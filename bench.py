@@ -563,7 +563,7 @@ def main():
                     from cattus_b200.selfplay import ChessSearch
 
                     per = []
-                    for speculate in (0, 15):
+                    for speculate in (0, 31):
                         for fen in (None, "r3k2r/p1ppqpb1/bn2pnp1/3PN3/1p2P3/2N2Q1p/PPPBBPPP/R3K2R w KQkq -"):
                             with ChessSearch({"mcts": ss_mc, "seed": 1, "speculate": speculate}, model=ss_nw) as search:
                                 best, st = search.go(fen, [])
@@ -574,8 +574,8 @@ def main():
                     selfplay["single_search"] = {"sim_num": 10000, "searches": per,
                                                  "seconds_per_search": float(np.mean([p["seconds"] for p in per if p["speculate"] == 0])),
                                                  "seconds_per_search_speculating": float(np.mean([p["seconds"] for p in per if p["speculate"]])),
-                                                 "note": "UCI `go` at sim_num 10000: one tree, one leaf in flight (the reference's arrangement); speculate = 15 lets "
-                                                         "up to 15 likely next leaves ride in the same evaluator call into the cache (same moves, fewer round "
+                                                 "note": "UCI `go` at sim_num 10000: one tree, one leaf in flight (the reference's arrangement); speculate = 31 lets "
+                                                         "up to 31 likely next leaves ride in the same evaluator call into the cache (same moves, fewer round "
                                                          "trips); cache hits without speculation are transpositions inside the one search"}
                 else:
                     ss_sum, _ = SelfPlayRunner(sp_game, {"mcts": ss_mc, "threads": 1, "games_per_thread": 1, "leaf_queue": 1,

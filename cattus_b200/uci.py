@@ -9,9 +9,9 @@ the `StockfishNet` placeholder it is built with today (cattus.rs:57-64; SURVEY.m
 "threads"}; `model.model_path` is a `.cb2` blob (cattus_b200.export) and `model.inference` may carry
 {"engine": "cuda-b200", "device": 0, "precision": "bf16"}.
 
-`speculate` (top-level key, default 15; 0 = the reference's behaviour) lets up to that many likely next leaves ride along
+`speculate` (top-level key, default 31; 0 = the reference's behaviour) lets up to that many likely next leaves ride along
 with the leaf the search is waiting for; they only land in the value-function cache, so the moves played are unchanged
-and a `go` needs about half the evaluator round trips.
+and a `go` needs about an eighth of the evaluator round trips.
 
 Commands handled as in uci.rs:27-73: uci, isready, setoption, ucinewgame, position [fen <FEN> | startpos] [moves ...],
 go (its arguments are parsed and ignored, as there), stop, quit.  One MctsPlayer per game: the tree of the previous
@@ -51,7 +51,7 @@ def parse_args(args: List[str], keys) -> dict:
 class UCI:
     def __init__(self, cfg: dict, model=None, eval_fn=None, out: TextIO = sys.stdout):
         cfg = dict(cfg)
-        cfg.setdefault("speculate", 15 if (cfg.get("mcts") or {}).get("cache_size") else 0)
+        cfg.setdefault("speculate", 31 if (cfg.get("mcts") or {}).get("cache_size") else 0)
         self.cfg = cfg
         self.model = model
         self.eval_fn = eval_fn
