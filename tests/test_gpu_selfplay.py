@@ -254,3 +254,39 @@ def test_gpu_uci_speculation_same_moves_fewer_round_trips():
                 results[speculate] = (out, stats, nw.metrics()["model.activation_count"])
     assert results[0][0] == results[7][0]
     assert results[7][1]["speculative_evaluations"] > 0 and results[7][2] < 0.8 * results[0][2]
+
+
+def test_self_player_cli_chess(tmp_path):
+    """The self-play executable's command line for chess (training/self-play/src/self_play_cmd.rs:14-31 with
+    ChessSerializer, serialize/chess.rs:18-57): 1280-byte entries that the trainer's parser layout accepts
+    (cattus_train/chess.py:22-49: 18 planes | 235-byte bitmap | 225 probabilities | winner)."""
+    import json
+    import struct
+
+    from cattus_b200 import self_player
+    from tests.util import blob
+
+    model = tmp_path / "model.cb2"
+    model.write_bytes(blob("chess_dev"))
+    cfg = {"mcts": {"sim_num": 20, "explore_factor": 1.41421, "temperature_policy": [[30, 1.0], [9999, 0.0]], "prior_noise_alpha": 0.03,
+                    "prior_noise_epsilon": 0.25, "cache_size": 1000},
+           "model": {"batch_size": 1, "inference": {"engine": "cuda-b200"}}, "threads": 2, "max_moves": 6}
+    (tmp_path / "config.json").write_text(json.dumps(cfg))
+    out = tmp_path / "games"
+    summary_file = tmp_path / "summary.json"
+    assert self_player.main([f"--model1-path={model}", f"--model2-path={model}", "--games-num=4", f"--out-dir1={out}", f"--out-dir2={out}",
+                             f"--summary-file={summary_file}", f"--config-file={tmp_path / 'config.json'}"]) == 0
+    s = json.loads(summary_file.read_text())
+    assert s["player1_wins"] + s["player2_wins"] + s["draws"] == 4
+    files = sorted(out.rglob("*.traindata"))
+    assert len(files) == s["metrics"]["selfplay.searches"] == 24
+    for f in files:
+        e = f.read_bytes()
+        assert len(e) == 18 * 8 + 235 + 225 * 4 + 1
+        planes = struct.unpack("<18Q", e[:144])
+        bitmap = np.frombuffer(e[144:379], dtype=np.uint8)
+        probs = np.frombuffer(e[379:1279], dtype="<f4")
+        n_legal = int(np.unpackbits(bitmap).sum())
+        assert planes[17] == 0xFFFFFFFFFFFFFFFF and bin(planes[5]).count("1") == 1 and bin(planes[11]).count("1") == 1  # one king each
+        assert (probs[:n_legal] >= 0).all() and (probs[n_legal:] == -1).all() and abs(float(probs[:n_legal].sum()) - 1.0) < 1e-4
+        assert struct.unpack("<b", e[1279:])[0] in (-1, 0, 1)
