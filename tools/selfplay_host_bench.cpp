@@ -1,8 +1,9 @@
 // Host-only throughput of the self-play driver: csrc/selfplay.cpp bound to a trivial evaluator (hash-derived priors), so
 // the time measured is the MCTS / rules / cache work of the worker threads alone.  Exploration tool, not part of the
-// library:  g++ -O3 -std=c++17 -ffp-contract=off -fno-trapping-math -fno-strict-aliasing -pthread \
-//               tools/selfplay_host_bench.cpp cattus_b200/csrc/selfplay.cpp -o /tmp/selfplay_host_bench
-//           /tmp/selfplay_host_bench chess 600 1 256 16      (game, sim_num, threads, games per thread, max_moves)
+// library:
+//   g++ -O3 -std=c++17 -ffp-contract=off -fno-trapping-math -fno-strict-aliasing -pthread tools/selfplay_host_bench.cpp
+//       cattus_b200/csrc/selfplay.cpp -o /tmp/selfplay_host_bench
+//   /tmp/selfplay_host_bench chess 600 1 256 16   (game, sim_num, threads, games per thread, max_moves[, games]; CACHE=n entries)
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
