@@ -58,7 +58,7 @@ class SelfPlaySummary(C.Structure):
         ("player1_wins", C.c_uint32), ("player2_wins", C.c_uint32), ("draws", C.c_uint32), ("games", C.c_uint32),
         ("simulations", C.c_uint64), ("searches", C.c_uint64), ("evaluations", C.c_uint64), ("cache_hits", C.c_uint64),
         ("cache_misses", C.c_uint64), ("batches", C.c_uint64), ("terminal_leaves", C.c_uint64), ("seconds", C.c_double),
-        ("search_duration", C.c_double), ("eval_wait_seconds", C.c_double),
+        ("search_duration", C.c_double), ("eval_wait_seconds", C.c_double), ("speculative_evaluations", C.c_uint64),
     ]
 
 

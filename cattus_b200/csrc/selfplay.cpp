@@ -536,7 +536,7 @@ struct GameRecord {
 
 struct Shared {
     // merged from the workers' private counters when they finish (no shared cache line on the per-simulation path)
-    uint64_t simulations = 0, searches = 0, evaluations = 0, cache_hits = 0, cache_misses = 0, batches = 0, terminal = 0;
+    uint64_t simulations = 0, searches = 0, evaluations = 0, cache_hits = 0, cache_misses = 0, batches = 0, terminal = 0, speculative = 0;
     uint32_t w1 = 0, w2 = 0, d = 0, games = 0;
     std::atomic<uint32_t> next_game{0};
     std::mutex mu;  // records, search_duration, first error
@@ -555,8 +555,16 @@ class Worker {
     using TreeT = Tree<Pos, Rules::kChess>;
     static constexpr bool kChess = Rules::kChess;
 
+    struct SimCand {
+        int32_t node, child;
+        int rank;  // 0: the node's best unvisited alternative, 1: its second best, ...
+    };
     struct Player {
         TreeT tree;
+        // speculation (cfg.speculate): (node block, child index) candidates of this tree -- the best-prior children of the nodes
+        // it expanded; consumed from spec_head
+        std::vector<std::pair<int32_t, int32_t>> spec_queue;
+        size_t spec_head = 0;
     };
     enum Phase { kIdle, kStartMove, kSimulate, kWaitEval };
     struct Slot {
@@ -586,6 +594,7 @@ class Worker {
         GameRecord rec;
         std::vector<std::pair<Pos, std::vector<std::pair<Move, float>>>> pending_entries;
         bool repetition = false;  // ChessGame::repetition_detected (chess/core.rs:441-449)
+        std::vector<SimCand> sim_cands;  // speculation: candidates seen along the simulation in progress
     };
     struct Pending {  // one batch under construction for one evaluator
         std::vector<uint64_t> planes;
@@ -634,7 +643,7 @@ class Worker {
         uint32_t inflight_n[2] = {0, 0};
     };
     struct Counters {
-        uint64_t simulations = 0, searches = 0, evaluations = 0, cache_hits = 0, cache_misses = 0, batches = 0, terminal = 0;
+        uint64_t simulations = 0, searches = 0, evaluations = 0, cache_hits = 0, cache_misses = 0, batches = 0, terminal = 0, speculative = 0;
         uint32_t w1 = 0, w2 = 0, d = 0, games = 0;
     };
 
@@ -664,6 +673,7 @@ class Worker {
             gr.pend[1].init(gr.count);
             for (uint32_t i = 0; i < gr.count; ++i) slots_[gr.first + i].group = g;
         }
+        if (cfg.speculate) set_speculation(cfg.speculate);
         val_.resize(static_cast<size_t>(R.max_children()) + 1);
         if (const char* e = std::getenv("CATTUS_B200_SELFPLAY_RING")) ring_size_ = std::max(1, std::min<int>(kMaxRing, std::atoi(e)));
         abi_wpp_ = (R.moves_num() + 63) / 64;
@@ -682,6 +692,7 @@ class Worker {
                         drain_all();
                         return;
                     }
+                    if (speculate_) fill_small_batches(gr);
                     for (int e = 0; e < 2; ++e)
                         if (!gr.pend[e].keys.empty()) {
                             send(gr, e);
@@ -707,6 +718,7 @@ class Worker {
         sh_.cache_misses += c_.cache_misses;
         sh_.batches += c_.batches;
         sh_.terminal += c_.terminal;
+        sh_.speculative += c_.speculative;
         sh_.w1 += c_.w1;
         sh_.w2 += c_.w2;
         sh_.d += c_.d;
@@ -728,7 +740,7 @@ class Worker {
     void set_speculation(uint32_t rows) {
         speculate_ = std::min<uint32_t>(rows, 255);
         for (Group& gr : groups_)  // the in-batch dedupe tables must hold the extra rows too
-            for (Pending& pb : gr.pend) pb.init(gr.count + speculate_);
+            for (Pending& pb : gr.pend) pb.init(gr.count + std::max<uint32_t>(speculate_, kSpecTargetRows));
     }
     void reseed(uint64_t seed) { slots_[0].rng = SplitMix64(game_seed(seed, 0)); }
     bool search_from(const std::vector<Pos>& history, Move* best, SearchStats* stats) {
@@ -744,13 +756,11 @@ class Worker {
         begin_search(s);
         s.phase = kSimulate;
         s.sel_node = -1;
-        spec_queue_.clear();  // block offsets of the previous tree
-        spec_head_ = 0;
-        spec_rows_ = 0;
+        const uint64_t spec_before = c_.speculative;
         Group& gr = groups_[0];
         while (s.phase != kStartMove) {
             if (!step(0)) {  // parked on the evaluator: evaluate now (one leaf in flight, like the reference)
-                add_speculative_rows(s, gr);
+                add_speculative_rows(s, gr, speculate_);
                 for (int e = 0; e < 2; ++e)
                     if (!gr.pend[e].keys.empty()) send(gr, e);
             }
@@ -768,7 +778,7 @@ class Worker {
             float top = 0.0f;
             for (auto& mp : probs) top = std::max(top, mp.second);
             stats->root_visits_best = static_cast<uint32_t>(top * static_cast<float>(params_[0].sim_num) + 0.5f);
-            stats->speculative = spec_rows_;
+            stats->speculative = static_cast<uint32_t>(c_.speculative - spec_before);
         }
         return true;
     }
@@ -858,7 +868,7 @@ class Worker {
                 return true;
             }
             s.path.clear();  // select (mod.rs:199-231) starts at the root
-            sim_cands_.clear();
+            s.sim_cands.clear();
             s.prepared_leaf = -1;
             s.sel_node = t.root;
             prefetch_block(t, t.root, t.hdr(t.root).count);
@@ -876,7 +886,7 @@ class Worker {
         }
         const int32_t count = nd.count;
         const int32_t best = select_child(t.init_score(node), t.score_w(node), t.simulations_n(node), count, params_[s.cur].explore_factor, sel_);
-        if constexpr (kChess) {
+        {
             if (speculate_) {  // the best-scoring children of this node that have no node yet, other than the one taken: likely next leaves
                 const uint32_t* ed = t.edge(node);
                 int32_t alt[kSpecPerLevel];
@@ -890,7 +900,7 @@ class Worker {
                     alt[at] = i;
                     n_alt = std::min(n_alt + 1, kSpecPerLevel);
                 }
-                for (int k = 0; k < n_alt; ++k) sim_cands_.push_back({node, alt[k], k});
+                for (int k = 0; k < n_alt; ++k) s.sim_cands.push_back({node, alt[k], k});
             }
         }
         int32_t c = TreeT::edge_child(t.edge(node)[best]);
@@ -1031,6 +1041,8 @@ class Worker {
             t.root = add_node(t, position);
         }
         s.sims_left = params_[s.cur].sim_num;
+        s.players[s.cur].spec_queue.clear();  // block offsets of the tree before reuse
+        s.players[s.cur].spec_head = 0;
     }
 
     // mod.rs:283-301, depth_limit = 3 (root, its children, their children).  Unvisited children have no node yet;
@@ -1309,7 +1321,7 @@ class Worker {
         }
         t.hdr(leaf).expanded = 1;
         if (leaf == t.root) add_dirichlet_noise(s, t, leaf);
-        if constexpr (kChess) {
+        {
             if (speculate_ && count > 0) {  // remember this node's two best-prior children as candidates to evaluate ahead
                 const float* init = t.init_score(leaf);
                 int32_t a = 0, b = -1;
@@ -1321,8 +1333,9 @@ class Worker {
                         b = i;
                     }
                 }
-                spec_queue_.emplace_back(leaf, a);
-                if (b >= 0) spec_queue_.emplace_back(leaf, b);
+                Player& pl = s.players[s.cur];
+                pl.spec_queue.emplace_back(leaf, a);
+                if (b >= 0) pl.spec_queue.emplace_back(leaf, b);
             }
         }
         float v = val[count];
@@ -1411,59 +1424,100 @@ class Worker {
         }
     }
 
-    // Appends up to `speculate_` candidate positions to the batch about to be sent; nobody is parked on those rows, so
-    // finish_batch only stores them in the cache.
-    void add_speculative_rows(Slot& s, Group& gr) {
+    // Speculation (cfg.speculate).  A device batch of 1 ... 256 positions costs the same time, so while leaves wait for the
+    // network, positions that are likely to be asked for next ride along and land in the cache: the best-scoring unvisited
+    // alternatives at every level of the path just walked, and the best-prior children of the nodes expanded before (where
+    // the next visit of such a node goes: all its children have n = 0, so select takes the largest prior).  Nobody is parked
+    // on those rows -- finish_batch only stores them -- and the cache returns exactly what a fresh evaluation returns (the
+    // evaluator is batch invariant), so every search is unchanged; only the number of round trips is.
+    //
+    // Appends up to `budget` candidates of slot `s` to its evaluator's pending batch; returns how many were added.
+    uint32_t add_speculative_rows(Slot& s, Group& gr, uint32_t budget) {
+        Evaluator& ev = *evals_[s.cur];
+        if (!budget || !ev.cache) return 0;
+        Player& pl = s.players[s.cur];
+        TreeT& t = pl.tree;
+        Pending& pb = gr.pend[evals_[0] == evals_[1] ? 0 : s.cur];
+        if (pb.keys.empty()) return 0;
+        uint32_t added = 0;
+        size_t sim_next = 0;
+        // every level's best alternative before any level's second best
+        std::stable_sort(s.sim_cands.begin(), s.sim_cands.end(), [](const SimCand& a, const SimCand& b) { return a.rank < b.rank; });
+        while (added < budget && (sim_next < s.sim_cands.size() || pl.spec_head < pl.spec_queue.size())) {
+            std::pair<int32_t, int32_t> cand;
+            if (sim_next < s.sim_cands.size()) {
+                cand = {s.sim_cands[sim_next].node, s.sim_cands[sim_next].child};
+                ++sim_next;
+            } else {
+                cand = pl.spec_queue[pl.spec_head++];
+            }
+            if (TreeT::edge_child(t.edge(cand.first)[cand.second]) >= 0) continue;  // visited in the meantime
+            if (add_row_ahead(t.hdr(cand.first).pos, move_at(t, cand.first, cand.second), pb, *ev.cache)) ++added;
+        }
+        s.sim_cands.erase(s.sim_cands.begin(), s.sim_cands.begin() + static_cast<std::ptrdiff_t>(sim_next));
+        c_.speculative += added;
+        if (pl.spec_head == pl.spec_queue.size()) {
+            pl.spec_queue.clear();
+            pl.spec_head = 0;
+        }
+        return added;
+    }
+
+    // The position after `m` in `parent` as one more row of `pb`, unless it is finished, cached or already in the batch.
+    bool add_row_ahead(const Pos& parent, Move m, Pending& pb, Cache& cache) {
         if constexpr (kChess) {
-            Evaluator& ev = *evals_[s.cur];
-            if (!speculate_ || !ev.cache) return;
-            TreeT& t = s.players[s.cur].tree;
-            Pending& pb = gr.pend[0];
-            if (pb.keys.empty()) return;
-            uint32_t added = 0;
-            size_t sim_next = 0;
-            // first the runner-up children along this simulation's path (every level's best before any level's second best),
-            // then the best-prior children of the nodes expanded before
-            std::stable_sort(sim_cands_.begin(), sim_cands_.end(), [](const SimCand& a, const SimCand& b) { return a.rank < b.rank; });
-            while (added < speculate_ && (sim_next < sim_cands_.size() || spec_head_ < spec_queue_.size())) {
-                std::pair<int32_t, int32_t> cand;
-                if (sim_next < sim_cands_.size()) {
-                    cand = {sim_cands_[sim_next].node, sim_cands_[sim_next].child};
-                    ++sim_next;
-                } else {
-                    cand = spec_queue_[spec_head_++];
-                }
-                if (TreeT::edge_child(t.edge(cand.first)[cand.second]) >= 0) continue;  // visited in the meantime
-                Pos child = R.moved(t.hdr(cand.first).pos, t.move16(cand.first)[cand.second]);
-                Move buf[256];
-                const int n = R.children(child, buf);
-                if (n == 0) continue;  // a finished position is never evaluated
-                uint64_t q[4];
-                R.key_planes(child, q);
-                const PosKey key{static_cast<u128>(q[0]) | (static_cast<u128>(q[1]) << 64), static_cast<u128>(q[2]) | (static_cast<u128>(q[3]) << 64)};
-                if (ev.cache->find(key, n, val_.data())) continue;
-                if (pb.find_or_reserve(key) >= 0) continue;
-                pb.keys.push_back(key);
-                uint64_t pl[Rules::kPlanes];
-                R.planes(child, pl);
-                pb.planes.insert(pb.planes.end(), pl, pl + Rules::kPlanes);
-                const size_t at = pb.legal.size();
-                pb.legal.resize(at + Rules::kLegalBytes, 0);
-                for (int k = 0; k < n; ++k) {
-                    const int idx = R.nn_idx(buf[k]);
-                    pb.legal[at + (idx >> 3)] |= static_cast<uint8_t>(1u << (idx & 7));
-                }
-                pb.n_legal.push_back(static_cast<uint8_t>(n));
-                ++added;
+            Pos child = R.moved(parent, m);
+            Move buf[256];
+            const int n = R.children(child, buf);
+            if (n == 0) return false;  // a finished position is never evaluated
+            uint64_t q[4];
+            R.key_planes(child, q);
+            const PosKey key{static_cast<u128>(q[0]) | (static_cast<u128>(q[1]) << 64), static_cast<u128>(q[2]) | (static_cast<u128>(q[3]) << 64)};
+            if (cache.find(key, n, val_.data())) return false;
+            if (pb.find_or_reserve(key) >= 0) return false;
+            pb.keys.push_back(key);
+            uint64_t pl[Rules::kPlanes];
+            R.planes(child, pl);
+            pb.planes.insert(pb.planes.end(), pl, pl + Rules::kPlanes);
+            const size_t at = pb.legal.size();
+            pb.legal.resize(at + Rules::kLegalBytes, 0);
+            for (int k = 0; k < n; ++k) {
+                const int idx = R.nn_idx(buf[k]);
+                pb.legal[at + (idx >> 3)] |= static_cast<uint8_t>(1u << (idx & 7));
             }
-            spec_rows_ += added;
-            if (spec_head_ == spec_queue_.size()) {
-                spec_queue_.clear();
-                spec_head_ = 0;
-            }
+            pb.n_legal.push_back(static_cast<uint8_t>(n));
+            return true;
         } else {
-            (void)s;
-            (void)gr;
+            const Pos child = R.moved(parent, m);
+            if (R.status(child) != 0) return false;
+            const Pos view = child.turn != 1 ? R.flipped_boards(child) : child;  // NNetwork::evaluate's flip (net/mod.rs:74-87)
+            const int n = popcount128(R.legal_mask(view));
+            const PosKey key = R.key(view);
+            if (cache.find(key, n, val_.data())) return false;
+            if (pb.find_or_reserve(key) >= 0) return false;
+            pb.keys.push_back(key);
+            u128 pl[3];
+            R.planes(view, pl);
+            for (int c = 0; c < 3; ++c)
+                for (int k = 0; k < abi_wpp_; ++k) pb.planes.push_back(static_cast<uint64_t>(pl[c] >> (64 * k)));
+            pb.n_legal.push_back(static_cast<uint8_t>(n));
+            return true;
+        }
+    }
+
+    // Self-play: a group whose batch is far below the size up to which the device time is flat takes speculative rows from
+    // the games parked on it (the trainer-sized job: a hundred games over a few threads).
+    void fill_small_batches(Group& gr) {
+        for (int e = 0; e < 2; ++e) {
+            Pending& pb = gr.pend[e];
+            const uint32_t real = static_cast<uint32_t>(pb.keys.size());
+            if (real == 0 || real >= kSpecTargetRows) continue;
+            uint32_t budget = kSpecTargetRows - real;
+            const uint32_t per_game = std::min<uint32_t>(speculate_, std::max<uint32_t>(1, budget / static_cast<uint32_t>(pb.parked.size())));
+            for (uint32_t si : pb.parked) {
+                if (!budget) break;
+                budget -= add_speculative_rows(slots_[si], gr, std::min(per_game, budget));
+            }
         }
     }
 
@@ -1589,15 +1643,9 @@ class Worker {
     std::vector<Slot> slots_;
     std::vector<Group> groups_;
     std::vector<std::vector<uint32_t>> pool_free_;  // retired tree buffers, reused by the next tree copy
-    uint32_t speculate_ = 0, spec_rows_ = 0;              // search sessions: rows evaluated ahead per call / so far in this search
-    std::vector<std::pair<int32_t, int32_t>> spec_queue_;  // (node block, child index) candidates of the current tree
-    struct SimCand {
-        int32_t node, child;
-        int rank;  // 0: the node's best unvisited alternative, 1: its second best, ...
-    };
+    uint32_t speculate_ = 0;  // rows evaluated ahead per game and evaluator call (cfg.speculate)
+    static constexpr uint32_t kSpecTargetRows = 192;  // batches below this take speculative rows (device time is flat to ~256)
     static constexpr int kSpecPerLevel = 4;
-    std::vector<SimCand> sim_cands_;  // candidates seen along the simulation in progress
-    size_t spec_head_ = 0;
     std::deque<std::pair<uint32_t, int>> inflight_;  // (group, evaluator) of this worker's batches in flight, oldest first
     int abi_wpp_ = 1;
     double eval_wait_ = 0.0;
@@ -1725,6 +1773,7 @@ static int selfplay_impl(sp::Evaluator& e1, sp::Evaluator* e2_or_null, const cat
         s.seconds = std::chrono::duration<double>(sp::Clock::now() - t0).count();
         s.search_duration = sh.search_duration;
         s.eval_wait_seconds = sh.eval_wait;
+        s.speculative_evaluations = sh.speculative;
         r->records = std::move(sh.records);
         std::sort(r->records.begin(), r->records.end(), [](const sp::GameRecord& a, const sp::GameRecord& b) { return a.game_idx < b.game_idx; });
         *out = r.release();

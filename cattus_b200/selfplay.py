@@ -173,6 +173,7 @@ class SelfPlayRunner:
                     "selfplay.games": s.games, "selfplay.simulations": s.simulations, "selfplay.searches": s.searches,
                     "selfplay.evaluations": s.evaluations, "selfplay.terminal_leaves": s.terminal_leaves,
                     "selfplay.seconds": s.seconds, "selfplay.eval_wait_seconds": s.eval_wait_seconds,
+                    "selfplay.speculative_evaluations": s.speculative_evaluations,
                     "selfplay.sims_per_sec": (s.simulations / s.seconds) if s.seconds > 0 else 0.0,
                 },
             }

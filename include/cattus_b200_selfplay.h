@@ -70,10 +70,12 @@ typedef struct cattus_b200_selfplay_cfg {
                                  * the next group (0 or 1 = one group; > 1 needs the B200 evaluator) */
     uint32_t max_moves; /* 0 (the reference): play every game to its end.  > 0: stop a game after this many moves and
                          * record it as a draw -- for benches and tools that need a bounded amount of work */
-    uint32_t speculate; /* cattus_b200_chess_search_* only (needs cache_size > 0): while a leaf waits for the network, up to
-                         * this many more positions ride in the same evaluator call and land in the cache -- the best-prior
-                         * unvisited children of recently expanded nodes.  The search itself is unchanged (the cache
-                         * returns what a fresh evaluation would); 0 = off, as the reference */
+    uint32_t speculate; /* needs cache_size > 0.  A device batch of 1 ... 256 positions costs the same time, so while leaves wait
+                         * for the network, up to this many more positions per game ride in the same evaluator call and land
+                         * in the cache: the best-scoring unvisited alternatives along the path just walked and the
+                         * best-prior children of nodes expanded before.  Every search is unchanged (the cache returns what a
+                         * fresh evaluation would); only batches below 192 rows are topped up.  For the UCI search and for
+                         * trainer-sized jobs (a hundred games over a few threads); 0 = off, as the reference */
 } cattus_b200_selfplay_cfg;
 
 /* Mirrors the summary file (self_play_cmd.rs:131-149) and the metric keys the trainer reads
@@ -90,6 +92,7 @@ typedef struct cattus_b200_selfplay_summary {
     double seconds;         /* wall clock of the whole call */
     double search_duration; /* RunningAverage(0.99) of per-search seconds: mcts.search_duration */
     double eval_wait_seconds; /* summed over workers: time blocked in the evaluator */
+    uint64_t speculative_evaluations; /* of `evaluations`: positions evaluated ahead into the cache (cfg.speculate) */
 } cattus_b200_selfplay_summary;
 
 typedef struct cattus_b200_selfplay cattus_b200_selfplay_t;

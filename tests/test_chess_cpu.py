@@ -424,3 +424,14 @@ def test_speculative_evaluation_does_not_change_the_search():
     assert out["plain"][0] == out["spec"][0]
     assert out["plain"][1]["speculative_evaluations"] == 0 and out["spec"][1]["speculative_evaluations"] > 0
     assert calls["spec"] < 0.8 * calls["plain"], calls
+
+
+def test_chess_speculation_in_self_play_same_games_fewer_calls():
+    net = chess_fake_net("hash")
+    kw = dict(sim_num=40, prior_noise_alpha=0.3, prior_noise_epsilon=0.25, temperature_policy=[[6, 1.0], [9999, 0.0]], cache_size=100000,
+              threads=2, games_per_thread=2, max_moves=12)
+    s0, plain = SelfPlayRunner("chess", chess_cfg(**kw)).run_with(chess_cb(net), None, 4, keep_records=True)
+    s1, spec = SelfPlayRunner("chess", chess_cfg(speculate=8, **kw)).run_with(chess_cb(net), None, 4, keep_records=True)
+    assert [(r.game_idx, r.moves, r.winner, r.entries) for r in spec] == [(r.game_idx, r.moves, r.winner, r.entries) for r in plain]
+    assert s1["metrics"]["selfplay.speculative_evaluations"] > 0
+    assert s1["metrics"]["model.activation_count"] < 0.8 * s0["metrics"]["model.activation_count"]

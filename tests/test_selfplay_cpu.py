@@ -318,3 +318,21 @@ def test_self_player_cli_rejects_other_engines_and_foreign_models(tmp_path):
     chess = tmp_path / "chess.cb2"
     chess.write_bytes(blob("chess_dev"))
     assert self_player.game_of_blob(chess) == ("chess", "chess")
+
+
+@pytest.mark.parametrize("game,threads,gpt", [("hex5", 1, 1), ("hex5", 2, 3), ("hex9", 1, 2), ("ttt", 1, 2)])
+def test_speculation_in_self_play_changes_nothing_but_the_number_of_calls(game, threads, gpt):
+    """cfg.speculate in the self-play driver (trainer-sized jobs: few games per thread, so batches are tiny and the device
+    time is flat): likely next leaves ride along into the cache.  Same games, same .traindata bytes, fewer evaluator calls."""
+    wpp = 1 if game == "ttt" else (int(game[3:]) ** 2 + 63) // 64
+    net = fake_net("hash")
+    kw = dict(sim_num=80, prior_noise_alpha=0.3, prior_noise_epsilon=0.25, temperature_policy=[[4, 1.0], [9999, 0.0]], cache_size=100000,
+              threads=threads, games_per_thread=gpt)
+    s0, plain = SelfPlayRunner(game, cfg_with(**kw)).run_with(cb_for(net, wpp), None, 6, keep_records=True)
+    s1, spec = SelfPlayRunner(game, cfg_with(speculate=8, **kw)).run_with(cb_for(net, wpp), None, 6, keep_records=True)
+    assert [(r.game_idx, r.moves, r.winner, r.entries) for r in spec] == [(r.game_idx, r.moves, r.winner, r.entries) for r in plain]
+    m0, m1 = s0["metrics"], s1["metrics"]
+    assert m0["selfplay.speculative_evaluations"] == 0 and m1["selfplay.speculative_evaluations"] > 0
+    assert m1["selfplay.simulations"] == m0["selfplay.simulations"]
+    if game != "ttt":  # tic-tac-toe trees are exhausted within a few dozen simulations either way
+        assert m1["model.activation_count"] < 0.8 * m0["model.activation_count"], (m0["model.activation_count"], m1["model.activation_count"])
