@@ -10,6 +10,8 @@ invokes it (training/cattus_train/train_process.py:159-170, :341-352):
 * `config.model.inference` may carry `{"engine": "cuda-b200", "device": 0, "precision": "bf16", "streams": 4}`;
   `config.model.batch_size` is the evaluator's max batch; the optional top-level keys `games_per_thread`, `leaf_queue`
   and `seed` select this backend's many-games-per-thread arrangement (default 64 games per worker thread);
+* with few games per worker thread (`games_num / threads` <= 96) `speculate` defaults on: likely next leaves are evaluated
+  ahead into the value-function cache in the otherwise nearly empty batches -- same games, several times fewer round trips;
 * `.traindata` files are byte-for-byte what the reference's serializers write (hex, tic-tac-toe and chess:
   serialize/{hex,ttt,chess}.rs), named `{game_idx:08}_{pos_idx:03}`;
 * the summary file has the reference's layout (:131-149): player1_wins, player2_wins, draws and the metric keys the
@@ -70,6 +72,12 @@ def main(argv=None) -> int:
     if game_of_blob(args.model2_path)[0] != game:
         raise SystemExit("model1 and model2 are for different games")
     cfg.setdefault("games_per_thread", 64)
+    # A trainer-sized job (self_play.games_num 100, threads 8) keeps only a dozen leaves in flight per worker, far below the
+    # ~256 positions a device batch can hold at no extra latency: let likely next leaves ride along into the cache (same games,
+    # fewer round trips).  Big jobs fill their batches with real leaves and need none.
+    slots = max(1, min(int(cfg["games_per_thread"]), -(-args.games_num // max(1, int(cfg.get("threads", 1))))))
+    if (cfg.get("mcts") or {}).get("cache_size"):
+        cfg.setdefault("speculate", min(31, 192 // slots) if slots <= 96 else 0)
     max_batch = max(int(cfg["model"].get("batch_size", 64)), min(4096, int(cfg["games_per_thread"])))
     kw = dict(device=device, batch_size=max_batch, n_streams=int(inference.get("streams", 4)), precision=inference.get("precision", "bf16"))
     if args.summary_file is not None and args.summary_file.exists():

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--leaf-queue", type=int, default=0)
     ap.add_argument("--groups", type=int, nargs="+", default=[0])
     ap.add_argument("--max-moves", type=int, default=0)
+    ap.add_argument("--speculate", type=int, nargs="+", default=[0], help="rows per game evaluated ahead into the cache (small batches only)")
     ap.add_argument("--batch", type=int, default=0, help="evaluator max batch (0 = games per thread, clamped to 64..4096)")
     args = ap.parse_args()
 
@@ -35,16 +36,17 @@ def main():
     cfg_net = net.CONFIGS[args.game]
     blob = export_blob(net.make_state_dict(cfg_net, 0), cfg_net.game)
     for th in args.threads:
-        for gpt, groups in [(g, k) for g in args.gpt for k in args.groups]:
+        for gpt, groups, speculate in [(g, k, sp) for g in args.gpt for k in args.groups for sp in args.speculate]:
             with CudaNetwork(blob, cfg_net.game, batch_size=args.batch or max(64, min(4096, gpt)), n_streams=args.streams) as nw:
                 cfg = {"mcts": {"sim_num": args.sim_num, "explore_factor": 1.41421, "temperature_policy": [[10, 1.0], [9999, 0.0]],
                                 "prior_noise_alpha": 0.03, "prior_noise_epsilon": 0.25, "cache_size": args.cache},
                        "threads": th, "games_per_thread": gpt, "groups_per_thread": groups, "leaf_queue": args.leaf_queue, "seed": 1,
-                       "max_moves": args.max_moves}
+                       "max_moves": args.max_moves, "speculate": speculate}
                 games = max(2, (args.games + 1) // 2 * 2)
                 summary, _ = SelfPlayRunner("chess" if args.game.startswith("chess") else args.game, cfg).generate_data(nw, None, games)
                 m = summary["metrics"]
-                print(json.dumps({"threads": th, "gpt": gpt, "groups": groups, "games": games, "sims_per_sec": round(m["selfplay.sims_per_sec"]),
+                print(json.dumps({"threads": th, "gpt": gpt, "groups": groups, "speculate": speculate, "games": games,
+                                  "spec_evals": m["selfplay.speculative_evaluations"], "sims_per_sec": round(m["selfplay.sims_per_sec"]),
                                   "seconds": round(m["selfplay.seconds"], 3), "evals": m["selfplay.evaluations"], "batches": m["model.activation_count"],
                                   "mean_batch": round(m["selfplay.evaluations"] / max(1, m["model.activation_count"]), 1),
                                   "hit_rate": round(m["cache.hits"] / max(1, m["cache.hits"] + m["cache.misses"]), 3),
