@@ -435,6 +435,7 @@ struct Evaluator {
     void* ctx = nullptr;
     cattus_b200_t* leaf_handle = nullptr;  // non-null: single-position requests use the per-leaf pinned queue
     cattus_b200_t* async_handle = nullptr; // non-null: batches go out with eval_batch_submit / _wait (kept in flight)
+    uint32_t max_rows = 0xFFFFFFFFu;       // the handle's max_batch: speculative rows never grow a batch beyond one device batch
     std::unique_ptr<Cache> cache;
 };
 
@@ -760,7 +761,7 @@ class Worker {
         Group& gr = groups_[0];
         while (s.phase != kStartMove) {
             if (!step(0)) {  // parked on the evaluator: evaluate now (one leaf in flight, like the reference)
-                add_speculative_rows(s, gr, speculate_);
+                add_speculative_rows(s, gr, std::min(speculate_, evals_[0]->max_rows - 1));
                 for (int e = 0; e < 2; ++e)
                     if (!gr.pend[e].keys.empty()) send(gr, e);
             }
@@ -1511,8 +1512,9 @@ class Worker {
         for (int e = 0; e < 2; ++e) {
             Pending& pb = gr.pend[e];
             const uint32_t real = static_cast<uint32_t>(pb.keys.size());
-            if (real == 0 || real >= kSpecTargetRows) continue;
-            uint32_t budget = kSpecTargetRows - real;
+            const uint32_t target = std::min(kSpecTargetRows, evals_[e]->max_rows);
+            if (real == 0 || real >= target) continue;
+            uint32_t budget = target - real;
             const uint32_t per_game = std::min<uint32_t>(speculate_, std::max<uint32_t>(1, budget / static_cast<uint32_t>(pb.parked.size())));
             for (uint32_t si : pb.parked) {
                 if (!budget) break;
@@ -1788,6 +1790,11 @@ static int selfplay_impl(sp::Evaluator& e1, sp::Evaluator* e2_or_null, const cat
     }
 }
 
+static uint32_t handle_max_batch(const cattus_b200_t* h) {
+    cattus_b200_info info;
+    return cattus_b200_get_info(h, &info) == CATTUS_B200_OK && info.max_batch ? info.max_batch : 1u;
+}
+
 static int engine_eval_thunk(void* ctx, const uint64_t* planes, const uint8_t* legal, uint32_t n, float* probs, size_t cap, uint32_t* offsets, float* values) {
     return cattus_b200_eval_batch(static_cast<cattus_b200_t*>(ctx), planes, legal, n, probs, cap, offsets, values);
 }
@@ -1803,12 +1810,14 @@ int cattus_b200_selfplay_run(cattus_b200_t* model1, cattus_b200_t* model2, const
     e1.fn = engine_eval_thunk;
     e1.ctx = model1;
     e1.async_handle = model1;
+    e1.max_rows = handle_max_batch(model1);
     if (cfg && cfg->leaf_queue) e1.leaf_handle = model1;
     const bool two = model2 && model2 != model1;
     if (two) {
         e2.fn = engine_eval_thunk;
         e2.ctx = model2;
         e2.async_handle = model2;
+        e2.max_rows = handle_max_batch(model2);
         if (cfg && cfg->leaf_queue) e2.leaf_handle = model2;
     }
     return selfplay_impl(e1, two ? &e2 : nullptr, cfg, out);
@@ -1917,6 +1926,7 @@ static int chess_search_create_impl(cattus_b200_eval_fn fn, void* ctx, cattus_b2
         s->ev.fn = fn;
         s->ev.ctx = ctx;
         s->ev.leaf_handle = leaf_handle;
+        if (leaf_handle) s->ev.max_rows = handle_max_batch(leaf_handle);
         // One tree fills the table slowly (<= sim_num entries per search), and every entry of a table sized for a million
         // positions would land on a fresh page: most of a search's host time went into page faults.  128 Ki entries hold the
         // last dozen searches; a smaller cache only changes hit rates, never results.

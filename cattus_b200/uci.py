@@ -130,7 +130,8 @@ def main(argv=None) -> int:
     inference = model_cfg.get("inference") or {}
     if inference.get("engine", "cuda-b200") != "cuda-b200":
         raise SystemExit(f"this executable is the cuda-b200 engine; config.model.inference.engine is {inference.get('engine')!r} (there is no CPU fallback)")
-    with CudaNetwork(Path(model_cfg["model_path"]), "chess", device=int(inference.get("device", 0)), batch_size=max(1, int(model_cfg.get("batch_size", 1))),
+    # room for the speculative rows: a device batch of up to 64 positions costs what one position costs
+    with CudaNetwork(Path(model_cfg["model_path"]), "chess", device=int(inference.get("device", 0)), batch_size=max(64, int(model_cfg.get("batch_size", 1))),
                      n_streams=1, precision=inference.get("precision", "bf16")) as nw:
         UCI(cfg, model=nw).run()
     return 0

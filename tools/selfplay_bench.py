@@ -37,7 +37,7 @@ def main():
     blob = export_blob(net.make_state_dict(cfg_net, 0), cfg_net.game)
     for th in args.threads:
         for gpt, groups, speculate in [(g, k, sp) for g in args.gpt for k in args.groups for sp in args.speculate]:
-            with CudaNetwork(blob, cfg_net.game, batch_size=args.batch or max(64, min(4096, gpt)), n_streams=args.streams) as nw:
+            with CudaNetwork(blob, cfg_net.game, batch_size=args.batch or max(256 if speculate else 64, min(4096, gpt)), n_streams=args.streams) as nw:
                 cfg = {"mcts": {"sim_num": args.sim_num, "explore_factor": 1.41421, "temperature_policy": [[10, 1.0], [9999, 0.0]],
                                 "prior_noise_alpha": 0.03, "prior_noise_epsilon": 0.25, "cache_size": args.cache},
                        "threads": th, "games_per_thread": gpt, "groups_per_thread": groups, "leaf_queue": args.leaf_queue, "seed": 1,

@@ -18,6 +18,7 @@ int cattus_b200_eval(cattus_b200_t*, const uint64_t*, const uint8_t*, float*, ui
 int cattus_b200_eval_batch(cattus_b200_t*, const uint64_t*, const uint8_t*, uint32_t, float*, size_t, uint32_t*, float*) { return CATTUS_B200_ENODEV; }
 int cattus_b200_eval_batch_submit(cattus_b200_t*, const uint64_t*, const uint8_t*, uint32_t, int, int32_t*) { return CATTUS_B200_ENODEV; }
 int cattus_b200_eval_batch_wait(cattus_b200_t*, int32_t, float*, size_t, uint32_t*, float*) { return CATTUS_B200_ENODEV; }
+int cattus_b200_get_info(const cattus_b200_t*, cattus_b200_info*) { return CATTUS_B200_ENODEV; }
 const char* cattus_b200_last_error(void) { return "host bench: no evaluator"; }
 }
 
