@@ -554,6 +554,26 @@ def main():
             "note": "rank 0's counters shown; value = simulations of all ranks / max seconds; games partitioned by index across GPUs, no collective"})
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             selfplay["cpu_baseline"] = time_cpu_selfplay(sp_game, 2, 2, cpu_selfplay_max_moves(args, sp_game))
+        if rank == 0:
+            # The job the trainer actually submits (self_play.games_num 100, engine.threads 8 in the shipped configs): a dozen
+            # leaves in flight per worker, so the device batches are nearly empty -- with and without speculative rows.
+            with CudaNetwork(export_blob(net.make_state_dict(sp_cfg, 0), sp_cfg.game), sp_cfg.game, device=local_rank, batch_size=256, n_streams=8,
+                             precision="bf16") as tr_nw:
+                trainer = []
+                for speculate in (0, 14):
+                    tr_runner = SelfPlayRunner(runner_game(sp_game), {"mcts": mc, "threads": 8, "games_per_thread": 64, "seed": 1,
+                                                                     "max_moves": sp_max_moves, "speculate": speculate})
+                    tr_runner.generate_data(tr_nw, None, 16)  # warm-up: graphs of the small buckets
+                    tr_sum, _ = tr_runner.generate_data(tr_nw, None, 100)
+                    tm = tr_sum["metrics"]
+                    trainer.append({"speculate": speculate, "sims_per_sec": tm["selfplay.sims_per_sec"], "seconds": tm["selfplay.seconds"],
+                                    "evaluator_calls": tm["model.activation_count"], "evaluations": tm["selfplay.evaluations"],
+                                    "speculative_evaluations": tm["selfplay.speculative_evaluations"],
+                                    "outcome": [tr_sum["player1_wins"], tr_sum["player2_wins"], tr_sum["draws"]]})
+                assert trainer[0]["outcome"] == trainer[1]["outcome"], "speculation changed game outcomes"
+                selfplay["trainer_sized_job"] = {"games": 100, "threads": 8, "runs": trainer,
+                                                 "note": "100 games over 8 worker threads as the shipped training configs ask for; speculate = rows per game "
+                                                         "evaluated ahead into the cache in the otherwise nearly empty device batches (same games)"}
         if rank == 0 and args.single_search:
             with CudaNetwork(export_blob(net.make_state_dict(sp_cfg, 0), sp_cfg.game), sp_cfg.game, device=local_rank, batch_size=64, n_streams=1,
                              precision="bf16") as ss_nw:
