@@ -290,3 +290,19 @@ def test_self_player_cli_chess(tmp_path):
         assert planes[17] == 0xFFFFFFFFFFFFFFFF and bin(planes[5]).count("1") == 1 and bin(planes[11]).count("1") == 1  # one king each
         assert (probs[:n_legal] >= 0).all() and (probs[n_legal:] == -1).all() and abs(float(probs[:n_legal].sum()) - 1.0) < 1e-4
         assert struct.unpack("<b", e[1279:])[0] in (-1, 0, 1)
+
+
+@pytest.mark.parametrize("name,game,kw", [("hex5", "hex5", dict(sim_num=200)), ("chess_dev", "chess", dict(sim_num=60, max_moves=10))])
+def test_gpu_selfplay_speculation_same_games_fewer_round_trips(name, game, kw):
+    """cfg.speculate in the self-play driver on the real evaluator (async batches, several lanes): the trainer-sized
+    arrangement -- a few games per worker -- with likely next leaves riding along into the cache.  Games must be identical."""
+    base = dict(cache_size=100000, prior_noise_alpha=0.3, prior_noise_epsilon=0.25, temperature_policy=[[6, 1.0], [9999, 0.0]], seed=5,
+                threads=4, games_per_thread=4, **kw)
+    out = {}
+    for speculate in (0, 14):
+        with make_network(name, batch_size=256, n_streams=4) as nw:
+            summary, recs = SelfPlayRunner(game, cfg_with(speculate=speculate, **base)).generate_data(nw, None, 16, keep_records=True)
+            out[speculate] = ([(r.game_idx, r.moves, r.winner, r.entries) for r in recs], summary["metrics"])
+    assert out[0][0] == out[14][0]
+    assert out[14][1]["selfplay.speculative_evaluations"] > 0 and out[0][1]["selfplay.speculative_evaluations"] == 0
+    assert out[14][1]["model.activation_count"] < 0.8 * out[0][1]["model.activation_count"]
