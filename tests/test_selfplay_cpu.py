@@ -336,3 +336,14 @@ def test_speculation_in_self_play_changes_nothing_but_the_number_of_calls(game, 
     assert m1["selfplay.simulations"] == m0["selfplay.simulations"]
     if game != "ttt":  # tic-tac-toe trees are exhausted within a few dozen simulations either way
         assert m1["model.activation_count"] < 0.8 * m0["model.activation_count"], (m0["model.activation_count"], m1["model.activation_count"])
+
+
+def test_speculation_with_two_evaluators_and_groups_of_games():
+    """Model comparison (two networks, two caches): a game's speculative rows go to the evaluator and cache of the side
+    that is searching."""
+    net1, net2 = fake_net("hash"), fake_net("hash", salt=99)
+    kw = dict(sim_num=60, cache_size=50000, threads=2, games_per_thread=3, prior_noise_alpha=0.3, prior_noise_epsilon=0.25)
+    _, plain = SelfPlayRunner("hex5", cfg_with(**kw)).run_with(cb_for(net1, 1), cb_for(net2, 1), 6, keep_records=True)
+    s, spec = SelfPlayRunner("hex5", cfg_with(speculate=6, **kw)).run_with(cb_for(net1, 1), cb_for(net2, 1), 6, keep_records=True)
+    assert [(r.game_idx, r.moves, r.winner, r.entries) for r in spec] == [(r.game_idx, r.moves, r.winner, r.entries) for r in plain]
+    assert s["metrics"]["selfplay.speculative_evaluations"] > 0
