@@ -557,11 +557,11 @@ def main():
         if rank == 0:
             # The job the trainer actually submits (self_play.games_num 100, engine.threads 8 in the shipped configs): a dozen
             # leaves in flight per worker, so the device batches are nearly empty -- with and without speculative rows.
-            with CudaNetwork(export_blob(net.make_state_dict(sp_cfg, 0), sp_cfg.game), sp_cfg.game, device=local_rank, batch_size=256, n_streams=8,
+            with CudaNetwork(export_blob(net.make_state_dict(sp_cfg, 0), sp_cfg.game), sp_cfg.game, device=local_rank, batch_size=256, n_streams=16,
                              precision="bf16") as tr_nw:
                 trainer = []
                 for speculate in (0, 14):
-                    tr_runner = SelfPlayRunner(runner_game(sp_game), {"mcts": mc, "threads": 8, "games_per_thread": 64, "seed": 1,
+                    tr_runner = SelfPlayRunner(runner_game(sp_game), {"mcts": mc, "threads": 8, "games_per_thread": 64, "seed": 1, "groups_per_thread": 2,
                                                                      "max_moves": sp_max_moves, "speculate": speculate})
                     tr_runner.generate_data(tr_nw, None, 16)  # warm-up: graphs of the small buckets
                     tr_sum, _ = tr_runner.generate_data(tr_nw, None, 100)
@@ -572,7 +572,7 @@ def main():
                                     "outcome": [tr_sum["player1_wins"], tr_sum["player2_wins"], tr_sum["draws"]]})
                 assert trainer[0]["outcome"] == trainer[1]["outcome"], "speculation changed game outcomes"
                 selfplay["trainer_sized_job"] = {"games": 100, "threads": 8, "runs": trainer,
-                                                 "note": "100 games over 8 worker threads as the shipped training configs ask for; speculate = rows per game "
+                                                 "note": "100 games over 8 worker threads (2 slot groups each) as the shipped training configs ask for; speculate = rows per game "
                                                          "evaluated ahead into the cache in the otherwise nearly empty device batches (same games)"}
         if rank == 0 and args.single_search:
             with CudaNetwork(export_blob(net.make_state_dict(sp_cfg, 0), sp_cfg.game), sp_cfg.game, device=local_rank, batch_size=64, n_streams=1,

@@ -78,6 +78,7 @@ def main(argv=None) -> int:
     slots = max(1, min(int(cfg["games_per_thread"]), -(-args.games_num // max(1, int(cfg.get("threads", 1))))))
     if (cfg.get("mcts") or {}).get("cache_size"):
         cfg.setdefault("speculate", min(31, 192 // slots) if slots <= 96 else 0)
+    cfg.setdefault("groups_per_thread", 2)  # a worker simulates one half of its games while the other half's leaves are on the GPU
     max_batch = max(int(cfg["model"].get("batch_size", 64)), min(4096, int(cfg["games_per_thread"])), 256 if cfg.get("speculate") else 1)
     kw = dict(device=device, batch_size=max_batch, n_streams=int(inference.get("streams", 4)), precision=inference.get("precision", "bf16"))
     if args.summary_file is not None and args.summary_file.exists():
