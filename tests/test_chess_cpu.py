@@ -435,3 +435,69 @@ def test_chess_speculation_in_self_play_same_games_fewer_calls():
     assert [(r.game_idx, r.moves, r.winner, r.entries) for r in spec] == [(r.game_idx, r.moves, r.winner, r.entries) for r in plain]
     assert s1["metrics"]["selfplay.speculative_evaluations"] > 0
     assert s1["metrics"]["model.activation_count"] < 0.8 * s0["metrics"]["model.activation_count"]
+
+
+# --------------------------------------------------------------------------------------------------------------
+# the reference's own chess rule tests (engine/src/chess/core.rs:617-730), restated for both rule sets
+# --------------------------------------------------------------------------------------------------------------
+def _san_to_move(pos: oc.ChessPosition, san: str):
+    """Enough SAN for the reference's test games: piece letter, optional from-file for pawn captures, destination."""
+    san = san.rstrip("+#")
+    kind = san[0].lower() if san[0] in "NBRQK" else "p"
+    dest = og.chess_move_to_idx("a1" + san[-2:]) % 64
+    from_file = ord(san[0]) - 97 if kind == "p" and "x" in san else None
+    found = [m for m in pos.legal_moves()
+             if m[1] == dest and pos.board[m[0]].lower() == kind and (from_file is None or m[0] % 8 == from_file)]
+    assert len(found) == 1, (san, found)
+    return found[0]
+
+
+def _play_san(moves):
+    """Plays the SAN moves on the oracle and on the library's rules; yields (oracle position, library info) BEFORE each move
+    and finally after the last one."""
+    pos = oc.ChessPosition.new()
+    played = []
+    for san in moves:
+        yield pos, chess_info(START, played)
+        m = _san_to_move(pos, san)
+        played.append(oc.move_to_u16(m))
+        pos = pos.moved_position(m)
+    yield pos, chess_info(START, played)
+
+
+def test_reference_simple_game_and_mate():
+    """core.rs:617-631: ongoing before every move, Finished(Some(Player1)) at the end."""
+    moves = ["e4", "e5", "d4", "exd4", "Qxd4", "Nc6", "Qa4", "a6", "Bg5", "h6", "Bc4", "Rb8", "Qb3", "Ra8", "Bxf7"]
+    states = list(_play_san(moves))
+    for pos, info in states[:-1]:
+        assert pos.status() == ("ongoing", None) and info.status == 0
+    pos, info = states[-1]
+    assert pos.status() == ("finished", oc.P1) and info.status == 1 and info.n_legal == 0 and info.in_check == 1
+
+
+def test_reference_fifty_rule_count():
+    """core.rs:633-670: two pawn moves, then the kings shuffle; the 50th quiet white move ends the game as a draw, and not
+    one move earlier (the count only advances on white's moves, core.rs:334-343; positions repeat, but repetition is the
+    game's business, not the position's)."""
+    moves = ["e4", "e5"] + ["Ke2", "Ke7", "Ke1", "Ke8"] * 24 + ["Ke2", "Ke7", "Ke1"]
+    states = list(_play_san(moves))
+    for pos, info in states[:-1]:
+        assert pos.status() == ("ongoing", None) and info.status == 0
+    pos, info = states[-1]
+    assert pos.status() == ("finished", None) and pos.fifty == 50
+    assert info.status == 3 and info.fifty_rule_count == 50 and info.n_legal == 0
+
+
+def test_reference_flip_positions():
+    """core.rs:672-693: the flipped position has the other side to move and flips back to the original; here also: the
+    library's view of a position (side to move plays white) is the oracle's flipped position for black to move."""
+    for fen in ["7r/2B3n1/K5R1/3nPP2/P1k2Pp1/4p1p1/2p4P/8 w - - 0 1", "8/5pB1/1P4P1/1p3q2/BK1pP2P/pQ1pP3/7k/8 w - - 0 1",
+                "2k5/2b1p1P1/1p5P/P1pnp3/QPK1b2p/8/5r2/8 b - - 0 1", "2b5/3N4/2B4p/1KP1R2r/n5p1/3N3P/k2B3b/q7 w - - 0 1",
+                "8/2P1r3/4k1p1/4n1p1/3Rq3/P3Pp2/P4PP1/5K1N b - - 0 1", "1N6/5pP1/P1pK3P/P3p3/2R3p1/k3pQ2/6r1/6N1 b - - 0 1",
+                "1B6/1r6/Q1ppKP2/qP1P1N1k/3p4/1pb5/7p/8 w - - 0 1", "3r4/1b2p3/7k/1P3R2/K4nrN/1N5P/n1Pp3P/8 b - - 0 1"]:
+        pos = oc.ChessPosition.from_fen(fen)
+        assert pos.flipped().turn == 3 - pos.turn and pos.flipped().flipped() == pos
+        info = chess_info(fen)
+        view = pos if pos.turn == oc.P1 else pos.flipped()
+        assert info.turn == pos.turn and list(info.planes) == view.planes()
+        assert {oc.move_from_u16(info.moves[i]) for i in range(info.n_legal)} == set(pos.legal_moves())
