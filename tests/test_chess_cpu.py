@@ -501,3 +501,34 @@ def test_reference_flip_positions():
         view = pos if pos.turn == oc.P1 else pos.flipped()
         assert info.turn == pos.turn and list(info.planes) == view.planes()
         assert {oc.move_from_u16(info.moves[i]) for i in range(info.n_legal)} == set(pos.legal_moves())
+
+
+def test_uci_plays_a_whole_game_with_legal_moves():
+    """training/tests/test_uci.py drives the reference's UCI binary with python-chess until the game is over; here the
+    oracle's rules play that part: every `bestmove` must be legal, the tree is reused from `go` to `go`."""
+    import io
+
+    from cattus_b200.uci import UCI
+
+    out = io.StringIO()
+    uci = UCI(chess_cfg(sim_num=25, prior_noise_alpha=0.03, prior_noise_epsilon=0.25, temperature_policy=[[9999, 1.0]], cache_size=100000, seed=2),
+              eval_fn=chess_cb(chess_fake_net("hash")), out=out)
+    assert uci.cfg["speculate"] == 31
+    uci.handle("uci")
+    uci.handle("ucinewgame")
+    board = oc.ChessPosition.new()
+    seen = {board: 1}
+    moves = []
+    for _ply in range(80):
+        if board.is_finished() or seen[board] >= 3:
+            break
+        uci.handle("position startpos" + (" moves " + " ".join(moves) if moves else ""))
+        uci.handle("go movetime 20000")
+        best = out.getvalue().strip().split("\n")[-1].split()[1]
+        legal = {oc.move_to_lan(m): m for m in board.legal_moves()}
+        assert best in legal, (best, sorted(legal))
+        moves.append(best)
+        board = board.moved_position(legal[best])
+        seen[board] = seen.get(board, 0) + 1
+    assert len(moves) >= 20
+    uci.handle("quit")

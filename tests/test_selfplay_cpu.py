@@ -347,3 +347,19 @@ def test_speculation_with_two_evaluators_and_groups_of_games():
     s, spec = SelfPlayRunner("hex5", cfg_with(speculate=6, **kw)).run_with(cb_for(net1, 1), cb_for(net2, 1), 6, keep_records=True)
     assert [(r.game_idx, r.moves, r.winner, r.entries) for r in spec] == [(r.game_idx, r.moves, r.winner, r.entries) for r in plain]
     assert s["metrics"]["selfplay.speculative_evaluations"] > 0
+
+
+def test_oracle_ttt_rules_match_reference_tests():
+    """engine/src/ttt/core.rs:290-339: simple_game_and_mate and flip."""
+    from oracle import games as og
+
+    def to_pos(s: str) -> om.TttPosition:
+        x, o, turn = og.ttt_position_from_str(s)
+        return om.TttPosition(x, o, turn, om.TttPosition._winner(x, o))
+
+    for s, winner in (("xxxoo____o", om.P1), ("oo_xxx___o", om.P1), ("oo____xxxo", om.P1), ("oxxo__ox_x", om.P2), ("xox_o_xo_x", om.P2),
+                      ("xxo__o_xox", om.P2), ("xxoooxxxoo", None)):
+        assert to_pos(s).status() == ("finished", winner), s
+    for s in ("oxx_o_o__o", "o_____xx_o", "xx_xx_xo_o", "ox___x_xox", "_x_o__o_xo", "ox__o____x", "_o__o_oxxo", "__xx_x__ox"):
+        pos = to_pos(s)
+        assert pos.flipped().turn == om.opposite(pos.turn) and pos.flipped().flipped() == pos
