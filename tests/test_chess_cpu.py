@@ -532,3 +532,31 @@ def test_uci_plays_a_whole_game_with_legal_moves():
         seen[board] = seen.get(board, 0) + 1
     assert len(moves) >= 20
     uci.handle("quit")
+
+
+def test_chess_entries_parse_like_the_trainer_parser():
+    """The consumer's side of the wire format: training/cattus_train/chess.py:22-49 (`Chess.load_data_entry`) restated without
+    `construct` -- 18 u64 planes, 235-byte bitmap unpacked little-endian bit order, the first popcount probabilities scattered
+    to the set indices, i8 winner -- applied to entries the driver produced."""
+    import struct
+
+    net = chess_fake_net("hash")
+    cfg = chess_cfg(sim_num=10, max_moves=9, temperature_policy=[[9999, 1.0]], seed=4)
+    _, records = SelfPlayRunner("chess", cfg).run_with(chess_cb(net), None, 2, keep_records=True)
+    for rec in records:
+        pos = oc.ChessPosition.new()
+        for k, entry in enumerate(rec.entries):
+            assert len(entry) == 18 * 8 + 235 + 225 * 4 + 1
+            planes = np.array(struct.unpack("<18Q", entry[:144]), dtype=np.uint64)
+            moves_bitmap = np.frombuffer(entry[144:379], dtype=np.uint8)
+            probs = np.frombuffer(entry[379:1279], dtype="<f4")
+            winner = float(struct.unpack("<b", entry[1279:])[0])
+            probs_all = np.full((1880,), -1.0, dtype=np.float32)
+            move_indices = np.where(np.unpackbits(moves_bitmap, count=1880, bitorder="little"))[0]
+            probs_all[move_indices] = probs[: len(move_indices)]
+            view = pos if pos.turn == oc.P1 else pos.flipped()  # entries are always written as Player1 to move
+            assert planes.tolist() == view.planes()
+            assert sorted(move_indices.tolist()) == sorted(oc.ChessPosition.to_nn_idx(m) for m in view.legal_moves())
+            assert abs(float(probs_all[move_indices].sum()) - 1.0) < 1e-5 and (probs[len(move_indices):] == -1.0).all()
+            assert winner == 0.0  # stopped by max_moves: recorded as a draw
+            pos = pos.moved_position(oc.move_from_u16(rec.moves[k]))
