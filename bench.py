@@ -598,13 +598,20 @@ def main():
                                                          "up to 31 likely next leaves ride in the same evaluator call into the cache (same moves, fewer round "
                                                          "trips); cache hits without speculation are transpositions inside the one search"}
                 else:
-                    ss_sum, _ = SelfPlayRunner(sp_game, {"mcts": ss_mc, "threads": 1, "games_per_thread": 1, "leaf_queue": 1,
-                                                                    "seed": 1}).generate_data(ss_nw, None, 2)
-                    sm = ss_sum["metrics"]
+                    per = {}
+                    for speculate in (0, 31):
+                        ss_sum, ss_rec = SelfPlayRunner(sp_game, {"mcts": ss_mc, "threads": 1, "games_per_thread": 1, "leaf_queue": 1, "seed": 1,
+                                                                  "speculate": speculate}).generate_data(ss_nw, None, 2, keep_records=True)
+                        per[speculate] = (ss_sum["metrics"], [r.moves for r in ss_rec])
+                    assert per[0][1] == per[31][1], "speculation changed a game"
+                    sm, sm_spec = per[0][0], per[31][0]
                     selfplay["single_search"] = {"sim_num": 10000, "searches": sm["selfplay.searches"],
                                                  "seconds_per_search": sm["selfplay.seconds"] / max(1, sm["selfplay.searches"]),
+                                                 "seconds_per_search_speculating": sm_spec["selfplay.seconds"] / max(1, sm_spec["selfplay.searches"]),
                                                  "sims_per_sec": sm["selfplay.sims_per_sec"], "evaluations": sm["selfplay.evaluations"],
-                                                 "note": "one tree, one leaf in flight (the reference's UCI arrangement), per-leaf cattus_b200_eval"}
+                                                 "evaluator_calls": sm["model.activation_count"], "evaluator_calls_speculating": sm_spec["model.activation_count"],
+                                                 "note": "two whole games of one tree, one leaf in flight (the reference's UCI arrangement), per-leaf "
+                                                         "cattus_b200_eval; speculating: up to 31 likely next leaves ride along into the cache (same games)"}
         selfplay_legs.append(selfplay)
     selfplay = selfplay_legs[0] if selfplay_legs else None
 
