@@ -7,7 +7,8 @@
 `cfg` is the same JSON object the reference executable reads (self_play_cmd.rs:34-53; written by
 training/cattus_train/self_play.py): {"model": {"batch_size", "inference"}, "mcts": {"sim_num", "explore_factor",
 "temperature_policy", "prior_noise_alpha", "prior_noise_epsilon", "cache_size"}, "threads"} plus the optional keys
-"games_per_thread", "groups_per_thread", "leaf_queue", "max_moves" and "seed" that only this backend understands.  The returned summary has the layout of
+"games_per_thread", "groups_per_thread", "leaf_queue", "max_moves", "speculate" and "seed" that only this backend
+understands (include/cattus_b200_selfplay.h documents each; none of them changes a game except "seed" and "max_moves").  The returned summary has the layout of
 the reference's summary file (self_play_cmd.rs:131-149) with the metric keys the trainer reads
 (training/cattus_train/train_process.py:176-186).
 
