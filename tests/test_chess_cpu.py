@@ -560,3 +560,37 @@ def test_chess_entries_parse_like_the_trainer_parser():
             assert abs(float(probs_all[move_indices].sum()) - 1.0) < 1e-5 and (probs[len(move_indices):] == -1.0).all()
             assert winner == 0.0  # stopped by max_moves: recorded as a draw
             pos = pos.moved_position(oc.move_from_u16(rec.moves[k]))
+
+
+@pytest.mark.parametrize("trial", range(8))
+def test_speculation_never_changes_a_game_randomised(trial):
+    """Random draws over game, evaluator (incl. exact ties), noise, temperature, cache size (incl. tiny caches that evict all the
+    time), one or two evaluators, threads x games per thread and rows per game: with and without cfg.speculate the records are
+    byte-identical."""
+    from tests.test_selfplay_cpu import cb_for, cfg_with, fake_net
+
+    rng = random.Random(100 + trial)
+    game = rng.choice(["hex4", "hex5", "hex7", "ttt", "chess"])
+    kind = rng.choice(["hash", "coarse", "uniform"])
+    kw = dict(sim_num=rng.choice([8, 30, 60]), prior_noise_alpha=rng.choice([0.0, 0.3]), prior_noise_epsilon=0.25,
+              temperature_policy=rng.choice([[[9999, 0.0]], [[3, 1.0], [9999, 0.0]], [[9999, 1.0]]]), cache_size=rng.choice([50, 5000, 100000]),
+              threads=rng.choice([1, 2, 3]), games_per_thread=rng.choice([1, 2, 5]), seed=rng.randrange(1000))
+    two = rng.random() < 0.3
+    spec = rng.choice([1, 4, 9, 31])
+    if game == "chess":
+        net1, net2 = chess_fake_net(kind), chess_fake_net(kind, salt=7)
+
+        def run(s):
+            return SelfPlayRunner("chess", chess_cfg(speculate=s, max_moves=10, **kw)).run_with(chess_cb(net1), chess_cb(net2) if two else None, 4,
+                                                                                                 keep_records=True)
+    else:
+        wpp = 1 if game == "ttt" else (int(game[3:]) ** 2 + 63) // 64
+        net1, net2 = fake_net(kind), fake_net(kind, salt=7)
+
+        def run(s):
+            return SelfPlayRunner(game, cfg_with(speculate=s, **kw)).run_with(cb_for(net1, wpp), cb_for(net2, wpp) if two else None, 4, keep_records=True)
+
+    _, plain = run(0)
+    summary, speculating = run(spec)
+    assert [(r.game_idx, r.moves, r.winner, r.entries) for r in speculating] == [(r.game_idx, r.moves, r.winner, r.entries) for r in plain]
+    assert summary["metrics"]["selfplay.speculative_evaluations"] > 0
