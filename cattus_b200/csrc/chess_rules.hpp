@@ -28,9 +28,9 @@
 #include <cstring>
 #include <string>
 
-namespace sp {
+#include "sp_rules.hpp"
 
-using u128c = unsigned __int128;
+namespace sp {
 
 struct ChessPos {
     uint64_t pc[6];              // pawns, knights, bishops, rooks, queens, kings (both sides)
@@ -86,7 +86,7 @@ struct ChessTables {
             for (int d = 0; d < 8; ++d) {
                 uint64_t rest = ray[d][a];
                 while (rest) {
-                    const int b = __builtin_ctzll(rest);
+                    const int b = ctz64(rest);
                     rest &= rest - 1;
                     between[a][b] = ray[d][a] & ray[opp[d]][b];
                     line[a][b] = ray[d][a] | ray[opp[d]][a] | (1ull << a);
@@ -123,56 +123,58 @@ struct ChessRules {
     static constexpr bool kChess = true;
     static constexpr int kMaxMoves = 224;  // the serializer's bound is 225 (serialize/chess.rs:34); no position exceeds 218
     static constexpr int kMovesNum = 1880, kLegalBytes = 235, kPlanes = 18;
-    const ChessTables& T = chess_tables();
+    const ChessTables& T;
+    ChessRules() : T(chess_tables()) {}
+    CB2_HD explicit ChessRules(const ChessTables& tables) : T(tables) {}  // device code: the tables live in global memory
 
-    int moves_num() const { return kMovesNum; }
-    int max_children() const { return kMaxMoves; }
+    CB2_HD int moves_num() const { return kMovesNum; }
+    CB2_HD int max_children() const { return kMaxMoves; }
 
-    static Move make_move(int from, int to, int promo) { return static_cast<Move>(from | (to << 6) | (promo << 12)); }
-    static int from_of(Move m) { return m & 63; }
-    static int to_of(Move m) { return (m >> 6) & 63; }
-    static int promo_of(Move m) { return m >> 12; }
+    CB2_HD static Move make_move(int from, int to, int promo) { return static_cast<Move>(from | (to << 6) | (promo << 12)); }
+    CB2_HD static int from_of(Move m) { return m & 63; }
+    CB2_HD static int to_of(Move m) { return (m >> 6) & 63; }
+    CB2_HD static int promo_of(Move m) { return m >> 12; }
     // ChessMove::flipped (core.rs:82-91)
-    static Move flip_move(Move m) { return static_cast<Move>(m ^ (56 | (56 << 6))); }
-    static Move real_move(const Pos& p, Move m) { return p.turn == 1 ? m : flip_move(m); }
+    CB2_HD static Move flip_move(Move m) { return static_cast<Move>(m ^ (56 | (56 << 6))); }
+    CB2_HD static Move real_move(const Pos& p, Move m) { return p.turn == 1 ? m : flip_move(m); }
     // ChessMove::to_idx + MOVE_TO_NN_INDEX (core.rs:55-72, :93-95) of a move in the network's view
-    int nn_idx(Move m) const {
+    CB2_HD int nn_idx(Move m) const {
         const int from = from_of(m), to = to_of(m), promo = promo_of(m);
         if (promo) {
-            static const int offset[5] = {0, 0, 3, 1, 2};  // q 0, r 1, b 2, n 3
+            const int offset[5] = {0, 0, 3, 1, 2};  // q 0, r 1, b 2, n 3
             return T.nn_index[64 * 64 + ((from & 7) * 2 + (to & 7)) * 4 + offset[promo]];
         }
         return T.nn_index[from * 64 + to];
     }
 
-    static uint64_t occ(const Pos& p) { return p.pc[0] | p.pc[1] | p.pc[2] | p.pc[3] | p.pc[4] | p.pc[5]; }
-    static int piece_on(const Pos& p, int sq) {
+    CB2_HD static uint64_t occ(const Pos& p) { return p.pc[0] | p.pc[1] | p.pc[2] | p.pc[3] | p.pc[4] | p.pc[5]; }
+    CB2_HD static int piece_on(const Pos& p, int sq) {
         for (int k = 0; k < 6; ++k)
             if (p.pc[k] >> sq & 1) return k;
         return -1;
     }
-    uint64_t ray_attack(int d, int sq, uint64_t all) const {
+    CB2_HD uint64_t ray_attack(int d, int sq, uint64_t all) const {
         uint64_t r = T.ray[d][sq];
         const uint64_t b = r & all;
         if (b) {
             const bool up = d == 0 || d == 2 || d == 4 || d == 5;  // directions that increase the square index
-            const int s = up ? __builtin_ctzll(b) : 63 - __builtin_clzll(b);
+            const int s = up ? ctz64(b) : 63 - clz64(b);
             r ^= T.ray[d][s];
         }
         return r;
     }
-    uint64_t rook_moves(int sq, uint64_t all) const { return ray_attack(0, sq, all) | ray_attack(1, sq, all) | ray_attack(2, sq, all) | ray_attack(3, sq, all); }
-    uint64_t bishop_moves(int sq, uint64_t all) const { return ray_attack(4, sq, all) | ray_attack(5, sq, all) | ray_attack(6, sq, all) | ray_attack(7, sq, all); }
+    CB2_HD uint64_t rook_moves(int sq, uint64_t all) const { return ray_attack(0, sq, all) | ray_attack(1, sq, all) | ray_attack(2, sq, all) | ray_attack(3, sq, all); }
+    CB2_HD uint64_t bishop_moves(int sq, uint64_t all) const { return ray_attack(4, sq, all) | ray_attack(5, sq, all) | ray_attack(6, sq, all) | ray_attack(7, sq, all); }
 
     // checkers / pinned of the side to move
-    void update_pins(Pos& p) const {
+    CB2_HD void update_pins(Pos& p) const {
         const uint64_t all = occ(p), them = all & ~p.us;
-        const int ksq = __builtin_ctzll(p.pc[kKing] & p.us);
+        const int ksq = ctz64(p.pc[kKing] & p.us);
         p.checkers = 0;
         p.pinned = 0;
         uint64_t pinners = them & ((T.bishop_rays[ksq] & (p.pc[kBishop] | p.pc[kQueen])) | (T.rook_rays[ksq] & (p.pc[kRook] | p.pc[kQueen])));
         while (pinners) {
-            const int sq = __builtin_ctzll(pinners);
+            const int sq = ctz64(pinners);
             pinners &= pinners - 1;
             const uint64_t bt = T.between[sq][ksq] & all;
             if (bt == 0)
@@ -184,7 +186,7 @@ struct ChessRules {
         p.checkers |= T.pawn_up[ksq] & them & p.pc[kPawn];
     }
 
-    Pos initial() const {
+    CB2_HD Pos initial() const {
         Pos p;
         p.pc[kPawn] = 0x00FF00000000FF00ull;
         p.pc[kKnight] = 0x4200000000000042ull;
@@ -201,16 +203,16 @@ struct ChessRules {
     }
 
     // ChessPosition::flipped (core.rs:366-399) on this representation: mirror the ranks and exchange the sides
-    void flip_view(Pos& p) const {
+    CB2_HD void flip_view(Pos& p) const {
         const uint64_t them = occ(p) & ~p.us;
-        for (int k = 0; k < 6; ++k) p.pc[k] = __builtin_bswap64(p.pc[k]);
-        p.us = __builtin_bswap64(them);
+        for (int k = 0; k < 6; ++k) p.pc[k] = bswap64(p.pc[k]);
+        p.us = bswap64(them);
         p.castle = static_cast<uint8_t>(((p.castle & 3) << 2) | (p.castle >> 2));
         if (p.ep != 64) p.ep ^= 56;
         p.turn = static_cast<uint8_t>(3 - p.turn);
     }
 
-    bool square_safe_for_king(const Pos& p, int dest) const {  // the crate's legal_king_move
+    CB2_HD bool square_safe_for_king(const Pos& p, int dest) const {  // the crate's legal_king_move
         const uint64_t them = occ(p) & ~p.us;
         const uint64_t all = (occ(p) ^ (p.pc[kKing] & p.us)) | (1ull << dest);
         if (rook_moves(dest, all) & (p.pc[kRook] | p.pc[kQueen]) & them) return false;
@@ -220,10 +222,10 @@ struct ChessRules {
         if (T.pawn_up[dest] & p.pc[kPawn] & them) return false;
         return true;
     }
-    bool legal_ep(const Pos& p, int src, int dest) const {  // the crate's legal_ep_move
+    CB2_HD bool legal_ep(const Pos& p, int src, int dest) const {  // the crate's legal_ep_move
         const uint64_t them = occ(p) & ~p.us;
         const uint64_t all = occ(p) ^ (1ull << p.ep) ^ (1ull << src) ^ (1ull << dest);
-        const int ksq = __builtin_ctzll(p.pc[kKing] & p.us);
+        const int ksq = ctz64(p.pc[kKing] & p.us);
         const uint64_t rooks = (p.pc[kRook] | p.pc[kQueen]) & them;
         if ((T.rook_rays[ksq] & rooks) && (rook_moves(ksq, all) & rooks)) return false;
         const uint64_t bishops = (p.pc[kBishop] | p.pc[kQueen]) & them;
@@ -231,9 +233,9 @@ struct ChessRules {
         return true;
     }
 
-    static int emit(Move* out, int n, int src, uint64_t dests, bool promo) {
+    CB2_HD static int emit(Move* out, int n, int src, uint64_t dests, bool promo) {
         while (dests) {
-            const int d = __builtin_ctzll(dests);
+            const int d = ctz64(dests);
             dests &= dests - 1;
             if (promo) {
                 for (int k = 1; k <= 4; ++k) out[n++] = make_move(src, d, k);
@@ -245,14 +247,14 @@ struct ChessRules {
     }
 
     // MoveGen::new_legal for the side to move, in the crate's order (see the header comment); returns the count
-    int gen(const Pos& p, Move* out) const {
+    CB2_HD int gen(const Pos& p, Move* out) const {
         const uint64_t all = occ(p), us = p.us, mask = ~us;
-        const int ksq = __builtin_ctzll(p.pc[kKing] & us);
-        const int n_checkers = __builtin_popcountll(p.checkers);
+        const int ksq = ctz64(p.pc[kKing] & us);
+        const int n_checkers = popc64(p.checkers);
         int n = 0;
         if (n_checkers <= 1) {
             const bool in_check = n_checkers == 1;
-            const uint64_t check_mask = in_check ? (T.between[__builtin_ctzll(p.checkers)][ksq] ^ p.checkers) : ~0ull;
+            const uint64_t check_mask = in_check ? (T.between[ctz64(p.checkers)][ksq] ^ p.checkers) : ~0ull;
             const uint64_t pawns = p.pc[kPawn] & us;
             auto pawn_moves = [&](int src) {
                 uint64_t m = T.pawn_up[src] & all;
@@ -264,18 +266,18 @@ struct ChessRules {
                 return m & mask;
             };
             for (uint64_t b = pawns & ~p.pinned; b; b &= b - 1) {
-                const int src = __builtin_ctzll(b);
+                const int src = ctz64(b);
                 n = emit(out, n, src, pawn_moves(src) & check_mask, (src >> 3) == 6);
             }
             if (!in_check)
                 for (uint64_t b = pawns & p.pinned; b; b &= b - 1) {
-                    const int src = __builtin_ctzll(b);
+                    const int src = ctz64(b);
                     n = emit(out, n, src, pawn_moves(src) & T.line[src][ksq], (src >> 3) == 6);
                 }
             if (p.ep != 64) {
                 const uint64_t rank = 0xFFull << (p.ep & 56);
                 for (uint64_t b = rank & T.adjacent_files[p.ep & 7] & pawns; b; b &= b - 1) {
-                    const int src = __builtin_ctzll(b);
+                    const int src = ctz64(b);
                     if (legal_ep(p, src, p.ep + 8)) out[n++] = make_move(src, p.ep + 8, 0);
                 }
             }
@@ -290,19 +292,19 @@ struct ChessRules {
                     }
                 };
                 for (uint64_t b = pieces & ~p.pinned; b; b &= b - 1) {
-                    const int src = __builtin_ctzll(b);
+                    const int src = ctz64(b);
                     n = emit(out, n, src, pseudo(src) & check_mask, false);
                 }
                 if (!in_check)
                     for (uint64_t b = pieces & p.pinned; b; b &= b - 1) {
-                        const int src = __builtin_ctzll(b);
+                        const int src = ctz64(b);
                         n = emit(out, n, src, pseudo(src) & T.line[src][ksq], false);
                     }
             }
         }
         uint64_t km = T.king[ksq] & mask;
         for (uint64_t b = km; b; b &= b - 1) {
-            const int d = __builtin_ctzll(b);
+            const int d = ctz64(b);
             if (!square_safe_for_king(p, d)) km ^= 1ull << d;
         }
         if (n_checkers == 0) {
@@ -315,7 +317,7 @@ struct ChessRules {
 
     // legal_moves() as the tree sees them (NNetwork::evaluate generates them on the flipped position and maps them
     // back, net/mod.rs:74-87): this view's order.  Also settles status(): ChessPosition::status, core.rs:348-364.
-    int children(Pos& p, Move* out) const {
+    CB2_HD int children(Pos& p, Move* out) const {
         const int n = gen(p, out);
         if (n == 0)
             p.st = p.checkers ? static_cast<uint8_t>(3 - p.turn) : 3;  // checkmate: the side that moved last wins; stalemate
@@ -325,11 +327,11 @@ struct ChessRules {
             p.st = 0;
         return p.st ? 0 : n;
     }
-    int status(const Pos& p) const { return p.st; }
+    CB2_HD int status(const Pos& p) const { return p.st; }
 
     // Board::make_move_new + ChessPosition::moved_position (core.rs:326-346); `m` is in this view; the result is
     // stored in the opponent's view.  status() of the result is settled by children().
-    Pos moved(const Pos& p, Move m) const {
+    CB2_HD Pos moved(const Pos& p, Move m) const {
         const int src = from_of(m), dst = to_of(m), promo = promo_of(m);
         const uint64_t sb = 1ull << src, db = 1ull << dst;
         const uint64_t all = occ(p), them = all & ~p.us;
@@ -339,7 +341,7 @@ struct ChessRules {
         if (capture)
             for (int k = 0; k < 6; ++k) r.pc[k] &= ~db;
         r.pc[piece] &= ~sb;
-        static const int promo_piece[5] = {0, kQueen, kKnight, kRook, kBishop};
+        const int promo_piece[5] = {0, kQueen, kKnight, kRook, kBishop};
         r.pc[promo ? promo_piece[promo] : piece] |= db;
         r.us = (p.us ^ sb) | db;
         uint8_t castle = p.castle;
@@ -371,12 +373,13 @@ struct ChessRules {
     }
 
     // ChessPosition == (core.rs:292-309): boards, castle rights, en passant, side to move -- not the fifty-move count
-    static bool same(const Pos& a, const Pos& b) {
-        return a.us == b.us && a.turn == b.turn && a.castle == b.castle && a.ep == b.ep && std::memcmp(a.pc, b.pc, sizeof(a.pc)) == 0;
+    CB2_HD static bool same(const Pos& a, const Pos& b) {
+        return a.us == b.us && a.turn == b.turn && a.castle == b.castle && a.ep == b.ep && a.pc[0] == b.pc[0] && a.pc[1] == b.pc[1] &&
+               a.pc[2] == b.pc[2] && a.pc[3] == b.pc[3] && a.pc[4] == b.pc[4] && a.pc[5] == b.pc[5];
     }
 
     // position_to_planes (chess/net/mod.rs:19-60) of this view (the side to move plays white)
-    void planes(const Pos& p, uint64_t out[18]) const {
+    CB2_HD void planes(const Pos& p, uint64_t out[18]) const {
         const uint64_t them = occ(p) & ~p.us;
         for (int k = 0; k < 6; ++k) {
             out[k] = p.pc[k] & p.us;
@@ -390,7 +393,7 @@ struct ChessRules {
     // Cache key of a position in the evaluator's view: 4 bits per square -- 1..6 our P N B R Q K, 7..12 theirs, 13 / 14
     // our / their rook that may still castle (a castle right implies the rook on its corner and the king on e1/e8),
     // 15 their pawn capturable en passant -- as four bitboards.  Equal keys <=> equal ChessPositions of this view.
-    void key_planes(const Pos& p, uint64_t q[4]) const {
+    CB2_HD void key_planes(const Pos& p, uint64_t q[4]) const {
         const uint64_t them = occ(p) & ~p.us;
         q[0] = q[1] = q[2] = q[3] = 0;
         for (int k = 0; k < 6; ++k) {
@@ -460,7 +463,7 @@ struct ChessRules {
         int ep_file = -1;
         if (*c >= 'a' && *c <= 'h') ep_file = *c - 'a';
         const uint64_t all = occ(p);
-        if (__builtin_popcountll(p.pc[kKing] & white) != 1 || __builtin_popcountll(p.pc[kKing] & ~white) != 1) return "each side needs exactly one king";
+        if (popc64(p.pc[kKing] & white) != 1 || popc64(p.pc[kKing] & ~white) != 1) return "each side needs exactly one king";
         const uint64_t black_occ = all & ~white;
         auto has = [&](int kind, uint64_t side, int sq) { return (p.pc[kind] & side) >> sq & 1; };
         if (((rights & 3) && !has(kKing, white, 4)) || ((rights & 1) && !has(kRook, white, 7)) || ((rights & 2) && !has(kRook, white, 0)) ||

@@ -38,71 +38,12 @@
 #include <sys/types.h>
 
 #include "../../include/cattus_b200_selfplay.h"
-#include "chess_rules.hpp"
+#include "sp_common.hpp"
 
 namespace sp {
 
-using u128 = unsigned __int128;
-using Clock = std::chrono::steady_clock;
-
-struct SpError {
-    int code;
-    std::string msg;
-};
-
-static inline int ctz128(u128 x) {
-    const uint64_t lo = static_cast<uint64_t>(x);
-    return lo ? __builtin_ctzll(lo) : 64 + __builtin_ctzll(static_cast<uint64_t>(x >> 64));
-}
-static inline int popcount128(u128 x) { return __builtin_popcountll(static_cast<uint64_t>(x)) + __builtin_popcountll(static_cast<uint64_t>(x >> 64)); }
-static inline u128 bit128(int i) { return static_cast<u128>(1) << i; }
-
-// ------------------------------------------------------------------------------------------------ random stream
-// The reference uses the unseeded thread-local rand::rng(); every game here owns this stream instead (same
-// definition in oracle/mcts.py so whole games can be compared).
-struct SplitMix64 {
-    uint64_t state;
-    explicit SplitMix64(uint64_t seed = 0) : state(seed) {}
-    uint64_t next_u64() {
-        state += 0x9E3779B97F4A7C15ull;
-        uint64_t z = state;
-        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-        return z ^ (z >> 31);
-    }
-    double next_f64() { return static_cast<double>(next_u64() >> 11) * (1.0 / 9007199254740992.0); }
-    double next_open_f64() { return (static_cast<double>(next_u64() >> 12) + 0.5) * (1.0 / 4503599627370496.0); }
-    double normal() {
-        const double u1 = next_open_f64();
-        const double u2 = next_f64();
-        return std::sqrt(-2.0 * std::log(u1)) * std::cos(2.0 * M_PI * u2);
-    }
-    double gamma(double alpha) {  // Marsaglia-Tsang; alpha < 1 boosted with U^(1/alpha)
-        if (alpha < 1.0) {
-            const double u = next_open_f64();
-            return gamma(alpha + 1.0) * std::pow(u, 1.0 / alpha);
-        }
-        const double d = alpha - 1.0 / 3.0;
-        const double c = 1.0 / std::sqrt(9.0 * d);
-        for (;;) {
-            const double x = normal();
-            double v = 1.0 + c * x;
-            if (v <= 0.0) continue;
-            v = v * v * v;
-            const double u = next_open_f64();
-            if (std::log(u) < 0.5 * x * x + d - d * v + d * std::log(v)) return d * v;
-        }
-    }
-};
-
-static inline uint64_t game_seed(uint64_t base, uint32_t game_idx) { return base ^ (0xD1B54A32D192ED03ull * (static_cast<uint64_t>(game_idx) + 1)); }
-
 // ------------------------------------------------------------------------------------------------ rules
 // status(): 0 ongoing, 1 Player1 won, 2 Player2 won, 3 draw
-struct PosKey {
-    u128 a, b;
-    bool operator==(const PosKey& o) const { return a == o.a && b == o.b; }
-};
 struct PosKeyHash {
     size_t operator()(const PosKey& k) const {
         auto mix = [](uint64_t x) {
@@ -114,199 +55,6 @@ struct PosKeyHash {
         uint64_t h = mix(static_cast<uint64_t>(k.a)) ^ (mix(static_cast<uint64_t>(k.a >> 64) + 0x9E3779B97F4A7C15ull) * 3);
         h ^= mix(static_cast<uint64_t>(k.b) + 0x632BE59BD9B4E019ull) * 5 ^ (mix(static_cast<uint64_t>(k.b >> 64) + 0x1234567ull) * 7);
         return static_cast<size_t>(mix(h));
-    }
-};
-
-// Board word W: uint64_t for boards up to 8x8 (every shipped hex config: half the node size and single-instruction bit
-// operations), unsigned __int128 up to 11x11 (the reference's u128, hex/core.rs:52-54).
-static inline int ctz_word(uint64_t x) { return __builtin_ctzll(x); }
-static inline int ctz_word(u128 x) { return ctz128(x); }
-
-template <class W>
-struct HexPosT {
-    W red = 0, blue = 0, left_red_reach = 0, top_blue_reach = 0;
-    uint8_t turn = 1, empty = 0, winner = 0;
-};
-
-// engine/src/hex/core.rs
-template <class W>
-struct HexRulesT {
-    using Pos = HexPosT<W>;
-    using Move = uint8_t;
-    static constexpr bool kChess = false;
-    int max_children() const { return cells; }
-    static W bit(int i) { return static_cast<W>(1) << i; }
-    int s = 0, cells = 0;
-    W full = 0, col0 = 0, col_last = 0, row0 = 0, row_last = 0;
-    W nb[121];
-    uint8_t tr[121];
-
-    explicit HexRulesT(int size) : s(size), cells(size * size) {
-        full = cells == static_cast<int>(8 * sizeof(W)) ? ~static_cast<W>(0) : static_cast<W>(bit(cells) - 1);
-        const int dirs[6][2] = {{0, 1}, {-1, 0}, {-1, -1}, {0, -1}, {1, 0}, {1, 1}};  // core.rs:204
-        for (int r = 0; r < s; ++r)
-            for (int c = 0; c < s; ++c) {
-                const int i = r * s + c;
-                tr[i] = static_cast<uint8_t>(c * s + r);
-                nb[i] = 0;
-                for (auto& d : dirs) {
-                    const int nr = r + d[0], nc = c + d[1];
-                    if (nr >= 0 && nr < s && nc >= 0 && nc < s) nb[i] |= bit(nr * s + nc);
-                }
-                if (c == 0) col0 |= bit(i);
-                if (c == s - 1) col_last |= bit(i);
-                if (r == 0) row0 |= bit(i);
-                if (r == s - 1) row_last |= bit(i);
-            }
-    }
-    int moves_num() const { return cells; }
-    int words_per_plane() const { return 2; }  // u128 -> [lo, hi] (serialize/hex.rs:16-28); the C ABI uses ceil(S*S/64)
-    Pos initial() const {
-        Pos p;
-        p.empty = static_cast<uint8_t>(cells);
-        return p;
-    }
-    int status(const Pos& p) const {  // core.rs:314-322
-        if (p.winner) return p.winner;
-        if (p.empty == 0) return 3;
-        return 0;
-    }
-    u128 legal_mask(const Pos& p) const { return static_cast<u128>(static_cast<W>(full & ~(p.red | p.blue))); }  // core.rs:297-305 (ascending index)
-    // core.rs:215-264: flood the player's reach map from the new stone; the first end-edge cell reached wins.
-    void update_reach(Pos& p, int idx, int player) const {
-        const W board = player == 1 ? p.red : p.blue;
-        W& reach = player == 1 ? p.left_red_reach : p.top_blue_reach;
-        const W begin = player == 1 ? col0 : row0;
-        const W end = player == 1 ? col_last : row_last;
-        if (!((begin & bit(idx)) || (nb[idx] & reach))) return;
-        W layer = bit(idx);
-        reach |= layer;
-        while (layer) {
-            const int i = ctz_word(layer);
-            layer &= static_cast<W>(~bit(i));
-            if (end & bit(i)) {
-                p.winner = static_cast<uint8_t>(player);
-            } else {
-                const W add = nb[i] & board & static_cast<W>(~reach);
-                reach |= add;
-                layer |= add;
-            }
-        }
-    }
-    Pos moved(const Pos& p, int m) const {  // core.rs:272-285
-        Pos r = p;
-        if (r.turn == 1)
-            r.red |= bit(m);
-        else
-            r.blue |= bit(m);
-        update_reach(r, m, r.turn);
-        r.empty -= 1;
-        r.turn = static_cast<uint8_t>(3 - r.turn);
-        return r;
-    }
-    W transpose(W bb) const {  // HexBitboard::flip, core.rs:61-71
-        W f = 0;
-        while (bb) {
-            const int i = ctz_word(bb);
-            bb &= bb - 1;
-            f |= bit(tr[i]);
-        }
-        return f;
-    }
-    Pos flipped(const Pos& p) const {  // core.rs:324-334
-        Pos r;
-        r.red = transpose(p.blue);
-        r.blue = transpose(p.red);
-        r.turn = static_cast<uint8_t>(3 - p.turn);
-        r.left_red_reach = transpose(p.top_blue_reach);
-        r.top_blue_reach = transpose(p.left_red_reach);
-        r.empty = p.empty;
-        r.winner = p.winner ? static_cast<uint8_t>(3 - p.winner) : 0;
-        return r;
-    }
-    // the part of flipped() the evaluator needs (planes, legal mask, cache key): boards and turn only
-    Pos flipped_boards(const Pos& p) const {
-        Pos r;
-        r.red = transpose(p.blue);
-        r.blue = transpose(p.red);
-        r.turn = static_cast<uint8_t>(3 - p.turn);
-        r.empty = p.empty;
-        return r;
-    }
-    int flip_move(int m) const { return tr[m]; }  // core.rs:36-38
-    bool same(const Pos& a, const Pos& b) const { return a.red == b.red && a.blue == b.blue && a.turn == b.turn; }
-    bool child_matches(const Pos& parent, int m, const Pos& target) const {
-        const W red = parent.turn == 1 ? static_cast<W>(parent.red | bit(m)) : parent.red;
-        const W blue = parent.turn == 1 ? parent.blue : static_cast<W>(parent.blue | bit(m));
-        return red == target.red && blue == target.blue && target.turn == 3 - parent.turn;
-    }
-    PosKey key(const Pos& p) const { return PosKey{static_cast<u128>(p.red), static_cast<u128>(p.blue)}; }
-    // position_to_planes (hex/net.rs:14-24): [red, blue, ones]
-    void planes(const Pos& p, u128 out[3]) const {
-        out[0] = p.red;
-        out[1] = p.blue;
-        out[2] = full;
-    }
-};
-
-struct TttPos {
-    uint16_t x = 0, o = 0;
-    uint8_t turn = 1, winner = 0;
-};
-
-// engine/src/ttt/core.rs
-struct TttRules {
-    using Pos = TttPos;
-    using Move = uint8_t;
-    static constexpr bool kChess = false;
-    int max_children() const { return 9; }
-    int moves_num() const { return 9; }
-    int words_per_plane() const { return 1; }
-    Pos initial() const { return Pos(); }
-    static uint8_t winner_of(uint16_t x, uint16_t o) {  // core.rs:170-193: x before o on every line, in this order
-        static const uint16_t lines[8] = {0b111000000, 0b000111000, 0b000000111, 0b100100100, 0b010010010, 0b001001001, 0b100010001, 0b001010100};
-        for (uint16_t w : lines) {
-            if ((x & w) == w) return 1;
-            if ((o & w) == w) return 2;
-        }
-        return 0;
-    }
-    int status(const Pos& p) const {
-        if (p.winner) return p.winner;
-        if ((p.x | p.o) == 0x1FF) return 3;
-        return 0;
-    }
-    u128 legal_mask(const Pos& p) const { return static_cast<u128>(0x1FFu & ~(p.x | p.o)); }
-    Pos moved(const Pos& p, int m) const {
-        Pos r = p;
-        if (r.turn == 1)
-            r.x |= static_cast<uint16_t>(1u << m);
-        else
-            r.o |= static_cast<uint16_t>(1u << m);
-        r.turn = static_cast<uint8_t>(3 - r.turn);
-        r.winner = winner_of(r.x, r.o);
-        return r;
-    }
-    Pos flipped(const Pos& p) const {
-        Pos r;
-        r.x = p.o;
-        r.o = p.x;
-        r.turn = static_cast<uint8_t>(3 - p.turn);
-        r.winner = p.winner ? static_cast<uint8_t>(3 - p.winner) : 0;
-        return r;
-    }
-    Pos flipped_boards(const Pos& p) const { return flipped(p); }
-    int flip_move(int m) const { return m; }
-    bool same(const Pos& a, const Pos& b) const { return a.x == b.x && a.o == b.o && a.turn == b.turn; }
-    bool child_matches(const Pos& parent, int m, const Pos& target) const {
-        const Pos c = moved(parent, m);
-        return same(c, target);
-    }
-    PosKey key(const Pos& p) const { return PosKey{p.x, p.o}; }
-    void planes(const Pos& p, u128 out[3]) const {
-        out[0] = p.x;
-        out[1] = p.o;
-        out[2] = 0x1FF;
     }
 };
 
@@ -512,41 +260,6 @@ struct Tree {
         h.expanded = 0;
         return static_cast<int32_t>(b);
     }
-};
-
-struct Params {
-    uint32_t sim_num;
-    float explore_factor;
-    std::vector<std::pair<uint32_t, float>> temperatures;
-    float last_temperature;
-    float noise_alpha, noise_eps;
-    float temperature_at(size_t move_num) const {  // TemperaturePolicy::get_temperature, mod.rs:482-488
-        for (auto& t : temperatures)
-            if (move_num < t.first) return t.second;
-        return last_temperature;
-    }
-};
-
-struct GameRecord {
-    uint32_t game_idx = 0;
-    uint8_t winner = 0;
-    std::vector<uint16_t> moves;  // hex / ttt: cell index; chess: from | to << 6 | promotion << 12, real board coordinates
-    std::vector<std::vector<uint8_t>> entries;
-    std::vector<uint8_t> entry_dir;
-};
-
-struct Shared {
-    // merged from the workers' private counters when they finish (no shared cache line on the per-simulation path)
-    uint64_t simulations = 0, searches = 0, evaluations = 0, cache_hits = 0, cache_misses = 0, batches = 0, terminal = 0, speculative = 0;
-    uint32_t w1 = 0, w2 = 0, d = 0, games = 0;
-    std::atomic<uint32_t> next_game{0};
-    std::mutex mu;  // records, search_duration, first error
-    std::vector<GameRecord> records;
-    double search_duration = 0.0;
-    double eval_wait = 0.0;
-    int error_code = 0;
-    std::string error;
-    std::atomic<bool> failed{false};
 };
 
 template <class Rules>
@@ -930,7 +643,7 @@ class Worker {
         for (size_t pos_idx = 0; pos_idx < s.pending_entries.size(); ++pos_idx) {
             auto& pe = s.pending_entries[pos_idx];
             std::vector<uint8_t> bytes;
-            const int dir = make_entry(s.game_idx, pe.first, pe.second, winner, bytes);
+            const int dir = make_entry(R, s.game_idx, pe.first, pe.second, winner, bytes);
             if (cfg_.out_dir1 && cfg_.out_dir2) write_entry_file(dir == 1 ? cfg_.out_dir1 : cfg_.out_dir2, s.game_idx, pos_idx, bytes);
             if (cfg_.keep_records) {
                 s.rec.entries.push_back(std::move(bytes));
@@ -951,77 +664,6 @@ class Worker {
             std::lock_guard<std::mutex> g(sh_.mu);
             sh_.records.push_back(std::move(s.rec));
         }
-    }
-
-    // write_data_entry + serializers (self_play.rs:248-276, :33-61; serialize/hex.rs:16-28; serialize/ttt.rs:17-22)
-    int make_entry(uint32_t game_idx, const Pos& pos_in, const std::vector<std::pair<Move, float>>& probs_in, uint8_t winner,
-                   std::vector<uint8_t>& bytes) const {
-        const int pair_p1[2] = {1, 2}, pair_p2[2] = {2, 1};
-        const int dir = (pos_in.turn == 1 ? pair_p1 : pair_p2)[game_idx % 2];
-        float w = winner == 0 ? 0.0f : (winner == 1 ? 1.0f : -1.0f);
-        if constexpr (kChess) {
-            // ChessSerializer (serialize/chess.rs:18-57).  The stored position and its moves already are the flipped,
-            // Player1-to-move view write_data_entry asks for (self_play.rs:260-268); only the winner's sign follows the turn.
-            if (pos_in.turn != 1) w = -w;
-            std::vector<std::pair<uint16_t, float>> by_idx;
-            by_idx.reserve(probs_in.size());
-            for (auto& mp : probs_in) by_idx.emplace_back(static_cast<uint16_t>(R.nn_idx(mp.first)), mp.second);
-            std::sort(by_idx.begin(), by_idx.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
-            if (by_idx.size() > 225) throw SpError{CATTUS_B200_ERANGE, "more than 225 legal moves"};
-            uint64_t pl[Rules::kPlanes];
-            R.planes(pos_in, pl);
-            bytes.assign(Rules::kPlanes * 8 + Rules::kLegalBytes + 225 * 4 + 1, 0);
-            uint8_t* p = bytes.data();
-            std::memcpy(p, pl, sizeof(pl));
-            p += sizeof(pl);
-            float probs[225];
-            for (float& x : probs) x = -1.0f;
-            for (size_t k = 0; k < by_idx.size(); ++k) {
-                p[by_idx[k].first >> 3] |= static_cast<uint8_t>(1u << (by_idx[k].first & 7));
-                probs[k] = by_idx[k].second;
-            }
-            p += Rules::kLegalBytes;
-            std::memcpy(p, probs, sizeof(probs));
-            p += sizeof(probs);
-            *p = static_cast<uint8_t>(static_cast<int8_t>(static_cast<int>(w)));
-            return dir;
-        } else {
-        Pos pos = pos_in;
-        const bool flipped = pos.turn != 1;
-        if (flipped) {
-            pos = R.flipped(pos);
-            w = -w;
-        }
-        const int M = R.moves_num();
-        std::vector<float> dense(M, -1.0f);
-        for (auto& mp : probs_in) dense[flipped ? R.flip_move(mp.first) : mp.first] = mp.second;
-        u128 pl[3];
-        R.planes(pos, pl);
-        const int wpp = R.words_per_plane();
-        bytes.resize(3 * wpp * 8 + M * 4 + 1);
-        uint8_t* p = bytes.data();
-        for (int c = 0; c < 3; ++c)
-            for (int k = 0; k < wpp; ++k) {
-                const uint64_t word = static_cast<uint64_t>(pl[c] >> (64 * k));
-                std::memcpy(p, &word, 8);
-                p += 8;
-            }
-        std::memcpy(p, dense.data(), M * 4);
-        p += M * 4;
-        *p = static_cast<uint8_t>(static_cast<int8_t>(static_cast<int>(w)));
-        return dir;
-        }
-    }
-
-    void write_entry_file(const char* dir, uint32_t game_idx, size_t pos_idx, const std::vector<uint8_t>& bytes) const {
-        char name[64];
-        std::snprintf(name, sizeof(name), "/%08u_%03zu.traindata", game_idx, pos_idx);  // format!("{game_idx:#08}_{pos_idx:#03}")
-        const std::string path = std::string(dir) + name;
-        FILE* f = std::fopen(path.c_str(), "wb");
-        if (!f) throw SpError{CATTUS_B200_EINVAL, "cannot create " + path};
-        const size_t n = std::fwrite(bytes.data(), 1, bytes.size(), f);
-        std::fclose(f);
-        if (n != bytes.size()) throw SpError{CATTUS_B200_EINVAL, "short write to " + path};
     }
 
     // ---------------------------------------------------------------- MctsPlayer
@@ -1164,12 +806,7 @@ class Worker {
         if (P.noise_alpha == 0.0f || P.noise_eps == 0.0f) return;
         const int32_t count = t.hdr(node).count;
         if (count < 2) return;
-        noise_.resize(count);
-        double tot = 0.0;
-        for (int i = 0; i < count; ++i) {
-            noise_[i] = s.rng.gamma(static_cast<double>(P.noise_alpha));
-            tot += noise_[i];
-        }
+        const double tot = draw_noise(s.rng, P.noise_alpha, count, noise_);
         const float eps = P.noise_eps;
         for (int i = 0; i < count; ++i) {  // zip(edges() order = newest first, noise)
             float& init = t.init_score(node)[count - 1 - i];
@@ -1376,35 +1013,7 @@ class Worker {
         }
         c_.searches += 1;
         if (probs.empty()) throw SpError{CATTUS_B200_EINVAL, "search produced no moves"};
-        // choose_move_from_probabilities
-        const float temperature = P.temperature_at(s.history.size() / 2);
-        int chosen = 0;
-        if (temperature == 0.0f) {
-            for (size_t i = 1; i < probs.size(); ++i)
-                if (!(probs[i].second < probs[chosen].second)) chosen = static_cast<int>(i);  // max_by(total_cmp): last maximum
-        } else {
-            const float inv = 1.0f / temperature;
-            weights_.resize(probs.size());
-            float tot = 0.0f;
-            for (size_t i = 0; i < probs.size(); ++i) {
-                weights_[i] = static_cast<float>(std::pow(static_cast<double>(probs[i].second), static_cast<double>(inv)));
-                tot += weights_[i];
-            }
-            float cum = 0.0f, cum_tot = 0.0f;
-            for (size_t i = 0; i < probs.size(); ++i) {
-                weights_[i] = weights_[i] / tot;
-                cum_tot += weights_[i];
-            }
-            const double x = s.rng.next_f64() * static_cast<double>(cum_tot);
-            chosen = static_cast<int>(probs.size()) - 1;
-            for (size_t i = 0; i < probs.size(); ++i) {
-                cum += weights_[i];
-                if (static_cast<double>(cum) > x) {
-                    chosen = static_cast<int>(i);
-                    break;
-                }
-            }
-        }
+        const int chosen = choose_move(P, s.history.size(), probs, s.rng, weights_);  // choose_move_from_probabilities
         const Move mv = probs[chosen].first;
         s.pending_entries.emplace_back(s.history.back(), std::move(probs));
         if constexpr (kChess) {
