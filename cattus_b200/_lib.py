@@ -49,7 +49,8 @@ class SelfPlayCfg(C.Structure):
         ("cache_size", C.c_uint32), ("threads", C.c_uint32), ("games_per_thread", C.c_uint32), ("leaf_queue", C.c_uint32),
         ("games_num", C.c_uint32), ("first_game", C.c_uint32), ("game_stride", C.c_uint32), ("seed", C.c_uint64),
         ("out_dir1", C.c_char_p), ("out_dir2", C.c_char_p), ("keep_records", C.c_uint32), ("groups_per_thread", C.c_uint32),
-        ("max_moves", C.c_uint32), ("speculate", C.c_uint32),
+        ("max_moves", C.c_uint32), ("speculate", C.c_uint32), ("device_games", C.c_uint32), ("device_tree_kwords", C.c_uint32),
+        ("device_waves_in_flight", C.c_uint32),
     ]
 
 

@@ -512,7 +512,7 @@ static inline int grid_for(long long work_items, int threads, int sm_count) {
 }
 
 std::vector<Op>& Engine::ops_for(Lane& lane, uint32_t bucket, bool dense_input) {
-    const uint32_t key = bucket | (dense_input ? 0x80000000u : 0u);
+    const uint32_t key = bucket | (dense_input ? 0x80000000u : 0u) | (lane.device_out ? 0x40000000u : 0u);
     auto it = lane.ops.find(key);
     if (it != lane.ops.end()) return it->second;
     std::vector<Op> ops;
@@ -535,7 +535,7 @@ void Engine::add_tail_ops(Lane& lane, uint32_t bucket, std::vector<Op>& ops, boo
         const float* hidden = lane.d_hidden.as<float>();
         const float* w2 = vfc2_w_.as<float>();
         const float b2 = vfc2_b_;
-        float* values = zero_copy_out(bucket, dense_input) ? lane.zc_values : lane.d_values.as<float>();
+        float* values = zero_copy_out(lane, bucket, dense_input) ? lane.zc_values : lane.d_values.as<float>();
         const int blocks = static_cast<int>(ceil_div(bucket * 32, 256));
         op.launch = [=](cudaStream_t st) { value_tail_kernel<<<blocks, 256, 0, st>>>(hidden, 128, w2, b2, n_ptr, values); };
         ops.push_back(op);
@@ -546,7 +546,7 @@ void Engine::add_tail_ops(Lane& lane, uint32_t bucket, std::vector<Op>& ops, boo
         op.stage = 3;
         op.name = "policy_tail";
         const float* logits = lane.d_logits.as<float>();
-        float* probs = zero_copy_out(bucket, dense_input) ? lane.zc_probs : lane.d_probs.as<float>();
+        float* probs = zero_copy_out(lane, bucket, dense_input) ? lane.zc_probs : lane.d_probs.as<float>();
         const int blocks = static_cast<int>(ceil_div(bucket * 32, 256));
         op.launch = [=](cudaStream_t st) { policy_tail_kernel<<<blocks, 256, 0, st>>>(logits, ld_logits, recs, L, n_ptr, probs); };
         ops.push_back(op);
@@ -835,7 +835,7 @@ void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
         p.epi = 1;
         p.w2 = vfc2_w_.as<float>();
         p.b2 = vfc2_b_;
-        p.values = zero_copy_out(bucket, dense_input) ? lane.zc_values : lane.d_values.as<float>();
+        p.values = zero_copy_out(lane, bucket, dense_input) ? lane.zc_values : lane.d_values.as<float>();
         p.n_ptr = n_ptr;
         op = make_tc_op(2, "value_fc1_tanh", p, ceil_div(bucket, 128), 1);
         value_tc = p;
@@ -849,7 +849,7 @@ void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
         p.epi = fuse_policy ? 2 : 3;
         p.recs = recs;
         p.rl = L;
-        p.probs = zero_copy_out(bucket, dense_input) ? lane.zc_probs : lane.d_probs.as<float>();
+        p.probs = zero_copy_out(lane, bucket, dense_input) ? lane.zc_probs : lane.d_probs.as<float>();
         p.n_ptr = n_ptr;
         op = make_tc_op(2, fuse_policy ? "policy_fc_softmax" : "policy_fc_masked", p, ceil_div(bucket, 128), pfc_.n_tiles);
     }
@@ -860,7 +860,7 @@ void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
         dp.b.epi = fuse_policy ? 2 : 3;
         dp.b.recs = recs;
         dp.b.rl = L;
-        dp.b.probs = zero_copy_out(bucket, dense_input) ? lane.zc_probs : lane.d_probs.as<float>();
+        dp.b.probs = zero_copy_out(lane, bucket, dense_input) ? lane.zc_probs : lane.d_probs.as<float>();
         dp.b.n_ptr = n_ptr;
         dp.a = value_tc;
         ops.pop_back();
@@ -878,7 +878,7 @@ void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
         Op op;
         op.stage = 3;
         op.name = "softmax_compact";
-        float* probs = zero_copy_out(bucket, dense_input) ? lane.zc_probs : lane.d_probs.as<float>();
+        float* probs = zero_copy_out(lane, bucket, dense_input) ? lane.zc_probs : lane.d_probs.as<float>();
         const int blocks = static_cast<int>(ceil_div(bucket * 32, 256));
         op.launch = [=](cudaStream_t st) { softmax_compact_kernel<<<blocks, 256, 0, st>>>(recs, L, n_ptr, probs); };
         ops.push_back(op);
@@ -893,7 +893,7 @@ void Engine::run_bucket(Lane& lane, uint32_t bucket, cudaStream_t stream, bool u
         CB2_CUDA(cudaGetLastError());
         return;
     }
-    const uint32_t key = bucket | (dense_input ? 0x80000000u : 0u);
+    const uint32_t key = bucket | (dense_input ? 0x80000000u : 0u) | (lane.device_out ? 0x40000000u : 0u);
     auto it = lane.graphs.find(key);
     if (it == lane.graphs.end()) {
         // capture on the lane's own stream (never on a caller's stream)
@@ -1015,7 +1015,7 @@ void Engine::submit(Lane& l, uint32_t n, uint32_t total_probs) {
     *reinterpret_cast<uint32_t*>(l.h_in) = n;
     CB2_CUDA(cudaMemcpyAsync(l.d_in.p, l.h_in, 16 + static_cast<size_t>(n) * rec_.rec_bytes, cudaMemcpyHostToDevice, l.stream));
     run_bucket(l, bucket_for(n), l.stream, true, false);
-    if (!zero_copy_out(bucket_for(n), false)) {  // small batches wrote h_values / h_probs directly (mapped pinned memory)
+    if (!zero_copy_out(l, bucket_for(n), false)) {  // small batches wrote h_values / h_probs directly (mapped pinned memory)
         CB2_CUDA(cudaMemcpyAsync(l.h_values, l.d_values.p, sizeof(float) * n, cudaMemcpyDeviceToHost, l.stream));
         if (total_probs) CB2_CUDA(cudaMemcpyAsync(l.h_probs, l.d_probs.p, sizeof(float) * total_probs, cudaMemcpyDeviceToHost, l.stream));
     }
@@ -1443,12 +1443,58 @@ void Engine::resident_download(uint32_t n, float* probs_out, size_t probs_cap, u
     std::memcpy(prob_offsets, resident_offsets_.data(), sizeof(uint32_t) * (n + 1));
     const uint32_t total = prob_offsets[n];
     if (total > probs_cap) throw Error(CATTUS_B200_ERANGE, "probs_cap is smaller than the number of legal moves");
-    if (zero_copy_out(bucket_for(n), false)) {
+    if (zero_copy_out(l, bucket_for(n), false)) {
         std::memcpy(probs_out, l.h_probs, sizeof(float) * total);
         std::memcpy(values_out, l.h_values, sizeof(float) * n);
     } else {
         CB2_CUDA(cudaMemcpy(probs_out, l.d_probs.p, sizeof(float) * total, cudaMemcpyDeviceToHost));
         CB2_CUDA(cudaMemcpy(values_out, l.d_values.p, sizeof(float) * n, cudaMemcpyDeviceToHost));
+    }
+}
+
+Engine::ResidentIo Engine::resident_acquire() {
+    CB2_CUDA(cudaSetDevice(device_));
+    Lane& l = acquire_lane();
+    l.device_out = true;
+    ResidentIo io;
+    io.lane = l.index;
+    io.d_block = l.d_in.as<uint8_t>();
+    io.d_values = l.d_values.as<float>();
+    io.d_probs = l.d_probs.as<float>();
+    io.rec_bytes = static_cast<uint32_t>(rec_.rec_bytes);
+    io.plane_words = static_cast<uint32_t>(rec_.planes * rec_.wpp);
+    io.max_batch = max_batch_;
+    io.moves = d_.moves;
+    try {
+        io.kernels = static_cast<uint32_t>(ops_for(l, bucket_for(max_batch_), false).size());
+    } catch (...) {
+        l.device_out = false;
+        release_lane(l);
+        throw;
+    }
+    return io;
+}
+
+void Engine::resident_enqueue(int lane, cudaStream_t stream) {
+    Lane& l = *lanes_.at(static_cast<size_t>(lane));
+    run_bucket(l, bucket_for(max_batch_), stream, false, false);
+}
+
+void Engine::resident_release(int lane) {
+    Lane& l = *lanes_.at(static_cast<size_t>(lane));
+    l.device_out = false;
+    release_lane(l);
+}
+
+void Engine::note_resident(uint64_t batches, uint64_t positions, uint64_t launches, double last_seconds) {
+    std::lock_guard<std::mutex> g(m_mu_);
+    metrics_.activation_count += batches;
+    metrics_.positions += positions;
+    metrics_.kernel_launches += launches;
+    if (batches) {
+        metrics_.run_duration_last = last_seconds;
+        metrics_.run_duration_ema = metrics_.run_duration_ema * (1.0 - 0.99) + last_seconds * 0.99;
+        metrics_.mean_batch_fill = static_cast<double>(metrics_.positions) / (static_cast<double>(metrics_.activation_count) * max_batch_);
     }
 }
 
@@ -1537,6 +1583,8 @@ void Engine::get_metrics(cattus_b200_metrics* m) const {
 struct cattus_b200 {
     cb2::Engine* engine;
 };
+
+#include "dsearch.cuh"
 
 static thread_local std::string g_last_error;
 

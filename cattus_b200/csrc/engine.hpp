@@ -102,7 +102,8 @@ struct Lane {
     DeviceBuf d_hidden;    // value FC1 output [max_batch][128] f32
     DeviceBuf d_logits;    // [max_batch][ld_logits] f32
     DeviceBuf d_dense;     // run_dense / encode staging (f32 NCHW)
-    std::map<uint32_t, std::vector<Op>> ops;     // key: bucket | (dense_input << 31)
+    bool device_out = false;  // outputs stay in d_values / d_probs whatever the batch size (device-resident search)
+    std::map<uint32_t, std::vector<Op>> ops;     // key: bucket | (dense_input << 31) | (device_out << 30)
     std::map<uint32_t, cudaGraphExec_t> graphs;  // same key
     // asynchronous batch in flight on this lane (eval_batch_submit .. eval_batch_wait)
     uint32_t async_n = 0, async_total = 0;
@@ -164,12 +165,27 @@ class Engine {
     void resident_download(uint32_t n, float* probs_out, size_t probs_cap, uint32_t* prob_offsets, float* values_out);
     void time_stage(uint32_t stage, uint32_t n, uint32_t iters, float* ms_out);
 
+    // Device-resident callers (the search of dsearch.cuh): reserve a lane, write records straight into its device input
+    // block, enqueue the evaluator's kernels on a stream of their own (capturable), read d_values / d_probs on the device.
+    struct ResidentIo {
+        int lane = -1;
+        uint8_t* d_block = nullptr;  // [u32 n][12 B pad][record 0 prefix 8 B | planes | legal bitmap] ...
+        float* d_values = nullptr;
+        float* d_probs = nullptr;    // capacity max_batch * moves floats
+        uint32_t rec_bytes = 0, plane_words = 0, max_batch = 0, moves = 0, kernels = 0;
+    };
+    ResidentIo resident_acquire();
+    void resident_enqueue(int lane, cudaStream_t stream);  // the max_batch bucket's launch sequence; rows read from the block
+    void resident_release(int lane);
+    void note_resident(uint64_t batches, uint64_t positions, uint64_t launches, double last_seconds);
+    int device() const { return device_; }
+
   private:
     // setup
     void upload_weights(const Blob& blob);
     void init_lane(Lane& lane);
     uint32_t bucket_for(uint32_t n) const;
-    bool zero_copy_out(uint32_t bucket, bool dense_input) const { return !dense_input && bucket <= 512; }
+    bool zero_copy_out(const Lane& lane, uint32_t bucket, bool dense_input) const { return !dense_input && !lane.device_out && bucket <= 512; }
     std::vector<Op>& ops_for(Lane& lane, uint32_t bucket, bool dense_input);
     void build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, bool dense_input);
     void build_ops_fp32(Lane& lane, uint32_t bucket, std::vector<Op>& ops, bool dense_input);

@@ -38,6 +38,7 @@
 #include <sys/types.h>
 
 #include "../../include/cattus_b200_selfplay.h"
+#include "dsearch_api.hpp"
 #include "sp_common.hpp"
 
 namespace sp {
@@ -1336,7 +1337,7 @@ static int selfplay_impl(sp::Evaluator& e1, sp::Evaluator* e2_or_null, const cat
         } else if (cfg->game != CATTUS_B200_GAME_TTT && cfg->game != CATTUS_B200_GAME_CHESS) {
             throw sp::SpError{CATTUS_B200_EINVAL, "unknown game"};
         }
-        if (cfg->cache_size) {
+        if (cfg->cache_size && !cfg->device_games) {
             // room per entry: the most legal moves a position can have, plus the value
             const int moves_num = cfg->game == CATTUS_B200_GAME_TTT     ? 9
                                   : cfg->game == CATTUS_B200_GAME_CHESS ? sp::ChessRules::kMaxMoves
@@ -1351,7 +1352,12 @@ static int selfplay_impl(sp::Evaluator& e1, sp::Evaluator* e2_or_null, const cat
         }
         sp::Shared sh;
         const auto t0 = sp::Clock::now();
-        if (cfg->game == CATTUS_B200_GAME_HEX) {
+        if (cfg->device_games) {
+            // trees in HBM, one warp per game (dsearch_core.hpp): needs the B200 evaluator's device buffers
+            if (!e1.async_handle || (e2_or_null && !e2_or_null->async_handle))
+                throw sp::SpError{CATTUS_B200_EINVAL, "device_games needs the B200 evaluator (cattus_b200_selfplay_run); a callback evaluator has no device buffers"};
+            cb2::dsearch_run(e1.async_handle, e2_or_null ? e2_or_null->async_handle : nullptr, *cfg, params, sh);
+        } else if (cfg->game == CATTUS_B200_GAME_HEX) {
             if (cfg->board_size <= 8) {
                 sp::HexRulesT<uint64_t> rules(static_cast<int>(cfg->board_size));
                 run_games(rules, *cfg, params, evals, sh);

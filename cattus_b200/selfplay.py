@@ -115,6 +115,9 @@ class SelfPlayRunner:
         c.groups_per_thread = int(cfg.get("groups_per_thread", 0))
         c.max_moves = int(cfg.get("max_moves", 0))
         c.speculate = int(cfg.get("speculate", 0))
+        c.device_games = int(cfg.get("device_games", 0))
+        c.device_tree_kwords = int(cfg.get("device_tree_kwords", 0))
+        c.device_waves_in_flight = int(cfg.get("device_waves_in_flight", 0))
         c.seed = int(cfg.get("seed", 0)) & 0xFFFFFFFFFFFFFFFF
         self._c = c
 

@@ -76,6 +76,14 @@ typedef struct cattus_b200_selfplay_cfg {
                          * best-prior children of nodes expanded before.  Every search is unchanged (the cache returns what a
                          * fresh evaluation would); only batches below 192 rows are topped up.  For the UCI search and for
                          * trainer-sized jobs (a hundred games over a few threads); 0 = off, as the reference */
+    uint32_t device_games; /* > 0: DEVICE-RESIDENT search (needs the B200 evaluator).  This many games run concurrently with
+                            * their search trees in HBM, one warp per game: select, expansion and backpropagation run on
+                            * the GPU, leaves go straight into the evaluator's device batch, and the host only acts once per
+                            * MOVE (move choice, Dirichlet sample, game status, .traindata).  Same games, move for move and
+                            * byte for byte, as the host-tree driver; threads / games_per_thread / cache_size / speculate /
+                            * leaf_queue are ignored.  Must not exceed the evaluator's max_batch.  0 = trees on the host */
+    uint32_t device_tree_kwords;     /* per tree buffer, in 1024 32-bit words; 0 = sized from sim_num and the free memory */
+    uint32_t device_waves_in_flight; /* select -> evaluate -> expand rounds queued ahead of the host; 0 = 2 */
 } cattus_b200_selfplay_cfg;
 
 /* Mirrors the summary file (self_play_cmd.rs:131-149) and the metric keys the trainer reads
