@@ -61,6 +61,25 @@ CONFIG_NOTES = {
 }
 
 
+def workload_config(workload: str, batch: int, per_step: int, cpu_sample: int) -> dict:
+    """The `config` object BOTH arms print (identical by construction): what is evaluated, not how."""
+    from oracle import net
+
+    cfg_name, _, _ = WORKLOADS[workload]
+    cfg = net.CONFIGS[cfg_name]
+    return {"workload": workload, "note": CONFIG_NOTES.get(workload, ""), "net": cfg.to_dict(),
+            "weights": "random-init (numpy PCG64 seed 0), BN folded", "positions": "synthetic (SURVEY.md section 8d generator)",
+            "positions_per_step": {"cattus_b200": batch * per_step, "reference": cpu_sample,
+                                   "why": "the reference arm times a bounded sample of the same workload on the host cores"},
+            "device_batch": batch,
+            "l2": "cattus_b200 arm: 256 MiB memset before every timed device batch (inputs are far smaller than L2); reference arm: CPU, n/a",
+            "parallelism": "replicas, one evaluator per GPU, no collective on the data path"}
+
+
+def cpu_sample_for(args, cfg) -> int:
+    return args.cpu_sample or (256 if cfg.filters >= 64 else 2048)
+
+
 def load_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -310,31 +329,59 @@ def cpu_batch_sweep(cfg, batches=(1, 8, 64, 256, 1024), seconds_each=1.2, seed=9
 
 
 def run_reference_arm(args, rank, world):
+    """The reference's CPU inference path on the host cores.  Nothing of the repo's library is loaded into this process:
+    the headline uses torch + oracle/ only, and the self-play legs (which need a search driver around the CPU evaluator) run
+    in a child process (`--impl reference-selfplay`)."""
     from oracle import net
 
     if rank != 0:
         return
-    cfg_name, _, _ = WORKLOADS[args.workload]
+    cfg_name, batch, per_step = WORKLOADS[args.workload]
+    if args.batch:
+        batch = args.batch
     cfg = net.CONFIGS[cfg_name]
-    sample_n = args.cpu_sample or (256 if cfg.filters >= 64 else 2048)
+    sample_n = cpu_sample_for(args, cfg)
     value, cores, sec_per_step, desc = time_cpu_reference(cfg, sample_n, budget_s=0, steps=max(1, args.steps), warmup=max(1, args.warmup))
     line = {
         "impl": "reference", "metric": "nn_evals_per_sec", "value": value, "unit": "positions/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "note": CONFIG_NOTES.get(args.workload, ""), "positions_per_step": sample_n,
-                   "reference": "CPU inference path of the reference (host cores only; the reference has no GPU kernels)"},
+        "config": workload_config(args.workload, batch, per_step, sample_n),
+        "reference": "CPU inference path of the reference (host cores only; the reference has no GPU kernels): torch-py engine restated "
+                     "(engine/src/net/model.rs:68-84) + C restatement of planes_to_tensor / calc_moves_probs",
         "cpu_baseline": {"value": value, "unit": "positions/s", "cores": cores, "kind": "port", "sample": desc,
                          "model_run_duration_batch1_us": time_cpu_run_duration_batch1(cfg) * 1e6},
         "e2e": {"value": value, "unit": "positions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     line["batch_sweep"] = cpu_batch_sweep(cfg)
+    if args.workload == DEFAULT_WORKLOAD and not args.no_other_workloads:
+        # BASELINE configs[0]: hex 4x4 on the current CPU inference backend ("runs today on CPU")
+        hcfg = net.CONFIGS["hex4"]
+        hv, hcores, _, hdesc = time_cpu_reference(hcfg, 2048, budget_s=2.0)
+        line["other_workloads"] = [{"workload": "hex4", "note": CONFIG_NOTES["hex4"], "value": hv, "unit": "positions/s", "cores": hcores, "sample": hdesc}]
     if not args.no_selfplay:
-        legs = [time_cpu_selfplay(g, 2, 2, cpu_selfplay_max_moves(args, g)) for g in args.selfplay_game]
-        line["selfplay"] = legs[0]
-        line["selfplay_others"] = legs[1:]
+        cmd = [sys.executable, str(ROOT / "bench.py"), "--impl", "reference-selfplay", "--selfplay-game", *args.selfplay_game,
+               "--selfplay-max-moves", str(args.selfplay_max_moves)]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        legs = None
+        for ln in res.stdout.splitlines():
+            if ln.startswith("{"):
+                legs = json.loads(ln)["legs"]
+        if legs:
+            line["selfplay"] = legs[0]
+            line["selfplay_others"] = legs[1:]
+        else:
+            line["selfplay"] = {"unavailable": (res.stderr or "no output")[-400:]}
     print(json.dumps(line), flush=True)
+
+
+def run_reference_selfplay(args):
+    """Child process of the reference arm: the repo's search driver bound to the reference's CPU evaluator (one tree per OS
+    thread, one leaf at a time -- the reference's arrangement).  This is 'repo driver + CPU evaluator', the closest runnable
+    stand-in for the reference's Rust self-play executable (no cargo here)."""
+    legs = [time_cpu_selfplay(g, 2, 2, cpu_selfplay_max_moves(args, g)) for g in args.selfplay_game]
+    print(json.dumps({"legs": legs}), flush=True)
 
 
 def main():
@@ -342,7 +389,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="cattus_b200", choices=["cattus_b200", "reference"])
+    ap.add_argument("--impl", default="cattus_b200", choices=["cattus_b200", "reference", "reference-selfplay"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="device batch (positions per launch sequence); default per workload")
     ap.add_argument("--streams", type=int, default=4)
@@ -351,8 +398,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-selfplay", action="store_true", help="skip the self-play sims/s leg")
     ap.add_argument("--no-other-workloads", action="store_true", help="skip the brief hex5 evals/s leg of the default run")
-    ap.add_argument("--selfplay-game", nargs="+", default=["hex5", "chess10x128"], choices=sorted(SELFPLAY_CFG),
-                    help="self-play legs: the first is reported as `selfplay` (BASELINE configs[1]), the rest under `selfplay_others` (configs[3])")
+    ap.add_argument("--selfplay-game", nargs="+", default=["hex5", "hex7", "chess10x128"], choices=sorted(SELFPLAY_CFG),
+                    help="self-play legs: the first is reported as `selfplay` (BASELINE configs[1]), the rest under `selfplay_others` "
+                         "(configs[2] hex7, configs[3] chess 10x128)")
+    ap.add_argument("--device-games", type=int, default=0,
+                    help="concurrent device-resident games per GPU in a self-play leg (0 = 16384 for the 16-filter nets, 4096 for chess 10x128)")
+    ap.add_argument("--no-host-driver", action="store_true", help="skip the host-tree driver's sims/s (kept beside the device-resident number)")
+    ap.add_argument("--sustained-seconds", type=float, default=2.2, help="length of the sustained leg (0 = skip)")
     ap.add_argument("--selfplay-games", type=int, default=0, help="games per GPU in a self-play leg (0 = 8192; chess: one wave, threads x games per thread)")
     ap.add_argument("--selfplay-threads", type=int, default=0, help="worker threads per GPU (0 = host cores / GPUs)")
     ap.add_argument("--selfplay-gpt", type=int, default=0, help="concurrent games per worker thread (0 = 512; chess 1024)")
@@ -372,6 +424,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
+        return
+    if args.impl == "reference-selfplay":
+        run_reference_selfplay(args)
         return
     args.warmup = max(args.warmup, 3)
 
@@ -410,26 +465,54 @@ def main():
     sampler.start()
     ms_all = nw.time_stage(4, batch, args.steps * per_step)
     barrier()
+    clocks = sampler.stop()
     t_value = max_over_ranks(float(ms_all.sum()) * 1e-3)
-    # trunk alone (same stream, same L2 flush discipline)
-    nw.time_stage(1, batch, 3)
-    ms_trunk = nw.time_stage(1, batch, max(5, args.steps))
-    ms_enc = nw.time_stage(0, batch, max(5, args.steps))
-    ms_heads = nw.time_stage(2, batch, max(5, args.steps))
-    ms_tail = nw.time_stage(3, batch, max(5, args.steps))
+
+    def timed_with_clocks(fn):
+        """One clock record per measurement: the power-cap state drifts between loops."""
+        smp = ClockSampler(local_rank)
+        smp.start()
+        out = fn()
+        c = smp.stop()
+        return out, {"sm_mhz": c.get("sm_mhz"), "power_w_max": c.get("power_w_max"), "reasons": c.get("reasons")}
+
+    stage_iters = max(8, args.steps)
+    # the stages of ONE pass (no L2 flush between them, as inside the graph): they must add up to the graph
+    nw.time_stage(5, batch, 3)
+    ms_split, clocks_split = timed_with_clocks(lambda: nw.time_stage(5, batch, stage_iters))
+    # the trunk stage alone, L2 flushed (the roofline's kernel), at the north star's batch sizes
+    trunk_alone = {}
+    for nb in sorted({b_ for b_ in (1024, 2048, 4096, batch) if b_ <= batch}):
+        nw.resident_upload(words[:nb], None if bitmaps is None else bitmaps[:nb])
+        nw.time_stage(1, nb, 3)
+        ms_nb, c_nb = timed_with_clocks(lambda nb=nb: nw.time_stage(1, nb, stage_iters))
+        trunk_alone[nb] = (float(np.mean(ms_nb)), c_nb)
+    nw.resident_upload(words[:batch], None if bitmaps is None else bitmaps[:batch])
+    # sustained: >= 2 s of device batches back to back, rotating over 4 distinct resident batches (no L2 flush needed)
+    sustained = None
+    if args.sustained_seconds > 0 and args.streams >= 4 and per_step >= 4:
+        iters = max(50, int(args.sustained_seconds / (float(np.mean(ms_all)) * 1e-3)))
+        nw.time_sustained(words, bitmaps, batch, 4, 20)
+        barrier()
+        ms_sus, clocks_sus = timed_with_clocks(lambda: nw.time_sustained(words, bitmaps, batch, 4, iters))
+        barrier()
+        sustained = {"device_batches": iters, "distinct_resident_batches": 4, "seconds": ms_sus * 1e-3, "ms_per_device_batch": ms_sus / iters,
+                     "positions_per_sec": world * iters * batch / (max_over_ranks(ms_sus * 1e-3)), "clocks": clocks_sus}
     barrier()
 
     # ---------------- end to end through the C ABI with host buffers
     for _ in range(args.warmup):
         nw.eval_batch(words, bitmaps)
     barrier()
+    e2e_sampler = ClockSampler(local_rank)
+    e2e_sampler.start()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         probs, offsets, values = nw.eval_batch(words, bitmaps)
     torch.cuda.synchronize(local_rank)
     t_e2e_local = time.perf_counter() - t0
     barrier()
-    clocks = sampler.stop()
+    clocks_e2e = e2e_sampler.stop()
     t_e2e = max_over_ranks(t_e2e_local)
     launches = nw.metrics()["model.kernel_launches"] - launches0
     # per position: 8-byte prefix (probability offset, #legal) + packed planes (+ the legal bitmap padded to 8 B for chess)
@@ -437,12 +520,11 @@ def main():
     h2d = positions_per_step * rec_bytes + 16 * per_step
     d2h = int(offsets[-1]) * 4 + positions_per_step * 4
     kernels_per_batch = nw.info.kernels_per_batch
-    fused = bool(nw.info.reserved & 1)
-    small = bool(nw.info.reserved & 2)
+    fused, small, trunk_path = nw.fused_trunk, nw.small_trunk, nw.trunk_path
     # ---------------- batch-size sweep (BASELINE configs[4]): whole graph, inputs resident, L2 flushed, CUDA events
     sweep = []
     if rank == 0:
-        for nb in (1, 8, 64, 512, 4096):
+        for nb in (1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192):  # every power of two (BASELINE configs[4]: 1-4096)
             if nb >= batch:
                 continue
             nw.resident_upload(words[:nb], None if bitmaps is None else bitmaps[:nb])
@@ -453,7 +535,7 @@ def main():
     # ---------------- per-leaf latency: one blocking cattus_b200_eval at a time (what a single-tree UCI search sees;
     # BASELINE configs[4], `--sim-num 10000`: NN part of one search = 10000 x this)
     leaf = None
-    if rank == 0:
+    if rank == 0 and world == 1:
         k = min(2000, positions_per_step)
         for i in range(50):
             nw.eval_planes(words[i], None if bitmaps is None else bitmaps[i])
@@ -474,7 +556,7 @@ def main():
     # On the production path both are fused away (encode into the trunk kernels, mask/softmax into the policy FC
     # epilogue), so the standalone kernels of the unfused comparison path (flags bit 0) are timed here as evidence.
     hbm_kernels = []
-    if rank == 0 and not args.no_other_workloads:
+    if rank == 0 and world == 1 and not args.no_other_workloads:
         with CudaNetwork(export_blob(sd, cfg.game), cfg.game, device=local_rank, batch_size=batch, n_streams=1, precision="bf16", fused_trunk=False) as unf:
             unf.resident_upload(words[:batch], None if bitmaps is None else bitmaps[:batch])
             for st in (0, 3):
@@ -522,25 +604,26 @@ def main():
                            "e2e": world * 3 * oper * obatch / ote, "unit": "positions/s", "ms_per_device_batch": float(np.mean(oms)),
                            "gpu_launches": int(olaunches)})
 
-    # ---------------- self-play MCTS sims/s (second half of the BASELINE metric): C++ driver + this GPU's evaluator
+    # ---------------- self-play MCTS sims/s (second half of the BASELINE metric).  Headline arrangement: DEVICE-RESIDENT search
+    # (trees in HBM, one warp per game, leaves written straight into the evaluator's device batch; csrc/dsearch_core.hpp) --
+    # the host only acts once per move, so sims/s no longer depends on the host cores per GPU.  The host-tree driver's
+    # number on the same evaluator is kept beside it.
     selfplay_legs = []
     for sp_game in ([] if args.no_selfplay else args.selfplay_game):
         from cattus_b200.selfplay import SelfPlayRunner
 
         sp_cfg = net.CONFIGS[sp_game]
         cores = len(os.sched_getaffinity(0))
-        threads = args.selfplay_threads or max(1, cores // max(1, world))
-        # chess leaves cost ~100x a hex leaf on the GPU: twice the games per worker keep its batches at ~430 positions
         chess_sp = sp_cfg.game == "chess"
-        gpt = args.selfplay_gpt or (1024 if chess_sp else 512)
-        games_total = max(2, (args.selfplay_games or (threads * gpt if chess_sp else 8192)) * world // 2 * 2)
         mc = SELFPLAY_CFG[sp_game]
-        with CudaNetwork(export_blob(net.make_state_dict(sp_cfg, 0), sp_cfg.game), sp_cfg.game, device=local_rank, batch_size=max(64, min(4096, gpt)),
-                         n_streams=max(4, min(32, threads * args.selfplay_groups)), precision="bf16") as sp_nw:
-            sp_max_moves = selfplay_max_moves(args, sp_game)
-            runner = SelfPlayRunner(runner_game(sp_game), {"mcts": mc, "threads": threads, "games_per_thread": gpt,
-                                                                       "groups_per_thread": args.selfplay_groups, "seed": 1, "max_moves": sp_max_moves})
-            runner.generate_data(sp_nw, None, 2 * threads, first_game=rank, game_stride=world)  # warm-up (graphs, caches of the allocator)
+        sp_max_moves = selfplay_max_moves(args, sp_game)
+        sp_blob = export_blob(net.make_state_dict(sp_cfg, 0), sp_cfg.game)
+        dg = args.device_games or (4096 if sp_cfg.filters >= 64 else 16384)
+        games_total = max(2, (args.selfplay_games or dg) * world // 2 * 2)
+        with CudaNetwork(sp_blob, sp_cfg.game, device=local_rank, batch_size=dg, n_streams=1, precision="bf16") as sp_nw:
+            runner = SelfPlayRunner(runner_game(sp_game), {"mcts": mc, "seed": 1, "max_moves": sp_max_moves, "device_games": dg})
+            SelfPlayRunner(runner_game(sp_game), {"mcts": dict(mc, sim_num=16), "seed": 1, "max_moves": 2, "device_games": 64}).generate_data(
+                sp_nw, None, 64 * world, first_game=rank, game_stride=world)  # warm-up: the evaluator's launch sequence, the allocator
             l0 = sp_nw.metrics()["model.kernel_launches"]
             barrier()
             summary, _ = runner.generate_data(sp_nw, None, games_total, first_game=rank, game_stride=world)
@@ -549,12 +632,37 @@ def main():
         m = summary["metrics"]
         sims_all = rep.sum_over_ranks(float(m["selfplay.simulations"]))
         secs = max_over_ranks(float(m["selfplay.seconds"]))
-        selfplay = selfplay_summary_to_dict(sp_game, mc, summary, games_total, threads, gpt, max_moves=sp_max_moves, extra={
+        selfplay = selfplay_summary_to_dict(sp_game, mc, summary, games_total, 1, dg, max_moves=sp_max_moves, extra={
             "value": sims_all / secs, "n_gpus": world, "host_cores": cores, "gpu_launches": int(sp_launches),
-            "note": "rank 0's counters shown; value = simulations of all ranks / max seconds; games partitioned by index across GPUs, no collective"})
+            "arrangement": "device-resident search: trees in HBM, one warp per game, one host thread per GPU acting once per move",
+            "device_games": dg, "waves": m["model.activation_count"], "ms_per_wave": 1e3 * m["selfplay.seconds"] / max(1, m["model.activation_count"]),
+            "note": "rank 0's counters shown; value = simulations of all ranks / max seconds (the whole call: allocation, all games to their end "
+                    "incl. the tail where finished games leave slots empty); games partitioned by index across GPUs, no collective"})
+        del selfplay["threads"], selfplay["games_per_thread"], selfplay["eval_wait_frac"], selfplay["cache_hit_rate"]
+        if not args.no_host_driver:
+            # the host-tree driver (round 1's arrangement) on the same evaluator: bound by the host cores per GPU
+            threads = args.selfplay_threads or max(1, cores // max(1, world))
+            gpt = args.selfplay_gpt or (1024 if chess_sp else 512)
+            h_games = max(2, (threads * gpt if chess_sp else min(8192, threads * gpt)) * world // 2 * 2)
+            h_max_moves = min(sp_max_moves, 8) if chess_sp else sp_max_moves
+            with CudaNetwork(sp_blob, sp_cfg.game, device=local_rank, batch_size=max(64, min(4096, gpt)),
+                             n_streams=max(4, min(32, threads * args.selfplay_groups)), precision="bf16") as h_nw:
+                h_runner = SelfPlayRunner(runner_game(sp_game), {"mcts": mc, "threads": threads, "games_per_thread": gpt,
+                                                                 "groups_per_thread": args.selfplay_groups, "seed": 1, "max_moves": h_max_moves})
+                h_runner.generate_data(h_nw, None, 2 * threads, first_game=rank, game_stride=world)
+                hl0 = h_nw.metrics()["model.kernel_launches"]
+                barrier()
+                h_sum, _ = h_runner.generate_data(h_nw, None, h_games, first_game=rank, game_stride=world)
+                barrier()
+                selfplay["gpu_launches"] += int(h_nw.metrics()["model.kernel_launches"] - hl0)
+            hm = h_sum["metrics"]
+            selfplay["host_driver"] = selfplay_summary_to_dict(sp_game, mc, h_sum, h_games, threads, gpt, max_moves=h_max_moves, extra={
+                "value": rep.sum_over_ranks(float(hm["selfplay.simulations"])) / max_over_ranks(float(hm["selfplay.seconds"])),
+                "arrangement": "trees on the host: worker threads x games per thread, batched leaves (csrc/selfplay.cpp)", "host_cores": cores})
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             selfplay["cpu_baseline"] = time_cpu_selfplay(sp_game, 2, 2, cpu_selfplay_max_moves(args, sp_game))
-        if rank == 0:
+        extras = rank == 0 and world == 1 and sp_game in (args.selfplay_game[0], "chess10x128")  # once per game family, at N = 1 only
+        if extras:
             # The job the trainer actually submits (self_play.games_num 100, engine.threads 8 in the shipped configs): a dozen
             # leaves in flight per worker, so the device batches are nearly empty -- with and without speculative rows.
             with CudaNetwork(export_blob(net.make_state_dict(sp_cfg, 0), sp_cfg.game), sp_cfg.game, device=local_rank, batch_size=256, n_streams=16,
@@ -574,7 +682,7 @@ def main():
                 selfplay["trainer_sized_job"] = {"games": 100, "threads": 8, "runs": trainer,
                                                  "note": "100 games over 8 worker threads (2 slot groups each) as the shipped training configs ask for; speculate = rows per game "
                                                          "evaluated ahead into the cache in the otherwise nearly empty device batches (same games)"}
-        if rank == 0 and args.single_search:
+        if extras and args.single_search:
             with CudaNetwork(export_blob(net.make_state_dict(sp_cfg, 0), sp_cfg.game), sp_cfg.game, device=local_rank, batch_size=64, n_streams=1,
                              precision="bf16") as ss_nw:
                 ss_mc = dict(mc, sim_num=10000)
@@ -621,7 +729,7 @@ def main():
     s2 = cfg.board_size ** 2
     stem_flops = 2 * 9 * cfg.planes * cfg.filters * s2
     trunk_flops = stem_flops + cfg.trunk_flops_per_position
-    t_trunk = float(np.mean(ms_trunk)) * 1e-3
+    t_trunk, clocks_trunk = trunk_alone[batch][0] * 1e-3, trunk_alone[batch][1]
     achieved = batch * trunk_flops / t_trunk / 1e12
     traffic = None
     try:  # DRAM bytes of the same kernel from the committed `ncu --set full` capture (per launch, same workload and batch)
@@ -632,15 +740,34 @@ def main():
                        "dram_bytes_write": te["dram_bytes_write"], "source": te["source"]}
     except Exception:
         traffic = None
+    split = np.mean(ms_split, axis=0)
+    split_sum, all_graph = float(split.sum()), float(np.mean(ms_all))
+    rel = abs(split_sum - all_graph) / all_graph
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
                 "traffic": traffic, "kernel": ("trunk_fused_kernel (stem + residual blocks, one launch)" if fused else
                            "trunk_small_kernel (encode + stem + residual blocks + head convs, one launch)" if small else
                            "tc_gemm_kernel x (1 + 2R) conv layers (stem + residual blocks)"),
+                "trunk_path": trunk_path,
                 "peak_source": peaks["source"] + ", burst figure (stage timed alone)", "flop_per_position": trunk_flops, "positions_per_launch": batch,
-                "ms": t_trunk * 1e3,
-                "stages_ms": {"encode": float(np.mean(ms_enc)), "trunk": float(np.mean(ms_trunk)), "heads": float(np.mean(ms_heads)),
-                              "tail": float(np.mean(ms_tail)), "all_graph": float(np.mean(ms_all))},
-                "whole_net_tflops": batch * cfg.flops_per_position / (float(np.mean(ms_all)) * 1e-3) / 1e12}
+                "ms": t_trunk * 1e3, "clocks": clocks_trunk,
+                # the north star's bar: >= 50 % of the bf16 peak on the trunk at batch >= 1024 -- the trunk stage alone (L2 flushed) per batch size
+                "by_batch": [{"positions_per_launch": nb, "ms": ms_nb, "achieved": nb * trunk_flops / (ms_nb * 1e-3) / 1e12,
+                              "frac": nb * trunk_flops / (ms_nb * 1e-3) / 1e12 / peaks["bf16_tflops"], "clocks": c_nb}
+                             for nb, (ms_nb, c_nb) in sorted(trunk_alone.items())],
+                # stages of ONE pass of the launch sequence (events between the stages, no L2 flush inside the pass)
+                "stages_ms": {"encode_trunk": float(split[0]), "heads": float(split[1]), "tail": float(split[2]), "sum": split_sum,
+                              "all_graph": all_graph, "rel_diff": rel, "clocks": clocks_split,
+                              "trusted": "both (within 3 %)" if rel <= 0.03 else "all_graph (the captured graph, which `value` is made of; the split pass "
+                                                                                 "adds an event record between stages and ran in another power-cap state)"},
+                "whole_net_tflops": batch * cfg.flops_per_position / (all_graph * 1e-3) / 1e12}
+    if sustained is not None:
+        tf = batch * cfg.flops_per_position / (sustained["ms_per_device_batch"] * 1e-3) / 1e12
+        sustained.update({"whole_net_tflops": tf, "peak": peaks["bf16_tflops_sustained"], "frac": tf / peaks["bf16_tflops_sustained"],
+                          # the trunk's share of a pass (split timing) applied to the sustained time per device batch
+                          "trunk_tflops_estimate": batch * trunk_flops / (sustained["ms_per_device_batch"] * 1e-3 * float(split[0]) / split_sum) / 1e12,
+                          "peak_source": peaks["source"] + ", sustained figure (kernels timed inside a seconds-long run)",
+                          "note": "frac = whole-network algorithmic FLOP (trunk + heads) / wall time of the run vs the sustained cuBLAS bf16 peak"})
+    roofline["sustained"] = sustained
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -654,11 +781,11 @@ def main():
             "metric": "nn_evals_per_sec", "value": value, "unit": "positions/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t_value / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": args.workload, "note": CONFIG_NOTES.get(args.workload, ""), "net": cfg.to_dict(), "device_batch": batch,
-                       "positions_per_step": positions_per_step, "streams": args.streams, "parallelism": f"replicas x{world}, no collective",
-                       "l2": "256 MiB memset between timed device batches", "weights": "random-init (numpy PCG64 seed 0), BN folded",
-                       "kernels_per_device_batch": kernels_per_batch},
+            "config": workload_config(args.workload, batch, per_step, cpu_sample_for(args, cfg)),
+            "run": {"streams": args.streams, "replicas": world, "kernels_per_device_batch": kernels_per_batch, "trunk_path": trunk_path,
+                    "positions_per_step": positions_per_step},
             "clocks": clocks,
+            "clocks_e2e": clocks_e2e,
             "e2e": {"value": e2e_value, "unit": "positions/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": t_e2e / args.steps * 1e3, "api": "cattus_b200_eval_batch (host buffers -> pinned block -> H2D -> graph -> D2H)"},
             "gpu_launches": int(launches) + sum(leg["gpu_launches"] for leg in selfplay_legs) + sum(o["gpu_launches"] for o in others),

@@ -14,6 +14,8 @@ from . import build as _build
 OK, EINVAL, ENODEV, ECUDA, ENOMEM, ERANGE, EDEVICE = 0, -1, -2, -3, -4, -5, -6
 GAME_TTT, GAME_HEX, GAME_CHESS = 0, 1, 2
 PRECISION_BF16, PRECISION_FP32_CHECK = 0, 1
+TRUNK_PER_LAYER, TRUNK_FUSED, TRUNK_SMALL, TRUNK_FP32 = 0, 1, 2, 3
+TRUNK_PATH_NAMES = {TRUNK_PER_LAYER: "per-layer", TRUNK_FUSED: "fused", TRUNK_SMALL: "small", TRUNK_FP32: "fp32-check"}
 GAME_IDS = {"ttt": GAME_TTT, "hex": GAME_HEX, "chess": GAME_CHESS}
 
 
@@ -37,7 +39,7 @@ class Info(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in (
         "game", "board_size", "planes", "moves", "filters", "blocks", "value_channels", "policy_channels",
         "words_per_plane", "legal_bitmap_bytes", "max_batch", "n_streams", "precision", "sm_count",
-        "kernels_per_batch", "reserved")]
+        "kernels_per_batch", "trunk_path")]
 
 
 class SelfPlayCfg(C.Structure):
@@ -100,6 +102,7 @@ SYMBOLS = {
     "cattus_b200_eval_resident": (C.c_int, [_H, C.c_uint32, C.c_void_p]),
     "cattus_b200_resident_download": (C.c_int, [_H, C.c_uint32, _f32p, C.c_size_t, _u32p, _f32p]),
     "cattus_b200_time_stage": (C.c_int, [_H, C.c_uint32, C.c_uint32, C.c_uint32, _f32p]),
+    "cattus_b200_time_sustained": (C.c_int, [_H, _u64p, _u8p, C.c_uint32, C.c_uint32, C.c_uint32, _f32p]),
     "cattus_b200_get_metrics": (C.c_int, [_H, C.POINTER(Metrics)]),
     "cattus_b200_last_error": (C.c_char_p, []),
     "cattus_b200_abi_version": (C.c_uint32, []),

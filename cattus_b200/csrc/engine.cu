@@ -1004,6 +1004,9 @@ uint32_t Engine::pack_record(uint8_t* dst, const uint64_t* planes, const uint8_t
         if (rec_.moves % 8) d[bm - 1] &= static_cast<uint8_t>((1u << (rec_.moves % 8)) - 1u);
         const uint64_t* w = reinterpret_cast<const uint64_t*>(d);
         for (int k = 0; k < padded / 8; ++k) cnt += static_cast<uint32_t>(__builtin_popcountll(w[k]));
+        // softmax_compact_kernel holds at most 8 x 32 logits per position; the reference's serializer caps a chess position at
+        // 225 legal moves (serialize/chess.rs:34) and no legal position exceeds 218
+        if (cnt > 256) throw Error(CATTUS_B200_ERANGE, "legal bitmap with " + std::to_string(cnt) + " moves set (at most 256 per position)");
     }
     uint32_t* prefix = reinterpret_cast<uint32_t*>(dst - kRecPrefix);
     prefix[0] = prob_offset;
@@ -1200,9 +1203,7 @@ void Engine::eval_batch(const uint64_t* planes, const uint8_t* legal, uint32_t n
             finish(*f.lane, f.n);
             stamp("drain done", f.first);
         } catch (...) {
-            release_lane(*f.lane);
-            for (auto& o : inflight) release_lane(*o.lane);
-            inflight.clear();
+            release_lane(*f.lane);  // the other chunks may still be executing: the caller's handler waits for them first
             throw;
         }
         std::memcpy(values_out + f.first, f.lane->h_values, sizeof(float) * f.n);
@@ -1501,6 +1502,10 @@ void Engine::note_resident(uint64_t batches, uint64_t positions, uint64_t launch
 // ms_out[i] = device time of iteration i of the selected stage(s) on lane 0's stream, CUDA events on that stream,
 // with an L2 flush (256 MiB memset) before every iteration, outside the timed bracket.
 void Engine::time_stage(uint32_t stage, uint32_t n, uint32_t iters, float* ms_out) {
+    if (stage == 5) {
+        time_stages_split(n, iters, ms_out);
+        return;
+    }
     if (n == 0 || n > max_batch_ || iters == 0 || stage > 4) throw Error(CATTUS_B200_EINVAL, "time_stage: bad argument");
     CB2_CUDA(cudaSetDevice(device_));
     Lane& l = *lanes_[0];
@@ -1552,6 +1557,84 @@ void Engine::time_stage(uint32_t stage, uint32_t n, uint32_t iters, float* ms_ou
     metrics_.kernel_launches += launched;
 }
 
+// stage 5: every iteration is ONE pass of the whole launch sequence (L2 flushed before it, not inside it) with an event
+// after each stage, so the three durations [encode + trunk, heads, tail] add up to the pass: the heads read the trunk's
+// output from L2 exactly as they do inside the graph.  ms_out holds 3 * iters values.
+void Engine::time_stages_split(uint32_t n, uint32_t iters, float* ms_out) {
+    if (n == 0 || n > max_batch_ || iters == 0) throw Error(CATTUS_B200_EINVAL, "time_stage: bad argument");
+    CB2_CUDA(cudaSetDevice(device_));
+    Lane& l = *lanes_[0];
+    if (flush_.p == nullptr) flush_.alloc(256ull << 20);
+    std::vector<Op>& ops = ops_for(l, bucket_for(n), false);
+    std::vector<cudaEvent_t> ev(4 * iters);
+    for (auto& x : ev) CB2_CUDA(cudaEventCreate(&x));
+    for (uint32_t it = 0; it < iters; ++it) {
+        CB2_CUDA(cudaMemsetAsync(flush_.p, static_cast<int>(it & 0xFF), flush_.bytes, l.stream));
+        CB2_CUDA(cudaEventRecord(ev[4 * it], l.stream));
+        int group = 0;  // 0: stages 0-1, 1: stage 2, 2: stage 3
+        for (const Op& op : ops) {
+            const int g = op.stage <= 1 ? 0 : op.stage - 1;
+            while (group < g) CB2_CUDA(cudaEventRecord(ev[4 * it + ++group], l.stream));
+            op.launch(l.stream);
+        }
+        while (group < 3) CB2_CUDA(cudaEventRecord(ev[4 * it + ++group], l.stream));
+    }
+    cudaError_t se = cudaStreamSynchronize(l.stream);
+    if (se != cudaSuccess) throw_device_error("time_stage", se);
+    for (uint32_t it = 0; it < iters; ++it)
+        for (int g = 0; g < 3; ++g) CB2_CUDA(cudaEventElapsedTime(&ms_out[3 * it + g], ev[4 * it + g], ev[4 * it + g + 1]));
+    for (auto& x : ev) cudaEventDestroy(x);
+    std::lock_guard<std::mutex> g(m_mu_);
+    metrics_.kernel_launches += static_cast<uint64_t>(iters) * ops.size();
+}
+
+// Sustained throughput: n_batches DISTINCT resident batches (one per lane), `iters` graph replays rotating over them back
+// to back on one stream, one pair of events around the lot.  No L2 flush: the rotation itself keeps the inputs cold and the
+// weights warm, as in production.
+void Engine::time_sustained(const uint64_t* planes, const uint8_t* legal, uint32_t n, uint32_t n_batches, uint32_t iters, float* total_ms) {
+    if (n == 0 || n > max_batch_ || n_batches == 0 || n_batches > lanes_.size() || iters == 0 || !planes || !total_ms)
+        throw Error(CATTUS_B200_EINVAL, "time_sustained: bad argument (n_batches must not exceed n_streams)");
+    CB2_CUDA(cudaSetDevice(device_));
+    std::vector<Lane*> held;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    try {
+        for (uint32_t k = 0; k < n_batches; ++k) held.push_back(&acquire_lane());
+        const size_t plane_words = static_cast<size_t>(rec_.planes) * rec_.wpp;
+        const size_t bm = d_.bitmap_bytes();
+        for (uint32_t k = 0; k < n_batches; ++k) {
+            Lane& l = *held[k];
+            uint32_t total = 0;
+            for (uint32_t i = 0; i < n; ++i) {
+                const size_t b = static_cast<size_t>(k) * n + i;
+                total += pack_record(l.h_in + kRecs0 + static_cast<size_t>(i) * rec_.rec_bytes, planes + b * plane_words, legal ? legal + b * bm : nullptr, total);
+            }
+            *reinterpret_cast<uint32_t*>(l.h_in) = n;
+            CB2_CUDA(cudaMemcpyAsync(l.d_in.p, l.h_in, 16 + static_cast<size_t>(n) * rec_.rec_bytes, cudaMemcpyHostToDevice, l.stream));
+            run_bucket(l, bucket_for(n), l.stream, true, false);  // builds / warms the lane's graph
+            CB2_CUDA(cudaStreamSynchronize(l.stream));
+        }
+        cudaStream_t st = held[0]->stream;
+        CB2_CUDA(cudaEventCreate(&e0));
+        CB2_CUDA(cudaEventCreate(&e1));
+        CB2_CUDA(cudaEventRecord(e0, st));
+        for (uint32_t it = 0; it < iters; ++it) run_bucket(*held[it % n_batches], bucket_for(n), st, true, false);
+        CB2_CUDA(cudaEventRecord(e1, st));
+        cudaError_t se = cudaStreamSynchronize(st);
+        if (se != cudaSuccess) throw_device_error("time_sustained", se);
+        CB2_CUDA(cudaEventElapsedTime(total_ms, e0, e1));
+        std::lock_guard<std::mutex> g(m_mu_);
+        metrics_.kernel_launches += static_cast<uint64_t>(iters + n_batches) * kernels_per_batch_;
+    } catch (...) {
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+        for (Lane* l : held) release_lane(*l);
+        throw;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    for (Lane* l : held) release_lane(*l);
+}
+
 void Engine::get_info(cattus_b200_info* info) const {
     std::memset(info, 0, sizeof(*info));
     info->game = d_.game;
@@ -1569,7 +1652,7 @@ void Engine::get_info(cattus_b200_info* info) const {
     info->precision = precision_;
     info->sm_count = static_cast<uint32_t>(sm_count_);
     info->kernels_per_batch = kernels_per_batch_;
-    info->reserved = (fused_trunk_ ? 1u : 0u) | (small_trunk_ ? 2u : 0u);
+    info->trunk_path = fused_trunk_ ? CATTUS_B200_TRUNK_FUSED : small_trunk_ ? CATTUS_B200_TRUNK_SMALL : precision_ == CATTUS_B200_PRECISION_FP32_CHECK ? CATTUS_B200_TRUNK_FP32 : CATTUS_B200_TRUNK_PER_LAYER;
 }
 
 void Engine::get_metrics(cattus_b200_metrics* m) const {
@@ -1723,6 +1806,14 @@ int cattus_b200_time_stage(cattus_b200_t* h, uint32_t stage, uint32_t n, uint32_
     return guarded([&] {
         if (!h || !ms_out) throw cb2::Error(CATTUS_B200_EINVAL, "null argument");
         h->engine->time_stage(stage, n, iters, ms_out);
+    });
+}
+
+int cattus_b200_time_sustained(cattus_b200_t* h, const uint64_t* planes, const uint8_t* legal_bitmaps, uint32_t n, uint32_t n_batches, uint32_t iters,
+                               float* total_ms) {
+    return guarded([&] {
+        if (!h) throw cb2::Error(CATTUS_B200_EINVAL, "null handle");
+        h->engine->time_sustained(planes, legal_bitmaps, n, n_batches, iters, total_ms);
     });
 }
 

@@ -164,6 +164,8 @@ class Engine {
     void eval_resident(uint32_t n, cudaStream_t stream);
     void resident_download(uint32_t n, float* probs_out, size_t probs_cap, uint32_t* prob_offsets, float* values_out);
     void time_stage(uint32_t stage, uint32_t n, uint32_t iters, float* ms_out);
+    void time_stages_split(uint32_t n, uint32_t iters, float* ms_out);
+    void time_sustained(const uint64_t* planes, const uint8_t* legal, uint32_t n, uint32_t n_batches, uint32_t iters, float* total_ms);
 
     // Device-resident callers (the search of dsearch.cuh): reserve a lane, write records straight into its device input
     // block, enqueue the evaluator's kernels on a stream of their own (capturable), read d_values / d_probs on the device.

@@ -417,12 +417,13 @@ class Worker {
                 if (!any && !outstanding) break;
             }
         } catch (const SpError& e) {
-            drain_all();
-            std::lock_guard<std::mutex> g(sh_.mu);
-            if (!sh_.failed.exchange(true)) {
-                sh_.error_code = e.code;
-                sh_.error = e.msg;
-            }
+            fail(e.code, e.msg);
+        } catch (const std::bad_alloc&) {
+            fail(CATTUS_B200_ENOMEM, "out of host memory in a self-play worker (search trees / batch rows)");
+        } catch (const std::exception& e) {
+            fail(CATTUS_B200_EINVAL, std::string("self-play worker: ") + e.what());
+        } catch (...) {
+            fail(CATTUS_B200_EINVAL, "self-play worker: unknown exception");
         }
         std::lock_guard<std::mutex> g(sh_.mu);
         sh_.eval_wait += eval_wait_;
@@ -460,6 +461,16 @@ class Worker {
     void reseed(uint64_t seed) { slots_[0].rng = SplitMix64(game_seed(seed, 0)); }
     bool search_from(const std::vector<Pos>& history, Move* best, SearchStats* stats) {
         Slot& s = slots_[0];
+        // a previous `go` may have ended in an evaluator error mid-search: nothing of it may survive into this one (a stale
+        // pending row would be delivered twice and the simulation counter would wrap)
+        drain_all();
+        for (Group& g : groups_)
+            for (Pending& pb : g.pend) pb.clear();
+        s.phase = kIdle;
+        s.sel_node = -1;
+        s.path.clear();
+        s.sim_cands.clear();
+        s.prepared_leaf = -1;
         s.history = history;
         s.pending_entries.clear();
         s.rec.moves.clear();
@@ -499,6 +510,19 @@ class Worker {
     }
 
   private:
+    // error path of run(): every ticket in flight is waited, the first error of the job is kept, the other workers stop
+    void fail(int code, const std::string& msg) noexcept {
+        try {
+            drain_all();
+        } catch (...) {
+        }
+        std::lock_guard<std::mutex> g(sh_.mu);
+        if (!sh_.failed.exchange(true)) {
+            sh_.error_code = code;
+            sh_.error = msg;
+        }
+    }
+
     // ---------------------------------------------------------------- game loop (self_play.rs:179-246)
     void start_next_game(Slot& s) {
         const uint32_t stride = std::max<uint32_t>(1, cfg_.game_stride);
@@ -1141,7 +1165,7 @@ class Worker {
         Pending& pb = gr.pend[e];
         Evaluator& ev = *evals_[e];
         const uint32_t n = static_cast<uint32_t>(pb.keys.size());
-        if (ev.async_handle && !(n == 1 && ev.leaf_handle)) {
+        if (ev.async_handle && !(n == 1 && ev.leaf_handle) && n <= ev.max_rows) {  // larger than one device batch: the synchronous call below chunks
             const auto t0 = Clock::now();
             int32_t ticket = -1;
             int rc = cattus_b200_eval_batch_submit(ev.async_handle, pb.planes.data(), legal_ptr(pb), n, 0, &ticket);
@@ -1293,10 +1317,15 @@ static void run_games(const Rules& rules, const cattus_b200_selfplay_cfg& cfg, c
     const uint32_t n_threads = std::max<uint32_t>(1, cfg.threads);
     std::vector<std::unique_ptr<sp::Worker<Rules>>> workers;
     for (uint32_t i = 0; i < n_threads; ++i) workers.emplace_back(new sp::Worker<Rules>(rules, cfg, params, evals, sh));
-    std::vector<std::thread> threads;
-    for (uint32_t i = 1; i < n_threads; ++i) threads.emplace_back([&, i] { workers[i]->run(); });
-    workers[0]->run();  // the calling thread does job 0 (self_play.rs:127-137)
-    for (auto& t : threads) t.join();
+    struct Joiner {  // joins on every exit path: an exception on the calling thread must not destroy joinable threads
+        std::vector<std::thread> threads;
+        ~Joiner() {
+            for (auto& t : threads)
+                if (t.joinable()) t.join();
+        }
+    } joiner;
+    for (uint32_t i = 1; i < n_threads; ++i) joiner.threads.emplace_back([&, i] { workers[i]->run(); });
+    workers[0]->run();  // the calling thread does job 0 (self_play.rs:127-137); run() itself never throws
 }
 
 // MctsParams from the config (mcts/mod.rs:72-110; TemperaturePolicy::scheduled, self_play_cmd.rs:68-72)

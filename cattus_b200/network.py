@@ -60,8 +60,9 @@ class CudaNetwork:
         self.bitmap_bytes = info.legal_bitmap_bytes
         self.max_batch = info.max_batch
         self.needs_bitmap = game == "chess"
-        self.fused_trunk = bool(info.reserved & 1)
-        self.small_trunk = bool(info.reserved & 2)
+        self.trunk_path = _lib.TRUNK_PATH_NAMES[info.trunk_path]  # "fused" / "small" / "per-layer" / "fp32-check" (cattus_b200_info.trunk_path)
+        self.fused_trunk = info.trunk_path == _lib.TRUNK_FUSED
+        self.small_trunk = info.trunk_path == _lib.TRUNK_SMALL
 
     # ------------------------------------------------------------------ lifetime
     def close(self):
@@ -149,10 +150,21 @@ class CudaNetwork:
         return probs[: int(offsets[n])], offsets, values
 
     def time_stage(self, stage: int, n: int, iters: int) -> np.ndarray:
-        """Per-iteration device milliseconds (CUDA events on the evaluator stream, L2 flushed between iterations)."""
-        ms = np.empty(iters, dtype=np.float32)
+        """Per-iteration device milliseconds (CUDA events on the evaluator stream, L2 flushed between iterations).
+        stage 5 returns [iters, 3]: (encode + trunk, heads, tail) of the same pass, which add up to the pass."""
+        ms = np.empty(iters * (3 if stage == 5 else 1), dtype=np.float32)
         check(self._lib.cattus_b200_time_stage(self._h, stage, n, iters, _ptr(ms, _lib._f32p)))
-        return ms
+        return ms.reshape(iters, 3) if stage == 5 else ms
+
+    def time_sustained(self, words: np.ndarray, bitmaps, n: int, n_batches: int, iters: int) -> float:
+        """Milliseconds for `iters` back-to-back device batches rotating over n_batches distinct resident batches of n."""
+        words = np.ascontiguousarray(words[: n * n_batches], dtype=np.uint64)
+        assert len(words) == n * n_batches
+        bm = None if bitmaps is None else np.ascontiguousarray(bitmaps[: n * n_batches], dtype=np.uint8)
+        ms = C.c_float()
+        check(self._lib.cattus_b200_time_sustained(self._h, _ptr(words, _lib._u64p), None if bm is None else _ptr(bm, _lib._u8p), n, n_batches, iters,
+                                                   C.byref(ms)))
+        return float(ms.value)
 
     def metrics(self) -> dict:
         """The keys the trainer reads from the self-play summary (train_process.py:176-186) + extras."""

@@ -98,8 +98,15 @@ typedef struct cattus_b200_info {
     uint32_t max_batch, n_streams, precision;
     uint32_t sm_count;
     uint32_t kernels_per_batch;  /* kernel nodes in one captured batch graph */
-    uint32_t reserved;
+    uint32_t trunk_path;         /* CATTUS_B200_TRUNK_*: which kernel family runs the stem + residual blocks of this handle */
 } cattus_b200_info;
+
+/* cattus_b200_info.trunk_path.  The whole-trunk kernels cover fixed shapes; every other net takes the per-layer kernel,
+ * which is correct for any ConvNetV1 within the blob's limits but re-reads its activations through L2 (about 2.5x slower). */
+#define CATTUS_B200_TRUNK_PER_LAYER 0 /* one tcgen05 implicit-GEMM launch per conv layer (tc_gemm.cuh); any shape */
+#define CATTUS_B200_TRUNK_FUSED 1     /* trunk_fused.cuh: 8x8 boards, 128 filters, <= 32 planes, VH + PH <= 64 */
+#define CATTUS_B200_TRUNK_SMALL 2     /* trunk_small.cuh: 16 filters, boards 3..11, <= 32 planes, VH + PH <= 32 */
+#define CATTUS_B200_TRUNK_FP32 3      /* precision FP32_CHECK: CUDA-core fp32 loops (parity only) */
 
 /* Replaces Model::new (engine/src/net/model.rs:61-144). */
 int cattus_b200_create(const cattus_b200_desc* desc, cattus_b200_t** out);
@@ -156,8 +163,16 @@ int cattus_b200_eval_resident(cattus_b200_t* h, uint32_t n, void* stream);
 int cattus_b200_resident_download(cattus_b200_t* h, uint32_t n, float* probs_out, size_t probs_cap,
                                   uint32_t* prob_offsets, float* values_out);
 /* Times `iters` replays of one trunk layer / one named stage on the handle's stream with CUDA events (ms each).
- * stage: 0 = encode, 1 = stem+residual trunk, 2 = heads (1x1 convs + FCs), 3 = mask/softmax/tanh tail, 4 = all. */
+ * stage: 0 = encode, 1 = stem+residual trunk, 2 = heads (1x1 convs + FCs), 3 = mask/softmax/tanh tail, 4 = all (the
+ * captured graph); an L2 flush (256 MiB memset) precedes every iteration, outside the timed bracket.
+ * stage 5: every iteration is one pass of the whole sequence with an event after each stage; ms_out holds 3 * iters
+ * values [encode + trunk, heads, tail] that add up to the pass (no flush between the stages, as inside the graph). */
 int cattus_b200_time_stage(cattus_b200_t* h, uint32_t stage, uint32_t n, uint32_t iters, float* ms_out);
+/* Sustained throughput: n_batches distinct resident batches of n positions (planes [n_batches * n][...], one batch per
+ * evaluator stream: n_batches <= n_streams), `iters` graph replays rotating over them back to back on one stream, one
+ * pair of CUDA events around the lot -> *total_ms.  No L2 flush: the rotation keeps the inputs cold. */
+int cattus_b200_time_sustained(cattus_b200_t* h, const uint64_t* planes, const uint8_t* legal_bitmaps, uint32_t n, uint32_t n_batches,
+                               uint32_t iters, float* total_ms);
 
 int cattus_b200_get_metrics(const cattus_b200_t* h, cattus_b200_metrics* out);
 const char* cattus_b200_last_error(void);
