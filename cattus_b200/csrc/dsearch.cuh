@@ -89,6 +89,23 @@ class DsCudaBackend {
             alloc(d_noise_, sizeof(float) * static_cast<size_t>(n_slots) * max_children);
             const uint32_t hist_cap = Rules::kChess ? 128u : 1u;
             alloc(d_hist_, sizeof(typename Rules::Pos) * static_cast<size_t>(n_slots) * hist_cap);
+            // ValueFuncCache in HBM, one per evaluator (cfg.cache_size entries, rounded up to whole buckets)
+            for (uint32_t e = 0; e < 2; ++e) p_.cache[e] = ds::CacheIo{};
+            if (cfg.cache_size) {
+                uint32_t buckets = 1;
+                while (static_cast<uint64_t>(buckets) * ds::kCacheWays < cfg.cache_size) buckets <<= 1;
+                for (uint32_t e = 0; e < n_evals_; ++e) {
+                    ds::CacheIo& c = p_.cache[e];
+                    c.entry_bytes = (40u + 4u * max_children + 15u) & ~15u;
+                    alloc(d_cache_meta_[e], static_cast<size_t>(buckets) * 32u);
+                    CB2_CUDA(cudaMemset(d_cache_meta_[e], 0, static_cast<size_t>(buckets) * 32u));
+                    alloc(d_cache_entries_[e], static_cast<size_t>(buckets) * ds::kCacheWays * c.entry_bytes);
+                    c.meta = static_cast<uint32_t*>(d_cache_meta_[e]);
+                    c.entries = static_cast<uint8_t*>(d_cache_entries_[e]);
+                    c.bucket_mask = buckets - 1;
+                    c.enabled = 1;
+                }
+            }
             cmd_stride_ = ds::cmd_stride_for(max_children);
             result_stride_ = ds::result_stride_for(max_children);
             cmd_bytes_ = 16 + static_cast<size_t>(n_slots) * cmd_stride_;
@@ -142,7 +159,16 @@ class DsCudaBackend {
             p_.done_count = static_cast<uint32_t*>(d_status_);
             p_.error = static_cast<uint32_t*>(d_status_) + 1;
             p_.counters = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(d_status_) + 16);
-            p_.begin_lead = 0;
+            // begin (per-move commands: tree reuse copies subtrees) runs on a side branch of the wave graph, beside select /
+            // evaluator / expand; its slots take part from the next wave on
+            p_.begin_lead = std::getenv("CATTUS_B200_DSEARCH_SERIAL_BEGIN") ? 0u : 1u;
+            p_.visit_budget = 24;  // measured on hex5 (sim_num 1400, whole games): 24 -> 57.1 M sims/s, 48 -> 54.4 M, 96 -> 49.4 M
+            if (const char* vb = std::getenv("CATTUS_B200_DSEARCH_VISIT_BUDGET")) p_.visit_budget = std::max(1, std::atoi(vb));
+            if (p_.begin_lead) {
+                CB2_CUDA(cudaStreamCreateWithFlags(&side_, cudaStreamNonBlocking));
+                CB2_CUDA(cudaEventCreateWithFlags(&fork_, cudaEventDisableTiming));
+                CB2_CUDA(cudaEventCreateWithFlags(&join_, cudaEventDisableTiming));
+            }
             capture();
         } catch (...) {
             destroy();
@@ -206,10 +232,18 @@ class DsCudaBackend {
         try {
             for (uint32_t e = 0; e < n_evals_; ++e) CB2_CUDA(cudaMemsetAsync(io_[e].d_block, 0, 4, stream_));
             CB2_CUDA(cudaMemsetAsync(d_status_, 0, 4, stream_));
-            ds_begin_kernel<Rules><<<blocks, 128, 0, stream_>>>(p_);
+            if (p_.begin_lead) {
+                CB2_CUDA(cudaEventRecord(fork_, stream_));
+                CB2_CUDA(cudaStreamWaitEvent(side_, fork_, 0));
+                ds_begin_kernel<Rules><<<blocks, 128, 0, side_>>>(p_);
+                CB2_CUDA(cudaEventRecord(join_, side_));
+            } else {
+                ds_begin_kernel<Rules><<<blocks, 128, 0, stream_>>>(p_);
+            }
             ds_select_kernel<Rules><<<blocks, 128, 0, stream_>>>(p_);
             for (uint32_t e = 0; e < n_evals_; ++e) eng_[e]->resident_enqueue(io_[e].lane, stream_);
             ds_expand_kernel<Rules><<<blocks, 128, 0, stream_>>>(p_);
+            if (p_.begin_lead) CB2_CUDA(cudaStreamWaitEvent(stream_, join_, 0));
             CB2_CUDA(cudaGetLastError());
         } catch (...) {
             cudaStreamEndCapture(stream_, &g);
@@ -233,7 +267,13 @@ class DsCudaBackend {
         events_.clear();
         if (stream_) cudaStreamDestroy(stream_);
         stream_ = nullptr;
-        for (void** q : {&d_rules_, &d_slots_, &d_pools_, &d_paths_, &d_noise_, &d_hist_, &d_cmds_, &d_status_}) {
+        if (side_) cudaStreamDestroy(side_);
+        side_ = nullptr;
+        if (fork_) cudaEventDestroy(fork_);
+        if (join_) cudaEventDestroy(join_);
+        fork_ = join_ = nullptr;
+        for (void** q : {&d_rules_, &d_slots_, &d_pools_, &d_paths_, &d_noise_, &d_hist_, &d_cmds_, &d_status_, &d_cache_meta_[0], &d_cache_meta_[1],
+                         &d_cache_entries_[0], &d_cache_entries_[1]}) {
             if (*q) cudaFree(*q);
             *q = nullptr;
         }
@@ -254,9 +294,10 @@ class DsCudaBackend {
     uint32_t n_evals_ = 1, depth_ = 2, n_bufs_ = 3, max_children_ = 0, pool_words_ = 0, cmd_stride_ = 0, result_stride_ = 0, kernels_per_wave_ = 0;
     size_t cmd_bytes_ = 0, result_buf_bytes_ = 0;
     void *d_rules_ = nullptr, *d_slots_ = nullptr, *d_pools_ = nullptr, *d_paths_ = nullptr, *d_noise_ = nullptr, *d_hist_ = nullptr, *d_cmds_ = nullptr,
-         *d_status_ = nullptr;
+         *d_status_ = nullptr, *d_cache_meta_[2] = {nullptr, nullptr}, *d_cache_entries_[2] = {nullptr, nullptr};
     uint8_t *h_results_ = nullptr, *h_cmds_ = nullptr, *h_status_ = nullptr;
-    cudaStream_t stream_ = nullptr;
+    cudaStream_t stream_ = nullptr, side_ = nullptr;
+    cudaEvent_t fork_ = nullptr, join_ = nullptr;
     std::vector<cudaEvent_t> events_;
     cudaGraphExec_t graph_ = nullptr;
     uint64_t waves_ = 0;

@@ -186,7 +186,9 @@ enum ErrBits : uint32_t { kErrPool = 1, kErrPath = 2, kErrRows = 4, kErrNoise = 
 
 // One per concurrent game.  Scalars only; the per-slot arrays (tree pools, path, noise, history) are separate.
 struct SlotState {
-    uint32_t phase, cur, sims_left, start_wave;
+    uint32_t phase;  // Phase in the low 2 bits | (first wave in which select may run the slot) << 2: ONE word, because begin
+                     // may run concurrently with the select of the same wave (begin_lead = 1)
+    uint32_t cur, sims_left, pad0;
     int32_t root[2];
     uint32_t used[2];  // words in use of each player's tree pool
     uint32_t buf[2];   // which of the slot's three pool buffers holds each player's tree
@@ -208,6 +210,19 @@ struct EvalIo {
     const float* values;  // [max_rows]
     const float* probs;   // row r owns [r * prob_stride, r * prob_stride + #legal)
     uint32_t rec_bytes, prob_stride, max_rows, plane_words;
+};
+
+// ValueFuncCache (engine/src/mcts/cache.rs:31-75) in HBM: position key -> (probabilities over the legal moves in ascending
+// nn index, value), exactly what the evaluator returned for it.  Set-associative: bucket = hash & mask, kCacheWays entries,
+// first-in-first-out within a bucket.  A hit returns what a fresh evaluation would return (the evaluator is batch
+// invariant), so games do not depend on the cache at all -- only the number of evaluator rows does.  Probes run in the
+// select kernel, inserts in the expand kernel: the two never overlap, so only concurrent INSERTS need the bucket lock.
+constexpr int kCacheWays = 4;
+struct CacheIo {
+    uint32_t* meta;    // per bucket 8 words: [lock][fifo cursor][tag x 4][pad x 2]; tag 0 = empty way
+    uint8_t* entries;  // per entry: key 4 x u64 | u32 #legal | f32 value | f32 probs[max_children], padded to entry_bytes
+    uint32_t bucket_mask, entry_bytes;
+    uint32_t enabled, pad;
 };
 
 // Command block written by the host for one wave: [u32 n_cmds][u32 wave][8 B pad] then n_cmds commands of cmd_stride
@@ -235,6 +250,7 @@ struct Params {
     typename Rules::Pos* hist;  // [n_slots][hist_cap] ring; hist_cap is a power of two
     uint32_t hist_cap;
     EvalIo eval[2];
+    CacheIo cache[2];
     uint32_t n_evals;
     uint32_t sim_num[2];
     float explore[2], noise_eps[2];
@@ -244,9 +260,10 @@ struct Params {
     uint32_t result_stride, n_result_bufs;
     unsigned long long result_buf_bytes;
     uint32_t* done_count;           // results posted in this wave (zeroed per wave)
-    unsigned long long* counters;  // [0] simulations [1] evaluations [2] terminal leaves [3] waves with a batch
+    unsigned long long* counters;  // [0] simulations [1] evaluations [2] terminal leaves [3] cache hits
     uint32_t* error;                // sticky OR of ErrBits
     uint32_t begin_lead;            // 0: begin runs before select in the same wave; 1: overlapped, effective next wave
+    uint32_t visit_budget;          // node visits per slot and wave after which select stops starting new simulations
 };
 
 template <class Pos>
@@ -495,12 +512,167 @@ struct Core {
         return row;
     }
 
+    // ---------------------------------------------------------------------------------------- evaluation cache
+    // The key of NNetwork::evaluate's cache lookup: the position as the network sees it (net/mod.rs:74-87).
+    CB2_HD static uint64_t position_key(const Rules& R, const Pos& pos, uint64_t k[4]) {
+        if constexpr (kChess) {
+            R.key_planes(pos, k);
+        } else {
+            const Pos ev = pos.turn != 1 ? R.flipped_boards(pos) : pos;
+            u128 pl[3];
+            R.planes(ev, pl);
+            k[0] = static_cast<uint64_t>(pl[0]);
+            k[1] = static_cast<uint64_t>(pl[0] >> 64);
+            k[2] = static_cast<uint64_t>(pl[1]);
+            k[3] = static_cast<uint64_t>(pl[1] >> 64);
+        }
+        uint64_t h = 0x9E3779B97F4A7C15ull;
+        for (int i = 0; i < 4; ++i) {
+            uint64_t x = k[i] + 0x632BE59BD9B4E019ull * static_cast<uint64_t>(i + 1);
+            x ^= x >> 33;
+            x *= 0xff51afd7ed558ccdull;
+            x ^= x >> 33;
+            h = (h ^ x) * 0xc4ceb9fe1a85ec53ull;
+        }
+        return h ^ (h >> 29);
+    }
+    CB2_HD static uint32_t cache_tag(uint64_t h) {
+        const uint32_t t = static_cast<uint32_t>(h >> 32);
+        return t ? t : 1u;
+    }
+    // the entry holding `k`, or nullptr (uniform over the warp: every lane reads the same words)
+    CB2_HD static const uint8_t* cache_find(const CacheIo& c, const uint64_t k[4], uint64_t h) {
+        const uint32_t b = static_cast<uint32_t>(h) & c.bucket_mask;
+        const uint32_t* meta = c.meta + static_cast<size_t>(b) * 8u;
+        const uint32_t tag = cache_tag(h);
+        for (int w = 0; w < kCacheWays; ++w) {
+            if (meta[2 + w] != tag) continue;
+            const uint8_t* e = c.entries + (static_cast<size_t>(b) * kCacheWays + static_cast<size_t>(w)) * c.entry_bytes;
+            const uint64_t* ek = reinterpret_cast<const uint64_t*>(e);
+            if (ek[0] == k[0] && ek[1] == k[1] && ek[2] == k[2] && ek[3] == k[3]) return e;
+        }
+        return nullptr;
+    }
+    // stores (probs[count], value) for `k` unless the key is already there (cache.rs:52-63)
+    CB2_HD static void cache_insert(const CacheIo& c, const uint64_t k[4], uint64_t h, int count, const float* probs, float value) {
+        const int ln = lane();
+        const uint32_t b = static_cast<uint32_t>(h) & c.bucket_mask;
+        uint32_t* meta = c.meta + static_cast<size_t>(b) * 8u;
+        const uint32_t tag = cache_tag(h);
+#if DS_DEVICE
+        if (ln == 0) {
+            while (atomicCAS(meta, 0u, 1u) != 0u) {
+            }
+            __threadfence();
+        }
+        __syncwarp();
+#endif
+        uint32_t way = 0xFFFFFFFFu;
+        if (ln == 0) {
+            bool present = false;
+            for (int w = 0; w < kCacheWays; ++w) {
+                const volatile uint32_t* vm = meta;
+                if (vm[2 + w] == tag) {
+                    const volatile uint64_t* ek = reinterpret_cast<const volatile uint64_t*>(c.entries + (static_cast<size_t>(b) * kCacheWays + static_cast<size_t>(w)) * c.entry_bytes);
+                    if (ek[0] == k[0] && ek[1] == k[1] && ek[2] == k[2] && ek[3] == k[3]) present = true;
+                }
+            }
+            if (!present) {
+                const volatile uint32_t* vm = meta;
+                for (int w = 0; w < kCacheWays && way == 0xFFFFFFFFu; ++w)
+                    if (vm[2 + w] == 0u) way = static_cast<uint32_t>(w);
+                if (way == 0xFFFFFFFFu) {  // bucket full: first in, first out within the bucket
+                    way = vm[1] % static_cast<uint32_t>(kCacheWays);
+                    meta[1] = way + 1u;
+                }
+            }
+        }
+        way = wbcast(way);
+        if (way != 0xFFFFFFFFu) {
+            uint8_t* e = c.entries + (static_cast<size_t>(b) * kCacheWays + way) * c.entry_bytes;
+            float* ep = reinterpret_cast<float*>(e + 40);
+            for (int i = ln; i < count; i += DS_LANES) ep[i] = probs[i];
+            if (ln == 0) {
+                uint64_t* ek = reinterpret_cast<uint64_t*>(e);
+                ek[0] = k[0];
+                ek[1] = k[1];
+                ek[2] = k[2];
+                ek[3] = k[3];
+                *reinterpret_cast<uint32_t*>(e + 32) = static_cast<uint32_t>(count);
+                *reinterpret_cast<float*>(e + 36) = value;
+            }
+        }
+#if DS_DEVICE
+        __threadfence();
+        __syncwarp();
+        if (ln == 0) {
+            if (way != 0xFFFFFFFFu) meta[2 + way] = tag;
+            __threadfence();
+            atomicExch(meta, 0u);
+        }
+#else
+        if (way != 0xFFFFFFFFu) meta[2 + way] = tag;
+#endif
+    }
+
+    // create_children + root noise + backpropagate (mod.rs:180-194, :246-262) for `leaf` with the evaluator's answer for it
+    // (fresh from the device batch, or from the cache): `probs` = calc_moves_probs' output, compact in ascending nn index.
+    CB2_HD static void apply_evaluation(const Rules& R, const P& p, uint32_t si, uint32_t cur, uint32_t* pool, int32_t leaf, int32_t root,
+                                        const float* probs, float value, uint32_t& noise_n, uint32_t depth) {
+        const int ln = lane();
+        Hdr* h = T::hdr(pool, leaf);
+        const int count = h->count;
+        const bool flipped = h->pos.turn != 1;
+        float* init = T::init(pool, leaf);
+        uint32_t* ed = T::edge(pool, leaf, count);
+        if constexpr (kChess) {
+            // child i takes the entry at the rank of its nn index among the legal ones (net/mod.rs:106-119 gathers per
+            // legal move); the edge row holds the nn indices while the ranks are counted, then becomes "no child yet"
+            const uint16_t* mv = T::mv16(pool, leaf, count);
+            for (int i = ln; i < count; i += DS_LANES) ed[i] = static_cast<uint32_t>(R.nn_idx(mv[i]));
+            wsync();
+            for (int i = ln; i < count; i += DS_LANES) {
+                const uint32_t idx = ed[i];
+                int rank = 0;
+                for (int j = 0; j < count; ++j) rank += ed[j] < idx ? 1 : 0;
+                init[i] = probs[rank];
+            }
+            wsync();
+            for (int i = ln; i < count; i += DS_LANES) ed[i] = T::pack_edge(-1, 0u);  // chess moves live in move16
+        } else {
+            // legal_moves() of the evaluated position, ascending; un-flipped by flip_score_if_needed (net/mod.rs:166-182)
+            const Pos ev = flipped ? R.flipped_boards(h->pos) : h->pos;
+            const u128 legal = R.legal_mask(ev);
+            const int cells = R.moves_num();
+            for (int cell = ln; cell < cells; cell += DS_LANES) {
+                if (static_cast<uint32_t>(legal >> cell) & 1u) {
+                    const int k = sp::popcount128(legal & (sp::bit128(cell) - 1));
+                    init[k] = probs[k];
+                    ed[k] = T::pack_edge(-1, static_cast<uint32_t>(flipped ? R.flip_move(cell) : cell));
+                }
+            }
+        }
+        if (ln == 0) h->expanded = 1;
+        wsync();
+        if (leaf == root && noise_n) {
+            if (noise_n == static_cast<uint32_t>(count))
+                apply_noise(pool, leaf, count, p.noise + static_cast<size_t>(si) * p.max_children, p.noise_eps[cur]);
+            else if (ln == 0)
+                atomic_or_u32(p.error, kErrNoise);
+            noise_n = 0;
+        }
+        const float v = flipped ? -value : value;
+        const uint8_t root_turn = T::hdr(pool, root)->pos.turn;
+        backpropagate(pool, p.paths + static_cast<size_t>(si) * p.path_cap, depth, root_turn, v);
+    }
+
     // ---------------------------------------------------------------------------------------- select (mod.rs:156-244)
     // Runs simulations of slot `si` until one needs the network (its record is written, the slot parks in kWaitEval) or
     // the search is out of simulations (results posted, kDone).  Terminal and repeated leaves are scored on the spot.
     CB2_HD static void select_slot(const Rules& R, const P& p, uint32_t si, uint32_t wave) {
         SlotState& S = p.slots[si];
-        const uint32_t phase0 = S.phase, start_wave = S.start_wave;
+        const uint32_t pw = S.phase;
+        const uint32_t phase0 = pw & 3u, start_wave = pw >> 2;
         const uint32_t cur = S.cur;
         uint32_t sims_left = S.sims_left;
         Tree t;
@@ -508,6 +680,7 @@ struct Core {
         t.used = S.used[cur & 1u];
         t.root = S.root[cur & 1u];
         const uint32_t hist_len = S.hist_len;
+        uint32_t noise_n = S.noise_n;
         wsync();  // every lane holds its copy before lane 0 stores anything back
         if (phase0 != kRun || start_wave > wave) return;
         const int ln = lane();
@@ -515,7 +688,8 @@ struct Core {
         PathStep* path = p.paths + static_cast<size_t>(si) * p.path_cap;
         const float ef = p.explore[cur];
         const uint8_t root_turn = T::hdr(t.pool, t.root)->pos.turn;
-        uint32_t err = 0, phase = kRun, row = 0, path_len = 0, n_sims = 0, n_term = 0;
+        uint32_t err = 0, phase = kRun, row = 0, path_len = 0, n_sims = 0, n_term = 0, n_hits = 0, visits = 0;
+        const CacheIo& cache = p.cache[e];
         int32_t leaf = -1;
         for (;;) {
             if (sims_left == 0) {
@@ -523,6 +697,11 @@ struct Core {
                 phase = kDone;
                 break;
             }
+            // Terminal and repeated leaves are scored on the spot and the slot goes on to its next simulation -- but only
+            // within a budget of node visits per wave: near the end of a game nearly every simulation ends in a finished
+            // position, and one warp walking hundreds of them would hold the whole wave (the kernel ends with its slowest
+            // warp).  A slot over budget just sits this wave's batch out; its games are the same games.
+            if (visits >= p.visit_budget) break;
             int32_t node = t.root;
             uint32_t depth = 0;
             for (;;) {
@@ -574,6 +753,7 @@ struct Core {
                 depth += 1;
                 node = c;
             }
+            visits += depth + 1;
             if (err) break;
             wsync();  // the path is visible to every lane
             const Hdr* lh = T::hdr(t.pool, node);
@@ -587,6 +767,20 @@ struct Core {
                 n_term += 1;
                 wsync();
                 continue;
+            }
+            if (cache.enabled) {  // ValueFuncCache::get_or_compute (cache.rs:31-75): a hit is expanded and scored on the spot
+                uint64_t key[4];
+                const uint64_t kh = position_key(R, lh->pos, key);
+                const uint8_t* ce = cache_find(cache, key, kh);
+                if (ce != nullptr && *reinterpret_cast<const uint32_t*>(ce + 32) == static_cast<uint32_t>(lh->count)) {
+                    apply_evaluation(R, p, si, cur, t.pool, node, t.root, reinterpret_cast<const float*>(ce + 40), *reinterpret_cast<const float*>(ce + 36),
+                                     noise_n, depth);
+                    sims_left -= 1;
+                    n_sims += 1;
+                    n_hits += 1;
+                    wsync();
+                    continue;
+                }
             }
             row = emit_record(R, p, e, t.pool, node);
             if (row == 0xFFFFFFFFu) {
@@ -610,6 +804,8 @@ struct Core {
             S.leaf = leaf;
             S.row = row;
             S.path_len = path_len;
+            S.noise_n = noise_n;
+            if (n_hits) atomic_add_u64(p.counters + 3, n_hits);
             if (n_sims) atomic_add_u64(p.counters + 0, n_sims);
             if (n_term) atomic_add_u64(p.counters + 2, n_term);
             if (phase == kWaitEval) atomic_add_u64(p.counters + 1, 1ull);
@@ -619,7 +815,7 @@ struct Core {
     // ------------------------------------------------- create_children + root noise + backpropagate (mod.rs:180-194)
     CB2_HD static void expand_slot(const Rules& R, const P& p, uint32_t si, uint32_t wave) {
         SlotState& S = p.slots[si];
-        const uint32_t phase0 = S.phase, cur = S.cur, row = S.row, depth = S.path_len;
+        const uint32_t phase0 = S.phase & 3u, cur = S.cur, row = S.row, depth = S.path_len;
         uint32_t sims_left = S.sims_left, noise_n = S.noise_n;
         const int32_t leaf = S.leaf;
         uint32_t* pool = p.pools + (static_cast<size_t>(si) * 3u + S.buf[cur & 1u]) * p.pool_words;
@@ -627,54 +823,16 @@ struct Core {
         wsync();
         if (phase0 != kWaitEval) return;
         const int ln = lane();
-        const EvalIo& io = p.eval[p.n_evals > 1 ? cur : 0u];
+        const uint32_t e = p.n_evals > 1 ? cur : 0u;
+        const EvalIo& io = p.eval[e];
         const float* probs = io.probs + static_cast<size_t>(row) * io.prob_stride;
         const float value = io.values[row];
-        Hdr* h = T::hdr(pool, leaf);
-        const int count = h->count;
-        const bool flipped = h->pos.turn != 1;
-        float* init = T::init(pool, leaf);
-        if constexpr (kChess) {
-            // calc_moves_probs (net/mod.rs:106-119) gathers per legal move; the evaluator returns the probabilities compact
-            // in ascending nn index, so child i takes the entry at the rank of its nn index among the legal ones (the
-            // record's bitmap, still in the evaluator's input block)
-            const uint64_t* bm = reinterpret_cast<const uint64_t*>(io.recs + static_cast<size_t>(row) * io.rec_bytes + Rules::kPlanes * 8);
-            const uint16_t* mv = T::mv16(pool, leaf, count);
-            uint32_t* ed = T::edge(pool, leaf, count);
-            for (int i = ln; i < count; i += DS_LANES) {
-                ed[i] = T::pack_edge(-1, 0u);  // no child visited yet; chess moves live in move16
-                const int idx = R.nn_idx(mv[i]);
-                int rank = 0;
-                for (int wd = 0; wd < (idx >> 6); ++wd) rank += sp::popc64(bm[wd]);
-                rank += sp::popc64(bm[idx >> 6] & ((1ull << (idx & 63)) - 1ull));
-                init[i] = probs[rank];
-            }
-        } else {
-            // legal_moves() of the evaluated position, ascending; un-flipped by flip_score_if_needed (net/mod.rs:166-182)
-            const Pos ev = flipped ? R.flipped_boards(h->pos) : h->pos;
-            const u128 legal = R.legal_mask(ev);
-            uint32_t* ed = T::edge(pool, leaf, count);
-            const int cells = R.moves_num();
-            for (int cell = ln; cell < cells; cell += DS_LANES) {
-                if (static_cast<uint32_t>(legal >> cell) & 1u) {
-                    const int k = sp::popcount128(legal & (sp::bit128(cell) - 1));
-                    init[k] = probs[k];
-                    ed[k] = T::pack_edge(-1, static_cast<uint32_t>(flipped ? R.flip_move(cell) : cell));
-                }
-            }
+        if (p.cache[e].enabled) {
+            uint64_t key[4];
+            const uint64_t kh = position_key(R, T::hdr(pool, leaf)->pos, key);
+            cache_insert(p.cache[e], key, kh, T::hdr(pool, leaf)->count, probs, value);
         }
-        if (ln == 0) h->expanded = 1;
-        wsync();
-        if (leaf == root && noise_n) {
-            if (noise_n == static_cast<uint32_t>(count))
-                apply_noise(pool, leaf, count, p.noise + static_cast<size_t>(si) * p.max_children, p.noise_eps[cur]);
-            else if (ln == 0)
-                atomic_or_u32(p.error, kErrNoise);
-            noise_n = 0;
-        }
-        const float v = flipped ? -value : value;
-        const uint8_t root_turn = T::hdr(pool, root)->pos.turn;
-        backpropagate(pool, p.paths + static_cast<size_t>(si) * p.path_cap, depth, root_turn, v);
+        apply_evaluation(R, p, si, cur, pool, leaf, root, probs, value, noise_n, depth);
         sims_left -= 1;
         uint32_t phase = kRun;
         if (sims_left == 0) {
@@ -755,94 +913,116 @@ struct Core {
     }
 
     // mod.rs:303-333: the subtree is copied into the slot's spare buffer; edges are re-inserted in iteration
-    // (newest-first) order, so every kept node's child order is reversed.  The copy is breadth-first with the new pool
-    // itself as the queue: a child's new header carries its old block (in `expanded`, offset by 2) until its turn comes.
+    // (newest-first) order, so every kept node's child order is reversed.  The copy is breadth-first with ONE NODE PER
+    // LANE: a queue of (new block, old block) pairs grows down from the top of the new pool while the blocks grow up
+    // from its bottom; each round the lanes take up to 32 queued nodes, size their visited children (pass 1), get their
+    // block and queue ranges from two warp scans, then copy their rows reversed and enqueue the children (pass 2).
+    // A node-serial copy made tree reuse the bottleneck of whole games: ~2 us of dependent loads per kept node.
     // Block offsets differ from the host driver's depth-first copy; nothing observable depends on them.
     CB2_HD static bool copy_subtree(const P& p, const uint32_t* old_pool_c, int32_t sub_root, Tree& nt) {
         uint32_t* old_pool = const_cast<uint32_t*>(old_pool_c);
         const int ln = lane();
-        nt.used = 0;
+        uint32_t* q = nt.pool + p.pool_words;  // entry e lives in q[-2 (e + 1)], q[-2 (e + 1) + 1]
         {
             const Hdr* oh = T::hdr(old_pool, sub_root);
             const uint32_t words = T::block_words(oh->count);
-            if (words > p.pool_words) return false;
+            if (words + 2u > p.pool_words) return false;
             if (ln == 0) {
                 Hdr* nh = T::hdr(nt.pool, 0);
                 nh->pos = oh->pos;
                 nh->count = oh->count;
-                nh->expanded = sub_root + 2;
+                nh->expanded = 0;
+                q[-2] = 0u;
+                q[-1] = static_cast<uint32_t>(sub_root);
             }
             nt.used = words;
             nt.root = 0;
         }
+        uint32_t q_head = 0, q_tail = 1;
         wsync();
-        uint32_t cursor = 0;
-        while (cursor < nt.used) {
-            Hdr* nh = T::hdr(nt.pool, static_cast<int32_t>(cursor));
-            const int32_t ob = nh->expanded - 2;
-            const int count = nh->count;
-            const Hdr* oh = T::hdr(old_pool, ob);
-            const bool expanded = oh->expanded != 0;
-            wsync();  // every lane has read the header before lane 0 overwrites `expanded`
-            const int32_t nb = static_cast<int32_t>(cursor);
-            if (!expanded) {
-                // visited but never expanded: no edges yet, nothing to reverse -- chess moves keep their generated order
-                uint32_t* rows = nt.pool + nb + T::kHdrWords + count;
-                for (int i = ln; i < 2 * count; i += DS_LANES) rows[i] = 0u;
-                if constexpr (kChess) {
-                    const uint16_t* om = T::mv16(old_pool, ob, count);
-                    uint16_t* nm = T::mv16(nt.pool, nb, count);
-                    for (int i = ln; i < count; i += DS_LANES) nm[i] = om[i];
+        while (q_head < q_tail) {
+            const uint32_t e = q_head + static_cast<uint32_t>(ln);
+            const bool active = e < q_tail;
+            int32_t nb = 0, ob = 0;
+            int count = 0, need = 0, kids = 0;
+            bool expanded = false;
+            if (active) {
+                nb = static_cast<int32_t>(q[-2 * static_cast<int32_t>(e + 1u)]);
+                ob = static_cast<int32_t>(q[-2 * static_cast<int32_t>(e + 1u) + 1]);
+                const Hdr* oh = T::hdr(old_pool, ob);
+                count = oh->count;
+                expanded = oh->expanded != 0;
+                if (expanded) {
+                    const uint32_t* oe = T::edge(old_pool, ob, count);
+                    for (int o = 0; o < count; ++o) {
+                        const int32_t oc = T::edge_child(oe[o]);
+                        if (oc >= 0) {
+                            need += static_cast<int>(T::block_words(T::hdr(old_pool, oc)->count));
+                            kids += 1;
+                        }
+                    }
                 }
-                if (ln == 0) nh->expanded = 0;
-            } else {
-                const float* oi = T::init(old_pool, ob);
-                const float* ow = T::w(old_pool, ob, count);
-                const int32_t* on = T::n(old_pool, ob, count);
-                const uint32_t* oe = T::edge(old_pool, ob, count);
-                float* ni = T::init(nt.pool, nb);
-                float* nw = T::w(nt.pool, nb, count);
-                int32_t* nn = T::n(nt.pool, nb, count);
-                uint32_t* ne = T::edge(nt.pool, nb, count);
-                for (int base = 0; base < count; base += DS_LANES) {
-                    const int i = base + ln;  // new insertion order = old iteration order (newest first)
-                    const bool valid = i < count;
-                    const int o = count - 1 - i;
-                    uint32_t e = 0;
-                    int32_t old_c = -1;
-                    int c_count = 0, need = 0;
-                    if (valid) {
-                        e = oe[o];
-                        old_c = T::edge_child(e);
+            }
+            int total_need = 0, total_kids = 0;
+            const int off = wexscan(need, total_need);
+            const int koff = wexscan(kids, total_kids);
+            // blocks grow up, the queue grows down: they must not meet
+            if (static_cast<unsigned long long>(nt.used) + static_cast<uint32_t>(total_need) + 2ull * (q_tail + static_cast<uint32_t>(total_kids)) > p.pool_words)
+                return false;
+            if (active) {
+                Hdr* nh = T::hdr(nt.pool, nb);
+                if (!expanded) {
+                    // visited but never expanded: no edges yet, nothing to reverse -- chess moves keep their generated order
+                    uint32_t* rows = nt.pool + nb + T::kHdrWords + count;
+                    for (int i = 0; i < 2 * count; ++i) rows[i] = 0u;
+                    if constexpr (kChess) {
+                        const uint16_t* om = T::mv16(old_pool, ob, count);
+                        uint16_t* nm = T::mv16(nt.pool, nb, count);
+                        for (int i = 0; i < count; ++i) nm[i] = om[i];
+                    }
+                    nh->expanded = 0;
+                } else {
+                    const float* oi = T::init(old_pool, ob);
+                    const float* ow = T::w(old_pool, ob, count);
+                    const int32_t* on = T::n(old_pool, ob, count);
+                    const uint32_t* oe = T::edge(old_pool, ob, count);
+                    float* ni = T::init(nt.pool, nb);
+                    float* nw = T::w(nt.pool, nb, count);
+                    int32_t* nn = T::n(nt.pool, nb, count);
+                    uint32_t* ne = T::edge(nt.pool, nb, count);
+                    uint32_t next_block = nt.used + static_cast<uint32_t>(off);
+                    uint32_t next_q = q_tail + static_cast<uint32_t>(koff);
+                    for (int i = 0; i < count; ++i) {  // new insertion order = old iteration order (newest first)
+                        const int o = count - 1 - i;
+                        const uint32_t ed = oe[o];
                         ni[i] = oi[o];
                         nw[i] = ow[o];
                         nn[i] = on[o];
                         if constexpr (kChess) T::mv16(nt.pool, nb, count)[i] = T::mv16(old_pool, ob, count)[o];
-                        if (old_c >= 0) {
-                            c_count = T::hdr(old_pool, old_c)->count;
-                            need = static_cast<int>(T::block_words(c_count));
-                        }
-                    }
-                    int total = 0;
-                    const int off = wexscan(need, total);
-                    if (nt.used + static_cast<uint32_t>(total) > p.pool_words) return false;
-                    if (valid) {
+                        const int32_t oc = T::edge_child(ed);
                         int32_t nc = -1;
-                        if (old_c >= 0) {
-                            nc = static_cast<int32_t>(nt.used) + off;
+                        if (oc >= 0) {
+                            const Hdr* och = T::hdr(old_pool, oc);
+                            nc = static_cast<int32_t>(next_block);
+                            next_block += T::block_words(och->count);
                             Hdr* ch = T::hdr(nt.pool, nc);
-                            ch->pos = T::hdr(old_pool, old_c)->pos;
-                            ch->count = c_count;
-                            ch->expanded = old_c + 2;
+                            ch->pos = och->pos;
+                            ch->count = och->count;
+                            ch->expanded = 0;
+                            q[-2 * static_cast<int32_t>(next_q + 1u)] = static_cast<uint32_t>(nc);
+                            q[-2 * static_cast<int32_t>(next_q + 1u) + 1] = static_cast<uint32_t>(oc);
+                            next_q += 1;
                         }
-                        ne[i] = T::pack_edge(nc, T::edge_move(e));
+                        ne[i] = T::pack_edge(nc, T::edge_move(ed));
                     }
-                    nt.used += static_cast<uint32_t>(total);
+                    nh->expanded = 1;
                 }
-                if (ln == 0) nh->expanded = 1;
             }
+            const uint32_t batch = q_tail - q_head < static_cast<uint32_t>(DS_LANES) ? q_tail - q_head : static_cast<uint32_t>(DS_LANES);
+            nt.used += static_cast<uint32_t>(total_need);
+            q_tail += static_cast<uint32_t>(total_kids);
+            q_head += batch;
             wsync();
-            cursor += T::block_words(count);
         }
         return true;
     }
@@ -952,13 +1132,12 @@ struct Core {
             S.noise_n = noise_n;
             S.leaf = -1;
             S.path_len = 0;
-            S.start_wave = wave + p.begin_lead;
             if (err) {
                 atomic_or_u32(p.error, err);
                 S.error = err;
                 S.phase = kIdle;
             } else {
-                S.phase = kRun;
+                S.phase = kRun | ((wave + p.begin_lead) << 2);
             }
         }
     }

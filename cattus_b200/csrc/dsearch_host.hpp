@@ -61,6 +61,7 @@ class Driver {
         const uint32_t depth = std::max<uint32_t>(1, be_.depth());
         for (;;) {
             bool submitted = false;
+            const auto ta = sp::Clock::now();
             if (active_ > 0) {
                 uint8_t* block = be_.cmd_block(wave);
                 const uint32_t n_cmds = static_cast<uint32_t>(cmds_.size() / cmd_stride_);
@@ -75,21 +76,30 @@ class Driver {
                 submitted = true;
                 waves_ += 1;
             }
+            const auto tb = sp::Clock::now();
             if (!inflight.empty() && (inflight.size() >= depth || !submitted)) {
                 const uint32_t w = inflight.front();
                 inflight.pop_front();
                 uint32_t n_done = 0;
                 const uint8_t* res = be_.wait(w, &n_done);
+                const auto tc = sp::Clock::now();
                 for (uint32_t k = 0; k < n_done; ++k) on_result(res + static_cast<size_t>(k) * result_stride_);
+                t_wait_ += std::chrono::duration<double>(tc - tb).count();
+                t_process_ += std::chrono::duration<double>(sp::Clock::now() - tc).count();
             }
+            t_submit_ += std::chrono::duration<double>(tb - ta).count();
             if (active_ == 0 && inflight.empty()) break;
         }
         unsigned long long c[4] = {0, 0, 0, 0};
         be_.read_counters(c);
+        if (std::getenv("CATTUS_B200_DSEARCH_PROFILE"))  // where the host thread's time went: a large `wait` share means the GPU is the limit
+            std::fprintf(stderr, "device search host thread: %llu waves, submit %.3f s, wait (GPU) %.3f s, per-move work %.3f s (%llu searches)\n",
+                         static_cast<unsigned long long>(waves_), t_submit_, t_wait_, t_process_, static_cast<unsigned long long>(searches_));
         std::lock_guard<std::mutex> g(sh_.mu);
         sh_.simulations += c[0];
         sh_.evaluations += c[1];
-        sh_.cache_misses += c[1];  // no cache on the device: every non-terminal leaf is evaluated
+        sh_.cache_misses += c[1];  // every evaluator row was a miss of the device-side cache (or there is no cache)
+        sh_.cache_hits += c[3];
         sh_.terminal += c[2];
         sh_.batches += waves_;
         sh_.searches += searches_;
@@ -255,7 +265,7 @@ class Driver {
     uint32_t active_ = 0;
     uint64_t waves_ = 0, searches_ = 0;
     uint32_t w1_ = 0, w2_ = 0, d_ = 0, games_done_ = 0;
-    double search_duration_ = 0.0;
+    double search_duration_ = 0.0, t_submit_ = 0.0, t_wait_ = 0.0, t_process_ = 0.0;
     std::vector<double> noise_;
     std::vector<float> nz_, weights_;
 };

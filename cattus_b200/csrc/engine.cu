@@ -1519,7 +1519,8 @@ void Engine::time_stage(uint32_t stage, uint32_t n, uint32_t iters, float* ms_ou
         CB2_CUDA(cudaMemsetAsync(flush_.p, static_cast<int>(it & 0xFF), flush_.bytes, l.stream));
         CB2_CUDA(cudaEventRecord(ev[2 * it], l.stream));
         if (stage == 4) {
-            run_bucket(l, bucket, l.stream, true, false);
+            static const bool no_graph = std::getenv("CATTUS_B200_TIME_NO_GRAPH") != nullptr;  // experiment: direct launches instead of the graph
+            run_bucket(l, bucket, l.stream, !no_graph, false);
             launched += ops.size();
         } else {
             for (const Op& op : ops)

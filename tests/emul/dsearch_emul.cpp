@@ -34,16 +34,19 @@ struct EmulBackend {
     uint32_t n_bufs;
     bool chess;
 
+    std::vector<uint32_t> cache_meta[2];
+    std::vector<uint8_t> cache_entries[2];
+
     EmulBackend(const Rules& rules, const void* rules_blob, uint32_t n_slots, uint32_t pool_words, uint32_t depth, const sp::Params params[2],
-                cattus_b200_eval_fn f1, void* c1, cattus_b200_eval_fn f2, void* c2)
-        : R(rules), depth_(depth) {
+                cattus_b200_eval_fn f1, void* c1, cattus_b200_eval_fn f2, void* c2, uint32_t cache_size)
+        : R(rules), depth_(depth & 0xFFu) {
         chess = Rules::kChess;
         fn[0] = f1;
         ctx[0] = c1;
         fn[1] = f2;
         ctx[1] = c2;
         const uint32_t maxc = Rules::kChess ? 224u : static_cast<uint32_t>(rules.max_children());
-        n_bufs = depth + 1;
+        n_bufs = (depth & 0xFFu) + 1;
         slots.assign(n_slots, ds::SlotState{});
         pools.assign(static_cast<size_t>(n_slots) * 3 * pool_words, 0xDEADBEEFu);  // stale memory must not matter
         const uint32_t path_cap = Rules::kChess ? 256u : maxc + 2u;
@@ -81,6 +84,20 @@ struct EmulBackend {
             p.explore[e] = params[e].explore_factor;
             p.noise_eps[e] = params[e].noise_eps;
         }
+        for (int e = 0; e < 2; ++e) {
+            p.cache[e] = ds::CacheIo{};
+            if (cache_size && (e == 0 || f2)) {
+                uint32_t buckets = 1;
+                while (buckets * ds::kCacheWays < cache_size) buckets <<= 1;
+                p.cache[e].entry_bytes = (40u + 4u * maxc + 15u) & ~15u;
+                cache_meta[e].assign(static_cast<size_t>(buckets) * 8, 0u);
+                cache_entries[e].assign(static_cast<size_t>(buckets) * ds::kCacheWays * p.cache[e].entry_bytes, 0xAB);
+                p.cache[e].meta = cache_meta[e].data();
+                p.cache[e].entries = cache_entries[e].data();
+                p.cache[e].bucket_mask = buckets - 1;
+                p.cache[e].enabled = 1;
+            }
+        }
         p.cmd_stride = ds::cmd_stride_for(maxc);
         p.result_stride = ds::result_stride_for(maxc);
         cmds.assign(16 + static_cast<size_t>(n_slots) * p.cmd_stride, 0);
@@ -92,7 +109,8 @@ struct EmulBackend {
         p.done_count = &done_count;
         p.counters = counters;
         p.error = &error;
-        p.begin_lead = 0;
+        p.begin_lead = (depth >> 8) & 1u;  // test knobs: bit 8 of `depth`; bits 16.. = visit budget (0 = 24)
+        p.visit_budget = (depth >> 16) ? (depth >> 16) : 24u;
         done_per_buf.assign(n_bufs, 0);
     }
     uint32_t n_slots() const { return p.n_slots; }
@@ -103,7 +121,6 @@ struct EmulBackend {
     void run_eval(int e) {
         const uint32_t n = *p.eval[e].n_ptr;
         if (n == 0) return;
-        counters[3] += 1;
         const uint32_t pw = p.eval[e].plane_words, rb = p.eval[e].rec_bytes;
         std::vector<uint64_t> planes(static_cast<size_t>(n) * pw);
         std::vector<uint8_t> legal(chess ? static_cast<size_t>(n) * 235 : 0);
@@ -133,8 +150,13 @@ struct EmulBackend {
         *p.eval[0].n_ptr = 0;
         *p.eval[1].n_ptr = 0;
         decltype(auto) rules = ds::RulesRef<Rules>::get(p.rules);
-        for (uint32_t ci = 0; ci < n_cmds; ++ci) ds::Core<Rules>::begin_slot(rules, p, ci, wave);
+        // begin_lead = 1 is the GPU's arrangement: begin runs beside select / evaluator / expand of the same wave and takes
+        // effect in the next one; here it runs in the middle of them
+        if (!p.begin_lead)
+            for (uint32_t ci = 0; ci < n_cmds; ++ci) ds::Core<Rules>::begin_slot(rules, p, ci, wave);
         for (uint32_t si = 0; si < p.n_slots; ++si) ds::Core<Rules>::select_slot(rules, p, si, wave);
+        if (p.begin_lead)
+            for (uint32_t ci = 0; ci < n_cmds; ++ci) ds::Core<Rules>::begin_slot(rules, p, ci, wave);
         for (uint32_t e = 0; e < p.n_evals; ++e) run_eval(static_cast<int>(e));
         for (uint32_t si = 0; si < p.n_slots; ++si) ds::Core<Rules>::expand_slot(rules, p, si, wave);
         done_per_buf[wave % n_bufs] = done_count;
@@ -173,7 +195,7 @@ void run_emul(const Rules& rules, const void* blob, const cattus_b200_selfplay_c
               cattus_b200_eval_fn f1, void* c1, cattus_b200_eval_fn f2, void* c2, sp::Shared& sh) {
     const sp::Params p = params_from(cfg);
     sp::Params params[2] = {p, p};
-    EmulBackend<Rules> be(rules, blob, n_slots, pool_words, depth, params, f1, c1, f2, c2);
+    EmulBackend<Rules> be(rules, blob, n_slots, pool_words, depth, params, f1, c1, f2, c2, cfg->cache_size);
     ds::Driver<Rules, EmulBackend<Rules>> drv(rules, *cfg, params, be, sh);
     drv.run();
 }
@@ -215,7 +237,7 @@ void dsearch_emul_counters(void* h, uint64_t out[8]) {
     out[1] = s.evaluations;
     out[2] = s.terminal;
     out[3] = s.searches;
-    out[4] = s.batches;
+    out[4] = s.cache_hits;
     out[5] = s.w1;
     out[6] = s.w2;
     out[7] = s.d;

@@ -68,7 +68,7 @@ def run(game: str, cfg: dict, eval1, eval2, games_num: int, *, n_slots: int, poo
             raise RuntimeError(err.decode())
         cnt = (C.c_uint64 * 8)()
         lib.dsearch_emul_counters(h, cnt)
-        counters = dict(zip(("simulations", "evaluations", "terminal", "searches", "waves", "w1", "w2", "draws"), [int(x) for x in cnt]))
+        counters = dict(zip(("simulations", "evaluations", "terminal", "searches", "cache_hits", "w1", "w2", "draws"), [int(x) for x in cnt]))
         records = []
         for k in range(lib.dsearch_emul_game_count(h)):
             gi, w, nm = C.c_uint32(), C.c_uint32(), C.c_uint32()

@@ -45,9 +45,39 @@ def test_results_do_not_depend_on_slots_or_pipeline_depth():
     net = fake_net("hash")
     cfg = cfg_with(sim_num=30, prior_noise_alpha=0.3, prior_noise_epsilon=0.25, temperature_policy=[[4, 1.0], [9999, 0.0]], seed=8)
     _, ref = host_games("hex5", cfg, cb_for(net, 1), None, 10)
-    for n_slots, depth in ((1, 1), (3, 2), (16, 3), (10, 4)):
+    for n_slots, depth in ((1, 1), (3, 2), (16, 3), (10, 4), (3, 2 | 256), (16, 1 | 256), (4, 2 | (1 << 16)),
+                           (4, 2 | 256 | (1000 << 16))):  # | 256: begin overlapped (a wave later); << 16: node-visit budget per wave (1: one simulation)
         _, got = emul.run("hex5", cfg, cb_for(net, 1), None, 10, n_slots=n_slots, pool_words=1 << 15, depth=depth)
         same_games(got, ref)
+
+
+@pytest.mark.parametrize("game,cache_size", [("hex5", 100000), ("hex5", 16), ("ttt", 1000)])
+def test_device_side_cache_changes_no_game(game, cache_size):
+    """ValueFuncCache in HBM: a hit is expanded on the spot inside select.  Same games; fewer evaluator rows."""
+    net = fake_net("coarse")
+    cfg = cfg_with(sim_num=60, prior_noise_alpha=0.3, prior_noise_epsilon=0.25, temperature_policy=[[4, 1.0], [9999, 0.0]], seed=4)
+    _, ref = host_games(game, cfg, cb_for(net, 1), None, 6)
+    plain, got0 = emul.run(game, cfg, cb_for(net, 1), None, 6, n_slots=3, pool_words=1 << 16)
+    cached, got = emul.run(game, dict(cfg, mcts=dict(cfg["mcts"], cache_size=cache_size)), cb_for(net, 1), None, 6, n_slots=3, pool_words=1 << 16)
+    same_games(got0, ref)
+    same_games(got, ref)
+    assert plain["cache_hits"] == 0 and cached["cache_hits"] > 0
+    assert cached["evaluations"] + cached["cache_hits"] == plain["evaluations"] == cached["simulations"] - cached["terminal"]
+
+
+def test_device_side_cache_chess_and_two_models():
+    net = chess_fake_net("hash")
+    cfg = chess_cfg(max_moves=30, sim_num=12, cache_size=5000, prior_noise_alpha=0.3, prior_noise_epsilon=0.25, temperature_policy=[[10, 1.0], [9999, 0.0]])
+    _, ref = host_games("chess", cfg, chess_cb(net), None, 2)
+    counters, got = emul.run("chess", cfg, chess_cb(net), None, 2, n_slots=2, pool_words=1 << 16)
+    same_games(got, ref)
+    assert counters["cache_hits"] > 0
+    n1, n2 = fake_net("hash"), fake_net("hash", salt=99)
+    cfg = cfg_with(sim_num=30, temperature_policy=[[9999, 1.0]], seed=3, cache_size=1000)
+    _, ref = host_games("hex4", cfg, cb_for(n1, 1), cb_for(n2, 1), 6)
+    counters, got = emul.run("hex4", cfg, cb_for(n1, 1), cb_for(n2, 1), 6, n_slots=3, pool_words=1 << 14)
+    same_games(got, ref)
+    assert counters["cache_hits"] > 0
 
 
 def test_no_noise_temperature_zero_and_tree_reuse():

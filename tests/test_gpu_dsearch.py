@@ -34,6 +34,23 @@ def test_device_games_equal_host_driver_games(name, sim_num, games_num):
         assert s_dev[k] == s_host[k]
 
 
+@pytest.mark.parametrize("name,game,kw", [("hex5", "hex5", dict(sim_num=120)), ("hex7", "hex7", dict(sim_num=60)),
+                                          ("chess_dev", "chess", dict(sim_num=24, max_moves=24)), ("ttt", "ttt", dict(sim_num=40))])
+def test_device_side_cache_same_games_fewer_rows(name, game, kw):
+    """cfg cache_size > 0 puts ValueFuncCache in HBM: hits are expanded inside the select kernel.  Same games."""
+    base = dict(prior_noise_alpha=0.3, prior_noise_epsilon=0.25, temperature_policy=[[6, 1.0], [9999, 0.0]], seed=13)
+    base.update(kw)
+    with make_network(name, batch_size=64) as nw:
+        _, host = SelfPlayRunner(game, cfg_with(cache_size=10000, threads=2, games_per_thread=4, **base)).generate_data(nw, None, 8, keep_records=True)
+        s0, plain = SelfPlayRunner(game, cfg_with(device_games=8, **base)).generate_data(nw, None, 8, keep_records=True)
+        s1, cached = SelfPlayRunner(game, cfg_with(device_games=8, cache_size=50000, **base)).generate_data(nw, None, 8, keep_records=True)
+        s2, tiny = SelfPlayRunner(game, cfg_with(device_games=8, cache_size=8, **base)).generate_data(nw, None, 8, keep_records=True)
+    assert games_of(plain) == games_of(host) and games_of(cached) == games_of(host) and games_of(tiny) == games_of(host)
+    m0, m1 = s0["metrics"], s1["metrics"]
+    assert m0["cache.hits"] == 0 and m1["cache.hits"] > 0
+    assert m1["selfplay.evaluations"] + m1["cache.hits"] == m0["selfplay.evaluations"]
+
+
 def test_device_games_equal_the_oracle_directly():
     from tests.test_gpu_selfplay import gpu_net_fn
 

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--max-moves", type=int, default=0)
     ap.add_argument("--speculate", type=int, nargs="+", default=[0], help="rows per game evaluated ahead into the cache (small batches only)")
     ap.add_argument("--device-games", type=int, nargs="+", default=[0], help="> 0: device-resident search with this many concurrent games")
+    ap.add_argument("--device-cache", action="store_true", help="device search: ValueFuncCache in HBM with --cache entries")
     ap.add_argument("--waves", type=int, default=0, help="device search: waves in flight (0 = default)")
     ap.add_argument("--tree-kwords", type=int, default=0, help="device search: words (x1024) per tree buffer (0 = auto)")
     ap.add_argument("--batch", type=int, default=0, help="evaluator max batch (0 = games per thread, clamped to 64..4096)")
@@ -41,14 +42,14 @@ def main():
     for dg in [d for d in args.device_games if d > 0]:
         with CudaNetwork(blob, cfg_net.game, batch_size=max(64, dg), n_streams=1) as nw:
             cfg = {"mcts": {"sim_num": args.sim_num, "explore_factor": 1.41421, "temperature_policy": [[10, 1.0], [9999, 0.0]],
-                            "prior_noise_alpha": 0.03, "prior_noise_epsilon": 0.25, "cache_size": 0},
+                            "prior_noise_alpha": 0.03, "prior_noise_epsilon": 0.25, "cache_size": args.cache if args.cache != 1000000 or args.device_cache else 0},
                    "seed": 1, "max_moves": args.max_moves, "device_games": dg, "device_waves_in_flight": args.waves, "device_tree_kwords": args.tree_kwords}
             games = max(2, (args.games + 1) // 2 * 2)
             summary, _ = SelfPlayRunner("chess" if args.game.startswith("chess") else args.game, cfg).generate_data(nw, None, games)
             m = summary["metrics"]
             print(json.dumps({"device_games": dg, "games": games, "sims_per_sec": round(m["selfplay.sims_per_sec"]), "seconds": round(m["selfplay.seconds"], 3),
                               "simulations": m["selfplay.simulations"], "evals": m["selfplay.evaluations"], "waves": m["model.activation_count"],
-                              "mean_batch": round(m["selfplay.evaluations"] / max(1, m["model.activation_count"]), 1),
+                              "mean_batch": round(m["selfplay.evaluations"] / max(1, m["model.activation_count"]), 1), "cache_hits": m["cache.hits"],
                               "ms_per_wave": round(1e3 * m["selfplay.seconds"] / max(1, m["model.activation_count"]), 4),
                               "p1": summary["player1_wins"], "p2": summary["player2_wins"], "draws": summary["draws"]}), flush=True)
     if args.device_games != [0]:
