@@ -40,6 +40,10 @@ WORKLOADS = {
     # name: (oracle config, device batch, device batches per step)
     "chess10x128": ("chess10x128", 4096, 4),
     "chess_dev": ("chess_dev", 4096, 4),
+    # widths outside the two whole-trunk kernels (per-layer tensor-core path; cattus_b200_info.trunk_path says which)
+    "chess_4x64": ("chess_4x64", 4096, 4),
+    "chess_4x256": ("chess_4x256", 4096, 4),
+    "chess20x256": ("chess20x256", 4096, 4),
     # 16-filter nets: a 4096-position batch is ONE round per CTA, so per-CTA setup and the 64-CTA FC launch are not
     # amortised; 16384 runs 4 rounds per CTA (hex5: 66.6 -> 93 M positions/s)
     "hex5": ("hex5", 16384, 4),
@@ -56,6 +60,9 @@ CONFIG_NOTES = {
     "hex7": "BASELINE.json configs[2]: hex 7x7, ConvNetV1 7x16 (heads 16/16) random-init",
     "hex4": "BASELINE.json configs[0]: hex 4x4, ConvNetV1 7x16 (heads 16/16) random-init",
     "chess_dev": "training/config/chess_dev.yaml: chess, ConvNetV1 7x16 (heads 8/8) random-init",
+    "chess_4x64": "chess, ConvNetV1 4 x 64 (heads 8/8): a width training/config/chess_dev.yaml:30-37 recommends, outside the whole-trunk kernels",
+    "chess_4x256": "chess, ConvNetV1 4 x 256 (heads 16/16): the widest net chess_dev.yaml:30-37 recommends, per-layer path",
+    "chess20x256": "chess, ConvNetV1 20 x 256 (heads 32/32): the top of the range chess_dev.yaml:30-37 recommends, per-layer path",
     "hex9": "hex 9x9 (training/self-play/src/bin/hex9_self_player.rs), ConvNetV1 7x16 (heads 16/16) random-init",
     "hex11": "hex 11x11, the reference's standard board (engine/src/hex/core.rs:341), ConvNetV1 7x16 (heads 16/16) random-init",
 }

@@ -34,6 +34,37 @@ Blob Blob::parse(const void* bytes, size_t n) {
     b.d.vh = h[8];
     b.d.ph = h[9];
     b.d.hidden = h[10];
+    b.d.arch = h[11];
+    if (b.d.arch == 1) {
+        // SimpleTwoHeadedModel (net_utils.py:92-121): dense1 w[n,n] b[n] | dense2 w b | value w[n] b[1] | policy w[M,n] b[M]
+        NetDims& s = b.d;
+        const size_t nf = s.features();
+        if (s.game > 2 || s.s < 2 || s.s > 11 || s.c_in == 0 || s.c_in > 64 || s.moves == 0 || s.moves > 4096 || s.f || s.r || s.vh || s.ph || s.hidden != nf)
+            throw Error(CATTUS_B200_EINVAL, "weight blob: SimpleTwoHeadedModel header out of the supported range");
+        size_t off = 0;
+        auto take = [&](size_t cnt) {
+            size_t o = off;
+            off += cnt;
+            return o;
+        };
+        b.d1_w = take(nf * nf);
+        b.d1_b = take(nf);
+        b.d2_w = take(nf * nf);
+        b.d2_b = take(nf);
+        b.vfc2_w = take(nf);
+        b.vfc2_b = take(1);
+        b.pfc_w = take(static_cast<size_t>(s.moves) * nf);
+        b.pfc_b = take(s.moves);
+        if (n != 64 + off * sizeof(float))
+            throw Error(CATTUS_B200_EINVAL, "weight blob: size " + std::to_string(n) + " does not match its SimpleTwoHeadedModel header (expected " +
+                                                std::to_string(64 + off * sizeof(float)) + ")");
+        b.data.resize(off);
+        std::memcpy(b.data.data(), static_cast<const uint8_t*>(bytes) + 64, off * sizeof(float));
+        for (float v : b.data)
+            if (!std::isfinite(v)) throw Error(CATTUS_B200_EINVAL, "weight blob: non-finite weight");
+        return b;
+    }
+    if (b.d.arch != 0) throw Error(CATTUS_B200_EINVAL, "weight blob: unknown architecture tag");
     const NetDims& d = b.d;
     if (d.game > 2 || d.s < 2 || d.s > 11 || d.c_in == 0 || d.c_in > 64 || d.moves == 0 || d.moves > 4096 || d.f == 0 ||
         d.f > 256 || d.vh == 0 || d.vh > 64 || d.ph == 0 || d.ph > 64 || d.hidden != 128 || d.r > 64)
@@ -114,6 +145,7 @@ Engine::Engine(const cattus_b200_desc& desc, const void* blob_bytes, size_t blob
     chk(desc.board_size, d_.s, "board_size");
     chk(desc.planes, d_.c_in, "planes");
     chk(desc.moves, d_.moves, "moves");
+    simple_ = d_.arch == 1;
     chk(desc.filters, d_.f, "filters");
     chk(desc.blocks, d_.r, "blocks");
     chk(desc.value_channels, d_.vh, "value_channels");
@@ -173,11 +205,11 @@ Engine::Engine(const cattus_b200_desc& desc, const void* blob_bytes, size_t blob
     CB2_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(kTcStagesDeep)));
     CB2_CUDA(cudaFuncSetAttribute(tc_gemm_dual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(kTcStagesDeep)));
     // whole-trunk kernel: 8x8 boards, 128 filters (flags bit 0 forces the per-layer path, used by the parity tests)
-    fused_trunk_ = precision_ == CATTUS_B200_PRECISION_BF16 && d_.s == 8 && d_.f == 128 && d_.c_in <= 32 && d_.wpp() == 1 &&
+    fused_trunk_ = !simple_ && precision_ == CATTUS_B200_PRECISION_BF16 && d_.s == 8 && d_.f == 128 && d_.c_in <= 32 && d_.wpp() == 1 &&
                    (desc.flags & 1u) == 0 && (sm_count_ >= 2) && vhp_ + php_ <= 64;
     if (fused_trunk_) CB2_CUDA(cudaFuncSetAttribute(trunk_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFtSmemBytes));
     // 16-filter nets (every shipped training config): whole trunk + both head convs in one kernel
-    small_trunk_ = precision_ == CATTUS_B200_PRECISION_BF16 && d_.f == 16 && d_.c_in <= 32 && d_.s >= 3 && d_.s <= 11 && vhp_ + php_ <= 32 &&
+    small_trunk_ = !simple_ && precision_ == CATTUS_B200_PRECISION_BF16 && d_.f == 16 && d_.c_in <= 32 && d_.s >= 3 && d_.s <= 11 && vhp_ + php_ <= 32 &&
                    (desc.flags & 1u) == 0;
     if (small_trunk_) {
         small_stem_kc_ = ceil_div(d_.c_in, 16);
@@ -240,7 +272,7 @@ Engine::~Engine() {
         c.w.free_();
         c.b.free_();
     }
-    for (GemmW* g : {&vconv_, &pconv_, &vfc1_, &pfc_}) {
+    for (GemmW* g : {&vconv_, &pconv_, &vfc1_, &pfc_, &dense1_, &dense2_}) {
         g->w.free_();
         g->b.free_();
     }
@@ -262,6 +294,40 @@ Engine::~Engine() {
 void Engine::upload_weights(const Blob& blob) {
     const uint32_t s2 = d_.s2();
     const float* D = blob.data.data();
+    if (simple_) {
+        // SimpleTwoHeadedModel: three dense layers over the NCHW-flattened planes (net_utils.py:112-121).  bf16: [N_pad][K_pad]
+        // K-major like every other contraction here, K index = the flatten index itself; fp32 check mode: PyTorch layouts.
+        const uint32_t nf = d_.features();
+        auto dense = [&](GemmW& g, size_t w_off, size_t b_off, uint32_t n_out) {
+            if (precision_ == CATTUS_B200_PRECISION_FP32_CHECK) {
+                upload(g.w, std::vector<float>(D + w_off, D + w_off + static_cast<size_t>(n_out) * nf));
+                upload(g.b, std::vector<float>(D + b_off, D + b_off + n_out));
+                return;
+            }
+            if (n_out <= 128) {
+                g.n_umma = round_up(n_out, 16);
+                g.n_tiles = 1;
+            } else {
+                g.n_umma = 128;
+                g.n_tiles = ceil_div(n_out, 128);
+            }
+            const uint32_t np = g.n_umma * g.n_tiles;
+            g.k_pad = round_up(nf, 64);
+            std::vector<float> w(static_cast<size_t>(np) * g.k_pad, 0.0f), b(np, 0.0f);
+            for (uint32_t o = 0; o < n_out; ++o) {
+                b[o] = D[b_off + o];
+                for (uint32_t k = 0; k < nf; ++k) w[static_cast<size_t>(o) * g.k_pad + k] = D[w_off + static_cast<size_t>(o) * nf + k];
+            }
+            upload(g.w, to_bf16(w));
+            upload(g.b, b);
+        };
+        dense(dense1_, blob.d1_w, blob.d1_b, nf);
+        dense(dense2_, blob.d2_w, blob.d2_b, nf);
+        dense(pfc_, blob.pfc_w, blob.pfc_b, d_.moves);
+        upload(vfc2_w_, std::vector<float>(D + blob.vfc2_w, D + blob.vfc2_w + nf));
+        vfc2_b_ = D[blob.vfc2_b];
+        return;
+    }
     if (precision_ == CATTUS_B200_PRECISION_FP32_CHECK) {
         auto up = [&](GemmW& g, size_t w, size_t wn, size_t b, size_t bn) {
             upload(g.w, std::vector<float>(D + w, D + w + wn));
@@ -431,6 +497,17 @@ void Engine::init_lane(Lane& l) {
     l.d_probs.alloc(sizeof(float) * max_batch_ * d_.moves);
     const uint32_t s2 = d_.s2();
     l.d_dense.alloc(sizeof(float) * max_batch_ * d_.c_in * s2);
+    if (simple_) {
+        // activations are [max_batch][K_pad] rows (bf16) / [max_batch][n] (fp32); columns beyond a layer's width stay zero
+        const size_t nf = d_.features(), kp = round_up(static_cast<uint32_t>(nf), 64);
+        const bool f32 = precision_ == CATTUS_B200_PRECISION_FP32_CHECK;
+        const size_t row_bytes = f32 ? nf * 4 : std::max<size_t>(kp, dense1_.n_umma * dense1_.n_tiles) * 2;
+        l.d_x.alloc(row_bytes * max_batch_);
+        l.d_act[0].alloc(row_bytes * max_batch_);
+        l.d_act[1].alloc(row_bytes * max_batch_);
+        l.d_logits.alloc(sizeof(float) * max_batch_ * (f32 ? d_.moves : pfc_.n_umma * pfc_.n_tiles));
+        return;
+    }
     l.d_hidden.alloc(sizeof(float) * max_batch_ * d_.hidden);
     if (precision_ == CATTUS_B200_PRECISION_FP32_CHECK) {
         l.d_x.alloc(sizeof(float) * max_batch_ * d_.c_in * s2);
@@ -516,7 +593,9 @@ std::vector<Op>& Engine::ops_for(Lane& lane, uint32_t bucket, bool dense_input) 
     auto it = lane.ops.find(key);
     if (it != lane.ops.end()) return it->second;
     std::vector<Op> ops;
-    if (precision_ == CATTUS_B200_PRECISION_FP32_CHECK)
+    if (simple_)
+        build_ops_simple(lane, bucket, ops, dense_input);
+    else if (precision_ == CATTUS_B200_PRECISION_FP32_CHECK)
         build_ops_fp32(lane, bucket, ops, dense_input);
     else
         build_ops_bf16(lane, bucket, ops, dense_input);
@@ -551,6 +630,119 @@ void Engine::add_tail_ops(Lane& lane, uint32_t bucket, std::vector<Op>& ops, boo
         op.launch = [=](cudaStream_t st) { policy_tail_kernel<<<blocks, 256, 0, st>>>(logits, ld_logits, recs, L, n_ptr, probs); };
         ops.push_back(op);
     }
+}
+
+// SimpleTwoHeadedModel.forward (net_utils.py:112-121): flatten -> dense1 + ReLU -> dense2 + ReLU -> {policy, tanh(value)}.
+// bf16: three tcgen05 GEMMs (tc_gemm.cuh) over [positions][K_pad] rows + a warp-per-position value dot product;
+// fp32 check mode: the CUDA-core loops.  The policy tail is the standalone clamp + mask + softmax kernel.
+void Engine::build_ops_simple(Lane& lane, uint32_t bucket, std::vector<Op>& ops, bool dense_input) {
+    const int n = static_cast<int>(bucket);
+    const int nf = static_cast<int>(d_.features());
+    const uint8_t* recs = lane.d_in.as<uint8_t>() + kRecs0;
+    const uint32_t* n_ptr = lane.d_in.as<uint32_t>();
+    const RecLayout L = rec_;
+    const int sm = sm_count_;
+    float* values = zero_copy_out(lane, bucket, dense_input) ? lane.zc_values : lane.d_values.as<float>();
+    const float* w2 = vfc2_w_.as<float>();
+    const float b2 = vfc2_b_;
+    const int vblocks = static_cast<int>(ceil_div(bucket * 32, 256));
+    if (precision_ == CATTUS_B200_PRECISION_FP32_CHECK) {
+        const float* x = dense_input ? lane.d_dense.as<float>() : lane.d_x.as<float>();
+        if (!dense_input) {
+            Op op;
+            op.stage = 0;
+            op.name = "encode_nchw_f32";
+            float* out = lane.d_x.as<float>();
+            const int blocks = grid_for(static_cast<long long>(n) * nf, 256, sm);
+            op.launch = [=](cudaStream_t st) { encode_nchw_f32_kernel<<<blocks, 256, 0, st>>>(recs, L, n_ptr, n, out); };
+            ops.push_back(op);
+        }
+        auto fc = [&](int stage, const char* name, const float* in, const GemmW& g, float* out, int no, int relu) {
+            Op op;
+            op.stage = stage;
+            op.name = name;
+            const float* w = g.w.as<float>();
+            const float* b = g.b.as<float>();
+            const int blocks = grid_for(static_cast<long long>(n) * no * 32, 256, sm);
+            op.launch = [=](cudaStream_t st) { fc_f32_kernel<<<blocks, 256, 0, st>>>(in, w, b, out, n, nf, no, no, relu); };
+            ops.push_back(op);
+        };
+        float* a0 = lane.d_act[0].as<float>();
+        float* a1 = lane.d_act[1].as<float>();
+        fc(1, "dense1", x, dense1_, a0, nf, 1);
+        fc(1, "dense2", a0, dense2_, a1, nf, 1);
+        {
+            Op op;
+            op.stage = 2;
+            op.name = "value_dot_tanh";
+            op.launch = [=](cudaStream_t st) { dot_tanh_kernel<float><<<vblocks, 256, 0, st>>>(a1, nf, nf, w2, b2, n_ptr, n, values); };
+            ops.push_back(op);
+        }
+        fc(2, "policy", a1, pfc_, lane.d_logits.as<float>(), static_cast<int>(d_.moves), 0);
+    } else {
+        const int kp = static_cast<int>(dense1_.k_pad);
+        const int ld = static_cast<int>(std::max<uint32_t>(dense1_.k_pad, dense1_.n_umma * dense1_.n_tiles));
+        __nv_bfloat16* x = lane.d_x.as<__nv_bfloat16>();
+        {
+            Op op;
+            op.stage = 0;
+            const int blocks = grid_for(static_cast<long long>(n) * (kp / 8), 256, sm);
+            if (dense_input) {
+                op.name = "nchw_f32_to_flat_bf16";
+                const float* in = lane.d_dense.as<float>();
+                op.launch = [=](cudaStream_t st) { nchw_f32_to_flat_bf16_kernel<<<blocks, 256, 0, st>>>(in, n, nf, kp, ld, x); };
+            } else {
+                op.name = "encode_flat_bf16";
+                op.launch = [=](cudaStream_t st) { encode_flat_bf16_kernel<<<blocks, 256, 0, st>>>(recs, L, n_ptr, n, nf, kp, ld, x); };
+            }
+            ops.push_back(op);
+        }
+        auto gemm = [&](int stage, const char* name, const void* a, const GemmW& g, void* out, uint32_t ld_out, bool out_f32, bool relu) {
+            TcGemmParams p;
+            std::memset(&p, 0, sizeof(p));
+            p.err = d_err_;
+            p.s2 = static_cast<int>(d_.s2());
+            p.nb = 1;
+            p.tma_a = make_map_2d(a, static_cast<uint64_t>(nf), bucket, static_cast<uint64_t>(ld) * 2, 128);
+            p.tma_b = make_map_2d(g.w.p, g.k_pad, static_cast<uint64_t>(g.n_umma) * g.n_tiles, g.k_pad * 2ull, g.n_umma);
+            p.bias = g.b.as<float>();
+            p.out = out;
+            p.mode = 0;
+            p.kh = 1;
+            p.num_kb = static_cast<int>(g.k_pad / 64);
+            p.n_umma = static_cast<int>(g.n_umma);
+            p.n_store = static_cast<int>(g.n_umma);
+            p.m_valid = static_cast<int>(bucket);
+            p.rows_per_tile = 128;
+            p.ld_out = static_cast<int>(ld_out);
+            p.out_f32 = out_f32 ? 1 : 0;
+            p.relu = relu ? 1 : 0;
+            p.tx_bytes = 128 * 128 + g.n_umma * 128;
+            ops.push_back(make_tc_op(stage, name, p, ceil_div(bucket, 128), g.n_tiles));
+        };
+        __nv_bfloat16* a0 = lane.d_act[0].as<__nv_bfloat16>();
+        __nv_bfloat16* a1 = lane.d_act[1].as<__nv_bfloat16>();
+        gemm(1, "dense1", x, dense1_, a0, static_cast<uint32_t>(ld), false, true);
+        gemm(1, "dense2", a0, dense2_, a1, static_cast<uint32_t>(ld), false, true);
+        {
+            Op op;
+            op.stage = 2;
+            op.name = "value_dot_tanh";
+            op.launch = [=](cudaStream_t st) { dot_tanh_kernel<__nv_bfloat16><<<vblocks, 256, 0, st>>>(a1, ld, nf, w2, b2, n_ptr, n, values); };
+            ops.push_back(op);
+        }
+        gemm(2, "policy", a1, pfc_, lane.d_logits.p, pfc_.n_umma * pfc_.n_tiles, true, false);
+    }
+    if (dense_input) return;  // run_dense returns raw logits (Model::run semantics)
+    Op op;
+    op.stage = 3;
+    op.name = "policy_tail";
+    const float* logits = lane.d_logits.as<float>();
+    const int ld_logits = precision_ == CATTUS_B200_PRECISION_FP32_CHECK ? static_cast<int>(d_.moves) : static_cast<int>(pfc_.n_umma * pfc_.n_tiles);
+    float* probs = zero_copy_out(lane, bucket, dense_input) ? lane.zc_probs : lane.d_probs.as<float>();
+    const int blocks = static_cast<int>(ceil_div(bucket * 32, 256));
+    op.launch = [=](cudaStream_t st) { policy_tail_kernel<<<blocks, 256, 0, st>>>(logits, ld_logits, recs, L, n_ptr, probs); };
+    ops.push_back(op);
 }
 
 void Engine::build_ops_fp32(Lane& lane, uint32_t bucket, std::vector<Op>& ops, bool dense_input) {
@@ -1653,7 +1845,7 @@ void Engine::get_info(cattus_b200_info* info) const {
     info->precision = precision_;
     info->sm_count = static_cast<uint32_t>(sm_count_);
     info->kernels_per_batch = kernels_per_batch_;
-    info->trunk_path = fused_trunk_ ? CATTUS_B200_TRUNK_FUSED : small_trunk_ ? CATTUS_B200_TRUNK_SMALL : precision_ == CATTUS_B200_PRECISION_FP32_CHECK ? CATTUS_B200_TRUNK_FP32 : CATTUS_B200_TRUNK_PER_LAYER;
+    info->trunk_path = simple_ ? CATTUS_B200_TRUNK_DENSE : fused_trunk_ ? CATTUS_B200_TRUNK_FUSED : small_trunk_ ? CATTUS_B200_TRUNK_SMALL : precision_ == CATTUS_B200_PRECISION_FP32_CHECK ? CATTUS_B200_TRUNK_FP32 : CATTUS_B200_TRUNK_PER_LAYER;
 }
 
 void Engine::get_metrics(cattus_b200_metrics* m) const {

@@ -47,6 +47,8 @@ struct Error : std::runtime_error {
 
 struct NetDims {
     uint32_t game = 0, s = 0, c_in = 0, moves = 0, f = 0, r = 0, vh = 0, ph = 0, hidden = 128;
+    uint32_t arch = 0;  // 0: ConvNetV1 (net_utils.py:45-89); 1: SimpleTwoHeadedModel (net_utils.py:92-121; f, r, vh, ph unused)
+    uint32_t features() const { return c_in * s * s; }  // SimpleTwoHeadedModel's width (net_utils.py:97-99)
     uint32_t s2() const { return s * s; }
     uint32_t wpp() const { return (s * s + 63) / 64; }
     uint32_t bitmap_bytes() const { return (moves + 7) / 8; }
@@ -64,6 +66,7 @@ struct Blob {
     std::vector<Conv> block_conv;  // 2 per block
     Conv vconv, pconv;
     size_t vfc1_w = 0, vfc1_b = 0, vfc2_w = 0, vfc2_b = 0, pfc_w = 0, pfc_b = 0;
+    size_t d1_w = 0, d1_b = 0, d2_w = 0, d2_b = 0;  // SimpleTwoHeadedModel: _dense1, _dense2 (value head = vfc2_*, policy head = pfc_*)
     static Blob parse(const void* bytes, size_t n);
 };
 
@@ -191,6 +194,7 @@ class Engine {
     std::vector<Op>& ops_for(Lane& lane, uint32_t bucket, bool dense_input);
     void build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, bool dense_input);
     void build_ops_fp32(Lane& lane, uint32_t bucket, std::vector<Op>& ops, bool dense_input);
+    void build_ops_simple(Lane& lane, uint32_t bucket, std::vector<Op>& ops, bool dense_input);
     void add_tail_ops(Lane& lane, uint32_t bucket, std::vector<Op>& ops, bool dense_input, bool value_tail, bool policy_tail);
     void run_bucket(Lane& lane, uint32_t bucket, cudaStream_t stream, bool use_graph, bool dense_input);
     void throw_device_error(const char* where, cudaError_t e);
@@ -221,6 +225,7 @@ class Engine {
     bool derive_legal_ = false;
     bool fused_trunk_ = false;  // S == 8 && F == 128: whole-trunk kernel (trunk_fused.cuh)
     bool small_trunk_ = false;  // F == 16: whole trunk + head convs in one kernel (trunk_small.cuh)
+    bool simple_ = false;       // SimpleTwoHeadedModel: three dense layers, no convolutions
 
     // derived layout constants (bf16 path)
     uint32_t cin_pad_ = 64;  // encoded-input channels (multiple of 64)
@@ -235,6 +240,7 @@ class Engine {
     };
     std::vector<GemmW> convs_;  // stem, then 2 per block (bf16: [Np][9*Cin_pad] bf16; fp32: torch layout f32)
     GemmW vconv_, pconv_, vfc1_, pfc_;
+    GemmW dense1_, dense2_;  // SimpleTwoHeadedModel
     DeviceBuf vfc2_w_;
     float vfc2_b_ = 0.0f;
     DeviceBuf fused_w_, fused_b_;  // trunk_fused.cuh weight images + biases

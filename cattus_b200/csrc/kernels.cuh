@@ -107,6 +107,68 @@ __global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ in, int n
     }
 }
 
+// ---------------------------------------------------------------------------------------------- SimpleTwoHeadedModel
+// nn.Flatten of the NCHW planes (net_utils.py:101,113): out[b][j] = bit(plane j / S^2, cell j % S^2), j < features; columns up
+// to k_pad and rows >= n are zero.  One thread writes 8 columns (16 B).
+__global__ void encode_flat_bf16_kernel(const uint8_t* __restrict__ recs, RecLayout L, const uint32_t* __restrict__ n_ptr, int batch,
+                                        int features, int k_pad, int ld, __nv_bfloat16* __restrict__ out) {
+    const int n = static_cast<int>(*n_ptr);
+    const int s2 = L.s * L.s;
+    const int chunks = k_pad / 8;
+    const long long total = static_cast<long long>(batch) * chunks;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int chunk = static_cast<int>(i % chunks);
+        const int b = static_cast<int>(i / chunks);
+        uint32_t w[4] = {0, 0, 0, 0};
+        if (b < n) {
+            const uint64_t* pl = reinterpret_cast<const uint64_t*>(recs + static_cast<size_t>(b) * L.rec_bytes);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int f = chunk * 8 + j;
+                if (f < features && plane_bit(pl, L.wpp, f / s2, f % s2)) w[j >> 1] |= (j & 1) ? 0x3F800000u : 0x00003F80u;  // bf16 1.0
+            }
+        }
+        *reinterpret_cast<uint4*>(out + static_cast<long long>(b) * ld + chunk * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+// run_dense entry: user f32 NCHW (already the flatten order) -> bf16 rows [batch][ld], columns >= features zero
+__global__ void nchw_f32_to_flat_bf16_kernel(const float* __restrict__ in, int batch, int features, int k_pad, int ld,
+                                             __nv_bfloat16* __restrict__ out) {
+    const int chunks = k_pad / 8;
+    const long long total = static_cast<long long>(batch) * chunks;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int chunk = static_cast<int>(i % chunks);
+        const int b = static_cast<int>(i / chunks);
+        __nv_bfloat16* o = out + static_cast<long long>(b) * ld + chunk * 8;
+        for (int j = 0; j < 8; ++j) {
+            const int f = chunk * 8 + j;
+            o[j] = __float2bfloat16(f < features ? in[static_cast<long long>(b) * features + f] : 0.0f);
+        }
+    }
+}
+
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+// value = tanh(b2 + sum_j x[b][j] * w2[j]) over k columns (net_utils.py:118-119); one warp per position; rows >= n zero
+template <class T>
+__global__ void dot_tanh_kernel(const T* __restrict__ x, int ld, int k, const float* __restrict__ w2, float b2,
+                                const uint32_t* __restrict__ n_ptr, int batch, float* __restrict__ values) {
+    const int n = n_ptr ? static_cast<int>(*n_ptr) : batch;
+    const int lane = threadIdx.x & 31;
+    const int b = static_cast<int>((blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5);
+    if (b >= batch || b >= n) return;
+    const T* row = x + static_cast<long long>(b) * ld;
+    float acc = 0.0f;
+    for (int j = lane; j < k; j += 32) acc = fmaf(to_f32(row[j]), w2[j], acc);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, d);
+    if (lane == 0) values[b] = tanhf(acc + b2);
+}
+
 // ---------------------------------------------------------------------------------------------- fp32 check path
 // Direct NCHW convolution, ksize 1 or 3, "same" zero padding, folded-BN bias, optional residual and ReLU.
 __global__ void conv_f32_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,

@@ -8,7 +8,7 @@ C++ engine at load time, so the file format is independent of the kernels.
 Fold (eval-mode BN, eps = 1e-5, training/cattus_train/net_utils.py:14,30,33 -- affine only where the reference has
 `affine=True`):   scale = gamma / sqrt(var + eps);   w' = w * scale[oc];   b' = beta - mean * scale.
 
-Layout: 64-byte header (u32 LE: magic "CB2\\0", version 1, game, S, C_in, M, F, R, VH, PH, hidden=128, 5 x 0), then f32 LE:
+Layout: 64-byte header (u32 LE: magic "CB2\\0", version 1, game, S, C_in, M, F, R, VH, PH, hidden=128, architecture tag 0, 4 x 0), then f32 LE:
   stem w[F,C,3,3] b[F] | R x (conv1 w[F,F,3,3] b[F], conv2 w b) | value conv w[VH,F] b[VH] | value fc1 w[128,VH*S*S] b[128]
   | value fc2 w[128] b[1] | policy conv w[PH,F] b[PH] | policy fc w[M,PH*S*S] b[M]
 """
@@ -58,7 +58,27 @@ def infer_dims(sd: Mapping[str, object], game: str) -> dict:
     return dict(game=game, board_size=s, planes=c_in, moves=moves, filters=f, blocks=r, value_channels=vh, policy_channels=ph)
 
 
+PLANES = {"ttt": 3, "hex": 3, "chess": 18}  # position_to_planes: ttt/net.rs:14-24, hex/net.rs:14-24, chess/net/mod.rs:19-60
+
+
+def export_simple_blob(sd: Mapping[str, object], game: str) -> bytes:
+    """SimpleTwoHeadedModel (net_utils.py:92-121): header with architecture tag 1 and `hidden` = C * S * S, then f32 LE
+    dense1 w[n,n] b[n] | dense2 w[n,n] b[n] | value w[n] b[1] | policy w[M,n] b[M]."""
+    n = _np(sd["_dense1.weight"]).shape[0]
+    planes = PLANES[game]
+    s = int(round((n / planes) ** 0.5))
+    assert planes * s * s == n, "SimpleTwoHeadedModel width is not planes * S * S for this game"
+    moves = _np(sd["_policy_head.weight"]).shape[0]
+    parts = [np.ascontiguousarray(_np(sd[k]), dtype="<f4").reshape(-1).tobytes()
+             for k in ("_dense1.weight", "_dense1.bias", "_dense2.weight", "_dense2.bias", "_value_head.weight", "_value_head.bias",
+                       "_policy_head.weight", "_policy_head.bias")]
+    header = struct.pack("<16I", MAGIC, 1, GAME_IDS[game], s, planes, moves, 0, 0, 0, 0, n, 1, 0, 0, 0, 0)
+    return header + b"".join(parts)
+
+
 def export_blob(sd: Mapping[str, object], game: str) -> bytes:
+    if "_dense1.weight" in sd:
+        return export_simple_blob(sd, game)
     d = infer_dims(sd, game)
     parts = []
 

@@ -107,6 +107,7 @@ typedef struct cattus_b200_info {
 #define CATTUS_B200_TRUNK_FUSED 1     /* trunk_fused.cuh: 8x8 boards, 128 filters, <= 32 planes, VH + PH <= 64 */
 #define CATTUS_B200_TRUNK_SMALL 2     /* trunk_small.cuh: 16 filters, boards 3..11, <= 32 planes, VH + PH <= 32 */
 #define CATTUS_B200_TRUNK_FP32 3      /* precision FP32_CHECK: CUDA-core fp32 loops (parity only) */
+#define CATTUS_B200_TRUNK_DENSE 4     /* SimpleTwoHeadedModel (net_utils.py:92-121): no convolutions, three dense layers */
 
 /* Replaces Model::new (engine/src/net/model.rs:61-144). */
 int cattus_b200_create(const cattus_b200_desc* desc, cattus_b200_t** out);

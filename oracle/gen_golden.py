@@ -118,8 +118,14 @@ def gen_net(nu, out_dir: Path):
         "hex5_2x2": ("synth", 8), "ttt": ("synth", 8), "hex4": ("synth", 8), "hex5": ("synth", 16), "hex7": ("synth", 8),
         "hex9": ("synth", 4), "hex11": ("synth", 4), "chess_dev": ("synth", 8), "chess_2x128": ("synth", 8),
         "chess10x128": ("synth", 8),
+        "chess_4x64": ("synth", 8), "chess_4x256": ("synth", 4), "hex7_4x32": ("synth", 8), "hex11_2x128": ("synth", 4),
+        "ttt_simple": ("fixtures", [games.ttt_position_to_planes(*games.ttt_position_from_str(s)[:2]) for s in TTT_FIXTURES]),
+        "hex5_simple": ("synth", 8), "hex11_simple": ("synth", 4), "chess_simple": ("synth", 8),
     }
+    only = set(sys.argv[1:])
     for name, (kind, arg) in cases.items():
+        if only and name not in only:
+            continue
         cfg = net.CONFIGS[name]
         if kind == "fixtures":
             words = games.pack_planes(arg, cfg.board_size)
@@ -129,8 +135,11 @@ def gen_net(nu, out_dir: Path):
             words, _ = games.synth_hex_positions(arg, cfg.board_size, seed=11)
         x = games.planes_to_tensor_fast(words, cfg.board_size, cfg.planes)
         sd = net.make_state_dict(cfg, seed=0)
-        model = nu.ConvNetV1((1, cfg.planes, cfg.board_size, cfg.board_size), cfg.blocks, cfg.filters,
-                             cfg.value_channels, cfg.policy_channels, cfg.moves)
+        if cfg.arch == "simple":  # the reference's second model type (net_utils.py:92-121)
+            model = nu.SimpleTwoHeadedModel((1, cfg.planes, cfg.board_size, cfg.board_size), cfg.moves)
+        else:
+            model = nu.ConvNetV1((1, cfg.planes, cfg.board_size, cfg.board_size), cfg.blocks, cfg.filters,
+                                 cfg.value_channels, cfg.policy_channels, cfg.moves)
         model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
         model.eval()
         with torch.no_grad():
@@ -155,6 +164,9 @@ def gen_chess_table(out: Path):
 if __name__ == "__main__":
     GOLDEN.mkdir(parents=True, exist_ok=True)
     nu = _load_reference_modules()
-    gen_encode(GOLDEN / "encode_ref.npz")
-    gen_net(nu, GOLDEN)
-    gen_chess_table(GOLDEN / "chess_nn_index.txt")
+    if len(sys.argv) > 1:  # `python oracle/gen_golden.py <config> ...`: only those networks' fixtures
+        gen_net(nu, GOLDEN)
+    else:
+        gen_encode(GOLDEN / "encode_ref.npz")
+        gen_net(nu, GOLDEN)
+        gen_chess_table(GOLDEN / "chess_nn_index.txt")

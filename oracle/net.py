@@ -1,4 +1,5 @@
-"""CPU oracle (TEST INFRASTRUCTURE ONLY) for the floating-point half of the path: the ConvNetV1 forward pass.
+"""CPU oracle (TEST INFRASTRUCTURE ONLY) for the floating-point half of the path: the ConvNetV1 forward pass (and
+the reference's second model type, SimpleTwoHeadedModel, net_utils.py:92-121).
 
 Restates `training/cattus_train/net_utils.py:4-89` (ConvBlock :4-20, ResidualBlock :23-42, ConvNetV1 :45-89)
 as explicit fp32 torch-functional calls over a plain `{state_dict key: numpy array}` mapping, so that it runs
@@ -34,14 +35,23 @@ class NetConfig:
     value_channels: int  # VH
     policy_channels: int  # PH
     game: str = "hex"  # "ttt" | "hex" | "chess"
+    arch: str = "convnet"  # "convnet" = ConvNetV1 (net_utils.py:45-89) | "simple" = SimpleTwoHeadedModel (:92-121; F, R, VH, PH unused)
 
     def to_dict(self):
         return asdict(self)
 
     @property
+    def features(self) -> int:
+        """SimpleTwoHeadedModel's width: C * H * W (net_utils.py:97-99)."""
+        return self.planes * self.board_size ** 2
+
+    @property
     def flops_per_position(self) -> int:
         """2*MAC, unpadded."""
         s2 = self.board_size ** 2
+        if self.arch == "simple":
+            n = self.features
+            return 2 * (2 * n * n) + 2 * n + 2 * n * self.moves
         f, r = self.filters, self.blocks
         return (2 * 9 * self.planes * f * s2 + r * 2 * (2 * 9 * f * f * s2) + 2 * f * self.value_channels * s2
                 + 2 * self.value_channels * s2 * VALUE_HIDDEN + 2 * VALUE_HIDDEN + 2 * f * self.policy_channels * s2
@@ -70,6 +80,18 @@ CONFIGS: Dict[str, NetConfig] = {
     "chess_1x1": NetConfig(8, 18, 1880, 1, 1, 1, 1, "chess"),
     "hex5_2x2": NetConfig(5, 3, 25, 2, 2, 4, 4, "hex"),
     "chess_2x128": NetConfig(8, 18, 1880, 128, 2, 32, 32, "chess"),
+    # widths and depths the reference's config recommends (training/config/chess_dev.yaml:30-37: 32-256 filters, 7-39 blocks)
+    # that neither whole-trunk kernel covers: they take the per-layer tensor-core path
+    "chess_4x64": NetConfig(8, 18, 1880, 64, 4, 8, 8, "chess"),
+    "chess_4x256": NetConfig(8, 18, 1880, 256, 4, 16, 16, "chess"),
+    "hex7_4x32": NetConfig(7, 3, 49, 32, 4, 16, 16, "hex"),
+    "hex11_2x128": NetConfig(11, 3, 121, 128, 2, 16, 16, "hex"),
+    "chess20x256": NetConfig(8, 18, 1880, 256, 20, 32, 32, "chess"),  # the top of the recommended range (bench workload only)
+    # SimpleTwoHeadedModel (net_utils.py:92-121; training/tests/test_simple_two_headed.py)
+    "ttt_simple": NetConfig(3, 3, 9, 0, 0, 0, 0, "ttt", "simple"),
+    "hex5_simple": NetConfig(5, 3, 25, 0, 0, 0, 0, "hex", "simple"),
+    "hex11_simple": NetConfig(11, 3, 121, 0, 0, 0, 0, "hex", "simple"),
+    "chess_simple": NetConfig(8, 18, 1880, 0, 0, 0, 0, "chess", "simple"),
     # depth ladder for the fused-trunk parity tests (stem only, one block)
     "chess_0x128": NetConfig(8, 18, 1880, 128, 0, 32, 32, "chess"),
     "chess_1x128": NetConfig(8, 18, 1880, 128, 1, 32, 32, "chess"),
@@ -80,6 +102,11 @@ def state_dict_spec(cfg: NetConfig):
     """(key, shape, kind) for every tensor of ConvNetV1's state_dict, in module order.
     kind: conv | bn_w | bn_b | bn_mean | bn_var | bn_nbt | fc_w | fc_b."""
     s2 = cfg.board_size ** 2
+    if cfg.arch == "simple":  # net_utils.py:101-110
+        n = cfg.features
+        return [("_dense1.weight", (n, n), "fc_w"), ("_dense1.bias", (n,), "fc_b"), ("_dense2.weight", (n, n), "fc_w"), ("_dense2.bias", (n,), "fc_b"),
+                ("_value_head.weight", (1, n), "fc_w"), ("_value_head.bias", (1,), "fc_b"),
+                ("_policy_head.weight", (cfg.moves, n), "fc_w"), ("_policy_head.bias", (cfg.moves,), "fc_b")]
     f = cfg.filters
     spec = [("_conv1._conv.weight", (f, cfg.planes, 3, 3), "conv")]
     spec += _bn("_conv1._bn", f, affine=True)
@@ -187,6 +214,12 @@ def _forward_torch(t, cfg: NetConfig, flow):
     (conv1x1 -> BN(no affine) -> ReLU -> flatten(NCHW) -> FC -> ReLU -> FC -> tanh); policy head :78-82 (raw logits)."""
     import torch
     import torch.nn.functional as F
+
+    if cfg.arch == "simple":  # SimpleTwoHeadedModel.forward (net_utils.py:112-121)
+        flow = flow.flatten(1)
+        flow = F.relu(F.linear(flow, t["_dense1.weight"], t["_dense1.bias"]))
+        flow = F.relu(F.linear(flow, t["_dense2.weight"], t["_dense2.bias"]))
+        return F.linear(flow, t["_policy_head.weight"], t["_policy_head.bias"]), torch.tanh(F.linear(flow, t["_value_head.weight"], t["_value_head.bias"]))
 
     def bn(f_, prefix, affine):
         return F.batch_norm(f_, t[f"{prefix}.running_mean"], t[f"{prefix}.running_var"],

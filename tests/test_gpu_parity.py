@@ -17,7 +17,11 @@ pytestmark = pytest.mark.gpu
 TOL_FP32 = 1e-4  # max abs error on probabilities and value, fp32 check mode
 TOL_BF16 = 1e-2  # max abs error on probabilities and value, bf16 tensor-core path
 
-ALL = ["ttt", "hex4", "hex5", "hex7", "hex9", "hex11", "chess_dev", "chess_2x128", "chess10x128", "ttt_1x1", "hex11_1x1", "chess_1x1", "hex5_2x2"]
+ALL = ["ttt", "hex4", "hex5", "hex7", "hex9", "hex11", "chess_dev", "chess_2x128", "chess10x128", "ttt_1x1", "hex11_1x1", "chess_1x1", "hex5_2x2",
+       # widths / depths the reference's config recommends (chess_dev.yaml:30-37) outside the two whole-trunk kernels: per-layer path
+       "chess_4x64", "chess_4x256", "hex7_4x32", "hex11_2x128",
+       # the reference's second model type (net_utils.py:92-121)
+       "ttt_simple", "hex5_simple", "hex11_simple", "chess_simple"]
 
 
 # ----------------------------------------------------------------------------------------------- encode (bit-exact)
@@ -56,7 +60,7 @@ def test_encode_random_large_and_errors():
 # ----------------------------------------------------------------------------------------------- Model::run parity
 @pytest.mark.parametrize("name", ALL)
 def test_run_dense_fp32_check_vs_reference_golden(name):
-    """fp32 check mode against the outputs the reference's ConvNetV1 produced (tests/golden/net_ref_*.npz)."""
+    """fp32 check mode against the outputs the reference's ConvNetV1 / SimpleTwoHeadedModel produced (tests/golden/net_ref_*.npz)."""
     g = np.load(GOLDEN / f"net_ref_{name}.npz")
     cfg = net.CONFIGS[name]
     x = games.planes_to_tensor_fast(g["words"], cfg.board_size, cfg.planes)
@@ -86,6 +90,18 @@ def test_run_dense_bf16_vs_reference_golden(name):
     assert err_l <= 0.08 * max(1.0, np.abs(g["logits"]).max())
 
 
+def test_info_says_which_trunk_path_a_handle_got():
+    """cattus_b200_info.trunk_path: the whole-trunk kernels cover fixed shapes; everything else takes the per-layer kernel."""
+    for name, want in (("chess10x128", "fused"), ("chess_2x128", "fused"), ("hex5", "small"), ("chess_dev", "small"), ("chess_4x64", "per-layer"),
+                       ("chess_4x256", "per-layer"), ("hex7_4x32", "per-layer"), ("hex11_2x128", "per-layer"), ("hex5_simple", "dense")):
+        with make_network(name, batch_size=16, n_streams=1) as nw:
+            assert nw.trunk_path == want, (name, nw.trunk_path)
+    with make_network("hex5", precision="fp32-check", batch_size=16, n_streams=1) as nw:
+        assert nw.trunk_path == "fp32-check"
+    with make_network("chess10x128", batch_size=16, n_streams=1, fused_trunk=False) as nw:
+        assert nw.trunk_path == "per-layer"
+
+
 # ----------------------------------------------------------------------------------------------- evaluate parity
 def _check_eval(name, precision, n, seed, tol, batch_size=256, n_streams=2):
     words, bitmaps, legal = synth_inputs(name, n, seed)
@@ -110,12 +126,14 @@ def _check_eval(name, precision, n, seed, tol, batch_size=256, n_streams=2):
     return probs, offsets, values
 
 
-@pytest.mark.parametrize("name", ["ttt", "hex4", "hex5", "hex7", "hex9", "hex11", "chess_dev", "chess_2x128"])
+@pytest.mark.parametrize("name", ["ttt", "hex4", "hex5", "hex7", "hex9", "hex11", "chess_dev", "chess_2x128", "chess_4x64", "hex7_4x32", "hex11_2x128",
+                                  "ttt_simple", "hex5_simple", "hex11_simple", "chess_simple"])
 def test_eval_batch_fp32_check(name):
     _check_eval(name, "fp32-check", 48, 101, TOL_FP32, batch_size=32)
 
 
-@pytest.mark.parametrize("name", ["ttt", "hex4", "hex5", "hex7", "hex9", "hex11", "chess_dev", "chess_2x128", "chess10x128"])
+@pytest.mark.parametrize("name", ["ttt", "hex4", "hex5", "hex7", "hex9", "hex11", "chess_dev", "chess_2x128", "chess10x128", "chess_4x64", "chess_4x256",
+                                  "hex7_4x32", "hex11_2x128", "ttt_simple", "hex5_simple", "hex11_simple", "chess_simple"])
 def test_eval_batch_bf16(name):
     _check_eval(name, "bf16", 300, 202, TOL_BF16, batch_size=128)
 
