@@ -576,6 +576,7 @@ Op Engine::make_tc_op(int stage, const char* name, const TcGemmParams& p, uint32
     const dim3 grid(m_tiles, n_tiles);
     TcGemmParams q = p;
     q.stages = tc_stages_for(m_tiles * n_tiles);
+    q.fault = (desc_.flags & 2u) && stage == 2 ? 1 : 0;
     const int smem_bytes = tc_smem_bytes(q.stages);
     op.launch = [q, grid, smem_bytes](cudaStream_t st) { tc_gemm_kernel<<<grid, kTcThreads, smem_bytes, st>>>(q); };
     return op;
@@ -1062,6 +1063,7 @@ void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
         op.name = "heads_fc_dual";
         const dim3 grid(ceil_div(bucket, 128), 1 + pfc_.n_tiles);
         dp.a.stages = dp.b.stages = tc_stages_for(grid.x * grid.y);
+        dp.a.fault = (desc_.flags & 2u) ? 1 : 0;
         const int smem_bytes = tc_smem_bytes(dp.a.stages);
         op.launch = [dp, grid, smem_bytes](cudaStream_t st) { tc_gemm_dual_kernel<<<grid, kTcThreads, smem_bytes, st>>>(dp); };
         ops.push_back(op);

@@ -55,10 +55,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 // Bounded wait.  `err` is a device word that receives `code` before the trap so the host can say which wait died.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t* err, uint32_t code) {
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t* err, uint32_t code, uint32_t max_spins = 1u << 24) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 24)) {
+        if (++spins > max_spins) {
             if (err) atomicExch(err, code);
             __threadfence_system();
             __trap();

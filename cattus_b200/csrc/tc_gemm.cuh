@@ -56,6 +56,7 @@ struct alignas(64) TcGemmParams {
     uint32_t tx_bytes;  // bytes one stage's two TMA boxes deliver
     int stages;         // smem ring depth (kTcStages or kTcStagesDeep); the launch passes tc_smem_bytes(stages)
     int epi;            // epilogue variant, see above
+    int fault;          // 1: fault injection, see the MMA issuer
     // epi 1
     const float* w2;    // [128]
     float b2;
@@ -141,7 +142,9 @@ __device__ __forceinline__ void tc_gemm_body(const TcGemmParams& p, const int m_
                 }
                 ptx::umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
             }
-            ptx::umma_commit(tmem_full_bar);  // accumulator complete
+            // fault injection (cattus_b200_desc.flags bit 1, tests only): tile (0, 0) never publishes its accumulator, so the
+            // epilogue's bounded wait below expires, records its code and traps -- the path a pipeline bug would take
+            if (!(p.fault && m_tile == 0 && n_tile == 0)) ptx::umma_commit(tmem_full_bar);  // accumulator complete
         }
     } else {
         // Epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32); warps 2,3,4,5 cover all four quarters.
@@ -156,7 +159,7 @@ __device__ __forceinline__ void tc_gemm_body(const TcGemmParams& p, const int m_
             ok = row < p.rows_per_tile && (m_tile * p.nb + row / p.s2) < p.m_valid;
             grow = static_cast<long long>(m_tile) * p.rows_per_tile + row;
         }
-        ptx::mbar_wait(tmem_full_bar, 0, p.err, 0x300);
+        ptx::mbar_wait(tmem_full_bar, 0, p.err, 0x300, p.fault ? (1u << 14) : (1u << 24));
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + ((q * 32u) << 16);
         if (p.epi == 1) {

@@ -29,7 +29,7 @@ def _ptr(a: np.ndarray, typ):
 
 class CudaNetwork:
     def __init__(self, model, game: str, *, device: int = 0, batch_size: int = 64, n_streams: int = 2,
-                 precision: str = "bf16", cache: Optional[ValueFuncCache] = None, fused_trunk: bool = True):
+                 precision: str = "bf16", cache: Optional[ValueFuncCache] = None, fused_trunk: bool = True, fault_inject: bool = False):
         """model: path to a .cb2 blob, or the blob bytes (cattus_b200.export.export_blob)."""
         self._lib = _lib.load()
         self._h = C.c_void_p()
@@ -42,6 +42,8 @@ class CudaNetwork:
         desc.max_batch = batch_size
         desc.n_streams = n_streams
         desc.flags = 0 if fused_trunk else 1  # bit 0: force the per-layer kernels (parity tests compare both paths)
+        if fault_inject:
+            desc.flags |= 2  # bit 1: tests only -- a head GEMM tile never publishes its accumulator (include/cattus_b200.h)
         desc.precision = {"bf16": _lib.PRECISION_BF16, "fp32-check": _lib.PRECISION_FP32_CHECK}[precision]
         if isinstance(model, (bytes, bytearray, memoryview)):
             buf = bytes(model)

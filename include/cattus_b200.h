@@ -76,7 +76,11 @@ typedef struct cattus_b200_desc {
     uint32_t max_batch;       /* positions per device batch (reference: engine.model.batch_size) */
     uint32_t n_streams;       /* evaluator streams, each with its own batch buffers and CUDA graphs (>=1) */
     uint32_t precision;       /* CATTUS_B200_PRECISION_* */
-    uint32_t flags;           /* reserved, 0 */
+    uint32_t flags;           /* bit 0: force the per-layer kernels and the standalone tail kernels (the comparison path of the
+                               * parity tests); bit 1: FAULT INJECTION for tests -- the first head GEMM tile of every batch never
+                               * publishes its accumulator, so the kernel's bounded wait expires and the call fails with
+                               * CATTUS_B200_EDEVICE (a device fault poisons the process's CUDA context: destroy the handle, and
+                               * evaluate again from a new process); other bits 0 */
     const char* weights_path; /* may be NULL when create_from_memory is used */
 } cattus_b200_desc;
 

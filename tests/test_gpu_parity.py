@@ -398,3 +398,43 @@ def test_non_finite_logits_are_clamped_like_the_reference(name, precision):
             seen_partial += 1
     assert seen_partial > 0 and (seen_all > 0 or bitmaps is None)
     assert np.abs(values - o_values.reshape(-1)).max() <= tol
+
+
+# ----------------------------------------------------------------------------------------------- the device fault path
+FAULT_SCRIPT = """
+import sys
+sys.path.insert(0, {root!r})
+from cattus_b200 import CudaNetwork
+from cattus_b200._lib import CattusB200Error, EDEVICE
+from tests.util import blob, synth_inputs
+words, bitmaps, _ = synth_inputs({name!r}, 8, 1)
+nw = CudaNetwork(blob({name!r}), {game!r}, batch_size=16, n_streams=1, fault_inject=True)   # creation itself evaluates nothing
+try:
+    nw.eval_batch(words, bitmaps)
+    print("NO-ERROR")
+except CattusB200Error as e:
+    print("CODE", e.code, "EDEVICE" if e.code == EDEVICE else "other", str(e))
+nw.close()   # must return: the context is poisoned, the handle is still destroyable
+print("CLOSED")
+"""
+
+
+@pytest.mark.parametrize("name,game", [("hex5", "hex"), ("chess10x128", "chess")])
+def test_pipeline_fault_comes_back_as_edevice_and_the_gpu_survives(name, game):
+    """Every mbarrier wait in the kernels is bounded.  With fault injection (desc.flags bit 1) one head GEMM tile never
+    publishes its accumulator: the epilogue's wait must expire, record its code (0x300) and trap; the call must come back
+    with CATTUS_B200_EDEVICE and the fault word instead of hanging; the handle must be destroyable; and a NEW process (the
+    fault poisons the old one's CUDA context) must create a handle and evaluate again."""
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = str(Path(__file__).resolve().parent.parent)
+    res = subprocess.run([sys.executable, "-c", FAULT_SCRIPT.format(root=root, name=name, game=game)], capture_output=True, text=True, timeout=300)
+    out = res.stdout
+    assert "CODE" in out and "EDEVICE" in out and "0x300" in out, (out, res.stderr[-2000:])
+    assert "CLOSED" in out, (out, res.stderr[-2000:])
+    words, bitmaps, legal = synth_inputs(name, 8, 1)
+    with make_network(name, batch_size=16, n_streams=1) as nw:  # this process's context is fine: the GPU was not wedged
+        probs, offsets, _ = nw.eval_batch(words, bitmaps)
+    assert np.diff(offsets.astype(np.int64)).tolist() == [len(l) for l in legal]
