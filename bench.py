@@ -651,7 +651,7 @@ def main():
             threads = args.selfplay_threads or max(1, cores // max(1, world))
             gpt = args.selfplay_gpt or (1024 if chess_sp else 512)
             h_games = max(2, (threads * gpt if chess_sp else min(8192, threads * gpt)) * world // 2 * 2)
-            h_max_moves = min(sp_max_moves, 8) if chess_sp else sp_max_moves
+            h_max_moves = sp_max_moves  # the same games as the device-resident leg (the host cache's hit rate depends on how far games go)
             with CudaNetwork(sp_blob, sp_cfg.game, device=local_rank, batch_size=max(64, min(4096, gpt)),
                              n_streams=max(4, min(32, threads * args.selfplay_groups)), precision="bf16") as h_nw:
                 h_runner = SelfPlayRunner(runner_game(sp_game), {"mcts": mc, "threads": threads, "games_per_thread": gpt,

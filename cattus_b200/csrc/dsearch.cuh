@@ -83,7 +83,7 @@ class DsCudaBackend {
             CB2_CUDA(cudaMemcpy(d_rules_, rules_blob, rules_bytes, cudaMemcpyHostToDevice));
             alloc(d_slots_, sizeof(ds::SlotState) * n_slots);
             CB2_CUDA(cudaMemset(d_slots_, 0, sizeof(ds::SlotState) * n_slots));
-            alloc(d_pools_, static_cast<size_t>(n_slots) * 3u * pool_words_ * 4u);
+            alloc(d_pools_, static_cast<size_t>(n_slots) * 3u * pool_words_ * 4u + 1024u);  // + slack: select fetches a node's first 32 child rows before it knows the count
             const uint32_t path_cap = Rules::kChess ? 256u : max_children + 2u;
             alloc(d_paths_, sizeof(ds::PathStep) * static_cast<size_t>(n_slots) * path_cap);
             alloc(d_noise_, sizeof(float) * static_cast<size_t>(n_slots) * max_children);

@@ -84,20 +84,23 @@ CB2_HD inline int wfirst(bool p) {
 #endif
 }
 // (v, i) of the maximal v over the warp; equal values -> the smaller i
-CB2_HD inline void wargmax(float& v, int& i) {
+CB2_HD inline void wargmax(float& v, int& i, uint32_t& payload) {
 #if DS_DEVICE
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
         const float ov = __shfl_xor_sync(0xFFFFFFFFu, v, d);
         const int oi = __shfl_xor_sync(0xFFFFFFFFu, i, d);
+        const uint32_t op = __shfl_xor_sync(0xFFFFFFFFu, payload, d);
         if (ov > v || (ov == v && oi < i)) {
             v = ov;
             i = oi;
+            payload = op;
         }
     }
 #else
     (void)v;
     (void)i;
+    (void)payload;
 #endif
 }
 // exclusive prefix sum over the lanes; total = sum over the warp
@@ -198,9 +201,19 @@ struct SlotState {
 };
 
 struct PathStep {
-    int32_t w_idx;  // word index of the taken child's score_w in the tree's pool
-    int32_t count;  // children of that node: simulations_n is `count` words further
+    int32_t c_idx;  // word index of the taken child's row {init, w, n, edge} in the tree's pool
+    int32_t pad;
     int32_t child;  // block of the node the step leads to
+};
+
+// One child of a node: MctsEdge (mod.rs:32-45) + the link to the child's block.  16 bytes, so a lane fetches its child with
+// ONE 128-bit load at an address that does not depend on the node's child count -- select issues it together with the
+// header load, and the winner's edge word arrives with its score: one dependent global round trip per tree level.
+struct alignas(16) Child {
+    float init;     // init_score
+    float w;        // score_w
+    int32_t n;      // simulations_n
+    uint32_t edge;  // (child block offset / 4 + 1) in the low 24 bits (0: not visited yet) | move << 24
 };
 
 // The evaluator's device-resident batch: [u32 n][pad to 16 B][record 0: 8-byte prefix | planes | legal bitmap] ...
@@ -273,19 +286,16 @@ struct alignas(16) NodeHdr {
     int32_t expanded;  // rows are valid: create_children has run (mod.rs:246-262)
 };
 
-// Search tree storage, as in the host driver: every visited node is one 16-byte-aligned block of 32-bit words
-//   Header | init_score[count] f32 | score_w[count] f32 | simulations_n[count] i32 | edge[count] | move16[count] (chess)
-// edge = (child block offset / 4 + 1) in the low 24 bits (0: child not visited yet) + the move in the high 8.
+// Search tree storage: every visited node is one 16-byte-aligned block of 32-bit words
+//   Header | Child[count] | move16[count] (chess)
+// (the host driver keeps the four child fields as separate rows for its SIMD select; here a row per child suits a warp).
 template <class Rules>
 struct TreeOps {
     using Pos = typename Rules::Pos;
     using Hdr = NodeHdr<Pos>;
     static constexpr int kHdrWords = static_cast<int>((sizeof(Hdr) + 15) / 16 * 4);
     CB2_HD static Hdr* hdr(uint32_t* pool, int32_t b) { return reinterpret_cast<Hdr*>(pool + b); }
-    CB2_HD static float* init(uint32_t* pool, int32_t b) { return reinterpret_cast<float*>(pool + b + kHdrWords); }
-    CB2_HD static float* w(uint32_t* pool, int32_t b, int count) { return reinterpret_cast<float*>(pool + b + kHdrWords + count); }
-    CB2_HD static int32_t* n(uint32_t* pool, int32_t b, int count) { return reinterpret_cast<int32_t*>(pool + b + kHdrWords + 2 * count); }
-    CB2_HD static uint32_t* edge(uint32_t* pool, int32_t b, int count) { return pool + b + kHdrWords + 3 * count; }
+    CB2_HD static Child* child(uint32_t* pool, int32_t b) { return reinterpret_cast<Child*>(pool + b + kHdrWords); }
     CB2_HD static uint16_t* mv16(uint32_t* pool, int32_t b, int count) { return reinterpret_cast<uint16_t*>(pool + b + kHdrWords + 4 * count); }
     CB2_HD static uint32_t block_words(int count) {
         const uint32_t c = static_cast<uint32_t>(count);
@@ -327,7 +337,7 @@ struct Core {
         if constexpr (kChess)
             return T::mv16(pool, node, count)[i];
         else
-            return T::edge_move(T::edge(pool, node, count)[i]);
+            return T::edge_move(T::child(pool, node)[i].edge);
     }
 
     // Appends the block of a node visited for the first time (rows zeroed, not expanded); -1 when the pool is full.
@@ -359,8 +369,8 @@ struct Core {
                 uint16_t* mv = T::mv16(t.pool, b, count);
                 for (int i = 0; i < count; ++i) mv[i] = buf[i];
             }
-            uint32_t* rows = t.pool + b + T::kHdrWords + count;  // score_w and simulations_n start at zero
-            for (int i = ln; i < 2 * count; i += DS_LANES) rows[i] = 0u;
+            Child* ch = T::child(t.pool, b);  // score_w and simulations_n start at zero, no child visited yet
+            for (int i = ln; i < count; i += DS_LANES) ch[i] = Child{0.0f, 0.0f, 0, 0u};
             wsync();
             return b;
         } else {
@@ -375,8 +385,8 @@ struct Core {
                 h->count = count;
                 h->expanded = 0;
             }
-            uint32_t* rows = t.pool + b + T::kHdrWords + count;
-            for (int i = ln; i < 2 * count; i += DS_LANES) rows[i] = 0u;
+            Child* ch = T::child(t.pool, b);
+            for (int i = ln; i < count; i += DS_LANES) ch[i] = Child{0.0f, 0.0f, 0, 0u};
             wsync();
             return b;
         }
@@ -388,7 +398,7 @@ struct Core {
         const Pos child = R.moved(T::hdr(t.pool, node)->pos, static_cast<typename Rules::Move>(m));
         const int32_t cb = add_node(R, p, t, child);
         if (cb < 0) return -1;
-        if (lane() == 0) T::edge(t.pool, node, count)[i] = T::pack_edge(cb, kChess ? 0u : m);
+        if (lane() == 0) T::child(t.pool, node)[i].edge = T::pack_edge(cb, kChess ? 0u : m);
         wsync();
         return cb;
     }
@@ -397,19 +407,18 @@ struct Core {
     CB2_HD static void backpropagate(uint32_t* pool, const PathStep* path, uint32_t depth, uint8_t root_turn, float score) {
         for (uint32_t j = static_cast<uint32_t>(lane()); j < depth; j += DS_LANES) {
             const uint8_t turn = (j & 1u) ? static_cast<uint8_t>(3 - root_turn) : root_turn;
-            const int32_t wi = path[j].w_idx;
-            reinterpret_cast<int32_t*>(pool)[wi + path[j].count] += 1;
-            float* wp = reinterpret_cast<float*>(pool) + wi;
-            *wp = fadd(*wp, turn == 1 ? score : -score);
+            Child* c = reinterpret_cast<Child*>(pool + path[j].c_idx);
+            c->n += 1;
+            c->w = fadd(c->w, turn == 1 ? score : -score);
         }
     }
 
     // mod.rs:419-446 with the host's sample: zip(edges() order = newest first, noise)
     CB2_HD static void apply_noise(uint32_t* pool, int32_t node, int count, const float* nz, float eps) {
-        float* init = T::init(pool, node);
+        Child* ch = T::child(pool, node);
         const float keep = 1.0f - eps;
         for (int i = lane(); i < count; i += DS_LANES) {
-            float* x = init + (count - 1 - i);
+            float* x = &ch[count - 1 - i].init;
             *x = fadd(fmul(keep, *x), fmul(eps, nz[i]));
         }
     }
@@ -429,9 +438,9 @@ struct Core {
         }
         uint32_t* rn = reinterpret_cast<uint32_t*>(e + sizeof(ResultHdr));
         uint16_t* rm = reinterpret_cast<uint16_t*>(e + sizeof(ResultHdr) + 4u * p.max_children);
-        const int32_t* nn = T::n(pool, root, count);
+        const Child* ch = T::child(pool, root);
         for (int i = ln; i < count; i += DS_LANES) {
-            rn[i] = static_cast<uint32_t>(nn[i]);
+            rn[i] = static_cast<uint32_t>(ch[i].n);
             rm[i] = static_cast<uint16_t>(move_at(pool, root, count, i));
         }
     }
@@ -623,22 +632,21 @@ struct Core {
         Hdr* h = T::hdr(pool, leaf);
         const int count = h->count;
         const bool flipped = h->pos.turn != 1;
-        float* init = T::init(pool, leaf);
-        uint32_t* ed = T::edge(pool, leaf, count);
+        Child* ch = T::child(pool, leaf);
         if constexpr (kChess) {
             // child i takes the entry at the rank of its nn index among the legal ones (net/mod.rs:106-119 gathers per
             // legal move); the edge row holds the nn indices while the ranks are counted, then becomes "no child yet"
             const uint16_t* mv = T::mv16(pool, leaf, count);
-            for (int i = ln; i < count; i += DS_LANES) ed[i] = static_cast<uint32_t>(R.nn_idx(mv[i]));
+            for (int i = ln; i < count; i += DS_LANES) ch[i].edge = static_cast<uint32_t>(R.nn_idx(mv[i]));
             wsync();
             for (int i = ln; i < count; i += DS_LANES) {
-                const uint32_t idx = ed[i];
+                const uint32_t idx = ch[i].edge;
                 int rank = 0;
-                for (int j = 0; j < count; ++j) rank += ed[j] < idx ? 1 : 0;
-                init[i] = probs[rank];
+                for (int j = 0; j < count; ++j) rank += ch[j].edge < idx ? 1 : 0;
+                ch[i].init = probs[rank];
             }
             wsync();
-            for (int i = ln; i < count; i += DS_LANES) ed[i] = T::pack_edge(-1, 0u);  // chess moves live in move16
+            for (int i = ln; i < count; i += DS_LANES) ch[i].edge = T::pack_edge(-1, 0u);  // chess moves live in move16
         } else {
             // legal_moves() of the evaluated position, ascending; un-flipped by flip_score_if_needed (net/mod.rs:166-182)
             const Pos ev = flipped ? R.flipped_boards(h->pos) : h->pos;
@@ -647,8 +655,8 @@ struct Core {
             for (int cell = ln; cell < cells; cell += DS_LANES) {
                 if (static_cast<uint32_t>(legal >> cell) & 1u) {
                     const int k = sp::popcount128(legal & (sp::bit128(cell) - 1));
-                    init[k] = probs[k];
-                    ed[k] = T::pack_edge(-1, static_cast<uint32_t>(flipped ? R.flip_move(cell) : cell));
+                    ch[k].init = probs[k];
+                    ch[k].edge = T::pack_edge(-1, static_cast<uint32_t>(flipped ? R.flip_move(cell) : cell));
                 }
             }
         }
@@ -706,32 +714,38 @@ struct Core {
             uint32_t depth = 0;
             for (;;) {
                 const Hdr* h = T::hdr(t.pool, node);
+                const Child* ch = T::child(t.pool, node);
+                // this lane's first child, fetched BEFORE the child count is known (the address does not depend on it; a block
+                // is followed by pool slack, so the read is in bounds even for a childless node) -- it travels with the header
+                const Child c0 = ch[ln];
                 const int count = h->count;
                 if (!h->expanded || R.status(h->pos) != 0) break;
-                const int32_t* nn = T::n(t.pool, node, count);
-                const float* in = T::init(t.pool, node);
-                const float* ww = T::w(t.pool, node, count);
                 int part = 0;
-                for (int i = ln; i < count; i += DS_LANES) part += nn[i];
+                for (int i = ln; i < count; i += DS_LANES) part += (i < DS_LANES ? c0.n : ch[i].n);
                 const int simcount = 1 + wsum(part);
                 const float sq = fsqrt(static_cast<float>(simcount));
                 float bv = -__builtin_inff();
                 int bi = 0x7FFFFFFF;
+                uint32_t be = 0;
                 for (int i = ln; i < count; i += DS_LANES) {
-                    const int ni = nn[i];
-                    const float exploit = ni == 0 ? 0.0f : fdiv(ww[i], static_cast<float>(ni));
-                    const float explore = fmul(fmul(ef, in[i]), fdiv(sq, static_cast<float>(1 + ni)));
+                    const Child c = i < DS_LANES ? c0 : ch[i];
+                    const float exploit = c.n == 0 ? 0.0f : fdiv(c.w, static_cast<float>(c.n));
+                    const float explore = fmul(fmul(ef, c.init), fdiv(sq, static_cast<float>(1 + c.n)));
                     const float v = fadd(exploit, explore);
                     // strict > over ascending i keeps the smallest index among equals; NaNs are never picked (the
                     // reference asserts them away, mod.rs:444)
                     if (v == v && (bi == 0x7FFFFFFF || v > bv)) {
                         bv = v;
                         bi = i;
+                        be = c.edge;
                     }
                 }
-                wargmax(bv, bi);
-                if (bi == 0x7FFFFFFF) bi = count - 1;
-                int32_t c = T::edge_child(T::edge(t.pool, node, count)[bi]);
+                wargmax(bv, bi, be);
+                if (bi == 0x7FFFFFFF) {
+                    bi = count - 1;
+                    be = ch[bi].edge;
+                }
+                int32_t c = T::edge_child(be);
                 if (c < 0) {
                     c = materialise(R, p, t, node, count, bi);
                     if (c < 0) {
@@ -745,8 +759,8 @@ struct Core {
                 }
                 if (ln == 0) {
                     PathStep ps;
-                    ps.w_idx = node + T::kHdrWords + count + bi;
-                    ps.count = count;
+                    ps.c_idx = node + T::kHdrWords + 4 * bi;
+                    ps.pad = 0;
                     ps.child = c;
                     path[depth] = ps;
                 }
@@ -870,12 +884,12 @@ struct Core {
         const Hdr* h = T::hdr(t.pool, node);
         if (!h->expanded) return -1;
         const int count = h->count;
-        const uint32_t* ed = T::edge(t.pool, node, count);
+        const Child* ch = T::child(t.pool, node);
         for (int base = 0; base < count; base += DS_LANES) {
             const int i = count - 1 - (base + lane());
             bool hit = false;
             if (i >= 0) {
-                const int32_t c = T::edge_child(ed[i]);
+                const int32_t c = T::edge_child(ch[i].edge);
                 if (c >= 0)
                     hit = R.same(T::hdr(t.pool, c)->pos, position);
                 else
@@ -884,7 +898,7 @@ struct Core {
             const int f = wfirst(hit);
             if (f >= 0) {
                 const int fi = count - 1 - (base + f);
-                int32_t c = T::edge_child(ed[fi]);
+                int32_t c = T::edge_child(ch[fi].edge);
                 if (c < 0) {
                     c = materialise(R, p, t, node, count, fi);
                     if (c < 0) return -2;
@@ -904,7 +918,7 @@ struct Core {
         if (!rh->expanded) return -1;
         const int count = rh->count;
         for (int i = count - 1; i >= 0; --i) {
-            const int32_t c = T::edge_child(T::edge(t.pool, t.root, count)[i]);
+            const int32_t c = T::edge_child(T::child(t.pool, t.root)[i].edge);
             if (c < 0) continue;
             r = scan_children(R, p, t, c, position);
             if (r != -1) return r;
@@ -953,9 +967,9 @@ struct Core {
                 count = oh->count;
                 expanded = oh->expanded != 0;
                 if (expanded) {
-                    const uint32_t* oe = T::edge(old_pool, ob, count);
+                    const Child* och = T::child(old_pool, ob);
                     for (int o = 0; o < count; ++o) {
-                        const int32_t oc = T::edge_child(oe[o]);
+                        const int32_t oc = T::edge_child(och[o].edge);
                         if (oc >= 0) {
                             need += static_cast<int>(T::block_words(T::hdr(old_pool, oc)->count));
                             kids += 1;
@@ -973,8 +987,8 @@ struct Core {
                 Hdr* nh = T::hdr(nt.pool, nb);
                 if (!expanded) {
                     // visited but never expanded: no edges yet, nothing to reverse -- chess moves keep their generated order
-                    uint32_t* rows = nt.pool + nb + T::kHdrWords + count;
-                    for (int i = 0; i < 2 * count; ++i) rows[i] = 0u;
+                    Child* nch = T::child(nt.pool, nb);
+                    for (int i = 0; i < count; ++i) nch[i] = Child{0.0f, 0.0f, 0, 0u};
                     if constexpr (kChess) {
                         const uint16_t* om = T::mv16(old_pool, ob, count);
                         uint16_t* nm = T::mv16(nt.pool, nb, count);
@@ -982,38 +996,30 @@ struct Core {
                     }
                     nh->expanded = 0;
                 } else {
-                    const float* oi = T::init(old_pool, ob);
-                    const float* ow = T::w(old_pool, ob, count);
-                    const int32_t* on = T::n(old_pool, ob, count);
-                    const uint32_t* oe = T::edge(old_pool, ob, count);
-                    float* ni = T::init(nt.pool, nb);
-                    float* nw = T::w(nt.pool, nb, count);
-                    int32_t* nn = T::n(nt.pool, nb, count);
-                    uint32_t* ne = T::edge(nt.pool, nb, count);
+                    const Child* och = T::child(old_pool, ob);
+                    Child* nch = T::child(nt.pool, nb);
                     uint32_t next_block = nt.used + static_cast<uint32_t>(off);
                     uint32_t next_q = q_tail + static_cast<uint32_t>(koff);
                     for (int i = 0; i < count; ++i) {  // new insertion order = old iteration order (newest first)
                         const int o = count - 1 - i;
-                        const uint32_t ed = oe[o];
-                        ni[i] = oi[o];
-                        nw[i] = ow[o];
-                        nn[i] = on[o];
+                        Child c = och[o];
                         if constexpr (kChess) T::mv16(nt.pool, nb, count)[i] = T::mv16(old_pool, ob, count)[o];
-                        const int32_t oc = T::edge_child(ed);
+                        const int32_t oc = T::edge_child(c.edge);
                         int32_t nc = -1;
                         if (oc >= 0) {
-                            const Hdr* och = T::hdr(old_pool, oc);
+                            const Hdr* ohc = T::hdr(old_pool, oc);
                             nc = static_cast<int32_t>(next_block);
-                            next_block += T::block_words(och->count);
-                            Hdr* ch = T::hdr(nt.pool, nc);
-                            ch->pos = och->pos;
-                            ch->count = och->count;
-                            ch->expanded = 0;
+                            next_block += T::block_words(ohc->count);
+                            Hdr* chd = T::hdr(nt.pool, nc);
+                            chd->pos = ohc->pos;
+                            chd->count = ohc->count;
+                            chd->expanded = 0;
                             q[-2 * static_cast<int32_t>(next_q + 1u)] = static_cast<uint32_t>(nc);
                             q[-2 * static_cast<int32_t>(next_q + 1u) + 1] = static_cast<uint32_t>(oc);
                             next_q += 1;
                         }
-                        ne[i] = T::pack_edge(nc, T::edge_move(ed));
+                        c.edge = T::pack_edge(nc, T::edge_move(c.edge));
+                        nch[i] = c;
                     }
                     nh->expanded = 1;
                 }

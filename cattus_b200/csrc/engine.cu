@@ -1407,8 +1407,21 @@ void Engine::eval_batch(const uint64_t* planes, const uint8_t* legal, uint32_t n
         stamp("copied out", f.first);
     };
     try {
-        for (uint32_t first = 0; first < n; first += max_batch_) {
-            const uint32_t cn = std::min(max_batch_, n - first);
+        // A call of several device batches ramps in and out with a quarter-size chunk: the GPU starts after a quarter of
+        // the first batch is packed and copied, and the last results to copy back are a quarter batch -- the pipeline's fill
+        // and drain are what an end-to-end call loses against resident inputs.
+        const uint32_t quarter = std::max<uint32_t>(64, max_batch_ / 4);
+        const bool ramp = n > max_batch_ && lanes_.size() >= 2 && max_batch_ >= 256;
+        uint32_t cn = 0;
+        for (uint32_t first = 0; first < n; first += cn) {
+            const uint32_t left = n - first;
+            cn = std::min(max_batch_, left);
+            if (ramp) {
+                if (first == 0)
+                    cn = quarter;
+                else if (left > quarter && left <= max_batch_ + quarter)
+                    cn = left - quarter;  // leaves exactly one quarter chunk for the end
+            }
             if (inflight.size() >= lanes_.size()) drain_one();
             Lane& l = acquire_lane();
             uint32_t total = 0;

@@ -48,7 +48,7 @@ struct EmulBackend {
         const uint32_t maxc = Rules::kChess ? 224u : static_cast<uint32_t>(rules.max_children());
         n_bufs = (depth & 0xFFu) + 1;
         slots.assign(n_slots, ds::SlotState{});
-        pools.assign(static_cast<size_t>(n_slots) * 3 * pool_words, 0xDEADBEEFu);  // stale memory must not matter
+        pools.assign(static_cast<size_t>(n_slots) * 3 * pool_words + 256, 0xDEADBEEFu);  // stale memory must not matter; + slack for select's early child fetch
         const uint32_t path_cap = Rules::kChess ? 256u : maxc + 2u;
         paths.resize(static_cast<size_t>(n_slots) * path_cap);
         noise.assign(static_cast<size_t>(n_slots) * maxc, 0.0f);
