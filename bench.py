@@ -627,7 +627,7 @@ def main():
         sp_blob = export_blob(net.make_state_dict(sp_cfg, 0), sp_cfg.game)
         dg = args.device_games or (4096 if sp_cfg.filters >= 64 else 16384)
         games_total = max(2, (args.selfplay_games or dg) * world // 2 * 2)
-        with CudaNetwork(sp_blob, sp_cfg.game, device=local_rank, batch_size=dg, n_streams=1, precision="bf16") as sp_nw:
+        with CudaNetwork(sp_blob, sp_cfg.game, device=local_rank, batch_size=dg, n_streams=2, precision="bf16") as sp_nw:  # two lanes: two slot populations take waves in turn
             runner = SelfPlayRunner(runner_game(sp_game), {"mcts": mc, "seed": 1, "max_moves": sp_max_moves, "device_games": dg})
             SelfPlayRunner(runner_game(sp_game), {"mcts": dict(mc, sim_num=16), "seed": 1, "max_moves": 2, "device_games": 64}).generate_data(
                 sp_nw, None, 64 * world, first_game=rank, game_stride=world)  # warm-up: the evaluator's launch sequence, the allocator

@@ -50,6 +50,9 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not is_stale():
         return LIB
     cmd = [nvcc_path(), *NVCC_FLAGS, "-o", str(LIB), str(CSRC / "engine.cu"), str(CSRC / "selfplay.cpp"), str(CSRC / "chess_api.cpp")]
+    for knob in ("DS_SELECT_MIN_BLOCKS", "DS_EXPAND_MIN_BLOCKS"):  # occupancy experiments on the device-search kernels
+        if os.environ.get(knob):
+            cmd.insert(1, f"-D{knob}={int(os.environ[knob])}")
     if os.environ.get("CATTUS_B200_TRUNK_TRACE"):  # diagnostic build with clock64 trace points (tools/trace_trunk.py)
         cmd.insert(1, "-DCB2_TRUNK_TRACE")
     if verbose:

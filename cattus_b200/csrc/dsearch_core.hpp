@@ -277,6 +277,7 @@ struct Params {
     uint32_t* error;                // sticky OR of ErrBits
     uint32_t begin_lead;            // 0: begin runs before select in the same wave; 1: overlapped, effective next wave
     uint32_t visit_budget;          // node visits per slot and wave after which select stops starting new simulations
+    uint32_t slot_base;             // the host's number of this population's slot 0 (two populations alternate waves)
 };
 
 template <class Pos>
@@ -433,7 +434,7 @@ struct Core {
         uint8_t* e = p.results + static_cast<unsigned long long>(wave % p.n_result_bufs) * p.result_buf_bytes + static_cast<size_t>(k) * p.result_stride;
         if (ln == 0) {
             ResultHdr* rh = reinterpret_cast<ResultHdr*>(e);
-            rh->slot = si;
+            rh->slot = si + p.slot_base;
             rh->count = static_cast<uint32_t>(count);
         }
         uint32_t* rn = reinterpret_cast<uint32_t*>(e + sizeof(ResultHdr));
@@ -1039,7 +1040,7 @@ struct Core {
         const uint8_t* cb = p.cmds + 16 + static_cast<size_t>(ci) * p.cmd_stride;
         const Cmd cmd = *reinterpret_cast<const Cmd*>(cb);
         const float* cmd_noise = reinterpret_cast<const float*>(cb + sizeof(Cmd));
-        const uint32_t si = cmd.slot;
+        const uint32_t si = cmd.slot - p.slot_base;
         if (si >= p.n_slots) return;
         SlotState& S = p.slots[si];
         int32_t root[2] = {S.root[0], S.root[1]};

@@ -54,27 +54,34 @@ class Driver {
     }
 
     void run() {
+        // Two POPULATIONS of slots (when the backend has two evaluator lanes) take waves in turn, each on its own stream: while
+        // one population's leaves are in the evaluator, the other's select / expand kernels run beside it, and a slot that
+        // finished a search gets its command in the very next wave of its population.
         const uint32_t n = be_.n_slots();
         for (uint32_t s = 0; s < n; ++s) start_next_game(s);
         std::deque<uint32_t> inflight;
-        uint32_t wave = 0;
+        uint32_t wave = 0, next_pop = 0;
         const uint32_t depth = std::max<uint32_t>(1, be_.depth());
+        const uint32_t pops = be_.populations();
         for (;;) {
             bool submitted = false;
             const auto ta = sp::Clock::now();
-            if (active_ > 0) {
+            uint32_t pop = next_pop;
+            if (pops == 2 && active_pop_[pop] == 0 && cmds_[pop].empty()) pop ^= 1u;  // nothing to do there: give the turn away
+            if (active_pop_[pop] > 0 || !cmds_[pop].empty()) {
                 uint8_t* block = be_.cmd_block(wave);
-                const uint32_t n_cmds = static_cast<uint32_t>(cmds_.size() / cmd_stride_);
+                const uint32_t n_cmds = static_cast<uint32_t>(cmds_[pop].size() / cmd_stride_);
                 uint32_t* hdr = reinterpret_cast<uint32_t*>(block);
                 hdr[0] = n_cmds;
                 hdr[1] = wave;
                 hdr[2] = hdr[3] = 0;
-                if (n_cmds) std::memcpy(block + 16, cmds_.data(), cmds_.size());
-                cmds_.clear();
-                be_.submit(wave, n_cmds);
+                if (n_cmds) std::memcpy(block + 16, cmds_[pop].data(), cmds_[pop].size());
+                cmds_[pop].clear();
+                be_.submit(wave, pop, n_cmds);
                 inflight.push_back(wave++);
                 submitted = true;
                 waves_ += 1;
+                next_pop = pops == 2 ? (pop ^ 1u) : 0u;
             }
             const auto tb = sp::Clock::now();
             if (!inflight.empty() && (inflight.size() >= depth || !submitted)) {
@@ -128,6 +135,7 @@ class Driver {
         g.history.push_back(R.initial());
         g.rec.game_idx = g.game_idx;
         active_ += 1;
+        active_pop_[be_.population_of(slot)] += 1;
         begin_move(slot, kCmdNewGame, 0);
     }
 
@@ -147,6 +155,7 @@ class Driver {
         if (st != 0) {
             finish_game(g, st);
             active_ -= 1;
+            active_pop_[be_.population_of(slot)] -= 1;
             start_next_game(slot);
             return;
         }
@@ -166,8 +175,9 @@ class Driver {
             for (uint32_t i = 0; i < noise_n; ++i) nz_[i] = static_cast<float>(noise_[i] / tot);
         }
         g.search_t0 = sp::Clock::now();
-        const size_t at = cmds_.size();
-        cmds_.resize(at + cmd_stride_, 0);
+        std::vector<uint8_t>& cmds = cmds_[be_.population_of(slot)];
+        const size_t at = cmds.size();
+        cmds.resize(at + cmd_stride_, 0);
         Cmd c;
         std::memset(&c, 0, sizeof(c));
         c.slot = slot;
@@ -175,8 +185,8 @@ class Driver {
         c.move = move;
         c.cur = static_cast<uint32_t>(g.cur);
         c.noise_n = noise_n;
-        std::memcpy(cmds_.data() + at, &c, sizeof(c));
-        if (noise_n) std::memcpy(cmds_.data() + at + sizeof(Cmd), nz_.data(), sizeof(float) * noise_n);
+        std::memcpy(cmds.data() + at, &c, sizeof(c));
+        if (noise_n) std::memcpy(cmds.data() + at + sizeof(Cmd), nz_.data(), sizeof(float) * noise_n);
     }
 
     // the rest of calc_moves_probabilities + choose_move_from_probabilities + the game step (mod.rs:364-417,
@@ -260,9 +270,9 @@ class Driver {
     sp::Shared& sh_;
     sp::Params params_[2];
     std::vector<Game> games_;
-    std::vector<uint8_t> cmds_;  // commands for the next wave
+    std::vector<uint8_t> cmds_[2];  // commands for each population's next wave
     uint32_t cmd_stride_ = 0, result_stride_ = 0;
-    uint32_t active_ = 0;
+    uint32_t active_ = 0, active_pop_[2] = {0, 0};
     uint64_t waves_ = 0, searches_ = 0;
     uint32_t w1_ = 0, w2_ = 0, d_ = 0, games_done_ = 0;
     double search_duration_ = 0.0, t_submit_ = 0.0, t_wait_ = 0.0, t_process_ = 0.0;

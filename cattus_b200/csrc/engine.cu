@@ -1660,11 +1660,13 @@ void Engine::resident_download(uint32_t n, float* probs_out, size_t probs_cap, u
     }
 }
 
-Engine::ResidentIo Engine::resident_acquire() {
+Engine::ResidentIo Engine::resident_acquire(bool block) {
     CB2_CUDA(cudaSetDevice(device_));
-    Lane& l = acquire_lane();
-    l.device_out = true;
     ResidentIo io;
+    Lane* lp = block ? &acquire_lane() : try_acquire_lane();
+    if (lp == nullptr) return io;  // lane == -1: every stream is taken
+    Lane& l = *lp;
+    l.device_out = true;
     io.lane = l.index;
     io.d_block = l.d_in.as<uint8_t>();
     io.d_values = l.d_values.as<float>();

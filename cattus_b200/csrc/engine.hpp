@@ -179,7 +179,7 @@ class Engine {
         float* d_probs = nullptr;    // capacity max_batch * moves floats
         uint32_t rec_bytes = 0, plane_words = 0, max_batch = 0, moves = 0, kernels = 0;
     };
-    ResidentIo resident_acquire();
+    ResidentIo resident_acquire(bool block = true);  // block == false: lane == -1 when every stream is taken
     void resident_enqueue(int lane, cudaStream_t stream);  // the max_batch bucket's launch sequence; rows read from the block
     void resident_release(int lane);
     void note_resident(uint64_t batches, uint64_t positions, uint64_t launches, double last_seconds);

@@ -25,8 +25,12 @@ struct EmulBackend {
     std::vector<ds::PathStep> paths;
     std::vector<float> noise;
     std::vector<Pos> hist;
-    std::vector<uint8_t> block[2];
-    std::vector<float> values[2], probs[2];
+    std::vector<uint8_t> block[2], block_b[2];          // _b: the second population's evaluator blocks and caches
+    std::vector<float> values[2], probs[2], values_b[2], probs_b[2];
+    std::vector<uint32_t> cache_meta_b[2];
+    std::vector<uint8_t> cache_entries_b[2];
+    ds::Params<Rules> p2{};
+    uint32_t n_pops = 1, split = 0, total_slots = 0;
     std::vector<uint8_t> cmds, results;
     std::vector<uint32_t> done_per_buf;
     uint32_t done_count = 0, error = 0;
@@ -109,16 +113,50 @@ struct EmulBackend {
         p.done_count = &done_count;
         p.counters = counters;
         p.error = &error;
-        p.begin_lead = (depth >> 8) & 1u;  // test knobs: bit 8 of `depth`; bits 16.. = visit budget (0 = 24)
+        p.begin_lead = (depth >> 8) & 1u;  // test knobs: bit 8 of `depth`: begin overlapped; bit 9: two populations; bits 16.. = visit budget (0 = 24)
         p.visit_budget = (depth >> 16) ? (depth >> 16) : 24u;
+        total_slots = n_slots;
+        split = n_slots;
+        if (((depth >> 9) & 1u) && n_slots >= 2) {
+            // the GPU's arrangement with two evaluator lanes: populations [0, split) and [split, n) take waves in turn, each with
+            // its own evaluator batch and its own cache
+            n_pops = 2;
+            split = (n_slots + 1) / 2;
+            p2 = p;
+            p.n_slots = split;
+            p2.n_slots = n_slots - split;
+            p2.slot_base = split;
+            p2.slots = p.slots + split;
+            p2.pools = p.pools + static_cast<size_t>(split) * 3 * pool_words;
+            p2.paths = p.paths + static_cast<size_t>(split) * path_cap;
+            p2.noise = p.noise + static_cast<size_t>(split) * maxc;
+            p2.hist = p.hist + static_cast<size_t>(split) * hist_cap;
+            for (int e = 0; e < 2; ++e) {
+                block_b[e].assign(block[e].size(), 0);
+                values_b[e].assign(n_slots, 0.0f);
+                probs_b[e].assign(static_cast<size_t>(n_slots) * maxc, 0.0f);
+                p2.eval[e].n_ptr = reinterpret_cast<uint32_t*>(block_b[e].data());
+                p2.eval[e].recs = block_b[e].data() + 16 + 8;
+                p2.eval[e].values = values_b[e].data();
+                p2.eval[e].probs = probs_b[e].data();
+                if (p.cache[e].enabled) {
+                    cache_meta_b[e].assign(cache_meta[e].size(), 0u);
+                    cache_entries_b[e].assign(cache_entries[e].size(), 0xCD);
+                    p2.cache[e].meta = cache_meta_b[e].data();
+                    p2.cache[e].entries = cache_entries_b[e].data();
+                }
+            }
+        }
         done_per_buf.assign(n_bufs, 0);
     }
-    uint32_t n_slots() const { return p.n_slots; }
+    uint32_t n_slots() const { return total_slots; }
+    uint32_t populations() const { return n_pops; }
+    uint32_t population_of(uint32_t slot) const { return slot >= split ? 1u : 0u; }
     uint32_t max_children() const { return p.max_children; }
     uint32_t depth() const { return depth_; }
     uint8_t* cmd_block(uint32_t) { return cmds.data(); }
 
-    void run_eval(int e) {
+    void run_eval(ds::Params<Rules>& p, std::vector<float>* probs, std::vector<float>* values, int e) {
         const uint32_t n = *p.eval[e].n_ptr;
         if (n == 0) return;
         const uint32_t pw = p.eval[e].plane_words, rb = p.eval[e].rec_bytes;
@@ -145,7 +183,10 @@ struct EmulBackend {
         }
     }
 
-    void submit(uint32_t wave, uint32_t n_cmds) {
+    void submit(uint32_t wave, uint32_t pop, uint32_t n_cmds) {
+        ds::Params<Rules>& p = pop ? p2 : this->p;
+        std::vector<float>* probs = pop ? probs_b : this->probs;
+        std::vector<float>* values = pop ? values_b : this->values;
         done_count = 0;
         *p.eval[0].n_ptr = 0;
         *p.eval[1].n_ptr = 0;
@@ -157,7 +198,7 @@ struct EmulBackend {
         for (uint32_t si = 0; si < p.n_slots; ++si) ds::Core<Rules>::select_slot(rules, p, si, wave);
         if (p.begin_lead)
             for (uint32_t ci = 0; ci < n_cmds; ++ci) ds::Core<Rules>::begin_slot(rules, p, ci, wave);
-        for (uint32_t e = 0; e < p.n_evals; ++e) run_eval(static_cast<int>(e));
+        for (uint32_t e = 0; e < p.n_evals; ++e) run_eval(p, probs, values, static_cast<int>(e));
         for (uint32_t si = 0; si < p.n_slots; ++si) ds::Core<Rules>::expand_slot(rules, p, si, wave);
         done_per_buf[wave % n_bufs] = done_count;
     }

@@ -46,7 +46,7 @@ def test_results_do_not_depend_on_slots_or_pipeline_depth():
     cfg = cfg_with(sim_num=30, prior_noise_alpha=0.3, prior_noise_epsilon=0.25, temperature_policy=[[4, 1.0], [9999, 0.0]], seed=8)
     _, ref = host_games("hex5", cfg, cb_for(net, 1), None, 10)
     for n_slots, depth in ((1, 1), (3, 2), (16, 3), (10, 4), (3, 2 | 256), (16, 1 | 256), (4, 2 | (1 << 16)),
-                           (4, 2 | 256 | (1000 << 16))):  # | 256: begin overlapped (a wave later); << 16: node-visit budget per wave (1: one simulation)
+                           (4, 2 | 256 | (1000 << 16)), (5, 2 | 256 | 512), (16, 3 | 512), (2, 2 | 256 | 512)):  # | 512: two populations taking waves in turn  # | 256: begin overlapped (a wave later); << 16: node-visit budget per wave (1: one simulation)
         _, got = emul.run("hex5", cfg, cb_for(net, 1), None, 10, n_slots=n_slots, pool_words=1 << 15, depth=depth)
         same_games(got, ref)
 
@@ -76,6 +76,9 @@ def test_device_side_cache_chess_and_two_models():
     cfg = cfg_with(sim_num=30, temperature_policy=[[9999, 1.0]], seed=3, cache_size=1000)
     _, ref = host_games("hex4", cfg, cb_for(n1, 1), cb_for(n2, 1), 6)
     counters, got = emul.run("hex4", cfg, cb_for(n1, 1), cb_for(n2, 1), 6, n_slots=3, pool_words=1 << 14)
+    same_games(got, ref)
+    assert counters["cache_hits"] > 0
+    counters, got = emul.run("hex4", cfg, cb_for(n1, 1), cb_for(n2, 1), 6, n_slots=4, pool_words=1 << 14, depth=2 | 256 | 512)  # two populations, each its own caches
     same_games(got, ref)
     assert counters["cache_hits"] > 0
 

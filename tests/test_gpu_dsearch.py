@@ -76,6 +76,16 @@ def test_results_do_not_depend_on_device_games_or_waves_in_flight():
         assert r == results[0]
 
 
+def test_two_populations_experiment_knob_same_games(monkeypatch):
+    """CATTUS_B200_DSEARCH_TWO_POPULATIONS: two halves of the slots take waves in turn on two streams (measured: no gain)."""
+    base = dict(sim_num=60, prior_noise_alpha=0.3, prior_noise_epsilon=0.25, temperature_policy=[[6, 1.0], [9999, 0.0]], seed=21, cache_size=20000)
+    with make_network("hex5", batch_size=256, n_streams=2) as nw:
+        _, one = SelfPlayRunner("hex5", cfg_with(device_games=128, **base)).generate_data(nw, None, 160, keep_records=True)
+        monkeypatch.setenv("CATTUS_B200_DSEARCH_TWO_POPULATIONS", "1")
+        _, two = SelfPlayRunner("hex5", cfg_with(device_games=128, **base)).generate_data(nw, None, 160, keep_records=True)
+    assert games_of(two) == games_of(one)
+
+
 def test_device_search_many_games_long_searches():
     """Tree reuse over whole games with hundreds of simulations per move and hundreds of games in flight."""
     base = dict(sim_num=300, prior_noise_alpha=0.3, prior_noise_epsilon=0.25, temperature_policy=[[6, 1.0], [9999, 0.0]], seed=11)

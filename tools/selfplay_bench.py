@@ -40,7 +40,7 @@ def main():
     cfg_net = net.CONFIGS[args.game]
     blob = export_blob(net.make_state_dict(cfg_net, 0), cfg_net.game)
     for dg in [d for d in args.device_games if d > 0]:
-        with CudaNetwork(blob, cfg_net.game, batch_size=max(64, dg), n_streams=1) as nw:
+        with CudaNetwork(blob, cfg_net.game, batch_size=max(64, dg), n_streams=args.streams if args.streams != 4 else 2) as nw:
             cfg = {"mcts": {"sim_num": args.sim_num, "explore_factor": 1.41421, "temperature_policy": [[10, 1.0], [9999, 0.0]],
                             "prior_noise_alpha": 0.03, "prior_noise_epsilon": 0.25, "cache_size": args.cache if args.cache != 1000000 or args.device_cache else 0},
                    "seed": 1, "max_moves": args.max_moves, "device_games": dg, "device_waves_in_flight": args.waves, "device_tree_kwords": args.tree_kwords}
