@@ -205,9 +205,13 @@ Engine::Engine(const cattus_b200_desc& desc, const void* blob_bytes, size_t blob
     CB2_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(kTcStagesDeep)));
     CB2_CUDA(cudaFuncSetAttribute(tc_gemm_dual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(kTcStagesDeep)));
     // whole-trunk kernel: 8x8 boards, 128 filters (flags bit 0 forces the per-layer path, used by the parity tests)
-    fused_trunk_ = !simple_ && precision_ == CATTUS_B200_PRECISION_BF16 && d_.s == 8 && d_.f == 128 && d_.c_in <= 32 && d_.wpp() == 1 &&
-                   (desc.flags & 1u) == 0 && (sm_count_ >= 2) && vhp_ + php_ <= 64;
-    if (fused_trunk_) CB2_CUDA(cudaFuncSetAttribute(trunk_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFtSmemBytes));
+    fused_trunk_ = !simple_ && precision_ == CATTUS_B200_PRECISION_BF16 && d_.s == 8 && (d_.f == 64 || d_.f == 128 || d_.f == 256) && d_.c_in <= 32 &&
+                   d_.wpp() == 1 && (desc.flags & 1u) == 0 && (sm_count_ >= 2) && vhp_ + php_ <= 64;
+    if (fused_trunk_) {
+        if (d_.f == 64) CB2_CUDA(cudaFuncSetAttribute(trunk_fused_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, FtG<64>::kSmemBytes));
+        if (d_.f == 128) CB2_CUDA(cudaFuncSetAttribute(trunk_fused_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, FtG<128>::kSmemBytes));
+        if (d_.f == 256) CB2_CUDA(cudaFuncSetAttribute(trunk_fused_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, FtG<256>::kSmemBytes));
+    }
     // 16-filter nets (every shipped training config): whole trunk + both head convs in one kernel
     small_trunk_ = !simple_ && precision_ == CATTUS_B200_PRECISION_BF16 && d_.f == 16 && d_.c_in <= 32 && d_.s >= 3 && d_.s <= 11 && vhp_ + php_ <= 32 &&
                    (desc.flags & 1u) == 0;
@@ -398,45 +402,53 @@ void Engine::upload_weights(const Blob& blob) {
     for (size_t i = 0; i < blob.block_conv.size(); ++i) conv3(convs_[1 + i], blob.block_conv[i], ca_);
     if (fused_trunk_) {
         // trunk_fused.cuh weight image: for each layer, each 16-channel k-chunk, each CTA rank (= half of the output
-        // channels): [tap 9][k-half 2][oc 64][ic 8] bf16 = one 18432-byte TMA stage.  Stem input channels padded to 32.
+        // channels) one block [tap 9][k-half 2][oc F / 2][ic 8] bf16, streamed as one TMA stage (F <= 128) or three (F = 256:
+        // 3 taps each).  Stem input channels padded to 32.  Last block per rank: the two head convs, 8 k-chunks per stage.
         const uint32_t layers = 1 + static_cast<uint32_t>(blob.block_conv.size());
-        size_t stages = 2 + static_cast<size_t>(layers - 1) * 8 + 1;  // + one stage for the two head convs
-        std::vector<float> img(stages * 2 * (kFtWStage / 2), 0.0f), bias(static_cast<size_t>(layers + 1) * 128, 0.0f);
+        const uint32_t F = d_.f, kcn = F / 16, npc = F / 2;
+        const size_t block_elems = static_cast<size_t>(9) * 2 * npc * 8;                   // FtG<F>::kBlockBytes / 2
+        const size_t stage_elems = static_cast<size_t>(F <= 128 ? 9 : 3) * 2 * npc * 8;   // FtG<F>::kWStage / 2
+        const uint32_t head_stages = kcn > 8 ? kcn / 8 : 1, head_kc = kcn / head_stages;
+        const size_t blocks = 2 + static_cast<size_t>(layers - 1) * kcn + 1;  // + one block for the two head convs
+        std::vector<float> img(blocks * 2 * block_elems, 0.0f), bias(static_cast<size_t>(layers + 1) * F, 0.0f);
         for (uint32_t l = 0; l < layers; ++l) {
             const Blob::Conv& c = l == 0 ? blob.stem : blob.block_conv[l - 1];
-            const uint32_t nkc = l == 0 ? 2 : 8;
-            const size_t base = l == 0 ? 0 : 2 + static_cast<size_t>(l - 1) * 8;
-            for (uint32_t o = 0; o < 128; ++o) bias[l * 128 + o] = D[c.b + o];
+            const uint32_t nkc = l == 0 ? 2 : kcn;
+            const size_t base = l == 0 ? 0 : 2 + static_cast<size_t>(l - 1) * kcn;
+            for (uint32_t o = 0; o < F; ++o) bias[l * F + o] = D[c.b + o];
             for (uint32_t kc = 0; kc < nkc; ++kc)
                 for (uint32_t rk = 0; rk < 2; ++rk) {
-                    float* blk = img.data() + ((base + kc) * 2 + rk) * (kFtWStage / 2);
+                    float* blk = img.data() + ((base + kc) * 2 + rk) * block_elems;
                     for (uint32_t tap = 0; tap < 9; ++tap)
                         for (uint32_t kh = 0; kh < 2; ++kh)
-                            for (uint32_t n = 0; n < 64; ++n)
-                                for (uint32_t e = 0; e < 8; ++e) {
-                                    const uint32_t ic = kc * 16 + kh * 8 + e, oc = rk * 64 + n;
-                                    if (ic < c.ci) blk[((tap * 2 + kh) * 64 + n) * 8 + e] = D[c.w + (static_cast<size_t>(oc) * c.ci + ic) * 9 + tap];
+                            for (uint32_t n = 0; n < npc; ++n)
+                                for (uint32_t e2 = 0; e2 < 8; ++e2) {
+                                    const uint32_t ic = kc * 16 + kh * 8 + e2, oc = rk * npc + n;
+                                    if (ic < c.ci) blk[((tap * 2 + kh) * npc + n) * 8 + e2] = D[c.w + (static_cast<size_t>(oc) * c.ci + ic) * 9 + tap];
                                 }
                 }
         }
         {
-            // head stage: [k-chunk 8][k-half 2][oc (vhp + php) / 2][ic 8] per CTA rank; channel list = value | policy
+            // head stages: [k-chunk][k-half 2][oc (vhp + php) / 2][ic 8] per CTA rank; channel list = value | policy
             const uint32_t nh = vhp_ + php_, half = nh / 2;
-            const size_t base = 2 + static_cast<size_t>(layers - 1) * 8;
+            const size_t base = 2 + static_cast<size_t>(layers - 1) * kcn;
             auto head_w = [&](uint32_t ch, uint32_t ic) -> float {
-                if (ch < vhp_) return ch < d_.vh ? D[blob.vconv.w + static_cast<size_t>(ch) * 128 + ic] : 0.0f;
+                if (ch < vhp_) return ch < d_.vh ? D[blob.vconv.w + static_cast<size_t>(ch) * F + ic] : 0.0f;
                 const uint32_t pc = ch - vhp_;
-                return pc < d_.ph ? D[blob.pconv.w + static_cast<size_t>(pc) * 128 + ic] : 0.0f;
+                return pc < d_.ph ? D[blob.pconv.w + static_cast<size_t>(pc) * F + ic] : 0.0f;
             };
             for (uint32_t rk = 0; rk < 2; ++rk) {
-                float* blk = img.data() + (base * 2 + rk) * (kFtWStage / 2);
-                for (uint32_t kc = 0; kc < 8; ++kc)
+                float* blk = img.data() + (base * 2 + rk) * block_elems;
+                for (uint32_t kc = 0; kc < kcn; ++kc) {
+                    float* st = blk + (kc / head_kc) * stage_elems;
+                    const uint32_t k8 = kc % head_kc;
                     for (uint32_t kh = 0; kh < 2; ++kh)
                         for (uint32_t n = 0; n < half; ++n)
-                            for (uint32_t e = 0; e < 8; ++e) blk[((kc * 2 + kh) * half + n) * 8 + e] = head_w(rk * half + n, kc * 16 + kh * 8 + e);
+                            for (uint32_t e2 = 0; e2 < 8; ++e2) st[((k8 * 2 + kh) * half + n) * 8 + e2] = head_w(rk * half + n, kc * 16 + kh * 8 + e2);
+                }
             }
-            for (uint32_t o = 0; o < d_.vh; ++o) bias[static_cast<size_t>(layers) * 128 + o] = D[blob.vconv.b + o];
-            for (uint32_t o = 0; o < d_.ph; ++o) bias[static_cast<size_t>(layers) * 128 + vhp_ + o] = D[blob.pconv.b + o];
+            for (uint32_t o = 0; o < d_.vh; ++o) bias[static_cast<size_t>(layers) * F + o] = D[blob.vconv.b + o];
+            for (uint32_t o = 0; o < d_.ph; ++o) bias[static_cast<size_t>(layers) * F + vhp_ + o] = D[blob.pconv.b + o];
         }
         upload(fused_w_, to_bf16(img));
         upload(fused_b_, bias);
@@ -898,7 +910,8 @@ void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
         {
             cuuint64_t gdim[2] = {256, w_rows};
             cuuint64_t gstr[1] = {256};
-            cuuint32_t box[2] = {256, static_cast<cuuint32_t>(kFtWRowsPerStage)};
+            const int rows_per_stage = d_.f == 64 ? FtG<64>::kWRowsPerStage : d_.f == 128 ? FtG<128>::kWRowsPerStage : FtG<256>::kWRowsPerStage;
+            cuuint32_t box[2] = {256, static_cast<cuuint32_t>(rows_per_stage)};
             cuuint32_t estr[2] = {1, 1};
             CUresult r = reinterpret_cast<EncodeTiledFn>(encode_tiled_)(&fp.tma_w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, fused_w_.p, gdim, gstr, box, estr,
                                                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -917,13 +930,19 @@ void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
         fp.planes = static_cast<int>(d_.c_in);
         fp.layers = 1 + 2 * static_cast<int>(d_.r);
         // small batches: one tile per CTA (4 boards per pair) while that still fits one wave -- half the MMAs per round
-        fp.tiles = static_cast<int>(ceil_div(bucket, 4)) <= sm / 2 ? 1 : 2;
+        // (256 filters: one tile per CTA always -- two tiles' activations do not fit beside the weight ring)
+        fp.tiles = (static_cast<int>(ceil_div(bucket, 4)) <= sm / 2 || d_.f == 256) ? 1 : 2;
         fp.num_rounds = static_cast<int>(ceil_div(bucket, 4u * static_cast<uint32_t>(fp.tiles)));
         const int pairs = std::min(sm / 2, fp.num_rounds);
         Op op;
         op.stage = 1;
         op.name = "trunk_fused";
-        op.launch = [fp, pairs](cudaStream_t st) { trunk_fused_kernel<<<2 * pairs, kFtThreads, kFtSmemBytes, st>>>(fp); };
+        if (d_.f == 64)
+            op.launch = [fp, pairs](cudaStream_t st) { trunk_fused_kernel<64><<<2 * pairs, kFtThreads, FtG<64>::kSmemBytes, st>>>(fp); };
+        else if (d_.f == 128)
+            op.launch = [fp, pairs](cudaStream_t st) { trunk_fused_kernel<128><<<2 * pairs, kFtThreads, FtG<128>::kSmemBytes, st>>>(fp); };
+        else
+            op.launch = [fp, pairs](cudaStream_t st) { trunk_fused_kernel<256><<<2 * pairs, kFtThreads, FtG<256>::kSmemBytes, st>>>(fp); };
         ops.push_back(op);
     } else if (small) {
         // encode + stem + all residual blocks + both 1x1 head convs in one launch (trunk_small.cuh)

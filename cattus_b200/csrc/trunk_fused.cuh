@@ -37,6 +37,15 @@
 // all 8 k-chunks of the [VH + PH][128] matrix (N = VH + PH <= 64 split across the pair like every other layer), no
 // taps, whose epilogue writes ReLU(bf16) straight into the FC kernels' A operands.  The 67 MB trunk output tensor
 // (and the two launches that re-read it) of the unfused arrangement never exists.
+//
+// Widths (round 2): the kernel is a template over the filter count F in {64, 128, 256} -- the range the reference's chess
+// config recommends (training/config/chess_dev.yaml:30-37).  What changes with F is geometry only (FtG<F> below): F / 16
+// k-chunks per layer, F / 8 chunk planes per activation buffer, F / 2 output channels per CTA of the pair, F TMEM columns
+// per accumulator.  F = 256 needs its activations (2 x 83 KB for ONE 128-row tile per CTA) and a weight ring in 227 KB, so
+// its weight stages hold 3 taps of a k-chunk (12 KB, ring of 4) instead of all 9 (F <= 128: 9 taps, ring of 3), and it
+// always runs one tile per CTA: layer l + 1's MMAs start on chunk 0 while layer l's epilogue is still writing chunk 1.., so
+// the tensor pipe stays fed without a second tile as long as a layer's MMAs outlast its epilogue (they do: 144 MMAs of
+// M256 x N256 x K16 against 16 epilogue chunks).
 #pragma once
 #include "kernels.cuh"
 #include "ptx.cuh"
@@ -49,22 +58,39 @@ constexpr int kFtPlaneCells = 162;                             // (16 + 2) segme
 constexpr int kFtCell0 = 19;                                   // cell(g = 0, x = 0)
 constexpr int kFtLbo = kFtPlaneCells * 16;                     // 2592
 constexpr int kFtSbo = kFtSegCells * 16;                       // 144
-constexpr int kFtBufBytes = 15 * kFtLbo + 181 * 16;            // 16 chunk planes, margins shared: 41776
-constexpr int kFtActBytes = 4 * kFtBufBytes;                   // tile0.P, tile0.Q, tile1.P, tile1.Q
-constexpr int kFtWOff = (kFtActBytes + 127) / 128 * 128;       // 167168
-constexpr int kFtTapBytes = 2 * 64 * 16;                       // one tap of one k-chunk: [2 halves][64 oc][8 ic] bf16
-constexpr int kFtWStage = 9 * kFtTapBytes;                     // 18432
-constexpr int kFtWStages = 3;
-constexpr int kFtBarOff = kFtWOff + kFtWStages * kFtWStage;    // 222464
-constexpr int kFtNumBars = 3 + 3 + 16 + 4;                     // w_full, w_empty, act_full[2][8], acc_full[2][2]
-constexpr int kFtSmemBytes = kFtBarOff + kFtNumBars * 8 + 16 + 128;
-constexpr int kFtWRowsPerStage = kFtWStage / 256;              // weight image is a u8 [rows][256] tensor: 72 rows per stage
+
+// Geometry of the F-filter variant.
+template <int F>
+struct FtG {
+    static_assert(F == 64 || F == 128 || F == 256, "trunk_fused covers 64, 128 and 256 filters");
+    static constexpr int kKc = F / 16;                                  // 16-channel k-chunks per layer
+    static constexpr int kBufBytes = (F / 8 - 1) * kFtLbo + 181 * 16;   // F / 8 chunk planes, margins shared (F = 128: 41776)
+    static constexpr int kTilesMax = F <= 128 ? 2 : 1;                  // 128-row tiles per CTA
+    static constexpr int kActBytes = 2 * kTilesMax * kBufBytes;         // per tile: P and Q
+    static constexpr int kWOff = (kActBytes + 127) / 128 * 128;
+    static constexpr int kNpc = F / 2;                                  // output channels per CTA of the pair
+    static constexpr int kTapBytes = 2 * kNpc * 16;                     // one tap of one k-chunk: [2 halves][kNpc oc][8 ic] bf16
+    static constexpr int kTapsPerStage = F <= 128 ? 9 : 3;
+    static constexpr int kSubStages = 9 / kTapsPerStage;                // weight stages per (layer, k-chunk)
+    static constexpr int kWStage = kTapsPerStage * kTapBytes;           // F = 128: 18432
+    static constexpr int kWStages = F <= 128 ? 3 : 4;                   // ring depth
+    static constexpr int kBlockBytes = 9 * kTapBytes;                   // weight image bytes of one (layer, k-chunk, CTA rank)
+    static constexpr int kHeadStages = kKc > 8 ? kKc / 8 : 1;           // the head convs' [k-chunk][2][nh / 2][8] matrix, 8 k-chunks per stage
+    static constexpr int kHeadKcPerStage = kKc / kHeadStages;
+    static constexpr int kBarOff = kWOff + kWStages * kWStage;
+    static constexpr int kNumBars = 2 * kWStages + kTilesMax * kKc + 2 * kTilesMax;  // w_full, w_empty, act_full[tile][kc], acc_full[tile][2]
+    static constexpr int kSmemBytes = kBarOff + kNumBars * 8 + 16 + 128;
+    static constexpr int kWRowsPerStage = kWStage / 256;                // weight image is a u8 [rows][256] tensor
+    static constexpr int kWRowsPerBlock = kBlockBytes / 256;
+    static_assert(kSmemBytes <= 227 * 1024, "trunk_fused: shared memory");
+    static_assert(kHeadKcPerStage * 64 * 16 <= kWStage, "trunk_fused: head stage");
+};
 
 struct alignas(64) TrunkFusedParams {
     CUtensorMap tma_w;       // weight image, u8 [rows][256], box {256, 72}
     const uint8_t* recs;     // packed records (planes first)
     const uint32_t* n_ptr;   // number of valid positions
-    const float* bias;       // [layers][128] folded-BN bias
+    const float* bias;       // [layers + 1][F] folded-BN bias (last row: the head convs)
     __nv_bfloat16* out_v;    // [boards * 64][vhp]  ReLU(value head conv)
     __nv_bfloat16* out_p;    // [boards * 64][php]  ReLU(policy head conv)
     uint32_t* err;
@@ -76,19 +102,25 @@ struct alignas(64) TrunkFusedParams {
     int vhp, php;    // padded head widths (multiples of 16, vhp + php <= 64)
 };
 
-// first weight stage of layer l (stem has 2 k-chunks, every other layer 8)
-__device__ __forceinline__ int ft_stage_base(int l) { return l == 0 ? 0 : 2 + (l - 1) * 8; }
+// first k-chunk block of layer l in the weight image (the stem has 2 k-chunks, every other layer F / 16)
+template <int F>
+__host__ __device__ __forceinline__ int ft_block_base(int l) {
+    return l == 0 ? 0 : 2 + (l - 1) * FtG<F>::kKc;
+}
 
+template <int F>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1) trunk_fused_kernel(const __grid_constant__ TrunkFusedParams p) {
+    using G = FtG<F>;
+    constexpr int kKc = G::kKc, kWS = G::kWStages;
     extern __shared__ uint8_t ft_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ft_smem_raw) + 127) & ~static_cast<uintptr_t>(127));
     uint8_t* act = smem;
-    uint8_t* wring = smem + kFtWOff;
-    uint64_t* w_full = reinterpret_cast<uint64_t*>(smem + kFtBarOff);
-    uint64_t* w_empty = w_full + 3;
-    uint64_t* act_full = w_empty + 3;   // [tile * 8 + kc]
-    uint64_t* acc_full = act_full + 16;  // [tile * 2 + parity]
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_full + 4);
+    uint8_t* wring = smem + G::kWOff;
+    uint64_t* w_full = reinterpret_cast<uint64_t*>(smem + G::kBarOff);
+    uint64_t* w_empty = w_full + kWS;
+    uint64_t* act_full = w_empty + kWS;                     // [tile * kKc + kc]
+    uint64_t* acc_full = act_full + G::kTilesMax * kKc;     // [tile * 2 + parity]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_full + 2 * G::kTilesMax);
 
     const uint32_t warp = threadIdx.x >> 5;
     const uint32_t lane = threadIdx.x & 31;
@@ -101,15 +133,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1) trunk
     const int rounds = min(p.num_rounds, (n_valid + 4 * p.tiles - 1) / (4 * p.tiles));
 
     // ---- one-time setup: zero the activation planes (halo cells stay zero for the whole kernel), barriers, TMEM
-    for (int i = threadIdx.x; i < kFtActBytes / 16; i += kFtThreads) reinterpret_cast<uint4*>(act)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < G::kActBytes / 16; i += kFtThreads) reinterpret_cast<uint4*>(act)[i] = make_uint4(0, 0, 0, 0);
     if (warp == 0 && lane == 0) ptx::prefetch_tensormap(&p.tma_w);
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < 3; ++s) {
+        for (int s = 0; s < kWS; ++s) {
             ptx::mbar_init(&w_full[s], 1);
             ptx::mbar_init(&w_empty[s], 1);
         }
-        for (int i = 0; i < 16; ++i) ptx::mbar_init(&act_full[i], 8);  // 4 epilogue warps x 2 CTAs
-        for (int i = 0; i < 4; ++i) ptx::mbar_init(&acc_full[i], 1);
+        for (int i = 0; i < G::kTilesMax * kKc; ++i) ptx::mbar_init(&act_full[i], 8);  // 4 epilogue warps x 2 CTAs
+        for (int i = 0; i < 2 * G::kTilesMax; ++i) ptx::mbar_init(&acc_full[i], 1);
         ptx::fence_barrier_init();
     }
     if (warp == 2) {
@@ -127,21 +159,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1) trunk
         // ================================================================== weight producer (both CTAs)
         if (lane == 0) {
             uint32_t it = 0;
+            auto load_stage = [&](int row) {
+                const uint32_t slot = it % kWS, ph = (it / kWS) & 1;
+                ptx::mbar_wait(&w_empty[slot], ph ^ 1, p.err, 0x1100 + slot);
+                if (rank == 0) ptx::mbar_arrive_expect_tx(&w_full[slot], 2 * G::kWStage);
+                ptx::tma_load_2d_pair(wring + slot * G::kWStage, &p.tma_w, ptx::mapa(ptx::smem_u32(&w_full[slot]), 0), 0, row);
+                ++it;
+            };
             for (int rd = pair; rd < rounds; rd += num_pairs) {
-                for (int l = 0; l <= p.layers; ++l) {             // l == layers: the head convs, one stage for all k-chunks
-                    const int nkc = l == 0 ? 2 : (l == p.layers ? 1 : 8);
-                    for (int kc = 0; kc < nkc; ++kc, ++it) {
-                        const uint32_t slot = it % 3, ph = (it / 3) & 1;
-                        ptx::mbar_wait(&w_empty[slot], ph ^ 1, p.err, 0x1100 + slot);
-                        if (rank == 0) ptx::mbar_arrive_expect_tx(&w_full[slot], 2 * kFtWStage);
-                        const int block = (ft_stage_base(l) + kc) * 2 + static_cast<int>(rank);
-                        ptx::tma_load_2d_pair(wring + slot * kFtWStage, &p.tma_w, ptx::mapa(ptx::smem_u32(&w_full[slot]), 0), 0,
-                                              block * kFtWRowsPerStage);
+                for (int l = 0; l < p.layers; ++l) {
+                    const int nkc = l == 0 ? 2 : kKc;
+                    for (int kc = 0; kc < nkc; ++kc) {
+                        const int block = (ft_block_base<F>(l) + kc) * 2 + static_cast<int>(rank);
+                        for (int sub = 0; sub < G::kSubStages; ++sub) load_stage(block * G::kWRowsPerBlock + sub * G::kWRowsPerStage);
                     }
                 }
+                // the head convs: kHeadStages stages inside one image block per CTA rank
+                const int hblock = ft_block_base<F>(p.layers) * 2 + static_cast<int>(rank);
+                for (int hs = 0; hs < G::kHeadStages; ++hs) load_stage(hblock * G::kWRowsPerBlock + hs * G::kWRowsPerStage);
             }
             // tail: do not leave while the leader's commits may still arrive on our barriers
-            for (uint32_t j = it; j < it + 3; ++j) ptx::mbar_wait(&w_empty[j % 3], ((j / 3) & 1) ^ 1, p.err, 0x1200 + (j % 3));
+            for (uint32_t j = it; j < it + kWS; ++j) ptx::mbar_wait(&w_empty[j % kWS], ((j / kWS) & 1) ^ 1, p.err, 0x1200 + (j % kWS));
         }
         __syncwarp();
     } else if (warp == 1) {
@@ -151,9 +189,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1) trunk
         // version that ran the loop inside `if (lane == 0)` spent ~25 SASS instructions per MMA converting registers
         // to uniform registers and was issue-bound at half the tensor-pipe rate (profiles/r01c).
         if (rank == 0) {
-            const uint32_t idesc = ptx::umma_idesc_bf16(256, 128);
+            const uint32_t idesc = ptx::umma_idesc_bf16(256, F);
             const uint64_t a_hi64 = ptx::umma_desc_none_hi(kFtLbo, kFtSbo);
-            const uint64_t b_hi64 = ptx::umma_desc_none_hi(64 * 16, 128);
+            const uint64_t b_hi64 = ptx::umma_desc_none_hi(G::kNpc * 16, 128);
             const uint32_t a_hi = static_cast<uint32_t>(a_hi64 >> 32), a_lo_fixed = static_cast<uint32_t>(a_hi64);
             const uint32_t b_hi = static_cast<uint32_t>(b_hi64 >> 32), b_lo_fixed = static_cast<uint32_t>(b_hi64);
             const uint32_t act_addr = ptx::smem_u32(act);
@@ -167,54 +205,59 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1) trunk
             const uint32_t bh_hi = static_cast<uint32_t>(bh_hi64 >> 32), bh_lo_fixed = static_cast<uint32_t>(bh_hi64);
             for (int rd = pair; rd < rounds; rd += num_pairs) {
                 for (int l = 0; l < p.layers; ++l) {
-                    const int nkc = l == 0 ? 2 : 8;
+                    const int nkc = l == 0 ? 2 : kKc;
                     const int in_buf = (l & 1) ? 1 : 0;  // stem and conv2 read P (0), conv1 reads Q (1)
-                    for (int kc = 0; kc < nkc; ++kc, ++it) {
-                        const uint32_t slot = it % 3, ph = (it / 3) & 1;
-                        ptx::mbar_wait(&w_full[slot], ph, p.err, 0x2100 + slot);
-                        const uint32_t b_lo0 = b_lo_fixed | ((w_addr + slot * kFtWStage) >> 4);
+                    for (int kc = 0; kc < nkc; ++kc) {
 #pragma unroll
-                        for (int t = 0; t < 2; ++t) {
-                            if (t >= p.tiles) break;
-                            const int bi = t * 8 + kc;
-                            ptx::mbar_wait(&act_full[bi], (act_par >> bi) & 1u, p.err, 0x2200 + bi);
-                            act_par ^= 1u << bi;
-                            ptx::tc_fence_after();
-                            const uint32_t a_lo0 = a_lo_fixed | ((act_addr + (t * 2 + in_buf) * kFtBufBytes + (2 * kc) * kFtLbo + kFtCell0 * 16) >> 4);
-                            const uint32_t d = tmem_base + static_cast<uint32_t>((t * 2 + (l & 1)) * 128);
-                            if (leader_lane) {
+                        for (int sub = 0; sub < G::kSubStages; ++sub, ++it) {
+                            const uint32_t slot = it % kWS, ph = (it / kWS) & 1;
+                            ptx::mbar_wait(&w_full[slot], ph, p.err, 0x2100 + slot);
+                            const uint32_t b_lo0 = b_lo_fixed | ((w_addr + slot * G::kWStage) >> 4);
 #pragma unroll
-                                for (int tap = 0; tap < 9; ++tap) {
-                                    const int shift16 = 18 * (tap / 3 - 1) + (tap % 3 - 1);  // in 16-byte units
-                                    ptx::umma_bf16_ss_pair_lohi(d, a_lo0 + shift16, a_hi, b_lo0 + tap * (kFtTapBytes / 16), b_hi, idesc,
-                                                                (kc | tap) != 0);
+                            for (int t = 0; t < G::kTilesMax; ++t) {
+                                if (t >= p.tiles) break;
+                                const int bi = t * kKc + kc;
+                                if (sub == 0) {
+                                    ptx::mbar_wait(&act_full[bi], (act_par >> bi) & 1u, p.err, 0x2200 + bi);
+                                    act_par ^= 1u << bi;
                                 }
-                                if (kc == nkc - 1) ptx::umma_commit_pair_multicast(&acc_full[t * 2 + (l & 1)], 3);
+                                ptx::tc_fence_after();
+                                const uint32_t a_lo0 = a_lo_fixed | ((act_addr + (t * 2 + in_buf) * G::kBufBytes + (2 * kc) * kFtLbo + kFtCell0 * 16) >> 4);
+                                const uint32_t d = tmem_base + static_cast<uint32_t>((t * 2 + (l & 1)) * F);
+                                if (leader_lane) {
+#pragma unroll
+                                    for (int ts = 0; ts < G::kTapsPerStage; ++ts) {
+                                        const int tap = sub * G::kTapsPerStage + ts;
+                                        const int shift16 = 18 * (tap / 3 - 1) + (tap % 3 - 1);  // in 16-byte units
+                                        ptx::umma_bf16_ss_pair_lohi(d, a_lo0 + shift16, a_hi, b_lo0 + ts * (G::kTapBytes / 16), b_hi, idesc, (kc | tap) != 0);
+                                    }
+                                    if (kc == nkc - 1 && sub == G::kSubStages - 1) ptx::umma_commit_pair_multicast(&acc_full[t * 2 + (l & 1)], 3);
+                                }
                             }
+                            if (leader_lane) ptx::umma_commit_pair_multicast(&w_empty[slot], 3);
+                            __syncwarp();
                         }
-                        if (leader_lane) ptx::umma_commit_pair_multicast(&w_empty[slot], 3);
-                        __syncwarp();
                     }
                 }
-                // ---- head convs: 8 k-chunks, no taps, N = vhp + php, input = Q (the last conv2 wrote it), accumulator parity 1
-                {
-                    const uint32_t slot = it % 3, ph = (it / 3) & 1;
-                    ++it;
+                // ---- head convs: kKc k-chunks, no taps, N = vhp + php, input = Q (the last conv2 wrote it), accumulator parity 1
+                for (int hs = 0; hs < G::kHeadStages; ++hs, ++it) {
+                    const uint32_t slot = it % kWS, ph = (it / kWS) & 1;
                     ptx::mbar_wait(&w_full[slot], ph, p.err, 0x2100 + slot);
-                    const uint32_t b_lo0 = bh_lo_fixed | ((w_addr + slot * kFtWStage) >> 4);
+                    const uint32_t b_lo0 = bh_lo_fixed | ((w_addr + slot * G::kWStage) >> 4);
 #pragma unroll
-                    for (int t = 0; t < 2; ++t) {
+                    for (int t = 0; t < G::kTilesMax; ++t) {
                         if (t >= p.tiles) break;
-                        const uint32_t d = tmem_base + static_cast<uint32_t>((t * 2 + 1) * 128);
-                        for (int kc = 0; kc < 8; ++kc) {
-                            const int bi = t * 8 + kc;
+                        const uint32_t d = tmem_base + static_cast<uint32_t>((t * 2 + 1) * F);
+                        for (int k8 = 0; k8 < G::kHeadKcPerStage; ++k8) {
+                            const int kc = hs * G::kHeadKcPerStage + k8;
+                            const int bi = t * kKc + kc;
                             ptx::mbar_wait(&act_full[bi], (act_par >> bi) & 1u, p.err, 0x2300 + bi);
                             act_par ^= 1u << bi;
                             ptx::tc_fence_after();
-                            const uint32_t a_lo = a_lo_fixed | ((act_addr + (t * 2 + 1) * kFtBufBytes + (2 * kc) * kFtLbo + kFtCell0 * 16) >> 4);
-                            if (leader_lane) ptx::umma_bf16_ss_pair_lohi(d, a_lo, a_hi, b_lo0 + kc * (nh / 2) * 2, bh_hi, idesc_head, kc != 0);
+                            const uint32_t a_lo = a_lo_fixed | ((act_addr + (t * 2 + 1) * G::kBufBytes + (2 * kc) * kFtLbo + kFtCell0 * 16) >> 4);
+                            if (leader_lane) ptx::umma_bf16_ss_pair_lohi(d, a_lo, a_hi, b_lo0 + k8 * (nh / 2) * 2, bh_hi, idesc_head, kc != 0);
                         }
-                        if (leader_lane) ptx::umma_commit_pair_multicast(&acc_full[t * 2 + 1], 3);
+                        if (leader_lane && hs == G::kHeadStages - 1) ptx::umma_commit_pair_multicast(&acc_full[t * 2 + 1], 3);
                     }
                     if (leader_lane) ptx::umma_commit_pair_multicast(&w_empty[slot], 3);
                     __syncwarp();
@@ -231,10 +274,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1) trunk
         const int j = g & 1, y = g >> 1;
         const int cell = y * 8 + x;
         const int pcell = kFtCell0 + g * kFtSegCells + x;
-        uint8_t* bufP = act + (t * 2 + 0) * kFtBufBytes + pcell * 16;
-        uint8_t* bufQ = act + (t * 2 + 1) * kFtBufBytes + pcell * 16;
-        const uint32_t leader_act = ptx::mapa(ptx::smem_u32(&act_full[t * 8]), 0);
-        const uint32_t tmem_row = tmem_base + ((q * 32u) << 16) + static_cast<uint32_t>(t * 2 * 128);
+        uint8_t* bufP = act + (t * 2 + 0) * G::kBufBytes + pcell * 16;
+        uint8_t* bufQ = act + (t * 2 + 1) * G::kBufBytes + pcell * 16;
+        const uint32_t leader_act = ptx::mapa(ptx::smem_u32(&act_full[t * kKc]), 0);
+        const uint32_t tmem_row = tmem_base + ((q * 32u) << 16) + static_cast<uint32_t>(t * 2 * F);
         uint32_t acc_par = 0;
         for (int rd = pair; rd < rounds; rd += num_pairs) {
             const int board = ((rd * p.tiles + t) * 2 + static_cast<int>(rank)) * 2 + j;  // tile-major: a 1-tile round is boards 4 rd .. 4 rd + 3
@@ -266,7 +309,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1) trunk
                 const int par = l & 1;
                 const bool has_resid = l >= 2 && par == 0;  // conv2 of a block: + block input (Q), result back into Q
                 uint8_t* outb = par ? bufP : bufQ;          // stem -> Q, conv1 -> P, conv2 -> Q
-                const float4* bias4 = reinterpret_cast<const float4*>(p.bias + l * 128);
+                const float4* bias4 = reinterpret_cast<const float4*>(p.bias + l * F);
                 float4 bn[4];  // bias of the chunk about to be processed, fetched one chunk ahead
 #pragma unroll
                 for (int i = 0; i < 4; ++i) bn[i] = __ldg(bias4 + i);
@@ -274,13 +317,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1) trunk
                 acc_par ^= 1u << par;
                 ptx::tc_fence_after();
 #pragma unroll 1
-                for (int kc = 0; kc < 8; ++kc) {
+                for (int kc = 0; kc < kKc; ++kc) {
                     uint32_t raw[16];
-                    ptx::tmem_ld_x16_issue(tmem_row + static_cast<uint32_t>(par * 128 + kc * 16), raw);
+                    ptx::tmem_ld_x16_issue(tmem_row + static_cast<uint32_t>(par * F + kc * 16), raw);
                     float4 bc[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) bc[i] = bn[i];
-                    if (kc < 7) {
+                    if (kc < kKc - 1) {
 #pragma unroll
                         for (int i = 0; i < 4; ++i) bn[i] = __ldg(bias4 + (kc + 1) * 4 + i);
                     }
@@ -322,7 +365,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1) trunk
             }
             // ---- both 1x1 head convolutions: accumulator (t, parity 1), columns [0, vhp) value, [vhp, vhp + php) policy
             {
-                const float4* hb4 = reinterpret_cast<const float4*>(p.bias + p.layers * 128);
+                const float4* hb4 = reinterpret_cast<const float4*>(p.bias + p.layers * F);
                 ptx::mbar_wait(&acc_full[t * 2 + 1], (acc_par >> 1) & 1u, p.err, 0x3200 + t);
                 acc_par ^= 1u << 1;
                 ptx::tc_fence_after();
@@ -330,7 +373,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1) trunk
                 const int nh = p.vhp + p.php;
                 for (int cb = 0; cb < nh; cb += 16) {
                     uint32_t raw[16];
-                    ptx::tmem_ld_x16_issue(tmem_row + static_cast<uint32_t>(128 + cb), raw);
+                    ptx::tmem_ld_x16_issue(tmem_row + static_cast<uint32_t>(F + cb), raw);
                     float4 bc[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) bc[i] = __ldg(hb4 + cb / 4 + i);

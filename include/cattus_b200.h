@@ -108,7 +108,7 @@ typedef struct cattus_b200_info {
 /* cattus_b200_info.trunk_path.  The whole-trunk kernels cover fixed shapes; every other net takes the per-layer kernel,
  * which is correct for any ConvNetV1 within the blob's limits but re-reads its activations through L2 (about 2.5x slower). */
 #define CATTUS_B200_TRUNK_PER_LAYER 0 /* one tcgen05 implicit-GEMM launch per conv layer (tc_gemm.cuh); any shape */
-#define CATTUS_B200_TRUNK_FUSED 1     /* trunk_fused.cuh: 8x8 boards, 128 filters, <= 32 planes, VH + PH <= 64 */
+#define CATTUS_B200_TRUNK_FUSED 1     /* trunk_fused.cuh: 8x8 boards, 64 / 128 / 256 filters, <= 32 planes, VH + PH <= 64 */
 #define CATTUS_B200_TRUNK_SMALL 2     /* trunk_small.cuh: 16 filters, boards 3..11, <= 32 planes, VH + PH <= 32 */
 #define CATTUS_B200_TRUNK_FP32 3      /* precision FP32_CHECK: CUDA-core fp32 loops (parity only) */
 #define CATTUS_B200_TRUNK_DENSE 4     /* SimpleTwoHeadedModel (net_utils.py:92-121): no convolutions, three dense layers */

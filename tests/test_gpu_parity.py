@@ -92,8 +92,8 @@ def test_run_dense_bf16_vs_reference_golden(name):
 
 def test_info_says_which_trunk_path_a_handle_got():
     """cattus_b200_info.trunk_path: the whole-trunk kernels cover fixed shapes; everything else takes the per-layer kernel."""
-    for name, want in (("chess10x128", "fused"), ("chess_2x128", "fused"), ("hex5", "small"), ("chess_dev", "small"), ("chess_4x64", "per-layer"),
-                       ("chess_4x256", "per-layer"), ("hex7_4x32", "per-layer"), ("hex11_2x128", "per-layer"), ("hex5_simple", "dense")):
+    for name, want in (("chess10x128", "fused"), ("chess_2x128", "fused"), ("hex5", "small"), ("chess_dev", "small"), ("chess_4x64", "fused"),
+                       ("chess_4x256", "fused"), ("hex7_4x32", "per-layer"), ("hex11_2x128", "per-layer"), ("hex5_simple", "dense")):
         with make_network(name, batch_size=16, n_streams=1) as nw:
             assert nw.trunk_path == want, (name, nw.trunk_path)
     with make_network("hex5", precision="fp32-check", batch_size=16, n_streams=1) as nw:
@@ -222,7 +222,9 @@ def test_non_finite_and_degenerate_policy_rows():
 
 
 # ----------------------------------------------------------------------------------------------- fused trunk
-@pytest.mark.parametrize("name,n,batch", [("chess_0x128", 37, 64), ("chess_1x128", 37, 64), ("chess_2x128", 150, 64), ("chess10x128", 700, 512)])
+@pytest.mark.parametrize("name,n,batch", [("chess_0x128", 37, 64), ("chess_1x128", 37, 64), ("chess_2x128", 150, 64), ("chess10x128", 700, 512),
+                                          # the other widths of the template (F = 64: two tiles per CTA at the larger batch; F = 256: 3-tap weight stages)
+                                          ("chess_4x64", 37, 64), ("chess_4x64", 1500, 2048), ("chess_4x256", 37, 64), ("chess_4x256", 900, 1024)])
 def test_fused_trunk_matches_per_layer_path_and_oracle(name, n, batch):
     """The whole-trunk kernel (trunk_fused.cuh: encode + stem + residual blocks, activations resident in shared memory,
     CTA pairs) against the per-layer tcgen05 GEMM path on the same handle parameters, and both against the oracle.
