@@ -613,7 +613,8 @@ struct Core {
             }
         }
 #if DS_DEVICE
-        __threadfence();
+        // entry, then tag, then one fence, then the unlock: the next holder of the lock (the only reader inside this kernel)
+        // fences after acquiring it; select reads in a later kernel
         __syncwarp();
         if (ln == 0) {
             if (way != 0xFFFFFFFFu) meta[2 + way] = tag;
