@@ -741,7 +741,8 @@ def main():
     traffic = None
     try:  # DRAM bytes of the same kernel from the committed `ncu --set full` capture (per launch, same workload and batch)
         tj = json.loads((ROOT / "profiles" / "traffic.json").read_text())
-        te = tj.get("trunk_fused_kernel" if fused else "trunk_small_kernel" if small else "")
+        kname = "trunk_fused_kernel" if fused else "trunk_small_kernel" if small else ""
+        te = tj.get(f"{kname}@{args.workload}") or tj.get(kname)
         if te and te["workload"] == args.workload and te["positions_per_launch"] == batch:
             traffic = {"bytes": te["dram_bytes_read"] + te["dram_bytes_write"], "dram_bytes_read": te["dram_bytes_read"],
                        "dram_bytes_write": te["dram_bytes_write"], "source": te["source"]}
@@ -751,7 +752,7 @@ def main():
     split_sum, all_graph = float(split.sum()), float(np.mean(ms_all))
     rel = abs(split_sum - all_graph) / all_graph
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
-                "traffic": traffic, "kernel": ("trunk_fused_kernel (stem + residual blocks, one launch)" if fused else
+                "traffic": traffic, "kernel": (f"trunk_fused_kernel<{cfg.filters}> (encode + stem + residual blocks + head convs, one launch)" if fused else
                            "trunk_small_kernel (encode + stem + residual blocks + head convs, one launch)" if small else
                            "tc_gemm_kernel x (1 + 2R) conv layers (stem + residual blocks)"),
                 "trunk_path": trunk_path,
