@@ -97,55 +97,81 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks + throttle reasons DURING the timed regions (B200_PROFILING.md recipe).  One sampler runs for the
+    whole process (nvidia-smi takes up to a second to deliver its first line, longer on an 8-GPU box); every measurement
+    brackets itself with time.monotonic() and reads the samples that fell inside its window."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, device: int):
         self.device = device
         self.proc = None
-        self.lines = []
+        self.samples = []  # (monotonic time, sm MHz, max MHz, W, [reasons])
+        self.t_start = None
 
-    def start(self):
+    def start(self, wait_s: float = 6.0):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25", "-i", str(self.device)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.device)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            t0 = time.monotonic()
+            while not self.samples and time.monotonic() - t0 < wait_s:
+                time.sleep(0.02)
         except Exception:
             self.proc = None
+        return self
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
-
-    def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons, power = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
             f = [x.strip() for x in line.split(",")]
             if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-                power.append(float(f[3]))
+                self.samples.append((time.monotonic(), float(f[1]), float(f[2]), float(f[3]),
+                                     [n for n, v in zip(self.NAMES, f[4:8]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for nme, val in zip(names, f[4:8]):
-                if val.lower().startswith("active"):
-                    reasons.add(nme)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+    def begin(self):
+        self.t_start = time.monotonic()
+
+    def window(self, t0: float = None, t1: float = None) -> dict:
+        """Median SM clock, max power and the union of the throttle reasons over [t0, t1] (default: since begin())."""
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t0 = self.t_start if t0 is None else t0
+        t1 = time.monotonic() if t1 is None else t1
+        inside = [s for s in self.samples if t0 <= s[0] <= t1 + 0.03]
+        nearest = False
+        if not inside and self.samples:  # a region shorter than the sampling period: the sample nearest to it
+            mid = 0.5 * (t0 + t1)
+            inside = [min(self.samples, key=lambda s: abs(s[0] - mid))]
+            nearest = True
+        if not inside:
+            return {"sm_mhz": None, "sm_max_mhz": None, "power_w_max": None, "samples": 0, "reasons": []}
+        reasons = sorted({r for s in inside for r in s[4]})
+        out = {"sm_mhz": statistics.median(s[1] for s in inside), "sm_max_mhz": max(s[2] for s in inside),
+               "power_w_max": max(s[3] for s in inside), "samples": len(inside), "reasons": reasons}
+        if nearest:
+            out["note"] = "region shorter than the sampling period: nearest sample"
+        return out
+
+    def stop(self) -> dict:
+        out = self.window()
+        self.close()
+        return out
+
+    def close(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            self.proc = None
 
 
 def make_inputs(cfg, n, seed):
@@ -466,22 +492,21 @@ def main():
     # ---------------- device-resident throughput (value) and the trunk roofline
     nw.resident_upload(words[:batch], None if bitmaps is None else bitmaps[:batch])
     nw.time_stage(4, batch, args.warmup * per_step)
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank).start()  # runs for the whole process; every measurement reads its own window
     launches0 = nw.metrics()["model.kernel_launches"]
     barrier()
-    sampler.start()
+    sampler.begin()
     ms_all = nw.time_stage(4, batch, args.steps * per_step)
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.window()
     t_value = max_over_ranks(float(ms_all.sum()) * 1e-3)
 
     def timed_with_clocks(fn):
         """One clock record per measurement: the power-cap state drifts between loops."""
-        smp = ClockSampler(local_rank)
-        smp.start()
+        t0 = time.monotonic()
         out = fn()
-        c = smp.stop()
-        return out, {"sm_mhz": c.get("sm_mhz"), "power_w_max": c.get("power_w_max"), "reasons": c.get("reasons")}
+        c = sampler.window(t0, time.monotonic())
+        return out, {"sm_mhz": c.get("sm_mhz"), "power_w_max": c.get("power_w_max"), "samples": c.get("samples"), "reasons": c.get("reasons")}
 
     stage_iters = max(8, args.steps)
     # the stages of ONE pass (no L2 flush between them, as inside the graph): they must add up to the graph
@@ -511,15 +536,14 @@ def main():
     for _ in range(args.warmup):
         nw.eval_batch(words, bitmaps)
     barrier()
-    e2e_sampler = ClockSampler(local_rank)
-    e2e_sampler.start()
+    t_e2e0 = time.monotonic()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         probs, offsets, values = nw.eval_batch(words, bitmaps)
     torch.cuda.synchronize(local_rank)
     t_e2e_local = time.perf_counter() - t0
     barrier()
-    clocks_e2e = e2e_sampler.stop()
+    clocks_e2e = sampler.window(t_e2e0, time.monotonic())
     t_e2e = max_over_ranks(t_e2e_local)
     launches = nw.metrics()["model.kernel_launches"] - launches0
     # per position: 8-byte prefix (probability offset, #legal) + packed planes (+ the legal bitmap padded to 8 B for chess)
@@ -564,12 +588,16 @@ def main():
     # epilogue), so the standalone kernels of the unfused comparison path (flags bit 0) are timed here as evidence.
     hbm_kernels = []
     if rank == 0 and world == 1 and not args.no_other_workloads:
-        with CudaNetwork(export_blob(sd, cfg.game), cfg.game, device=local_rank, batch_size=batch, n_streams=1, precision="bf16", fused_trunk=False) as unf:
-            unf.resident_upload(words[:batch], None if bitmaps is None else bitmaps[:batch])
+        # at a size where the launch latency does not dominate (round 1 timed 4096 positions: 21 us of which ~5 us are launch)
+        hb = min(65536, 16 * batch)
+        hwords = np.concatenate([words] * (hb // len(words) + 1))[:hb]
+        hbitmaps = None if bitmaps is None else np.concatenate([bitmaps] * (hb // len(bitmaps) + 1))[:hb]
+        with CudaNetwork(export_blob(sd, cfg.game), cfg.game, device=local_rank, batch_size=hb, n_streams=1, precision="bf16", fused_trunk=False) as unf:
+            unf.resident_upload(hwords, hbitmaps)
             for st in (0, 3):
-                unf.time_stage(st, batch, 3)
-            t_enc = float(np.mean(unf.time_stage(0, batch, 10))) * 1e-3
-            t_tail = float(np.mean(unf.time_stage(3, batch, 10))) * 1e-3
+                unf.time_stage(st, hb, 3)
+            t_enc = float(np.mean(unf.time_stage(0, hb, 10))) * 1e-3
+            t_tail = float(np.mean(unf.time_stage(3, hb, 10))) * 1e-3
         s2 = cfg.board_size ** 2
         wpp = (s2 + 63) // 64
         enc_alg = cfg.planes * wpp * 8 + cfg.planes * s2 * 2           # packed planes in + unpadded bf16 activations out
@@ -578,9 +606,10 @@ def main():
         tail_alg = 2 * 4 * cfg.moves + (cfg.moves + 7) // 8 + 512       # logits read (twice counted in SURVEY 8d) + mask + value hidden row
         for name_k, t_k, alg, act in (("encode_nhwc_bf16_kernel", t_enc, enc_alg, enc_act),
                                       ("value_tail_kernel + policy_tail_kernel", t_tail, tail_alg, 4 * cfg.moves + (cfg.moves + 7) // 8 + 512 + 4 * legal_mean)):
-            hbm_kernels.append({"kernel": name_k, "bound": "hbm", "ms": t_k * 1e3, "positions_per_launch": batch, "algorithmic_bytes_per_position": alg,
-                                "actual_bytes_per_position": act, "achieved": batch * alg / t_k / 1e9, "achieved_actual": batch * act / t_k / 1e9,
-                                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": batch * alg / t_k / 1e9 / peaks["hbm_gbs"],
+            hbm_kernels.append({"kernel": name_k, "bound": "hbm", "ms": t_k * 1e3, "positions_per_launch": hb, "algorithmic_bytes_per_position": alg,
+                                "actual_bytes_per_position": act, "achieved": hb * alg / t_k / 1e9, "achieved_actual": hb * act / t_k / 1e9,
+                                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hb * alg / t_k / 1e9 / peaks["hbm_gbs"],
+                                "frac_actual": hb * act / t_k / 1e9 / peaks["hbm_gbs"],
                                 "note": "unfused comparison path (flags bit 0); fused away on the production path"})
 
     # ---------------- the other single-GPU configuration of BASELINE.json (configs[1], hex5) in the same line, briefly
@@ -633,7 +662,9 @@ def main():
                 sp_nw, None, 64 * world, first_game=rank, game_stride=world)  # warm-up: the evaluator's launch sequence, the allocator
             l0 = sp_nw.metrics()["model.kernel_launches"]
             barrier()
+            t_sp0 = time.monotonic()
             summary, _ = runner.generate_data(sp_nw, None, games_total, first_game=rank, game_stride=world)
+            sp_clocks = sampler.window(t_sp0, time.monotonic())
             barrier()
             sp_launches = sp_nw.metrics()["model.kernel_launches"] - l0
         m = summary["metrics"]
@@ -642,7 +673,7 @@ def main():
         selfplay = selfplay_summary_to_dict(sp_game, mc, summary, games_total, 1, dg, max_moves=sp_max_moves, extra={
             "value": sims_all / secs, "n_gpus": world, "host_cores": cores, "gpu_launches": int(sp_launches),
             "arrangement": "device-resident search: trees in HBM, one warp per game, one host thread per GPU acting once per move",
-            "device_games": dg, "waves": m["model.activation_count"], "ms_per_wave": 1e3 * m["selfplay.seconds"] / max(1, m["model.activation_count"]),
+            "device_games": dg, "clocks": sp_clocks, "waves": m["model.activation_count"], "ms_per_wave": 1e3 * m["selfplay.seconds"] / max(1, m["model.activation_count"]),
             "note": "rank 0's counters shown; value = simulations of all ranks / max seconds (the whole call: allocation, all games to their end "
                     "incl. the tail where finished games leave slots empty); games partitioned by index across GPUs, no collective"})
         del selfplay["threads"], selfplay["games_per_thread"], selfplay["eval_wait_frac"], selfplay["cache_hit_rate"]
@@ -807,6 +838,7 @@ def main():
             "selfplay_others": selfplay_legs[1:],
         }
         print(json.dumps(line), flush=True)
+    sampler.close()
     rep.close()
 
 
