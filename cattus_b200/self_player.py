@@ -71,6 +71,14 @@ def main(argv=None) -> int:
     game, family = game_of_blob(args.model1_path)
     if game_of_blob(args.model2_path)[0] != game:
         raise SystemExit("model1 and model2 are for different games")
+    # Big jobs run the DEVICE-RESIDENT search (trees in HBM, one warp per game): sims/s then no longer
+    # depends on the host cores.  "device_games" in the config file decides; without it, jobs of >= 2048 games take it on
+    # their own (same games either way).  Small jobs keep their trees on the host, where speculative rows hide the latency.
+    with open(args.model1_path, "rb") as f:
+        filters = struct.unpack("<16I", f.read(64))[6]
+    if "device_games" not in cfg and args.games_num >= 2048:
+        cfg["device_games"] = min(args.games_num, 4096 if filters >= 64 else 16384)
+    device_games = int(cfg.get("device_games", 0))
     cfg.setdefault("games_per_thread", 64)
     # A trainer-sized job (self_play.games_num 100, threads 8) keeps only a dozen leaves in flight per worker, far below the
     # ~256 positions a device batch can hold at no extra latency: let likely next leaves ride along into the cache (same games,
@@ -79,7 +87,7 @@ def main(argv=None) -> int:
     if (cfg.get("mcts") or {}).get("cache_size"):
         cfg.setdefault("speculate", min(31, 192 // slots) if slots <= 96 else 0)
     cfg.setdefault("groups_per_thread", 2)  # a worker simulates one half of its games while the other half's leaves are on the GPU
-    max_batch = max(int(cfg["model"].get("batch_size", 64)), min(4096, int(cfg["games_per_thread"])), 256 if cfg.get("speculate") else 1)
+    max_batch = max(int(cfg["model"].get("batch_size", 64)), min(4096, int(cfg["games_per_thread"])), 256 if cfg.get("speculate") else 1, device_games)
     kw = dict(device=device, batch_size=max_batch, n_streams=int(inference.get("streams", 4)), precision=inference.get("precision", "bf16"))
     if args.summary_file is not None and args.summary_file.exists():
         raise SystemExit(f"{args.summary_file} exists")  # File::create_new (self_play_cmd.rs:150)

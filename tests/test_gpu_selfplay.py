@@ -114,6 +114,17 @@ def test_self_player_cli_is_a_drop_in_for_the_trainer(tmp_path):
     files = sorted(out.rglob("*.traindata"))
     assert len(files) == s["metrics"]["selfplay.searches"] and files[0].name == "00000000_000.traindata"
     assert all(f.stat().st_size == 6 * 8 + 16 * 4 + 1 for f in files)
+    # the same job with "device_games" in the config file: trees in HBM, the very same files
+    cfg["device_games"] = 4
+    (tmp_path / "config2.json").write_text(json.dumps(cfg))
+    out2 = tmp_path / "games" / "run1"
+    rc = self_player.main([f"--model1-path={model}", f"--model2-path={model}", "--games-num=6", f"--out-dir1={out2}", f"--out-dir2={out2}",
+                           f"--summary-file={tmp_path / 'summary2.json'}", f"--config-file={tmp_path / 'config2.json'}"])
+    assert rc == 0
+    files2 = sorted(out2.rglob("*.traindata"))
+    assert [f.name for f in files2] == [f.name for f in files] and all(a.read_bytes() == b.read_bytes() for a, b in zip(files, files2))
+    s2 = json.loads((tmp_path / "summary2.json").read_text())
+    assert (s2["player1_wins"], s2["player2_wins"], s2["draws"]) == (s["player1_wins"], s["player2_wins"], s["draws"])
 
 
 def test_gpu_selfplay_groups_with_batches_in_flight_same_games():
