@@ -51,6 +51,19 @@ def test_device_side_cache_same_games_fewer_rows(name, game, kw):
     assert m1["selfplay.evaluations"] + m1["cache.hits"] == m0["selfplay.evaluations"]
 
 
+def test_cache_on_and_off_same_games_at_scale():
+    """Thousands of concurrent games hammer the HBM cache's buckets (concurrent inserts take the bucket lock; probes run in
+    another kernel): with and without the cache, and from run to run, every game must be the same game."""
+    base = dict(sim_num=100, prior_noise_alpha=0.3, prior_noise_epsilon=0.25, temperature_policy=[[6, 1.0], [9999, 0.0]], seed=31)
+    with make_network("hex5", batch_size=4096, n_streams=2) as nw:
+        s0, plain = SelfPlayRunner("hex5", cfg_with(device_games=4096, **base)).generate_data(nw, None, 4096, keep_records=True)
+        s1, cached = SelfPlayRunner("hex5", cfg_with(device_games=4096, cache_size=4096, **base)).generate_data(nw, None, 4096, keep_records=True)
+        s2, again = SelfPlayRunner("hex5", cfg_with(device_games=2048, cache_size=200000, **base)).generate_data(nw, None, 4096, keep_records=True)
+    key = lambda recs: [(r.game_idx, r.moves, r.winner) for r in recs]  # noqa: E731
+    assert key(cached) == key(plain) and key(again) == key(plain)
+    assert s1["metrics"]["cache.hits"] > 0 and s1["metrics"]["selfplay.simulations"] == s0["metrics"]["selfplay.simulations"]
+
+
 def test_device_games_equal_the_oracle_directly():
     from tests.test_gpu_selfplay import gpu_net_fn
 
