@@ -213,6 +213,7 @@ class DsCudaBackend {
                 p.result_buf_bytes = result_buf_bytes_;
                 p.done_count = static_cast<uint32_t*>(P.d_status);
                 p.error = static_cast<uint32_t*>(P.d_status) + 1;
+                p.max_used = static_cast<uint32_t*>(P.d_status) + 2;
                 p.counters = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(P.d_status) + 16);
                 // begin (per-move commands: tree reuse copies subtrees) runs on a side branch of the wave graph, beside select /
                 // evaluator / expand; its slots take part from the population's next wave on
@@ -274,11 +275,15 @@ class DsCudaBackend {
         for (int i = 0; i < 4; ++i) out[i] = 0;
         for (uint32_t k = 0; k < n_pops_; ++k) {
             unsigned long long c[4];
+            uint32_t hw = 0;
             CB2_CUDA(cudaStreamSynchronize(pop_[k].stream));
             CB2_CUDA(cudaMemcpy(c, static_cast<uint8_t*>(pop_[k].d_status) + 16, sizeof(c), cudaMemcpyDeviceToHost));
+            CB2_CUDA(cudaMemcpy(&hw, static_cast<uint8_t*>(pop_[k].d_status) + 8, sizeof(hw), cudaMemcpyDeviceToHost));
             for (int i = 0; i < 4; ++i) out[i] += c[i];
+            max_used_ = std::max(max_used_, hw);
         }
     }
+    uint32_t max_used() const { return max_used_; }
     uint64_t waves() const { return waves_; }
     uint32_t kernels_per_wave() const { return kernels_per_wave_; }
 
@@ -367,6 +372,7 @@ class DsCudaBackend {
     std::vector<cudaEvent_t> events_;
     std::vector<uint32_t> wave_pop_;
     uint64_t waves_ = 0;
+    uint32_t max_used_ = 0;
     double setup_seconds_ = 0.0;
 };
 
@@ -386,6 +392,9 @@ static void dsearch_run_rules(const Rules& rules, const void* blob, size_t blob_
     drv.run();
     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     const uint64_t waves = be.waves();
+    if (std::getenv("CATTUS_B200_DSEARCH_PROFILE"))
+        std::fprintf(stderr, "device search: fullest tree buffer used %u of %u words (%.0f %%)\n", be.max_used(), be.pool_words(),
+                     100.0 * be.max_used() / std::max(1u, be.pool_words()));
     e1->note_resident(waves, sh.evaluations, waves * be.kernels_per_wave(), waves ? secs / static_cast<double>(waves) : 0.0);
 }
 

@@ -275,6 +275,7 @@ struct Params {
     uint32_t* done_count;           // results posted in this wave (zeroed per wave)
     unsigned long long* counters;  // [0] simulations [1] evaluations [2] terminal leaves [3] cache hits
     uint32_t* error;                // sticky OR of ErrBits
+    uint32_t* max_used;             // high-water mark of the words in use in any tree buffer (how close the pools came to full)
     uint32_t begin_lead;            // 0: begin runs before select in the same wave; 1: overlapped, effective next wave
     uint32_t visit_budget;          // node visits per slot and wave after which select stops starting new simulations
     uint32_t slot_base;             // the host's number of this population's slot 0 (two populations alternate waves)
@@ -817,6 +818,10 @@ struct Core {
             S.phase = phase;
             S.sims_left = sims_left;
             S.used[cur & 1u] = t.used;
+            if (t.used > S.pad0) {  // this slot's own high-water mark keeps the atomic off the common path
+                S.pad0 = t.used;
+                atomic_max_u32(p.max_used, t.used);
+            }
             S.leaf = leaf;
             S.row = row;
             S.path_len = path_len;

@@ -33,7 +33,7 @@ struct EmulBackend {
     uint32_t n_pops = 1, split = 0, total_slots = 0;
     std::vector<uint8_t> cmds, results;
     std::vector<uint32_t> done_per_buf;
-    uint32_t done_count = 0, error = 0;
+    uint32_t done_count = 0, error = 0, max_used = 0;
     unsigned long long counters[4] = {0, 0, 0, 0};
     uint32_t n_bufs;
     bool chess;
@@ -113,6 +113,7 @@ struct EmulBackend {
         p.done_count = &done_count;
         p.counters = counters;
         p.error = &error;
+        p.max_used = &max_used;
         p.begin_lead = (depth >> 8) & 1u;  // test knobs: bit 8 of `depth`: begin overlapped; bit 9: two populations; bits 16.. = visit budget (0 = 24)
         p.visit_budget = (depth >> 16) ? (depth >> 16) : 24u;
         total_slots = n_slots;

@@ -138,6 +138,18 @@ def test_device_chess_games_equal_host_driver_games(name, kw):
     assert s_dev["metrics"]["selfplay.simulations"] == s_host["metrics"]["selfplay.simulations"]
 
 
+def test_device_chess_whole_games_many_slots():
+    """64 chess games played to their end (mate, stalemate, fifty moves or threefold repetition) with the cache on: tree reuse,
+    repetition detection inside the search and the 128-deep history ring over hundreds of plies."""
+    base = dict(sim_num=32, prior_noise_alpha=0.3, prior_noise_epsilon=0.25, temperature_policy=[[30, 1.0], [9999, 0.0]], seed=5, max_moves=0)
+    with make_network("chess_dev", batch_size=64) as nw:
+        s_host, host = SelfPlayRunner("chess", cfg_with(cache_size=200000, threads=4, games_per_thread=16, **base)).generate_data(nw, None, 64, keep_records=True)
+        s_dev, dev = SelfPlayRunner("chess", cfg_with(device_games=64, cache_size=100000, **base)).generate_data(nw, None, 64, keep_records=True)
+    assert games_of(dev) == games_of(host)
+    assert max(len(r.moves) for r in dev) > 100
+    assert s_dev["metrics"]["selfplay.terminal_leaves"] == s_host["metrics"]["selfplay.terminal_leaves"]
+
+
 def test_device_games_beyond_max_batch_is_an_error():
     from cattus_b200.selfplay import SelfPlayError
 
