@@ -508,7 +508,7 @@ def main():
         c = sampler.window(t0, time.monotonic())
         return out, {"sm_mhz": c.get("sm_mhz"), "power_w_max": c.get("power_w_max"), "samples": c.get("samples"), "reasons": c.get("reasons")}
 
-    stage_iters = max(8, args.steps)
+    stage_iters = max(40, 2 * args.steps)  # tens of milliseconds per stage measurement: a stable mean and a few clock samples per window
     # the stages of ONE pass (no L2 flush between them, as inside the graph): they must add up to the graph
     nw.time_stage(5, batch, 3)
     ms_split, clocks_split = timed_with_clocks(lambda: nw.time_stage(5, batch, stage_iters))
@@ -516,7 +516,7 @@ def main():
     trunk_alone = {}
     for nb in sorted({b_ for b_ in (1024, 2048, 4096, batch) if b_ <= batch}):
         nw.resident_upload(words[:nb], None if bitmaps is None else bitmaps[:nb])
-        nw.time_stage(1, nb, 3)
+        nw.time_stage(1, nb, 8)
         ms_nb, c_nb = timed_with_clocks(lambda nb=nb: nw.time_stage(1, nb, stage_iters))
         trunk_alone[nb] = (float(np.mean(ms_nb)), c_nb)
     nw.resident_upload(words[:batch], None if bitmaps is None else bitmaps[:batch])
