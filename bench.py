@@ -97,74 +97,119 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons DURING the timed regions (B200_PROFILING.md recipe).  One sampler runs for the
-    whole process (nvidia-smi takes up to a second to deliver its first line, longer on an 8-GPU box); every measurement
-    brackets itself with time.monotonic() and reads the samples that fell inside its window."""
+    """SM clock, power and throttle reasons DURING the timed regions (B200_PROFILING.md recipe: the fields of its nvidia-smi
+    line).  Read through NVML in this process (what nvidia-smi itself calls; no start-up latency, which on an 8-GPU box was
+    longer than the timed region) and ONLY while a measurement window is open: polling the driver all the time was measured
+    to slow small kernels down (batch-1 graph 0.124 -> 0.148 ms with a 20 ms nvidia-smi loop running throughout).  Falls
+    back to an nvidia-smi child process if NVML cannot be loaded."""
 
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, device: int):
         self.device = device
-        self.proc = None
         self.samples = []  # (monotonic time, sm MHz, max MHz, W, [reasons])
-        self.t_start = None
+        self.active = False
+        self.stopping = False
+        self.t_open = 0.0
+        self.nvml = None
+        self.proc = None
+        self.thread = None
 
-    def start(self, wait_s: float = 6.0):
+    def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.device)],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            index = int(visible.split(",")[self.device]) if visible and all(v.strip().isdigit() for v in visible.split(",")) else self.device
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
             self.thread.start()
-            t0 = time.monotonic()
-            while not self.samples and time.monotonic() - t0 < wait_s:
-                time.sleep(0.02)
         except Exception:
-            self.proc = None
+            self.nvml = None
+            try:  # the recipe's own command, sampled for the whole run at its 200 ms period
+                self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.device)],
+                                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self.thread = threading.Thread(target=self._read_smi, daemon=True)
+                self.thread.start()
+                t0 = time.monotonic()
+                while not self.samples and time.monotonic() - t0 < 6.0:
+                    time.sleep(0.02)
+            except Exception:
+                self.proc = None
         return self
 
-    def _read(self):
+    def _sample_nvml(self):
+        n = self.nvml
+        try:
+            sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+            power = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+            try:
+                mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+            except Exception:
+                mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+            self.samples.append((time.monotonic(), sm, self.max_mhz, power, [k for k, bit in self.REASONS.items() if mask & bit]))
+        except Exception:
+            pass
+
+    def _poll_nvml(self):
+        while not self.stopping:
+            if self.active:
+                self._sample_nvml()
+                # dense at the start of a window (short kernels loops), sparse in seconds-long legs
+                time.sleep(0.01 if time.monotonic() - self.t_open < 0.5 else 0.2)
+            else:
+                time.sleep(0.002)
+
+    def _read_smi(self):
+        names = list(self.REASONS)
         for line in self.proc.stdout:
             f = [x.strip() for x in line.split(",")]
             if len(f) < 8:
                 continue
             try:
                 self.samples.append((time.monotonic(), float(f[1]), float(f[2]), float(f[3]),
-                                     [n for n, v in zip(self.NAMES, f[4:8]) if v.lower().startswith("active")]))
+                                     [n for n, v in zip(names, f[4:8]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
 
     def begin(self):
-        self.t_start = time.monotonic()
+        """Opens a measurement window (NVML: sampling starts now)."""
+        self.t_open = time.monotonic()
+        self.active = True
+        return self.t_open
 
-    def window(self, t0: float = None, t1: float = None) -> dict:
-        """Median SM clock, max power and the union of the throttle reasons over [t0, t1] (default: since begin())."""
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        t0 = self.t_start if t0 is None else t0
-        t1 = time.monotonic() if t1 is None else t1
+    def end(self, t0: float = None) -> dict:
+        """Closes the window opened at t0 (default: the last begin()) and summarises its samples: median SM clock, max power,
+        union of the throttle reasons."""
+        t1 = time.monotonic()
+        if self.nvml is not None and self.active:
+            self._sample_nvml()  # at least one sample inside even the shortest window
+        self.active = False
+        t0 = self.t_open if t0 is None else t0
+        if self.nvml is None and self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi / NVML unavailable"]}
         inside = [s for s in self.samples if t0 <= s[0] <= t1 + 0.03]
-        nearest = False
-        if not inside and self.samples:  # a region shorter than the sampling period: the sample nearest to it
+        note = None
+        if not inside and self.samples:  # nvidia-smi fallback and a region shorter than its period
             mid = 0.5 * (t0 + t1)
             inside = [min(self.samples, key=lambda s: abs(s[0] - mid))]
-            nearest = True
+            note = "region shorter than the sampling period: nearest sample"
         if not inside:
             return {"sm_mhz": None, "sm_max_mhz": None, "power_w_max": None, "samples": 0, "reasons": []}
-        reasons = sorted({r for s in inside for r in s[4]})
         out = {"sm_mhz": statistics.median(s[1] for s in inside), "sm_max_mhz": max(s[2] for s in inside),
-               "power_w_max": max(s[3] for s in inside), "samples": len(inside), "reasons": reasons}
-        if nearest:
-            out["note"] = "region shorter than the sampling period: nearest sample"
-        return out
-
-    def stop(self) -> dict:
-        out = self.window()
-        self.close()
+               "power_w_max": max(s[3] for s in inside), "samples": len(inside), "reasons": sorted({r for s in inside for r in s[4]}),
+               "source": "NVML" if self.nvml is not None else "nvidia-smi -lms 200"}
+        if note:
+            out["note"] = note
         return out
 
     def close(self):
+        self.stopping = True
         if self.proc is not None:
             self.proc.terminate()
             try:
@@ -498,14 +543,14 @@ def main():
     sampler.begin()
     ms_all = nw.time_stage(4, batch, args.steps * per_step)
     barrier()
-    clocks = sampler.window()
+    clocks = sampler.end()
     t_value = max_over_ranks(float(ms_all.sum()) * 1e-3)
 
     def timed_with_clocks(fn):
         """One clock record per measurement: the power-cap state drifts between loops."""
-        t0 = time.monotonic()
+        t0 = sampler.begin()
         out = fn()
-        c = sampler.window(t0, time.monotonic())
+        c = sampler.end(t0)
         return out, {"sm_mhz": c.get("sm_mhz"), "power_w_max": c.get("power_w_max"), "samples": c.get("samples"), "reasons": c.get("reasons")}
 
     stage_iters = max(40, 2 * args.steps)  # tens of milliseconds per stage measurement: a stable mean and a few clock samples per window
@@ -536,14 +581,14 @@ def main():
     for _ in range(args.warmup):
         nw.eval_batch(words, bitmaps)
     barrier()
-    t_e2e0 = time.monotonic()
+    t_e2e0 = sampler.begin()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         probs, offsets, values = nw.eval_batch(words, bitmaps)
     torch.cuda.synchronize(local_rank)
     t_e2e_local = time.perf_counter() - t0
     barrier()
-    clocks_e2e = sampler.window(t_e2e0, time.monotonic())
+    clocks_e2e = sampler.end(t_e2e0)
     t_e2e = max_over_ranks(t_e2e_local)
     launches = nw.metrics()["model.kernel_launches"] - launches0
     # per position: 8-byte prefix (probability offset, #legal) + packed planes (+ the legal bitmap padded to 8 B for chess)
@@ -662,9 +707,9 @@ def main():
                 sp_nw, None, 64 * world, first_game=rank, game_stride=world)  # warm-up: the evaluator's launch sequence, the allocator
             l0 = sp_nw.metrics()["model.kernel_launches"]
             barrier()
-            t_sp0 = time.monotonic()
+            t_sp0 = sampler.begin()
             summary, _ = runner.generate_data(sp_nw, None, games_total, first_game=rank, game_stride=world)
-            sp_clocks = sampler.window(t_sp0, time.monotonic())
+            sp_clocks = sampler.end(t_sp0)
             barrier()
             sp_launches = sp_nw.metrics()["model.kernel_launches"] - l0
         m = summary["metrics"]
