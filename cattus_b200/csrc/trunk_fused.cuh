@@ -265,9 +265,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1) trunk
             }
         }
         __syncwarp();
-    } else if (warp >= 4 && static_cast<int>(warp - 4) >> 2 < p.tiles) {
+    } else if (warp >= 4) {
         // ================================================================== encode + epilogue (4 warps per tile)
-        const int t = static_cast<int>(warp - 4) >> 2;
+        // With ONE tile per CTA (small batches; F = 256 always) the second set of four warps would idle: it takes the odd
+        // 16-channel chunks of tile 0 instead, so a layer's epilogue -- what the next layer's MMAs wait for -- takes half the
+        // time.  Every chunk is still written and signalled by exactly four warps per CTA (one per TMEM lane quarter).
+        const int wset = static_cast<int>(warp - 4) >> 2;
+        const bool split = p.tiles == 1;
+        const int t = split ? 0 : wset;
+        const int kc0 = split ? wset : 0, kcs = split ? 2 : 1;
         const uint32_t q = warp & 3;  // TMEM lane quarter this warp may access
         const int r = static_cast<int>(q * 32 + lane);
         const int g = r >> 3, x = r & 7;
@@ -283,7 +289,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1) trunk
             const int board = ((rd * p.tiles + t) * 2 + static_cast<int>(rank)) * 2 + j;  // tile-major: a 1-tile round is boards 4 rd .. 4 rd + 3
             const bool valid = board < n_valid;
             // ---- planes_to_tensor for my cell: channels 0..31 of the stem input (planes >= C_in are zero)
-            {
+            if (!split || wset == 0) {
                 uint32_t w[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) w[i] = 0;
@@ -312,20 +318,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1) trunk
                 const float4* bias4 = reinterpret_cast<const float4*>(p.bias + l * F);
                 float4 bn[4];  // bias of the chunk about to be processed, fetched one chunk ahead
 #pragma unroll
-                for (int i = 0; i < 4; ++i) bn[i] = __ldg(bias4 + i);
+                for (int i = 0; i < 4; ++i) bn[i] = __ldg(bias4 + kc0 * 4 + i);
                 ptx::mbar_wait(&acc_full[t * 2 + par], (acc_par >> par) & 1u, p.err, 0x3100 + t * 2 + par);
                 acc_par ^= 1u << par;
                 ptx::tc_fence_after();
 #pragma unroll 1
-                for (int kc = 0; kc < kKc; ++kc) {
+                for (int kc = kc0; kc < kKc; kc += kcs) {
                     uint32_t raw[16];
                     ptx::tmem_ld_x16_issue(tmem_row + static_cast<uint32_t>(par * F + kc * 16), raw);
                     float4 bc[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) bc[i] = bn[i];
-                    if (kc < kKc - 1) {
+                    if (kc + kcs < kKc) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) bn[i] = __ldg(bias4 + (kc + 1) * 4 + i);
+                        for (int i = 0; i < 4; ++i) bn[i] = __ldg(bias4 + (kc + kcs) * 4 + i);
                     }
                     ptx::tmem_ld_wait(raw);
                     float v[16];
@@ -371,7 +377,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1) trunk
                 ptx::tc_fence_after();
                 const size_t row = static_cast<size_t>(board) * 64 + cell;
                 const int nh = p.vhp + p.php;
-                for (int cb = 0; cb < nh; cb += 16) {
+                for (int cb = 16 * kc0; cb < nh; cb += 16 * kcs) {
                     uint32_t raw[16];
                     ptx::tmem_ld_x16_issue(tmem_row + static_cast<uint32_t>(F + cb), raw);
                     float4 bc[4];
@@ -395,6 +401,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1) trunk
                     }
                 }
                 ptx::tc_fence_before();
+                // one tile, two warp sets: the next round's encode (set 0) lets the stem MMAs start, which in turn lets conv1
+                // overwrite the parity-1 accumulator -- not before BOTH sets have read this round's head results out of it
+                if (split) asm volatile("bar.sync 1, 256;" ::: "memory");
             }
         }
     }
