@@ -74,11 +74,17 @@ struct FtG {
     static constexpr int kSubStages = 9 / kTapsPerStage;                // weight stages per (layer, k-chunk)
     static constexpr int kWStage = kTapsPerStage * kTapBytes;           // F = 128: 18432
     static constexpr int kWStages = F <= 128 ? 3 : 4;                   // ring depth
+    // One tile per CTA (small batches) leaves the second tile's two activation buffers unused: they become extra ring slots.
+    // A lone CTA pair pulls its weights from L2 with ~1 us per TMA round trip; three stages in flight deliver one stage per
+    // ~0.33 us, about what its 9 MMAs take (0.29 us), so every hiccup shows -- a deeper ring keeps the tensor pipe fed.
+    static constexpr int kExtraOff = (2 * kBufBytes + 127) / 128 * 128;
+    static constexpr int kExtraStages = kTilesMax == 2 ? (kWOff - kExtraOff) / kWStage : 0;
+    static constexpr int kWStagesMax = kWStages + kExtraStages;
     static constexpr int kBlockBytes = 9 * kTapBytes;                   // weight image bytes of one (layer, k-chunk, CTA rank)
     static constexpr int kHeadStages = kKc > 8 ? kKc / 8 : 1;           // the head convs' [k-chunk][2][nh / 2][8] matrix, 8 k-chunks per stage
     static constexpr int kHeadKcPerStage = kKc / kHeadStages;
     static constexpr int kBarOff = kWOff + kWStages * kWStage;
-    static constexpr int kNumBars = 2 * kWStages + kTilesMax * kKc + 2 * kTilesMax;  // w_full, w_empty, act_full[tile][kc], acc_full[tile][2]
+    static constexpr int kNumBars = 2 * kWStagesMax + kTilesMax * kKc + 2 * kTilesMax;  // w_full, w_empty, act_full[tile][kc], acc_full[tile][2]
     static constexpr int kSmemBytes = kBarOff + kNumBars * 8 + 16 + 128;
     static constexpr int kWRowsPerStage = kWStage / 256;                // weight image is a u8 [rows][256] tensor
     static constexpr int kWRowsPerBlock = kBlockBytes / 256;
@@ -111,14 +117,14 @@ __host__ __device__ __forceinline__ int ft_block_base(int l) {
 template <int F>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1) trunk_fused_kernel(const __grid_constant__ TrunkFusedParams p) {
     using G = FtG<F>;
-    constexpr int kKc = G::kKc, kWS = G::kWStages;
+    constexpr int kKc = G::kKc;
+    const uint32_t kWS = p.tiles == 1 ? G::kWStagesMax : G::kWStages;  // ring depth in use (uniform over the cluster)
     extern __shared__ uint8_t ft_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ft_smem_raw) + 127) & ~static_cast<uintptr_t>(127));
     uint8_t* act = smem;
-    uint8_t* wring = smem + G::kWOff;
     uint64_t* w_full = reinterpret_cast<uint64_t*>(smem + G::kBarOff);
-    uint64_t* w_empty = w_full + kWS;
-    uint64_t* act_full = w_empty + kWS;                     // [tile * kKc + kc]
+    uint64_t* w_empty = w_full + G::kWStagesMax;
+    uint64_t* act_full = w_empty + G::kWStagesMax;          // [tile * kKc + kc]
     uint64_t* acc_full = act_full + G::kTilesMax * kKc;     // [tile * 2 + parity]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_full + 2 * G::kTilesMax);
 
@@ -136,7 +142,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1) trunk
     for (int i = threadIdx.x; i < G::kActBytes / 16; i += kFtThreads) reinterpret_cast<uint4*>(act)[i] = make_uint4(0, 0, 0, 0);
     if (warp == 0 && lane == 0) ptx::prefetch_tensormap(&p.tma_w);
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < kWS; ++s) {
+        for (int s = 0; s < G::kWStagesMax; ++s) {
             ptx::mbar_init(&w_full[s], 1);
             ptx::mbar_init(&w_empty[s], 1);
         }
@@ -154,6 +160,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1) trunk
     ptx::cluster_sync();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    // byte offset (from `smem`) of ring slot i: the ring proper, then the idle tile's activation buffers
+    auto slot_off = [](uint32_t i) -> uint32_t {
+        return i < static_cast<uint32_t>(G::kWStages) ? static_cast<uint32_t>(G::kWOff) + i * G::kWStage
+                                                      : static_cast<uint32_t>(G::kExtraOff) + (i - G::kWStages) * G::kWStage;
+    };
 
     if (warp == 0) {
         // ================================================================== weight producer (both CTAs)
@@ -163,7 +174,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1) trunk
                 const uint32_t slot = it % kWS, ph = (it / kWS) & 1;
                 ptx::mbar_wait(&w_empty[slot], ph ^ 1, p.err, 0x1100 + slot);
                 if (rank == 0) ptx::mbar_arrive_expect_tx(&w_full[slot], 2 * G::kWStage);
-                ptx::tma_load_2d_pair(wring + slot * G::kWStage, &p.tma_w, ptx::mapa(ptx::smem_u32(&w_full[slot]), 0), 0, row);
+                ptx::tma_load_2d_pair(smem + slot_off(slot), &p.tma_w, ptx::mapa(ptx::smem_u32(&w_full[slot]), 0), 0, row);
                 ++it;
             };
             for (int rd = pair; rd < rounds; rd += num_pairs) {
@@ -195,7 +206,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1) trunk
             const uint32_t a_hi = static_cast<uint32_t>(a_hi64 >> 32), a_lo_fixed = static_cast<uint32_t>(a_hi64);
             const uint32_t b_hi = static_cast<uint32_t>(b_hi64 >> 32), b_lo_fixed = static_cast<uint32_t>(b_hi64);
             const uint32_t act_addr = ptx::smem_u32(act);
-            const uint32_t w_addr = ptx::smem_u32(wring);
+            const uint32_t smem_addr = ptx::smem_u32(smem);
             const bool leader_lane = ptx::elect_one();
             uint32_t act_par = 0;
             uint32_t it = 0;
@@ -212,7 +223,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1) trunk
                         for (int sub = 0; sub < G::kSubStages; ++sub, ++it) {
                             const uint32_t slot = it % kWS, ph = (it / kWS) & 1;
                             ptx::mbar_wait(&w_full[slot], ph, p.err, 0x2100 + slot);
-                            const uint32_t b_lo0 = b_lo_fixed | ((w_addr + slot * G::kWStage) >> 4);
+                            const uint32_t b_lo0 = b_lo_fixed | ((smem_addr + slot_off(slot)) >> 4);
 #pragma unroll
                             for (int t = 0; t < G::kTilesMax; ++t) {
                                 if (t >= p.tiles) break;
@@ -243,7 +254,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1) trunk
                 for (int hs = 0; hs < G::kHeadStages; ++hs, ++it) {
                     const uint32_t slot = it % kWS, ph = (it / kWS) & 1;
                     ptx::mbar_wait(&w_full[slot], ph, p.err, 0x2100 + slot);
-                    const uint32_t b_lo0 = bh_lo_fixed | ((w_addr + slot * G::kWStage) >> 4);
+                    const uint32_t b_lo0 = bh_lo_fixed | ((smem_addr + slot_off(slot)) >> 4);
 #pragma unroll
                     for (int t = 0; t < G::kTilesMax; ++t) {
                         if (t >= p.tiles) break;
