@@ -1743,8 +1743,9 @@ void Engine::time_stage(uint32_t stage, uint32_t n, uint32_t iters, float* ms_ou
     std::vector<cudaEvent_t> ev(2 * iters);
     for (auto& e : ev) CB2_CUDA(cudaEventCreate(&e));
     uint64_t launched = 0;
+    static const bool no_flush = std::getenv("CATTUS_B200_TIME_NO_FLUSH") != nullptr;  // experiment: weights stay in L2 between iterations
     for (uint32_t it = 0; it < iters; ++it) {
-        CB2_CUDA(cudaMemsetAsync(flush_.p, static_cast<int>(it & 0xFF), flush_.bytes, l.stream));
+        if (!no_flush) CB2_CUDA(cudaMemsetAsync(flush_.p, static_cast<int>(it & 0xFF), flush_.bytes, l.stream));
         CB2_CUDA(cudaEventRecord(ev[2 * it], l.stream));
         if (stage == 4) {
             static const bool no_graph = std::getenv("CATTUS_B200_TIME_NO_GRAPH") != nullptr;  // experiment: direct launches instead of the graph
