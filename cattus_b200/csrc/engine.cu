@@ -127,6 +127,25 @@ static std::vector<__nv_bfloat16> to_bf16(const std::vector<float>& v) {
     for (size_t i = 0; i < v.size(); ++i) o[i] = __float2bfloat16_rn(v[i]);
     return o;
 }
+
+// B operand image of tc_gemm: the [N_pad][K_pad] K-major matrix cut into the kernel's smem stages, each stage (n_umma rows x
+// 64 k = 128 B per row) stored CONTIGUOUSLY and already in the 128-byte-swizzled order the UMMA descriptor reads (16-byte
+// chunk c of row r sits at chunk c ^ (r & 7)), stages ordered [n_tile][k-block].  One stage is then ONE linear bulk copy
+// (cp.async.bulk) instead of a tensor-map box of n_umma separate 128-byte rows: the producer thread of the policy FC spent
+// ~300 cycles per box on those, 786 cycles per k-block at B = 1 whatever the ring depth (clock64 trace).
+template <class G>
+static std::vector<float> tile_b(const std::vector<float>& w, const G& g) {
+    const size_t num_kb = g.k_pad / 64, np = static_cast<size_t>(g.n_umma) * g.n_tiles;
+    std::vector<float> t(w.size());
+    for (size_t o = 0; o < np; ++o) {
+        const size_t r = o % g.n_umma;
+        for (size_t k = 0; k < g.k_pad; ++k) {
+            const size_t c = (k % 64) / 8, e = k % 8;
+            t[(((o / g.n_umma) * num_kb + k / 64) * g.n_umma + r) * 64 + ((c ^ (r & 7)) * 8 + e)] = w[o * g.k_pad + k];
+        }
+    }
+    return t;
+}
 template <class T>
 static void upload(DeviceBuf& buf, const std::vector<T>& v) {
     buf.alloc(v.size() * sizeof(T));
@@ -202,8 +221,10 @@ Engine::Engine(const cattus_b200_desc& desc, const void* blob_bytes, size_t blob
     CB2_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h_err_), 64, cudaHostAllocMapped));
     std::memset(h_err_, 0, 64);
     CB2_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_err_), h_err_, 0));
-    CB2_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(kTcStagesDeep)));
-    CB2_CUDA(cudaFuncSetAttribute(tc_gemm_dual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(kTcStagesDeep)));
+    CB2_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<kTcStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(kTcStages)));
+    CB2_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<kTcStagesDeep>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(kTcStagesDeep)));
+    CB2_CUDA(cudaFuncSetAttribute(tc_gemm_dual_kernel<kTcStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(kTcStages)));
+    CB2_CUDA(cudaFuncSetAttribute(tc_gemm_dual_kernel<kTcStagesDeep>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(kTcStagesDeep)));
     // whole-trunk kernel: 8x8 boards, 128 filters (flags bit 0 forces the per-layer path, used by the parity tests)
     fused_trunk_ = !simple_ && precision_ == CATTUS_B200_PRECISION_BF16 && d_.s == 8 && (d_.f == 64 || d_.f == 128 || d_.f == 256) && d_.c_in <= 32 &&
                    d_.wpp() == 1 && (desc.flags & 1u) == 0 && (sm_count_ >= 2) && vhp_ + php_ <= 64;
@@ -322,7 +343,7 @@ void Engine::upload_weights(const Blob& blob) {
                 b[o] = D[b_off + o];
                 for (uint32_t k = 0; k < nf; ++k) w[static_cast<size_t>(o) * g.k_pad + k] = D[w_off + static_cast<size_t>(o) * nf + k];
             }
-            upload(g.w, to_bf16(w));
+            upload(g.w, to_bf16(tile_b(w, g)));
             upload(g.b, b);
         };
         dense(dense1_, blob.d1_w, blob.d1_b, nf);
@@ -368,7 +389,7 @@ void Engine::upload_weights(const Blob& blob) {
             for (uint32_t i = 0; i < c.ci; ++i)
                 for (uint32_t t = 0; t < 9; ++t) w[static_cast<size_t>(o) * g.k_pad + t * ci_pad + i] = D[c.w + (static_cast<size_t>(o) * c.ci + i) * 9 + t];
         }
-        upload(g.w, to_bf16(w));
+        upload(g.w, to_bf16(tile_b(w, g)));
         upload(g.b, b);
     };
     auto conv1 = [&](GemmW& g, const Blob::Conv& c, uint32_t co_pad) {
@@ -380,7 +401,7 @@ void Engine::upload_weights(const Blob& blob) {
             b[o] = D[c.b + o];
             for (uint32_t i = 0; i < c.ci; ++i) w[static_cast<size_t>(o) * ca_ + i] = D[c.w + static_cast<size_t>(o) * c.ci + i];
         }
-        upload(g.w, to_bf16(w));
+        upload(g.w, to_bf16(tile_b(w, g)));
         upload(g.b, b);
     };
     auto fc = [&](GemmW& g, size_t w_off, size_t b_off, uint32_t n_out, uint32_t ch, uint32_t ch_pad) {
@@ -394,7 +415,7 @@ void Engine::upload_weights(const Blob& blob) {
                 for (uint32_t cell = 0; cell < s2; ++cell)
                     w[static_cast<size_t>(o) * g.k_pad + cell * ch_pad + c] = D[w_off + static_cast<size_t>(o) * ch * s2 + c * s2 + cell];
         }
-        upload(g.w, to_bf16(w));
+        upload(g.w, to_bf16(tile_b(w, g)));
         upload(g.b, b);
     };
     convs_.resize(1 + blob.block_conv.size());
@@ -561,6 +582,7 @@ CUtensorMap Engine::make_map_2d(const void* base, uint64_t inner, uint64_t rows,
     return m;
 }
 
+
 // NHWC activations [boards][S][S][channels]; box = {64 channels, S, S, nb boards}.  Out-of-bounds halo -> zeros.
 CUtensorMap Engine::make_map_conv(const void* base, uint32_t channels, uint32_t boards, uint32_t nb) {
     CUtensorMap m;
@@ -576,10 +598,15 @@ CUtensorMap Engine::make_map_conv(const void* base, uint32_t channels, uint32_t 
     return m;
 }
 
-// Ring depth of the GEMM kernel.  A 6-deep ring (one CTA per SM) for grids that leave SMs idle was measured and does
-// not help (chess B = 1 graph 0.123 -> 0.126 ms, hex5 0.035 -> 0.037 ms): the small-batch k-loop is not bound by TMA
-// round trips, so every launch keeps 3 stages and two CTAs per SM.
-int Engine::tc_stages_for(uint32_t) const { return kTcStages; }
+// Ring depth of the GEMM kernel: 6 stages and one CTA per SM for grids that leave SMs idle anyway AND have a long k-loop
+// (the chess head FCs, 32 k-blocks: B = 1 ... 256 graph -2 to -4 us); 3 stages and two CTAs per SM otherwise.  Short
+// k-loops gain nothing from the depth and the 197 KB launch costs the hex5 graph 2-4 us (A/B with CATTUS_B200_TC_NO_DEEP).
+// (Round 1 measured no gain from the deep ring at all: the k-loop was then paced by the single-lane issue loops, not by
+// the loads -- see tc_gemm.cuh.)
+int Engine::tc_stages_for(uint32_t ctas, int num_kb) const {
+    static const bool no_deep = std::getenv("CATTUS_B200_TC_NO_DEEP") != nullptr;  // A/B knob
+    return !no_deep && ctas <= static_cast<uint32_t>(sm_count_) && num_kb >= 16 ? kTcStagesDeep : kTcStages;
+}
 
 Op Engine::make_tc_op(int stage, const char* name, const TcGemmParams& p, uint32_t m_tiles, uint32_t n_tiles) {
     Op op;
@@ -587,10 +614,13 @@ Op Engine::make_tc_op(int stage, const char* name, const TcGemmParams& p, uint32
     op.name = name;
     const dim3 grid(m_tiles, n_tiles);
     TcGemmParams q = p;
-    q.stages = tc_stages_for(m_tiles * n_tiles);
+    const int stages = tc_stages_for(m_tiles * n_tiles, p.num_kb);
     q.fault = (desc_.flags & 2u) && stage == 2 ? 1 : 0;
-    const int smem_bytes = tc_smem_bytes(q.stages);
-    op.launch = [q, grid, smem_bytes](cudaStream_t st) { tc_gemm_kernel<<<grid, kTcThreads, smem_bytes, st>>>(q); };
+    const int smem_bytes = tc_smem_bytes(stages);
+    if (stages == kTcStagesDeep)
+        op.launch = [q, grid, smem_bytes](cudaStream_t st) { tc_gemm_kernel<kTcStagesDeep><<<grid, kTcThreads, smem_bytes, st>>>(q); };
+    else
+        op.launch = [q, grid, smem_bytes](cudaStream_t st) { tc_gemm_kernel<kTcStages><<<grid, kTcThreads, smem_bytes, st>>>(q); };
     return op;
 }
 
@@ -716,8 +746,8 @@ void Engine::build_ops_simple(Lane& lane, uint32_t bucket, std::vector<Op>& ops,
             p.err = d_err_;
             p.s2 = static_cast<int>(d_.s2());
             p.nb = 1;
-            p.tma_a = make_map_2d(a, static_cast<uint64_t>(nf), bucket, static_cast<uint64_t>(ld) * 2, 128);
-            p.tma_b = make_map_2d(g.w.p, g.k_pad, static_cast<uint64_t>(g.n_umma) * g.n_tiles, g.k_pad * 2ull, g.n_umma);
+            p.tma_a = make_map_2d(a, static_cast<uint64_t>(nf), bucket, static_cast<uint64_t>(ld) * 2, std::min(128u, bucket));
+            p.b_img = g.w.as<uint8_t>();
             p.bias = g.b.as<float>();
             p.out = out;
             p.mode = 0;
@@ -730,7 +760,7 @@ void Engine::build_ops_simple(Lane& lane, uint32_t bucket, std::vector<Op>& ops,
             p.ld_out = static_cast<int>(ld_out);
             p.out_f32 = out_f32 ? 1 : 0;
             p.relu = relu ? 1 : 0;
-            p.tx_bytes = 128 * 128 + g.n_umma * 128;
+            p.tx_bytes = std::min(128u, bucket) * 128 + g.n_umma * 128;
             ops.push_back(make_tc_op(stage, name, p, ceil_div(bucket, 128), g.n_tiles));
         };
         __nv_bfloat16* a0 = lane.d_act[0].as<__nv_bfloat16>();
@@ -859,7 +889,7 @@ void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
     auto conv3 = [&](const char* name, const __nv_bfloat16* in, uint32_t cpad, const GemmW& g, const __nv_bfloat16* resid, __nv_bfloat16* out) {
         TcGemmParams p = base_params();
         p.tma_a = make_map_conv(in, cpad, boards, nb_);
-        p.tma_b = make_map_2d(g.w.p, g.k_pad, static_cast<uint64_t>(g.n_umma) * g.n_tiles, g.k_pad * 2ull, g.n_umma);
+        p.b_img = g.w.as<uint8_t>();
         p.bias = g.b.as<float>();
         p.resid = resid;
         p.out = out;
@@ -882,8 +912,9 @@ void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
     auto gemm = [&](int stage, const char* name, const void* a, uint64_t k_real, uint64_t rows, uint64_t row_stride_bytes, const GemmW& g,
                     void* out, uint32_t ld_out, bool out_f32, bool relu) {
         TcGemmParams p = base_params();
-        p.tma_a = make_map_2d(a, k_real, rows, row_stride_bytes, 128);
-        p.tma_b = make_map_2d(g.w.p, g.k_pad, static_cast<uint64_t>(g.n_umma) * g.n_tiles, g.k_pad * 2ull, g.n_umma);
+        const uint32_t a_rows = static_cast<uint32_t>(std::min<uint64_t>(128, rows));
+        p.tma_a = make_map_2d(a, k_real, rows, row_stride_bytes, a_rows);
+        p.b_img = g.w.as<uint8_t>();
         p.bias = g.b.as<float>();
         p.out = out;
         p.mode = 0;
@@ -896,7 +927,7 @@ void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
         p.ld_out = static_cast<int>(ld_out);
         p.out_f32 = out_f32 ? 1 : 0;
         p.relu = relu ? 1 : 0;
-        p.tx_bytes = 128 * 128 + g.n_umma * 128;
+        p.tx_bytes = a_rows * 128 + g.n_umma * 128;
         last_tc = p;
         ops.push_back(make_tc_op(stage, name, p, ceil_div(static_cast<uint32_t>(rows), 128), g.n_tiles));
     };
@@ -1072,7 +1103,9 @@ void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
         dp.b.epi = fuse_policy ? 2 : 3;
         dp.b.recs = recs;
         dp.b.rl = L;
-        dp.b.probs = zero_copy_out(lane, bucket, dense_input) ? lane.zc_probs : lane.d_probs.as<float>();
+        // the masked logits of epi 3 stay in HBM: softmax_compact reads them there and writes the probabilities to wherever
+        // the caller reads them (zero-copy host memory for small buckets -- no read has to cross PCIe)
+        dp.b.probs = compact_policy || !zero_copy_out(lane, bucket, dense_input) ? lane.d_probs.as<float>() : lane.zc_probs;
         dp.b.n_ptr = n_ptr;
         dp.a = value_tc;
         ops.pop_back();
@@ -1081,19 +1114,27 @@ void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
         op.stage = 2;
         op.name = "heads_fc_dual";
         const dim3 grid(ceil_div(bucket, 128), 1 + pfc_.n_tiles);
-        dp.a.stages = dp.b.stages = tc_stages_for(grid.x * grid.y);
+        const int stages = tc_stages_for(grid.x * grid.y, std::max(dp.a.num_kb, dp.b.num_kb));
         dp.a.fault = (desc_.flags & 2u) ? 1 : 0;
-        const int smem_bytes = tc_smem_bytes(dp.a.stages);
-        op.launch = [dp, grid, smem_bytes](cudaStream_t st) { tc_gemm_dual_kernel<<<grid, kTcThreads, smem_bytes, st>>>(dp); };
+        if (std::getenv("CATTUS_B200_TRACE_HEADS")) {  // diagnostic: clock64 trace of the policy FC's tile (0, 1), printed by time_stage
+            if (trace_.p == nullptr) trace_.alloc(512 * sizeof(unsigned long long));
+            dp.a.dbg = dp.b.dbg = trace_.as<unsigned long long>();
+        }
+        const int smem_bytes = tc_smem_bytes(stages);
+        if (stages == kTcStagesDeep)
+            op.launch = [dp, grid, smem_bytes](cudaStream_t st) { tc_gemm_dual_kernel<kTcStagesDeep><<<grid, kTcThreads, smem_bytes, st>>>(dp); };
+        else
+            op.launch = [dp, grid, smem_bytes](cudaStream_t st) { tc_gemm_dual_kernel<kTcStages><<<grid, kTcThreads, smem_bytes, st>>>(dp); };
         ops.push_back(op);
     }
     if (compact_policy) {
         Op op;
         op.stage = 3;
         op.name = "softmax_compact";
+        const float* logits = lane.d_probs.as<float>();
         float* probs = zero_copy_out(lane, bucket, dense_input) ? lane.zc_probs : lane.d_probs.as<float>();
         const int blocks = static_cast<int>(ceil_div(bucket * 32, 256));
-        op.launch = [=](cudaStream_t st) { softmax_compact_kernel<<<blocks, 256, 0, st>>>(recs, L, n_ptr, probs); };
+        op.launch = [=](cudaStream_t st) { softmax_compact_kernel<<<blocks, 256, 0, st>>>(recs, L, n_ptr, logits, probs); };
         ops.push_back(op);
     }
     add_tail_ops(lane, bucket, ops, dense_input, !fuse_tails, !(fuse_policy || compact_policy));
@@ -1763,7 +1804,7 @@ void Engine::time_stage(uint32_t stage, uint32_t n, uint32_t iters, float* ms_ou
     cudaError_t e = cudaStreamSynchronize(l.stream);
     if (e != cudaSuccess) throw_device_error("time_stage", e);
     for (uint32_t it = 0; it < iters; ++it) CB2_CUDA(cudaEventElapsedTime(&ms_out[it], ev[2 * it], ev[2 * it + 1]));
-    if (trace_.p != nullptr && stage == 1) {
+    if (trace_.p != nullptr && stage == 1 && std::getenv("CATTUS_B200_TRACE_TRUNK")) {
         std::vector<unsigned long long> t(512);
         CB2_CUDA(cudaMemcpy(t.data(), trace_.p, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
         const unsigned long long t0 = t[0];
@@ -1781,6 +1822,27 @@ void Engine::time_stage(uint32_t stage, uint32_t n, uint32_t iters, float* ms_ou
                 std::fprintf(stderr, "  l%u t%u: %8lld %8lld %8lld\n", l, g0, static_cast<long long>(e[0] - t0), static_cast<long long>(e[1] - t0),
                              static_cast<long long>(e[2] - t0));
             }
+    }
+    if (trace_.p != nullptr && stage == 2 && std::getenv("CATTUS_B200_TRACE_HEADS")) {
+        std::vector<unsigned long long> t(512);
+        CB2_CUDA(cudaMemcpy(t.data(), trace_.p, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        const unsigned long long t0 = t[0];
+        std::fprintf(stderr, "heads trace (cycles since entry; n=%u): past n check %lld, setup done %lld, acc full %lld, epilogue done %lld, exit %lld\n", n,
+                     static_cast<long long>(t[1] - t0), static_cast<long long>(t[2] - t0), static_cast<long long>(t[3] - t0),
+                     static_cast<long long>(t[4] - t0), static_cast<long long>(t[5] - t0));
+        unsigned long long ns0 = ~0ull;
+        for (int y = 0; y < 17; ++y)
+            if (t[256 + 4 * y] != 0) ns0 = std::min(ns0, t[256 + 4 * y]);
+        std::fprintf(stderr, "  CTA (value, then policy N tiles): entry ns, exit ns (since the first entry), cycles inside\n");
+        for (int y = 0; y < 17; ++y)
+            if (t[256 + 4 * y] != 0)
+                std::fprintf(stderr, "  %2d: %6lld %6lld %8lld\n", y, static_cast<long long>(t[256 + 4 * y] - ns0), static_cast<long long>(t[256 + 4 * y + 2] - ns0),
+                             static_cast<long long>(t[256 + 4 * y + 3] - t[256 + 4 * y + 1]));
+        std::fprintf(stderr, "  k-block: stage free (producer) | arrives at wait, stage full (issuer)\n");
+        for (int kb = 0; kb < 40; ++kb)
+            if (t[8 + kb] != 0)
+                std::fprintf(stderr, "  %2d: %8lld | %8lld %8lld\n", kb, static_cast<long long>(t[48 + kb] - t0), static_cast<long long>(t[88 + kb] - t0),
+                             static_cast<long long>(t[8 + kb] - t0));
     }
     for (auto& x : ev) cudaEventDestroy(x);
     std::lock_guard<std::mutex> g(m_mu_);

@@ -213,7 +213,7 @@ class Engine {
     CUtensorMap make_map_2d(const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes, uint32_t box_rows);
     CUtensorMap make_map_conv(const void* base, uint32_t channels, uint32_t boards, uint32_t nb);
     Op make_tc_op(int stage, const char* name, const TcGemmParams& p, uint32_t m_tiles, uint32_t n_tiles);
-    int tc_stages_for(uint32_t ctas) const;
+    int tc_stages_for(uint32_t ctas, int num_kb) const;
 
     NetDims d_;
     cattus_b200_desc desc_{};
@@ -238,7 +238,7 @@ class Engine {
         DeviceBuf w, b;
         uint32_t n_umma = 16, n_tiles = 1, k_pad = 64;
     };
-    std::vector<GemmW> convs_;  // stem, then 2 per block (bf16: [Np][9*Cin_pad] bf16; fp32: torch layout f32)
+    std::vector<GemmW> convs_;  // stem, then 2 per block (bf16: [Np][9*Cin_pad] cut into contiguous pre-swizzled smem stages, tile_b() in engine.cu; fp32: torch layout f32)
     GemmW vconv_, pconv_, vfc1_, pfc_;
     GemmW dense1_, dense2_;  // SimpleTwoHeadedModel
     DeviceBuf vfc2_w_;

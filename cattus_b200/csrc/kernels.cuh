@@ -274,24 +274,26 @@ __global__ void policy_tail_kernel(const float* __restrict__ logits, int ld_logi
     }
 }
 
-// In place over the compact legal logits the policy FC epilogue wrote (tc_gemm.cuh, epi 3): probs = softmax(logits) per
-// position (calc_moves_probs, engine/src/net/mod.rs:106-119).  One warp per position; offset and count come from the
-// record prefix.
+// Over the compact legal logits the policy FC epilogue wrote (tc_gemm.cuh, epi 3): probs = softmax(logits) per position
+// (calc_moves_probs, engine/src/net/mod.rs:106-119).  One warp per position; offset and count come from the record
+// prefix.  `logits` and `probs` use the same offsets and may be the same buffer (large batches: in place in HBM) or differ
+// (small batches: logits in HBM, probabilities straight into the caller's zero-copy host block).
 __global__ void softmax_compact_kernel(const uint8_t* __restrict__ recs, RecLayout L, const uint32_t* __restrict__ n_ptr,
-                                       float* __restrict__ probs) {
+                                       const float* logits, float* probs) {
     const int n = static_cast<int>(*n_ptr);
     const int lane = threadIdx.x & 31;
     const int b = static_cast<int>((blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5);
     if (b >= n) return;
     const uint32_t* prefix = reinterpret_cast<const uint32_t*>(recs + static_cast<size_t>(b) * L.rec_bytes - 8);
     const uint32_t off = prefix[0], cnt = prefix[1];
+    const float* in = logits + off;
     float* row = probs + off;
     float x[8];  // <= 256 legal moves per position (chess: <= 218)
     float mx = -FLT_MAX;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const uint32_t i = lane + 32u * k;
-        x[k] = i < cnt ? row[i] : -FLT_MAX;
+        x[k] = i < cnt ? in[i] : -FLT_MAX;
         mx = fmaxf(mx, x[k]);
     }
 #pragma unroll

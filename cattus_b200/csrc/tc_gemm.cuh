@@ -2,6 +2,9 @@
 // (reference network: training/cattus_train/net_utils.py:45-89; engines it replaces: engine/src/net/model.rs:146-218).
 //
 //   D[128 x N] (fp32, TMEM) = sum over k-blocks of A[128 x 64] * B[N x 64]^T      (bf16 operands, 64 = one 128-byte row)
+// B lives in memory as the sequence of its smem stages ([n_tile][k-block][N rows][64 k], rows already 128-byte swizzled,
+// engine.cu tile_b()): one stage is one linear bulk copy.  A mode-0 A box holds min(128, rows) rows: the accumulator rows of
+// the stale smem rows below it are never read.
 //
 // mode 0 (matrix):  A is a row-major [rows][K] bf16 matrix (FC layers, 1x1 head convs).
 // mode 1 (conv3x3): A is the NHWC activation tensor [B][S][S][C]; the k-loop walks (tap, 64-channel slice) and each
@@ -18,7 +21,7 @@
 //   3 = policy mask fused for M > 128 (chess, 15 N tiles): + bias, non-finite -> f32::MIN, and only the logits of LEGAL
 //       moves are written, compactly, at (record offset + number of legal moves in earlier columns) -- 0.5 MB instead of
 //       the 31.5 MB dense f32 logits tensor per 4096 chess positions; softmax_compact_kernel then normalises in place.
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one lane), warps 2..5 = epilogue
+// Warp roles (224 threads): warp 0 = A producer (TMA), warp 6 = B producer (bulk copy), warp 1 = MMA issuer, warps 2..5 = epilogue
 // (TMEM -> registers -> +bias (+residual) -> ReLU -> bf16/f32 -> global).  3-stage smem ring (two CTAs per SM), full/empty mbarriers.
 #pragma once
 #include "kernels.cuh"
@@ -29,14 +32,14 @@ namespace cb2 {
 constexpr int kTcStages = 3;      // ring depth of large grids (two CTAs per SM)
 constexpr int kTcStagesDeep = 6;  // small grids (one latency-bound CTA per SM): deeper prefetch, see tc_smem_bytes()
 constexpr int kTcTileBytes = 128 * 128;  // 128 rows x 128 B
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 224;
 constexpr int kTcTmemCols = 128;
 constexpr int kTcSmemBytes = 2 * kTcStages * kTcTileBytes + 256 + 1024;  // tiles + barriers + alignment slack
 constexpr int tc_smem_bytes(int stages) { return 2 * stages * kTcTileBytes + 256 + 1024; }
 
 struct alignas(64) TcGemmParams {
     CUtensorMap tma_a;
-    CUtensorMap tma_b;
+    const uint8_t* b_img;         // B as pre-swizzled smem stages [n_tile][k-block][n_umma rows][128 B] (engine.cu tile_b())
     const float* bias;            // [n_tiles * n_umma], zero padded
     const __nv_bfloat16* resid;   // same layout as out (bf16) or nullptr
     void* out;
@@ -54,7 +57,6 @@ struct alignas(64) TcGemmParams {
     int out_f32;
     int relu;
     uint32_t tx_bytes;  // bytes one stage's two TMA boxes deliver
-    int stages;         // smem ring depth (kTcStages or kTcStagesDeep); the launch passes tc_smem_bytes(stages)
     int epi;            // epilogue variant, see above
     int fault;          // 1: fault injection, see the MMA issuer
     // epi 1
@@ -67,17 +69,29 @@ struct alignas(64) TcGemmParams {
     float* probs;         // compact output
     // epi 1, 2
     const uint32_t* n_ptr;
+    unsigned long long* dbg;  // optional clock64 trace of tile (0, 1) (CATTUS_B200_TRACE_HEADS=1, printed by time_stage), else nullptr
 };
 
+template <int kStages>
 __device__ __forceinline__ void tc_gemm_body(const TcGemmParams& p, const int m_tile, const int n_tile) {
     // An M tile that holds nothing but padding positions (the launch is sized for the batch bucket) has no live output.
     // Mode 1 tiles are whole boards; mode 0 rows are positions only for the head FCs (the epilogues 1-3), elsewhere rows
     // are board cells and the tile is always computed.
+    const bool trace = p.dbg != nullptr && m_tile == 0 && n_tile == 1 && p.epi != 1;
+    const int trace_slot = 256 + 4 * (p.epi == 1 ? 0 : n_tile + 1);  // every CTA of the first M tile: entry / exit in ns and cycles
+    if (p.dbg != nullptr && m_tile == 0 && threadIdx.x == 0) {
+        unsigned long long ns;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+        p.dbg[trace_slot] = ns;
+        p.dbg[trace_slot + 1] = clock64();
+    }
+    if (trace && threadIdx.x == 0) p.dbg[0] = clock64();
     if (p.n_ptr != nullptr && (p.mode == 1 || p.epi != 0) && m_tile * (p.mode == 0 ? 128 : p.nb) >= static_cast<int>(*p.n_ptr)) return;
+    if (trace && threadIdx.x == 0) p.dbg[1] = clock64();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint8_t* smem_a = smem;
-    const int stages = p.stages;
+    constexpr int stages = kStages;  // compile time: the loops below unroll over one trip around the ring
     uint8_t* smem_b = smem + stages * kTcTileBytes;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + 2 * stages * kTcTileBytes);
     uint64_t* empty_bar = full_bar + stages;
@@ -89,11 +103,10 @@ __device__ __forceinline__ void tc_gemm_body(const TcGemmParams& p, const int m_
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&p.tma_a);
-        ptx::prefetch_tensormap(&p.tma_b);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < stages; ++s) {
-            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&full_bar[s], 2);  // the A and the B producer each arrive with their own byte count
             ptx::mbar_init(&empty_bar[s], 1);
         }
         ptx::mbar_init(tmem_full_bar, 1);
@@ -107,45 +120,98 @@ __device__ __forceinline__ void tc_gemm_body(const TcGemmParams& p, const int m_
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    if (trace && threadIdx.x == 0) p.dbg[2] = clock64();
 
+    // Producer and issuer: the WHOLE warp runs the loop (warp-uniform control flow and addresses, so descriptors and
+    // coordinates stay in uniform registers) and one elected lane issues the TMA / tcgen05 instructions.  With the loops
+    // inside `if (lane == 0)` the issuer needed ~600 cycles per k-block of four MMAs (256 cycles of tensor-pipe work) and the
+    // producer ~680 per pair of loads: every GEMM of this file was issue-bound (clock64 trace).
+    // Both loops are unrolled over one trip around the ring (the ring depth is a template parameter), so slot, barrier and
+    // tile addresses are immediates, and the rest of the bookkeeping is incremental: one warp runs a dependent chain, and the
+    // `kb % stages` / `kb / kh` divisions alone were ~60 of the ~100 instructions per k-block.
     if (warp == 0) {
-        if (lane == 0) {
-            for (int kb = 0; kb < p.num_kb; ++kb) {
-                const int s = kb % stages;
-                const uint32_t ph = (kb / stages) & 1;
-                ptx::mbar_wait(&empty_bar[s], ph ^ 1, p.err, 0x100 + s);
-                ptx::mbar_arrive_expect_tx(&full_bar[s], p.tx_bytes);
-                if (p.mode == 0) {
-                    ptx::tma_load_2d(smem_a + s * kTcTileBytes, &p.tma_a, &full_bar[s], kb * 64, m_tile * 128);
-                } else {
-                    const int tap = kb / p.kh, slice = kb - tap * p.kh;
-                    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-                    ptx::tma_load_4d(smem_a + s * kTcTileBytes, &p.tma_a, &full_bar[s], slice * 64, dx, dy, m_tile * p.nb);
+        // ---- A producer
+        const bool leader = ptx::elect_one();
+        const uint32_t a_bytes = p.tx_bytes - static_cast<uint32_t>(p.n_umma) * 128;
+        const int num_kb = p.num_kb, kh = p.kh, mode = p.mode;
+        const int a_c1 = mode == 0 ? m_tile * 128 : m_tile * p.nb;
+        int slice = 0, dx = -1, dy = -1;
+        uint32_t ph = 1;  // parity of the `empty` phase to wait for: the first trip passes on fresh barriers
+        for (int kb0 = 0; kb0 < num_kb; kb0 += stages, ph ^= 1) {
+#pragma unroll
+            for (int s = 0; s < stages; ++s) {
+                const int kb = kb0 + s;
+                if (kb >= num_kb) break;
+                ptx::mbar_wait(&empty_bar[s], ph, p.err, 0x100 + s);
+                if (trace && lane == 0 && kb < 40) p.dbg[48 + kb] = clock64();
+                if (leader) {
+                    ptx::mbar_arrive_expect_tx(&full_bar[s], a_bytes);
+                    if (mode == 0)
+                        ptx::tma_load_2d(smem_a + s * kTcTileBytes, &p.tma_a, &full_bar[s], kb * 64, a_c1);
+                    else
+                        ptx::tma_load_4d(smem_a + s * kTcTileBytes, &p.tma_a, &full_bar[s], slice * 64, dx, dy, a_c1);
                 }
-                ptx::tma_load_2d(smem_b + s * kTcTileBytes, &p.tma_b, &full_bar[s], kb * 64, n_tile * p.n_umma);
+                if (++slice == kh) {  // mode 1: k-blocks walk (tap, 64-channel slice), taps row-major over (dy, dx)
+                    slice = 0;
+                    if (++dx == 2) {
+                        dx = -1;
+                        ++dy;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 6) {
+        // ---- B producer (its own warp: try_wait + expect_tx + one load is ~250 cycles of dependent issue, the MMAs of one
+        // k-block take 256; one warp issuing both loads needed ~470 and paced the whole k-loop)
+        const bool leader = ptx::elect_one();
+        const uint8_t* b_src = p.b_img + static_cast<size_t>(n_tile) * p.num_kb * p.n_umma * 128;
+        const uint32_t b_bytes = static_cast<uint32_t>(p.n_umma) * 128;
+        const int num_kb = p.num_kb;
+        uint32_t ph = 1;
+        for (int kb0 = 0; kb0 < num_kb; kb0 += stages, ph ^= 1) {
+#pragma unroll
+            for (int s = 0; s < stages; ++s) {
+                if (kb0 + s >= num_kb) break;
+                ptx::mbar_wait(&empty_bar[s], ph, p.err, 0x180 + s);
+                if (leader) {
+                    ptx::mbar_arrive_expect_tx(&full_bar[s], b_bytes);
+                    ptx::bulk_load(smem_b + s * kTcTileBytes, b_src, b_bytes, &full_bar[s]);
+                }
+                b_src += b_bytes;
+                __syncwarp();
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = ptx::umma_idesc_bf16(128, p.n_umma);
-            for (int kb = 0; kb < p.num_kb; ++kb) {
-                const int s = kb % stages;
-                const uint32_t ph = (kb / stages) & 1;
+        const uint32_t idesc = ptx::umma_idesc_bf16(128, p.n_umma);
+        const uint64_t desc0 = ptx::umma_desc_sw128(0, 1024);  // stage tiles are 1024-byte aligned: only the start address varies
+        const uint32_t d_hi = static_cast<uint32_t>(desc0 >> 32), d_lo_fixed = static_cast<uint32_t>(desc0);
+        const uint32_t a_lo0 = d_lo_fixed | (ptx::smem_u32(smem_a) >> 4), b_lo0 = d_lo_fixed | (ptx::smem_u32(smem_b) >> 4);
+        const bool leader = ptx::elect_one();
+        const int num_kb = p.num_kb;
+        uint32_t ph = 0;
+        for (int kb0 = 0; kb0 < num_kb; kb0 += stages, ph ^= 1) {
+#pragma unroll
+            for (int s = 0; s < stages; ++s) {
+                const int kb = kb0 + s;
+                if (kb >= num_kb) break;
+                if (trace && lane == 0 && kb < 40) p.dbg[88 + kb] = clock64();
                 ptx::mbar_wait(&full_bar[s], ph, p.err, 0x200 + s);
                 ptx::tc_fence_after();
-                const uint32_t a_addr = ptx::smem_u32(smem_a + s * kTcTileBytes);
-                const uint32_t b_addr = ptx::smem_u32(smem_b + s * kTcTileBytes);
+                if (trace && lane == 0 && kb < 40) p.dbg[8 + kb] = clock64();
+                if (leader) {
+                    const uint32_t a_lo = a_lo0 + s * (kTcTileBytes >> 4), b_lo = b_lo0 + s * (kTcTileBytes >> 4);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {  // 4 x (K = 16 bf16 = 32 B) inside the 128-byte swizzle row
-                    ptx::umma_bf16_ss(tmem_base, ptx::umma_desc_sw128(a_addr + k * 32, 1024),
-                                      ptx::umma_desc_sw128(b_addr + k * 32, 1024), idesc, (kb | k) != 0);
+                    for (int k = 0; k < 4; ++k)  // 4 x (K = 16 bf16 = 32 B) inside the 128-byte swizzle row
+                        ptx::umma_bf16_ss_lohi(tmem_base, a_lo + 2 * k, d_hi, b_lo + 2 * k, d_hi, idesc, (kb | k) != 0);
+                    ptx::umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
                 }
-                ptx::umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+                __syncwarp();
             }
-            // fault injection (cattus_b200_desc.flags bit 1, tests only): tile (0, 0) never publishes its accumulator, so the
-            // epilogue's bounded wait below expires, records its code and traps -- the path a pipeline bug would take
-            if (!(p.fault && m_tile == 0 && n_tile == 0)) ptx::umma_commit(tmem_full_bar);  // accumulator complete
         }
+        // fault injection (cattus_b200_desc.flags bit 1, tests only): tile (0, 0) never publishes its accumulator, so the
+        // epilogue's bounded wait below expires, records its code and traps -- the path a pipeline bug would take
+        if (leader && !(p.fault && m_tile == 0 && n_tile == 0)) ptx::umma_commit(tmem_full_bar);  // accumulator complete
     } else {
         // Epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32); warps 2,3,4,5 cover all four quarters.
         const uint32_t q = warp & 3;
@@ -161,6 +227,7 @@ __device__ __forceinline__ void tc_gemm_body(const TcGemmParams& p, const int m_
         }
         ptx::mbar_wait(tmem_full_bar, 0, p.err, 0x300, p.fault ? (1u << 14) : (1u << 24));
         ptx::tc_fence_after();
+        if (trace && threadIdx.x == 64) p.dbg[3] = clock64();
         const uint32_t taddr = tmem_base + ((q * 32u) << 16);
         if (p.epi == 1) {
             // ---- value head: tanh(b2 + sum_j relu(acc_j + b1_j) * w2_j)
@@ -314,13 +381,22 @@ __device__ __forceinline__ void tc_gemm_body(const TcGemmParams& p, const int m_
         }
     }
 
+    if (trace && threadIdx.x == 64) p.dbg[4] = clock64();
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 2) ptx::tmem_dealloc(tmem_base, kTcTmemCols);
+    if (trace && threadIdx.x == 64) p.dbg[5] = clock64();
+    if (p.dbg != nullptr && m_tile == 0 && threadIdx.x == 64) {
+        unsigned long long ns;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+        p.dbg[trace_slot + 2] = ns;
+        p.dbg[trace_slot + 3] = clock64();
+    }
 }
 
-__global__ void __launch_bounds__(kTcThreads, 2) tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
-    tc_gemm_body(p, blockIdx.x, blockIdx.y);
+template <int kStages>
+__global__ void __launch_bounds__(kTcThreads, kStages > kTcStages ? 1 : 2) tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
+    tc_gemm_body<kStages>(p, blockIdx.x, blockIdx.y);
 }
 
 // Two independent GEMMs in one launch: blockIdx.y == 0 runs problem `a` (one N tile), blockIdx.y >= 1 runs N tile
@@ -330,11 +406,12 @@ struct alignas(64) TcGemmDualParams {
     TcGemmParams a;
     TcGemmParams b;
 };
-__global__ void __launch_bounds__(kTcThreads, 2) tc_gemm_dual_kernel(const __grid_constant__ TcGemmDualParams d) {
+template <int kStages>
+__global__ void __launch_bounds__(kTcThreads, kStages > kTcStages ? 1 : 2) tc_gemm_dual_kernel(const __grid_constant__ TcGemmDualParams d) {
     if (blockIdx.y == 0)
-        tc_gemm_body(d.a, blockIdx.x, 0);
+        tc_gemm_body<kStages>(d.a, blockIdx.x, 0);
     else
-        tc_gemm_body(d.b, blockIdx.x, static_cast<int>(blockIdx.y) - 1);
+        tc_gemm_body<kStages>(d.b, blockIdx.x, static_cast<int>(blockIdx.y) - 1);
 }
 
 }  // namespace cb2
