@@ -960,6 +960,11 @@ void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
         fp.rec_bytes = rec_.rec_bytes;
         fp.planes = static_cast<int>(d_.c_in);
         fp.layers = 1 + 2 * static_cast<int>(d_.r);
+        fp.dbg = nullptr;
+        if (std::getenv("CATTUS_B200_TRACE_TRUNK")) {  // diagnostic: per-layer clock64 trace of pair 0, printed by time_stage
+            if (trace_.p == nullptr) trace_.alloc(512 * sizeof(unsigned long long));
+            fp.dbg = trace_.as<unsigned long long>();
+        }
         // small batches: one tile per CTA (4 boards per pair) while that still fits one wave -- half the MMAs per round
         // (256 filters: one tile per CTA always -- two tiles' activations do not fit beside the weight ring)
         fp.tiles = (static_cast<int>(ceil_div(bucket, 4)) <= sm / 2 || d_.f == 256) ? 1 : 2;
@@ -1808,10 +1813,14 @@ void Engine::time_stage(uint32_t stage, uint32_t n, uint32_t iters, float* ms_ou
         std::vector<unsigned long long> t(512);
         CB2_CUDA(cudaMemcpy(t.data(), trace_.p, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
         const unsigned long long t0 = t[0];
+        if (fused_trunk_)
+            std::fprintf(stderr, "trunk trace (cycles since the stem's inputs; n=%u): layer: issuer has k-chunk 0 / 1 / last, last MMA issued | epilogue sees the accumulator, "
+                                 "first chunk signalled by warp set 0 / 1, last chunk signalled\n", n);
+        else
         std::fprintf(stderr, "trunk trace (cycles since layer 0 issue; n=%u): layer: inputs_ready mma_issued | acc_full ld_done stored fenced arrived\n", n);
         for (uint32_t l = 0; l <= 1 + 2 * d_.r && l < 64; ++l) {
             std::fprintf(stderr, "  l%-2u:", l);
-            for (int k = 0; k < 7; ++k) std::fprintf(stderr, " %8lld", static_cast<long long>(t[l * 8 + k] - t0));
+            for (int k = 0; k < (fused_trunk_ ? 8 : 7); ++k) std::fprintf(stderr, " %8lld", static_cast<long long>(t[l * 8 + k] - t0));
             std::fprintf(stderr, "\n");
         }
         std::fprintf(stderr, "issuer per (layer, first tile of group): arrive_at_wait inputs_ready issued\n");

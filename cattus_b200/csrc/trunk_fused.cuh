@@ -106,6 +106,7 @@ struct alignas(64) TrunkFusedParams {
     int num_rounds;  // ceil(boards / (4 * tiles))
     int tiles;       // 128-row tiles per CTA in use: 2 (8 boards per pair and round) or, for small batches, 1 (4 boards: half the MMAs per round)
     int vhp, php;    // padded head widths (multiples of 16, vhp + php <= 64)
+    unsigned long long* dbg;  // optional [layer][8] clock64 trace of pair 0, round 0 (CATTUS_B200_TRACE_TRUNK=1), else nullptr
 };
 
 // first k-chunk block of layer l in the weight image (the stem has 2 k-chunks, every other layer F / 16)
@@ -233,6 +234,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1) trunk
                                     act_par ^= 1u << bi;
                                 }
                                 ptx::tc_fence_after();
+                                if (p.dbg != nullptr && pair == 0 && rd == 0 && t == 0 && sub == 0 && lane == 0 && (kc == 0 || kc == 1 || kc == nkc - 1))
+                                    p.dbg[l * 8 + (kc == 0 ? 0 : kc == 1 ? 1 : 2)] = clock64();  // inputs of k-chunk 0 / 1 / last are there
                                 const uint32_t a_lo0 = a_lo_fixed | ((act_addr + (t * 2 + in_buf) * G::kBufBytes + (2 * kc) * kFtLbo + kFtCell0 * 16) >> 4);
                                 const uint32_t d = tmem_base + static_cast<uint32_t>((t * 2 + (l & 1)) * F);
                                 if (leader_lane) {
@@ -244,6 +247,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1) trunk
                                     }
                                     if (kc == nkc - 1 && sub == G::kSubStages - 1) ptx::umma_commit_pair_multicast(&acc_full[t * 2 + (l & 1)], 3);
                                 }
+                                if (p.dbg != nullptr && pair == 0 && rd == 0 && t == 0 && lane == 0 && kc == nkc - 1 && sub == G::kSubStages - 1)
+                                    p.dbg[l * 8 + 3] = clock64();  // last MMA of the layer issued
                             }
                             if (leader_lane) ptx::umma_commit_pair_multicast(&w_empty[slot], 3);
                             __syncwarp();
@@ -333,6 +338,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1) trunk
                 ptx::mbar_wait(&acc_full[t * 2 + par], (acc_par >> par) & 1u, p.err, 0x3100 + t * 2 + par);
                 acc_par ^= 1u << par;
                 ptx::tc_fence_after();
+                const bool tr = p.dbg != nullptr && pair == 0 && rd == 0 && rank == 0 && t == 0 && q == 0 && lane == 0;
+                if (tr && wset == 0) p.dbg[l * 8 + 4] = clock64();  // accumulator complete (seen by the epilogue)
 #pragma unroll 1
                 for (int kc = kc0; kc < kKc; kc += kcs) {
                     uint32_t raw[16];
@@ -378,6 +385,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1) trunk
                     ptx::fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive_cluster(leader_act + kc * 8);
+                    if (tr && kc == kc0) p.dbg[l * 8 + 5 + (split ? wset : 0)] = clock64();  // first chunk of this warp set signalled
+                    if (tr && kc + kcs >= kKc && (!split || wset == 1)) p.dbg[l * 8 + 7] = clock64();  // last chunk signalled
                 }
             }
             // ---- both 1x1 head convolutions: accumulator (t, parity 1), columns [0, vhp) value, [vhp, vhp + php) policy
