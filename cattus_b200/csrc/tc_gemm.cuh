@@ -20,9 +20,9 @@
 //       the reference's sequential `iter().sum()`.
 //   3 = policy mask fused for M > 128 (chess, 15 N tiles): + bias, non-finite -> f32::MIN, and only the logits of LEGAL
 //       moves are written, compactly, at (record offset + number of legal moves in earlier columns) -- 0.5 MB instead of
-//       the 31.5 MB dense f32 logits tensor per 4096 chess positions; softmax_compact_kernel then normalises in place.
+//       the 31.5 MB dense f32 logits tensor per 4096 chess positions; softmax_compact_kernel then normalises.
 // Warp roles (224 threads): warp 0 = A producer (TMA), warp 6 = B producer (bulk copy), warp 1 = MMA issuer, warps 2..5 = epilogue
-// (TMEM -> registers -> +bias (+residual) -> ReLU -> bf16/f32 -> global).  3-stage smem ring (two CTAs per SM), full/empty mbarriers.
+// (TMEM -> registers -> +bias (+residual) -> ReLU -> bf16/f32 -> global).  Smem ring of 3 stages (two CTAs per SM) or 6 (one CTA per SM; template parameter), full/empty mbarriers.
 #pragma once
 #include "kernels.cuh"
 #include "ptx.cuh"
