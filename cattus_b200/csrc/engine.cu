@@ -608,6 +608,24 @@ int Engine::tc_stages_for(uint32_t ctas, int num_kb) const {
     return !no_deep && ctas <= static_cast<uint32_t>(sm_count_) && num_kb >= 16 ? kTcStagesDeep : kTcStages;
 }
 
+// Launch with programmatic stream serialization: the kernel may be staged while its predecessor on the stream still runs
+// (ptx.cuh: grid_dep_wait / grid_dep_launch).  Captured into the bucket graphs as a programmatic dependency edge.
+template <class... P, class... Args>
+static void launch_pdl(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    static const bool off = std::getenv("CATTUS_B200_NO_PDL") != nullptr;  // A/B knob
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = off ? 0 : 1;
+    CB2_CUDA(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
+}
+
 Op Engine::make_tc_op(int stage, const char* name, const TcGemmParams& p, uint32_t m_tiles, uint32_t n_tiles) {
     Op op;
     op.stage = stage;
@@ -1127,9 +1145,9 @@ void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
         }
         const int smem_bytes = tc_smem_bytes(stages);
         if (stages == kTcStagesDeep)
-            op.launch = [dp, grid, smem_bytes](cudaStream_t st) { tc_gemm_dual_kernel<kTcStagesDeep><<<grid, kTcThreads, smem_bytes, st>>>(dp); };
+            op.launch = [dp, grid, smem_bytes](cudaStream_t st) { launch_pdl(tc_gemm_dual_kernel<kTcStagesDeep>, grid, dim3(kTcThreads), smem_bytes, st, dp); };
         else
-            op.launch = [dp, grid, smem_bytes](cudaStream_t st) { tc_gemm_dual_kernel<kTcStages><<<grid, kTcThreads, smem_bytes, st>>>(dp); };
+            op.launch = [dp, grid, smem_bytes](cudaStream_t st) { launch_pdl(tc_gemm_dual_kernel<kTcStages>, grid, dim3(kTcThreads), smem_bytes, st, dp); };
         ops.push_back(op);
     }
     if (compact_policy) {
@@ -1139,7 +1157,7 @@ void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
         const float* logits = lane.d_probs.as<float>();
         float* probs = zero_copy_out(lane, bucket, dense_input) ? lane.zc_probs : lane.d_probs.as<float>();
         const int blocks = static_cast<int>(ceil_div(bucket * 32, 256));
-        op.launch = [=](cudaStream_t st) { softmax_compact_kernel<<<blocks, 256, 0, st>>>(recs, L, n_ptr, logits, probs); };
+        op.launch = [=](cudaStream_t st) { launch_pdl(softmax_compact_kernel, dim3(blocks), dim3(256), 0, st, recs, L, n_ptr, logits, probs); };
         ops.push_back(op);
     }
     add_tail_ops(lane, bucket, ops, dense_input, !fuse_tails, !(fuse_policy || compact_policy));

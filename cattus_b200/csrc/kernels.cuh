@@ -280,6 +280,7 @@ __global__ void policy_tail_kernel(const float* __restrict__ logits, int ld_logi
 // (small batches: logits in HBM, probabilities straight into the caller's zero-copy host block).
 __global__ void softmax_compact_kernel(const uint8_t* __restrict__ recs, RecLayout L, const uint32_t* __restrict__ n_ptr,
                                        const float* logits, float* probs) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // launched beside the tail of the policy FC (ptx.cuh: grid_dep_wait)
     const int n = static_cast<int>(*n_ptr);
     const int lane = threadIdx.x & 31;
     const int b = static_cast<int>((blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5);

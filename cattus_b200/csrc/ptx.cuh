@@ -28,6 +28,14 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start (and run its prologue) while the
+// kernel before it on the stream is still running, once every CTA of that kernel has called grid_dep_launch() or exited;
+// grid_dep_wait() blocks until the earlier kernel has completed and its memory is visible.  Both are no-ops in a kernel
+// launched the ordinary way.
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

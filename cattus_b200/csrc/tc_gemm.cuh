@@ -120,6 +120,9 @@ __device__ __forceinline__ void tc_gemm_body(const TcGemmParams& p, const int m_
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    // Everything above ran beside the tail of the kernel before this one (the trunk); its output is read from here on.
+    ptx::grid_dep_wait();
+    ptx::grid_dep_launch();  // the next kernel (softmax_compact) may stage itself; it waits for this whole grid before it reads
     if (trace && threadIdx.x == 0) p.dbg[2] = clock64();
 
     // Producer and issuer: the WHOLE warp runs the loop (warp-uniform control flow and addresses, so descriptors and

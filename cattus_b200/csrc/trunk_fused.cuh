@@ -161,6 +161,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1) trunk
     ptx::cluster_sync();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    ptx::grid_dep_launch();  // the head FC kernel may stage its CTAs on SMs this grid leaves free; it waits for this grid's end
     // byte offset (from `smem`) of ring slot i: the ring proper, then the idle tile's activation buffers
     auto slot_off = [](uint32_t i) -> uint32_t {
         return i < static_cast<uint32_t>(G::kWStages) ? static_cast<uint32_t>(G::kWOff) + i * G::kWStage

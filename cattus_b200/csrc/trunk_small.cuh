@@ -141,6 +141,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) trunk_small_kernel(const __grid
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    ptx::grid_dep_launch();  // the head FC kernel may stage its CTAs beside this grid; it waits for this grid's end
 
     if (warp >= kTsIssuerWarp) {
         // ================================================================== MMA issuers (warp 16: even groups, 17: odd)
