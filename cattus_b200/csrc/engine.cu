@@ -598,14 +598,16 @@ CUtensorMap Engine::make_map_conv(const void* base, uint32_t channels, uint32_t 
     return m;
 }
 
-// Ring depth of the GEMM kernel: 6 stages and one CTA per SM for grids that leave SMs idle anyway AND have a long k-loop
-// (the chess head FCs, 32 k-blocks: B = 1 ... 256 graph -2 to -4 us); 3 stages and two CTAs per SM otherwise.  Short
-// k-loops gain nothing from the depth and the 197 KB launch costs the hex5 graph 2-4 us (A/B with CATTUS_B200_TC_NO_DEEP).
-// (Round 1 measured no gain from the deep ring at all: the k-loop was then paced by the single-lane issue loops, not by
-// the loads -- see tc_gemm.cuh.)
-int Engine::tc_stages_for(uint32_t ctas, int num_kb) const {
-    static const bool no_deep = std::getenv("CATTUS_B200_TC_NO_DEEP") != nullptr;  // A/B knob
-    return !no_deep && ctas <= static_cast<uint32_t>(sm_count_) && num_kb >= 16 ? kTcStagesDeep : kTcStages;
+// Ring depth of the GEMM kernel: 6 stages and one CTA per SM for the smallest batches (<= 64 rows) of GEMMs with a long
+// k-loop (the chess head FCs, 32 k-blocks: B = 1 ... 64 graph -2 to -4 us); 3 stages and two CTAs per SM otherwise.
+// Short k-loops gain nothing from the depth and the 197 KB launch costs the hex5 graph 2-4 us; larger small batches
+// usually come from many lanes at once (trainer-sized jobs with speculative rows: ~100 rows per batch on 16 streams),
+// where CTAs that each take a whole SM cost 12 % of the job's throughput (1.24 M -> 1.09 M sims/s), more than the 2-4 us
+// they save a lone batch.  A/B knob: CATTUS_B200_TC_NO_DEEP.  (Round 1 measured no gain from the deep ring at all: the
+// k-loop was then paced by the single-lane issue loops, not by the loads -- see tc_gemm.cuh.)
+int Engine::tc_stages_for(uint32_t ctas, int num_kb, uint32_t rows) const {
+    static const bool no_deep = std::getenv("CATTUS_B200_TC_NO_DEEP") != nullptr;
+    return !no_deep && ctas <= static_cast<uint32_t>(sm_count_) && num_kb >= 16 && rows <= 64 ? kTcStagesDeep : kTcStages;
 }
 
 // Launch with programmatic stream serialization: the kernel may be staged while its predecessor on the stream still runs
@@ -632,7 +634,7 @@ Op Engine::make_tc_op(int stage, const char* name, const TcGemmParams& p, uint32
     op.name = name;
     const dim3 grid(m_tiles, n_tiles);
     TcGemmParams q = p;
-    const int stages = tc_stages_for(m_tiles * n_tiles, p.num_kb);
+    const int stages = tc_stages_for(m_tiles * n_tiles, p.num_kb, p.mode == 0 ? static_cast<uint32_t>(p.m_valid) : 0xFFFFFFFFu);
     q.fault = (desc_.flags & 2u) && stage == 2 ? 1 : 0;
     const int smem_bytes = tc_smem_bytes(stages);
     if (stages == kTcStagesDeep)
@@ -1137,7 +1139,7 @@ void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
         op.stage = 2;
         op.name = "heads_fc_dual";
         const dim3 grid(ceil_div(bucket, 128), 1 + pfc_.n_tiles);
-        const int stages = tc_stages_for(grid.x * grid.y, std::max(dp.a.num_kb, dp.b.num_kb));
+        const int stages = tc_stages_for(grid.x * grid.y, std::max(dp.a.num_kb, dp.b.num_kb), bucket);
         dp.a.fault = (desc_.flags & 2u) ? 1 : 0;
         if (std::getenv("CATTUS_B200_TRACE_HEADS")) {  // diagnostic: clock64 trace of the policy FC's tile (0, 1), printed by time_stage
             if (trace_.p == nullptr) trace_.alloc(512 * sizeof(unsigned long long));

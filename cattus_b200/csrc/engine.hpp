@@ -213,7 +213,7 @@ class Engine {
     CUtensorMap make_map_2d(const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes, uint32_t box_rows);
     CUtensorMap make_map_conv(const void* base, uint32_t channels, uint32_t boards, uint32_t nb);
     Op make_tc_op(int stage, const char* name, const TcGemmParams& p, uint32_t m_tiles, uint32_t n_tiles);
-    int tc_stages_for(uint32_t ctas, int num_kb) const;
+    int tc_stages_for(uint32_t ctas, int num_kb, uint32_t rows) const;
 
     NetDims d_;
     cattus_b200_desc desc_{};

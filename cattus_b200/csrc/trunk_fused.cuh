@@ -161,7 +161,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1) trunk
     ptx::cluster_sync();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
-    ptx::grid_dep_launch();  // the head FC kernel may stage its CTAs on SMs this grid leaves free; it waits for this grid's end
     // byte offset (from `smem`) of ring slot i: the ring proper, then the idle tile's activation buffers
     auto slot_off = [](uint32_t i) -> uint32_t {
         return i < static_cast<uint32_t>(G::kWStages) ? static_cast<uint32_t>(G::kWOff) + i * G::kWStage
@@ -329,6 +328,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1) trunk
                 }
             }
             for (int l = 0; l < p.layers; ++l) {
+                // Last layer of this pair's last round: the head FC kernel may be staged now (it runs its prologue and then waits
+                // for this whole grid).  Not earlier: staged CTAs hold their shared memory while they wait, and with many lanes
+                // in flight they would take SMs away from the other lanes' trunks for the length of this kernel.
+                if (l == p.layers - 1 && rd + num_pairs >= rounds && warp == 4 && lane == 0) ptx::grid_dep_launch();
                 const int par = l & 1;
                 const bool has_resid = l >= 2 && par == 0;  // conv2 of a block: + block input (Q), result back into Q
                 uint8_t* outb = par ? bufP : bufQ;          // stem -> Q, conv1 -> P, conv2 -> Q

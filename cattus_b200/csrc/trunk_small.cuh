@@ -141,7 +141,6 @@ __global__ void __launch_bounds__(kTsThreads, 1) trunk_small_kernel(const __grid
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
-    ptx::grid_dep_launch();  // the head FC kernel may stage its CTAs beside this grid; it waits for this grid's end
 
     if (warp >= kTsIssuerWarp) {
         // ================================================================== MMA issuers (warp 16: even groups, 17: odd)
@@ -242,6 +241,10 @@ __global__ void __launch_bounds__(kTsThreads, 1) trunk_small_kernel(const __grid
             }
             for (int l = 0; l <= p.layers; ++l) {
                 const bool head = l == p.layers;
+                // Last layer of this CTA's last round: the head FC kernel may be staged now (it runs its prologue and then waits
+                // for this whole grid).  Not earlier: staged CTAs hold their shared memory while they wait, and with many lanes
+                // in flight they would take SMs away from the other lanes' trunks for the length of this kernel.
+                if (l == p.layers - 1 && rd + static_cast<int>(gridDim.x) >= rounds && warp == 0 && lane == 0) ptx::grid_dep_launch();
                 const uint32_t par = static_cast<uint32_t>(l & 1);
                 const bool has_resid = l >= 2 && par == 0;  // conv2 of a block: + block input (Q), result back into Q
                 uint8_t* outb = par ? bufP : bufQ;          // stem -> Q, conv1 -> P, conv2 -> Q

@@ -278,8 +278,10 @@ def test_per_leaf_eval_is_thread_safe_and_batch_invariant():
     with make_network(name, precision="bf16", batch_size=32, n_streams=2) as nw:
         ref_probs, ref_off, ref_vals = nw.eval_batch(words)
         out = [None] * n
+        start = threading.Barrier(16)
 
         def worker(k):
+            start.wait()
             for i in range(k, n, 16):
                 out[i] = nw.eval_planes(words[i])
 
@@ -289,9 +291,11 @@ def test_per_leaf_eval_is_thread_safe_and_batch_invariant():
         m = nw.metrics()
         for i in range(n):
             p, v = out[i]
-            assert np.array_equal(p, ref_probs[ref_off[i]:ref_off[i + 1]]) and v == ref_vals[i]
-        # 16 concurrent callers must have shared device batches
-        assert m["model.activation_count"] < n + (n + 31) // 32
+            assert np.array_equal(p, ref_probs[ref_off[i]:ref_off[i + 1]]), f"position {i}: probabilities differ from the bulk call's"
+            assert v == ref_vals[i], f"position {i}: value {v} differs from the bulk call's {ref_vals[i]}"
+        # 16 concurrent callers must have shared device batches (they leave the barrier together; how many leaves ride in one
+        # batch afterwards depends on the host's thread scheduling, so only "not every leaf alone" is asserted)
+        assert m["model.activation_count"] < n + (n + 31) // 32, f"no two leaves shared a device batch: {m['model.activation_count']} activations"
         print("leaf batches:", m["model.activation_count"], "fill:", m["model.mean_batch_fill"])
 
 
