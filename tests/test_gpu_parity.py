@@ -277,26 +277,34 @@ def test_per_leaf_eval_is_thread_safe_and_batch_invariant():
     words, _, legal = synth_inputs(name, n, 404)
     with make_network(name, precision="bf16", batch_size=32, n_streams=2) as nw:
         ref_probs, ref_off, ref_vals = nw.eval_batch(words)
-        out = [None] * n
-        start = threading.Barrier(16)
+        # 16 concurrent callers must share device batches.  How many leaves ride together depends on the host's thread
+        # scheduling (a loaded box can serialise the Python threads), so the workload is repeated until one pass shows sharing;
+        # the results are checked on every pass.
+        shared = False
+        for attempt in range(5):
+            out = [None] * n
+            start = threading.Barrier(16)
+            before = nw.metrics()["model.activation_count"]
 
-        def worker(k):
-            start.wait()
-            for i in range(k, n, 16):
-                out[i] = nw.eval_planes(words[i])
+            def worker(k):
+                start.wait()
+                for i in range(k, n, 16):
+                    out[i] = nw.eval_planes(words[i])
 
-        threads = [threading.Thread(target=worker, args=(k,)) for k in range(16)]
-        [t.start() for t in threads]
-        [t.join() for t in threads]
-        m = nw.metrics()
-        for i in range(n):
-            p, v = out[i]
-            assert np.array_equal(p, ref_probs[ref_off[i]:ref_off[i + 1]]), f"position {i}: probabilities differ from the bulk call's"
-            assert v == ref_vals[i], f"position {i}: value {v} differs from the bulk call's {ref_vals[i]}"
-        # 16 concurrent callers must have shared device batches (they leave the barrier together; how many leaves ride in one
-        # batch afterwards depends on the host's thread scheduling, so only "not every leaf alone" is asserted)
-        assert m["model.activation_count"] < n + (n + 31) // 32, f"no two leaves shared a device batch: {m['model.activation_count']} activations"
-        print("leaf batches:", m["model.activation_count"], "fill:", m["model.mean_batch_fill"])
+            threads = [threading.Thread(target=worker, args=(k,)) for k in range(16)]
+            [t.start() for t in threads]
+            [t.join() for t in threads]
+            m = nw.metrics()
+            for i in range(n):
+                p, v = out[i]
+                assert np.array_equal(p, ref_probs[ref_off[i]:ref_off[i + 1]]), f"position {i}: probabilities differ from the bulk call's"
+                assert v == ref_vals[i], f"position {i}: value {v} differs from the bulk call's {ref_vals[i]}"
+            leaf_batches = m["model.activation_count"] - before
+            print("leaf batches:", leaf_batches, "fill:", m["model.mean_batch_fill"])
+            if leaf_batches < n:
+                shared = True
+                break
+        assert shared, "no two leaves shared a device batch in 5 passes of 16 concurrent callers"
 
 
 @pytest.mark.parametrize("name", ["chess_dev", "hex5"])
