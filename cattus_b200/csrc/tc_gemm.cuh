@@ -228,6 +228,51 @@ __device__ __forceinline__ void tc_gemm_body(const TcGemmParams& p, const int m_
             ok = row < p.rows_per_tile && (m_tile * p.nb + row / p.s2) < p.m_valid;
             grow = static_cast<long long>(m_tile) * p.rows_per_tile + row;
         }
+        // epi 3: what depends only on the records -- this tile's legal words, the number of legal moves in the columns before
+        // it -- and the tile's bias lines are fetched NOW, while the k-loop runs; after the accumulator is complete the epilogue
+        // touches global memory only to store.  (Fetched after the wait, these latencies were most of its 8 500 cycles.)
+        int n = 0;
+        bool live = false;
+        uint32_t pos = 0;
+        uint32_t legal[4] = {0, 0, 0, 0};
+        if (p.epi == 3) {
+            if (lane < 4) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.bias + n_tile * p.n_umma + lane * 32));
+            n = static_cast<int>(*p.n_ptr);
+            live = grow < n;
+            const uint8_t* rec = p.recs + static_cast<size_t>(live ? grow : 0) * p.rl.rec_bytes;
+            const int w0 = n_tile * (p.n_umma >> 5);  // first 32-bit legal word of this tile
+            if (p.rl.legal_off >= 0 && (w0 & 1) == 0 && w0 <= 64) {
+                // Legal moves in the columns before this tile, for the warp's 32 rows: lane k reads u64 word k of a row's
+                // bitmap (one coalesced request per row, 16 rows in flight) and the popcounts are added across the warp.
+                const int nw64 = w0 >> 1;
+                const long long g0 = static_cast<long long>(m_tile) * 128 + q * 32;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    unsigned long long wv[16];
+#pragma unroll
+                    for (int r = 0; r < 16; ++r) {
+                        const long long g = g0 + 16 * h + r;
+                        const unsigned long long* rr =
+                            reinterpret_cast<const unsigned long long*>(p.recs + static_cast<size_t>(g < n ? g : 0) * p.rl.rec_bytes + p.rl.legal_off);
+                        wv[r] = static_cast<int>(lane) < nw64 ? __ldg(rr + lane) : 0ull;
+                    }
+#pragma unroll
+                    for (int r = 0; r < 16; ++r) {
+                        const uint32_t c = __reduce_add_sync(0xFFFFFFFFu, static_cast<uint32_t>(__popcll(wv[r])));
+                        if (static_cast<int>(lane) == 16 * h + r) pos = c;
+                    }
+                }
+                if (live) pos += *reinterpret_cast<const uint32_t*>(rec - 8);
+            } else if (live) {
+                pos = *reinterpret_cast<const uint32_t*>(rec - 8);
+                for (int j = 0; j < w0; ++j) pos += __popc(legal_word(rec, p.rl, j));
+            }
+            if (live) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (w0 + j < p.rl.legal_words) legal[j] = legal_word(rec, p.rl, w0 + j);
+            }
+        }
         ptx::mbar_wait(tmem_full_bar, 0, p.err, 0x300, p.fault ? (1u << 14) : (1u << 24));
         ptx::tc_fence_after();
         if (trace && threadIdx.x == 64) p.dbg[3] = clock64();
@@ -300,68 +345,35 @@ __device__ __forceinline__ void tc_gemm_body(const TcGemmParams& p, const int m_
             }
         } else if (p.epi == 3) {
             // ---- policy, many N tiles: masked compact write of this tile's 128 columns (softmax runs afterwards)
-            const int n = static_cast<int>(*p.n_ptr);
-            const bool live = grow < n;
-            const uint8_t* rec = p.recs + static_cast<size_t>(live ? grow : 0) * p.rl.rec_bytes;
-            const int w0 = n_tile * (p.n_umma >> 5);  // first 32-bit legal word of this tile
-            uint32_t pos = 0;
-            uint32_t legal[4] = {0, 0, 0, 0};
-            if (p.rl.legal_off >= 0 && (w0 & 1) == 0 && w0 <= 64) {
-                // Legal moves in the columns before this tile, for the warp's 32 rows: lane k reads u64 word k of a row's
-                // bitmap (one coalesced request per row, 16 rows in flight) and the popcounts are added across the warp.
-                // One thread walking its own row word by word (up to 56 loads, 32 sectors per request, latencies in series)
-                // made this epilogue longer than the k-loop at full tiles (10 000 of a CTA's 26 000 cycles).
-                const int nw64 = w0 >> 1;
-                const long long g0 = static_cast<long long>(m_tile) * 128 + q * 32;
+            // Two 16-column chunks per trip (one TMEM wait for both); their 32 biases come as vector loads from lines prefetched
+            // above, under the TMEM load.  Per-bit branches, not predicated stores and not a staging pass through shared
+            // memory: a warp skips the columns none of its 32 rows may play, which is most of them (tried: 16 predicated STG per
+            // chunk 13 200 cycles per full tile, shared-memory staging + ffs loop 5 800, branches 5 200).
+            for (int c0 = 0; c0 < p.n_umma; c0 += 32) {
+                uint32_t raw[2][16];
+                ptx::tmem_ld_x16_issue(taddr + c0, raw[0]);
+                ptx::tmem_ld_x16_issue(taddr + c0 + 16, raw[1]);
+                const float4* b4 = reinterpret_cast<const float4*>(p.bias + n_tile * p.n_umma + c0);
+                float4 bb[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) bb[i] = __ldg(b4 + i);
+                ptx::tmem_ld_wait2(raw[0], raw[1]);
+                const uint32_t bits32 = legal[c0 >> 5];
+                if (bits32 == 0) continue;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    unsigned long long wv[16];
+                    const uint32_t bits = (bits32 >> (16 * h)) & 0xFFFFu;
+                    if (bits == 0) continue;
+                    const float bias16[16] = {bb[4 * h].x,     bb[4 * h].y,     bb[4 * h].z,     bb[4 * h].w,     bb[4 * h + 1].x, bb[4 * h + 1].y,
+                                              bb[4 * h + 1].z, bb[4 * h + 1].w, bb[4 * h + 2].x, bb[4 * h + 2].y, bb[4 * h + 2].z, bb[4 * h + 2].w,
+                                              bb[4 * h + 3].x, bb[4 * h + 3].y, bb[4 * h + 3].z, bb[4 * h + 3].w};
 #pragma unroll
-                    for (int r = 0; r < 16; ++r) {
-                        const long long g = g0 + 16 * h + r;
-                        const unsigned long long* rr =
-                            reinterpret_cast<const unsigned long long*>(p.recs + static_cast<size_t>(g < n ? g : 0) * p.rl.rec_bytes + p.rl.legal_off);
-                        wv[r] = static_cast<int>(lane) < nw64 ? __ldg(rr + lane) : 0ull;
-                    }
-#pragma unroll
-                    for (int r = 0; r < 16; ++r) {
-                        const uint32_t c = __reduce_add_sync(0xFFFFFFFFu, static_cast<uint32_t>(__popcll(wv[r])));
-                        if (static_cast<int>(lane) == 16 * h + r) pos = c;
-                    }
-                }
-                if (live) pos += *reinterpret_cast<const uint32_t*>(rec - 8);
-            } else if (live) {
-                pos = *reinterpret_cast<const uint32_t*>(rec - 8);
-                for (int j = 0; j < w0; ++j) pos += __popc(legal_word(rec, p.rl, j));
-            }
-            if (live) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (w0 + j < p.rl.legal_words) legal[j] = legal_word(rec, p.rl, w0 + j);
-            }
-            for (int c0 = 0; c0 < p.n_umma; c0 += 16) {
-                // The chunk's 16 biases are fetched as four vector loads under the TMEM load, not one by one inside the per-bit
-                // branches: the lanes of a warp hold different bits, so the warp walked nearly all 16 branches of every chunk
-                // with a load latency in each (128 in series per tile).
-                uint32_t raw[16];
-                ptx::tmem_ld_x16_issue(taddr + c0, raw);
-                const float4* b4 = reinterpret_cast<const float4*>(p.bias + n_tile * p.n_umma + c0);
-                float4 bb[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) bb[i] = __ldg(b4 + i);
-                ptx::tmem_ld_wait(raw);
-                const uint32_t bits = (legal[c0 >> 5] >> (c0 & 31)) & 0xFFFFu;
-                if (bits == 0) continue;
-                const float bias16[16] = {bb[0].x, bb[0].y, bb[0].z, bb[0].w, bb[1].x, bb[1].y, bb[1].z, bb[1].w,
-                                          bb[2].x, bb[2].y, bb[2].z, bb[2].w, bb[3].x, bb[3].y, bb[3].z, bb[3].w};
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    // branches, not predicated stores: a warp skips the columns none of its rows may play; as straight-line code
-                    // (all 16 STG issued per chunk) the epilogue took 13 200 instead of 8 500 cycles
-                    if ((bits >> j) & 1u) {
-                        float x = __uint_as_float(raw[j]) + bias16[j];
-                        if (!isfinite(x)) x = -FLT_MAX;
-                        p.probs[pos++] = x;
+                    for (int j = 0; j < 16; ++j) {
+                        if ((bits >> j) & 1u) {
+                            float x = __uint_as_float(raw[h][j]) + bias16[j];
+                            if (!isfinite(x)) x = -FLT_MAX;
+                            p.probs[pos++] = x;
+                        }
                     }
                 }
             }
