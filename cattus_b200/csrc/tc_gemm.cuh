@@ -228,13 +228,25 @@ __device__ __forceinline__ void tc_gemm_body(const TcGemmParams& p, const int m_
             ok = row < p.rows_per_tile && (m_tile * p.nb + row / p.s2) < p.m_valid;
             grow = static_cast<long long>(m_tile) * p.rows_per_tile + row;
         }
-        // epi 3: what depends only on the records -- this tile's legal words, the number of legal moves in the columns before
+        // epi 2 and 3: what depends only on the records -- this tile's legal words, the number of legal moves in the columns before
         // it -- and the tile's bias lines are fetched NOW, while the k-loop runs; after the accumulator is complete the epilogue
         // touches global memory only to store.  (Fetched after the wait, these latencies were most of its 8 500 cycles.)
         int n = 0;
         bool live = false;
         uint32_t pos = 0;
         uint32_t legal[4] = {0, 0, 0, 0};
+        if (p.epi == 2) {
+            n = static_cast<int>(*p.n_ptr);
+            live = grow < n;
+            if (static_cast<int>(lane) * 32 < p.n_umma) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.bias + lane * 32));
+            if (live) {
+                const uint8_t* rec = p.recs + static_cast<size_t>(grow) * p.rl.rec_bytes;
+                pos = *reinterpret_cast<const uint32_t*>(rec - 8);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (j < p.rl.legal_words) legal[j] = legal_word(rec, p.rl, j);
+            }
+        }
         if (p.epi == 3) {
             if (lane < 4) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.bias + n_tile * p.n_umma + lane * 32));
             n = static_cast<int>(*p.n_ptr);
@@ -297,16 +309,8 @@ __device__ __forceinline__ void tc_gemm_body(const TcGemmParams& p, const int m_
             }
             if (grow < n) p.values[grow] = tanhf(dot + p.b2);
         } else if (p.epi == 2) {
-            // ---- policy: masked softmax over this position's row, three passes over TMEM (max, sum, write)
-            const int n = static_cast<int>(*p.n_ptr);
-            const bool live = grow < n;
-            const uint8_t* rec = p.recs + static_cast<size_t>(live ? grow : 0) * p.rl.rec_bytes;
-            uint32_t legal[4] = {0, 0, 0, 0};
-            if (live) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (j < p.rl.legal_words) legal[j] = legal_word(rec, p.rl, j);
-            }
+            // ---- policy: masked softmax over this position's row, three passes over TMEM (max, sum, write); the legal words and
+            // the output offset were fetched before the accumulator wait
             float mx = -FLT_MAX;
             for (int c0 = 0; c0 < p.n_umma; c0 += 16) {
                 float v[16];
@@ -331,7 +335,6 @@ __device__ __forceinline__ void tc_gemm_body(const TcGemmParams& p, const int m_
                     if ((bits >> j) & 1u) sum += expf(x - mx);
                 }
             }
-            uint32_t pos = live ? *reinterpret_cast<const uint32_t*>(rec - 8) : 0u;
             for (int c0 = 0; c0 < p.n_umma; c0 += 16) {
                 float v[16];
                 ptx::tmem_ld_x16(taddr + c0, v);
