@@ -221,10 +221,10 @@ Engine::Engine(const cattus_b200_desc& desc, const void* blob_bytes, size_t blob
     CB2_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h_err_), 64, cudaHostAllocMapped));
     std::memset(h_err_, 0, 64);
     CB2_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_err_), h_err_, 0));
-    CB2_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<kTcStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(kTcStages)));
-    CB2_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<kTcStagesDeep>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(kTcStagesDeep)));
-    CB2_CUDA(cudaFuncSetAttribute(tc_gemm_dual_kernel<kTcStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(kTcStages)));
-    CB2_CUDA(cudaFuncSetAttribute(tc_gemm_dual_kernel<kTcStagesDeep>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(kTcStagesDeep)));
+    CB2_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(kTcStages)));
+    CB2_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(kTcStagesDeep)));
+    CB2_CUDA(cudaFuncSetAttribute(tc_gemm_dual_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(kTcStages)));
+    CB2_CUDA(cudaFuncSetAttribute(tc_gemm_dual_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(kTcStagesDeep)));
     // whole-trunk kernel: 8x8 boards, 128 filters (flags bit 0 forces the per-layer path, used by the parity tests)
     fused_trunk_ = !simple_ && precision_ == CATTUS_B200_PRECISION_BF16 && d_.s == 8 && (d_.f == 64 || d_.f == 128 || d_.f == 256) && d_.c_in <= 32 &&
                    d_.wpp() == 1 && (desc.flags & 1u) == 0 && (sm_count_ >= 2) && vhp_ + php_ <= 64;
@@ -598,8 +598,9 @@ CUtensorMap Engine::make_map_conv(const void* base, uint32_t channels, uint32_t 
     return m;
 }
 
-// Ring depth of the GEMM kernel: 6 stages and one CTA per SM for the smallest batches (<= 64 rows) of GEMMs with a long
-// k-loop (the chess head FCs, 32 k-blocks: B = 1 ... 64 graph -2 to -4 us); 3 stages and two CTAs per SM otherwise.
+// Ring of the GEMM kernel: the deep form (3 slots of two k-blocks = 6 tile pairs, one CTA per SM) for the smallest batches
+// (<= 64 rows) of GEMMs with a long k-loop (the chess head FCs, 32 k-blocks: B = 1 ... 64 graph -2 to -4 us); 3 slots of
+// one k-block and two CTAs per SM otherwise.
 // Short k-loops gain nothing from the depth and the 197 KB launch costs the hex5 graph 2-4 us; larger small batches
 // usually come from many lanes at once (trainer-sized jobs with speculative rows: ~100 rows per batch on 16 streams),
 // where CTAs that each take a whole SM cost 12 % of the job's throughput (1.24 M -> 1.09 M sims/s), more than the 2-4 us
@@ -607,7 +608,7 @@ CUtensorMap Engine::make_map_conv(const void* base, uint32_t channels, uint32_t 
 // k-loop was then paced by the single-lane issue loops, not by the loads -- see tc_gemm.cuh.)
 int Engine::tc_stages_for(uint32_t ctas, int num_kb, uint32_t rows) const {
     static const bool no_deep = std::getenv("CATTUS_B200_TC_NO_DEEP") != nullptr;
-    return !no_deep && ctas <= static_cast<uint32_t>(sm_count_) && num_kb >= 16 && rows <= 64 ? kTcStagesDeep : kTcStages;
+    return !no_deep && ctas <= static_cast<uint32_t>(sm_count_) && num_kb >= 16 && num_kb % 2 == 0 && rows <= 64 ? kTcStagesDeep : kTcStages;
 }
 
 // Launch with programmatic stream serialization: the kernel may be staged while its predecessor on the stream still runs
@@ -638,9 +639,9 @@ Op Engine::make_tc_op(int stage, const char* name, const TcGemmParams& p, uint32
     q.fault = (desc_.flags & 2u) && stage == 2 ? 1 : 0;
     const int smem_bytes = tc_smem_bytes(stages);
     if (stages == kTcStagesDeep)
-        op.launch = [q, grid, smem_bytes](cudaStream_t st) { tc_gemm_kernel<kTcStagesDeep><<<grid, kTcThreads, smem_bytes, st>>>(q); };
+        op.launch = [q, grid, smem_bytes](cudaStream_t st) { tc_gemm_kernel<2><<<grid, kTcThreads, smem_bytes, st>>>(q); };
     else
-        op.launch = [q, grid, smem_bytes](cudaStream_t st) { tc_gemm_kernel<kTcStages><<<grid, kTcThreads, smem_bytes, st>>>(q); };
+        op.launch = [q, grid, smem_bytes](cudaStream_t st) { tc_gemm_kernel<1><<<grid, kTcThreads, smem_bytes, st>>>(q); };
     return op;
 }
 
@@ -1139,7 +1140,9 @@ void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
         op.stage = 2;
         op.name = "heads_fc_dual";
         const dim3 grid(ceil_div(bucket, 128), 1 + pfc_.n_tiles);
-        const int stages = tc_stages_for(grid.x * grid.y, std::max(dp.a.num_kb, dp.b.num_kb), bucket);
+        // the deep form needs an even number of k-blocks in BOTH problems (an odd one falls back to the 3-stage ring)
+        const int kb_both = (dp.a.num_kb % 2 == 0 && dp.b.num_kb % 2 == 0) ? std::max(dp.a.num_kb, dp.b.num_kb) : 1;
+        const int stages = tc_stages_for(grid.x * grid.y, kb_both, bucket);
         dp.a.fault = (desc_.flags & 2u) ? 1 : 0;
         if (std::getenv("CATTUS_B200_TRACE_HEADS")) {  // diagnostic: clock64 trace of the policy FC's tile (0, 1), printed by time_stage
             if (trace_.p == nullptr) trace_.alloc(512 * sizeof(unsigned long long));
@@ -1147,9 +1150,9 @@ void Engine::build_ops_bf16(Lane& lane, uint32_t bucket, std::vector<Op>& ops, b
         }
         const int smem_bytes = tc_smem_bytes(stages);
         if (stages == kTcStagesDeep)
-            op.launch = [dp, grid, smem_bytes](cudaStream_t st) { launch_pdl(tc_gemm_dual_kernel<kTcStagesDeep>, grid, dim3(kTcThreads), smem_bytes, st, dp); };
+            op.launch = [dp, grid, smem_bytes](cudaStream_t st) { launch_pdl(tc_gemm_dual_kernel<2>, grid, dim3(kTcThreads), smem_bytes, st, dp); };
         else
-            op.launch = [dp, grid, smem_bytes](cudaStream_t st) { launch_pdl(tc_gemm_dual_kernel<kTcStages>, grid, dim3(kTcThreads), smem_bytes, st, dp); };
+            op.launch = [dp, grid, smem_bytes](cudaStream_t st) { launch_pdl(tc_gemm_dual_kernel<1>, grid, dim3(kTcThreads), smem_bytes, st, dp); };
         ops.push_back(op);
     }
     if (compact_policy) {

@@ -22,7 +22,7 @@
 //       moves are written, compactly, at (record offset + number of legal moves in earlier columns) -- 0.5 MB instead of
 //       the 31.5 MB dense f32 logits tensor per 4096 chess positions; softmax_compact_kernel then normalises.
 // Warp roles (224 threads): warp 0 = A producer (TMA), warp 6 = B producer (bulk copy), warp 1 = MMA issuer, warps 2..5 = epilogue
-// (TMEM -> registers -> +bias (+residual) -> ReLU -> bf16/f32 -> global).  Smem ring of 3 stages (two CTAs per SM) or 6 (one CTA per SM; template parameter), full/empty mbarriers.
+// (TMEM -> registers -> +bias (+residual) -> ReLU -> bf16/f32 -> global).  Smem ring of 3 slots of one k-block (two CTAs per SM) or of two (one CTA per SM; template parameter), full/empty mbarriers.
 #pragma once
 #include "kernels.cuh"
 #include "ptx.cuh"
@@ -30,7 +30,7 @@
 namespace cb2 {
 
 constexpr int kTcStages = 3;      // ring depth of large grids (two CTAs per SM)
-constexpr int kTcStagesDeep = 6;  // small grids (one latency-bound CTA per SM): deeper prefetch, see tc_smem_bytes()
+constexpr int kTcStagesDeep = 6;  // tile pairs of the deep form (3 slots of 2 k-blocks, one CTA per SM), see tc_gemm_body
 constexpr int kTcTileBytes = 128 * 128;  // 128 rows x 128 B
 constexpr int kTcThreads = 224;
 constexpr int kTcTmemCols = 128;
@@ -72,7 +72,11 @@ struct alignas(64) TcGemmParams {
     unsigned long long* dbg;  // optional clock64 trace of tile (0, 1) (CATTUS_B200_TRACE_HEADS=1, printed by time_stage), else nullptr
 };
 
-template <int kStages>
+// kStages ring slots of kKPer k-blocks each.  <3, 1>: the general form, two CTAs per SM.  <3, 2> ("deep", one CTA per SM,
+// the same 192 KB as six single slots would take): half the barrier traffic per k -- the issuer's chain per slot is one
+// wait + 8 MMAs + one commit, which fits under the 8 MMAs' 512 cycles of tensor work, where one wait + 4 MMAs + one commit
+// (~430 cycles) did not fit under 256.  Needs an even number of k-blocks.
+template <int kStages, int kKPer>
 __device__ __forceinline__ void tc_gemm_body(const TcGemmParams& p, const int m_tile, const int n_tile) {
     // An M tile that holds nothing but padding positions (the launch is sized for the batch bucket) has no live output.
     // Mode 1 tiles are whole boards; mode 0 rows are positions only for the head FCs (the epilogues 1-3), elsewhere rows
@@ -92,8 +96,9 @@ __device__ __forceinline__ void tc_gemm_body(const TcGemmParams& p, const int m_
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint8_t* smem_a = smem;
     constexpr int stages = kStages;  // compile time: the loops below unroll over one trip around the ring
-    uint8_t* smem_b = smem + stages * kTcTileBytes;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + 2 * stages * kTcTileBytes);
+    constexpr int kSlotBytes = kKPer * kTcTileBytes;  // per operand
+    uint8_t* smem_b = smem + stages * kSlotBytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + 2 * stages * kSlotBytes);
     uint64_t* empty_bar = full_bar + stages;
     uint64_t* tmem_full_bar = empty_bar + stages;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
@@ -140,25 +145,28 @@ __device__ __forceinline__ void tc_gemm_body(const TcGemmParams& p, const int m_
         const int a_c1 = mode == 0 ? m_tile * 128 : m_tile * p.nb;
         int slice = 0, dx = -1, dy = -1;
         uint32_t ph = 1;  // parity of the `empty` phase to wait for: the first trip passes on fresh barriers
-        for (int kb0 = 0; kb0 < num_kb; kb0 += stages, ph ^= 1) {
+        for (int kb0 = 0; kb0 < num_kb; kb0 += stages * kKPer, ph ^= 1) {
 #pragma unroll
             for (int s = 0; s < stages; ++s) {
-                const int kb = kb0 + s;
+                const int kb = kb0 + s * kKPer;
                 if (kb >= num_kb) break;
                 ptx::mbar_wait(&empty_bar[s], ph, p.err, 0x100 + s);
                 if (trace && lane == 0 && kb < 40) p.dbg[48 + kb] = clock64();
-                if (leader) {
-                    ptx::mbar_arrive_expect_tx(&full_bar[s], a_bytes);
-                    if (mode == 0)
-                        ptx::tma_load_2d(smem_a + s * kTcTileBytes, &p.tma_a, &full_bar[s], kb * 64, a_c1);
-                    else
-                        ptx::tma_load_4d(smem_a + s * kTcTileBytes, &p.tma_a, &full_bar[s], slice * 64, dx, dy, a_c1);
-                }
-                if (++slice == kh) {  // mode 1: k-blocks walk (tap, 64-channel slice), taps row-major over (dy, dx)
-                    slice = 0;
-                    if (++dx == 2) {
-                        dx = -1;
-                        ++dy;
+                if (leader) ptx::mbar_arrive_expect_tx(&full_bar[s], a_bytes * kKPer);
+#pragma unroll
+                for (int i = 0; i < kKPer; ++i) {
+                    if (leader) {
+                        if (mode == 0)
+                            ptx::tma_load_2d(smem_a + (s * kKPer + i) * kTcTileBytes, &p.tma_a, &full_bar[s], (kb + i) * 64, a_c1);
+                        else
+                            ptx::tma_load_4d(smem_a + (s * kKPer + i) * kTcTileBytes, &p.tma_a, &full_bar[s], slice * 64, dx, dy, a_c1);
+                    }
+                    if (++slice == kh) {  // mode 1: k-blocks walk (tap, 64-channel slice), taps row-major over (dy, dx)
+                        slice = 0;
+                        if (++dx == 2) {
+                            dx = -1;
+                            ++dy;
+                        }
                     }
                 }
                 __syncwarp();
@@ -172,16 +180,18 @@ __device__ __forceinline__ void tc_gemm_body(const TcGemmParams& p, const int m_
         const uint32_t b_bytes = static_cast<uint32_t>(p.n_umma) * 128;
         const int num_kb = p.num_kb;
         uint32_t ph = 1;
-        for (int kb0 = 0; kb0 < num_kb; kb0 += stages, ph ^= 1) {
+        for (int kb0 = 0; kb0 < num_kb; kb0 += stages * kKPer, ph ^= 1) {
 #pragma unroll
             for (int s = 0; s < stages; ++s) {
-                if (kb0 + s >= num_kb) break;
+                if (kb0 + s * kKPer >= num_kb) break;
                 ptx::mbar_wait(&empty_bar[s], ph, p.err, 0x180 + s);
                 if (leader) {
-                    ptx::mbar_arrive_expect_tx(&full_bar[s], b_bytes);
-                    ptx::bulk_load(smem_b + s * kTcTileBytes, b_src, b_bytes, &full_bar[s]);
+                    ptx::mbar_arrive_expect_tx(&full_bar[s], b_bytes * kKPer);
+#pragma unroll
+                    for (int i = 0; i < kKPer; ++i)  // a k-block's rows start a whole tile apart in smem whatever n_umma is
+                        ptx::bulk_load(smem_b + (s * kKPer + i) * kTcTileBytes, b_src + i * b_bytes, b_bytes, &full_bar[s]);
                 }
-                b_src += b_bytes;
+                b_src += b_bytes * kKPer;
                 __syncwarp();
             }
         }
@@ -193,21 +203,24 @@ __device__ __forceinline__ void tc_gemm_body(const TcGemmParams& p, const int m_
         const bool leader = ptx::elect_one();
         const int num_kb = p.num_kb;
         uint32_t ph = 0;
-        for (int kb0 = 0; kb0 < num_kb; kb0 += stages, ph ^= 1) {
+        for (int kb0 = 0; kb0 < num_kb; kb0 += stages * kKPer, ph ^= 1) {
 #pragma unroll
             for (int s = 0; s < stages; ++s) {
-                const int kb = kb0 + s;
+                const int kb = kb0 + s * kKPer;
                 if (kb >= num_kb) break;
                 if (trace && lane == 0 && kb < 40) p.dbg[88 + kb] = clock64();
                 ptx::mbar_wait(&full_bar[s], ph, p.err, 0x200 + s);
                 ptx::tc_fence_after();
                 if (trace && lane == 0 && kb < 40) p.dbg[8 + kb] = clock64();
                 if (leader) {
-                    const uint32_t a_lo = a_lo0 + s * (kTcTileBytes >> 4), b_lo = b_lo0 + s * (kTcTileBytes >> 4);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)  // 4 x (K = 16 bf16 = 32 B) inside the 128-byte swizzle row
-                        ptx::umma_bf16_ss_lohi(tmem_base, a_lo + 2 * k, d_hi, b_lo + 2 * k, d_hi, idesc, (kb | k) != 0);
-                    ptx::umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+                    for (int i = 0; i < kKPer; ++i) {
+                        const uint32_t a_lo = a_lo0 + (s * kKPer + i) * (kTcTileBytes >> 4), b_lo = b_lo0 + (s * kKPer + i) * (kTcTileBytes >> 4);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)  // 4 x (K = 16 bf16 = 32 B) inside the 128-byte swizzle row
+                            ptx::umma_bf16_ss_lohi(tmem_base, a_lo + 2 * k, d_hi, b_lo + 2 * k, d_hi, idesc, (kb | i | k) != 0);
+                    }
+                    ptx::umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
                 }
                 __syncwarp();
             }
@@ -449,9 +462,9 @@ __device__ __forceinline__ void tc_gemm_body(const TcGemmParams& p, const int m_
     }
 }
 
-template <int kStages>
-__global__ void __launch_bounds__(kTcThreads, kStages > kTcStages ? 1 : 2) tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
-    tc_gemm_body<kStages>(p, blockIdx.x, blockIdx.y);
+template <int kKPer>
+__global__ void __launch_bounds__(kTcThreads, kKPer > 1 ? 1 : 2) tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
+    tc_gemm_body<kTcStages, kKPer>(p, blockIdx.x, blockIdx.y);
 }
 
 // Two independent GEMMs in one launch: blockIdx.y == 0 runs problem `a` (one N tile), blockIdx.y >= 1 runs N tile
@@ -461,12 +474,12 @@ struct alignas(64) TcGemmDualParams {
     TcGemmParams a;
     TcGemmParams b;
 };
-template <int kStages>
-__global__ void __launch_bounds__(kTcThreads, kStages > kTcStages ? 1 : 2) tc_gemm_dual_kernel(const __grid_constant__ TcGemmDualParams d) {
+template <int kKPer>
+__global__ void __launch_bounds__(kTcThreads, kKPer > 1 ? 1 : 2) tc_gemm_dual_kernel(const __grid_constant__ TcGemmDualParams d) {
     if (blockIdx.y == 0)
-        tc_gemm_body<kStages>(d.a, blockIdx.x, 0);
+        tc_gemm_body<kTcStages, kKPer>(d.a, blockIdx.x, 0);
     else
-        tc_gemm_body<kStages>(d.b, blockIdx.x, static_cast<int>(blockIdx.y) - 1);
+        tc_gemm_body<kTcStages, kKPer>(d.b, blockIdx.x, static_cast<int>(blockIdx.y) - 1);
 }
 
 }  // namespace cb2
