@@ -1181,7 +1181,13 @@ void Engine::run_bucket(Lane& lane, uint32_t bucket, cudaStream_t stream, bool u
         // capture on the lane's own stream (never on a caller's stream)
         cudaGraph_t graph = nullptr;
         CB2_CUDA(cudaStreamBeginCapture(lane.stream, cudaStreamCaptureModeThreadLocal));
-        for (const Op& op : ops) op.launch(lane.stream);
+        try {
+            for (const Op& op : ops) op.launch(lane.stream);
+        } catch (...) {  // a launch that throws (launch_pdl checks its result) must not leave the stream capturing
+            cudaStreamEndCapture(lane.stream, &graph);
+            if (graph) cudaGraphDestroy(graph);
+            throw;
+        }
         cudaError_t ce = cudaStreamEndCapture(lane.stream, &graph);
         if (ce != cudaSuccess) throw Error(CATTUS_B200_ECUDA, std::string("graph capture failed: ") + cudaGetErrorString(ce));
         cudaGraphExec_t exec = nullptr;
