@@ -381,8 +381,9 @@ def time_cpu_selfplay(game, games, threads, max_moves=0):
     summary, _ = runner.run_with(cb, None, games)
     return selfplay_summary_to_dict(game, mc, summary, games, threads, 1, max_moves=max_moves, extra={
         "value": summary["metrics"]["selfplay.sims_per_sec"], "cores": cores, "kind": "port",
-        "sample": f"{games} games, {threads} threads x 1 tree each (the reference's arrangement; its Mutex<Model> serialises evaluations, so more "
-                  f"threads add nothing), per-leaf torch-CPU fp32 evaluation with 1 intra-op thread"})
+        "sample": f"repo driver + CPU evaluator: {games} games, {threads} threads x 1 tree each, one leaf at a time (the reference's thread "
+                  f"arrangement; its Mutex<Model> serialises evaluations, so more threads add nothing), per-leaf torch-CPU fp32 evaluation "
+                  f"with 1 intra-op thread"})
 
 
 def cpu_batch_sweep(cfg, batches=(1, 8, 64, 256, 1024), seconds_each=1.2, seed=99):
